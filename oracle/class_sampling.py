@@ -39,16 +39,27 @@ def gmm_sample_from_normals(means, covs_diag, comp_ids, normals):
 
 def lr_target_proba(z32, coef, intercept, target_col):
     """`RejSampleBase.score_clf` (density_modeling.py:43-48): binary
-    LogisticRegression.predict_proba column `target_col`.  z is fp32 promoted to
-    fp64 by sklearn; p1 = expit(z.coef + b); columns are [1 - p1, p1]."""
-    s = z32.astype(np.float64) @ np.asarray(coef, dtype=np.float64).reshape(-1) + float(intercept)
-    p1 = 1.0 / (1.0 + np.exp(-s))
-    return p1 if target_col == 1 else 1.0 - p1
+    LogisticRegression.predict_proba column `target_col`
+    (sklearn linear_model/_base.py:366-396,429-440): s = X @ coef + b,
+    p1 = expit(s), columns [1 - p1, p1].  The arithmetic type follows the dtype of
+    the fitted coefficients: `build_clfZ` (sample_pipeline.py:169-186) fits on
+    float32 z's, and sklearn 1.9 then keeps coef_ float32, so the whole score path
+    is float32 (sgemv + float32 expit); a classifier fitted on float64 data scores
+    in float64 (the float32 z is promoted)."""
+    from scipy.special import expit
+    coef = np.asarray(coef).reshape(-1)
+    if coef.dtype == np.float32:
+        s = z32.astype(np.float32) @ coef + np.float32(intercept)
+    else:
+        s = z32.astype(np.float64) @ coef.astype(np.float64) + float(intercept)
+    p1 = expit(s)
+    return p1 if target_col == 1 else 1 - p1
 
 
 def rejection_accept(z32, uniforms, clfs):
     """`RejSampleBase.rejection_sample` (density_modeling.py:50-60) after the
-    draw: accum = 1.0 * prod_a p_a(z); accepted = u < accum.  `clfs` is an
+    draw: accum = 1.0 * prod_a p_a(z) (in the scores' dtype); accepted = u < accum
+    with u float64.  `clfs` is an
     ordered list of (name, coef[D], intercept, target_col).  Returns
     (scores dict as the reference names them, accepted bool[n])."""
     accum = 1.0
