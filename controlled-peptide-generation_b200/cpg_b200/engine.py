@@ -1,0 +1,239 @@
+"""Thin functional layer over the C ABI: flat parameter state, the WAE forward /
+backward / fused-step calls and the individual loss ops.  All tensors are torch
+CUDA tensors owned by the caller; this module only marshals pointers.
+"""
+import math
+from collections import OrderedDict
+from ctypes import byref, c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import (SC, SC_COUNT, ZREGU, LossNoise, TrainHparams, WaeInputs, check, context, lib, ptr,
+                   stream_ptr)
+
+# layout order of cpg_vae_param_layout (== unique tensors of RNN_VAE.vae_params(), models/model.py:88-94)
+PARAM_NAMES = (
+    'word_emb.weight',
+    'encoder.rnn.weight_ih_l0', 'encoder.rnn.weight_hh_l0', 'encoder.rnn.bias_ih_l0', 'encoder.rnn.bias_hh_l0',
+    'encoder.rnn.weight_ih_l0_reverse', 'encoder.rnn.weight_hh_l0_reverse',
+    'encoder.rnn.bias_ih_l0_reverse', 'encoder.rnn.bias_hh_l0_reverse',
+    'encoder.q_mu.weight', 'encoder.q_mu.bias', 'encoder.q_logvar.weight', 'encoder.q_logvar.bias',
+    'decoder.rnn.weight_ih_l0', 'decoder.rnn.weight_hh_l0', 'decoder.rnn.bias_ih_l0', 'decoder.rnn.bias_hh_l0',
+    'decoder.fc.1.weight', 'decoder.fc.1.bias',
+)
+EMB, ENC_H, ZD, CD, DEC_H = 150, 80, 100, 2, 102
+
+
+def param_shapes(n_vocab):
+    ge, gd = 3 * ENC_H, 3 * DEC_H
+    shapes = [(n_vocab, EMB),
+              (ge, EMB), (ge, ENC_H), (ge,), (ge,), (ge, EMB), (ge, ENC_H), (ge,), (ge,),
+              (ZD, 2 * ENC_H), (ZD,), (ZD, 2 * ENC_H), (ZD,),
+              (gd, EMB + DEC_H), (gd, DEC_H), (gd,), (gd,),
+              (n_vocab, DEC_H), (n_vocab,)]
+    return OrderedDict(zip(PARAM_NAMES, shapes))
+
+
+class FlatState:
+    """Flat fp32 buffers (params, grads, Adam m/v) in the library's layout, with
+    named views so that nn.Parameters / state_dicts can alias them."""
+
+    def __init__(self, n_vocab, device=None):
+        self.n_vocab = int(n_vocab)
+        self.device = _lib.tensor_device(device)
+        self.offsets, self.sizes, self.total = _lib.param_layout(self.n_vocab)
+        self.shapes = param_shapes(self.n_vocab)
+        z = lambda: torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.params, self.grads, self.adam_m, self.adam_v = z(), z(), z(), z()
+        self.step = 0
+
+    def views(self, flat):
+        out = OrderedDict()
+        for name, off, n in zip(PARAM_NAMES, self.offsets, self.sizes):
+            out[name] = flat[off:off + n].view(self.shapes[name])
+        return out
+
+    def load(self, named_tensors):
+        """Copy tensors (dict keyed by the reference's state_dict names) into the flat params."""
+        v = self.views(self.params)
+        with torch.no_grad():
+            for name in PARAM_NAMES:
+                src = named_tensors[name] if name in named_tensors else named_tensors['decoder.emb.weight']
+                v[name].copy_(src.to(self.device, torch.float32))
+
+    def export(self, flat=None):
+        return OrderedDict((k, t.clone()) for k, t in self.views(self.params if flat is None else flat).items())
+
+
+def _inputs(tokens, eps, c, word_drop, out_keep, p_out):
+    inp = WaeInputs()
+    inp.tokens = ptr(tokens, torch.int64, allow_none=False)
+    inp.eps = ptr(eps, torch.float32)
+    inp.c = ptr(c, torch.float32)
+    inp.word_drop = ptr(word_drop, torch.uint8)
+    inp.out_keep = ptr(out_keep, torch.uint8)
+    inp.p_out_dropout = float(p_out)
+    return inp
+
+
+def _check_shapes(tokens, eps, c, word_drop, out_keep):
+    if tokens.dim() != 2:
+        raise ValueError('tokens must be [B, L]')
+    B, L = tokens.shape
+    for name, t, shp in (('eps', eps, (B, ZD)), ('c', c, (B, CD)), ('word_drop', word_drop, (B, L)),
+                         ('out_keep', out_keep, (B, L, DEC_H))):
+        if t is not None and tuple(t.shape) != shp:
+            raise ValueError('%s must have shape %s, got %s' % (name, shp, tuple(t.shape)))
+    return B, L
+
+
+def wae_forward(params, n_vocab, tokens, eps, c, word_drop=None, out_keep=None, p_out=0.3, want_logits=True,
+                keep_for_backward=False):
+    """RNN_VAE.forward arithmetic (models/model.py:146-195) on explicit noise."""
+    B, L = _check_shapes(tokens, eps, c, word_drop, out_keep)
+    dev = tokens.device
+    mu = torch.empty(B, ZD, device=dev)
+    logvar = torch.empty(B, ZD, device=dev)
+    z = torch.empty(B, ZD, device=dev)
+    logits = torch.empty(B, L, n_vocab, device=dev) if want_logits else None
+    inp = _inputs(tokens, eps, c, word_drop, out_keep, p_out)
+    check(lib().cpg_wae_forward(context(dev), stream_ptr(), ptr(params), n_vocab, B, L, byref(inp), ptr(mu),
+                                ptr(logvar), ptr(z), ptr(logits), 1 if keep_for_backward else 0), 'cpg_wae_forward')
+    return mu, logvar, z, logits
+
+
+def wae_backward(params, n_vocab, tokens, eps, c, word_drop, out_keep, p_out, d_mu, d_logvar, d_z, d_logits,
+                 grads_out=None):
+    B, L = _check_shapes(tokens, eps, c, word_drop, out_keep)
+    dev = tokens.device
+    if grads_out is None:
+        grads_out = torch.empty_like(params)
+    inp = _inputs(tokens, eps, c, word_drop, out_keep, p_out)
+    check(lib().cpg_wae_backward(context(dev), stream_ptr(), ptr(params), n_vocab, B, L, byref(inp), ptr(d_mu),
+                                 ptr(d_logvar), ptr(d_z), ptr(d_logits), ptr(grads_out)), 'cpg_wae_backward')
+    return grads_out
+
+
+def wae_encode(params, n_vocab, tokens):
+    B, L = tokens.shape
+    dev = tokens.device
+    mu = torch.empty(B, ZD, device=dev)
+    logvar = torch.empty(B, ZD, device=dev)
+    check(lib().cpg_wae_encode(context(dev), stream_ptr(), ptr(params), n_vocab, B, L,
+                               ptr(tokens, torch.int64, allow_none=False), ptr(mu), ptr(logvar)), 'cpg_wae_encode')
+    return mu, logvar
+
+
+def make_hparams(lr=1e-3, betas=(0.9, 0.999), adam_eps=1e-8, clip_norm=5.0, beta=1.0, lambda_logvar_l1=0.0,
+                 lambda_logvar_kl=1e-3, z_regu='mmdrf', mmd_sigma=7.0, rf_dim=500, compute_full_mmd=True,
+                 adam_step=1, global_batch=0):
+    hp = TrainHparams()
+    hp.lr, hp.beta1, hp.beta2, hp.adam_eps = lr, betas[0], betas[1], adam_eps
+    hp.clip_norm, hp.beta = clip_norm, beta
+    hp.lambda_logvar_l1, hp.lambda_logvar_kl = lambda_logvar_l1, lambda_logvar_kl
+    hp.z_regu = ZREGU[z_regu] if isinstance(z_regu, str) else int(z_regu)
+    hp.mmd_sigma, hp.rf_dim = mmd_sigma, rf_dim
+    hp.compute_full_mmd = 1 if compute_full_mmd else 0
+    hp.adam_step, hp.global_batch = adam_step, global_batch
+    return hp
+
+
+def _loss_noise(noise):
+    nz = LossNoise()
+    nz.z_prior_full = ptr(noise.get('z_prior_full'), torch.float32)
+    nz.z_prior_rf = ptr(noise['z_prior_rf'], torch.float32, allow_none=False)
+    nz.rf_w = ptr(noise['rf_w'], torch.float32, allow_none=False)
+    nz.rf_b = ptr(noise['rf_b'], torch.float32, allow_none=False)
+    return nz
+
+
+def train_step(state, tokens, noise, hp, p_out=0.3, want=()):
+    """One fused iteration of train_vae.py:24-42 on one GPU.  `noise` holds eps, c,
+    word_drop, out_keep, z_prior_full, z_prior_rf, rf_w, rf_b (device tensors).
+    Returns (scalars[SC_COUNT] device tensor, dict of requested extras)."""
+    B, L = _check_shapes(tokens, noise['eps'], noise['c'], noise.get('word_drop'), noise.get('out_keep'))
+    dev = tokens.device
+    V = state.n_vocab
+    scalars = torch.zeros(SC_COUNT, device=dev)
+    extras = {}
+    for k, shp in (('mu', (B, ZD)), ('logvar', (B, ZD)), ('z', (B, ZD)), ('logits', (B, L, V))):
+        extras[k] = torch.empty(shp, device=dev) if k in want else None
+    inp = _inputs(tokens, noise['eps'], noise['c'], noise.get('word_drop'), noise.get('out_keep'), p_out)
+    nz = _loss_noise(noise)
+    state.step += 1
+    hp.adam_step = state.step
+    check(lib().cpg_wae_train_step(context(dev), stream_ptr(), ptr(state.params), ptr(state.grads), ptr(state.adam_m),
+                                   ptr(state.adam_v), V, B, L, byref(inp), byref(nz), byref(hp), ptr(scalars),
+                                   ptr(extras['mu']), ptr(extras['logvar']), ptr(extras['z']), ptr(extras['logits'])),
+          'cpg_wae_train_step')
+    return scalars, {k: v for k, v in extras.items() if v is not None}
+
+
+def step_phase1(state, tokens, noise, hp, p_out=0.3):
+    B, L = _check_shapes(tokens, noise['eps'], noise['c'], noise.get('word_drop'), noise.get('out_keep'))
+    dev = tokens.device
+    coupled = torch.zeros(int(lib().cpg_coupled_count(hp.rf_dim)), device=dev)
+    inp = _inputs(tokens, noise['eps'], noise['c'], noise.get('word_drop'), noise.get('out_keep'), p_out)
+    nz = _loss_noise(noise)
+    z = torch.empty(B, ZD, device=dev)
+    check(lib().cpg_wae_step_phase1(context(dev), stream_ptr(), ptr(state.params), state.n_vocab, B, L, byref(inp),
+                                    byref(nz), byref(hp), ptr(coupled), c_void_p(None), c_void_p(None), ptr(z)),
+          'cpg_wae_step_phase1')
+    return coupled, z
+
+
+def step_phase2(state, tokens, noise, hp, coupled, p_out=0.3):
+    B, L = tokens.shape
+    dev = tokens.device
+    scalars = torch.zeros(SC_COUNT, device=dev)
+    inp = _inputs(tokens, noise['eps'], noise['c'], noise.get('word_drop'), noise.get('out_keep'), p_out)
+    nz = _loss_noise(noise)
+    check(lib().cpg_wae_step_phase2(context(dev), stream_ptr(), ptr(state.params), ptr(state.grads), state.n_vocab,
+                                    B, L, byref(inp), byref(nz), byref(hp), ptr(coupled), ptr(scalars),
+                                    c_void_p(None)), 'cpg_wae_step_phase2')
+    return scalars
+
+
+def clip_adam(state, hp):
+    dev = state.params.device
+    gn = torch.zeros(1, device=dev)
+    check(lib().cpg_clip_adam_step(context(dev), stream_ptr(), ptr(state.params), ptr(state.grads), ptr(state.adam_m),
+                                   ptr(state.adam_v), state.n_vocab, byref(hp), ptr(gn)), 'cpg_clip_adam_step')
+    return gn
+
+
+# ------------------------------------------------------------------ losses.py ops
+def softmax_xent(logits, tokens, want_grad=False):
+    B, L, V = logits.shape
+    dev = logits.device
+    out = torch.empty(2, device=dev)
+    dl = torch.empty_like(logits) if want_grad else None
+    check(lib().cpg_softmax_xent(context(dev), stream_ptr(), ptr(logits.contiguous(), torch.float32),
+                                 ptr(tokens, torch.int64), B, L, V, ptr(out), ptr(dl)), 'cpg_softmax_xent')
+    return out, dl
+
+
+def latent_stats(mu, logvar):
+    out = torch.empty(5, device=mu.device)
+    check(lib().cpg_latent_stats(context(mu.device), stream_ptr(), ptr(mu.contiguous(), torch.float32),
+                                 ptr(logvar.contiguous(), torch.float32), mu.shape[0], ptr(out)), 'cpg_latent_stats')
+    return out
+
+
+def mmd_full(z, z_prior, sigma):
+    out = torch.empty(1, device=z.device)
+    check(lib().cpg_mmd_full(context(z.device), stream_ptr(), ptr(z.contiguous(), torch.float32),
+                             ptr(z_prior.contiguous(), torch.float32), z.shape[0], float(sigma), ptr(out)),
+          'cpg_mmd_full')
+    return out
+
+
+def mmd_rf(z, z_prior, rf_w, rf_b, sigma, want_grad=False):
+    out = torch.empty(1, device=z.device)
+    dz = torch.empty_like(z) if want_grad else None
+    check(lib().cpg_mmd_rf(context(z.device), stream_ptr(), ptr(z.contiguous(), torch.float32),
+                           ptr(z_prior.contiguous(), torch.float32), ptr(rf_w.contiguous(), torch.float32),
+                           ptr(rf_b.contiguous(), torch.float32), z.shape[0], rf_w.shape[1], float(sigma), ptr(out),
+                           ptr(dz)), 'cpg_mmd_rf')
+    return out, dz

@@ -1,0 +1,92 @@
+// Global-norm gradient clipping + Adam on the flat parameter buffer, reproducing the
+// reference optimizer semantics of train_vae.py:15,41-42 -- including the fact that
+// `RNN_VAE.vae_params()` (models/model.py:88-94) yields the shared embedding matrix TWICE:
+//   (i)  its squared gradient norm enters the total norm twice,
+//   (ii) `clip_grad_norm_` scales its gradient once per list entry (coef^2 overall),
+//   (iii) Adam applies two sequential updates per iteration to it (its step counter += 2).
+#include "kernels.h"
+#include "adam.h"
+
+namespace cpg {
+
+constexpr int NORM_THREADS = 256;
+
+__global__ void __launch_bounds__(NORM_THREADS)
+k_sumsq_partial(const float* __restrict__ g, int64_t n, int64_t dup_off, int64_t dup_n, float* __restrict__ part) {
+    __shared__ float red[NORM_THREADS / 32];
+    float s = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = g[i];
+        float w = (i >= dup_off && i < dup_off + dup_n) ? 2.f : 1.f;
+        s = fmaf(w * v, v, s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < NORM_THREADS / 32; ++w) t += red[w];
+        part[blockIdx.x] = t;
+    }
+}
+
+// total norm, clip coefficient (torch: clamp(max_norm / (total + 1e-6), max=1))
+__global__ void k_norm_final(const float* __restrict__ part, int nparts, float max_norm, float* __restrict__ norm_out,
+                             float* __restrict__ coef_out) {
+    if (threadIdx.x != 0) return;
+    double s = 0.0;
+    for (int i = 0; i < nparts; ++i) s += (double)part[i];
+    float total = (float)sqrt(s);
+    if (norm_out != nullptr) *norm_out = total;
+    float c = max_norm / (total + 1e-6f);
+    *coef_out = c < 1.0f ? c : 1.0f;
+}
+
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamStep& st, float b1,
+                                            float b2, float eps) {
+    m = m + (g - m) * (1.0f - b1);                       // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * b2 + (1.0f - b2) * g * g;                    // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    float denom = sqrtf(v) / st.bc2_sqrt + eps;
+    p = p - st.step_size * (m / denom);                  // addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+__global__ void k_clip_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int64_t n, int64_t dup_off, int64_t dup_n, const float* __restrict__ coef_ptr,
+                            AdamHyper h) {
+    const float coef = *coef_ptr;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool dup = (i >= dup_off && i < dup_off + dup_n);
+        float gi = g[i] * coef;
+        if (dup) gi *= coef;
+        g[i] = gi;
+        float pi = p[i], mi = m[i], vi = v[i];
+        if (dup) {
+            adam_update(pi, mi, vi, gi, h.dup_first, h.beta1, h.beta2, h.eps);
+            adam_update(pi, mi, vi, gi, h.dup_second, h.beta1, h.beta2, h.eps);
+        } else {
+            adam_update(pi, mi, vi, gi, h.single, h.beta1, h.beta2, h.eps);
+        }
+        p[i] = pi; m[i] = mi; v[i] = vi;
+    }
+}
+
+int adam_norm_parts(int64_t n, int sm_count) {
+    int64_t want = (n + NORM_THREADS * 4 - 1) / (NORM_THREADS * 4);
+    int cap = 2 * (sm_count > 0 ? sm_count : 1);
+    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+void launch_grad_norm(cudaStream_t s, const float* g, int64_t n, int64_t dup_off, int64_t dup_n, float max_norm,
+                      int sm_count, float* part, float* norm_out, float* coef_out) {
+    int parts = adam_norm_parts(n, sm_count);
+    CPG_LAUNCH(k_sumsq_partial, parts, NORM_THREADS, 0, s, g, n, dup_off, dup_n, part);
+    CPG_LAUNCH(k_norm_final, 1, 32, 0, s, part, parts, max_norm, norm_out, coef_out);
+}
+
+void launch_clip_adam(cudaStream_t s, float* p, float* g, float* m, float* v, int64_t n, int64_t dup_off,
+                      int64_t dup_n, const float* coef, const AdamHyper& h, int sm_count) {
+    int parts = adam_norm_parts(n, sm_count);
+    CPG_LAUNCH(k_clip_adam, parts, NORM_THREADS, 0, s, p, g, m, v, n, dup_off, dup_n, coef, h);
+}
+
+}  // namespace cpg

@@ -1,0 +1,552 @@
+// C ABI: context, workspace and the WAE training / inference entry points.
+#include <string.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string>
+#include "ctx.h"
+
+namespace cpg {
+
+long long g_launch_count = 0;
+static thread_local std::string g_err;
+void set_error(const std::string& m) { g_err = m; }
+
+#ifdef CPG_EMU
+static int dev_alloc(void** p, size_t n) { *p = calloc(1, n); return *p ? 0 : -1; }
+static void dev_free(void* p) { free(p); }
+static int dev_d2h(void* dst, const void* src, size_t n, cudaStream_t) { memcpy(dst, src, n); return 0; }
+static int dev_sync(cudaStream_t) { return 0; }
+static int dev_memset(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
+static int dev_copy(void* d, const void* s_, size_t n, cudaStream_t) { memcpy(d, s_, n); return 0; }
+static int dev_last_error(const char** msg) { *msg = ""; return 0; }
+#else
+static int dev_alloc(void** p, size_t n) { return cudaMalloc(p, n) == cudaSuccess ? 0 : -1; }
+static void dev_free(void* p) { cudaFree(p); }
+static int dev_d2h(void* dst, const void* src, size_t n, cudaStream_t s) {
+    if (cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
+    return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -1;
+}
+static int dev_sync(cudaStream_t s) { return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -1; }
+static int dev_memset(void* p, int v, size_t n, cudaStream_t s) {
+    return cudaMemsetAsync(p, v, n, s) == cudaSuccess ? 0 : -1;
+}
+static int dev_copy(void* d, const void* s_, size_t n, cudaStream_t s) {
+    return cudaMemcpyAsync(d, s_, n, cudaMemcpyDeviceToDevice, s) == cudaSuccess ? 0 : -1;
+}
+static int dev_last_error(const char** msg) {
+    cudaError_t e = cudaGetLastError();
+    *msg = cudaGetErrorString(e);
+    return e == cudaSuccess ? 0 : -1;
+}
+#endif
+
+int check_launch(const char* where) {
+    const char* msg;
+    if (dev_last_error(&msg) != 0) {
+        set_error(std::string(where) + ": CUDA error: " + msg);
+        return CPG_ECUDA;
+    }
+    return CPG_OK;
+}
+
+struct Bump {
+    char* base; size_t off;
+    template <typename T> T* take(size_t n) {
+        off = align_up(off, 256);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, int R, char* base) {
+    Bump a{base, 0};
+    const size_t BL = (size_t)B * L;
+    const int sm = ctx->sm_count;
+    w.B = B; w.L = L; w.V = V; w.R = R;
+    // derived weights
+    for (int d = 0; d < 2; ++d) w.d.t_enc[d] = a.take<float>((size_t)V * 3 * ENC_H);
+    w.d.t_dec = a.take<float>((size_t)V * 3 * DEC_HP);
+    for (int d = 0; d < 2; ++d) w.d.whh_t_enc[d] = a.take<float>((size_t)ENC_H * 3 * ENC_H);
+    w.d.whh_t_dec = a.take<float>((size_t)DEC_HP * 3 * DEC_HP);
+    w.d.whh_dec = a.take<float>((size_t)DEC_HP * 3 * DEC_HP);
+    w.d.wizc_t = a.take<float>((size_t)DEC_HP * 3 * DEC_HP);
+    w.d.wizc = a.take<float>((size_t)DEC_HP * 3 * DEC_HP);
+    for (int d = 0; d < 2; ++d) w.d.bhn_enc[d] = a.take<float>(ENC_H);
+    w.d.bhn_dec = a.take<float>(DEC_HP);
+    w.d.fc_w = a.take<float>((size_t)VMAX * DEC_HP);
+    w.d.fc_b = a.take<float>(VMAX);
+    // tokens
+    w.tok = a.take<uint8_t>(BL); w.tokd = a.take<uint8_t>(BL); w.tgt = a.take<uint8_t>(BL);
+    // encoder
+    for (int d = 0; d < 2; ++d) {
+        w.enc_hs[d] = a.take<float>(BL * ENC_H);
+        w.enc_gates[d] = a.take<float>(BL * 4 * ENC_H);
+        w.enc_dg[d] = a.take<float>(BL * 4 * ENC_H);
+    }
+    w.hfin = a.take<float>((size_t)B * 2 * ENC_H);
+    w.mu = a.take<float>((size_t)B * ZD); w.logvar = a.take<float>((size_t)B * ZD); w.z = a.take<float>((size_t)B * ZD);
+    w.zc = a.take<float>((size_t)B * DEC_HP);
+    w.rowbias = a.take<float>((size_t)B * 3 * DEC_HP);
+    // decoder
+    w.dec_hs = a.take<float>(BL * DEC_HP);
+    w.dec_gates = a.take<float>(BL * 4 * DEC_HP);
+    w.dec_dg = a.take<float>(BL * 4 * DEC_HP);
+    w.dec_dh_out = a.take<float>(BL * DEC_HP);
+    w.drow = a.take<float>((size_t)B * 3 * DEC_HP);
+    w.dh0 = a.take<float>((size_t)B * DEC_HP);
+    w.dmu = a.take<float>((size_t)B * ZD); w.dlv = a.take<float>((size_t)B * ZD);
+    w.dhfin = a.take<float>((size_t)B * 2 * ENC_H);
+    // random features
+    w.rf_nchunk = std::max(1, std::min(B, 2 * sm));
+    w.rf_pre1 = a.take<float>((size_t)B * R); w.rf_pre2 = a.take<float>((size_t)B * R);
+    w.rf_part = a.take<float>((size_t)w.rf_nchunk * R);
+    w.rf_sum1 = a.take<float>(R); w.rf_sum2 = a.take<float>(R); w.rf_coef = a.take<float>(R);
+    w.dz_rf = a.take<float>((size_t)B * ZD);
+    w.lat_nparts = std::max(1, std::min(ceil_div(B, 8), 2 * sm));
+    w.lat_part = a.take<float>((size_t)w.lat_nparts * 5); w.lat_sums = a.take<float>(8);
+    w.mmd_ws = a.take<float>(mmd_full_ws_floats(B)); w.mmd_out = a.take<float>(4); w.mmdrf_out = a.take<float>(4);
+    // decoder output partials
+    int parts = dec_out_parts(B, L, sm);
+    w.do_part_w = a.take<float>((size_t)parts * VMAX * DEC_HP);
+    w.do_part_b = a.take<float>((size_t)parts * VMAX);
+    w.do_part_nll = a.take<float>(parts);
+    w.nll_sum = a.take<float>(4);
+    // weight-gradient partials
+    int ws_ = wgrad_splits(B, L, sm);
+    w.wg_part = a.take<float>((size_t)ws_ * 3 * DEC_HP * DEC_HP);
+    int ds_ = dtable_splits(B, L, sm);
+    w.dt_part = a.take<float>((size_t)ds_ * V * 4 * DEC_HP);
+    for (int d = 0; d < 2; ++d) w.dT_enc[d] = a.take<float>((size_t)V * 4 * ENC_H);
+    w.dT_dec = a.take<float>((size_t)V * 4 * DEC_HP);
+    w.dwizc = a.take<float>((size_t)3 * DEC_HP * DEC_HP);
+    w.gemm_splits = std::max(1, std::min(ceil_div(B, 64), sm / 2));
+    w.gemm_ws = a.take<float>((size_t)w.gemm_splits * 3 * DEC_HP * (2 * ENC_H));
+    w.colsum_ws = a.take<float>((size_t)64 * 512);
+    w.norm_part = a.take<float>(2 * sm + 8);
+    w.clip_coef = a.take<float>(4);
+    w.scalars = a.take<float>(SC_COUNT);
+    w.ntok_f = a.take<float>(4);
+    w.coupled = a.take<float>(8 + 2 * (size_t)R);
+    return align_up(a.off, 256);
+}
+
+int ensure_workspace(cpg_ctx* ctx, int B, int L, int V, int R, cudaStream_t stream) {
+    Workspace& w = ctx->ws;
+    if (w.B == B && w.L == L && w.V == V && w.R == R && ctx->base != nullptr) return CPG_OK;
+    Workspace probe;
+    size_t need = layout_workspace(ctx, probe, B, L, V, R, nullptr);
+    if (need > ctx->capacity) {
+        dev_sync(stream);
+        if (ctx->base) dev_free(ctx->base);
+        ctx->base = nullptr;
+        ctx->capacity = 0;
+        void* p = nullptr;
+        if (dev_alloc(&p, need) != 0) {
+            set_error("workspace allocation of " + std::to_string(need) + " bytes failed");
+            return CPG_ENOMEM;
+        }
+        ctx->base = p;
+        ctx->capacity = need;
+    }
+    layout_workspace(ctx, w, B, L, V, R, (char*)ctx->base);
+    ctx->have_stash = false;
+    return CPG_OK;
+}
+
+static int check_dims(int V, int B, int L) {
+    if (V < 4 || V > VMAX) { set_error("n_vocab must be in [4, 32]"); return CPG_EINVAL; }
+    if (B < 1) { set_error("batch must be >= 1"); return CPG_EINVAL; }
+    if (L < 2 || L > LMAX) { set_error("seq_len must be in [2, 32]"); return CPG_EINVAL; }
+    return CPG_OK;
+}
+
+// ------------------------------------------------------------------------------------ forward
+static void forward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, const ParamLayout& lay, int V, int B, int L,
+                         const cpg_wae_inputs* in, float* mu, float* logvar, float* z, bool stash, bool encoder_only) {
+    Workspace& w = ctx->ws;
+    launch_prep_tokens(s, in->tokens, in->word_drop, B, L, V, w.tok, w.tokd, w.tgt, ctx->ints, ctx->ints + 1);
+    launch_prep_weights(s, params, lay, V, w.d);
+    GruSeq enc[2];
+    for (int d = 0; d < 2; ++d) {
+        GruSeq& q = enc[d];
+        memset(&q, 0, sizeof(q));
+        q.tok = w.tok; q.table = w.d.t_enc[d]; q.whh_t = w.d.whh_t_enc[d]; q.bhn = w.d.bhn_enc[d];
+        q.hs = stash ? w.enc_hs[d] : nullptr;
+        q.gates = stash ? w.enc_gates[d] : nullptr;
+        q.hfin = w.hfin + d * ENC_H; q.hfin_stride = 2 * ENC_H;
+        q.reverse = d;
+    }
+    launch_gru_fwd_enc(s, enc, B, L);
+    // q_mu / q_logvar heads (models/encoder.py:50-51)
+    launch_sgemm(s, B, ZD, 2 * ENC_H, 1.f, w.hfin, 2 * ENC_H, 1, params + lay.off[P_QMU_W], 1, 2 * ENC_H, 0.f,
+                 mu, ZD, params + lay.off[P_QMU_B], 1, nullptr);
+    launch_sgemm(s, B, ZD, 2 * ENC_H, 1.f, w.hfin, 2 * ENC_H, 1, params + lay.off[P_QLV_W], 1, 2 * ENC_H, 0.f,
+                 logvar, ZD, params + lay.off[P_QLV_B], 1, nullptr);
+    if (encoder_only) return;
+    launch_reparam(s, mu, logvar, in->eps, in->c, B, z, w.zc);
+    // per-row input projection of [z;c] (the non-embedding columns of decoder W_ih)
+    launch_sgemm(s, B, 3 * DEC_HP, DEC_HP, 1.f, w.zc, DEC_HP, 1, w.d.wizc_t, 3 * DEC_HP, 1, 0.f, w.rowbias,
+                 3 * DEC_HP, nullptr, 1, nullptr);
+    GruSeq q;
+    memset(&q, 0, sizeof(q));
+    q.tok = w.tokd; q.table = w.d.t_dec; q.rowbias = w.rowbias; q.whh_t = w.d.whh_t_dec; q.bhn = w.d.bhn_dec;
+    q.h0 = w.zc; q.hs = w.dec_hs; q.gates = stash ? w.dec_gates : nullptr;
+    launch_gru_fwd_dec(s, q, B, L);
+}
+
+static DecOutArgs dec_out_args(cpg_ctx* ctx, const cpg_wae_inputs* in, int V, int B, int L) {
+    Workspace& w = ctx->ws;
+    DecOutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.hs = w.dec_hs;
+    a.out_keep = in->out_keep;
+    a.keep_scale = 1.0f / (1.0f - in->p_out_dropout);
+    a.fc_w = w.d.fc_w; a.fc_b = w.d.fc_b; a.tgt = w.tgt;
+    a.part_w = w.do_part_w; a.part_b = w.do_part_b; a.part_nll = w.do_part_nll;
+    a.B = B; a.L = L; a.V = V;
+    return a;
+}
+
+// ----------------------------------------------------------------------------------- backward
+// Everything after the decoder-output layer has produced dec_dh_out.  dz_rf / external latent
+// gradients are optional.
+static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, const ParamLayout& lay, float* grads,
+                          int V, int B, int L, const cpg_wae_inputs* in, const LatentBwdArgs& lat_in) {
+    Workspace& w = ctx->ws;
+    const int sm = ctx->sm_count;
+    // decoder BPTT
+    GruSeq q;
+    memset(&q, 0, sizeof(q));
+    q.whh = w.d.whh_dec; q.h0 = w.zc; q.hs = w.dec_hs; q.gates = w.dec_gates;
+    q.dh_out = w.dec_dh_out; q.dg = w.dec_dg; q.dh0 = w.dh0; q.drow = w.drow;
+    launch_gru_bwd_dec(s, q, B, L);
+    // gradient at [z;c]:  dh0 + drow @ W_ih[:,150:]   (in place on dh0)
+    launch_sgemm(s, B, DEC_HP, 3 * DEC_HP, 1.f, w.drow, 3 * DEC_HP, 1, w.d.wizc, DEC_HP, 1, 1.f, w.dh0, DEC_HP,
+                 nullptr, 1, nullptr);
+    // dW_ih[:,150:] = drow^T @ [z;c]
+    launch_sgemm(s, 3 * DEC_HP, DEC_HP, B, 1.f, w.drow, 1, 3 * DEC_HP, w.zc, DEC_HP, 1, 0.f, w.dwizc, DEC_HP,
+                 nullptr, w.gemm_splits, w.gemm_ws);
+    // latent
+    LatentBwdArgs la = lat_in;
+    la.mu = w.mu; la.logvar = w.logvar; la.eps = in->eps; la.dzc = w.dh0; la.B = B;
+    la.dmu = w.dmu; la.dlv = w.dlv;
+    launch_latent_bwd(s, la);
+    // heads
+    const float* wmu = params + lay.off[P_QMU_W];
+    const float* wlv = params + lay.off[P_QLV_W];
+    launch_sgemm(s, B, 2 * ENC_H, ZD, 1.f, w.dmu, ZD, 1, wmu, 2 * ENC_H, 1, 0.f, w.dhfin, 2 * ENC_H, nullptr, 1, nullptr);
+    launch_sgemm(s, B, 2 * ENC_H, ZD, 1.f, w.dlv, ZD, 1, wlv, 2 * ENC_H, 1, 1.f, w.dhfin, 2 * ENC_H, nullptr, 1, nullptr);
+    launch_sgemm(s, ZD, 2 * ENC_H, B, 1.f, w.dmu, 1, ZD, w.hfin, 2 * ENC_H, 1, 0.f, grads + lay.off[P_QMU_W],
+                 2 * ENC_H, nullptr, w.gemm_splits, w.gemm_ws);
+    launch_sgemm(s, ZD, 2 * ENC_H, B, 1.f, w.dlv, 1, ZD, w.hfin, 2 * ENC_H, 1, 0.f, grads + lay.off[P_QLV_W],
+                 2 * ENC_H, nullptr, w.gemm_splits, w.gemm_ws);
+    launch_colsum(s, w.dmu, B, ZD, ZD, grads + lay.off[P_QMU_B], w.colsum_ws, 64);
+    launch_colsum(s, w.dlv, B, ZD, ZD, grads + lay.off[P_QLV_B], w.colsum_ws, 64);
+    // encoder BPTT
+    GruSeq enc[2];
+    for (int d = 0; d < 2; ++d) {
+        GruSeq& e = enc[d];
+        memset(&e, 0, sizeof(e));
+        e.whh = params + lay.off[d == 0 ? P_ENC_WHH_F : P_ENC_WHH_R];
+        e.hs = w.enc_hs[d]; e.gates = w.enc_gates[d];
+        e.dh_fin = w.dhfin + d * ENC_H; e.dh_fin_stride = 2 * ENC_H;
+        e.dg = w.enc_dg[d];
+    }
+    launch_gru_bwd_enc(s, enc, B, L);
+    // recurrent weight gradients
+    launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[0], w.enc_hs[0], nullptr, B, L, sm, w.wg_part, grads + lay.off[P_ENC_WHH_F]);
+    launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[1], w.enc_hs[1], nullptr, B, L, sm, w.wg_part, grads + lay.off[P_ENC_WHH_R]);
+    launch_wgrad_hh(s, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, B, L, sm, w.wg_part, grads + lay.off[P_DEC_WHH]);
+    // token-table gradients -> embedding / W_ih / biases
+    launch_dtable(s, ENC_H, w.enc_dg[0], w.tok, B, L, 0, V, sm, w.dt_part, w.dT_enc[0]);
+    launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part, w.dT_enc[1]);
+    launch_dtable(s, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part, w.dT_dec);
+    InputGradArgs ia;
+    memset(&ia, 0, sizeof(ia));
+    ia.emb = params + lay.off[P_EMB];
+    ia.enc_wih[0] = params + lay.off[P_ENC_WIH_F]; ia.enc_wih[1] = params + lay.off[P_ENC_WIH_R];
+    ia.dec_wih = params + lay.off[P_DEC_WIH];
+    ia.dT_enc[0] = w.dT_enc[0]; ia.dT_enc[1] = w.dT_enc[1]; ia.dT_dec = w.dT_dec; ia.dwizc = w.dwizc;
+    ia.g_emb = grads + lay.off[P_EMB];
+    ia.g_enc_wih[0] = grads + lay.off[P_ENC_WIH_F]; ia.g_enc_bih[0] = grads + lay.off[P_ENC_BIH_F];
+    ia.g_enc_bhh[0] = grads + lay.off[P_ENC_BHH_F];
+    ia.g_enc_wih[1] = grads + lay.off[P_ENC_WIH_R]; ia.g_enc_bih[1] = grads + lay.off[P_ENC_BIH_R];
+    ia.g_enc_bhh[1] = grads + lay.off[P_ENC_BHH_R];
+    ia.g_dec_wih = grads + lay.off[P_DEC_WIH]; ia.g_dec_bih = grads + lay.off[P_DEC_BIH];
+    ia.g_dec_bhh = grads + lay.off[P_DEC_BHH];
+    ia.V = V;
+    launch_input_grads(s, ia);
+}
+
+static AdamHyper adam_hyper(const cpg_train_hparams* hp) {
+    AdamHyper h;
+    h.beta1 = hp->beta1; h.beta2 = hp->beta2; h.eps = hp->adam_eps;
+    auto mk = [&](int step) {
+        AdamStep st;
+        double bc1 = 1.0 - pow((double)hp->beta1, (double)step);
+        double bc2 = 1.0 - pow((double)hp->beta2, (double)step);
+        st.step_size = (float)((double)hp->lr / bc1);
+        st.bc2_sqrt = (float)sqrt(bc2);
+        return st;
+    };
+    h.single = mk(hp->adam_step);
+    h.dup_first = mk(2 * hp->adam_step - 1);
+    h.dup_second = mk(2 * hp->adam_step);
+    return h;
+}
+
+}  // namespace cpg
+
+using namespace cpg;
+
+extern "C" {
+
+int cpg_abi_version(void) { return CPG_ABI_VERSION; }
+const char* cpg_last_error(void) { return g_err.c_str(); }
+
+int cpg_create(cpg_ctx** out, int device) {
+    if (out == nullptr) { set_error("cpg_create: out is null"); return CPG_EINVAL; }
+    cpg_ctx* c = new cpg_ctx();
+    c->device = device;
+#ifndef CPG_EMU
+    if (cudaSetDevice(device) != cudaSuccess) {
+        set_error("cpg_create: cudaSetDevice failed (is a CUDA device present?)");
+        delete c;
+        return CPG_ECUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        set_error("cpg_create: cudaGetDeviceProperties failed");
+        delete c;
+        return CPG_ECUDA;
+    }
+    if (prop.major < 10) {
+        set_error(std::string("cpg_create: device '") + prop.name + "' is not sm_100-class; this library is built for sm_100a only");
+        delete c;
+        return CPG_ECUDA;
+    }
+    c->sm_count = prop.multiProcessorCount;
+#endif
+    void* p = nullptr;
+    if (dev_alloc(&p, 64) != 0) { set_error("cpg_create: allocation failed"); delete c; return CPG_ENOMEM; }
+    c->ints = (int*)p;
+    dev_memset(c->ints, 0, 64, nullptr);
+    dev_sync(nullptr);
+    *out = c;
+    return CPG_OK;
+}
+
+int cpg_destroy(cpg_ctx* c) {
+    if (c == nullptr) return CPG_OK;
+    if (c->base) dev_free(c->base);
+    if (c->ints) dev_free(c->ints);
+    delete c;
+    return CPG_OK;
+}
+
+int cpg_sm_count(const cpg_ctx* c) { return c ? c->sm_count : 0; }
+int64_t cpg_workspace_bytes(const cpg_ctx* c) { return c ? (int64_t)c->capacity : 0; }
+int64_t cpg_launch_count(const cpg_ctx*) { return (int64_t)g_launch_count; }
+
+int cpg_check_errors(cpg_ctx* c, cpg_stream stream) {
+    int host[2] = {0, 0};
+    if (dev_d2h(host, c->ints, sizeof(host), (cudaStream_t)stream) != 0) { set_error("cpg_check_errors: copy failed"); return CPG_ECUDA; }
+    if (host[1] != 0) { set_error("token id outside [0, n_vocab) in an input batch"); return CPG_ETOKEN; }
+    return check_launch("cpg_check_errors");
+}
+
+int64_t cpg_vae_param_count(int V) { return make_layout(V).total; }
+int cpg_vae_param_layout(int V, int64_t offsets[CPG_N_PARAM_TENSORS], int64_t sizes[CPG_N_PARAM_TENSORS]) {
+    if (V < 4 || V > VMAX) { set_error("n_vocab must be in [4, 32]"); return CPG_EINVAL; }
+    ParamLayout l = make_layout(V);
+    for (int i = 0; i < P_COUNT; ++i) { offsets[i] = l.off[i]; sizes[i] = l.size[i]; }
+    return CPG_OK;
+}
+
+int cpg_wae_encode(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int B, int L, const int64_t* tokens,
+                   float* mu, float* logvar) {
+    int rc = check_dims(V, B, L);
+    if (rc) return rc;
+    if (!ctx || !params || !tokens || !mu || !logvar) { set_error("cpg_wae_encode: null argument"); return CPG_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = ensure_workspace(ctx, B, L, V, ctx->ws.R > 0 ? ctx->ws.R : 500, s))) return rc;
+    cpg_wae_inputs in;
+    memset(&in, 0, sizeof(in));
+    in.tokens = tokens;
+    forward_impl(ctx, s, params, make_layout(V), V, B, L, &in, mu, logvar, nullptr, false, true);
+    ctx->have_stash = false;
+    return check_launch("cpg_wae_encode");
+}
+
+int cpg_wae_forward(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int B, int L, const cpg_wae_inputs* in,
+                    float* mu, float* logvar, float* z, float* logits, int keep) {
+    int rc = check_dims(V, B, L);
+    if (rc) return rc;
+    if (!ctx || !params || !in || !in->tokens || !in->c) { set_error("cpg_wae_forward: null argument"); return CPG_EINVAL; }
+    if (in->out_keep && !(in->p_out_dropout >= 0.f && in->p_out_dropout < 1.f)) { set_error("p_out_dropout must be in [0,1)"); return CPG_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = ensure_workspace(ctx, B, L, V, ctx->ws.R > 0 ? ctx->ws.R : 500, s))) return rc;
+    Workspace& w = ctx->ws;
+    ParamLayout lay = make_layout(V);
+    forward_impl(ctx, s, params, lay, V, B, L, in, w.mu, w.logvar, w.z, keep != 0, false);
+    if (mu) dev_copy(mu, w.mu, (size_t)B * ZD * 4, s);
+    if (logvar) dev_copy(logvar, w.logvar, (size_t)B * ZD * 4, s);
+    if (z) dev_copy(z, w.z, (size_t)B * ZD * 4, s);
+    if (logits) {
+        DecOutArgs a = dec_out_args(ctx, in, V, B, L);
+        a.logits_out = logits;
+        a.part_nll = nullptr;
+        launch_dec_out(s, a, ctx->sm_count);
+    }
+    ctx->have_stash = keep != 0;
+    return check_launch("cpg_wae_forward");
+}
+
+int cpg_wae_backward(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int B, int L, const cpg_wae_inputs* in,
+                     const float* d_mu, const float* d_logvar, const float* d_z, const float* d_logits, float* grads) {
+    int rc = check_dims(V, B, L);
+    if (rc) return rc;
+    if (!ctx || !params || !in || !grads) { set_error("cpg_wae_backward: null argument"); return CPG_EINVAL; }
+    Workspace& w = ctx->ws;
+    if (!ctx->have_stash || w.B != B || w.L != L || w.V != V) {
+        set_error("cpg_wae_backward: no matching cpg_wae_forward(keep_for_backward=1) stash");
+        return CPG_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    ParamLayout lay = make_layout(V);
+    dev_memset(grads, 0, (size_t)lay.total * 4, s);
+    DecOutArgs a = dec_out_args(ctx, in, V, B, L);
+    a.dlogits_in = d_logits;           // null -> zero gradient through the logits
+    a.dh_out = w.dec_dh_out;
+    a.part_nll = nullptr;
+    launch_dec_out(s, a, ctx->sm_count);
+    launch_dec_out_reduce(s, a, ctx->sm_count, grads + lay.off[P_FC_W], grads + lay.off[P_FC_B], nullptr);
+    LatentBwdArgs la;
+    memset(&la, 0, sizeof(la));
+    la.dz_ext = d_z; la.dmu_ext = d_mu; la.dlv_ext = d_logvar;
+    la.B_global = B;
+    backward_impl(ctx, s, params, lay, grads, V, B, L, in, la);
+    return check_launch("cpg_wae_backward");
+}
+
+int64_t cpg_coupled_count(int rf_dim) { return 8 + 2 * (int64_t)rf_dim; }
+
+int cpg_wae_step_phase1(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int B, int L,
+                        const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
+                        float* coupled, float* mu, float* logvar, float* z) {
+    int rc = check_dims(V, B, L);
+    if (rc) return rc;
+    if (!ctx || !params || !in || !nz || !hp || !coupled || !in->tokens || !in->c) { set_error("cpg_wae_step_phase1: null argument"); return CPG_EINVAL; }
+    if (!nz->z_prior_rf || !nz->rf_w || !nz->rf_b) { set_error("cpg_wae_step_phase1: RF-MMD noise is required"); return CPG_EINVAL; }
+    const int R = hp->rf_dim;
+    if (R < 1 || R > 4096) { set_error("rf_dim out of range"); return CPG_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = ensure_workspace(ctx, B, L, V, R, s))) return rc;
+    Workspace& w = ctx->ws;
+    ParamLayout lay = make_layout(V);
+    forward_impl(ctx, s, params, lay, V, B, L, in, w.mu, w.logvar, w.z, true, false);
+    // local statistics that couple the batch: token count, latent sums, RF feature sums
+    launch_int_to_float(s, ctx->ints, coupled + 0, 1);
+    launch_latent_stats(s, w.mu, w.logvar, B, w.lat_part, w.lat_nparts, coupled + 2);
+    launch_sgemm(s, B, R, ZD, 1.f, w.z, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre1, R, nullptr, 1, nullptr);
+    launch_sgemm(s, B, R, ZD, 1.f, nz->z_prior_rf, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre2, R, nullptr, 1, nullptr);
+    launch_rf_colsum(s, w.rf_pre1, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8);
+    launch_rf_colsum(s, w.rf_pre2, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8 + R);
+    if (mu) dev_copy(mu, w.mu, (size_t)B * ZD * 4, s);
+    if (logvar) dev_copy(logvar, w.logvar, (size_t)B * ZD * 4, s);
+    if (z) dev_copy(z, w.z, (size_t)B * ZD * 4, s);
+    ctx->have_stash = true;
+    return check_launch("cpg_wae_step_phase1");
+}
+
+int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, float* grads, int V, int B, int L,
+                        const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
+                        const float* coupled, float* scalars, float* logits) {
+    int rc = check_dims(V, B, L);
+    if (rc) return rc;
+    if (!ctx || !params || !grads || !in || !nz || !hp || !coupled) { set_error("cpg_wae_step_phase2: null argument"); return CPG_EINVAL; }
+    Workspace& w = ctx->ws;
+    if (!ctx->have_stash || w.B != B || w.L != L || w.V != V || w.R != hp->rf_dim) {
+        set_error("cpg_wae_step_phase2: phase1 was not run for this shape");
+        return CPG_EINVAL;
+    }
+    if (hp->z_regu == CPG_ZREGU_MMD) { set_error("z_regu_loss='mmd' (full-kernel MMD in the loss) has no backward here; use mmdrf or kl"); return CPG_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int R = hp->rf_dim;
+    const int Bg = hp->global_batch > 0 ? hp->global_batch : B;
+    ParamLayout lay = make_layout(V);
+    dev_memset(grads, 0, (size_t)lay.total * 4, s);
+    // reconstruction loss fwd+bwd with the global token count (coupled[0])
+    DecOutArgs a = dec_out_args(ctx, in, V, B, L);
+    a.ntok = coupled + 0;
+    a.fused_ce = 1;
+    a.logits_out = logits;
+    a.dh_out = w.dec_dh_out;
+    launch_dec_out(s, a, ctx->sm_count);
+    launch_dec_out_reduce(s, a, ctx->sm_count, grads + lay.off[P_FC_W], grads + lay.off[P_FC_B], w.nll_sum);
+    // RF-MMD from the global feature sums
+    const float w_rf = hp->z_regu == CPG_ZREGU_MMDRF ? hp->beta : 0.f;
+    launch_rf_loss(s, coupled + 8, coupled + 8 + R, R, Bg, hp->mmd_sigma, w_rf, w.rf_coef, w.mmdrf_out);
+    const float* dz_rf = nullptr;
+    if (w_rf != 0.f) {
+        launch_rf_grad_prep(s, w.rf_pre1, nz->rf_b, w.rf_coef, B, R, hp->mmd_sigma);
+        launch_sgemm(s, B, ZD, R, 1.f, w.rf_pre1, R, 1, nz->rf_w, 1, R, 0.f, w.dz_rf, ZD, nullptr, 1, nullptr);
+        dz_rf = w.dz_rf;
+    }
+    if (hp->compute_full_mmd && nz->z_prior_full)
+        launch_mmd_full_simt(s, w.z, nz->z_prior_full, B, hp->mmd_sigma, w.mmd_ws, w.mmd_out);
+    LatentBwdArgs la;
+    memset(&la, 0, sizeof(la));
+    la.dz_rf = dz_rf;
+    la.w_kl = hp->z_regu == CPG_ZREGU_KL ? hp->beta : 0.f;
+    la.w_klsm = hp->lambda_logvar_kl;
+    la.w_l1 = hp->lambda_logvar_l1;
+    la.B_global = Bg;
+    backward_impl(ctx, s, params, lay, grads, V, B, L, in, la);
+    if (scalars) {
+        ComposeArgs c;
+        memset(&c, 0, sizeof(c));
+        c.ntok = coupled + 0; c.nll_sum = w.nll_sum; c.lat_sums = coupled + 2;
+        c.mmd = (hp->compute_full_mmd && nz->z_prior_full) ? w.mmd_out : nullptr;
+        c.mmdrf = w.mmdrf_out;
+        c.beta = hp->beta; c.lambda_l1 = hp->lambda_logvar_l1; c.lambda_kl = hp->lambda_logvar_kl;
+        c.z_regu = hp->z_regu; c.B_global = Bg; c.out = scalars;
+        launch_compose_scalars(s, c);
+    }
+    return check_launch("cpg_wae_step_phase2");
+}
+
+int cpg_clip_adam_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* m, float* v, int V,
+                       const cpg_train_hparams* hp, float* grad_norm_out) {
+    if (!ctx || !params || !grads || !m || !v || !hp) { set_error("cpg_clip_adam_step: null argument"); return CPG_EINVAL; }
+    if (V < 4 || V > VMAX) { set_error("n_vocab must be in [4, 32]"); return CPG_EINVAL; }
+    if (hp->adam_step < 1) { set_error("adam_step is 1-based"); return CPG_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if (ctx->base == nullptr && (rc = ensure_workspace(ctx, 1, 2, V, 500, s))) return rc;
+    Workspace& w = ctx->ws;
+    ParamLayout lay = make_layout(V);
+    launch_grad_norm(s, grads, lay.total, lay.off[P_EMB], lay.size[P_EMB], hp->clip_norm, ctx->sm_count, w.norm_part,
+                     grad_norm_out, w.clip_coef);
+    launch_clip_adam(s, params, grads, m, v, lay.total, lay.off[P_EMB], lay.size[P_EMB], w.clip_coef, adam_hyper(hp),
+                     ctx->sm_count);
+    return check_launch("cpg_clip_adam_step");
+}
+
+int cpg_wae_train_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* m, float* v, int V, int B,
+                       int L, const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
+                       float* scalars, float* mu, float* logvar, float* z, float* logits) {
+    if (!ctx || !hp) { set_error("cpg_wae_train_step: null argument"); return CPG_EINVAL; }
+    cpg_train_hparams h = *hp;
+    h.global_batch = B;
+    int rc = ensure_workspace(ctx, B, L, V, h.rf_dim, (cudaStream_t)stream);
+    if (rc) return rc;
+    float* cpl = ctx->ws.coupled;
+    if ((rc = cpg_wae_step_phase1(ctx, stream, params, V, B, L, in, nz, &h, cpl, mu, logvar, z))) return rc;
+    if ((rc = cpg_wae_step_phase2(ctx, stream, params, grads, V, B, L, in, nz, &h, cpl, scalars, logits))) return rc;
+    float* gn = scalars ? scalars + SC_GRAD_NORM : nullptr;
+    return cpg_clip_adam_step(ctx, stream, params, grads, m, v, V, &h, gn);
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+// Context + workspace of the C ABI (internal).
+#pragma once
+#include <string>
+#include "kernels.h"
+#include "dec_out.h"
+#include "latent.h"
+#include "wgrad.h"
+#include "adam.h"
+#include "../../include/cpg_b200.h"
+
+namespace cpg {
+
+struct Workspace {
+    // geometry this layout was made for
+    int B = 0, L = 0, V = 0, R = 0;
+    Derived d;
+    uint8_t *tok, *tokd, *tgt;
+    float *enc_hs[2], *enc_gates[2], *enc_dg[2];
+    float *hfin, *mu, *logvar, *z, *zc, *rowbias;
+    float *dec_hs, *dec_gates, *dec_dg, *dec_dh_out;
+    float *drow, *dh0, *dmu, *dlv, *dhfin;
+    float *rf_pre1, *rf_pre2, *rf_part, *rf_sum1, *rf_sum2, *rf_coef, *dz_rf;
+    float *lat_part, *lat_sums;
+    float *mmd_ws, *mmd_out, *mmdrf_out;
+    float *do_part_w, *do_part_b, *do_part_nll, *nll_sum;
+    float *wg_part, *dt_part, *dT_enc[2], *dT_dec, *dwizc;
+    float *gemm_ws, *colsum_ws;
+    float *norm_part, *clip_coef, *scalars, *ntok_f, *coupled;
+    int lat_nparts, rf_nchunk, gemm_splits;
+};
+
+}  // namespace cpg
+
+struct cpg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    void* base = nullptr;          // one device allocation
+    size_t capacity = 0;
+    int* ints = nullptr;           // [0] ntok (int), [1] sticky token-range error flag
+    cpg::Workspace ws;
+    bool have_stash = false;
+    int64_t launches = 0;
+};
+
+namespace cpg {
+void set_error(const std::string& msg);
+int ensure_workspace(cpg_ctx* ctx, int B, int L, int V, int R, cudaStream_t stream);
+}

@@ -1,0 +1,28 @@
+#pragma once
+#include "cpg_common.cuh"
+
+namespace cpg {
+
+struct DecOutArgs {
+    const float* hs;          // [B][L][104] decoder hidden states by step
+    const uint8_t* out_keep;  // [B][L][102] 1 = keep, or null (eval mode)
+    float keep_scale;         // 1 / (1 - p_out_dropout)
+    const float* fc_w;        // [VMAX][104] zero padded
+    const float* fc_b;        // [VMAX]
+    const uint8_t* tgt;       // [B][L]
+    const float* ntok;        // device scalar: global number of non-<pad> targets
+    const float* dlogits_in;  // [B][L][V] upstream gradient (module API) or null
+    float* logits_out;        // [B][L][V] or null
+    float* dh_out;            // [B][L][104] or null (forward only)
+    float* part_w;            // [parts][VMAX][104]
+    float* part_b;            // [parts][VMAX]
+    float* part_nll;          // [parts] or null
+    int fused_ce;             // compute CE + its gradient in place
+    int B, L, V;
+};
+
+int dec_out_parts(int B, int L, int sm_count);
+void launch_dec_out(cudaStream_t s, const DecOutArgs& a, int sm_count);
+void launch_dec_out_reduce(cudaStream_t s, const DecOutArgs& a, int sm_count, float* dW, float* db, float* nll_sum);
+
+}  // namespace cpg

@@ -1,0 +1,347 @@
+// Latent-space pieces of the WAE step: reparameterisation, KL / KL-shared-mu / L1
+// statistics and their gradients, the random-feature MMD (forward + backward) and
+// the full-kernel MMD (forward, log only).
+//
+// Reference: models/model.py:107-112 (sample_z), losses.py:8-15 (KL terms),
+// train_vae.py:33 (logvar L1), losses.py:59-93 (RF MMD), losses.py:47-56,96-108
+// (full-kernel MMD, including the `H - torch.diag(H)` row-broadcast quirk).
+#include "kernels.h"
+#include "latent.h"
+
+namespace cpg {
+
+// z = mu + exp(logvar/2) * eps ; zc = [z ; c ; 0 0] (decoder h0 and input tail)
+__global__ void k_reparam(const float* __restrict__ mu, const float* __restrict__ logvar,
+                          const float* __restrict__ eps, const float* __restrict__ c, int B,
+                          float* __restrict__ z, float* __restrict__ zc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * DEC_HP) return;
+    int b = i / DEC_HP, j = i % DEC_HP;
+    float v = 0.f;
+    if (j < ZD) {
+        float m = mu[b * ZD + j];
+        v = (eps != nullptr) ? m + expf(logvar[b * ZD + j] / 2) * eps[b * ZD + j] : m;
+        if (z != nullptr) z[b * ZD + j] = v;
+    } else if (j < DEC_H) {
+        v = c[b * CD + (j - ZD)];
+    }
+    zc[i] = v;
+}
+void launch_reparam(cudaStream_t s, const float* mu, const float* logvar, const float* eps, const float* c, int B,
+                    float* z, float* zc) {
+    CPG_LAUNCH(k_reparam, ceil_div(B * DEC_HP, 256), 256, 0, s, mu, logvar, eps, c, B, z, zc);
+}
+__global__ void k_make_zc(const float* __restrict__ z, const float* __restrict__ c, int B, float* __restrict__ zc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * DEC_HP) return;
+    int b = i / DEC_HP, j = i % DEC_HP;
+    zc[i] = (j < ZD) ? z[b * ZD + j] : (j < DEC_H ? c[b * CD + (j - ZD)] : 0.f);
+}
+void launch_make_zc(cudaStream_t s, const float* z, const float* c, int B, float* zc) {
+    CPG_LAUNCH(k_make_zc, ceil_div(B * DEC_HP, 256), 256, 0, s, z, c, B, zc);
+}
+
+// Per-row reductions over the 100 latent dims with warp shuffles; one warp per row,
+// per-CTA partials (no float atomics), ordered final sum.
+//   part[cta][0..4] = sum_b { 1/2 sum(e^lv + mu^2 - 1 - lv), 1/2 sum(e^lv - 1 - lv), sum|lv|, sum|mu|, sum lv }
+constexpr int LS_WARPS = 8;
+__global__ void __launch_bounds__(LS_WARPS * 32)
+k_latent_stats(const float* __restrict__ mu, const float* __restrict__ logvar, int B, float* __restrict__ part) {
+    __shared__ float red[LS_WARPS][5];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int b = blockIdx.x * LS_WARPS + warp; b < B; b += gridDim.x * LS_WARPS) {
+        float r[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int j = lane; j < ZD; j += 32) {
+            float m = mu[b * ZD + j], lv = logvar[b * ZD + j];
+            float e = expf(lv);
+            r[0] += e + m * m - 1.0f - lv;
+            r[1] += e - 1.0f - lv;
+            r[2] += fabsf(lv);
+            r[3] += fabsf(m);
+            r[4] += lv;
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) r[q] = warp_sum(r[q]);
+        a[0] += 0.5f * r[0]; a[1] += 0.5f * r[1]; a[2] += r[2]; a[3] += r[3]; a[4] += r[4];
+    }
+    if (lane == 0)
+        for (int q = 0; q < 5; ++q) red[warp][q] = a[q];
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        float s = 0.f;
+        for (int w = 0; w < LS_WARPS; ++w) s += red[w][threadIdx.x];
+        part[blockIdx.x * 5 + threadIdx.x] = s;
+    }
+}
+__global__ void k_latent_stats_final(const float* __restrict__ part, int nparts, float* __restrict__ sums) {
+    int q = threadIdx.x;
+    if (q >= 5) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += (double)part[p * 5 + q];
+    sums[q] = (float)s;
+}
+void launch_latent_stats(cudaStream_t s, const float* mu, const float* logvar, int B, float* part, int nparts,
+                         float* sums5) {
+    nparts = max(1, min(nparts, ceil_div(B, LS_WARPS)));
+    CPG_LAUNCH(k_latent_stats, nparts, LS_WARPS * 32, 0, s, mu, logvar, B, part);
+    CPG_LAUNCH(k_latent_stats_final, 1, 32, 0, s, part, nparts, sums5);
+}
+
+// Gradient wrt (mu, logvar) of  beta*[kl] + l_l1*L1 + l_kl*KLsharedmu  plus the chain through
+// z = mu + exp(lv/2) eps of the gradient arriving at z (decoder h0/input path + RF-MMD + external).
+__global__ void k_latent_bwd(LatentBwdArgs a) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.B * ZD) return;
+    int b = i / ZD, j = i % ZD;
+    float dz = 0.f;
+    if (a.dzc != nullptr) dz += a.dzc[b * DEC_HP + j];
+    if (a.dz_rf != nullptr) dz += a.dz_rf[i];
+    if (a.dz_ext != nullptr) dz += a.dz_ext[i];
+    const float m = a.mu[i], lv = a.logvar[i];
+    const float e = expf(lv);
+    const float invB = 1.0f / (float)a.B_global;
+    float dmu = dz + a.w_kl * m * invB;
+    float dlv = (a.w_kl + a.w_klsm) * 0.5f * (e - 1.0f) * invB;
+    dlv += a.w_l1 * (lv > 0.f ? 1.f : (lv < 0.f ? -1.f : 0.f)) * invB;
+    if (a.eps != nullptr) dlv += dz * a.eps[i] * 0.5f * expf(lv / 2);
+    if (a.dmu_ext != nullptr) dmu += a.dmu_ext[i];
+    if (a.dlv_ext != nullptr) dlv += a.dlv_ext[i];
+    a.dmu[i] = dmu;
+    a.dlv[i] = dlv;
+}
+void launch_latent_bwd(cudaStream_t s, const LatentBwdArgs& a) {
+    CPG_LAUNCH(k_latent_bwd, ceil_div(a.B * ZD, 256), 256, 0, s, a);
+}
+
+// ---- random-feature MMD.  pre = z @ rf_w (raw GEMM); phi = cos(pre / sigma + b) * sqrt(2/R)
+__global__ void k_rf_colsum_partial(const float* __restrict__ pre, const float* __restrict__ rf_b, int B, int R,
+                                    float sigma, int rows_per_chunk, float* __restrict__ part) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = blockIdx.y;
+    if (r >= R) return;
+    const float scale = sqrtf(2.0f / (float)R);
+    const float bb = rf_b[r];
+    int b0 = c * rows_per_chunk, b1 = min(B, b0 + rows_per_chunk);
+    float s = 0.f;
+    for (int b = b0; b < b1; ++b) s += cosf(pre[(size_t)b * R + r] / sigma + bb) * scale;
+    part[(size_t)c * R + r] = s;
+}
+__global__ void k_rf_colsum_final(const float* __restrict__ part, int nchunk, int R, float* __restrict__ out) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float s = 0.f;
+    for (int c = 0; c < nchunk; ++c) s += part[(size_t)c * R + r];
+    out[r] = s;
+}
+void launch_rf_colsum(cudaStream_t s, const float* pre, const float* rf_b, int B, int R, float sigma, float* part,
+                      int nchunk, float* out) {
+    nchunk = max(1, min(nchunk, B));
+    int rpc = ceil_div(B, nchunk);
+    nchunk = ceil_div(B, rpc);
+    CPG_LAUNCH(k_rf_colsum_partial, dim3(ceil_div(R, 128), nchunk), 128, 0, s, pre, rf_b, B, R, sigma, rpc, part);
+    CPG_LAUNCH(k_rf_colsum_final, ceil_div(R, 128), 128, 0, s, part, nchunk, R, out);
+}
+
+// loss = sum_r (mean1 - mean2)^2 from the GLOBAL feature sums; also
+// coef[r] = w * 2 (mean1 - mean2) * sqrt(2/R) / (B_global * sigma) for the backward pass.
+__global__ void k_rf_loss(const float* __restrict__ sum1, const float* __restrict__ sum2, int R, int B_global,
+                          float sigma, float w, float* __restrict__ coef, float* __restrict__ loss_out) {
+    __shared__ float red[32];
+    const float invB = 1.0f / (float)B_global;
+    const float scale = sqrtf(2.0f / (float)R);
+    float acc = 0.f;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        float d = sum1[r] * invB - sum2[r] * invB;
+        acc += d * d;
+        if (coef != nullptr) coef[r] = w * 2.0f * d * scale * invB / sigma;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        *loss_out = s;
+    }
+}
+void launch_rf_loss(cudaStream_t s, const float* sum1, const float* sum2, int R, int B_global, float sigma, float w,
+                    float* coef, float* loss_out) {
+    CPG_LAUNCH(k_rf_loss, 1, 256, 0, s, sum1, sum2, R, B_global, sigma, w, coef, loss_out);
+}
+// G[b][r] = coef[r] * (-sin(pre/sigma + b)) in place; then dz = G @ rf_w^T (gemm)
+__global__ void k_rf_grad_prep(float* __restrict__ pre, const float* __restrict__ rf_b,
+                               const float* __restrict__ coef, int B, int R, float sigma) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * R) return;
+    int r = (int)(i % R);
+    pre[i] = -coef[r] * sinf(pre[i] / sigma + rf_b[r]);
+}
+void launch_rf_grad_prep(cudaStream_t s, float* pre, const float* rf_b, const float* coef, int B, int R, float sigma) {
+    CPG_LAUNCH(k_rf_grad_prep, (unsigned)(((size_t)B * R + 255) / 256), 256, 0, s, pre, rf_b, coef, B, R, sigma);
+}
+
+// ---- full-kernel MMD, SIMT version.  X = [z ; z_prior] (2N rows).  With s_i = +1 for z rows and
+// -1 for prior rows,  sum(H) = sum_{i,j} s_i s_j K(x_i, x_j);  the reference then evaluates
+// (sum(H) - N * sum_j H_jj) / (N (N-1)),  H_jj = 2 - 2 K(z_j, zp_j).
+__global__ void k_mmd_rownorm(const float* __restrict__ z, const float* __restrict__ zp, int N, float sigma,
+                              float* __restrict__ norms, float* __restrict__ diag_part) {
+    __shared__ float red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float dacc = 0.f;
+    for (int b = blockIdx.x * 8 + warp; b < N; b += gridDim.x * 8) {
+        float n1 = 0.f, n2 = 0.f, dd = 0.f;
+        for (int j = lane; j < ZD; j += 32) {
+            float a = z[b * ZD + j], c = zp[b * ZD + j];
+            n1 += a * a; n2 += c * c; dd += (a - c) * (a - c);
+        }
+        n1 = warp_sum(n1); n2 = warp_sum(n2); dd = warp_sum(dd);
+        if (lane == 0) { norms[b] = n1; norms[N + b] = n2; dacc += expf(-dd / (sigma * sigma)); }
+    }
+    if (lane == 0) red[warp] = dacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        diag_part[blockIdx.x] = s;
+    }
+}
+
+constexpr int MT = 64, MK = 50;
+__global__ void __launch_bounds__(256)
+k_mmd_gram(const float* __restrict__ z, const float* __restrict__ zp, const float* __restrict__ norms, int N,
+           float sigma, float* __restrict__ part) {
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    const int pidx = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tj < ti) { if (threadIdx.x == 0) part[pidx] = 0.f; return; }
+    __shared__ __align__(16) float Xi[MK][MT + 4];
+    __shared__ __align__(16) float Xj[MK][MT + 4];
+    __shared__ float red[8];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int M2 = 2 * N;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < ZD; k0 += MK) {
+        for (int idx = tid; idx < MT * MK; idx += 256) {
+            int k = idx % MK, r = idx / MK;
+            int gi = ti * MT + r, gj = tj * MT + r;
+            float vi = 0.f, vj = 0.f;
+            if (gi < M2) vi = (gi < N) ? z[(size_t)gi * ZD + k0 + k] : zp[(size_t)(gi - N) * ZD + k0 + k];
+            if (gj < M2) vj = (gj < N) ? z[(size_t)gj * ZD + k0 + k] : zp[(size_t)(gj - N) * ZD + k0 + k];
+            Xi[k][r] = vi;
+            Xj[k][r] = vj;
+        }
+        __syncthreads();
+#pragma unroll 10
+        for (int k = 0; k < MK; ++k) {
+            const float4 av = ld4(&Xi[k][ty * 4]);
+            const float4 bv = ld4(&Xj[k][tx * 4]);
+            const float a4[4] = {av.x, av.y, av.z, av.w};
+            const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    const float inv_s2 = 1.0f / (sigma * sigma);
+    float tsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int gi = ti * MT + ty * 4 + i;
+        if (gi >= M2) continue;
+        float ni = norms[gi];
+        float si = gi < N ? 1.f : -1.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int gj = tj * MT + tx * 4 + j;
+            if (gj >= M2) continue;
+            if (ti == tj && gj < gi) continue;              // upper triangle only
+            float d2 = fmaxf(ni + norms[gj] - 2.0f * acc[i][j], 0.f);
+            if (gi == gj) d2 = 0.f;
+            float kv = expf(-d2 * inv_s2);
+            float sj = gj < N ? 1.f : -1.f;
+            float wgt = (gi == gj) ? 1.f : 2.f;             // symmetric counterpart
+            tsum += wgt * si * sj * kv;
+        }
+    }
+    tsum = warp_sum(tsum);
+    if ((tid & 31) == 0) red[tid >> 5] = tsum;
+    __syncthreads();
+    if (tid == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        part[pidx] = s;
+    }
+}
+__global__ void k_mmd_final(const float* __restrict__ part, int nparts, const float* __restrict__ diag_part,
+                            int ndiag, int N, float* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += (double)part[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double hs = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) hs += red[i];
+        double k12d = 0.0;
+        for (int i = 0; i < ndiag; ++i) k12d += (double)diag_part[i];
+        double hdiag = 2.0 * N - 2.0 * k12d;
+        *out = (float)((hs - (double)N * hdiag) / ((double)N * (double)(N - 1)));
+    }
+}
+size_t mmd_full_ws_floats(int N) {
+    int nt = ceil_div(2 * N, MT);
+    return (size_t)2 * N + (size_t)nt * nt + 256 + 64;
+}
+void launch_mmd_full_simt(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float* ws, float* out) {
+    int nt = ceil_div(2 * N, MT);
+    float* norms = ws;
+    float* diag_part = ws + 2 * N;
+    float* part = diag_part + 256;
+    int ndiag = max(1, min(256, ceil_div(N, 8)));
+    CPG_LAUNCH(k_mmd_rownorm, ndiag, 256, 0, s, z, zp, N, sigma, norms, diag_part);
+    CPG_LAUNCH(k_mmd_gram, dim3(nt, nt), 256, 0, s, z, zp, norms, N, sigma, part);
+    CPG_LAUNCH(k_mmd_final, 1, 256, 0, s, part, nt * nt, diag_part, ndiag, N, out);
+}
+
+// total loss and logging scalars (train_vae.py:31-37,44-53) from the reduced sums (single-rank view)
+__global__ void k_compose_scalars(ComposeArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float invB = 1.0f / (float)a.B_global;
+    float ntok = *a.ntok;
+    float recon = ntok > 0.f ? *a.nll_sum / ntok : 0.f;
+    float kl = a.lat_sums[0] * invB, klsm = a.lat_sums[1] * invB, l1 = a.lat_sums[2] * invB;
+    float mmd = a.mmd != nullptr ? *a.mmd : 0.f;
+    float mmdrf = *a.mmdrf;
+    float regu = a.z_regu == 0 ? kl : (a.z_regu == 1 ? mmd : mmdrf);
+    float* o = a.out;
+    o[SC_LOSS] = recon + a.beta * regu + a.lambda_l1 * l1 + a.lambda_kl * klsm;
+    o[SC_RECON] = recon;
+    o[SC_KL] = kl;
+    o[SC_MMD] = mmd;
+    o[SC_MMDRF] = mmdrf;
+    o[SC_LOGVAR_L1] = l1;
+    o[SC_LOGVAR_KL] = klsm;
+    o[SC_Z_MU_L1] = a.lat_sums[3] * invB / (float)ZD;
+    o[SC_Z_LOGVAR] = a.lat_sums[4] * invB / (float)ZD;
+    o[SC_BETA] = a.beta;
+    o[SC_NTOK] = ntok;
+    o[SC_NLL_SUM] = *a.nll_sum;
+}
+void launch_compose_scalars(cudaStream_t s, const ComposeArgs& a) { CPG_LAUNCH(k_compose_scalars, 1, 32, 0, s, a); }
+
+__global__ void k_int_to_float(const int* __restrict__ src, float* __restrict__ dst, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
+}
+void launch_int_to_float(cudaStream_t s, const int* src, float* dst, int n) {
+    CPG_LAUNCH(k_int_to_float, ceil_div(n, 32), 32, 0, s, src, dst, n);
+}
+
+}  // namespace cpg

@@ -1,0 +1,49 @@
+#pragma once
+#include "cpg_common.cuh"
+
+namespace cpg {
+
+// slots of the per-step scalar block (matches CPG_SC_* in include/cpg_b200.h)
+enum ScalarSlot {
+    SC_LOSS = 0, SC_RECON, SC_KL, SC_MMD, SC_MMDRF, SC_LOGVAR_L1, SC_LOGVAR_KL, SC_Z_MU_L1, SC_Z_LOGVAR,
+    SC_BETA, SC_GRAD_NORM, SC_NTOK, SC_NLL_SUM, SC_COUNT = 16
+};
+
+struct LatentBwdArgs {
+    const float* mu; const float* logvar; const float* eps;   // eps null: z = mu
+    const float* dzc;       // [B][104] gradient at [z;c] from the decoder, or null
+    const float* dz_rf;     // [B][100] RF-MMD gradient (already weighted), or null
+    const float* dz_ext;    // [B][100] external upstream gradient at z, or null
+    const float* dmu_ext;   // external upstream gradients at mu / logvar, or null
+    const float* dlv_ext;
+    float w_kl;             // beta if z_regu == kl else 0
+    float w_klsm;           // lambda_logvar_KL
+    float w_l1;             // lambda_logvar_L1
+    int B, B_global;
+    float* dmu; float* dlv; // [B][100] out
+};
+
+struct ComposeArgs {
+    const float* ntok; const float* nll_sum; const float* lat_sums; const float* mmd; const float* mmdrf;
+    float beta, lambda_l1, lambda_kl;
+    int z_regu, B_global;
+    float* out;
+};
+
+void launch_reparam(cudaStream_t s, const float* mu, const float* logvar, const float* eps, const float* c, int B,
+                    float* z, float* zc);
+void launch_make_zc(cudaStream_t s, const float* z, const float* c, int B, float* zc);
+void launch_latent_stats(cudaStream_t s, const float* mu, const float* logvar, int B, float* part, int nparts,
+                         float* sums5);
+void launch_latent_bwd(cudaStream_t s, const LatentBwdArgs& a);
+void launch_rf_colsum(cudaStream_t s, const float* pre, const float* rf_b, int B, int R, float sigma, float* part,
+                      int nchunk, float* out);
+void launch_rf_loss(cudaStream_t s, const float* sum1, const float* sum2, int R, int B_global, float sigma, float w,
+                    float* coef, float* loss_out);
+void launch_rf_grad_prep(cudaStream_t s, float* pre, const float* rf_b, const float* coef, int B, int R, float sigma);
+size_t mmd_full_ws_floats(int N);
+void launch_mmd_full_simt(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float* ws, float* out);
+void launch_compose_scalars(cudaStream_t s, const ComposeArgs& a);
+void launch_int_to_float(cudaStream_t s, const int* src, float* dst, int n);
+
+}  // namespace cpg

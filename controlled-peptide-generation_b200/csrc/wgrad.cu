@@ -1,0 +1,211 @@
+// Weight gradients of the three GRUs from the (dr_pre, dz_pre, dn_pre, dhn) planes the BPTT
+// kernels write (gru.cu):
+//   dW_hh = sum_{b,s} [dr_pre, dz_pre, dhn]^T h_{s-1}       (contraction over B*L rows, split-K)
+//   dT[v] = sum_{(b,s): token == v} [dr_pre, dz_pre, dn_pre, dhn]   (token-table gradient)
+//   dW_ih[:, :150] = dT^T E,  dE = dT W_ih[:, :150],  db_ih = sum_v dT,  db_hh = (same r,z ; dhn for n)
+// which is what autograd produces for nn.GRU + nn.Embedding in the reference
+// (train_vae.py:40 loss.backward()), restructured around the token table.
+#include "kernels.h"
+#include "wgrad.h"
+
+namespace cpg {
+
+constexpr int WG_ROWS = 16;
+
+template <int HP>
+__global__ void __launch_bounds__((HP / 4) * (HP / 8))
+k_wgrad_hh(const float* __restrict__ dg, const float* __restrict__ hs, const float* __restrict__ h0, int B, int L,
+           int rows_per_split, float* __restrict__ part) {
+    constexpr int NG = HP / 4, NK = HP / 8, NT = NG * NK;
+    __shared__ __align__(16) float As[WG_ROWS][HP];
+    __shared__ __align__(16) float Hs[WG_ROWS][HP];
+    const int pl = blockIdx.x;                 // 0: r, 1: z, 2: n (uses the dhn plane)
+    const int src_plane = pl == 2 ? 3 : pl;
+    const int split = blockIdx.y;
+    const int tid = threadIdx.x, gx = tid % NG, kx = tid / NG;
+    const int nrows = B * L;
+    const int rbeg = split * rows_per_split, rend = min(nrows, rbeg + rows_per_split);
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    for (int r0 = rbeg; r0 < rend; r0 += WG_ROWS) {
+        for (int idx = tid; idx < WG_ROWS * (HP / 4); idx += NT) {
+            int rr = idx / (HP / 4), c4 = (idx % (HP / 4)) * 4;
+            int row = r0 + rr;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), h = a;
+            if (row < rend) {
+                a = ld4(dg + ((size_t)row * 4 + src_plane) * HP + c4);
+                int b = row / L, s = row % L;
+                if (s > 0) h = ld4(hs + (size_t)(row - 1) * HP + c4);
+                else if (h0 != nullptr) h = ld4(h0 + (size_t)b * HP + c4);
+            }
+            st4(&As[rr][c4], a);
+            st4(&Hs[rr][c4], h);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int rr = 0; rr < WG_ROWS; ++rr) {
+            const float4 av = ld4(&As[rr][gx * 4]);
+            const float4 h0v = ld4(&Hs[rr][kx * 8]);
+            const float4 h1v = ld4(&Hs[rr][kx * 8 + 4]);
+            const float a4[4] = {av.x, av.y, av.z, av.w};
+            const float h8[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a4[i], h8[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* out = part + ((size_t)split * 3 * HP + pl * HP) * HP;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float* o = out + (size_t)(gx * 4 + i) * HP + kx * 8;
+        st4(o, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+        st4(o + 4, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+    }
+}
+
+// dW_hh [3H][H] (unpadded) = ordered sum of the split partials [split][3HP][HP]
+__global__ void k_wgrad_hh_reduce(const float* __restrict__ part, int nsplit, int HP, int H, float* __restrict__ dW) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * H * H) return;
+    int g = i / H, k = i % H, pl = g / H, j = g % H;
+    float s = 0.f;
+    for (int p = 0; p < nsplit; ++p) s += part[((size_t)p * 3 * HP + pl * HP + j) * HP + k];
+    dW[i] = s;
+}
+
+int wgrad_splits(int B, int L, int sm_count) {
+    int nrows = B * L;
+    int want = max(1, sm_count / 3);
+    int rps = ceil_div(ceil_div(nrows, want), WG_ROWS) * WG_ROWS;
+    return ceil_div(nrows, rps);
+}
+
+void launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0, int B, int L,
+                     int sm_count, float* part, float* dW) {
+    int nrows = B * L;
+    int want = max(1, sm_count / 3);
+    int rps = ceil_div(ceil_div(nrows, want), WG_ROWS) * WG_ROWS;
+    int nsplit = ceil_div(nrows, rps);
+    if (HP == ENC_H) {
+        CPG_LAUNCH(k_wgrad_hh<ENC_H>, dim3(3, nsplit), (ENC_H / 4) * (ENC_H / 8), 0, s, dg, hs, h0, B, L, rps, part);
+    } else {
+        CPG_LAUNCH(k_wgrad_hh<DEC_HP>, dim3(3, nsplit), (DEC_HP / 4) * (DEC_HP / 8), 0, s, dg, hs, h0, B, L, rps, part);
+    }
+    CPG_LAUNCH(k_wgrad_hh_reduce, ceil_div(3 * H * H, 256), 256, 0, s, part, nsplit, HP, H, dW);
+}
+
+// token-table gradient: thread c owns column c of the 4*HP planes; accumulators [V][4HP] in smem
+__global__ void k_dtable(const float* __restrict__ dg, const uint8_t* __restrict__ tok, int B, int L, int reverse,
+                         int HP4, int V, int rows_per_split, float* __restrict__ part) {
+    CPG_DYN_SMEM(float, acc);                 // [V][HP4]
+    const int c = threadIdx.x;
+    for (int v = 0; v < V; ++v) acc[v * HP4 + c] = 0.f;
+    const int nrows = B * L;
+    const int rbeg = blockIdx.x * rows_per_split, rend = min(nrows, rbeg + rows_per_split);
+    for (int row = rbeg; row < rend; ++row) {
+        int b = row / L, s = row % L;
+        int t = reverse ? (L - 1 - s) : s;
+        int tk = tok[b * L + t];
+        acc[tk * HP4 + c] += dg[(size_t)row * HP4 + c];
+    }
+    float* out = part + (size_t)blockIdx.x * V * HP4;
+    for (int v = 0; v < V; ++v) out[v * HP4 + c] = acc[v * HP4 + c];
+}
+__global__ void k_dtable_reduce(const float* __restrict__ part, int nsplit, int n, float* __restrict__ dT) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.f;
+    for (int p = 0; p < nsplit; ++p) s += part[(size_t)p * n + i];
+    dT[i] = s;
+}
+int dtable_splits(int B, int L, int sm_count) { return max(1, min(B * L, 2 * sm_count)); }
+void launch_dtable(cudaStream_t s, int HP, const float* dg, const uint8_t* tok, int B, int L, int reverse, int V,
+                   int sm_count, float* part, float* dT) {
+    int nrows = B * L;
+    int nsplit = dtable_splits(B, L, sm_count);
+    int rps = ceil_div(nrows, nsplit);
+    nsplit = ceil_div(nrows, rps);
+    int HP4 = 4 * HP;
+    size_t smem = (size_t)V * HP4 * sizeof(float);
+    CPG_SET_MAX_SMEM(k_dtable, smem);
+    CPG_LAUNCH(k_dtable, nsplit, HP4, smem, s, dg, tok, B, L, reverse, HP4, V, rps, part);
+    CPG_LAUNCH(k_dtable_reduce, ceil_div(V * HP4, 256), 256, 0, s, part, nsplit, V * HP4, dT);
+}
+
+// input-side parameter gradients from the three table gradients
+__global__ void k_input_grads(InputGradArgs a) {
+    const int task = blockIdx.y;
+    const int stride = gridDim.x * blockDim.x;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int V = a.V;
+    if (task < 2) {                         // encoder dW_ih [240][150], db_ih, db_hh
+        const int d = task, H = ENC_H, G = 3 * H, HP4 = 4 * H;
+        const float* dT = a.dT_enc[d];
+        for (int i = t0; i < G * EMB; i += stride) {
+            int g = i / EMB, e = i % EMB;
+            float s = 0.f;
+            for (int v = 0; v < V; ++v) s = fmaf(dT[v * HP4 + g], a.emb[v * EMB + e], s);
+            a.g_enc_wih[d][i] = s;
+        }
+        for (int g = t0; g < G; g += stride) {
+            float si = 0.f, sh = 0.f;
+            for (int v = 0; v < V; ++v) {
+                si += dT[v * HP4 + g];
+                sh += (g < 2 * H) ? dT[v * HP4 + g] : dT[v * HP4 + 3 * H + (g - 2 * H)];
+            }
+            a.g_enc_bih[d][g] = si;
+            a.g_enc_bhh[d][g] = sh;
+        }
+    } else if (task == 2) {                 // decoder dW_ih [306][252] (embedding cols from dT, zc cols from dwizc)
+        const int H = DEC_H, HP = DEC_HP, G = 3 * H, HP4 = 4 * HP;
+        const float* dT = a.dT_dec;
+        for (int i = t0; i < G * DEC_IN; i += stride) {
+            int g = i / DEC_IN, e = i % DEC_IN, gate = g / H, j = g % H;
+            float s = 0.f;
+            if (e < EMB) {
+                for (int v = 0; v < V; ++v) s = fmaf(dT[v * HP4 + gate * HP + j], a.emb[v * EMB + e], s);
+            } else {
+                s = a.dwizc[(size_t)(gate * HP + j) * HP + (e - EMB)];
+            }
+            a.g_dec_wih[i] = s;
+        }
+        for (int g = t0; g < G; g += stride) {
+            int gate = g / H, j = g % H;
+            float si = 0.f, sh = 0.f;
+            for (int v = 0; v < V; ++v) {
+                si += dT[v * HP4 + gate * HP + j];
+                sh += dT[v * HP4 + (gate < 2 ? gate : 3) * HP + j];
+            }
+            a.g_dec_bih[g] = si;
+            a.g_dec_bhh[g] = sh;
+        }
+    } else {                                // embedding gradient [V][150]; <pad> row stays 0 (model.py:47)
+        for (int i = t0; i < V * EMB; i += stride) {
+            int v = i / EMB, e = i % EMB;
+            float s = 0.f;
+            if (v != PAD) {
+                for (int d = 0; d < 2; ++d) {
+                    const float* dT = a.dT_enc[d] + v * 4 * ENC_H;
+                    const float* w = a.enc_wih[d];
+                    for (int g = 0; g < 3 * ENC_H; ++g) s = fmaf(dT[g], w[g * EMB + e], s);
+                }
+                const float* dT = a.dT_dec + v * 4 * DEC_HP;
+                for (int gate = 0; gate < 3; ++gate)
+                    for (int j = 0; j < DEC_H; ++j)
+                        s = fmaf(dT[gate * DEC_HP + j], a.dec_wih[(size_t)(gate * DEC_H + j) * DEC_IN + e], s);
+            }
+            a.g_emb[i] = s;
+        }
+    }
+}
+void launch_input_grads(cudaStream_t s, const InputGradArgs& a) {
+    CPG_LAUNCH(k_input_grads, dim3(32, 4), 256, 0, s, a);
+}
+
+}  // namespace cpg

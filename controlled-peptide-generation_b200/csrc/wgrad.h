@@ -1,0 +1,27 @@
+#pragma once
+#include "cpg_common.cuh"
+
+namespace cpg {
+
+struct InputGradArgs {
+    const float* emb;               // [V][150]
+    const float* enc_wih[2];        // [240][150]
+    const float* dec_wih;           // [306][252]
+    const float* dT_enc[2];         // [V][4*80]
+    const float* dT_dec;            // [V][4*104]
+    const float* dwizc;             // [312][104] padded gradient of W_ih[:,150:]
+    float* g_emb;
+    float* g_enc_wih[2]; float* g_enc_bih[2]; float* g_enc_bhh[2];
+    float* g_dec_wih; float* g_dec_bih; float* g_dec_bhh;
+    int V;
+};
+
+int wgrad_splits(int B, int L, int sm_count);
+int dtable_splits(int B, int L, int sm_count);
+void launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0, int B, int L,
+                     int sm_count, float* part, float* dW);
+void launch_dtable(cudaStream_t s, int HP, const float* dg, const uint8_t* tok, int B, int L, int reverse, int V,
+                   int sm_count, float* part, float* dT);
+void launch_input_grads(cudaStream_t s, const InputGradArgs& a);
+
+}  // namespace cpg

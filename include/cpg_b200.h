@@ -1,0 +1,176 @@
+/* cpg_b200 -- C ABI of the B200-native (sm_100a) hot path of IBM/controlled-peptide-generation.
+ *
+ * The reference (pure Python on PyTorch / scikit-learn) has no FFI boundary of its own: its hot path
+ * is reached through the Python API of models/model.py, losses.py, train_vae.py, density_modeling.py
+ * and sample_pipeline.py.  This library sits UNDER that API: every entry point below replaces the
+ * vendor-library calls the cited reference lines make, and the Python package next to it
+ * (controlled-peptide-generation_b200/) keeps the reference's module / class / function names and
+ * binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless a parameter is documented as host.  The caller
+ *     (PyTorch) owns every buffer; the library owns only the per-context workspace.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls enqueue work and return; no hidden syncs
+ *     (workspace growth, which happens when a larger batch is seen first, synchronises once).
+ *   - Return value: 0 on success, negative CPG_E* code on failure; cpg_last_error() gives the text.
+ *   - Geometry is the reference configuration (cfg.py:258-281): emb 150, encoder bi-GRU h 80,
+ *     z 100, c 2, decoder GRU h 102; vocabulary n_vocab <= 32, sequence length <= 32.
+ *   - fp32 storage and arithmetic except where stated (fp64 for the GMM / score path).
+ */
+#ifndef CPG_B200_H
+#define CPG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPG_ABI_VERSION 1
+
+#define CPG_OK 0
+#define CPG_EINVAL (-1)   /* bad argument (shape, null pointer, unsupported geometry) */
+#define CPG_ECUDA (-2)    /* CUDA runtime error */
+#define CPG_ENOMEM (-3)   /* workspace allocation failed */
+#define CPG_ETOKEN (-4)   /* token id outside [0, n_vocab) seen by a previous call */
+
+typedef struct cpg_ctx cpg_ctx;
+typedef void* cpg_stream;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int cpg_abi_version(void);
+const char* cpg_last_error(void);
+int cpg_create(cpg_ctx** out, int device_ordinal);
+int cpg_destroy(cpg_ctx* ctx);
+int cpg_sm_count(const cpg_ctx* ctx);
+/* bytes currently held by the context's workspace */
+int64_t cpg_workspace_bytes(const cpg_ctx* ctx);
+/* number of kernel launches enqueued by this context since creation */
+int64_t cpg_launch_count(const cpg_ctx* ctx);
+/* device->host check of the sticky token-range flag (synchronises `stream`) */
+int cpg_check_errors(cpg_ctx* ctx, cpg_stream stream);
+
+/* ---- flat parameter layout ------------------------------------------------------------------
+ * The 19 unique tensors of RNN_VAE.vae_params() (models/model.py:88-94) live in ONE flat fp32
+ * buffer, each segment padded to a multiple of 4 floats, in this order:
+ *   word_emb.weight, encoder.rnn.{weight_ih,weight_hh,bias_ih,bias_hh}_l0, the same four with
+ *   _reverse, encoder.q_mu.{weight,bias}, encoder.q_logvar.{weight,bias},
+ *   decoder.rnn.{weight_ih,weight_hh,bias_ih,bias_hh}_l0, decoder.fc.1.{weight,bias}.
+ * Gradients and Adam moments use the same layout. */
+#define CPG_N_PARAM_TENSORS 19
+int64_t cpg_vae_param_count(int n_vocab);
+int cpg_vae_param_layout(int n_vocab, int64_t offsets[CPG_N_PARAM_TENSORS], int64_t sizes[CPG_N_PARAM_TENSORS]);
+
+/* ---- WAE forward / backward (module-level API) ----------------------------------------------
+ * Replaces RNN_VAE.forward (models/model.py:146-195): forward_encoder -> sample_z ->
+ * forward_decoder, i.e. nn.Embedding + bi-nn.GRU + 2 nn.Linear (models/encoder.py:38-52),
+ * the reparameterisation (model.py:107-112), WordDropout + nn.Embedding + nn.GRU + nn.Dropout +
+ * nn.Linear (models/decoder.py:56-84).  All randomness is an INPUT. */
+typedef struct {
+    const int64_t* tokens;     /* [B, L] int64, batch.text of the reference                       */
+    const float* eps;          /* [B, 100] N(0,1) noise of sample_z; NULL -> z = mu ("max")       */
+    const float* c;            /* [B, 2] code fed to the decoder (one-hot prior or softmax)       */
+    const uint8_t* word_drop;  /* [B, L] 1 = replace input token by <unk>; NULL = no word dropout */
+    const uint8_t* out_keep;   /* [B, L, 102] 1 = keep (nn.Dropout mask); NULL = eval mode        */
+    float p_out_dropout;       /* 0.3 in cfg.py:279; kept activations scale by 1/(1-p)            */
+} cpg_wae_inputs;
+
+/* mu, logvar, z: [B,100]; logits: [B,L,V] or NULL.  keep_for_backward != 0 stashes activations in
+ * the context for a following cpg_wae_backward on the same (B, L). */
+int cpg_wae_forward(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_vocab, int B, int L,
+                    const cpg_wae_inputs* in, float* mu, float* logvar, float* z, float* logits,
+                    int keep_for_backward);
+/* encoder only (sample_pipeline.py:49-70 / build_index.py:93-118 extraction): mu, logvar */
+int cpg_wae_encode(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_vocab, int B, int L,
+                   const int64_t* tokens, float* mu, float* logvar);
+/* Backward of the last cpg_wae_forward(keep_for_backward=1): upstream gradients (any may be NULL)
+ * -> flat parameter gradient (overwritten).  This is what loss.backward() (train_vae.py:40) does. */
+int cpg_wae_backward(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_vocab, int B, int L,
+                     const cpg_wae_inputs* in, const float* d_mu, const float* d_logvar, const float* d_z,
+                     const float* d_logits, float* grads);
+
+/* ---- fused training iteration (train_vae.py:24-42) ------------------------------------------ */
+#define CPG_ZREGU_KL 0
+#define CPG_ZREGU_MMD 1
+#define CPG_ZREGU_MMDRF 2
+typedef struct {
+    float lr, beta1, beta2, adam_eps;   /* optim.Adam(lr=cfg.vae.lr) defaults: 1e-3, .9, .999, 1e-8  */
+    float clip_norm;                    /* cfg.shared.clip_grad = 5.0                                 */
+    float beta;                         /* utils.anneal(cfg.vae.beta, it)                             */
+    float lambda_logvar_l1;             /* cfg.vae.lambda_logvar_L1                                   */
+    float lambda_logvar_kl;             /* cfg.vae.lambda_logvar_KL                                   */
+    int z_regu;                         /* CPG_ZREGU_* (cfg.vae.z_regu_loss)                          */
+    float mmd_sigma;                    /* cfg.losses.wae_mmd.sigma                                   */
+    int rf_dim;                         /* cfg.losses.wae_mmd.rf_dim                                  */
+    int compute_full_mmd;               /* the reference always evaluates it (train_vae.py:29)        */
+    int adam_step;                      /* 1-based iteration count (Adam's `step` of ordinary params) */
+    int global_batch;                   /* B summed over data-parallel ranks (= B on one GPU)         */
+} cpg_train_hparams;
+
+typedef struct {
+    const float* z_prior_full;  /* [B,100] randn_like(z) of the full-kernel MMD call (losses.py:37) */
+    const float* z_prior_rf;    /* [B,100] randn_like(z) of the RF MMD call                         */
+    const float* rf_w;          /* [100, R] cached random features (losses.py:75)                   */
+    const float* rf_b;          /* [R]      (losses.py:76)                                          */
+} cpg_loss_noise;
+
+/* slots of the scalar block written by the step (device float[CPG_SC_COUNT]) */
+#define CPG_SC_LOSS 0
+#define CPG_SC_RECON 1
+#define CPG_SC_KL 2
+#define CPG_SC_MMD 3
+#define CPG_SC_MMDRF 4
+#define CPG_SC_LOGVAR_L1 5
+#define CPG_SC_LOGVAR_KL 6
+#define CPG_SC_Z_MU_L1 7
+#define CPG_SC_Z_LOGVAR 8
+#define CPG_SC_BETA 9
+#define CPG_SC_GRAD_NORM 10
+#define CPG_SC_NTOK 11
+#define CPG_SC_NLL_SUM 12
+#define CPG_SC_COUNT 16
+
+/* One whole iteration on one GPU: forward, the five losses, backward, clip_grad_norm_, Adam.
+ * params / grads / adam_m / adam_v: flat buffers (cpg_vae_param_count floats), updated in place.
+ * scalars: device float[CPG_SC_COUNT].  mu/logvar/z/logits: optional outputs (may be NULL). */
+int cpg_wae_train_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* adam_m, float* adam_v,
+                       int n_vocab, int B, int L, const cpg_wae_inputs* in, const cpg_loss_noise* noise,
+                       const cpg_train_hparams* hp, float* scalars, float* mu, float* logvar, float* z,
+                       float* logits);
+
+/* The same iteration split at its data-parallel exchange points:
+ *   phase1: forward through the decoder GRU + local loss statistics.  Writes `coupled`
+ *           (device float[cpg_coupled_count(rf_dim)]) = [n_tok, nll placeholder, 5 latent sums,
+ *           RF feature sums of z (R), of z_prior (R)] -- the caller all-reduces (sums) it.
+ *   phase2: CE fwd/bwd with the GLOBAL token count, BPTT, weight gradients -> grads (local sum
+ *           contribution; the caller all-reduces grads), scalars from the reduced statistics.
+ *   cpg_clip_adam_step: global-norm clip + Adam with the duplicated-embedding semantics. */
+int64_t cpg_coupled_count(int rf_dim);
+int cpg_wae_step_phase1(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_vocab, int B, int L,
+                        const cpg_wae_inputs* in, const cpg_loss_noise* noise, const cpg_train_hparams* hp,
+                        float* coupled, float* mu, float* logvar, float* z);
+int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, float* grads, int n_vocab, int B, int L,
+                        const cpg_wae_inputs* in, const cpg_loss_noise* noise, const cpg_train_hparams* hp,
+                        const float* coupled, float* scalars, float* logits);
+int cpg_clip_adam_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* adam_m, float* adam_v,
+                       int n_vocab, const cpg_train_hparams* hp, float* grad_norm_out);
+
+/* ---- individual losses (losses.py) ---------------------------------------------------------- */
+/* recon_dec (losses.py:18-31): mean NLL over non-<pad> next-token targets; optional d_logits.
+ * loss_out: device float[2] = {mean nll, n_tok}. */
+int cpg_softmax_xent(cpg_ctx* ctx, cpg_stream stream, const float* logits, const int64_t* tokens, int B, int L,
+                     int n_vocab, float* loss_out, float* d_logits);
+/* kl_gaussianprior, kl_gaussian_sharedmu (losses.py:8-15), logvar L1 (train_vae.py:33),
+ * mean|mu|, mean logvar -> device float[5] */
+int cpg_latent_stats(cpg_ctx* ctx, cpg_stream stream, const float* mu, const float* logvar, int B, float* out5);
+/* mmd_full_kernel (losses.py:47-56,96-108), gaussian kernel, as executed by the reference */
+int cpg_mmd_full(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* z_prior, int B, float sigma,
+                 float* loss_out);
+/* mmd_rf (losses.py:59-93); dz may be NULL; dz = d loss / d z */
+int cpg_mmd_rf(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* z_prior, const float* rf_w,
+               const float* rf_b, int B, int rf_dim, float sigma, float* loss_out, float* dz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPG_B200_H */

@@ -1,0 +1,207 @@
+"""GPU parity of the WAE path (C ABI -> sm_100a kernels) against the oracle and the
+golden fixtures of the live reference.  Tolerances from BASELINE.json: losses and logits
+within 1e-4 relative (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from helpers import (assert_params_close, clipped, dev_noise, digest, rel_err)
+from oracle import wae as ow
+
+pytestmark = pytest.mark.gpu
+V = 24
+LOG_TO_SC = dict(zip(
+    ['train_z_mu_L1', 'train_z_logvar', 'train_z_logvar_L1', 'train_z_logvar_KL_penalty', 'train_L_vae',
+     'train_L_vae_recon', 'train_L_vae_kl', 'train_L_wae_mmd', 'train_L_wae_mmdrf', 'train_beta'],
+    ['z_mu_l1', 'z_logvar', 'logvar_l1', 'logvar_kl', 'loss', 'recon', 'kl', 'mmd', 'mmdrf', 'beta']))
+
+
+@pytest.fixture(scope='module')
+def eng():
+    from cpg_b200 import engine
+    return engine
+
+
+def _params(name='params_init_v24.npz'):
+    fx = load_golden(name)
+    return {k: torch.from_numpy(fx[k].copy()) for k in fx.files}
+
+
+@pytest.mark.parametrize('batch', [1, 7, 32, 33, 100])
+def test_forward_matches_oracle(eng, batch):
+    dev = torch.device('cuda')
+    p = ow.random_params(V, seed=3)
+    tokens = ow.synthetic_tokens(batch, V, seed=5)
+    noise = ow.draw_noise(batch, seed=9)
+    st = eng.FlatState(V, dev)
+    st.load(p)
+    nz = dev_noise(noise, dev)
+    mu, lv, z, logits = eng.wae_forward(st.params, V, tokens.to(dev), nz['eps'], nz['c'], nz['word_drop'],
+                                        nz['out_keep'], 0.3)
+    omu, olv = ow.encoder_forward(p, tokens)
+    oz = ow.reparameterize(omu, olv, noise['eps'])
+    ol = ow.decoder_forward(p, ow.word_dropout(tokens, noise['word_drop']), oz, noise['c'], noise['out_keep'], 0.3)
+    for name, a, b in (('mu', mu, omu), ('logvar', lv, olv), ('z', z, oz), ('logits', logits, ol)):
+        np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=1e-4, atol=2e-6, err_msg=name)
+
+
+def test_inference_forward_matches_reference_golden(eng):
+    dev = torch.device('cuda')
+    fx = load_golden('infer_b48.npz')
+    st = eng.FlatState(V, dev)
+    st.load(_params())
+    tokens = torch.from_numpy(fx['tokens']).to(dev)
+    mu, lv = eng.wae_encode(st.params, V, tokens)
+    np.testing.assert_allclose(mu.cpu().numpy(), fx['mu'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(lv.cpu().numpy(), fx['logvar'], rtol=1e-4, atol=1e-6)
+    # decoder in eval mode with c from the golden (softmax of the CNN classifier), z = mu
+    c = torch.from_numpy(fx['c']).to(dev)
+    _, _, z, logits = eng.wae_forward(st.params, V, tokens, None, c, None, None, 0.3)
+    np.testing.assert_allclose(z.cpu().numpy(), fx['mu'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(logits.cpu().numpy(), fx['dec_logits'], rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize('batch', [5, 32])
+def test_train_iterations_match_reference_golden(eng, batch):
+    """Three consecutive iterations of the reference's own train_vae loop (goldens)."""
+    dev = torch.device('cuda')
+    fx = load_golden('wae_b%d.npz' % batch)
+    st = eng.FlatState(V, dev)
+    st.load(_params())
+    keys = [str(k) for k in fx['logged_keys']]
+    for it in range(int(fx['n_it'])):
+        tokens = torch.from_numpy(fx['it%d/tokens' % it]).to(dev)
+        pre = 'it%d/noise/' % it
+        noise = {k[len(pre):]: torch.from_numpy(fx[k].copy()).to(dev) for k in fx.files if k.startswith(pre)}
+        hp = eng.make_hparams(beta=float(fx['betas'][it]))
+        scal, ex = eng.train_step(st, tokens, noise, hp, want=('mu', 'logvar', 'z', 'logits'))
+        scal = scal.cpu()
+        for j, k in enumerate(keys):
+            got = float(scal[eng.SC[LOG_TO_SC[k]]])
+            assert got == pytest.approx(float(fx['logged'][it][j]), rel=1e-4, abs=1e-7), (it, k)
+        if it == 0:
+            for k in ('mu', 'logvar', 'z', 'logits'):
+                np.testing.assert_allclose(ex[k].cpu().numpy(), fx['it0/' + k], rtol=1e-4, atol=2e-6, err_msg=k)
+            g = st.views(st.grads)
+            for k in ow.UNIQUE_VAE_PARAMS:
+                ref = fx['it0/grad/' + k]
+                scale = np.abs(ref).max() + 1e-12
+                np.testing.assert_allclose(g[k].cpu().numpy(), ref, rtol=1e-3, atol=1e-4 * scale, err_msg=k)
+        for k in ow.UNIQUE_VAE_PARAMS:
+            np.testing.assert_allclose(digest(k, st.views(st.grads)[k])[:2], fx['it%d/grad_digest/%s' % (it, k)][:2],
+                                       rtol=1e-3, atol=1e-6, err_msg='grad digest ' + k)
+    final = {k: torch.from_numpy(fx['final/param/' + k]) for k in ow.UNIQUE_VAE_PARAMS}
+    g0 = {k: torch.from_numpy(fx['it0/grad/' + k]) for k in ow.UNIQUE_VAE_PARAMS}
+    assert_params_close(st.views(st.params), final, g0, 'final', max_outliers=3)
+
+
+@pytest.mark.parametrize('batch,z_regu', [(6, 'mmdrf'), (40, 'mmdrf'), (40, 'kl'), (131, 'mmdrf')])
+def test_train_step_matches_oracle(eng, batch, z_regu):
+    dev = torch.device('cuda')
+    p = ow.random_params(V, seed=11)
+    st = eng.FlatState(V, dev)
+    st.load(p)
+    ostate = {}
+    for it in range(2):
+        tokens = ow.synthetic_tokens(batch, V, seed=50 + it)
+        noise = ow.draw_noise(batch, seed=60 + it)
+        beta = 1.0 + 0.25 * it
+        hp = eng.make_hparams(beta=beta, z_regu=z_regu, lambda_logvar_l1=0.01)
+        scal, _ = eng.train_step(st, tokens.to(dev), dev_noise(noise, dev), hp)
+        scal = scal.cpu()
+        oscal, ograds, _ = ow.train_step(p, ostate, tokens, noise, it=it, beta=beta, z_regu=z_regu, lambda_l1=0.01)
+        for k, ok in (('loss', 'loss'), ('recon', 'recon'), ('kl', 'kl'), ('mmd', 'mmd'), ('mmdrf', 'mmdrf'),
+                      ('logvar_l1', 'logvar_l1'), ('logvar_kl', 'logvar_kl'), ('z_mu_l1', 'z_mu_l1'),
+                      ('z_logvar', 'z_logvar_mean'), ('grad_norm', 'grad_norm')):
+            assert float(scal[eng.SC[k]]) == pytest.approx(oscal[ok], rel=1e-4, abs=1e-7), (it, k)
+        want = clipped(ograds, oscal['grad_norm'])
+        got = st.views(st.grads)
+        for k in ow.UNIQUE_VAE_PARAMS:
+            scale = float(want[k].abs().max()) + 1e-12
+            np.testing.assert_allclose(got[k].cpu().numpy(), want[k].numpy(), rtol=1e-3, atol=1e-4 * scale, err_msg=k)
+        assert_params_close(st.views(st.params), p, want, 'it%d' % it)
+
+
+def test_full_batch_4096_matches_reference_golden(eng):
+    """BASELINE config 2 (B=4096): inputs regenerated from the recorded seeds; scalars and
+    gradient / parameter digests from the live reference."""
+    dev = torch.device('cuda')
+    fx = load_golden('wae_b4096.npz')
+    B = int(fx['batch'])
+    st = eng.FlatState(V, dev)
+    st.load(_params())
+    tokens = ow.synthetic_tokens(B, V, seed=int(fx['token_seeds'][0]))
+    noise = ow.draw_noise(B, seed=int(fx['noise_seeds'][0]))
+    hp = eng.make_hparams(beta=float(fx['betas'][0]))
+    scal, ex = eng.train_step(st, tokens.to(dev), dev_noise(noise, dev), hp, want=('mu', 'logvar', 'logits'))
+    scal = scal.cpu()
+    keys = [str(k) for k in fx['logged_keys']]
+    for j, k in enumerate(keys):
+        assert float(scal[eng.SC[LOG_TO_SC[k]]]) == pytest.approx(float(fx['logged'][0][j]), rel=1e-4, abs=1e-7), k
+    for k in ('mu', 'logvar', 'logits'):
+        np.testing.assert_allclose(digest(k, ex[k]), fx['it0/%s_digest' % k], rtol=2e-4, atol=2e-5, err_msg=k)
+    for k in ow.UNIQUE_VAE_PARAMS:
+        ref = fx['it0/grad_digest/' + k]
+        np.testing.assert_allclose(digest(k, st.views(st.grads)[k]), ref, rtol=2e-3, atol=2e-4 * abs(ref[1]) + 1e-7,
+                                   err_msg='grad ' + k)
+
+
+def test_loss_ops_match_oracle(eng):
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(4)
+    B = 77
+    mu, lv = torch.randn(B, 100, generator=g) * 0.5, torch.randn(B, 100, generator=g) * 0.3 - 1
+    z, zp = torch.randn(B, 100, generator=g), torch.randn(B, 100, generator=g)
+    rf_w, rf_b = torch.randn(100, 500, generator=g), 6.28 * torch.rand(500, generator=g)
+    out = eng.latent_stats(mu.to(dev), lv.to(dev)).cpu()
+    want = [ow.kl_gaussianprior(mu, lv), ow.kl_gaussian_sharedmu(mu, lv), lv.abs().sum(1).mean(0), mu.abs().mean(),
+            lv.mean()]
+    np.testing.assert_allclose(out.numpy(), np.array([float(w) for w in want]), rtol=1e-5)
+    got = eng.mmd_full(z.to(dev), zp.to(dev), 7.0).cpu()
+    assert float(got) == pytest.approx(float(ow.mmd_full_kernel(z, zp, 7.0)), rel=1e-5)
+    zr = z.clone().requires_grad_(True)
+    loss = ow.mmd_rf(zr, zp, rf_w, rf_b)
+    loss.backward()
+    got, dz = eng.mmd_rf(z.to(dev), zp.to(dev), rf_w.to(dev), rf_b.to(dev), 7.0, want_grad=True)
+    assert float(got) == pytest.approx(float(loss), rel=1e-4)
+    np.testing.assert_allclose(dz.cpu().numpy(), zr.grad.numpy(), rtol=1e-3, atol=1e-5 * float(zr.grad.abs().max()))
+    tokens = ow.synthetic_tokens(B, V, seed=2)
+    logits = torch.randn(B, 25, V, generator=g)
+    lr = logits.clone().requires_grad_(True)
+    want = ow.recon_dec(tokens, lr)
+    want.backward()
+    out, dl = eng.softmax_xent(logits.to(dev), tokens.to(dev), want_grad=True)
+    assert float(out[0]) == pytest.approx(float(want), rel=1e-5)
+    np.testing.assert_allclose(dl.cpu().numpy(), lr.grad.numpy(), rtol=1e-4, atol=1e-8)
+
+
+def test_module_level_backward_matches_oracle(eng):
+    """cpg_wae_forward / cpg_wae_backward with arbitrary upstream gradients (autograd path)."""
+    dev = torch.device('cuda')
+    B = 19
+    p = ow.random_params(V, seed=21)
+    tokens = ow.synthetic_tokens(B, V, seed=22)
+    noise = ow.draw_noise(B, seed=23)
+    g = torch.Generator().manual_seed(24)
+    d_mu, d_lv, d_z = (torch.randn(B, 100, generator=g) * 0.1 for _ in range(3))
+    d_logits = torch.randn(B, 25, V, generator=g) * 0.01
+    leaves = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    mu, lv = ow.encoder_forward(leaves, tokens)
+    z = ow.reparameterize(mu, lv, noise['eps'])
+    logits = ow.decoder_forward(leaves, ow.word_dropout(tokens, noise['word_drop']), z, noise['c'], noise['out_keep'])
+    ((mu * d_mu).sum() + (lv * d_lv).sum() + (z * d_z).sum() + (logits * d_logits).sum()).backward()
+    st = eng.FlatState(V, dev)
+    st.load(p)
+    nz = dev_noise(noise, dev)
+    tk = tokens.to(dev)
+    eng.wae_forward(st.params, V, tk, nz['eps'], nz['c'], nz['word_drop'], nz['out_keep'], 0.3, True, True)
+    eng.wae_backward(st.params, V, tk, nz['eps'], nz['c'], nz['word_drop'], nz['out_keep'], 0.3, d_mu.to(dev),
+                     d_lv.to(dev), d_z.to(dev), d_logits.to(dev), st.grads)
+    got = st.views(st.grads)
+    for k in ow.UNIQUE_VAE_PARAMS:
+        want = leaves[k].grad.clone()
+        if k == 'word_emb.weight':
+            want[ow.PAD_IDX] = 0
+        scale = float(want.abs().max()) + 1e-12
+        np.testing.assert_allclose(got[k].cpu().numpy(), want.numpy(), rtol=1e-3, atol=1e-4 * scale, err_msg=k)
