@@ -8,7 +8,7 @@ machine, or no CUDA device is present.
 import ctypes
 import os
 import threading
-from ctypes import (POINTER, Structure, byref, c_char_p, c_float, c_int, c_int64, c_void_p)
+from ctypes import (POINTER, Structure, byref, c_char_p, c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p)
 
 import torch
 
@@ -80,6 +80,18 @@ def _signatures(L):
         'cpg_latent_stats': (I, [P, P, P, P, I, P]),
         'cpg_mmd_full': (I, [P, P, P, P, I, F, P]),
         'cpg_mmd_rf': (I, [P, P, P, P, P, P, I, I, F, P, P]),
+        'cpg_fill_step_noise': (I, [P, P, c_uint64, c_uint32, I, I, F, F, P, P, P, P, P, P]),
+        'cpg_fill_normal': (I, [P, P, c_uint64, c_uint32, I64, P]),
+        'cpg_fill_uniform': (I, [P, P, c_uint64, c_uint32, F, I64, P]),
+        'cpg_beam_decode': (I, [P, P, P, I, I, I, P, P, I, I, P, P, P]),
+        'cpg_sample_decode': (I, [P, P, P, I, I, I, P, P, I, F, c_uint64, P, P]),
+        'cpg_cnn_classifier_fwd': (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P, P, P]),
+        'cpg_class_score_accept': (I, [P, P, P, P, I64, I, P, P, P, P, P, P, P]),
+        'cpg_class_sample': (I, [P, P, P, P, P, I, I, P, P, P, P, c_uint64, I64, I64, P, P, P, P, P, P]),
+        'cpg_gmm_logpdf': (I, [P, P, P, I64, P, P, P, I, P]),
+        'cpg_prior_logpdf': (I, [P, P, P, I64, P]),
+        'cpg_profile_enable': (I, [I]),
+        'cpg_profile_read': (I, [P, I, P, P, I]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -174,3 +186,22 @@ def param_layout(n_vocab):
 
 def launch_count():
     return int(lib().cpg_launch_count(None))
+
+
+def profile_enable(on=True):
+    lib().cpg_profile_enable(1 if on else 0)
+
+
+def profile_read(cap=128):
+    """-> list of (kernel label, total ms, launches) since the last read (synchronises)."""
+    stride = 64
+    names = ctypes.create_string_buffer(cap * stride)
+    ms = (c_float * cap)()
+    cnt = (c_int * cap)()
+    n = lib().cpg_profile_read(ctypes.cast(names, c_void_p), stride, ctypes.cast(ms, c_void_p),
+                               ctypes.cast(cnt, c_void_p), cap)
+    out = []
+    for i in range(n):
+        label = names.raw[i * stride:(i + 1) * stride].split(b'\0', 1)[0].decode()
+        out.append((label, float(ms[i]), int(cnt[i])))
+    return out

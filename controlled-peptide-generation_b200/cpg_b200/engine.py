@@ -237,3 +237,45 @@ def mmd_rf(z, z_prior, rf_w, rf_b, sigma, want_grad=False):
                            ptr(rf_b.contiguous(), torch.float32), z.shape[0], rf_w.shape[1], float(sigma), ptr(out),
                            ptr(dz)), 'cpg_mmd_rf')
     return out, dz
+
+
+# ------------------------------------------------------------------ perf-mode noise + trainer
+def fill_step_noise(noise, seed, step, p_word=0.3, p_out=0.3):
+    """Regenerate the per-iteration noise tensors in place (Philox; pure function of seed/step)."""
+    B, L = noise['word_drop'].shape
+    dev = noise['eps'].device
+    check(lib().cpg_fill_step_noise(context(dev), stream_ptr(), int(seed), int(step), B, L, float(p_word),
+                                    float(p_out), ptr(noise['eps']), ptr(noise['c']), ptr(noise['word_drop']),
+                                    ptr(noise['out_keep']), ptr(noise.get('z_prior_full')),
+                                    ptr(noise['z_prior_rf'])), 'cpg_fill_step_noise')
+
+
+def fill_normal(out, seed, stream_id):
+    check(lib().cpg_fill_normal(context(out.device), stream_ptr(), int(seed), int(stream_id), out.numel(), ptr(out)),
+          'cpg_fill_normal')
+    return out
+
+
+def fill_uniform(out, seed, stream_id, scale=1.0):
+    check(lib().cpg_fill_uniform(context(out.device), stream_ptr(), int(seed), int(stream_id), float(scale),
+                                 out.numel(), ptr(out)), 'cpg_fill_uniform')
+    return out
+
+
+def alloc_noise(B, L, device, rf_dim=500, seed=1238, full_mmd=True):
+    """Device buffers for one iteration's noise; rf_w / rf_b are drawn once (losses.py:73-81 caches them)."""
+    dev = _lib.tensor_device(device)
+    noise = {
+        'eps': torch.empty(B, ZD, device=dev),
+        'c': torch.empty(B, CD, device=dev),
+        'word_drop': torch.empty(B, L, dtype=torch.uint8, device=dev),
+        'out_keep': torch.empty(B, L, DEC_H, dtype=torch.uint8, device=dev),
+        'z_prior_rf': torch.empty(B, ZD, device=dev),
+        'rf_w': torch.empty(ZD, rf_dim, device=dev),
+        'rf_b': torch.empty(rf_dim, device=dev),
+    }
+    if full_mmd:
+        noise['z_prior_full'] = torch.empty(B, ZD, device=dev)
+    fill_normal(noise['rf_w'], seed, 0xF001)
+    fill_uniform(noise['rf_b'], seed, 0xF002, scale=2 * math.pi)
+    return noise

@@ -1,0 +1,256 @@
+// CLaSS latent-space sampling: draw z ~ Q (diag Gaussian mixture), score with the z-space
+// attribute classifiers, rejection-accept; plus batched mixture / prior log-densities.
+//
+// Replaces, per draw, the CPU numpy / scikit-learn calls of density_modeling.py:50-60
+// (`rejection_sample`): GaussianMixture.sample (sklearn mixture/_base.py:434-511; 83 % of the
+// reference's time), LogisticRegression.predict_proba (density_modeling.py:43-48), the running
+// product of target-class probabilities and `np.random.uniform(n) < prod`.  Log densities replace
+// the per-point Python loop of evaluate_nll (density_modeling.py:99-108): mogQ.logpdf (:75-77,
+// sklearn _gaussian_mixture.py:536-542 + logsumexp) and prior_logpdf (:11-14).
+//
+// Score arithmetic follows the dtype of the fitted classifier (see oracle/class_sampling.py):
+// float32 when the classifier was fitted on float32 z's (the reference pipeline), float64 otherwise.
+#include "ctx.h"
+
+namespace cpg {
+int check_launch(const char* where);
+
+constexpr int MAX_CLF = 4;
+struct ClfSpec {
+    const double* coef[MAX_CLF];   // [D] each (device, stored as fp64; rounded to fp32 when f32 != 0)
+    double intercept[MAX_CLF];
+    int target_col[MAX_CLF];
+    int f32[MAX_CLF];
+    int n_clf;
+};
+
+__device__ __forceinline__ float expit_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ double expit_d(double x) { return 1.0 / (1.0 + exp(-x)); }
+
+// ---- parity mode: z and u are inputs (the reference's own draws) ------------------------------
+// one thread per draw; coefficients in shared memory
+__global__ void __launch_bounds__(128)
+k_score_accept(const float* __restrict__ z, const double* __restrict__ u, int64_t n, ClfSpec cs,
+               double* __restrict__ probs, double* __restrict__ accum_out, uint8_t* __restrict__ accept) {
+    __shared__ double coef_s[MAX_CLF][ZD];
+    for (int i = threadIdx.x; i < cs.n_clf * ZD; i += blockDim.x) coef_s[i / ZD][i % ZD] = cs.coef[i / ZD][i % ZD];
+    __syncthreads();
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* zi = z + i * ZD;
+    double acc_d = 1.0;
+    float acc_f = 1.0f;
+    bool all_f32 = true;
+    for (int a = 0; a < cs.n_clf; ++a) {
+        double p;
+        if (cs.f32[a]) {
+            float s = 0.f;
+            for (int d = 0; d < ZD; ++d) s = fmaf(zi[d], (float)coef_s[a][d], s);
+            s += (float)cs.intercept[a];
+            float p1 = expit_f(s);
+            float pf = cs.target_col[a] == 1 ? p1 : 1.0f - p1;
+            acc_f *= pf;
+            acc_d *= (double)pf;
+            p = (double)pf;
+        } else {
+            all_f32 = false;
+            double s = 0.0;
+            for (int d = 0; d < ZD; ++d) s = fma((double)zi[d], coef_s[a][d], s);
+            s += cs.intercept[a];
+            double p1 = expit_d(s);
+            p = cs.target_col[a] == 1 ? p1 : 1.0 - p1;
+            acc_d *= p;
+        }
+        if (probs != nullptr) probs[(size_t)a * n + i] = p;
+    }
+    double accum = all_f32 ? (double)acc_f : acc_d;     // numpy keeps float32 products in float32
+    if (accum_out != nullptr) accum_out[i] = accum;
+    accept[i] = u[i] < accum ? 1 : 0;
+}
+
+// ---- perf mode: everything drawn in-kernel (Philox), one warp per draw ------------------------
+struct GmmSpec {
+    const float* mean;      // [K][D] fp32
+    const float* sd;        // [K][D] sqrt(cov), fp32
+    const float* cdf;       // [K] cumulative weights (last = 1)
+    int K;
+};
+constexpr int CS_WARPS = 8;
+__global__ void __launch_bounds__(CS_WARPS * 32)
+k_class_sample(GmmSpec g, ClfSpec cs, uint64_t seed, int64_t offset, int64_t n, float* __restrict__ z_out,
+               double* __restrict__ probs, double* __restrict__ accum_out, uint8_t* __restrict__ accept,
+               int* __restrict__ comp_out, unsigned long long* __restrict__ n_accepted) {
+    __shared__ float coef_s[MAX_CLF][ZD + 28];
+    __shared__ float cdf_s[1024];
+    for (int i = threadIdx.x; i < cs.n_clf * ZD; i += blockDim.x) coef_s[i / ZD][i % ZD] = (float)cs.coef[i / ZD][i % ZD];
+    for (int i = threadIdx.x; i < g.K; i += blockDim.x) cdf_s[i] = g.cdf[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long local_acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * CS_WARPS + warp; i < n; i += (int64_t)gridDim.x * CS_WARPS) {
+        const uint64_t gid = (uint64_t)(offset + i);
+        uint32_t r[4];
+        // stream 0: component + acceptance uniform (same for every lane), stream 1+lane: normals
+        Philox::gen(seed, gid, 0u, r);
+        const float uc = (float)(r[0] >> 8) * (1.0f / 16777216.0f);
+        const double ua = u64_to_unit(r[2], r[3]);
+        int lo = 0, hi = g.K - 1;                            // first k with cdf[k] > uc
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf_s[mid] > uc) hi = mid; else lo = mid + 1; }
+        const int k = lo;
+        Philox::gen(seed, gid, 1u + (uint32_t)lane, r);
+        float nrm[4];
+        {
+            float u1 = u32_to_unit_open(r[0]), u2 = u32_to_unit_open(r[1]);
+            float rad = sqrtf(-2.0f * __logf(u1)); float sn, cn; __sincosf(6.283185307179586f * u2, &sn, &cn);
+            nrm[0] = rad * cn; nrm[1] = rad * sn;
+            u1 = u32_to_unit_open(r[2]); u2 = u32_to_unit_open(r[3]);
+            rad = sqrtf(-2.0f * __logf(u1)); __sincosf(6.283185307179586f * u2, &sn, &cn);
+            nrm[2] = rad * cn; nrm[3] = rad * sn;
+        }
+        float zv[4];
+        float dots[MAX_CLF] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int d = lane + 32 * q;
+            zv[q] = 0.f;
+            if (d < ZD) {
+                zv[q] = fmaf(nrm[q], __ldg(g.sd + (size_t)k * ZD + d), __ldg(g.mean + (size_t)k * ZD + d));
+                if (z_out != nullptr) z_out[(size_t)i * ZD + d] = zv[q];
+#pragma unroll
+                for (int a = 0; a < MAX_CLF; ++a)
+                    if (a < cs.n_clf) dots[a] = fmaf(zv[q], coef_s[a][d], dots[a]);
+            }
+        }
+        float accf = 1.0f;
+#pragma unroll
+        for (int a = 0; a < MAX_CLF; ++a) {
+            if (a < cs.n_clf) {
+                float s = warp_sum(dots[a]) + (float)cs.intercept[a];
+                float p1 = expit_f(s);
+                float p = cs.target_col[a] == 1 ? p1 : 1.0f - p1;
+                accf *= p;
+                if (probs != nullptr && lane == 0) probs[(size_t)a * n + i] = (double)p;
+            }
+        }
+        if (lane == 0) {
+            const int acc = ua < (double)accf ? 1 : 0;
+            accept[i] = (uint8_t)acc;
+            if (accum_out != nullptr) accum_out[i] = (double)accf;
+            if (comp_out != nullptr) comp_out[i] = k;
+            local_acc += acc;
+        }
+    }
+    if (n_accepted != nullptr && lane == 0 && local_acc) atomicAdd(n_accepted, local_acc);
+}
+
+// ---- log densities (fp64) -----------------------------------------------------------------------
+// log sum_k w_k N(x; mu_k, diag(cov_k)); one warp per point, lanes over components
+constexpr int LP_WARPS = 8;
+__global__ void __launch_bounds__(LP_WARPS * 32)
+k_gmm_logpdf(const float* __restrict__ x, int64_t n, const double* __restrict__ mean_t, const double* __restrict__ prec_t,
+             const double* __restrict__ logw_norm, int K, double* __restrict__ out) {
+    // mean_t / prec_t are [D][K] (component-fastest) so that lanes read consecutive addresses
+    __shared__ double xs[LP_WARPS][ZD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t i = (int64_t)blockIdx.x * LP_WARPS + warp; i < n; i += (int64_t)gridDim.x * LP_WARPS) {
+        for (int d = lane; d < ZD; d += 32) xs[warp][d] = (double)x[i * ZD + d];
+        __syncwarp();
+        double m = -INFINITY, ssum = 0.0;                   // running logsumexp over this lane's components
+        for (int k = lane; k < K; k += 32) {
+            double q = 0.0;
+            for (int d = 0; d < ZD; ++d) {
+                double df = xs[warp][d] - mean_t[(size_t)d * K + k];
+                q = fma(df * df, prec_t[(size_t)d * K + k], q);
+            }
+            double lp = logw_norm[k] - 0.5 * q;
+            if (lp > m) { ssum = ssum * exp(m - lp) + 1.0; m = lp; } else { ssum += exp(lp - m); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double om = __shfl_xor_sync(0xffffffffu, m, o);
+            double os = __shfl_xor_sync(0xffffffffu, ssum, o);
+            double nm = fmax(m, om);
+            if (nm == -INFINITY) { ssum = 0.0; } else { ssum = ssum * exp(m - nm) + os * exp(om - nm); }
+            m = nm;
+        }
+        if (lane == 0) out[i] = m + log(ssum);
+        __syncwarp();
+    }
+}
+
+// -D/2 log(2 pi) - |z|^2 / 2
+__global__ void __launch_bounds__(LP_WARPS * 32)
+k_prior_logpdf(const float* __restrict__ x, int64_t n, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t i = (int64_t)blockIdx.x * LP_WARPS + warp; i < n; i += (int64_t)gridDim.x * LP_WARPS) {
+        double s = 0.0;
+        for (int d = lane; d < ZD; d += 32) { double v = (double)x[i * ZD + d]; s = fma(v, v, s); }
+        s = warp_sum(s);
+        if (lane == 0) out[i] = -0.5 * (double)ZD * 1.8378770664093453 - 0.5 * s;
+    }
+}
+
+static int fill_clf(ClfSpec& cs, int n_clf, const double* const* coef, const double* intercept, const int* target_col,
+                    const int* f32) {
+    if (n_clf < 0 || n_clf > MAX_CLF) { set_error("at most 4 attribute classifiers are supported"); return CPG_EINVAL; }
+    memset(&cs, 0, sizeof(cs));
+    cs.n_clf = n_clf;
+    for (int a = 0; a < n_clf; ++a) {
+        if (!coef[a]) { set_error("null classifier coefficients"); return CPG_EINVAL; }
+        cs.coef[a] = coef[a]; cs.intercept[a] = intercept[a]; cs.target_col[a] = target_col[a]; cs.f32[a] = f32[a];
+    }
+    return CPG_OK;
+}
+
+}  // namespace cpg
+
+using namespace cpg;
+
+extern "C" {
+
+int cpg_class_score_accept(cpg_ctx* ctx, cpg_stream stream, const float* z, const double* u, int64_t n, int n_clf,
+                           const double* const* coef, const double* intercept, const int* target_col, const int* f32,
+                           double* probs, double* accum, uint8_t* accept) {
+    if (!ctx || !z || !u || !accept || n < 1) { set_error("cpg_class_score_accept: bad argument"); return CPG_EINVAL; }
+    ClfSpec cs;
+    int rc = fill_clf(cs, n_clf, coef, intercept, target_col, f32);
+    if (rc) return rc;
+    CPG_LAUNCH(k_score_accept, (unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream, z, u, n, cs, probs, accum, accept);
+    return check_launch("cpg_class_score_accept");
+}
+
+int cpg_class_sample(cpg_ctx* ctx, cpg_stream stream, const float* gmm_mean, const float* gmm_sd, const float* gmm_cdf,
+                     int K, int n_clf, const double* const* coef, const double* intercept, const int* target_col,
+                     const int* f32, uint64_t seed, int64_t offset, int64_t n, float* z_out, double* probs,
+                     double* accum, uint8_t* accept, int* comp_out, unsigned long long* n_accepted) {
+    if (!ctx || !gmm_mean || !gmm_sd || !gmm_cdf || !accept || n < 1) { set_error("cpg_class_sample: bad argument"); return CPG_EINVAL; }
+    if (K < 1 || K > 1024) { set_error("cpg_class_sample: 1 <= n_components <= 1024"); return CPG_EINVAL; }
+    ClfSpec cs;
+    int rc = fill_clf(cs, n_clf, coef, intercept, target_col, f32);
+    if (rc) return rc;
+    GmmSpec g{gmm_mean, gmm_sd, gmm_cdf, K};
+    int64_t want = (n + CS_WARPS - 1) / CS_WARPS;
+    int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 8);
+    CPG_LAUNCH(k_class_sample, grid, CS_WARPS * 32, 0, (cudaStream_t)stream, g, cs, seed, offset, n, z_out, probs, accum,
+               accept, comp_out, n_accepted);
+    return check_launch("cpg_class_sample");
+}
+
+int cpg_gmm_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, const double* mean_t,
+                   const double* prec_t, const double* logw_norm, int K, double* out) {
+    if (!ctx || !x || !mean_t || !prec_t || !logw_norm || !out || n < 1 || K < 1) { set_error("cpg_gmm_logpdf: bad argument"); return CPG_EINVAL; }
+    int64_t want = (n + LP_WARPS - 1) / LP_WARPS;
+    int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 8);
+    CPG_LAUNCH(k_gmm_logpdf, grid, LP_WARPS * 32, 0, (cudaStream_t)stream, x, n, mean_t, prec_t, logw_norm, K, out);
+    return check_launch("cpg_gmm_logpdf");
+}
+
+int cpg_prior_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, double* out) {
+    if (!ctx || !x || !out || n < 1) { set_error("cpg_prior_logpdf: bad argument"); return CPG_EINVAL; }
+    int64_t want = (n + LP_WARPS - 1) / LP_WARPS;
+    int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 8);
+    CPG_LAUNCH(k_prior_logpdf, grid, LP_WARPS * 32, 0, (cudaStream_t)stream, x, n, out);
+    return check_launch("cpg_prior_logpdf");
+}
+
+}  // extern "C"

@@ -5,14 +5,23 @@
 
 #ifdef CPG_EMU
 #include "cuda_emu.h"                       // tools/cuda_emu (developer tool, g++ build)
-#define CPG_LAUNCH(kernel, grid, block, smem, stream, ...) \
+#define CPG_LAUNCH_NAMED(label, kernel, grid, block, smem, stream, ...) \
     do { ++cpg::g_launch_count; emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); }); } while (0)
+#define CPG_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    CPG_LAUNCH_NAMED(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
 #define CPG_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::cur_block()->dyn_smem)
 #define CPG_SET_MAX_SMEM(kernel, bytes) 0
 #else
 #include <cuda_runtime.h>
+#define CPG_LAUNCH_NAMED(label, kernel, grid, block, smem, stream, ...)                      \
+    do {                                                                                     \
+        ++cpg::g_launch_count;                                                               \
+        if (cpg::g_profile_on) cpg::prof_begin(label, (stream));                             \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
+        if (cpg::g_profile_on) cpg::prof_end((stream));                                      \
+    } while (0)
 #define CPG_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    do { ++cpg::g_launch_count; kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); } while (0)
+    CPG_LAUNCH_NAMED(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
 #define CPG_DYN_SMEM(type, name)                                   \
     extern __shared__ __align__(128) unsigned char name##_raw_[];  \
     type* name = reinterpret_cast<type*>(name##_raw_)
@@ -23,6 +32,12 @@
 namespace cpg {
 
 extern long long g_launch_count;      // kernels enqueued by this library (reported by cpg_launch_count)
+// optional per-kernel CUDA-event timing (cpg_profile_*): off by default, one branch per launch
+extern bool g_profile_on;
+#ifndef CPG_EMU
+void prof_begin(const char* label, cudaStream_t s);
+void prof_end(cudaStream_t s);
+#endif
 
 // ---- token ids (models/mutils.py:5-8)
 constexpr int UNK = 0, PAD = 1, START = 2, EOS = 3;

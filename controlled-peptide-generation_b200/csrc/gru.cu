@@ -299,28 +299,28 @@ void launch_gru_fwd_enc(cudaStream_t s, const GruSeq* two, int B, int L) {
     GruSeqPair pr; pr.s[0] = two[0]; pr.s[1] = two[1];
     auto kfn = k_gru_fwd<ENC_H, GRU_R>;
     CPG_SET_MAX_SMEM(kfn, C::SMEM_FWD);
-    CPG_LAUNCH(kfn, dim3(ceil_div(B, GRU_R), 2), C::NT, C::SMEM_FWD, s, pr, B, L);
+    CPG_LAUNCH_NAMED("k_gru_fwd_enc", kfn, dim3(ceil_div(B, GRU_R), 2), C::NT, C::SMEM_FWD, s, pr, B, L);
 }
 void launch_gru_fwd_dec(cudaStream_t s, const GruSeq& seq, int B, int L) {
     using C = GruCfg<DEC_HP, GRU_R>;
     GruSeqPair pr; pr.s[0] = seq; pr.s[1] = seq;
     auto kfn = k_gru_fwd<DEC_HP, GRU_R>;
     CPG_SET_MAX_SMEM(kfn, C::SMEM_FWD);
-    CPG_LAUNCH(kfn, dim3(ceil_div(B, GRU_R), 1), C::NT, C::SMEM_FWD, s, pr, B, L);
+    CPG_LAUNCH_NAMED("k_gru_fwd_dec", kfn, dim3(ceil_div(B, GRU_R), 1), C::NT, C::SMEM_FWD, s, pr, B, L);
 }
 void launch_gru_bwd_enc(cudaStream_t s, const GruSeq* two, int B, int L) {
     using C = GruCfg<ENC_H, GRU_R>;
     GruSeqPair pr; pr.s[0] = two[0]; pr.s[1] = two[1];
     auto kfn = k_gru_bwd<ENC_H, GRU_R, false>;
     CPG_SET_MAX_SMEM(kfn, C::SMEM_BWD);
-    CPG_LAUNCH(kfn, dim3(ceil_div(B, GRU_R), 2), C::NT, C::SMEM_BWD, s, pr, B, L);
+    CPG_LAUNCH_NAMED("k_gru_bwd_enc", kfn, dim3(ceil_div(B, GRU_R), 2), C::NT, C::SMEM_BWD, s, pr, B, L);
 }
 void launch_gru_bwd_dec(cudaStream_t s, const GruSeq& seq, int B, int L) {
     using C = GruCfg<DEC_HP, GRU_R>;
     GruSeqPair pr; pr.s[0] = seq; pr.s[1] = seq;
     auto kfn = k_gru_bwd<DEC_HP, GRU_R, true>;
     CPG_SET_MAX_SMEM(kfn, C::SMEM_BWD);
-    CPG_LAUNCH(kfn, dim3(ceil_div(B, GRU_R), 1), C::NT, C::SMEM_BWD, s, pr, B, L);
+    CPG_LAUNCH_NAMED("k_gru_bwd_dec", kfn, dim3(ceil_div(B, GRU_R), 1), C::NT, C::SMEM_BWD, s, pr, B, L);
 }
 
 }  // namespace cpg

@@ -1,0 +1,82 @@
+// Optional per-kernel timing with CUDA events on the launching stream (used by bench.py for the
+// roofline block and by developers as a poor man's launch list).  Off by default.
+#include <map>
+#include <string>
+#include <vector>
+#include <string.h>
+#include "ctx.h"
+
+namespace cpg {
+
+bool g_profile_on = false;
+
+#ifndef CPG_EMU
+struct ProfRec { const char* label; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_pool;
+static cudaEvent_t g_pending_a = nullptr;
+static const char* g_pending_label = nullptr;
+
+static cudaEvent_t take_event() {
+    if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(const char* label, cudaStream_t s) {
+    g_pending_a = take_event();
+    g_pending_label = label;
+    cudaEventRecord(g_pending_a, s);
+}
+void prof_end(cudaStream_t s) {
+    cudaEvent_t b = take_event();
+    cudaEventRecord(b, s);
+    g_recs.push_back(ProfRec{g_pending_label, g_pending_a, b});
+}
+#endif
+
+}  // namespace cpg
+
+using namespace cpg;
+
+extern "C" {
+
+int cpg_profile_enable(int on) {
+    g_profile_on = on != 0;
+    return CPG_OK;
+}
+
+// Synchronises, then writes up to `cap` records "label\0" packed into `names` (name_stride bytes each),
+// total milliseconds and launch counts per label; clears the recorded events.  Returns the number of labels.
+int cpg_profile_read(char* names, int name_stride, float* total_ms, int* counts, int cap) {
+#ifdef CPG_EMU
+    (void)names; (void)name_stride; (void)total_ms; (void)counts; (void)cap;
+    return 0;
+#else
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<double, int>> acc;
+    std::vector<std::string> order;
+    for (auto& r : g_recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto it = acc.find(r.label);
+        if (it == acc.end()) { acc[r.label] = {ms, 1}; order.push_back(r.label); }
+        else { it->second.first += ms; it->second.second += 1; }
+        g_pool.push_back(r.a);
+        g_pool.push_back(r.b);
+    }
+    g_recs.clear();
+    int n = 0;
+    for (auto& name : order) {
+        if (n >= cap) break;
+        strncpy(names + (size_t)n * name_stride, name.c_str(), name_stride - 1);
+        names[(size_t)n * name_stride + name_stride - 1] = 0;
+        total_ms[n] = (float)acc[name].first;
+        counts[n] = acc[name].second;
+        ++n;
+    }
+    return n;
+#endif
+}
+
+}  // extern "C"

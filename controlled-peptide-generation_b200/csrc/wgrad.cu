@@ -93,9 +93,9 @@ void launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float
     int rps = ceil_div(ceil_div(nrows, want), WG_ROWS) * WG_ROWS;
     int nsplit = ceil_div(nrows, rps);
     if (HP == ENC_H) {
-        CPG_LAUNCH(k_wgrad_hh<ENC_H>, dim3(3, nsplit), (ENC_H / 4) * (ENC_H / 8), 0, s, dg, hs, h0, B, L, rps, part);
+        CPG_LAUNCH_NAMED("k_wgrad_hh_enc", k_wgrad_hh<ENC_H>, dim3(3, nsplit), (ENC_H / 4) * (ENC_H / 8), 0, s, dg, hs, h0, B, L, rps, part);
     } else {
-        CPG_LAUNCH(k_wgrad_hh<DEC_HP>, dim3(3, nsplit), (DEC_HP / 4) * (DEC_HP / 8), 0, s, dg, hs, h0, B, L, rps, part);
+        CPG_LAUNCH_NAMED("k_wgrad_hh_dec", k_wgrad_hh<DEC_HP>, dim3(3, nsplit), (DEC_HP / 4) * (DEC_HP / 8), 0, s, dg, hs, h0, B, L, rps, part);
     }
     CPG_LAUNCH(k_wgrad_hh_reduce, ceil_div(3 * H * H, 256), 256, 0, s, part, nsplit, HP, H, dW);
 }

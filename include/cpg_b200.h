@@ -170,6 +170,72 @@ int cpg_mmd_full(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* z
 int cpg_mmd_rf(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* z_prior, const float* rf_w,
                const float* rf_b, int B, int rf_dim, float sigma, float* loss_out, float* dz);
 
+/* ---- perf-mode noise (Philox4x32-10 counter RNG) ----------------------------------------------
+ * Replaces the per-iteration host/device RNG draws of SURVEY.md appendix A: torch.randn (eps,
+ * model.py:111), np.random.multinomial (c, model.py:125), np.random.binomial (word dropout,
+ * decoder.py:124-127), nn.Dropout mask (decoder.py:44), torch.randn_like (z_prior x2, losses.py:37).
+ * Every tensor is a pure function of (seed, step, index).  Any output pointer may be NULL. */
+int cpg_fill_step_noise(cpg_ctx* ctx, cpg_stream stream, uint64_t seed, uint32_t step, int B, int L, float p_word,
+                        float p_out, float* eps, float* c, uint8_t* word_drop, uint8_t* out_keep,
+                        float* z_prior_full, float* z_prior_rf);
+/* N(0,1) / U[0,1)*scale fills, e.g. rf_w = randn(100,R), rf_b = 2*pi*rand(R) (losses.py:75-76) */
+int cpg_fill_normal(cpg_ctx* ctx, cpg_stream stream, uint64_t seed, uint32_t stream_id, int64_t n, float* out);
+int cpg_fill_uniform(cpg_ctx* ctx, cpg_stream stream, uint64_t seed, uint32_t stream_id, float scale, int64_t n,
+                     float* out);
+
+/* ---- decoding from (z, c) -------------------------------------------------------------------
+ * Replaces RNN_VAE.sample_G (models/model.py:225-385) + GRUDecoder.forward_sample
+ * (models/decoder.py:86-109) + Beam (models/Beam.py:56-132) as driven by generate_sentences
+ * (model.py:197-223) and sample_pipeline.decode_from_z (sample_pipeline.py:129-139).  Eval mode. */
+/* Beam search (beam_size must be 5, n_best <= 5).  out_tokens: int32 [n][n_best][L+1], -1 padded,
+ * hypothesis starts with <start>; out_len: [n][n_best]; out_score: [n][n_best] summed log-probs.
+ * Ties in top-k: larger score first, then lower flat (beam, word) index. */
+int cpg_beam_decode(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_vocab, int n, int L, const float* z,
+                    const float* c, int beam_size, int n_best, int* out_tokens, int* out_len, float* out_score);
+/* mode 1 = greedy (argmax), 2 = categorical (softmax(logits/temp), Philox uniforms keyed by seed).
+ * out_tokens: int32 [n][L+1] with <start> first and <pad> after <eos>; *out_steps = number of steps
+ * until every sample had finished (the reference truncates its output there, model.py:361-363). */
+int cpg_sample_decode(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_vocab, int n, int L, const float* z,
+                      const float* c, int mode, float temp, uint64_t seed, int* out_tokens, int* out_steps);
+
+/* ---- CNN attribute classifier forward (models/classifier.py:39-60, eval mode) ---------------- */
+/* conv weights [100][1][w][150] for w = 3,4,5; fc [2][300]; table_ws: 12*n_vocab*100 floats scratch. */
+int cpg_cnn_classifier_fwd(cpg_ctx* ctx, cpg_stream stream, const float* emb, const float* conv_w3, const float* conv_b3,
+                           const float* conv_w4, const float* conv_b4, const float* conv_w5, const float* conv_b5,
+                           const float* fc_w, const float* fc_b, int n_vocab, int B, int L, const int64_t* tokens,
+                           float* table_ws, float* logits);
+
+/* ---- CLaSS latent sampling (density_modeling.py) ---------------------------------------------
+ * Classifier spec, n_clf <= 4: coef[a] = DEVICE pointer to 100 doubles (the array of pointers itself
+ * is HOST memory), intercept[a], target_col[a] in {0,1} (column of predict_proba kept,
+ * sample_pipeline.py:290), f32[a] != 0 -> float32 score arithmetic (classifier fitted on float32). */
+/* parity mode of RejSampleBase.rejection_sample (density_modeling.py:50-60) after the draw:
+ * z [n][100] fp32 and u [n] fp64 are the reference's own draws.  probs: [n_clf][n] (may be NULL),
+ * accum [n] (may be NULL), accept uint8 [n] = (u < prod_a p_a). */
+int cpg_class_score_accept(cpg_ctx* ctx, cpg_stream stream, const float* z, const double* u, int64_t n, int n_clf,
+                           const double* const* coef, const double* intercept, const int* target_col, const int* f32,
+                           double* probs, double* accum, uint8_t* accept);
+/* perf mode: draw n samples with global indices [offset, offset+n) from the diag-GMM
+ * (mean, sd = sqrt(cov): fp32 [K][100]; cdf: cumulative weights [K]) with Philox(seed), score, accept.
+ * z_out / probs / accum / comp_out / n_accepted may be NULL.  Draws are i.i.d. (the reference returns
+ * them grouped by component, sklearn mixture/_base.py:461-511; same distribution). */
+int cpg_class_sample(cpg_ctx* ctx, cpg_stream stream, const float* gmm_mean, const float* gmm_sd, const float* gmm_cdf,
+                     int K, int n_clf, const double* const* coef, const double* intercept, const int* target_col,
+                     const int* f32, uint64_t seed, int64_t offset, int64_t n, float* z_out, double* probs,
+                     double* accum, uint8_t* accept, int* comp_out, unsigned long long* n_accepted);
+/* mogQ.logpdf batched (density_modeling.py:75-77): mean_t, prec_t fp64 [100][K] (component fastest),
+ * logw_norm[k] = log w_k - 50 log(2 pi) + 0.5 sum_d log prec_kd; out fp64 [n]. */
+int cpg_gmm_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, const double* mean_t,
+                   const double* prec_t, const double* logw_norm, int K, double* out);
+/* prior_logpdf batched (density_modeling.py:11-14) */
+int cpg_prior_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, double* out);
+
+/* ---- per-kernel timing (CUDA events on the launching stream; off by default) ------------------ */
+int cpg_profile_enable(int on);
+/* Synchronises the device; fills names[i*name_stride..], total_ms[i], counts[i] per kernel label in first-launch
+ * order and clears the records.  Returns the number of labels written (<= cap). */
+int cpg_profile_read(char* names, int name_stride, float* total_ms, int* counts, int cap);
+
 #ifdef __cplusplus
 }
 #endif
