@@ -67,6 +67,7 @@ def _signatures(L):
         'cpg_vae_param_layout': (I, [I, POINTER(I64), POINTER(I64)]),
         'cpg_wae_forward': (I, [P, P, P, I, I, I, POINTER(WaeInputs), P, P, P, P, I]),
         'cpg_wae_encode': (I, [P, P, P, I, I, I, P, P, P]),
+        'cpg_wae_decode_teacher': (I, [P, P, P, I, I, I, POINTER(WaeInputs), P, P]),
         'cpg_wae_backward': (I, [P, P, P, I, I, I, POINTER(WaeInputs), P, P, P, P, P]),
         'cpg_wae_train_step': (I, [P, P, P, P, P, P, I, I, I, POINTER(WaeInputs), POINTER(LossNoise),
                                    POINTER(TrainHparams), P, P, P, P, P]),

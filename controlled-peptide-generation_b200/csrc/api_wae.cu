@@ -549,4 +549,30 @@ int cpg_wae_train_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* gr
     return cpg_clip_adam_step(ctx, stream, params, grads, m, v, V, &h, gn);
 }
 
+int cpg_wae_decode_teacher(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int B, int L,
+                           const cpg_wae_inputs* in, const float* z, float* logits) {
+    int rc = check_dims(V, B, L);
+    if (rc) return rc;
+    if (!ctx || !params || !in || !in->tokens || !in->c || !z || !logits) { set_error("cpg_wae_decode_teacher: null argument"); return CPG_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = ensure_workspace(ctx, B, L, V, ctx->ws.R > 0 ? ctx->ws.R : 500, s))) return rc;
+    Workspace& w = ctx->ws;
+    launch_prep_tokens(s, in->tokens, in->word_drop, B, L, V, w.tok, w.tokd, w.tgt, ctx->ints, ctx->ints + 1);
+    launch_prep_weights(s, params, make_layout(V), V, w.d);
+    launch_make_zc(s, z, in->c, B, w.zc);
+    launch_sgemm(s, B, 3 * DEC_HP, DEC_HP, 1.f, w.zc, DEC_HP, 1, w.d.wizc_t, 3 * DEC_HP, 1, 0.f, w.rowbias,
+                 3 * DEC_HP, nullptr, 1, nullptr);
+    GruSeq q;
+    memset(&q, 0, sizeof(q));
+    q.tok = w.tokd; q.table = w.d.t_dec; q.rowbias = w.rowbias; q.whh_t = w.d.whh_t_dec; q.bhn = w.d.bhn_dec;
+    q.h0 = w.zc; q.hs = w.dec_hs;
+    launch_gru_fwd_dec(s, q, B, L);
+    DecOutArgs a = dec_out_args(ctx, in, V, B, L);
+    a.logits_out = logits;
+    a.part_nll = nullptr;
+    launch_dec_out(s, a, ctx->sm_count);
+    ctx->have_stash = false;
+    return check_launch("cpg_wae_decode_teacher");
+}
+
 }  // extern "C"

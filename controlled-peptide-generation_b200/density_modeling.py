@@ -1,0 +1,134 @@
+"""Latent density Q(z) + attribute-conditioned rejection sampling with the reference's names
+(density_modeling.py of IBM/controlled-peptide-generation).
+
+`mogQ` still FITS with scikit-learn (setup, not hot: reference density_modeling.py:64-73), but
+sampling, classifier scoring, the accept test and the log densities run on the GPU:
+  rejection_sample(n)            -> cpg_class_sample   (Philox draws; `mode='reference_rng'` replays the
+                                    numpy/sklearn stream on the host and scores on the GPU instead)
+  logpdf / logpdf_batch          -> cpg_gmm_logpdf
+  prior_logpdf / evaluate_nll    -> cpg_prior_logpdf / batched kernels (no per-point Python loop)
+"""
+import math
+
+import numpy as np
+import torch
+
+from cpg_b200 import _lib, sampling
+
+
+def _device(device=None):
+    return _lib.tensor_device(device)
+
+
+def prior_logpdf(z):
+    """log N(z; 0, I) for one point (reference density_modeling.py:11-14)."""
+    dev = _device()
+    return float(sampling.prior_logpdf(z.reshape(1, -1).float().to(dev))[0])
+
+
+class RejSampleBase:
+    seed = 1238
+    _draw_offset = 0
+
+    def init_attr_classifiers(self, attr_clfs, clf_targets):
+        """attr_clfs: ordered dict name -> fitted sklearn LogisticRegression (binary);
+        clf_targets: name -> column of predict_proba to keep (sample_pipeline.py:290)."""
+        self.attr_clfs = attr_clfs
+        self.clf_targets = clf_targets
+        self._spec = None
+
+    def _clf_list(self):
+        return [(name, np.asarray(clf.coef_).reshape(-1), np.asarray(clf.intercept_).reshape(-1),
+                 int(self.clf_targets[name])) for name, clf in self.attr_clfs.items()]
+
+    def _clf_spec(self, dev):
+        if getattr(self, '_spec', None) is None or self._spec_dev != dev:
+            self._spec = sampling.ClassifierSpec(self._clf_list(), dev)
+            self._spec_dev = dev
+        return self._spec
+
+    def score_clf(self, attr_name, z):
+        """P(attr == target | z) from the z-space classifier (reference density_modeling.py:43-48)."""
+        dev = _device()
+        name, coef, b, col = [c for c in self._clf_list() if c[0] == attr_name][0]
+        spec = sampling.ClassifierSpec([(name, coef, b, col)], dev)
+        zd = z.float().to(dev)
+        probs, _, _ = sampling.score_accept(zd, torch.zeros(zd.shape[0], dtype=torch.float64, device=dev), spec)
+        out = probs[0].cpu().numpy()
+        return out.astype(np.float32) if spec.all_f32 else out
+
+    def rejection_sample(self, n_samples, prefix='clfZ', mode='philox', device=None):
+        """-> (samples_z float32 [n,100] (CPU tensor), scores dict, accepted bool[n]) like the reference
+        (density_modeling.py:50-60).  mode='philox' (default) draws on the GPU; mode='reference_rng'
+        consumes numpy's global stream exactly as the reference does (z via sklearn, then the uniforms)
+        and only scores / accepts on the GPU -- bit-comparable with the reference under the same seed."""
+        dev = _device(device)
+        spec = self._clf_spec(dev)
+        if mode == 'reference_rng':
+            z = self.sample(n_samples).to(dev)
+            u = torch.from_numpy(np.random.uniform(size=n_samples)).to(dev)
+            probs, accum, accept = sampling.score_accept(z, u, spec)
+        else:
+            out = sampling.class_sample(self._gmm_device(dev), spec, n_samples, self.seed, self._draw_offset)
+            self._draw_offset += n_samples
+            z, probs, accum, accept = out['z'], out['probs'], out['accum'], out['accept']
+        cast = (lambda a: a.astype(np.float32)) if spec.all_f32 else (lambda a: a)
+        scores_z = {}
+        for i, name in enumerate(spec.names):
+            scores_z['{}_{}={}'.format(prefix, name, spec.target[i])] = cast(probs[i].cpu().numpy())
+        scores_z[prefix + '_prob_accum'] = cast(accum.cpu().numpy())
+        return z.cpu(), scores_z, accept.cpu().numpy().astype(bool)
+
+
+class mogQ(RejSampleBase):
+    def __init__(self, mu, logvar, n_components=10, z_num_samples=10, **mog_kwargs):
+        import sklearn.mixture
+        if mog_kwargs.get('covariance_type', 'full') != 'diag':
+            raise NotImplementedError("the GPU sampler implements covariance_type='diag' (sample_pipeline default)")
+        self.mu, self.logvar = mu, logvar
+        self.N, self.D = mu.shape
+        self.z = torch.cat([mu + (0.5 * logvar).exp() * torch.randn_like(logvar) for _ in range(z_num_samples)], dim=0)
+        self.n_components = n_components
+        self.mog = sklearn.mixture.GaussianMixture(n_components=n_components, **mog_kwargs)
+        self.mog.fit(self.z.cpu().numpy())
+        self._gmm = None
+        print('mog-{}. Converged: {} in {} iters, log likelihood lower bound: {:.4f}'.format(
+            n_components, self.mog.converged_, self.mog.n_iter_, self.mog.lower_bound_))
+
+    @classmethod
+    def from_fitted(cls, mog):
+        """Wrap an already fitted sklearn GaussianMixture (diag)."""
+        self = cls.__new__(cls)
+        self.mog, self.n_components, self._gmm = mog, mog.n_components, None
+        self.D = mog.means_.shape[1]
+        return self
+
+    def _gmm_device(self, dev):
+        if self._gmm is None or self._gmm.device != dev:
+            self._gmm = sampling.GmmDevice(self.mog.weights_, self.mog.means_, self.mog.covariances_, dev)
+        return self._gmm
+
+    def logpdf(self, x):
+        assert x.dim() == 1, 'expecting  single sample'
+        return float(self.logpdf_batch(x.view(1, -1))[0])
+
+    def logpdf_batch(self, x):
+        dev = _device()
+        return sampling.gmm_logpdf(self._gmm_device(dev), x.float().to(dev)).cpu().numpy()
+
+    def sample(self, n_samples):
+        """Host draw through sklearn / numpy's global RNG (reference density_modeling.py:79-80)."""
+        return torch.from_numpy(self.mog.sample(n_samples)[0]).float()
+
+
+def evaluate_nll(q, points):
+    """-> (nll under Q, nll under the prior) of z = mu + exp(.5 lv) * eps with ONE scalar eps per point
+    (reference density_modeling.py:99-108), batched on the GPU."""
+    mu, lv = points
+    n = mu.shape[0]
+    eps = torch.tensor([torch.randn(1).item() for _ in range(n)], dtype=mu.dtype)
+    z = mu + (0.5 * lv).exp() * eps[:, None]
+    dev = _device()
+    llq = q.logpdf_batch(z)
+    llp = sampling.prior_logpdf(z.float().to(dev)).cpu().numpy()
+    return -float(llq.sum()) / n, -float(llp.sum()) / n

@@ -1,0 +1,137 @@
+"""Phase-1 WAE/VAE training loop with the reference's entry point
+`train_vae(cfgv, model, dataset)` (train_vae.py:13-68 of IBM/controlled-peptide-generation).
+
+Default (cfg.b200.fused_step): each iteration is ONE call into libcpg_b200 --
+Philox noise -> forward -> the five losses -> BPTT -> clip_grad_norm_ -> Adam (with the
+duplicated-embedding semantics of `vae_params()`), all on the current CUDA stream; the host only
+moves the token batch (if the loader produced it on the host) and, on logging iterations, reads the
+16-float scalar block back (the reference reads nine `.item()`s every iteration).
+
+cfg.b200.fused_step = False runs the reference-style loop (model() -> losses.* -> loss.backward()
+-> clip_grad_norm_ -> torch.optim.Adam) over the same kernels through autograd.Functions.
+"""
+import sys
+
+import torch
+import torch.optim as optim
+
+import cfg
+import losses
+import utils
+from cpg_b200 import engine
+from models.mutils import save_model
+from tb_json_logger import log_value
+
+train = None   # alias set below (BASELINE.json calls the entry point "train_vae.train()")
+
+_SCALAR_LOG = (('z_mu_L1', 'z_mu_l1'), ('z_logvar', 'z_logvar'), ('z_logvar_L1', 'logvar_l1'),
+               ('z_logvar_KL_penalty', 'logvar_kl'), ('L_vae', 'loss'), ('L_vae_recon', 'recon'),
+               ('L_vae_kl', 'kl'), ('L_wae_mmd', 'mmd'), ('L_wae_mmdrf', 'mmdrf'))
+
+
+def _progress(rng):
+    try:
+        from tqdm import tqdm
+        return tqdm(rng, disable=None), tqdm.write
+    except Exception:  # noqa: BLE001
+        return rng, print
+
+
+def _log_sample(model, dataset, write):
+    log_sent, _, _ = model.generate_sentences(1, sample_mode='categorical')
+    write('Sample (cat T=1.0): "{}"'.format(dataset.idx2sentence(log_sent.squeeze())))
+    sys.stdout.flush()
+
+
+def _train_fused(cfgv, model, dataset):
+    st = model.bind_grads()
+    dev = st.device
+    wm = cfg.losses.wae_mmd
+    if wm.kernel != 'gaussian':
+        raise NotImplementedError("only the gaussian MMD kernel is built")
+    hp = engine.make_hparams(lr=cfgv.lr, clip_norm=cfgv.clip_grad, lambda_logvar_l1=cfgv.lambda_logvar_L1,
+                             lambda_logvar_kl=cfgv.lambda_logvar_KL, z_regu=cfgv.z_regu_loss, mmd_sigma=wm.sigma,
+                             rf_dim=wm.rf_dim, compute_full_mmd=True)
+    p_word, p_out = model.decoder.word_dropout.p, model.decoder.p_out_dropout
+    seed = int(cfg.b200.noise_seed)
+    every = max(1, int(cfg.b200.full_mmd_every))
+    noise = None
+    it_range, write = _progress(range(cfgv.s_iter, cfgv.s_iter + cfgv.n_iter + 1))
+    for it in it_range:
+        log_it = it % cfgv.cheaplog_every == 0 or it % cfgv.expsvlog_every == 0
+        inputs = dataset.next_batch('train_vae')
+        tokens = inputs.text
+        if not engine._lib._on_device(tokens):
+            tokens = tokens.to(dev, non_blocking=True)
+        B, L = tokens.shape
+        if noise is None or noise['eps'].shape[0] != B or noise['word_drop'].shape[1] != L:
+            noise = engine.alloc_noise(B, L, dev, rf_dim=wm.rf_dim, seed=seed)
+        hp.beta = float(utils.anneal(cfgv.beta, it))
+        hp.compute_full_mmd = 1 if (it % every == 0 or log_it) else 0
+        engine.fill_step_noise(noise, seed, it, p_word, p_out)
+        scal, _ = engine.train_step(st, tokens.contiguous(), noise, hp, p_out=p_out)
+        if log_it:
+            vals = scal.cpu()                                        # the only device->host read
+            for name, slot in _SCALAR_LOG:
+                log_value('train_' + name, float(vals[engine.SC[slot]]), it)
+            log_value('train_beta', hp.beta, it)
+            write('ITER {} TRAINING (phase 1). loss_vae: {:.4f}; loss_recon: {:.4f}; loss_kl: {:.4f}; '
+                  'loss_mmd: {:.4f}; Grad_norm: {:.4e} '.format(
+                      it, float(vals[engine.SC['loss']]), float(vals[engine.SC['recon']]),
+                      float(vals[engine.SC['kl']]), float(vals[engine.SC['mmd']]),
+                      float(vals[engine.SC['grad_norm']])))
+            _log_sample(model, dataset, write)
+        if it % cfgv.expsvlog_every == 0 and it > 0:
+            save_model(model, cfgv.chkpt_path.format(it))
+    return st
+
+
+def _train_modular(cfgv, model, dataset):
+    trainer = optim.Adam(model.vae_params(), lr=cfgv.lr)
+    it_range, write = _progress(range(cfgv.s_iter, cfgv.s_iter + cfgv.n_iter + 1))
+    for it in it_range:
+        log_it = it % cfgv.cheaplog_every == 0 or it % cfgv.expsvlog_every == 0
+        inputs = dataset.next_batch('train_vae')
+        tokens = inputs.text
+        if not engine._lib._on_device(tokens):
+            tokens = tokens.to(model._param_device())
+        beta = utils.anneal(cfgv.beta, it)
+        (z_mu, z_logvar), (z, c), dec_logits = model(tokens, q_c='prior', sample_z=1)
+        recon_loss = losses.recon_dec(tokens, dec_logits)
+        kl_loss = losses.kl_gaussianprior(z_mu, z_logvar)
+        wae_mmd_loss = losses.wae_mmd_gaussianprior(z.detach(), method='full_kernel')
+        wae_mmdrf_loss = losses.wae_mmd_gaussianprior(z, method='rf')
+        if cfgv.z_regu_loss == 'mmd':
+            raise NotImplementedError("z_regu_loss='mmd' needs the full-kernel MMD backward; use mmdrf or kl")
+        z_regu_loss = {'kl': kl_loss, 'mmdrf': wae_mmdrf_loss}[cfgv.z_regu_loss]
+        z_logvar_L1 = z_logvar.abs().sum(1).mean(0)
+        z_logvar_KL_penalty = losses.kl_gaussian_sharedmu(z_mu, z_logvar)
+        loss = recon_loss + beta * z_regu_loss + cfgv.lambda_logvar_L1 * z_logvar_L1 \
+            + cfgv.lambda_logvar_KL * z_logvar_KL_penalty
+        trainer.zero_grad()
+        loss.backward()
+        grad_norm = torch.nn.utils.clip_grad_norm_(model.vae_params(), cfgv.clip_grad)
+        trainer.step()
+        if log_it:
+            for name, val in (('z_mu_L1', z_mu.data.abs().mean()), ('z_logvar', z_logvar.data.mean()),
+                              ('z_logvar_L1', z_logvar_L1), ('z_logvar_KL_penalty', z_logvar_KL_penalty),
+                              ('L_vae', loss), ('L_vae_recon', recon_loss), ('L_vae_kl', kl_loss),
+                              ('L_wae_mmd', wae_mmd_loss), ('L_wae_mmdrf', wae_mmdrf_loss)):
+                log_value('train_' + name, val.item(), it)
+            log_value('train_beta', beta, it)
+            write('ITER {} TRAINING (phase 1). loss_vae: {:.4f}; loss_recon: {:.4f}; loss_kl: {:.4f}; '
+                  'loss_mmd: {:.4f}; Grad_norm: {:.4e} '.format(it, loss.item(), recon_loss.item(), kl_loss.item(),
+                                                               wae_mmd_loss.item(), float(grad_norm)))
+            _log_sample(model, dataset, write)
+        if it % cfgv.expsvlog_every == 0 and it > 0:
+            save_model(model, cfgv.chkpt_path.format(it))
+
+
+def train_vae(cfgv, model, dataset):
+    print('Training base vae ...')
+    if bool(cfg.b200.fused_step):
+        return _train_fused(cfgv, model, dataset)
+    return _train_modular(cfgv, model, dataset)
+
+
+train = train_vae

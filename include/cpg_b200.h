@@ -83,6 +83,9 @@ int cpg_wae_forward(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_
 /* encoder only (sample_pipeline.py:49-70 / build_index.py:93-118 extraction): mu, logvar */
 int cpg_wae_encode(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_vocab, int B, int L,
                    const int64_t* tokens, float* mu, float* logvar);
+/* teacher-forced decoder only (RNN_VAE.forward_decoder, models/model.py:128-133): logits [B,L,V] from given z, c */
+int cpg_wae_decode_teacher(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_vocab, int B, int L,
+                           const cpg_wae_inputs* in, const float* z, float* logits);
 /* Backward of the last cpg_wae_forward(keep_for_backward=1): upstream gradients (any may be NULL)
  * -> flat parameter gradient (overwritten).  This is what loss.backward() (train_vae.py:40) does. */
 int cpg_wae_backward(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_vocab, int B, int L,
