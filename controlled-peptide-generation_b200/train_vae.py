@@ -18,7 +18,7 @@ import torch.optim as optim
 import cfg
 import losses
 import utils
-from cpg_b200 import engine
+from cpg_b200 import engine, parallel
 from models.mutils import save_model
 from tb_json_logger import log_value
 
@@ -56,6 +56,7 @@ def _train_fused(cfgv, model, dataset):
     seed = int(cfg.b200.noise_seed)
     every = max(1, int(cfg.b200.full_mmd_every))
     noise = None
+    global_batch = None
     it_range, write = _progress(range(cfgv.s_iter, cfgv.s_iter + cfgv.n_iter + 1))
     for it in it_range:
         log_it = it % cfgv.cheaplog_every == 0 or it % cfgv.expsvlog_every == 0
@@ -68,8 +69,16 @@ def _train_fused(cfgv, model, dataset):
             noise = engine.alloc_noise(B, L, dev, rf_dim=wm.rf_dim, seed=seed)
         hp.beta = float(utils.anneal(cfgv.beta, it))
         hp.compute_full_mmd = 1 if (it % every == 0 or log_it) else 0
-        engine.fill_step_noise(noise, seed, it, p_word, p_out)
-        scal, _ = engine.train_step(st, tokens.contiguous(), noise, hp, p_out=p_out)
+        if parallel.is_distributed():
+            # shards of one global batch: rank-distinct noise rows, shared rf_w / rf_b, gradients all-reduced
+            if global_batch is None:
+                global_batch = parallel.global_batch_size(B, dev)
+            rank_seed = seed + 0x9E3779B97F4A7C15 * (1 + parallel.dist.get_rank()) % (1 << 63)
+            engine.fill_step_noise(noise, rank_seed, it, p_word, p_out)
+            scal = parallel.dp_train_step(st, tokens.contiguous(), noise, hp, p_out=p_out, global_batch=global_batch)
+        else:
+            engine.fill_step_noise(noise, seed, it, p_word, p_out)
+            scal, _ = engine.train_step(st, tokens.contiguous(), noise, hp, p_out=p_out)
         if log_it:
             vals = scal.cpu()                                        # the only device->host read
             for name, slot in _SCALAR_LOG:

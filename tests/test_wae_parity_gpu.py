@@ -176,6 +176,48 @@ def test_loss_ops_match_oracle(eng):
     np.testing.assert_allclose(dl.cpu().numpy(), lr.grad.numpy(), rtol=1e-4, atol=1e-8)
 
 
+def test_data_parallel_phases_virtual_ranks(eng):
+    """cpg_wae_step_phase1/phase2 on two shards (sequentially, one GPU) with the coupled block and the
+    gradients summed by hand == the fused single-process step on the whole batch."""
+    dev = torch.device('cuda')
+    B, cut = 37, 20
+    p = ow.random_params(V, seed=31)
+    tokens = ow.synthetic_tokens(B, V, seed=32).to(dev)
+    noise = dev_noise(ow.draw_noise(B, seed=33), dev)
+    full = eng.FlatState(V, dev)
+    full.load(p)
+    hp = eng.make_hparams(beta=1.2)
+    scal_full, _ = eng.train_step(full, tokens, noise, hp)
+    shards = []
+    for lo, hi in ((0, cut), (cut, B)):
+        shards.append((tokens[lo:hi].contiguous(),
+                       {k: (v[lo:hi].contiguous() if v.shape[0] == B else v) for k, v in noise.items()}))
+    st = eng.FlatState(V, dev)
+    st.load(p)
+    hp2 = eng.make_hparams(beta=1.2, global_batch=B)
+    coupled = sum(eng.step_phase1(st, tk, nz, hp2)[0] for tk, nz in shards)
+    grads = torch.zeros_like(st.grads)
+    nll = 0.0
+    for tk, nz in shards:
+        eng.step_phase1(st, tk, nz, hp2)                     # re-create this shard's stash
+        sc = eng.step_phase2(st, tk, nz, hp2, coupled)
+        grads += st.grads
+        nll += float(sc[eng.SC['nll_sum']])
+    st.grads.copy_(grads)
+    st.step = 1
+    hp2.adam_step = 1
+    gn = eng.clip_adam(st, hp2)
+    assert float(gn) == pytest.approx(float(scal_full[eng.SC['grad_norm']]), rel=1e-4)
+    assert nll / float(coupled[0]) == pytest.approx(float(scal_full[eng.SC['recon']]), rel=1e-5)
+    assert float(sc[eng.SC['mmdrf']]) == pytest.approx(float(scal_full[eng.SC['mmdrf']]), rel=1e-4)
+    assert float(sc[eng.SC['kl']]) == pytest.approx(float(scal_full[eng.SC['kl']]), rel=1e-5)
+    a, b = st.views(st.grads), full.views(full.grads)
+    for k in ow.UNIQUE_VAE_PARAMS:
+        scale = float(b[k].abs().max()) + 1e-12
+        np.testing.assert_allclose(a[k].cpu().numpy(), b[k].cpu().numpy(), rtol=1e-3, atol=1e-4 * scale, err_msg=k)
+    assert_params_close(st.views(st.params), full.views(full.params), b, 'dp')
+
+
 def test_module_level_backward_matches_oracle(eng):
     """cpg_wae_forward / cpg_wae_backward with arbitrary upstream gradients (autograd path)."""
     dev = torch.device('cuda')
