@@ -77,6 +77,11 @@ def gmm_logpdf(x, weights, means, covs_diag):
     point; batched here: log sum_k w_k N(x; mu_k, diag cov_k), fp64, using
     sklearn's expansion  sum(mu^2 prec) - 2 x.(mu prec) + x^2.prec."""
     x = np.asarray(x, dtype=np.float64)
+    # a mixture fitted on float32 z's has float32 parameters and sklearn then scores in float32
+    # (rel ~2e-7); the oracle evaluates the same expression with everything promoted to fp64
+    weights = np.asarray(weights, dtype=np.float64)
+    means = np.asarray(means, dtype=np.float64)
+    covs_diag = np.asarray(covs_diag, dtype=np.float64)
     prec = 1.0 / covs_diag
     d = means.shape[1]
     quad = (means ** 2 * prec).sum(1)[None, :] - 2.0 * (x @ (means * prec).T) + (x ** 2) @ prec.T

@@ -189,7 +189,9 @@ def test_perf_mode_sampler_statistics(mods):
     # the accept decision is consistent with the scores the kernel reports
     accum = out['accum'].cpu().numpy()
     oscores, _ = oc.rejection_accept(z, np.zeros(n), clfs)
-    np.testing.assert_allclose(accum, oscores['clfZ_prob_accum'], rtol=1e-4, atol=1e-7)
+    # float32 score path: 1 - expit(s) cancels for s >> 0, so tiny probabilities carry an absolute
+    # error of a few ulp(1) = 6e-8 whatever their size
+    np.testing.assert_allclose(accum, oscores['clfZ_prob_accum'], rtol=1e-4, atol=4e-7)
     assert abs(acc.mean() - accum.mean()) < 4 * np.sqrt(0.25 / n)
     # moments of the mixture
     mean_want = (w[:, None] * m).sum(0)
