@@ -91,6 +91,7 @@ def _signatures(L):
         'cpg_class_sample': (I, [P, P, P, P, P, I, I, P, P, P, P, c_uint64, I64, I64, P, P, P, P, P, P]),
         'cpg_gmm_logpdf': (I, [P, P, P, I64, P, P, P, I, P]),
         'cpg_prior_logpdf': (I, [P, P, P, I64, P]),
+        'cpg_set_option': (I, [c_char_p, I]),
         'cpg_profile_enable': (I, [I]),
         'cpg_profile_read': (I, [P, I, P, P, I]),
     }
@@ -206,3 +207,7 @@ def profile_read(cap=128):
         label = names.raw[i * stride:(i + 1) * stride].split(b'\0', 1)[0].decode()
         out.append((label, float(ms[i]), int(cnt[i])))
     return out
+
+
+def set_option(name, value):
+    check(lib().cpg_set_option(name.encode(), int(value)), 'cpg_set_option')

@@ -111,7 +111,7 @@ int cpg_mmd_full(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* z
     if ((ctx->base == nullptr || ctx->ws.B < B) && (rc = ensure_workspace(ctx, B, ctx->ws.L > 0 ? ctx->ws.L : 2,
                                                                       ctx->ws.V > 0 ? ctx->ws.V : 4,
                                                                       ctx->ws.R > 0 ? ctx->ws.R : 500, s))) return rc;
-    launch_mmd_full_simt(s, z, zp, B, sigma, ctx->ws.mmd_ws, out);
+    if ((rc = launch_mmd_full(s, z, zp, B, sigma, ctx->ws.mmd_ws, out))) return rc;
     return check_launch("cpg_mmd_full");
 }
 
@@ -133,6 +133,13 @@ int cpg_mmd_rf(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* zp,
         launch_sgemm(s, B, ZD, R, 1.f, w.rf_pre1, R, 1, rf_w, 1, R, 0.f, dz, ZD, nullptr, 1, nullptr);
     }
     return check_launch("cpg_mmd_rf");
+}
+
+int cpg_set_option(const char* name, int value) {
+    if (name == nullptr) { set_error("cpg_set_option: null name"); return CPG_EINVAL; }
+    if (strcmp(name, "mmd_tensor_core") == 0) { g_opt_mmd_tc = value; return CPG_OK; }
+    set_error(std::string("cpg_set_option: unknown option ") + name);
+    return CPG_EINVAL;
 }
 
 }  // extern "C"

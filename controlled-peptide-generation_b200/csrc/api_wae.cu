@@ -105,7 +105,7 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
     w.dz_rf = a.take<float>((size_t)B * ZD);
     w.lat_nparts = std::max(1, std::min(ceil_div(B, 8), 2 * sm));
     w.lat_part = a.take<float>((size_t)w.lat_nparts * 5); w.lat_sums = a.take<float>(8);
-    w.mmd_ws = a.take<float>(mmd_full_ws_floats(B)); w.mmd_out = a.take<float>(4); w.mmdrf_out = a.take<float>(4);
+    w.mmd_ws = a.take<float>(mmd_ws_floats(B)); w.mmd_out = a.take<float>(4); w.mmdrf_out = a.take<float>(4);
     // decoder output partials
     int parts = dec_out_parts(B, L, sm);
     w.do_part_w = a.take<float>((size_t)parts * VMAX * DEC_HP);
@@ -495,7 +495,7 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
         dz_rf = w.dz_rf;
     }
     if (hp->compute_full_mmd && nz->z_prior_full)
-        launch_mmd_full_simt(s, w.z, nz->z_prior_full, B, hp->mmd_sigma, w.mmd_ws, w.mmd_out);
+        if ((rc = launch_mmd_full(s, w.z, nz->z_prior_full, B, hp->mmd_sigma, w.mmd_ws, w.mmd_out))) return rc;
     LatentBwdArgs la;
     memset(&la, 0, sizeof(la));
     la.dz_rf = dz_rf;

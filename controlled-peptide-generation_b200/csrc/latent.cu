@@ -7,6 +7,7 @@
 // (full-kernel MMD, including the `H - torch.diag(H)` row-broadcast quirk).
 #include "kernels.h"
 #include "latent.h"
+#include <algorithm>
 
 namespace cpg {
 
@@ -308,6 +309,22 @@ void launch_mmd_full_simt(cudaStream_t s, const float* z, const float* zp, int N
     CPG_LAUNCH(k_mmd_rownorm, ndiag, 256, 0, s, z, zp, N, sigma, norms, diag_part);
     CPG_LAUNCH(k_mmd_gram, dim3(nt, nt), 256, 0, s, z, zp, norms, N, sigma, part);
     CPG_LAUNCH(k_mmd_final, 1, 256, 0, s, part, nt * nt, diag_part, ndiag, N, out);
+}
+
+int g_opt_mmd_tc = 1;
+size_t mmd_ws_floats(int N) {
+#ifdef CPG_EMU
+    return mmd_full_ws_floats(N);
+#else
+    return std::max(mmd_full_ws_floats(N), mmd_tc_ws_floats(N));
+#endif
+}
+int launch_mmd_full(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float* ws, float* out) {
+#ifndef CPG_EMU
+    if (g_opt_mmd_tc) return launch_mmd_full_tc(s, z, zp, N, sigma, ws, out);
+#endif
+    launch_mmd_full_simt(s, z, zp, N, sigma, ws, out);
+    return 0;
 }
 
 // total loss and logging scalars (train_vae.py:31-37,44-53) from the reduced sums (single-rank view)

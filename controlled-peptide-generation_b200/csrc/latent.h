@@ -43,6 +43,12 @@ void launch_rf_loss(cudaStream_t s, const float* sum1, const float* sum2, int R,
 void launch_rf_grad_prep(cudaStream_t s, float* pre, const float* rf_b, const float* coef, int B, int R, float sigma);
 size_t mmd_full_ws_floats(int N);
 void launch_mmd_full_simt(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float* ws, float* out);
+// tcgen05 / TMA version (mmd_tc.cu) and the dispatcher used by the API (option "mmd_tensor_core")
+size_t mmd_tc_ws_floats(int N);
+int launch_mmd_full_tc(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float* ws, float* out);
+size_t mmd_ws_floats(int N);
+int launch_mmd_full(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float* ws, float* out);
+extern int g_opt_mmd_tc;
 void launch_compose_scalars(cudaStream_t s, const ComposeArgs& a);
 void launch_int_to_float(cudaStream_t s, const int* src, float* dst, int n);
 

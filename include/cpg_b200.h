@@ -233,6 +233,10 @@ int cpg_gmm_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, c
 /* prior_logpdf batched (density_modeling.py:11-14) */
 int cpg_prior_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, double* out);
 
+/* ---- options ------------------------------------------------------------------------------------
+ * "mmd_tensor_core" (default 1): full-kernel MMD Gram tiles on tcgen05 (tf32) instead of the fp32 SIMT kernel. */
+int cpg_set_option(const char* name, int value);
+
 /* ---- per-kernel timing (CUDA events on the launching stream; off by default) ------------------ */
 int cpg_profile_enable(int on);
 /* Synchronises the device; fills names[i*name_stride..], total_ms[i], counts[i] per kernel label in first-launch

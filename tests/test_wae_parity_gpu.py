@@ -176,6 +176,26 @@ def test_loss_ops_match_oracle(eng):
     np.testing.assert_allclose(dl.cpu().numpy(), lr.grad.numpy(), rtol=1e-4, atol=1e-8)
 
 
+@pytest.mark.parametrize('n', [2, 63, 64, 65, 200, 1000])
+def test_mmd_full_tensor_core_vs_simt_vs_oracle(eng, n):
+    """tcgen05 (tf32) Gram tiles vs the fp32 SIMT kernel vs the oracle; 1e-4 relative on the loss."""
+    from cpg_b200 import _lib
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(n)
+    z = torch.randn(n, 100, generator=g) * 0.9 + 0.1
+    zp = torch.randn(n, 100, generator=g)
+    want = float(ow.mmd_full_kernel(z, zp, 7.0))
+    try:
+        _lib.set_option('mmd_tensor_core', 1)
+        tc_val = float(eng.mmd_full(z.to(dev), zp.to(dev), 7.0))
+        _lib.set_option('mmd_tensor_core', 0)
+        simt_val = float(eng.mmd_full(z.to(dev), zp.to(dev), 7.0))
+    finally:
+        _lib.set_option('mmd_tensor_core', 1)
+    assert simt_val == pytest.approx(want, rel=1e-5)
+    assert tc_val == pytest.approx(want, rel=1e-4)
+
+
 def test_data_parallel_phases_virtual_ranks(eng):
     """cpg_wae_step_phase1/phase2 on two shards (sequentially, one GPU) with the coupled block and the
     gradients summed by hand == the fused single-process step on the whole batch."""
