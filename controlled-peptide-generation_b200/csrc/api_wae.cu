@@ -113,7 +113,7 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
     w.do_part_nll = a.take<float>(parts);
     w.nll_sum = a.take<float>(4);
     // weight-gradient partials
-    int ws_ = wgrad_splits(B, L, sm);
+    int ws_ = std::max(wgrad_splits(B, L, sm), wgrad_tc_splits(sm));
     w.wg_part = a.take<float>((size_t)ws_ * 3 * DEC_HP * DEC_HP);
     int ds_ = dtable_splits(B, L, sm);
     w.dt_part = a.take<float>((size_t)ds_ * V * 4 * DEC_HP);
@@ -255,9 +255,12 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     }
     launch_gru_bwd_enc(s, enc, B, L);
     // recurrent weight gradients
-    launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[0], w.enc_hs[0], nullptr, B, L, sm, w.wg_part, grads + lay.off[P_ENC_WHH_F]);
-    launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[1], w.enc_hs[1], nullptr, B, L, sm, w.wg_part, grads + lay.off[P_ENC_WHH_R]);
-    launch_wgrad_hh(s, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, B, L, sm, w.wg_part, grads + lay.off[P_DEC_WHH]);
+    launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[0], w.enc_hs[0], nullptr, B, L, sm, w.wg_part, grads + lay.off[P_ENC_WHH_F],
+                    w.gemm_ws, w.gemm_splits);
+    launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[1], w.enc_hs[1], nullptr, B, L, sm, w.wg_part, grads + lay.off[P_ENC_WHH_R],
+                    w.gemm_ws, w.gemm_splits);
+    launch_wgrad_hh(s, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, B, L, sm, w.wg_part, grads + lay.off[P_DEC_WHH],
+                    w.gemm_ws, w.gemm_splits);
     // token-table gradients -> embedding / W_ih / biases
     launch_dtable(s, ENC_H, w.enc_dg[0], w.tok, B, L, 0, V, sm, w.dt_part, w.dT_enc[0]);
     launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part, w.dT_enc[1]);

@@ -1,119 +1,217 @@
-// Decoder output layer: out-dropout -> Linear(102 -> V) -> softmax cross-entropy,
-// forward and backward fused, one warp per (sample, step) row and one lane per
-// vocabulary class (V <= 32).
+// Decoder output layer: out-dropout -> Linear(102 -> V) -> softmax cross-entropy, forward and
+// backward fused over 64-row tiles of the [B*L, 104] hidden-state matrix.
 //
 // Replaces nn.Dropout + nn.Linear at models/decoder.py:43-45,83 and
 // F.cross_entropy(..., reduction='mean', ignore_index=PAD) at losses.py:27-30:
 //   nll_row = logsumexp(logits) - logits[tgt]   (0 where tgt == <pad>)
 //   dlogits = (softmax - onehot(tgt)) / N_tok    (0 where tgt == <pad>)
 // with N_tok the number of non-<pad> targets of the WHOLE (global) batch.
+//
+// Per tile, three small contractions run out of shared memory with float4 operands:
+//   logits = hd W^T (64x32x104),  dhd = dlogits W (64x104x32),  dW += dlogits^T hd (32x104x64)
+// dW / db / nll accumulate in registers across the tiles of a persistent CTA and leave as one
+// partial per CTA (ordered reduction afterwards, no float atomics).
 #include "kernels.h"
 #include "dec_out.h"
 
 namespace cpg {
 
-constexpr int DO_WARPS = 4;
-constexpr int WSTR = DEC_HP + 1;      // odd stride: lane v reading W[v][j] is conflict free
+constexpr int DT = 64;                 // rows per tile
+constexpr int DSTR = 108;              // padded row stride (floats) of the hd and W tiles
+constexpr int LSTR = 36;               // padded row stride of the dlogits tile
+constexpr int DO_THREADS = 256;
+constexpr int NF4 = DEC_HP / 4;        // 26 float4 per hidden row
 
-__global__ void __launch_bounds__(DO_WARPS * 32)
+__global__ void __launch_bounds__(DO_THREADS, 2)
 k_dec_out(DecOutArgs a) {
-    __shared__ float Ws[VMAX * WSTR];
-    __shared__ float hd_s[DO_WARPS][DEC_HP];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    CPG_DYN_SMEM(float, smem);                              // 57 KB: above the 48 KB static limit
+    float* Ws = smem;                                       // [VMAX][DSTR]
+    float* hd_s = Ws + VMAX * DSTR;                         // [DT][DSTR]
+    float* dl_s = hd_s + DT * DSTR;                         // [DT][LSTR]
+    unsigned char* keep_s = reinterpret_cast<unsigned char*>(dl_s + DT * LSTR);   // [DT][DEC_HP]
+    __shared__ float red_nll[DO_THREADS / 32];
+    const int tid = threadIdx.x;
     const int V = a.V;
-    for (int i = threadIdx.x; i < VMAX * DEC_HP; i += blockDim.x) {
-        int v = i / DEC_HP, j = i % DEC_HP;
-        Ws[v * WSTR + j] = a.fc_w[i];
-    }
-    __syncthreads();
-    const float bias = (lane < V) ? a.fc_b[lane] : 0.f;
-    const float inv_ntok = (a.ntok != nullptr && *a.ntok > 0.f) ? 1.0f / *a.ntok : 0.f;
-    const bool want_grad = a.dh_out != nullptr;
-
-    float accW[VMAX][4];
-    float accb = 0.f, accn = 0.f;
-#pragma unroll
-    for (int v = 0; v < VMAX; ++v)
-#pragma unroll
-        for (int m = 0; m < 4; ++m) accW[v][m] = 0.f;
-
     const int nrows = a.B * a.L;
-    const int gw = blockIdx.x * DO_WARPS + warp, nw = gridDim.x * DO_WARPS;
-    for (int row = gw; row < nrows; row += nw) {
-        float hd[4], ks[4];
+    const bool want_grad = a.dh_out != nullptr;
+    const bool has_mask = a.out_keep != nullptr;
+    const float inv_ntok = (a.ntok != nullptr && *a.ntok > 0.f) ? 1.0f / *a.ntok : 0.f;
+
+    for (int i = tid; i < VMAX * DEC_HP; i += DO_THREADS) Ws[(i / DEC_HP) * DSTR + (i % DEC_HP)] = a.fc_w[i];
+    // phase B / C mapping: 2 rows x 4 classes per thread
+    const int rp = tid >> 3, vq = tid & 7;
+    float bias4[4];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            int j = lane + 32 * m;
-            float h = 0.f, k = 1.f;
-            if (j < DEC_HP) h = a.hs[(size_t)row * DEC_HP + j];
-            if (a.out_keep != nullptr) k = (j < DEC_H) ? (a.out_keep[(size_t)row * DEC_H + j] ? a.keep_scale : 0.f) : 0.f;
-            hd[m] = h * k;
-            ks[m] = k;
-            if (j < DEC_HP) hd_s[warp][j] = hd[m];
-        }
-        __syncwarp();
-        float logit = -INFINITY;
-        if (lane < V) {
-            float s = 0.f;
-            const float* w = Ws + lane * WSTR;
-#pragma unroll 8
-            for (int j = 0; j < DEC_H; ++j) s = fmaf(hd_s[warp][j], w[j], s);
-            logit = s + bias;
-            if (a.logits_out != nullptr) a.logits_out[(size_t)row * V + lane] = logit;
-        }
-        float dl = 0.f;
-        if (a.fused_ce) {
-            const float mx = warp_max(logit);
-            const float e = (lane < V) ? expf(logit - mx) : 0.f;
-            const float se = warp_sum(e);
-            const int tg = a.tgt[row];
-            const float lt = __shfl_sync(0xffffffffu, logit, tg);
-            if (tg != PAD) {
-                accn += (mx + logf(se)) - lt;                    // every lane holds the same value
-                dl = (e / se - (lane == tg ? 1.f : 0.f)) * inv_ntok;
+    for (int c = 0; c < 4; ++c) bias4[c] = (vq * 4 + c < V) ? a.fc_b[vq * 4 + c] : 0.f;
+    // phase E mapping: class v, float4 columns jq + 8 i
+    const int ev = tid >> 3, ejq = tid & 7;
+    float4 accW[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) accW[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float accb = 0.f, accn = 0.f;
+
+    const int ntiles = ceil_div(nrows, DT);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = tile * DT;
+        __syncthreads();                                   // previous tile fully consumed (and Ws visible)
+        // ---- A) stage hd = h * keep * scale (and the keep bytes) for 64 rows
+        for (int idx = tid; idx < DT * NF4; idx += DO_THREADS) {
+            const int r = idx / NF4, f = idx % NF4;
+            const int row = row0 + r;
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned char k4[4] = {0, 0, 0, 0};
+            if (row < nrows) {
+                h = ld4(a.hs + (size_t)row * DEC_HP + f * 4);
+                float hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = f * 4 + c;
+                    unsigned char k = j < DEC_H ? (has_mask ? a.out_keep[(size_t)row * DEC_H + j] : 1) : 0;
+                    k4[c] = k;
+                    hv[c] = k ? (has_mask ? hv[c] * a.keep_scale : hv[c]) : 0.f;
+                }
+                h = make_float4(hv[0], hv[1], hv[2], hv[3]);
             }
-        } else if (a.dlogits_in != nullptr && lane < V) {
-            dl = a.dlogits_in[(size_t)row * V + lane];
+            st4(hd_s + r * DSTR + f * 4, h);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) keep_s[r * DEC_HP + f * 4 + c] = k4[c];
         }
-        if (want_grad) {
-            float dhd[4] = {0.f, 0.f, 0.f, 0.f};
+        __syncthreads();
+        // ---- B) logits for rows (2 rp, 2 rp + 1), classes 4 vq .. 4 vq + 3
+        float lg[2][4];
 #pragma unroll
-            for (int v = 0; v < VMAX; ++v) {
-                if (v < V) {
-                    const float dv = __shfl_sync(0xffffffffu, dl, v);
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        int j = lane + 32 * m;
-                        float w = (j < DEC_HP) ? Ws[v * WSTR + j] : 0.f;
-                        dhd[m] = fmaf(dv, w, dhd[m]);
-                        accW[v][m] = fmaf(dv, hd[m], accW[v][m]);
+            for (int c = 0; c < 4; ++c) lg[i][c] = 0.f;
+#pragma unroll 2
+        for (int f = 0; f < NF4; ++f) {
+            const float4 h0 = ld4(hd_s + (2 * rp) * DSTR + f * 4);
+            const float4 h1 = ld4(hd_s + (2 * rp + 1) * DSTR + f * 4);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4 w = ld4(Ws + (vq * 4 + c) * DSTR + f * 4);
+                lg[0][c] = fmaf(h0.x, w.x, fmaf(h0.y, w.y, fmaf(h0.z, w.z, fmaf(h0.w, w.w, lg[0][c]))));
+                lg[1][c] = fmaf(h1.x, w.x, fmaf(h1.y, w.y, fmaf(h1.z, w.z, fmaf(h1.w, w.w, lg[1][c]))));
+            }
+        }
+        // ---- C) softmax / CE per row (8 consecutive lanes hold the 32 classes of a row)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = 2 * rp + i, row = row0 + r;
+            float dl[4] = {0.f, 0.f, 0.f, 0.f};
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                lg[i][c] = (vq * 4 + c < V) ? lg[i][c] + bias4[c] : -INFINITY;
+                mx = fmaxf(mx, lg[i][c]);
+            }
+            if (row < nrows && a.logits_out != nullptr) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (vq * 4 + c < V) a.logits_out[(size_t)row * V + vq * 4 + c] = lg[i][c];
+            }
+            if (a.fused_ce) {
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+                float e[4], se = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { e[c] = (vq * 4 + c < V) ? expf(lg[i][c] - mx) : 0.f; se += e[c]; }
+                se += __shfl_xor_sync(0xffffffffu, se, 1);
+                se += __shfl_xor_sync(0xffffffffu, se, 2);
+                se += __shfl_xor_sync(0xffffffffu, se, 4);
+                const int tg = row < nrows ? a.tgt[row] : PAD;
+                float lt = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (vq * 4 + c == tg) lt = lg[i][c];
+                lt += __shfl_xor_sync(0xffffffffu, lt, 1);
+                lt += __shfl_xor_sync(0xffffffffu, lt, 2);
+                lt += __shfl_xor_sync(0xffffffffu, lt, 4);
+                if (tg != PAD) {
+                    if (vq == 0) accn += (mx + logf(se)) - lt;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        dl[c] = (vq * 4 + c < V) ? (e[c] / se - (vq * 4 + c == tg ? 1.f : 0.f)) * inv_ntok : 0.f;
+                }
+            } else if (a.dlogits_in != nullptr && row < nrows) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (vq * 4 + c < V) dl[c] = a.dlogits_in[(size_t)row * V + vq * 4 + c];
+            }
+            st4(dl_s + r * LSTR + vq * 4, make_float4(dl[0], dl[1], dl[2], dl[3]));
+        }
+        if (!want_grad) continue;
+        __syncthreads();
+        // ---- D) dh = (dlogits W) * keep * scale : row r = tid / 4, float4 columns jq + 4 i
+        {
+            const int r = tid >> 2, jq = tid & 3, row = row0 + r;
+            float4 acc[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int v = 0; v < V; ++v) {
+                const float d = dl_s[r * LSTR + v];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    const int f = jq + 4 * i;
+                    if (f < NF4) {
+                        const float4 w = ld4(Ws + v * DSTR + f * 4);
+                        acc[i].x = fmaf(d, w.x, acc[i].x); acc[i].y = fmaf(d, w.y, acc[i].y);
+                        acc[i].z = fmaf(d, w.z, acc[i].z); acc[i].w = fmaf(d, w.w, acc[i].w);
                     }
                 }
             }
+            if (row < nrows) {
+                const float sc = has_mask ? a.keep_scale : 1.0f;
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                int j = lane + 32 * m;
-                if (j < DEC_HP) a.dh_out[(size_t)row * DEC_HP + j] = dhd[m] * ks[m];
+                for (int i = 0; i < 7; ++i) {
+                    const int f = jq + 4 * i;
+                    if (f < NF4) {
+                        const unsigned char* k = keep_s + r * DEC_HP + f * 4;
+                        st4(a.dh_out + (size_t)row * DEC_HP + f * 4,
+                            make_float4(k[0] ? acc[i].x * sc : 0.f, k[1] ? acc[i].y * sc : 0.f,
+                                        k[2] ? acc[i].z * sc : 0.f, k[3] ? acc[i].w * sc : 0.f));
+                    }
+                }
             }
-            accb += dl;
         }
-        __syncwarp();
-    }
-    if (want_grad) {
-        float* pw = a.part_w + (size_t)gw * VMAX * DEC_HP;
+        // ---- E) dW[v][:] += sum_r dlogits[r][v] hd[r][:],  db[v] += sum_r dlogits[r][v]
+        for (int r = 0; r < DT; ++r) {
+            const float d = dl_s[r * LSTR + ev];
 #pragma unroll
-        for (int v = 0; v < VMAX; ++v)
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                int j = lane + 32 * m;
-                if (j < DEC_HP) pw[v * DEC_HP + j] = accW[v][m];
+            for (int i = 0; i < 4; ++i) {
+                const int f = ejq + 8 * i;
+                if (f < NF4) {
+                    const float4 h = ld4(hd_s + r * DSTR + f * 4);
+                    accW[i].x = fmaf(d, h.x, accW[i].x); accW[i].y = fmaf(d, h.y, accW[i].y);
+                    accW[i].z = fmaf(d, h.z, accW[i].z); accW[i].w = fmaf(d, h.w, accW[i].w);
+                }
             }
-        a.part_b[(size_t)gw * VMAX + lane] = accb;
+            if (ejq == 0) accb += d;
+        }
     }
-    if (a.part_nll != nullptr && lane == 0) a.part_nll[gw] = accn;
+    // ---- per-CTA partials
+    if (want_grad) {
+        float* pw = a.part_w + (size_t)blockIdx.x * VMAX * DEC_HP;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = ejq + 8 * i;
+            if (f < NF4) st4(pw + ev * DEC_HP + f * 4, accW[i]);
+        }
+        if (ejq == 0) a.part_b[(size_t)blockIdx.x * VMAX + ev] = accb;
+    }
+    if (a.part_nll != nullptr) {
+        accn = warp_sum(accn);
+        if ((tid & 31) == 0) red_nll[tid >> 5] = accn;
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.f;
+            for (int w = 0; w < DO_THREADS / 32; ++w) s += red_nll[w];
+            a.part_nll[blockIdx.x] = s;
+        }
+    }
 }
 
-// ordered reduction of the per-warp partials into dW_fc [V][102], db_fc [V], sum nll
+// ordered reduction of the per-CTA partials into dW_fc [V][102], db_fc [V], sum nll
 __global__ void k_dec_out_reduce(const float* __restrict__ part_w, const float* __restrict__ part_b,
                                  const float* __restrict__ part_nll, int nparts, int V,
                                  float* __restrict__ dW, float* __restrict__ db, float* __restrict__ nll_sum) {
@@ -136,14 +234,14 @@ __global__ void k_dec_out_reduce(const float* __restrict__ part_w, const float* 
 }
 
 int dec_out_parts(int B, int L, int sm_count) {
-    int rows = B * L;
-    int ctas = min(ceil_div(rows, DO_WARPS), max(1, sm_count));
-    return ctas * DO_WARPS;
+    int tiles = ceil_div(B * L, DT);
+    return max(1, min(tiles, 2 * max(1, sm_count)));
 }
 
 void launch_dec_out(cudaStream_t s, const DecOutArgs& a, int sm_count) {
-    int parts = dec_out_parts(a.B, a.L, sm_count);
-    CPG_LAUNCH(k_dec_out, parts / DO_WARPS, DO_WARPS * 32, 0, s, a);
+    const size_t smem = (size_t)(VMAX * DSTR + DT * DSTR + DT * LSTR) * sizeof(float) + DT * DEC_HP;
+    CPG_SET_MAX_SMEM(k_dec_out, smem);
+    CPG_LAUNCH(k_dec_out, dec_out_parts(a.B, a.L, sm_count), DO_THREADS, smem, s, a);
 }
 
 void launch_dec_out_reduce(cudaStream_t s, const DecOutArgs& a, int sm_count, float* dW, float* db, float* nll_sum) {

@@ -19,7 +19,7 @@ constexpr int TCK = 128;              // padded K (floats); 4 swizzle atoms of 3
 constexpr int TC_KSTEPS = 13;         // ceil(100 / 8) MMAs of K = 8
 
 int make_tmap_2d_f32_sw128(CUtensorMap* out, const float* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
-                           uint32_t box_rows) {
+                           uint32_t box_rows, bool atom32) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -38,7 +38,8 @@ int make_tmap_2d_f32_sw128(CUtensorMap* out, const float* base, uint64_t cols, u
     cuuint32_t box[2] = {32, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));

@@ -96,6 +96,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
 //   K-major  : rows = M/N index, 128 B of K per row; 8-row groups 1024 B apart (SBO)
 //   MN-major : rows = K index, 128 B of M/N per row; 8-row (K) groups 1024 B apart (SBO); the next
 //              128-byte chunk of M/N lives LBO bytes further
+// layout_type: 2 = SWIZZLE_128B (16-byte atoms; K-major operands of any type, MN-major 16-bit types),
+//              1 = SWIZZLE_128B_BASE32B (32-byte atoms; the ONLY layout for MN-major tf32 operands:
+//                  32 floats of M/N per 128-byte row, 4-row (K) groups SBO bytes apart, next 128-byte chunk of M/N at LBO)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
@@ -121,7 +133,7 @@ __device__ __forceinline__ float to_tf32_rn(float x) {
 
 // host: 2-D fp32 row-major tensor map with 128-byte swizzle, box = {32 floats, box_rows}
 int make_tmap_2d_f32_sw128(CUtensorMap* out, const float* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
-                           uint32_t box_rows);
+                           uint32_t box_rows, bool atom32 = false);   // atom32: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
 
 }  // namespace cpg
 #endif  // CPG_EMU

@@ -18,8 +18,14 @@ struct InputGradArgs {
 
 int wgrad_splits(int B, int L, int sm_count);
 int dtable_splits(int B, int L, int sm_count);
+// gemm_ws / gemm_splits: split-K scratch of launch_sgemm (used for the decoder's h0 rows on the tensor-core path)
 void launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0, int B, int L,
-                     int sm_count, float* part, float* dW);
+                     int sm_count, float* part, float* dW, float* gemm_ws, int gemm_splits);
+// tcgen05 version (wgrad_tc.cu): partials [nsplit][3*HP][HP] over all rows with s > 0 (h0 rows excluded)
+int wgrad_tc_splits(int sm_count);
+int launch_wgrad_hh_tc(cudaStream_t s, int HP, const float* dg, const float* hs, int B, int L, int sm_count,
+                       float* part, int* nsplit_out);
+extern int g_opt_wgrad_tc;
 void launch_dtable(cudaStream_t s, int HP, const float* dg, const uint8_t* tok, int B, int L, int reverse, int V,
                    int sm_count, float* part, float* dT);
 void launch_input_grads(cudaStream_t s, const InputGradArgs& a);

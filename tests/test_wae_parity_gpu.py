@@ -196,6 +196,36 @@ def test_mmd_full_tensor_core_vs_simt_vs_oracle(eng, n):
     assert tc_val == pytest.approx(want, rel=1e-4)
 
 
+@pytest.mark.parametrize('batch', [3, 50, 333])
+def test_wgrad_tensor_core_vs_simt(eng, batch):
+    """dW_hh from the tcgen05 split-K contraction (tf32, round-to-nearest operands) vs the fp32 SIMT kernel."""
+    from cpg_b200 import _lib
+    dev = torch.device('cuda')
+    p = ow.random_params(V, seed=71)
+    tokens = ow.synthetic_tokens(batch, V, seed=72).to(dev)
+    noise = dev_noise(ow.draw_noise(batch, seed=73), dev)
+    grads = {}
+    try:
+        for flag in (0, 2):                       # 2 = force the tensor-core path whatever the batch
+            _lib.set_option('wgrad_tensor_core', flag)
+            st = eng.FlatState(V, dev)
+            st.load(p)
+            eng.train_step(st, tokens, noise, eng.make_hparams(clip_norm=1e9))
+            grads[flag] = {k: v.clone() for k, v in st.views(st.grads).items()}
+    finally:
+        _lib.set_option('wgrad_tensor_core', 1)
+    # tf32 operand rounding (2^-11 relative, unbiased) over a B*25-long reduction: noise relative to the
+    # largest entry shrinks like 1/sqrt(rows); 5e-4 covers B=3 (75 rows), B=333 is ~10x tighter
+    tol = 5e-4 if batch < 100 else 1e-4
+    for k in ('encoder.rnn.weight_hh_l0', 'encoder.rnn.weight_hh_l0_reverse', 'decoder.rnn.weight_hh_l0'):
+        a, b = grads[2][k].cpu().numpy(), grads[0][k].cpu().numpy()
+        scale = float(np.abs(b).max()) + 1e-12
+        np.testing.assert_allclose(a, b, rtol=1e-3, atol=tol * scale, err_msg=k)
+    for k in ow.UNIQUE_VAE_PARAMS:
+        if 'weight_hh' not in k:
+            assert torch.equal(grads[0][k], grads[2][k]), k
+
+
 def test_data_parallel_phases_virtual_ranks(eng):
     """cpg_wae_step_phase1/phase2 on two shards (sequentially, one GPU) with the coupled block and the
     gradients summed by hand == the fused single-process step on the whole batch."""
