@@ -87,6 +87,9 @@ def kernel_work(B, L=SEQ_LEN, V=N_VOCAB):
         'k_gru_bwd_dec': (2 * B * L * Hd * 3 * Hd, B * L * (6 * HP + 4 * HP) * f4),
         'k_wgrad_hh_enc': (2 * B * L * He * 3 * He, B * L * (4 * He) * f4),
         'k_wgrad_hh_dec': (2 * B * L * Hd * 3 * Hd, B * L * (4 * HP) * f4),
+        'k_wgrad_hh_tc_enc': (2 * B * L * He * 3 * He, B * L * (4 * He) * f4),      # 3 gate planes + h read once
+        'k_wgrad_hh_tc_dec': (2 * B * L * Hd * 3 * Hd, B * L * (4 * HP) * f4),
+        'k_mmd_gram_tc': (3 * 2 * B * B * 100, 2 * B * 128 * f4),
         'k_dec_out': (2 * 3 * B * L * Hd * V, B * L * (2 * HP * f4 + Hd)),
         'k_mmd_gram': (3 * 2 * B * B * 100, 2 * B * 100 * f4),
         'k_dtable': (B * L * 4 * HP, B * L * 4 * HP * f4),
@@ -190,7 +193,15 @@ def run_ours(args):
     else:
         roof = {'bound': 'hbm', 'achieved': round(gbs, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                 'frac': round(hbm_frac, 5)}
-    roof.update({'kernel': dom, 'kernel_ms': round(per_kernel[dom][0], 4), 'launches_per_step': per_kernel[dom][1],
+    per_kernel_roof = {}
+    for name, (kms, per_step) in per_kernel.items():
+        if name in work and kms > 0:
+            f, nb = work[name]
+            per_kernel_roof[name] = {'ms': round(kms, 4), 'launches_per_step': per_step,
+                                     'tflops': round(f / (kms / 1e3) / 1e12, 2), 'gbs': round(nb / (kms / 1e3) / 1e9, 1),
+                                     'frac_tensor': round(f / (kms / 1e3) / 1e12 / peaks['bf16_tflops_sustained'], 4),
+                                     'frac_hbm': round(nb / (kms / 1e3) / 1e9 / peaks['hbm_gbs'], 4)}
+    roof.update({'per_kernel': per_kernel_roof, 'kernel': dom, 'kernel_ms': round(per_kernel[dom][0], 4), 'launches_per_step': per_kernel[dom][1],
                  'share_of_step': round(step_share[dom] / sum(step_share.values()), 4), 'traffic': None,
                  'peak_source': peak_src + ' (MEASURED_PEAKS.json, sustained)' if peak_src == 'measured' else peak_src,
                  'note': 'fp32 SIMT kernel: FLOP/s shown against the bf16 tensor peak; see DESIGN.md',
@@ -310,8 +321,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')

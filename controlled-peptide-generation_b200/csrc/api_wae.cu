@@ -330,6 +330,7 @@ int cpg_create(cpg_ctx** out, int device) {
         return CPG_ECUDA;
     }
     c->sm_count = prop.multiProcessorCount;
+    g_sm_count = c->sm_count;
 #endif
     void* p = nullptr;
     if (dev_alloc(&p, 64) != 0) { set_error("cpg_create: allocation failed"); delete c; return CPG_ENOMEM; }

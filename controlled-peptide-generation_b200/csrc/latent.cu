@@ -312,6 +312,7 @@ void launch_mmd_full_simt(cudaStream_t s, const float* z, const float* zp, int N
 }
 
 int g_opt_mmd_tc = 1;
+int g_sm_count = 148;
 size_t mmd_ws_floats(int N) {
 #ifdef CPG_EMU
     return mmd_full_ws_floats(N);
@@ -321,7 +322,8 @@ size_t mmd_ws_floats(int N) {
 }
 int launch_mmd_full(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float* ws, float* out) {
 #ifndef CPG_EMU
-    if (g_opt_mmd_tc) return launch_mmd_full_tc(s, z, zp, N, sigma, ws, out);
+    if (g_opt_mmd_tc == 1) return launch_mmd_full_tc2(s, z, zp, N, sigma, g_sm_count, ws, out);   // persistent, pipelined
+    if (g_opt_mmd_tc) return launch_mmd_full_tc(s, z, zp, N, sigma, ws, out);                       // one tile per CTA
 #endif
     launch_mmd_full_simt(s, z, zp, N, sigma, ws, out);
     return 0;

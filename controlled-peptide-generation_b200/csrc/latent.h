@@ -48,7 +48,10 @@ size_t mmd_tc_ws_floats(int N);
 int launch_mmd_full_tc(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float* ws, float* out);
 size_t mmd_ws_floats(int N);
 int launch_mmd_full(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float* ws, float* out);
-extern int g_opt_mmd_tc;
+int launch_mmd_full_tc2(cudaStream_t s, const float* z, const float* zp, int N, float sigma, int sm_count, float* ws,
+                        float* out);
+extern int g_opt_mmd_tc;     // 0 = fp32 SIMT, 1 = persistent tcgen05 (default), 3 = one-tile-per-CTA tcgen05
+extern int g_sm_count;
 void launch_compose_scalars(cudaStream_t s, const ComposeArgs& a);
 void launch_int_to_float(cudaStream_t s, const int* src, float* dst, int n);
 

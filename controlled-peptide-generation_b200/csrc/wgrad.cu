@@ -133,11 +133,22 @@ __global__ void k_dtable(const float* __restrict__ dg, const uint8_t* __restrict
     for (int v = 0; v < V; ++v) acc[v * HP4 + c] = 0.f;
     const int nrows = B * L;
     const int rbeg = blockIdx.x * rows_per_split, rend = min(nrows, rbeg + rows_per_split);
-    for (int row = rbeg; row < rend; ++row) {
-        int b = row / L, s = row % L;
-        int t = reverse ? (L - 1 - s) : s;
-        int tk = tok[b * L + t];
-        acc[tk * HP4 + c] += dg[(size_t)row * HP4 + c];
+    // 8 rows per trip: the global loads are issued together (independent), then the shared-memory
+    // read-modify-writes (which depend on the token) follow -- otherwise every row pays a full DRAM latency
+    for (int row = rbeg; row < rend; row += 8) {
+        float v[8];
+        int tk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = row + i;
+            const bool ok = r < rend;
+            const int b = (ok ? r : rbeg) / L, s = (ok ? r : rbeg) % L;
+            const int t = reverse ? (L - 1 - s) : s;
+            tk[i] = tok[b * L + t];
+            v[i] = ok ? dg[(size_t)r * HP4 + c] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[tk[i] * HP4 + c] += v[i];
     }
     float* out = part + (size_t)blockIdx.x * V * HP4;
     for (int v = 0; v < V; ++v) out[v * HP4 + c] = acc[v * HP4 + c];
