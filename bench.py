@@ -212,7 +212,8 @@ def run_ours(args):
     import train_vae as tv
     cfgv = cfg.Bunch(cfg.vae)
     cfgv.update(cfg.shared)
-    cfgv.cheaplog_every, cfgv.expsvlog_every = 1, 10 ** 9          # scalar block read back every iteration
+    cfgv.cheaplog_every, cfgv.expsvlog_every = 10 ** 9, 10 ** 9    # no sample generation / checkpoints in the timed loop
+    cfg.b200.sync_scalars_every = 1                                # ... but the scalar block is read back every iteration
     ds = types.SimpleNamespace(next_batch=lambda name: types.SimpleNamespace(text=tokens_host),
                                idx2sentence=lambda idxs, print_special_tokens=True: '')
     tb_json_logger.configure()

@@ -153,7 +153,8 @@ _DEFAULTS = {
         'fused_step': True,        # train_vae() runs the fused C-ABI iteration instead of autograd + torch.optim
         'noise_seed': 1238,        # Philox key of the perf-mode noise
         'full_mmd_every': 1,       # the reference evaluates the (log-only) full-kernel MMD every iteration
-        'log_scalars_every': 1,    # device->host read of the scalar block (only used on log iterations)
+        'sync_scalars_every': 0,   # > 0: also read the 16-float scalar block back every n-th iteration
+                                   # (train_vae.last_scalars; e.g. for a NaN watchdog); 0 = log iterations only
     },
     'dataset': 'amp',
 }

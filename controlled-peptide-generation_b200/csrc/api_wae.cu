@@ -255,16 +255,16 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     }
     launch_gru_bwd_enc(s, enc, B, L);
     // recurrent weight gradients
-    launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[0], w.enc_hs[0], nullptr, B, L, sm, w.wg_part, grads + lay.off[P_ENC_WHH_F],
-                    w.gemm_ws, w.gemm_splits);
-    launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[1], w.enc_hs[1], nullptr, B, L, sm, w.wg_part, grads + lay.off[P_ENC_WHH_R],
-                    w.gemm_ws, w.gemm_splits);
-    launch_wgrad_hh(s, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, B, L, sm, w.wg_part, grads + lay.off[P_DEC_WHH],
-                    w.gemm_ws, w.gemm_splits);
-    // token-table gradients -> embedding / W_ih / biases
-    launch_dtable(s, ENC_H, w.enc_dg[0], w.tok, B, L, 0, V, sm, w.dt_part, w.dT_enc[0]);
-    launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part, w.dT_enc[1]);
-    launch_dtable(s, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part, w.dT_dec);
+    // (the tensor-core path produces the token-table gradient in the same pass over dg)
+    const bool t0 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[0], w.enc_hs[0], nullptr, w.tok, 0, V, B, L, sm, w.wg_part,
+                                    w.dt_part, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0]);
+    if (!t0) launch_dtable(s, ENC_H, w.enc_dg[0], w.tok, B, L, 0, V, sm, w.dt_part, w.dT_enc[0]);
+    const bool t1 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[1], w.enc_hs[1], nullptr, w.tok, 1, V, B, L, sm, w.wg_part,
+                                    w.dt_part, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1]);
+    if (!t1) launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part, w.dT_enc[1]);
+    const bool t2 = launch_wgrad_hh(s, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, w.tokd, 0, V, B, L, sm, w.wg_part,
+                                    w.dt_part, grads + lay.off[P_DEC_WHH], w.dT_dec);
+    if (!t2) launch_dtable(s, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part, w.dT_dec);
     InputGradArgs ia;
     memset(&ia, 0, sizeof(ia));
     ia.emb = params + lay.off[P_EMB];

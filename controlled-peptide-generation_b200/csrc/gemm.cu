@@ -1,68 +1,105 @@
-// Small fp32 SIMT GEMM used for the dense layers around the recurrences
-// (q_mu / q_logvar heads, [z;c] input projection, random-feature map and their
-// backward contractions).  These are 1-3 % of the step's FLOPs; the kernel is a
-// plain 64x64x16 register-tiled SGEMM with general operand strides and a
-// deterministic split-K (partials + ordered reduction, no float atomics).
+// fp32 SIMT GEMM used for the dense layers around the recurrences (q_mu / q_logvar heads, [z;c]
+// input projection, random-feature map and their backward contractions; ~6 % of the step's FLOPs).
+// 128x64x16 tiles, 256 threads, 8x4 register tile per thread, register-prefetched (double-buffered)
+// global loads, general operand strides, and a deterministic split-K (partials + ordered
+// reduction, no float atomics).  These stay in exact fp32 because the forward ones (mu, logvar,
+// the [z;c] projection) feed results that are compared at 1e-4.
 #include "kernels.h"
 
 namespace cpg {
 
-constexpr int GM = 64, GN = 64, GK = 16;
+constexpr int GM = 128, GN = 64, GK = 16;
 
 __global__ void __launch_bounds__(256)
 k_sgemm(int M, int N, int K, float alpha, const float* __restrict__ A, int64_t sam, int64_t sak,
         const float* __restrict__ Bm, int64_t sbk, int64_t sbn, float beta, float* __restrict__ C, int64_t ldc,
         const float* __restrict__ bias, int kchunk, float* __restrict__ ws) {
-    __shared__ __align__(16) float As[GK][GM + 4];
-    __shared__ __align__(16) float Bs[GK][GN + 4];
+    __shared__ __align__(16) float As[2][GK][GM + 4];
+    __shared__ __align__(16) float Bs[2][GK][GN + 4];
     const int tid = threadIdx.x;
-    const int tx = tid % 16, ty = tid / 16;
+    const int tx = tid % 16, ty = tid / 16;            // 16 column groups (4 cols) x 16 row groups (8 rows)
     const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
     const int kbeg = blockIdx.z * kchunk;
     const int kend = min(K, kbeg + kchunk);
-    float acc[4][4];
+    float acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+    // element -> (m, k) / (k, n) assignment of this thread for the global->shared copies:
+    // the fastest-varying index follows the operand's unit stride so that loads coalesce
     const bool a_kfast = (sak == 1);
     const bool b_nfast = (sbn == 1);
-    for (int k0 = kbeg; k0 < kend; k0 += GK) {
+    float ra[8], rb[4];
+    auto load_tile = [&](int k0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            int idx = tid + 256 * i;
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + 256 * i;
             int m, k;
             if (a_kfast) { k = idx % GK; m = idx / GK; } else { m = idx % GM; k = idx / GM; }
-            int gm = m0 + m, gk = k0 + k;
-            As[k][m] = (gm < M && gk < kend) ? A[gm * sam + gk * sak] : 0.f;
-            int n, kb;
-            if (b_nfast) { n = idx % GN; kb = idx / GN; } else { kb = idx % GK; n = idx / GK; }
-            int gn = n0 + n, gkb = k0 + kb;
-            Bs[kb][n] = (gn < N && gkb < kend) ? Bm[gkb * sbk + gn * sbn] : 0.f;
+            const int gm = m0 + m, gk = k0 + k;
+            ra[i] = (gm < M && gk < kend) ? A[gm * sam + gk * sak] : 0.f;
         }
-        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + 256 * i;
+            int n, k;
+            if (b_nfast) { n = idx % GN; k = idx / GN; } else { k = idx % GK; n = idx / GK; }
+            const int gn = n0 + n, gk = k0 + k;
+            rb[i] = (gn < N && gk < kend) ? Bm[gk * sbk + gn * sbn] : 0.f;
+        }
+    };
+    auto store_tile = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + 256 * i;
+            int m, k;
+            if (a_kfast) { k = idx % GK; m = idx / GK; } else { m = idx % GM; k = idx / GM; }
+            As[buf][k][m] = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + 256 * i;
+            int n, k;
+            if (b_nfast) { n = idx % GN; k = idx / GN; } else { k = idx % GK; n = idx / GK; }
+            Bs[buf][k][n] = rb[i];
+        }
+    };
+
+    int buf = 0;
+    if (kbeg < kend) {
+        load_tile(kbeg);
+        store_tile(0);
+    }
+    __syncthreads();
+    for (int k0 = kbeg; k0 < kend; k0 += GK) {
+        const bool more = k0 + GK < kend;
+        if (more) load_tile(k0 + GK);                   // global loads in flight during the FMAs below
 #pragma unroll
         for (int k = 0; k < GK; ++k) {
-            const float4 av = ld4(&As[k][ty * 4]);
-            const float4 bv = ld4(&Bs[k][tx * 4]);
-            const float a4[4] = {av.x, av.y, av.z, av.w};
+            const float4 a0 = ld4(&As[buf][k][ty * 8]);
+            const float4 a1 = ld4(&As[buf][k][ty * 8 + 4]);
+            const float4 bv = ld4(&Bs[buf][k][tx * 4]);
+            const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a8[i], b4[j], acc[i][j]);
         }
+        if (more) store_tile(buf ^ 1);
         __syncthreads();
+        buf ^= 1;
     }
     const bool split = gridDim.z > 1;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int gm = m0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+        const int gm = m0 + ty * 8 + i;
         if (gm >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int gn = n0 + tx * 4 + j;
+            const int gn = n0 + tx * 4 + j;
             if (gn >= N) continue;
             if (split) {
                 ws[((size_t)blockIdx.z * M + gm) * N + gn] = acc[i][j];

@@ -91,29 +91,32 @@ int g_opt_wgrad_tc = 1;
 int wgrad_tc_splits(int) { return 1; }      // the tcgen05 kernel is compiled out of the CPU emulation
 #endif
 
-void launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0, int B, int L,
-                     int sm_count, float* part, float* dW, float* gemm_ws, int gemm_splits) {
+__global__ void k_dtable_reduce(const float* __restrict__ part, int nsplit, int n, float* __restrict__ dT);
+
+bool launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0,
+                     const uint8_t* tok, int reverse, int V, int B, int L, int sm_count, float* part, float* dt_part,
+                     float* dW, float* dT) {
     int nrows = B * L;
 #ifndef CPG_EMU
     // tf32 operands (round-to-nearest, fp32 accumulate): the rounding noise averages out over the
     // B*L-long reduction, so the tensor-core path is used where the reduction is long (>= 8192 rows);
-    // short reductions (tiny batches) stay on the exact fp32 SIMT kernel.  g_opt_wgrad_tc = 2 forces it.
+    // short reductions (tiny batches) stay on the exact fp32 SIMT kernels.  g_opt_wgrad_tc = 2 forces it.
     if ((g_opt_wgrad_tc == 1 && nrows >= 8192) || g_opt_wgrad_tc == 2) {
-        // tcgen05 path (wgrad_tc.cu): everything except the h0 rows, which are added below for the decoder
         int nsplit = 0;
-        if (launch_wgrad_hh_tc(s, HP, dg, hs, B, L, sm_count, part, &nsplit) == 0) {
+        if (launch_wgrad_tc(s, HP, dg, hs, h0, tok, reverse, B, L, V, sm_count, part, dt_part, &nsplit) == 0) {
             CPG_LAUNCH(k_wgrad_hh_reduce, ceil_div(3 * H * H, 256), 256, 0, s, part, nsplit, HP, H, dW);
-            if (h0 != nullptr) {
-                for (int g = 0; g < 3; ++g) {
-                    const int plane = g == 2 ? 3 : g;
-                    launch_sgemm(s, H, H, B, 1.f, dg + (size_t)plane * HP, 1, (int64_t)L * 4 * HP, h0, HP, 1, 1.f,
-                                 dW + (size_t)g * H * H, H, nullptr, gemm_splits, gemm_ws);
-                }
-            }
-            return;
+            CPG_LAUNCH(k_dtable_reduce, ceil_div(V * 4 * HP, 256), 256, 0, s, dt_part, nsplit, V * 4 * HP, dT);
+            return true;                               // W_hh gradient (h0 rows included) and dT both done
         }
     }
 #endif
+    launch_wgrad_hh_simt(s, HP, H, dg, hs, h0, B, L, sm_count, part, dW);
+    return false;
+}
+
+void launch_wgrad_hh_simt(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0, int B, int L,
+                          int sm_count, float* part, float* dW) {
+    int nrows = B * L;
     int want = max(1, sm_count / 3);
     int rps = ceil_div(ceil_div(nrows, want), WG_ROWS) * WG_ROWS;
     int nsplit = ceil_div(nrows, rps);

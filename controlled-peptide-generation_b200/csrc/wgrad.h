@@ -18,13 +18,16 @@ struct InputGradArgs {
 
 int wgrad_splits(int B, int L, int sm_count);
 int dtable_splits(int B, int L, int sm_count);
-// gemm_ws / gemm_splits: split-K scratch of launch_sgemm (used for the decoder's h0 rows on the tensor-core path)
-void launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0, int B, int L,
-                     int sm_count, float* part, float* dW, float* gemm_ws, int gemm_splits);
-// tcgen05 version (wgrad_tc.cu): partials [nsplit][3*HP][HP] over all rows with s > 0 (h0 rows excluded)
+// dW_hh (and, on the tensor-core path, the token-table gradient dT as well: returns true then).
+bool launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0,
+                     const uint8_t* tok, int reverse, int V, int B, int L, int sm_count, float* part, float* dt_part,
+                     float* dW, float* dT);
+void launch_wgrad_hh_simt(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0, int B, int L,
+                          int sm_count, float* part, float* dW);
+// tcgen05 version (wgrad_tc.cu): partials part_w [nsplit][3*HP][HP] and part_t [nsplit][V][4*HP]
 int wgrad_tc_splits(int sm_count);
-int launch_wgrad_hh_tc(cudaStream_t s, int HP, const float* dg, const float* hs, int B, int L, int sm_count,
-                       float* part, int* nsplit_out);
+int launch_wgrad_tc(cudaStream_t s, int HP, const float* dg, const float* hs, const float* h0, const uint8_t* tok,
+                    int reverse, int B, int L, int V, int sm_count, float* part_w, float* part_t, int* nsplit_out);
 extern int g_opt_wgrad_tc;
 void launch_dtable(cudaStream_t s, int HP, const float* dg, const uint8_t* tok, int B, int L, int reverse, int V,
                    int sm_count, float* part, float* dT);

@@ -1,56 +1,66 @@
-// Recurrent weight gradients on the 5th-gen tensor cores:
-//     dW_hh[g][k] = sum_{r=(b,s)} dgh[r][g] * h_{s-1}[r][k]         (K = B*L = 102,400 at B=4096)
-// a pure contraction over the batch*time axis, split across one CTA per SM, each CTA streaming its
-// row range through a TMA -> (tf32 rounding) -> tcgen05.mma pipeline with the three gate tiles
-// accumulating in TMEM for the whole range.
+// Recurrent weight gradients AND token-table gradients on the 5th-gen tensor cores.
 //
-// Both operands are "MN-major" for UMMA: a row r of `dg` ([B*L][4*HP]) holds the M index (gate column)
-// contiguously, a row of `hs` ([B*L][HP]) holds the N index (hidden unit) contiguously; TMA boxes of
-// {32 floats, 32 rows} with the 128-byte / 32-byte-atom swizzle (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) land
-// exactly in the canonical MN-major SWIZZLE_128B_BASE32B layout -- the only one tcgen05 accepts for MN-major tf32.
-// h_{s-1} is the hs row ABOVE (TMA row coordinate r-1, row -1 zero-filled); rows with s == 0 are
-// zeroed by the conversion pass (their h0 term is added by the caller for the decoder; the encoder
-// starts from h0 = 0).  Operands are rounded to tf32 (round-to-nearest) in shared memory by four
-// conversion warps, which keeps the products unbiased (the tensor core itself truncates).
+// Both are contractions over the batch*time axis r = (b, s)  (K = B*L = 102,400 at B = 4096):
+//     dW_hh[g][k]   = sum_r dgh[r][g] * h_prev[r][k]            (3 gate planes, N = H)
+//     dT[v][pl][j]  = sum_r [tok_r == v] * dg[r][pl][j]          (4 planes, N = 32 one-hot columns)
+// The range is split over one persistent CTA per SM; each CTA streams its rows through a
+// TMA -> convert -> tcgen05.mma pipeline (2 stages of 32 rows) with all seven accumulator tiles
+// (3 x [128 x H] + 4 x [128 x 32]) resident in TMEM for the whole range, so dg is read from HBM once.
+//
+// Operands are "MN-major" for UMMA: a row of `dg` ([B*L][4*HP]) holds the M index (gate column)
+// contiguously, a row of `hs` ([B*L][HP]) the N index.  TMA boxes of {32 floats, 32 rows} with the
+// 128-byte / 32-byte-atom swizzle (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) land exactly in the canonical
+// MN-major SWIZZLE_128B_BASE32B layout -- the only layout tcgen05 accepts for MN-major tf32.
+// h_prev is the hs row ABOVE (TMA row coordinate r-1); for rows with s == 0 the conversion warps
+// overwrite it with h0 (decoder: [z;c]) or zeros (encoder).  The conversion warps also round every
+// operand to tf32 (round-to-nearest: unbiased products; the tensor core itself truncates) and build the
+// one-hot token tile in the same swizzled layout.
 //
 // Warp roles (192 threads): warp 4 = TMA producer, warp 5 = MMA issuer (+ TMEM owner),
-// warps 0-3 = tf32 conversion per stage, then the TMEM -> global epilogue.
+// warps 0-3 = conversion per stage, then the TMEM -> global epilogue.
 #include "ctx.h"
 #ifndef CPG_EMU
 #include "tc_common.cuh"
-#include <stdio.h>
 
 namespace cpg {
 int check_launch(const char* where);
 
 constexpr int WT_RK = 32;                 // reduction rows per pipeline stage
 constexpr int WT_CHUNK = WT_RK * 128;     // bytes of one {32 floats x 32 rows} box
-constexpr int WT_STAGES = 3;
+constexpr int WT_STAGES = 2;
+constexpr int WT_A_BYTES = 4 * 4 * WT_CHUNK;      // 4 planes x 4 chunks (M = 128 lanes per plane)
+constexpr int WT_B_BYTES = 4 * WT_CHUNK;          // h_prev: up to 128 columns
+constexpr int WT_O_BYTES = WT_CHUNK;              // one-hot tokens: 32 columns
+constexpr int WT_STAGE_BYTES = WT_A_BYTES + WT_B_BYTES + WT_O_BYTES;
+constexpr size_t WT_SMEM = (size_t)WT_STAGES * WT_STAGE_BYTES + 1024;
+constexpr int WT_TCOL = 384;              // TMEM column of the first dT accumulator (4 x 32 columns)
 
-template <int HP>
-struct WgTc {
-    static constexpr int NCH = (HP + 31) / 32;                   // 32-float chunks that hold valid columns
-    static constexpr int N_MMA = (HP + 15) / 16 * 16;            // UMMA N (multiple of 16 for M = 128)
-    static constexpr int A_BYTES = 3 * 4 * WT_CHUNK;             // 3 gates x 4 chunks (M = 128 lanes)
-    static constexpr int B_BYTES = 4 * WT_CHUNK;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr size_t SMEM = (size_t)WT_STAGES * STAGE_BYTES + 1024;
+struct WgTcArgs {
+    const uint8_t* tok;      // [B][L] tokens that fed this GRU
+    const float* h0;         // [B][HP] initial hidden state, or null (zeros)
+    float* part_w;           // [nsplit][3*HP][HP]
+    float* part_t;           // [nsplit][V][4*HP]
+    int nrows, L, V, reverse, rows_per_cta;
 };
+
+// byte offset of 16-byte unit u (columns 4u..4u+3) of row i inside one swizzled 4 KB box
+__device__ __forceinline__ int wt_unit_off(int i, int u) { return i * 128 + ((((u >> 1) ^ (i & 3))) << 5) + ((u & 1) << 4); }
 
 template <int HP>
 __global__ void __launch_bounds__(192, 1)
-k_wgrad_hh_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ CUtensorMap tmap_hs, int nrows,
-              int L, int rows_per_cta, float* __restrict__ part, int dbg) {
-    using C = WgTc<HP>;
+k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ CUtensorMap tmap_hs, WgTcArgs a) {
+    constexpr int NCH = (HP + 31) / 32;                 // 32-float chunks holding valid columns
+    constexpr int N_MMA = (HP + 15) / 16 * 16;          // UMMA N for the W_hh tiles
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t bar_full[WT_STAGES], bar_conv[WT_STAGES], bar_empty[WT_STAGES], bar_done;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int r_begin = blockIdx.x * rows_per_cta;
-    const int r_end = min(nrows, r_begin + rows_per_cta);
-    const int n_stage_iters = r_end > r_begin ? (r_end - r_begin + WT_RK - 1) / WT_RK : 0;
+    const int L = a.L;
+    const int r_begin = blockIdx.x * a.rows_per_cta;
+    const int r_end = min(a.nrows, r_begin + a.rows_per_cta);
+    const int n_iters = r_end > r_begin ? (r_end - r_begin + WT_RK - 1) / WT_RK : 0;
 
     if (warp == 5) {
         if (lane == 0) {
@@ -75,19 +85,17 @@ k_wgrad_hh_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant
         if (lane == 0) {
             tc::tma_prefetch_desc(&tmap_dg);
             tc::tma_prefetch_desc(&tmap_hs);
-            for (int it = 0; it < n_stage_iters; ++it) {
-                const int st = it % WT_STAGES, ph = (it / WT_STAGES) & 1;
-                if (it >= WT_STAGES) tc::mbar_wait(&bar_empty[st], ph ^ 1);
-                unsigned char* sa = smem + (size_t)st * C::STAGE_BYTES;
-                unsigned char* sb = sa + C::A_BYTES;
+            for (int it = 0; it < n_iters; ++it) {
+                const int st = it % WT_STAGES, u = it / WT_STAGES;
+                if (u >= 1) tc::mbar_wait(&bar_empty[st], (u - 1) & 1);
+                unsigned char* sa = smem + (size_t)st * WT_STAGE_BYTES;
+                unsigned char* sb = sa + WT_A_BYTES;
                 const int r0 = r_begin + it * WT_RK;
-                tc::mbar_expect_tx(&bar_full[st], (3 * C::NCH + C::NCH) * WT_CHUNK);
-                for (int g = 0; g < 3; ++g) {
-                    const int plane = g == 2 ? 3 : g;                 // (dr_pre, dz_pre, dhn)
-                    for (int c = 0; c < C::NCH; ++c)
-                        tc::tma_load_2d(sa + (g * 4 + c) * WT_CHUNK, &tmap_dg, &bar_full[st], plane * HP + c * 32, r0);
-                }
-                for (int c = 0; c < C::NCH; ++c)
+                tc::mbar_expect_tx(&bar_full[st], (4 * NCH + NCH) * WT_CHUNK);
+                for (int pl = 0; pl < 4; ++pl)
+                    for (int c = 0; c < NCH; ++c)
+                        tc::tma_load_2d(sa + (pl * 4 + c) * WT_CHUNK, &tmap_dg, &bar_full[st], pl * HP + c * 32, r0);
+                for (int c = 0; c < NCH; ++c)
                     tc::tma_load_2d(sb + c * WT_CHUNK, &tmap_hs, &bar_full[st], c * 32, r0 - 1);
             }
         }
@@ -95,23 +103,27 @@ k_wgrad_hh_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant
     } else if (warp == 5) {
         // ---------------- MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = tc::make_idesc_tf32(128, C::N_MMA, 1, 1);
-            for (int it = 0; it < n_stage_iters; ++it) {
-                const int st = it % WT_STAGES, ph = (it / WT_STAGES) & 1;
-                tc::mbar_wait(&bar_conv[st], ph);
+            constexpr uint32_t idesc_w = tc::make_idesc_tf32(128, N_MMA, 1, 1);
+            constexpr uint32_t idesc_t = tc::make_idesc_tf32(128, 32, 1, 1);
+            // MN-major SWIZZLE_128B_BASE32B: next 32 floats of M/N one 4 KB box further (LBO),
+            // 4-row K groups 512 B apart (SBO); one K = 8 MMA spans two such groups
+            constexpr uint32_t lbo = WT_CHUNK, sbo = 512u;
+            for (int it = 0; it < n_iters; ++it) {
+                const int st = it % WT_STAGES, u = it / WT_STAGES;
+                tc::mbar_wait(&bar_conv[st], u & 1);
                 tc::tc_fence_after();
-                const uint32_t sa = tc::smem_u32(smem + (size_t)st * C::STAGE_BYTES);
-                const uint32_t sb = sa + C::A_BYTES;
+                const uint32_t sa = tc::smem_u32(smem + (size_t)st * WT_STAGE_BYTES);
+                const uint32_t sb = sa + WT_A_BYTES, so = sb + WT_B_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < WT_RK / 8; ++ks) {
-                    // MN-major SWIZZLE_128B_BASE32B: next 32 floats of M/N one 4 KB box further (LBO),
-                    // 4-row K groups 512 B apart (SBO); one K=8 MMA spans two such groups
-                    const uint32_t lbo = (uint32_t)WT_CHUNK, sbo = 512u;
+                    const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
                     const uint64_t db = tc::make_smem_desc(sb + ks * 1024, lbo, sbo, 1);
+                    const uint64_t dt_ = tc::make_smem_desc(so + ks * 1024, lbo, sbo, 1);
 #pragma unroll
-                    for (int g = 0; g < 3; ++g) {
-                        const uint64_t da = tc::make_smem_desc(sa + g * 4 * WT_CHUNK + ks * 1024, lbo, sbo, 1);
-                        tc::umma_tf32(tmem_d + g * 128, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                    for (int pl = 0; pl < 4; ++pl) {
+                        const uint64_t da = tc::make_smem_desc(sa + pl * 4 * WT_CHUNK + ks * 1024, lbo, sbo, 1);
+                        if (pl != 2) tc::umma_tf32(tmem_d + (pl == 3 ? 2 : pl) * 128, da, db, idesc_w, acc);   // dr, dz, dhn
+                        tc::umma_tf32(tmem_d + WT_TCOL + pl * 32, da, dt_, idesc_t, acc);
                     }
                 }
                 tc::umma_commit(&bar_empty[st]);          // stage reusable once these MMAs have read it
@@ -120,66 +132,108 @@ k_wgrad_hh_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant
         }
         __syncwarp();
     } else {
-        // ---------------- tf32 conversion (in place), 128 threads
-        for (int it = 0; it < n_stage_iters; ++it) {
-            const int st = it % WT_STAGES, ph = (it / WT_STAGES) & 1;
-            tc::mbar_wait(&bar_full[st], ph);
-            unsigned char* sa = smem + (size_t)st * C::STAGE_BYTES;
+        // ---------------- conversion (in place), 128 threads:
+        // thread -> 16-byte unit (tid & 7) of rows (tid >> 3) and (tid >> 3) + 16 of every 4 KB box
+        for (int it = 0; it < n_iters; ++it) {
+            const int st = it % WT_STAGES, u_it = it / WT_STAGES;
+            tc::mbar_wait(&bar_full[st], u_it & 1);
+            unsigned char* sa = smem + (size_t)st * WT_STAGE_BYTES;
+            unsigned char* sb = sa + WT_A_BYTES;
+            unsigned char* so = sb + WT_B_BYTES;
             const int r0 = r_begin + it * WT_RK;
-            // A: 3 gates x NCH chunks; each chunk = 32 rows x 8 float4 (row i = bytes [128 i, 128 i + 128))
-            // thread -> float4 slot (tid & 7) of rows (tid >> 3) and (tid >> 3) + 16 of every 4 KB box
+            const int un = tid & 7;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const int row = (tid >> 3) + 16 * half;
                 const int r = r0 + row;
-                const bool zero_row = (r >= r_end) || (r % L) == 0;
-                const int slot = row * 8 + (tid & 7);
+                const bool dead = r >= r_end;                 // rows of the next CTA's range (or past the end)
+                const int rr = dead ? r_begin : r;
+                const int b = rr / L, s = rr % L;
+                const int slot = row * 8 + un;                // unit index in box-linear order (swizzle agnostic)
 #pragma unroll
-                for (int g = 0; g < 3; ++g)
+                for (int pl = 0; pl < 4; ++pl)
 #pragma unroll
-                    for (int c = 0; c < C::NCH; ++c) {
-                        float4* p = reinterpret_cast<float4*>(sa + (g * 4 + c) * WT_CHUNK) + slot;
+                    for (int c = 0; c < NCH; ++c) {
+                        float4* p = reinterpret_cast<float4*>(sa + (pl * 4 + c) * WT_CHUNK) + slot;
                         float4 v = *p;
-                        if (zero_row) {
+                        if (dead) {
                             v = make_float4(0.f, 0.f, 0.f, 0.f);
                         } else {
                             v.x = tc::to_tf32_rn(v.x); v.y = tc::to_tf32_rn(v.y); v.z = tc::to_tf32_rn(v.z); v.w = tc::to_tf32_rn(v.w);
                         }
                         *p = v;
                     }
+                if (s == 0) {
+                    // h_prev of a first step is h0, not the row above: rewrite it (swizzle-aware addressing)
 #pragma unroll
-                for (int c = 0; c < C::NCH; ++c) {
-                    float4* p = reinterpret_cast<float4*>(sa + C::A_BYTES + c * WT_CHUNK) + slot;
-                    float4 v = *p;
-                    v.x = tc::to_tf32_rn(v.x); v.y = tc::to_tf32_rn(v.y); v.z = tc::to_tf32_rn(v.z); v.w = tc::to_tf32_rn(v.w);
-                    *p = v;
+                    for (int c = 0; c < NCH; ++c) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int col = c * 32 + un * 4;
+                        if (a.h0 != nullptr && col < HP) v = ld4(a.h0 + (size_t)b * HP + col);
+                        v.x = tc::to_tf32_rn(v.x); v.y = tc::to_tf32_rn(v.y); v.z = tc::to_tf32_rn(v.z); v.w = tc::to_tf32_rn(v.w);
+                        *reinterpret_cast<float4*>(sb + c * WT_CHUNK + wt_unit_off(row, un)) = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        float4* p = reinterpret_cast<float4*>(sb + c * WT_CHUNK) + slot;
+                        float4 v = *p;
+                        v.x = tc::to_tf32_rn(v.x); v.y = tc::to_tf32_rn(v.y); v.z = tc::to_tf32_rn(v.z); v.w = tc::to_tf32_rn(v.w);
+                        *p = v;
+                    }
                 }
+                // one-hot row of the token that fed step s (time L-1-s for the reverse direction)
+                const int t = a.reverse ? (L - 1 - s) : s;
+                const int tk = a.tok[(size_t)b * L + t];
+                float4 oh = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((tk >> 2) == un) {
+                    const int k = tk & 3;
+                    oh.x = k == 0 ? 1.f : 0.f; oh.y = k == 1 ? 1.f : 0.f; oh.z = k == 2 ? 1.f : 0.f; oh.w = k == 3 ? 1.f : 0.f;
+                }
+                *reinterpret_cast<float4*>(so + wt_unit_off(row, un)) = oh;
             }
             tc::fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core
             tc::mbar_arrive(&bar_conv[st]);
         }
-        // ---------------- epilogue: TMEM -> per-CTA partial [3*HP][HP]
-        if (n_stage_iters > 0) {
+        // ---------------- epilogue: TMEM -> per-CTA partials
+        if (n_iters > 0) {
             tc::mbar_wait(&bar_done, 0);
             tc::tc_fence_after();
         }
-        float* out = part + (size_t)blockIdx.x * 3 * HP * HP;
+        float* out_w = a.part_w + (size_t)blockIdx.x * 3 * HP * HP;
+        float* out_t = a.part_t + (size_t)blockIdx.x * a.V * 4 * HP;
+        const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
         for (int g = 0; g < 3; ++g) {
 #pragma unroll 1
-            for (int c = 0; c < C::NCH; ++c) {
+            for (int c = 0; c < NCH; ++c) {
                 float v[32];
-                if (n_stage_iters > 0) {
-                    tc::tmem_ld_32x32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 128 + c * 32), v);
+                if (n_iters > 0) {
+                    tc::tmem_ld_32x32(lane_addr + (uint32_t)(g * 128 + c * 32), v);
                 } else {
 #pragma unroll
                     for (int q = 0; q < 32; ++q) v[q] = 0.f;
                 }
                 if (tid < HP) {
-                    float* o = out + ((size_t)g * HP + tid) * HP + c * 32;
+                    float* o = out_w + ((size_t)g * HP + tid) * HP + c * 32;
 #pragma unroll
                     for (int q = 0; q < 32; ++q)
                         if (c * 32 + q < HP) o[q] = v[q];
                 }
+            }
+        }
+#pragma unroll 1
+        for (int pl = 0; pl < 4; ++pl) {
+            float v[32];
+            if (n_iters > 0) {
+                tc::tmem_ld_32x32(lane_addr + (uint32_t)(WT_TCOL + pl * 32), v);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = 0.f;
+            }
+            if (tid < HP) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    if (q < a.V) out_t[(size_t)q * 4 * HP + pl * HP + tid] = v[q];
             }
         }
     }
@@ -190,9 +244,9 @@ k_wgrad_hh_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant
 
 int wgrad_tc_splits(int sm_count) { return sm_count > 0 ? sm_count : 1; }
 
-int g_dbg_wgrad = 0;
-int launch_wgrad_hh_tc(cudaStream_t s, int HP, const float* dg, const float* hs, int B, int L, int sm_count,
-                       float* part, int* nsplit_out) {
+// Fills part_w ([nsplit][3*HP][HP]) and part_t ([nsplit][V][4*HP]); the caller reduces them.
+int launch_wgrad_tc(cudaStream_t s, int HP, const float* dg, const float* hs, const float* h0, const uint8_t* tok,
+                    int reverse, int B, int L, int V, int sm_count, float* part_w, float* part_t, int* nsplit_out) {
     const int nrows = B * L;
     int nsplit = std::min(wgrad_tc_splits(sm_count), ceil_div(nrows, WT_RK));
     int rpc = ceil_div(ceil_div(nrows, nsplit), WT_RK) * WT_RK;
@@ -203,30 +257,22 @@ int launch_wgrad_hh_tc(cudaStream_t s, int HP, const float* dg, const float* hs,
     if (rc) return rc;
     rc = make_tmap_2d_f32_sw128(&tm_hs, hs, (uint64_t)HP, (uint64_t)nrows, (uint64_t)HP * sizeof(float), WT_RK, true);
     if (rc) return rc;
+    WgTcArgs a;
+    a.tok = tok; a.h0 = h0; a.part_w = part_w; a.part_t = part_t;
+    a.nrows = nrows; a.L = L; a.V = V; a.reverse = reverse; a.rows_per_cta = rpc;
     if (HP == ENC_H) {
-        auto kfn = k_wgrad_hh_tc<ENC_H>;
+        auto kfn = k_wgrad_tc<ENC_H>;
         static bool once = false;
-        if (!once) { cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgTc<ENC_H>::SMEM); once = true; }
-        CPG_LAUNCH_NAMED("k_wgrad_hh_tc_enc", kfn, nsplit, 192, WgTc<ENC_H>::SMEM, s, tm_dg, tm_hs, nrows, L, rpc, part, g_dbg_wgrad);
+        if (!once) { cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM); once = true; }
+        CPG_LAUNCH_NAMED("k_wgrad_tc_enc", kfn, nsplit, 192, WT_SMEM, s, tm_dg, tm_hs, a);
     } else {
-        auto kfn = k_wgrad_hh_tc<DEC_HP>;
+        auto kfn = k_wgrad_tc<DEC_HP>;
         static bool once = false;
-        if (!once) { cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgTc<DEC_HP>::SMEM); once = true; }
-        CPG_LAUNCH_NAMED("k_wgrad_hh_tc_dec", kfn, nsplit, 192, WgTc<DEC_HP>::SMEM, s, tm_dg, tm_hs, nrows, L, rpc, part, g_dbg_wgrad);
+        if (!once) { cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM); once = true; }
+        CPG_LAUNCH_NAMED("k_wgrad_tc_dec", kfn, nsplit, 192, WT_SMEM, s, tm_dg, tm_hs, a);
     }
     return CPG_OK;
 }
 
 }  // namespace cpg
 #endif  // CPG_EMU
-
-#ifndef CPG_EMU
-// developer probe: run the tensor-core contraction alone and return the raw per-CTA partials
-extern "C" int cpg_debug_wgrad_tc(cpg_ctx* ctx, void* stream, int HP, const float* dg, const float* hs, int B, int L,
-                                  float* part, int* nsplit, int dbg) {
-    cpg::g_dbg_wgrad = dbg;
-    int rc = cpg::launch_wgrad_hh_tc((cudaStream_t)stream, HP, dg, hs, B, L, ctx->sm_count, part, nsplit);
-    if (rc) return rc;
-    return cpg::check_launch("cpg_debug_wgrad_tc");
-}
-#endif

@@ -1,11 +1,14 @@
 """Phase-1 WAE/VAE training loop with the reference's entry point
 `train_vae(cfgv, model, dataset)` (train_vae.py:13-68 of IBM/controlled-peptide-generation).
 
-Default (cfg.b200.fused_step): each iteration is ONE call into libcpg_b200 --
-Philox noise -> forward -> the five losses -> BPTT -> clip_grad_norm_ -> Adam (with the
+Default (cfg.b200.fused_step): each iteration is two calls into libcpg_b200 --
+Philox noise, then forward -> the five losses -> BPTT -> clip_grad_norm_ -> Adam (with the
 duplicated-embedding semantics of `vae_params()`), all on the current CUDA stream; the host only
-moves the token batch (if the loader produced it on the host) and, on logging iterations, reads the
-16-float scalar block back (the reference reads nine `.item()`s every iteration).
+moves the token batch (if the loader produced it on the host: one async copy from pinned memory into
+a persistent device buffer) and, on logging iterations (or every `cfg.b200.sync_scalars_every`
+iterations), reads the 16-float scalar block back (the reference reads nine `.item()`s every
+iteration).  Under torch.distributed (one process per GPU) the batch each rank receives is its shard
+of the global batch and the iteration runs through cpg_b200.parallel.dp_train_step.
 
 cfg.b200.fused_step = False runs the reference-style loop (model() -> losses.* -> loss.backward()
 -> clip_grad_norm_ -> torch.optim.Adam) over the same kernels through autograd.Functions.
@@ -23,6 +26,7 @@ from models.mutils import save_model
 from tb_json_logger import log_value
 
 train = None   # alias set below (BASELINE.json calls the entry point "train_vae.train()")
+last_scalars = None   # host copy of the most recent scalar block read back (engine.SC slots)
 
 _SCALAR_LOG = (('z_mu_L1', 'z_mu_l1'), ('z_logvar', 'z_logvar'), ('z_logvar_L1', 'logvar_l1'),
                ('z_logvar_KL_penalty', 'logvar_kl'), ('L_vae', 'loss'), ('L_vae_recon', 'recon'),
@@ -44,6 +48,7 @@ def _log_sample(model, dataset, write):
 
 
 def _train_fused(cfgv, model, dataset):
+    global last_scalars
     st = model.bind_grads()
     dev = st.device
     wm = cfg.losses.wae_mmd
@@ -55,35 +60,40 @@ def _train_fused(cfgv, model, dataset):
     p_word, p_out = model.decoder.word_dropout.p, model.decoder.p_out_dropout
     seed = int(cfg.b200.noise_seed)
     every = max(1, int(cfg.b200.full_mmd_every))
-    noise = None
-    global_batch = None
+    sync_every = int(getattr(cfg.b200, 'sync_scalars_every', 0))
+    distributed = parallel.is_distributed()
+    if distributed:
+        # rank-distinct noise rows; rf_w / rf_b come from the shared seed inside alloc_noise
+        rank_seed = (seed + 0x9E3779B97F4A7C15 * (1 + parallel.dist.get_rank())) % (1 << 63)
+    stepper, tok_dev, global_batch = None, None, None
     it_range, write = _progress(range(cfgv.s_iter, cfgv.s_iter + cfgv.n_iter + 1))
     for it in it_range:
         log_it = it % cfgv.cheaplog_every == 0 or it % cfgv.expsvlog_every == 0
-        inputs = dataset.next_batch('train_vae')
-        tokens = inputs.text
-        if not engine._lib._on_device(tokens):
-            tokens = tokens.to(dev, non_blocking=True)
+        tokens = dataset.next_batch('train_vae').text
         B, L = tokens.shape
-        if noise is None or noise['eps'].shape[0] != B or noise['word_drop'].shape[1] != L:
-            noise = engine.alloc_noise(B, L, dev, rf_dim=wm.rf_dim, seed=seed)
-        hp.beta = float(utils.anneal(cfgv.beta, it))
-        hp.compute_full_mmd = 1 if (it % every == 0 or log_it) else 0
-        if parallel.is_distributed():
-            # shards of one global batch: rank-distinct noise rows, shared rf_w / rf_b, gradients all-reduced
-            if global_batch is None:
-                global_batch = parallel.global_batch_size(B, dev)
-            rank_seed = seed + 0x9E3779B97F4A7C15 * (1 + parallel.dist.get_rank()) % (1 << 63)
-            engine.fill_step_noise(noise, rank_seed, it, p_word, p_out)
-            scal = parallel.dp_train_step(st, tokens.contiguous(), noise, hp, p_out=p_out, global_batch=global_batch)
+        if stepper is None or stepper.B != B or stepper.L != L:
+            stepper = engine.FusedStepper(st, B, L, hp, seed=seed, p_word=p_word, p_out=p_out, rf_dim=wm.rf_dim)
+            tok_dev = torch.empty(B, L, dtype=torch.int64, device=dev)
+            global_batch = parallel.global_batch_size(B, dev) if distributed else B
+        if engine._lib._on_device(tokens):
+            tok = tokens if tokens.is_contiguous() else tokens.contiguous()
         else:
-            engine.fill_step_noise(noise, seed, it, p_word, p_out)
-            scal, _ = engine.train_step(st, tokens.contiguous(), noise, hp, p_out=p_out)
+            tok_dev.copy_(tokens, non_blocking=True)                 # H2D (async when the loader pins its batches)
+            tok = tok_dev
+        beta = float(utils.anneal(cfgv.beta, it))
+        hp.compute_full_mmd = 1 if (it % every == 0 or log_it) else 0
+        if distributed:
+            hp.beta = beta
+            engine.fill_step_noise(stepper.noise, rank_seed, it, p_word, p_out)
+            scal = parallel.dp_train_step(st, tok, stepper.noise, hp, p_out=p_out, global_batch=global_batch)
+        else:
+            scal = stepper.step(tok, it, beta)
+        if log_it or (sync_every > 0 and it % sync_every == 0):
+            last_scalars = vals = scal.cpu()                         # the only device->host read
         if log_it:
-            vals = scal.cpu()                                        # the only device->host read
             for name, slot in _SCALAR_LOG:
                 log_value('train_' + name, float(vals[engine.SC[slot]]), it)
-            log_value('train_beta', hp.beta, it)
+            log_value('train_beta', beta, it)
             write('ITER {} TRAINING (phase 1). loss_vae: {:.4f}; loss_recon: {:.4f}; loss_kl: {:.4f}; '
                   'loss_mmd: {:.4f}; Grad_norm: {:.4e} '.format(
                       it, float(vals[engine.SC['loss']]), float(vals[engine.SC['recon']]),
