@@ -162,6 +162,10 @@ static int check_dims(int V, int B, int L) {
 }
 
 // ------------------------------------------------------------------------------------ forward
+// Tensor-core recurrences pay off once a 128-row tile per CTA fills a good part of the chip;
+// tiny batches stay on the 32-row fp32 SIMT kernels.  g_opt_gru_tc: 0 = never, 1 = auto, 2 = always.
+int g_opt_gru_tc = 1;
+static bool use_gru_tc(int B) { return g_opt_gru_tc == 2 || (g_opt_gru_tc == 1 && B >= 1024); }
 static void forward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, const ParamLayout& lay, int V, int B, int L,
                          const cpg_wae_inputs* in, float* mu, float* logvar, float* z, bool stash, bool encoder_only) {
     Workspace& w = ctx->ws;
@@ -177,7 +181,13 @@ static void forward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, cons
         q.hfin = w.hfin + d * ENC_H; q.hfin_stride = 2 * ENC_H;
         q.reverse = d;
     }
-    launch_gru_fwd_enc(s, enc, B, L);
+    if (use_gru_tc(B)) {
+        enc[0].whh = params + lay.off[P_ENC_WHH_F];
+        enc[1].whh = params + lay.off[P_ENC_WHH_R];
+        launch_gru_fwd_enc_tc(s, enc, B, L, V);
+    } else {
+        launch_gru_fwd_enc(s, enc, B, L);
+    }
     // q_mu / q_logvar heads (models/encoder.py:50-51)
     launch_sgemm(s, B, ZD, 2 * ENC_H, 1.f, w.hfin, 2 * ENC_H, 1, params + lay.off[P_QMU_W], 1, 2 * ENC_H, 0.f,
                  mu, ZD, params + lay.off[P_QMU_B], 1, nullptr);
@@ -192,7 +202,12 @@ static void forward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, cons
     memset(&q, 0, sizeof(q));
     q.tok = w.tokd; q.table = w.d.t_dec; q.rowbias = w.rowbias; q.whh_t = w.d.whh_t_dec; q.bhn = w.d.bhn_dec;
     q.h0 = w.zc; q.hs = w.dec_hs; q.gates = stash ? w.dec_gates : nullptr;
-    launch_gru_fwd_dec(s, q, B, L);
+    if (use_gru_tc(B)) {
+        q.whh = w.d.whh_dec;
+        launch_gru_fwd_dec_tc(s, q, B, L, V);
+    } else {
+        launch_gru_fwd_dec(s, q, B, L);
+    }
 }
 
 static DecOutArgs dec_out_args(cpg_ctx* ctx, const cpg_wae_inputs* in, int V, int B, int L) {
@@ -220,7 +235,8 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     memset(&q, 0, sizeof(q));
     q.whh = w.d.whh_dec; q.h0 = w.zc; q.hs = w.dec_hs; q.gates = w.dec_gates;
     q.dh_out = w.dec_dh_out; q.dg = w.dec_dg; q.dh0 = w.dh0; q.drow = w.drow;
-    launch_gru_bwd_dec(s, q, B, L);
+    if (use_gru_tc(B)) launch_gru_bwd_dec_tc(s, q, B, L);
+    else launch_gru_bwd_dec(s, q, B, L);
     // gradient at [z;c]:  dh0 + drow @ W_ih[:,150:]   (in place on dh0)
     launch_sgemm(s, B, DEC_HP, 3 * DEC_HP, 1.f, w.drow, 3 * DEC_HP, 1, w.d.wizc, DEC_HP, 1, 1.f, w.dh0, DEC_HP,
                  nullptr, 1, nullptr);
@@ -253,7 +269,8 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
         e.dh_fin = w.dhfin + d * ENC_H; e.dh_fin_stride = 2 * ENC_H;
         e.dg = w.enc_dg[d];
     }
-    launch_gru_bwd_enc(s, enc, B, L);
+    if (use_gru_tc(B)) launch_gru_bwd_enc_tc(s, enc, B, L);
+    else launch_gru_bwd_enc(s, enc, B, L);
     // recurrent weight gradients
     // (the tensor-core path produces the token-table gradient in the same pass over dg)
     const bool t0 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[0], w.enc_hs[0], nullptr, w.tok, 0, V, B, L, sm, w.wg_part,

@@ -1,22 +1,27 @@
-// Encoder bi-GRU forward recurrence on the 5th-gen tensor cores with fp32-grade accuracy.
+// GRU recurrences (forward with activation stash, and BPTT) on the 5th-gen tensor cores, with
+// fp32-grade accuracy.  Same math and the same HBM stash layouts as the fp32 SIMT kernels of gru.cu
+// (models/encoder.py:25-30,42 and models/decoder.py:40,77; gate order r,z,n; h' = (1-z) n + z h),
+// so either flavour of forward pairs with either flavour of backward.
 //
-// Per step the hidden-state contraction  G[128 x 240] = h[128 x 80] . W_hh^T  runs as tcgen05.mma
-// (kind::f16, bf16 operands, fp32 accumulation in TMEM).  To keep the fp32 parity the path is held to
-// (1e-4 on mu / logvar / logits), both operands are split into three bf16 terms,
-//     x = x1 + x2 + x3   (8 + 8 + 8 mantissa bits),
-// and the six products whose weight is >= 2^-16 are accumulated:  h1W1 + h1W2 + h2W1 + h2W2 + h3W1 + h1W3
-// (the dropped terms are <= 2^-24 relative, i.e. fp32 rounding level).  30 MMAs of M=128, N=240, K=16
-// per step replace 128*80*240 fp32 FMAs.
+// Formulation.  The batch is the N side of the MMA and the weights are the M side ("transposed"):
+//     forward   G^T[3H x nb] = W_hh[3H x H]   . h^T[H x nb]          (M tiles of 128 gate rows)
+//     backward  dh^T[H x nb] = W_hh^T[H x 3H] . (dr,dz,dhn)^T[3H x nb]
+// N = 32 batch rows per MMA, so B = 4096 gives 128 CTAs whatever the hidden size (the row-major
+// variant is stuck at M = 128 rows per tile, i.e. 32..64 CTAs on 148 SMs).  tcgen05.mma kind::f16 with
+// bf16 operands and fp32 accumulation in TMEM; every fp32 operand x is split x = x1 + x2 (two bf16
+// terms, 16 mantissa bits) and the three products x1 w1 + x1 w2 + x2 w1 are accumulated: relative
+// error 2^-16 per term, well inside the 1e-4 parity bar of the path (a single bf16/tf32 pass is not).
 //
-// One CTA owns 128 batch rows of one direction for all L steps:
-//   warp 8      : TMEM owner + MMA issuer
-//   warps 0..7  : gate epilogue; warp w serves TMEM lanes 32 (w % 4) .. +31 (thread = batch row) and the
-//                 hidden units 40 (w / 4) .. +39.  Per step: tcgen05.ld the three gate pre-activations,
-//                 add the token-table row, sigmoid / tanh, h' = (1-z) n + z h, stash (h, r, z, n, hn)
-//                 for BPTT, split h' into 3 bf16 terms and write them as the next step's A operand.
-// W_hh splits (115 KB), the h splits (60 KB) and the token table (23 KB) stay in shared memory.
-// Operand layout: K-major, no swizzle ("interleaved" 8x16-byte core matrices), so a thread's 16-byte
-// store of 8 consecutive units of its row is exactly one core-matrix row.
+// One CTA = NSUB sub-tiles of 32 batch rows of one direction, all L steps:
+//   warp NW (last) : TMEM owner; one elected thread issues the MMAs of a sub-tile as soon as that
+//                    sub-tile's operand tile of the previous step is complete (mbarrier bar_x)
+//   warps 0..NW-1  : per sub-tile and step
+//        phase 1  tcgen05.ld (lane = gate row, 32 batch columns) -> P[batch][gate] in shared memory
+//        phase 2  thread = (batch row, 4 consecutive hidden units): gate math, fp32 stash to HBM with
+//                 row-contiguous float4 stores, next operand tile (bf16 split, K-major core matrices)
+//   With NSUB = 2 the MMAs of one sub-tile run under the epilogue of the other (ping-pong).
+// W_hh (both bf16 terms) stays in shared memory for all L steps; operand tiles use the no-swizzle
+// K-major core-matrix layout with a 16-byte pad on the K stride (bank-conflict-free 8-byte stores).
 #include "ctx.h"
 #ifndef CPG_EMU
 #include <cuda_bf16.h>
@@ -26,17 +31,10 @@ namespace cpg {
 int check_launch(const char* where);
 
 namespace {
-constexpr int TH = ENC_H;                 // 80
-constexpr int TG = 3 * TH;                // 240 gate columns
-constexpr int TM = 128;                   // rows per CTA
-constexpr int KC = TH / 8;                // 10 K core matrices (8 bf16 each)
-constexpr int KSTEPS = TH / 16;           // 5 MMAs of K = 16 per product
-constexpr int W_SPLIT_BYTES = TG * TH * 2;            // 38,400
-constexpr int A_SPLIT_BYTES = TM * TH * 2;            // 20,480
-constexpr int W_LBO = (TG / 8) * 128, W_SBO = 128;    // K-adjacent / N-adjacent core-matrix strides
-constexpr int A_LBO = (TM / 8) * 128, A_SBO = 128;
-constexpr int EPI_WARPS = 8;
-constexpr int NTHREADS = (EPI_WARPS + 1) * 32;
+constexpr int NBS = 32;                               // batch rows per sub-tile = MMA N
+constexpr int X_LBO = (NBS / 8) * 128 + 16;           // K-adjacent core matrices of an operand tile (padded)
+constexpr int X_SBO = 128;                            // N-adjacent core matrices
+constexpr int W_SBO = 128;                            // M-adjacent core matrices of the weight tile
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -49,81 +47,152 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
-// x -> three bf16 terms (round-to-nearest each), packed pairwise by the caller
-__device__ __forceinline__ void split3(float x, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
-    a = __float2bfloat16_rn(x);
-    float r1 = x - __bfloat162float(a);
-    b = __float2bfloat16_rn(r1);
-    float r2 = r1 - __bfloat162float(b);
-    c = __float2bfloat16_rn(r2);
-}
 __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
     return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
 }
+// 4 fp32 -> 4 bf16 leading terms + 4 bf16 remainders
+__device__ __forceinline__ void split4(const float (&x)[4], uint2& hi, uint2& lo) {
+    __nv_bfloat16 a[4], b[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        a[e] = __float2bfloat16_rn(x[e]);
+        b[e] = __float2bfloat16_rn(x[e] - __bfloat162float(a[e]));
+    }
+    hi = make_uint2(pack2(a[0], a[1]), pack2(a[2], a[3]));
+    lo = make_uint2(pack2(b[0], b[1]), pack2(b[2], b[3]));
+}
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+    __nv_bfloat16 a[8], b[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        a[e] = __float2bfloat16_rn(x[e]);
+        b[e] = __float2bfloat16_rn(x[e] - __bfloat162float(a[e]));
+    }
+    hi = make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
+    lo = make_uint4(pack2(b[0], b[1]), pack2(b[2], b[3]), pack2(b[4], b[5]), pack2(b[6], b[7]));
+}
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-struct EncTcArgs {
+// (operand-tile term, weight term) of the three accumulated products
+__device__ constexpr int XS[3] = {0, 0, 1};
+__device__ constexpr int WS[3] = {0, 1, 0};
+
+// ------------------------------------------------------------------------------------- forward
+template <int HP_, int KP_, int NSUB_, bool DEC_>
+struct FwdCfg {
+    static constexpr int HP = HP_, KP = KP_, NSUB = NSUB_;
+    static constexpr bool DEC = DEC_;
+    static constexpr int G3 = 3 * HP;                       // gate rows (M)
+    static constexpr int MT = (G3 + 127) / 128;             // M tiles
+    static constexpr int NQ = HP / 4;                       // unit quads per row
+    static constexpr int ITEMS = 2;                         // (row, quad) items per thread and sub-tile
+    static constexpr int NT_EPI = NBS * NQ / ITEMS;         // 320 | 416
+    static constexpr int NW_EPI = NT_EPI / 32;
+    static constexpr int NTHREADS = NT_EPI + 32;
+    static constexpr int KC = KP / 8, KSTEPS = KP / 16;
+    static constexpr int W_LBO = (G3 / 8) * 128;
+    static constexpr int W_SPLIT = KC * W_LBO;
+    static constexpr int X_SPLIT = KC * X_LBO;
+    static constexpr int P_FLOATS = NBS * G3;
+    static constexpr uint32_t TMEM_COLS = 128;
+    static_assert(NSUB * MT * NBS <= 128, "TMEM columns");
+    static_assert(NT_EPI % 32 == 0 && NT_EPI % NQ == 0 && MT * 4 <= NW_EPI, "thread mapping");
+    static_assert(HP % 8 == 0 && KP % 16 == 0 && G3 % 8 == 0, "core-matrix geometry");
+    static size_t smem_bytes(int V, int L) {
+        return 2 * (size_t)W_SPLIT + (size_t)NSUB * 2 * X_SPLIT + (size_t)NSUB * P_FLOATS * 4 +
+               (DEC ? 0 : (size_t)V * G3 * 4) + (size_t)NSUB * NBS * L + 128;
+    }
+};
+
+struct FwdArgs {
     const uint8_t* tok;        // [B][L]
-    const float* table[2];     // [V][240] per direction
-    const float* whh[2];       // [240][80] natural (N x K, K contiguous)
-    const float* bhn[2];       // [80]
-    float* hs[2];              // [B][L][80] by step (nullable)
-    float* gates[2];           // [B][L][4][80] (nullable)
-    float* hfin;               // [B][160]
+    const float* table[2];     // [V][3*HP] per direction
+    const float* whh[2];       // [3*HP][HP] natural (zero padded for the decoder)
+    const float* bhn[2];       // [HP]
+    const float* rowbias;      // decoder: [B][3*HP]
+    const float* h0;           // decoder: [B][HP]
+    float* hs[2];              // [B][L][HP] by step (nullable)
+    float* gates[2];           // [B][L][4][HP] (nullable)
+    float* hfin;               // encoder: [B][2*HP]
     int B, L, V;
 };
-}  // namespace
 
-__global__ void __launch_bounds__(NTHREADS, 1)
-k_gru_fwd_enc_tc(EncTcArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+template <class C>
+__global__ void __launch_bounds__(C::NTHREADS, 1)
+k_gru_fwd_tc(FwdArgs a) {
+    constexpr int HP = C::HP, G3 = C::G3, MT = C::MT, NQ = C::NQ, NSUB = C::NSUB, KC = C::KC;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    unsigned char* Wb = smem;                                   // [3][KC][TG/8][128 B]
-    unsigned char* Ab = Wb + 3 * W_SPLIT_BYTES;                 // [3][KC][TM/8][128 B]
-    float* tab = reinterpret_cast<float*>(Ab + 3 * A_SPLIT_BYTES);   // [V][240]
-    __shared__ __align__(8) uint64_t bar_a, bar_d;
+    unsigned char* Wb = smem;                                            // [2 terms][KC][G3/8][128 B]
+    unsigned char* Xb = Wb + 2 * C::W_SPLIT;                             // [NSUB][2 terms][KC][X_LBO]
+    float* Pb = reinterpret_cast<float*>(Xb + NSUB * 2 * C::X_SPLIT);    // [NSUB][NBS][G3]
+    float* tab = Pb + NSUB * C::P_FLOATS;                                // encoder: [V][G3]
+    uint8_t* toks = reinterpret_cast<uint8_t*>(tab + (C::DEC ? 0 : a.V * G3));   // [NSUB*NBS][L]
+    __shared__ __align__(8) uint64_t bar_x[NSUB], bar_d[NSUB];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
-    const int row0 = blockIdx.x * TM;
-    const int B = a.B, L = a.L, V = a.V;
+    const int row0 = blockIdx.x * (NSUB * NBS);
+    const int B = a.B, L = a.L;
 
-    // ---- one-time setup: W_hh -> 3 bf16 splits in core-matrix layout, table -> smem, A tiles = 0 (h0 = 0)
-    for (int idx = tid; idx < TG * KC; idx += NTHREADS) {
-        const int n = idx / KC, kc = idx % KC;
-        const float* src = a.whh[dir] + (size_t)n * TH + kc * 8;
-        const float4 f0 = ld4(src), f1 = ld4(src + 4);
-        const float x[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-        __nv_bfloat16 s1[8], s2[8], s3[8];
+    // ---- one-time setup
+    {
+        constexpr int WLD = HP;                                          // row stride of the natural weights
+        const float* whh = a.whh[dir];
+        for (int idx = tid; idx < G3 * KC; idx += C::NTHREADS) {
+            const int m = idx / KC, kc = idx % KC;
+            float x[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) split3(x[e], s1[e], s2[e], s3[e]);
-        const int off = kc * W_LBO + (n >> 3) * W_SBO + (n & 7) * 16;
-        *reinterpret_cast<uint4*>(Wb + 0 * W_SPLIT_BYTES + off) = make_uint4(pack2(s1[0], s1[1]), pack2(s1[2], s1[3]), pack2(s1[4], s1[5]), pack2(s1[6], s1[7]));
-        *reinterpret_cast<uint4*>(Wb + 1 * W_SPLIT_BYTES + off) = make_uint4(pack2(s2[0], s2[1]), pack2(s2[2], s2[3]), pack2(s2[4], s2[5]), pack2(s2[6], s2[7]));
-        *reinterpret_cast<uint4*>(Wb + 2 * W_SPLIT_BYTES + off) = make_uint4(pack2(s3[0], s3[1]), pack2(s3[2], s3[3]), pack2(s3[4], s3[5]), pack2(s3[6], s3[7]));
+            for (int e = 0; e < 8; ++e) x[e] = 0.f;
+            if (kc * 8 + 8 <= WLD) {
+                const float4 f0 = ldg4(whh + (size_t)m * WLD + kc * 8), f1 = ldg4(whh + (size_t)m * WLD + kc * 8 + 4);
+                x[0] = f0.x; x[1] = f0.y; x[2] = f0.z; x[3] = f0.w; x[4] = f1.x; x[5] = f1.y; x[6] = f1.z; x[7] = f1.w;
+            }
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            const int off = kc * C::W_LBO + (m >> 3) * W_SBO + (m & 7) * 16;
+            *reinterpret_cast<uint4*>(Wb + off) = hi;
+            *reinterpret_cast<uint4*>(Wb + C::W_SPLIT + off) = lo;
+        }
+        for (int idx = tid; idx < NSUB * NBS * KC; idx += C::NTHREADS) {
+            const int bb = idx / KC, kc = idx % KC, sub = bb / NBS, b = bb % NBS;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = 0.f;
+            if (C::DEC && kc * 8 + 8 <= HP) {
+                const int row = min(row0 + bb, B - 1);
+                const float4 f0 = ldg4(a.h0 + (size_t)row * HP + kc * 8), f1 = ldg4(a.h0 + (size_t)row * HP + kc * 8 + 4);
+                x[0] = f0.x; x[1] = f0.y; x[2] = f0.z; x[3] = f0.w; x[4] = f1.x; x[5] = f1.y; x[6] = f1.z; x[7] = f1.w;
+            }
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            const int off = kc * X_LBO + (b >> 3) * X_SBO + (b & 7) * 16;
+            *reinterpret_cast<uint4*>(Xb + (sub * 2 + 0) * C::X_SPLIT + off) = hi;
+            *reinterpret_cast<uint4*>(Xb + (sub * 2 + 1) * C::X_SPLIT + off) = lo;
+        }
+        if (!C::DEC)
+            for (int i = tid; i < a.V * G3; i += C::NTHREADS) tab[i] = a.table[dir][i];
+        for (int i = tid; i < NSUB * NBS * L; i += C::NTHREADS) {
+            const int row = min(row0 + i / L, B - 1);
+            toks[i] = a.tok[(size_t)row * L + i % L];
+        }
     }
-    for (int i = tid; i < 3 * A_SPLIT_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(Ab)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < V * TG; i += NTHREADS) tab[i] = a.table[dir][i];
-    if (warp == EPI_WARPS) {
+    if (warp == C::NW_EPI) {
         if (lane == 0) {
-            tc::mbar_init(&bar_a, EPI_WARPS * 32);
-            tc::mbar_init(&bar_d, 1);
+            for (int i = 0; i < NSUB; ++i) {
+                tc::mbar_init(&bar_x[i], C::NT_EPI);
+                tc::mbar_init(&bar_d[i], 1);
+            }
             tc::fence_barrier_init();
         }
         __syncwarp();
-        tc::tmem_alloc<256>(&tmem_slot);
+        tc::tmem_alloc<C::TMEM_COLS>(&tmem_slot);
     }
     tc::fence_proxy_async();
     tc::tc_fence_before();
@@ -131,114 +200,433 @@ k_gru_fwd_enc_tc(EncTcArgs a) {
     tc::tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
 
-    if (warp == EPI_WARPS) {
+    if (warp == C::NW_EPI) {
         // ---------------- MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(TM, TG);
-            const uint32_t a0 = tc::smem_u32(Ab), w0 = tc::smem_u32(Wb);
-            // (h split, W split) products with weight >= 2^-16
-            const int ha[6] = {0, 0, 1, 1, 2, 0};
-            const int wb[6] = {0, 1, 0, 1, 0, 2};
+            constexpr uint32_t idesc = make_idesc_bf16(128, NBS);
+            const uint32_t w0 = tc::smem_u32(Wb), x0 = tc::smem_u32(Xb);
             for (int s = 0; s < L; ++s) {
-                if (s > 0) {
-                    tc::mbar_wait(&bar_a, (s - 1) & 1);          // h of step s-1 written by all epilogue threads
-                    tc::tc_fence_after();
-                }
-                uint32_t acc = 0;
 #pragma unroll
-                for (int p = 0; p < 6; ++p) {
-#pragma unroll
-                    for (int ks = 0; ks < KSTEPS; ++ks) {
-                        const uint64_t da = tc::make_smem_desc(a0 + ha[p] * A_SPLIT_BYTES + ks * 2 * A_LBO, A_LBO, A_SBO, 0);
-                        const uint64_t db = tc::make_smem_desc(w0 + wb[p] * W_SPLIT_BYTES + ks * 2 * W_LBO, W_LBO, W_SBO, 0);
-                        umma_bf16(tmem_d, da, db, idesc, acc);
-                        acc = 1;
+                for (int sub = 0; sub < NSUB; ++sub) {
+                    if (s > 0) {
+                        tc::mbar_wait(&bar_x[sub], (s - 1) & 1);
+                        tc::tc_fence_after();
                     }
+#pragma unroll
+                    for (int t = 0; t < MT; ++t) {
+                        uint32_t acc = 0;
+#pragma unroll
+                        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+                            for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                                const uint64_t da = tc::make_smem_desc(w0 + WS[p] * C::W_SPLIT + t * 16 * W_SBO + ks * 2 * C::W_LBO,
+                                                                       C::W_LBO, W_SBO, 0);
+                                const uint64_t db = tc::make_smem_desc(x0 + (sub * 2 + XS[p]) * C::X_SPLIT + ks * 2 * X_LBO,
+                                                                       X_LBO, X_SBO, 0);
+                                umma_bf16(tmem_d + (uint32_t)((sub * MT + t) * NBS), da, db, idesc, acc);
+                                acc = 1;
+                            }
+                        }
+                    }
+                    tc::umma_commit(&bar_d[sub]);
                 }
-                tc::umma_commit(&bar_d);
             }
         }
         __syncwarp();
     } else {
-        // ---------------- gate epilogue: thread = batch row (TMEM lane), 40 hidden units
-        const int q = warp & 3, half = warp >> 2;
-        const int rl = q * 32 + lane;                           // row within the tile = TMEM lane
-        const int row = row0 + rl;
-        const bool ok = row < B;
-        const int rowc = ok ? row : (B - 1);
-        const int u0 = half * (TH / 2);
-        const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16);
-        float hprev[TH / 2];
+        // ---------------- epilogue
+        const int quad = tid % NQ, j0 = quad * 4, bq = tid / NQ;        // item it -> batch row bq + 16 it
+        const float4 bhn4 = ldg4(a.bhn[dir] + j0);
+        const float bhn[4] = {bhn4.x, bhn4.y, bhn4.z, bhn4.w};
+        float hprev[NSUB][C::ITEMS][4];
+        float rb[C::DEC ? C::ITEMS : 1][3][4];
 #pragma unroll
-        for (int i = 0; i < TH / 2; ++i) hprev[i] = 0.f;
-        const float* bhn = a.bhn[dir];
+        for (int sub = 0; sub < NSUB; ++sub)
+#pragma unroll
+            for (int it = 0; it < C::ITEMS; ++it) {
+                const int row = min(row0 + sub * NBS + bq + 16 * it, B - 1);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (C::DEC) {
+                    v = ldg4(a.h0 + (size_t)row * HP + j0);
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        const float4 r4 = ldg4(a.rowbias + (size_t)row * G3 + g * HP + j0);
+                        rb[C::DEC ? it : 0][g][0] = r4.x; rb[C::DEC ? it : 0][g][1] = r4.y;
+                        rb[C::DEC ? it : 0][g][2] = r4.z; rb[C::DEC ? it : 0][g][3] = r4.w;
+                    }
+                }
+                hprev[sub][it][0] = v.x; hprev[sub][it][1] = v.y; hprev[sub][it][2] = v.z; hprev[sub][it][3] = v.w;
+            }
+        const float* tabg = C::DEC ? a.table[dir] : tab;
+        float* hs_g = a.hs[dir];
+        float* gates_g = a.gates[dir];
+
         for (int s = 0; s < L; ++s) {
             const int t = dir ? (L - 1 - s) : s;
-            const int tk = a.tok[(size_t)rowc * L + t];
-            const float* trow = tab + tk * TG;
-            tc::mbar_wait(&bar_d, s & 1);
-            tc::tc_fence_after();
-            const size_t bs = (size_t)rowc * L + s;
 #pragma unroll
-            for (int blk = 0; blk < TH / 16; ++blk) {            // 5 blocks of 8 units
-                const int j0 = u0 + blk * 8;
-                float gr[8], gz[8], gn[8];
-                tmem_ld_32x8(lane_addr + (uint32_t)(j0), gr);
-                tmem_ld_32x8(lane_addr + (uint32_t)(TH + j0), gz);
-                tmem_ld_32x8(lane_addr + (uint32_t)(2 * TH + j0), gn);
-                tmem_ld_wait();
-                float hn[8], rr[8], zz[8], nn[8], hh[8];
+            for (int sub = 0; sub < NSUB; ++sub) {
+                float* P = Pb + sub * C::P_FLOATS;
+                tc::mbar_wait(&bar_d[sub], s & 1);
+                tc::tc_fence_after();
+                // phase 1: accumulator (lane = gate row, 32 batch columns) -> P[batch][gate]
+                if (warp < MT * 4) {
+                    const int tq = warp >> 2, q = warp & 3;
+                    float v[32];
+                    tc::tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((sub * MT + tq) * NBS), v);
+                    const int m = tq * 128 + q * 32 + lane;
+                    if (m < G3) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int j = j0 + e;
-                    rr[e] = sigmoid_fast(trow[j] + gr[e]);
-                    zz[e] = sigmoid_fast(trow[TH + j] + gz[e]);
-                    hh[e] = gn[e] + bhn[j];
-                    nn[e] = tanh_fast(trow[2 * TH + j] + rr[e] * hh[e]);
-                    hn[e] = (1.0f - zz[e]) * nn[e] + zz[e] * hprev[blk * 8 + e];
-                    hprev[blk * 8 + e] = hn[e];
-                }
-                __nv_bfloat16 s1[8], s2[8], s3[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split3(hn[e], s1[e], s2[e], s3[e]);
-                const int off = (j0 >> 3) * A_LBO + (rl >> 3) * A_SBO + (rl & 7) * 16;
-                *reinterpret_cast<uint4*>(Ab + 0 * A_SPLIT_BYTES + off) = make_uint4(pack2(s1[0], s1[1]), pack2(s1[2], s1[3]), pack2(s1[4], s1[5]), pack2(s1[6], s1[7]));
-                *reinterpret_cast<uint4*>(Ab + 1 * A_SPLIT_BYTES + off) = make_uint4(pack2(s2[0], s2[1]), pack2(s2[2], s2[3]), pack2(s2[4], s2[5]), pack2(s2[6], s2[7]));
-                *reinterpret_cast<uint4*>(Ab + 2 * A_SPLIT_BYTES + off) = make_uint4(pack2(s3[0], s3[1]), pack2(s3[2], s3[3]), pack2(s3[4], s3[5]), pack2(s3[6], s3[7]));
-                if (ok) {
-                    if (a.hs[dir] != nullptr) {
-                        float* o = a.hs[dir] + bs * TH + j0;
-                        st4(o, make_float4(hn[0], hn[1], hn[2], hn[3]));
-                        st4(o + 4, make_float4(hn[4], hn[5], hn[6], hn[7]));
-                    }
-                    if (a.gates[dir] != nullptr) {
-                        float* g = a.gates[dir] + bs * 4 * TH + j0;
-                        st4(g, make_float4(rr[0], rr[1], rr[2], rr[3])); st4(g + 4, make_float4(rr[4], rr[5], rr[6], rr[7]));
-                        st4(g + TH, make_float4(zz[0], zz[1], zz[2], zz[3])); st4(g + TH + 4, make_float4(zz[4], zz[5], zz[6], zz[7]));
-                        st4(g + 2 * TH, make_float4(nn[0], nn[1], nn[2], nn[3])); st4(g + 2 * TH + 4, make_float4(nn[4], nn[5], nn[6], nn[7]));
-                        st4(g + 3 * TH, make_float4(hh[0], hh[1], hh[2], hh[3])); st4(g + 3 * TH + 4, make_float4(hh[4], hh[5], hh[6], hh[7]));
-                    }
-                    if (s == L - 1) {
-                        float* f = a.hfin + (size_t)row * (2 * TH) + dir * TH + j0;
-                        st4(f, make_float4(hn[0], hn[1], hn[2], hn[3]));
-                        st4(f + 4, make_float4(hn[4], hn[5], hn[6], hn[7]));
+                        for (int c = 0; c < 32; ++c) P[c * G3 + m] = v[c];
                     }
                 }
+                tc::tc_fence_before();
+                epi_bar_sync<C::NT_EPI>();
+                // phase 2: gates for (row, 4 units)
+#pragma unroll
+                for (int it = 0; it < C::ITEMS; ++it) {
+                    const int b = bq + 16 * it;
+                    const int row = row0 + sub * NBS + b;
+                    const int tk = toks[(sub * NBS + b) * L + t];
+                    const float4 pr = ld4(P + b * G3 + j0), pz = ld4(P + b * G3 + HP + j0), pn = ld4(P + b * G3 + 2 * HP + j0);
+                    const float* trow = tabg + tk * G3 + j0;
+                    float4 tr, tz, tn;
+                    if (C::DEC) { tr = ldg4(trow); tz = ldg4(trow + HP); tn = ldg4(trow + 2 * HP); }
+                    else { tr = ld4(trow); tz = ld4(trow + HP); tn = ld4(trow + 2 * HP); }
+                    float gr[4] = {tr.x + pr.x, tr.y + pr.y, tr.z + pr.z, tr.w + pr.w};
+                    float gz[4] = {tz.x + pz.x, tz.y + pz.y, tz.z + pz.z, tz.w + pz.w};
+                    float gn[4] = {tn.x, tn.y, tn.z, tn.w};
+                    const float pnv[4] = {pn.x, pn.y, pn.z, pn.w};
+                    float rr[4], zz[4], nn[4], hh[4], hn[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (C::DEC) {
+                            gr[e] += rb[C::DEC ? it : 0][0][e];
+                            gz[e] += rb[C::DEC ? it : 0][1][e];
+                            gn[e] += rb[C::DEC ? it : 0][2][e];
+                        }
+                        rr[e] = sigmoid_fast(gr[e]);
+                        zz[e] = sigmoid_fast(gz[e]);
+                        hh[e] = pnv[e] + bhn[e];
+                        nn[e] = tanh_fast(gn[e] + rr[e] * hh[e]);
+                        hn[e] = (1.0f - zz[e]) * nn[e] + zz[e] * hprev[sub][it][e];
+                        hprev[sub][it][e] = hn[e];
+                    }
+                    uint2 hi, lo;
+                    split4(hn, hi, lo);
+                    const int off = (j0 >> 3) * X_LBO + (b >> 3) * X_SBO + (b & 7) * 16 + (j0 & 7) * 2;
+                    *reinterpret_cast<uint2*>(Xb + (sub * 2 + 0) * C::X_SPLIT + off) = hi;
+                    *reinterpret_cast<uint2*>(Xb + (sub * 2 + 1) * C::X_SPLIT + off) = lo;
+                    if (row < B) {
+                        const size_t bs = (size_t)row * L + s;
+                        if (hs_g != nullptr) st4(hs_g + bs * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
+                        if (gates_g != nullptr) {
+                            float* g = gates_g + bs * 4 * HP + j0;
+                            st4(g, make_float4(rr[0], rr[1], rr[2], rr[3]));
+                            st4(g + HP, make_float4(zz[0], zz[1], zz[2], zz[3]));
+                            st4(g + 2 * HP, make_float4(nn[0], nn[1], nn[2], nn[3]));
+                            st4(g + 3 * HP, make_float4(hh[0], hh[1], hh[2], hh[3]));
+                        }
+                        if (!C::DEC && s == L - 1)
+                            st4(a.hfin + (size_t)row * (2 * HP) + dir * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
+                    }
+                }
+                tc::fence_proxy_async();                         // operand-tile stores -> visible to the tensor core
+                tc::mbar_arrive(&bar_x[sub]);
             }
-            tc::fence_proxy_async();                             // A-tile stores -> visible to the tensor core
-            tc::tc_fence_before();                               // TMEM reads ordered before the next MMA overwrites D
-            tc::mbar_arrive(&bar_a);
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == EPI_WARPS) tc::tmem_dealloc<256>(tmem_d);
+    if (warp == C::NW_EPI) tc::tmem_dealloc<C::TMEM_COLS>(tmem_d);
 }
 
-size_t gru_tc_enc_smem(int V) { return (size_t)3 * W_SPLIT_BYTES + 3 * A_SPLIT_BYTES + (size_t)V * TG * 4 + 256; }
+// ------------------------------------------------------------------------------------ backward
+// Per step (reverse step order), as in gru.cu:
+//   dht = dh + dh_out[s];  dn = dht (1-z); dz = dht (h_prev - n); carry = dht z
+//   dn_pre = dn (1-n^2); dr = dn_pre hn; dhn = dn_pre r; dr_pre = dr r (1-r); dz_pre = dz z (1-z)
+//   dh = carry + W_hh^T [dr_pre, dz_pre, dhn]
+template <int HP_, int NSUB_, bool DEC_>
+struct BwdCfg {
+    static constexpr int HP = HP_, NSUB = NSUB_;
+    static constexpr bool DEC = DEC_;
+    static constexpr int K3 = 3 * HP;
+    static constexpr int KPAD = (K3 + 15) / 16 * 16;        // 240 | 320
+    static constexpr int KC = KPAD / 8, KSTEPS = KPAD / 16;
+    static constexpr int NQ = HP / 4;
+    static constexpr int ITEMS = 2;
+    static constexpr int NT_EPI = NBS * NQ / ITEMS;
+    static constexpr int NW_EPI = NT_EPI / 32;
+    static constexpr int NTHREADS = NT_EPI + 32;
+    static constexpr int A_LBO = (HP / 8) * 128;
+    static constexpr int A_SPLIT = KC * A_LBO;
+    static constexpr int X_SPLIT = KC * X_LBO;
+    static constexpr int P_FLOATS = NBS * HP;
+    static constexpr uint32_t TMEM_COLS = NSUB * NBS < 32 ? 32 : NSUB * NBS;
+    static_assert(HP <= 128 && NT_EPI % NQ == 0 && NW_EPI >= 4, "thread mapping");
+    // the M = 128 tile reads 16 core-matrix rows per K chunk; rows >= HP alias the next chunk / the
+    // operand tiles that follow (finite garbage in accumulator rows nobody reads)
+    static size_t smem_bytes() { return 2 * (size_t)A_SPLIT + (size_t)NSUB * 2 * X_SPLIT + (size_t)NSUB * P_FLOATS * 4 + 128; }
+};
+
+struct BwdArgs {
+    const float* whh[2];       // [3*HP][HP] natural
+    const float* hs[2];        // [B][L][HP]
+    const float* gates[2];     // [B][L][4][HP]
+    const float* h0;           // decoder: [B][HP] (null = zeros)
+    const float* dh_out;       // decoder: [B][L][HP]
+    const float* dh_fin;       // encoder: [B][2*HP]
+    float* dg[2];              // [B][L][4][HP]
+    float* dh0;                // decoder: [B][HP]
+    float* drow;               // decoder: [B][3*HP]
+    int B, L;
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NTHREADS, 1)
+k_gru_bwd_tc(BwdArgs a) {
+    constexpr int HP = C::HP, NQ = C::NQ, NSUB = C::NSUB, KC = C::KC, K3 = C::K3;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    unsigned char* Ab = smem;                                            // W_hh^T: [2 terms][KC][HP/8][128 B]
+    unsigned char* Xb = Ab + 2 * C::A_SPLIT;                             // [NSUB][2 terms][KC][X_LBO]
+    float* Pb = reinterpret_cast<float*>(Xb + NSUB * 2 * C::X_SPLIT);    // [NSUB][NBS][HP]
+    __shared__ __align__(8) uint64_t bar_x[NSUB], bar_d[NSUB];
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dir = blockIdx.y;
+    const int row0 = blockIdx.x * (NSUB * NBS);
+    const int B = a.B, L = a.L;
+
+    // ---- one-time setup: A[j][k] = W_hh[k][j] as two bf16 terms; operand tiles zeroed (K padding stays 0)
+    {
+        const float* whh = a.whh[dir];
+        for (int idx = tid; idx < KC * HP; idx += C::NTHREADS) {
+            const int kc = idx / HP, j = idx % HP;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = kc * 8 + e;
+                x[e] = k < K3 ? __ldg(whh + (size_t)k * HP + j) : 0.f;
+            }
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            const int off = kc * C::A_LBO + (j >> 3) * W_SBO + (j & 7) * 16;
+            *reinterpret_cast<uint4*>(Ab + off) = hi;
+            *reinterpret_cast<uint4*>(Ab + C::A_SPLIT + off) = lo;
+        }
+        for (int i = tid; i < NSUB * 2 * C::X_SPLIT / 16; i += C::NTHREADS) reinterpret_cast<uint4*>(Xb)[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (warp == C::NW_EPI) {
+        if (lane == 0) {
+            for (int i = 0; i < NSUB; ++i) {
+                tc::mbar_init(&bar_x[i], C::NT_EPI);
+                tc::mbar_init(&bar_d[i], 1);
+            }
+            tc::fence_barrier_init();
+        }
+        __syncwarp();
+        tc::tmem_alloc<C::TMEM_COLS>(&tmem_slot);
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = tmem_slot;
+
+    if (warp == C::NW_EPI) {
+        // ---------------- MMA issuer: iteration i handles step s = L-1-i
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, NBS);
+            const uint32_t a0 = tc::smem_u32(Ab), x0 = tc::smem_u32(Xb);
+            for (int i = 0; i < L; ++i) {
+#pragma unroll
+                for (int sub = 0; sub < NSUB; ++sub) {
+                    tc::mbar_wait(&bar_x[sub], i & 1);
+                    tc::tc_fence_after();
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+#pragma unroll 5
+                        for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                            const uint64_t da = tc::make_smem_desc(a0 + WS[p] * C::A_SPLIT + ks * 2 * C::A_LBO, C::A_LBO, W_SBO, 0);
+                            const uint64_t db = tc::make_smem_desc(x0 + (sub * 2 + XS[p]) * C::X_SPLIT + ks * 2 * X_LBO, X_LBO, X_SBO, 0);
+                            umma_bf16(tmem_d + (uint32_t)(sub * NBS), da, db, idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    tc::umma_commit(&bar_d[sub]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- epilogue
+        const int quad = tid % NQ, j0 = quad * 4, bq = tid / NQ;
+        const float* hs_g = a.hs[dir];
+        const float* gates_g = a.gates[dir];
+        float* dg_g = a.dg[dir];
+        float carry[NSUB][C::ITEMS][4];
+        float rs[C::DEC ? C::ITEMS : 1][3][4];
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub)
+#pragma unroll
+            for (int it = 0; it < C::ITEMS; ++it)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) carry[sub][it][e] = 0.f;
+        if (C::DEC) {
+#pragma unroll
+            for (int it = 0; it < C::ITEMS; ++it)
+#pragma unroll
+                for (int g = 0; g < 3; ++g)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) rs[C::DEC ? it : 0][g][e] = 0.f;
+        }
+        // prefetch registers for the step about to be processed: gates (r,z,n,hn), h_prev, dh_out
+        float4 pg[NSUB][C::ITEMS][4], ph[NSUB][C::ITEMS], pd[NSUB][C::ITEMS];
+        auto prefetch = [&](int sub, int s) {
+#pragma unroll
+            for (int it = 0; it < C::ITEMS; ++it) {
+                const int row = min(row0 + sub * NBS + bq + 16 * it, B - 1);
+                const size_t bs = (size_t)row * L + s;
+                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int pl = 0; pl < 4; ++pl) pg[sub][it][pl] = ldg4(gates_g + (bs * 4 + pl) * HP + j0);
+                if (s > 0) ph[sub][it] = ldg4(hs_g + (bs - 1) * HP + j0);
+                else ph[sub][it] = (C::DEC && a.h0 != nullptr) ? ldg4(a.h0 + (size_t)row * HP + j0) : zero;
+                if (C::DEC) pd[sub][it] = ldg4(a.dh_out + bs * HP + j0);
+                else pd[sub][it] = (s == L - 1) ? ldg4(a.dh_fin + (size_t)row * (2 * HP) + dir * HP + j0) : zero;
+            }
+        };
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) prefetch(sub, L - 1);
+
+        for (int i = 0; i <= L; ++i) {
+            const int s = L - 1 - i;                             // i == L: only collects the last contraction (dh0)
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+                float* P = Pb + sub * C::P_FLOATS;
+                if (i > 0) {
+                    tc::mbar_wait(&bar_d[sub], (i - 1) & 1);
+                    tc::tc_fence_after();
+                    if (warp < 4) {                              // lane = hidden unit j (rows >= HP unused)
+                        float v[32];
+                        tc::tmem_ld_32x32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * NBS), v);
+                        const int j = warp * 32 + lane;
+                        if (j < HP) {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) P[c * HP + j] = v[c];
+                        }
+                    }
+                    tc::tc_fence_before();
+                    epi_bar_sync<C::NT_EPI>();
+                }
+#pragma unroll
+                for (int it = 0; it < C::ITEMS; ++it) {
+                    const int b = bq + 16 * it;
+                    const int row = row0 + sub * NBS + b;
+                    float dh[4] = {carry[sub][it][0], carry[sub][it][1], carry[sub][it][2], carry[sub][it][3]};
+                    if (i > 0) {
+                        const float4 p4 = ld4(P + b * HP + j0);
+                        dh[0] += p4.x; dh[1] += p4.y; dh[2] += p4.z; dh[3] += p4.w;
+                    }
+                    if (i == L) {
+                        if (C::DEC && row < B) {
+                            if (a.dh0 != nullptr) st4(a.dh0 + (size_t)row * HP + j0, make_float4(dh[0], dh[1], dh[2], dh[3]));
+                            if (a.drow != nullptr) {
+#pragma unroll
+                                for (int g = 0; g < 3; ++g)
+                                    st4(a.drow + (size_t)row * K3 + g * HP + j0,
+                                        make_float4(rs[C::DEC ? it : 0][g][0], rs[C::DEC ? it : 0][g][1],
+                                                    rs[C::DEC ? it : 0][g][2], rs[C::DEC ? it : 0][g][3]));
+                            }
+                        }
+                        continue;
+                    }
+                    const float r4[4] = {pg[sub][it][0].x, pg[sub][it][0].y, pg[sub][it][0].z, pg[sub][it][0].w};
+                    const float z4[4] = {pg[sub][it][1].x, pg[sub][it][1].y, pg[sub][it][1].z, pg[sub][it][1].w};
+                    const float n4[4] = {pg[sub][it][2].x, pg[sub][it][2].y, pg[sub][it][2].z, pg[sub][it][2].w};
+                    const float hn4[4] = {pg[sub][it][3].x, pg[sub][it][3].y, pg[sub][it][3].z, pg[sub][it][3].w};
+                    const float hp4[4] = {ph[sub][it].x, ph[sub][it].y, ph[sub][it].z, ph[sub][it].w};
+                    const float do4[4] = {pd[sub][it].x, pd[sub][it].y, pd[sub][it].z, pd[sub][it].w};
+                    float o_r[4], o_z[4], o_n[4], o_hn[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float dht = dh[e] + do4[e];
+                        const float dn = dht * (1.0f - z4[e]);
+                        const float dz = dht * (hp4[e] - n4[e]);
+                        carry[sub][it][e] = dht * z4[e];
+                        const float dn_pre = dn * (1.0f - n4[e] * n4[e]);
+                        const float dr = dn_pre * hn4[e];
+                        o_hn[e] = dn_pre * r4[e];
+                        o_r[e] = dr * r4[e] * (1.0f - r4[e]);
+                        o_z[e] = dz * z4[e] * (1.0f - z4[e]);
+                        o_n[e] = dn_pre;
+                        if (C::DEC) {
+                            rs[C::DEC ? it : 0][0][e] += o_r[e];
+                            rs[C::DEC ? it : 0][1][e] += o_z[e];
+                            rs[C::DEC ? it : 0][2][e] += o_n[e];
+                        }
+                    }
+                    // operand tile: K index = g*HP + j for (dr_pre, dz_pre, dhn)
+                    const int boff = (b >> 3) * X_SBO + (b & 7) * 16;
+                    uint2 hi, lo;
+                    unsigned char* X0 = Xb + (sub * 2 + 0) * C::X_SPLIT;
+                    unsigned char* X1 = Xb + (sub * 2 + 1) * C::X_SPLIT;
+                    split4(o_r, hi, lo);
+                    int k = j0;
+                    *reinterpret_cast<uint2*>(X0 + (k >> 3) * X_LBO + boff + (k & 7) * 2) = hi;
+                    *reinterpret_cast<uint2*>(X1 + (k >> 3) * X_LBO + boff + (k & 7) * 2) = lo;
+                    split4(o_z, hi, lo);
+                    k = HP + j0;
+                    *reinterpret_cast<uint2*>(X0 + (k >> 3) * X_LBO + boff + (k & 7) * 2) = hi;
+                    *reinterpret_cast<uint2*>(X1 + (k >> 3) * X_LBO + boff + (k & 7) * 2) = lo;
+                    split4(o_hn, hi, lo);
+                    k = 2 * HP + j0;
+                    *reinterpret_cast<uint2*>(X0 + (k >> 3) * X_LBO + boff + (k & 7) * 2) = hi;
+                    *reinterpret_cast<uint2*>(X1 + (k >> 3) * X_LBO + boff + (k & 7) * 2) = lo;
+                    if (row < B) {
+                        float* gp = dg_g + ((size_t)row * L + s) * 4 * HP + j0;
+                        st4(gp, make_float4(o_r[0], o_r[1], o_r[2], o_r[3]));
+                        st4(gp + HP, make_float4(o_z[0], o_z[1], o_z[2], o_z[3]));
+                        st4(gp + 2 * HP, make_float4(o_n[0], o_n[1], o_n[2], o_n[3]));
+                        st4(gp + 3 * HP, make_float4(o_hn[0], o_hn[1], o_hn[2], o_hn[3]));
+                    }
+                }
+                if (i < L) {
+                    tc::fence_proxy_async();
+                    tc::mbar_arrive(&bar_x[sub]);
+                    if (s > 0) prefetch(sub, s - 1);             // in flight under the other sub-tile / the MMAs
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == C::NW_EPI) tc::tmem_dealloc<C::TMEM_COLS>(tmem_d);
+}
+
+using EncFwd = FwdCfg<ENC_H, ENC_H, 2, false>;
+using DecFwd = FwdCfg<DEC_HP, 112, 1, true>;
+using EncBwd = BwdCfg<ENC_H, 2, false>;
+using DecBwd = BwdCfg<DEC_HP, 1, true>;
+
+template <class K>
+int set_smem(K kfn, size_t bytes, size_t& set_for) {
+    if (set_for < bytes) {
+        if (cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return CPG_ECUDA;
+        }
+        set_for = bytes;
+    }
+    return CPG_OK;
+}
+}  // namespace
 
 int launch_gru_fwd_enc_tc(cudaStream_t s, const GruSeq* two, int B, int L, int V) {
-    EncTcArgs a;
+    FwdArgs a;
+    memset(&a, 0, sizeof(a));
     a.tok = two[0].tok;
     for (int d = 0; d < 2; ++d) {
         a.table[d] = two[d].table; a.whh[d] = two[d].whh; a.bhn[d] = two[d].bhn;
@@ -246,13 +634,51 @@ int launch_gru_fwd_enc_tc(cudaStream_t s, const GruSeq* two, int B, int L, int V
     }
     a.hfin = two[0].hfin;
     a.B = B; a.L = L; a.V = V;
-    const size_t smem = gru_tc_enc_smem(V);
+    const size_t smem = EncFwd::smem_bytes(V, L);
     static size_t set_for = 0;
-    if (set_for < smem) {
-        cudaFuncSetAttribute((const void*)k_gru_fwd_enc_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        set_for = smem;
+    if (set_smem(k_gru_fwd_tc<EncFwd>, smem, set_for)) return CPG_ECUDA;
+    CPG_LAUNCH_NAMED("k_gru_fwd_enc_tc", k_gru_fwd_tc<EncFwd>, dim3(ceil_div(B, EncFwd::NSUB * NBS), 2), EncFwd::NTHREADS, smem, s, a);
+    return CPG_OK;
+}
+
+int launch_gru_fwd_dec_tc(cudaStream_t s, const GruSeq& q, int B, int L, int V) {
+    FwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tok = q.tok; a.table[0] = q.table; a.whh[0] = q.whh; a.bhn[0] = q.bhn;
+    a.rowbias = q.rowbias; a.h0 = q.h0; a.hs[0] = q.hs; a.gates[0] = q.gates;
+    a.B = B; a.L = L; a.V = V;
+    const size_t smem = DecFwd::smem_bytes(V, L);
+    static size_t set_for = 0;
+    if (set_smem(k_gru_fwd_tc<DecFwd>, smem, set_for)) return CPG_ECUDA;
+    CPG_LAUNCH_NAMED("k_gru_fwd_dec_tc", k_gru_fwd_tc<DecFwd>, dim3(ceil_div(B, DecFwd::NSUB * NBS), 1), DecFwd::NTHREADS, smem, s, a);
+    return CPG_OK;
+}
+
+int launch_gru_bwd_enc_tc(cudaStream_t s, const GruSeq* two, int B, int L) {
+    BwdArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int d = 0; d < 2; ++d) {
+        a.whh[d] = two[d].whh; a.hs[d] = two[d].hs; a.gates[d] = two[d].gates; a.dg[d] = two[d].dg;
     }
-    CPG_LAUNCH_NAMED("k_gru_fwd_enc_tc", k_gru_fwd_enc_tc, dim3(ceil_div(B, TM), 2), NTHREADS, smem, s, a);
+    a.dh_fin = two[0].dh_fin;
+    a.B = B; a.L = L;
+    const size_t smem = EncBwd::smem_bytes();
+    static size_t set_for = 0;
+    if (set_smem(k_gru_bwd_tc<EncBwd>, smem, set_for)) return CPG_ECUDA;
+    CPG_LAUNCH_NAMED("k_gru_bwd_enc_tc", k_gru_bwd_tc<EncBwd>, dim3(ceil_div(B, EncBwd::NSUB * NBS), 2), EncBwd::NTHREADS, smem, s, a);
+    return CPG_OK;
+}
+
+int launch_gru_bwd_dec_tc(cudaStream_t s, const GruSeq& q, int B, int L) {
+    BwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.whh[0] = q.whh; a.hs[0] = q.hs; a.gates[0] = q.gates; a.dg[0] = q.dg;
+    a.h0 = q.h0; a.dh_out = q.dh_out; a.dh0 = q.dh0; a.drow = q.drow;
+    a.B = B; a.L = L;
+    const size_t smem = DecBwd::smem_bytes();
+    static size_t set_for = 0;
+    if (set_smem(k_gru_bwd_tc<DecBwd>, smem, set_for)) return CPG_ECUDA;
+    CPG_LAUNCH_NAMED("k_gru_bwd_dec_tc", k_gru_bwd_tc<DecBwd>, dim3(ceil_div(B, DecBwd::NSUB * NBS), 1), DecBwd::NTHREADS, smem, s, a);
     return CPG_OK;
 }
 

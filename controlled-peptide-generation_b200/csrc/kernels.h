@@ -68,6 +68,12 @@ void launch_gru_fwd_enc(cudaStream_t s, const GruSeq* two_dirs, int B, int L);
 void launch_gru_fwd_dec(cudaStream_t s, const GruSeq& seq, int B, int L);
 void launch_gru_bwd_enc(cudaStream_t s, const GruSeq* two_dirs, int B, int L);
 void launch_gru_bwd_dec(cudaStream_t s, const GruSeq& seq, int B, int L);
+// tcgen05 recurrences (gru_tc.cu); GruSeq::whh must hold the natural [3H][H] recurrent weights
+int launch_gru_fwd_enc_tc(cudaStream_t s, const GruSeq* two_dirs, int B, int L, int V);
+int launch_gru_fwd_dec_tc(cudaStream_t s, const GruSeq& seq, int B, int L, int V);
+int launch_gru_bwd_enc_tc(cudaStream_t s, const GruSeq* two_dirs, int B, int L);
+int launch_gru_bwd_dec_tc(cudaStream_t s, const GruSeq& seq, int B, int L);
+extern int g_opt_gru_tc;
 
 // C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C ; generic strides (elements):
 // A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn], C(m,n) = C[m*ldc + n]; optional bias[n].
