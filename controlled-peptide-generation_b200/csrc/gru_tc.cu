@@ -126,8 +126,7 @@ template <class C>
 __global__ void __launch_bounds__(C::NTHREADS, 1)
 k_gru_fwd_tc(FwdArgs a) {
     constexpr int HP = C::HP, G3 = C::G3, MT = C::MT, NQ = C::NQ, NSUB = C::NSUB, KC = C::KC;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(1024) unsigned char smem[];   // used directly: keeps every access an LDS/STS
     unsigned char* Wb = smem;                                            // [2 terms][KC][G3/8][128 B]
     unsigned char* Xb = Wb + 2 * C::W_SPLIT;                             // [NSUB][2 terms][KC][X_LBO]
     float* Pb = reinterpret_cast<float*>(Xb + NSUB * 2 * C::X_SPLIT);    // [NSUB][NBS][G3]
@@ -144,7 +143,7 @@ k_gru_fwd_tc(FwdArgs a) {
     // ---- one-time setup
     {
         constexpr int WLD = HP;                                          // row stride of the natural weights
-        const float* whh = a.whh[dir];
+        const float* whh = (dir ? a.whh[1] : a.whh[0]);
         for (int idx = tid; idx < G3 * KC; idx += C::NTHREADS) {
             const int m = idx / KC, kc = idx % KC;
             float x[8];
@@ -177,7 +176,7 @@ k_gru_fwd_tc(FwdArgs a) {
             *reinterpret_cast<uint4*>(Xb + (sub * 2 + 1) * C::X_SPLIT + off) = lo;
         }
         if (!C::DEC)
-            for (int i = tid; i < a.V * G3; i += C::NTHREADS) tab[i] = a.table[dir][i];
+            for (int i = tid; i < a.V * G3; i += C::NTHREADS) tab[i] = (dir ? a.table[1] : a.table[0])[i];
         for (int i = tid; i < NSUB * NBS * L; i += C::NTHREADS) {
             const int row = min(row0 + i / L, B - 1);
             toks[i] = a.tok[(size_t)row * L + i % L];
@@ -236,7 +235,7 @@ k_gru_fwd_tc(FwdArgs a) {
     } else {
         // ---------------- epilogue
         const int quad = tid % NQ, j0 = quad * 4, bq = tid / NQ;        // item it -> batch row bq + 16 it
-        const float4 bhn4 = ldg4(a.bhn[dir] + j0);
+        const float4 bhn4 = ldg4((dir ? a.bhn[1] : a.bhn[0]) + j0);
         const float bhn[4] = {bhn4.x, bhn4.y, bhn4.z, bhn4.w};
         float hprev[NSUB][C::ITEMS][4];
         float rb[C::DEC ? C::ITEMS : 1][3][4];
@@ -257,15 +256,24 @@ k_gru_fwd_tc(FwdArgs a) {
                 }
                 hprev[sub][it][0] = v.x; hprev[sub][it][1] = v.y; hprev[sub][it][2] = v.z; hprev[sub][it][3] = v.w;
             }
-        const float* tabg = C::DEC ? a.table[dir] : tab;
-        float* hs_g = a.hs[dir];
-        float* gates_g = a.gates[dir];
+        const float* tabg = C::DEC ? (dir ? a.table[1] : a.table[0]) : tab;
+        float* hs_g = (dir ? a.hs[1] : a.hs[0]);
+        float* gates_g = (dir ? a.gates[1] : a.gates[0]);
 
         for (int s = 0; s < L; ++s) {
             const int t = dir ? (L - 1 - s) : s;
 #pragma unroll
             for (int sub = 0; sub < NSUB; ++sub) {
                 float* P = Pb + sub * C::P_FLOATS;
+                // input-side pre-activations do not depend on the MMA: fetch them before waiting on it
+                float4 tin[C::ITEMS][3];
+#pragma unroll
+                for (int it = 0; it < C::ITEMS; ++it) {
+                    const int tk = toks[(sub * NBS + bq + 16 * it) * L + t];
+                    const float* trow = tabg + tk * G3 + j0;
+                    if (C::DEC) { tin[it][0] = ldg4(trow); tin[it][1] = ldg4(trow + HP); tin[it][2] = ldg4(trow + 2 * HP); }
+                    else { tin[it][0] = ld4(trow); tin[it][1] = ld4(trow + HP); tin[it][2] = ld4(trow + 2 * HP); }
+                }
                 tc::mbar_wait(&bar_d[sub], s & 1);
                 tc::tc_fence_after();
                 // phase 1: accumulator (lane = gate row, 32 batch columns) -> P[batch][gate]
@@ -286,12 +294,8 @@ k_gru_fwd_tc(FwdArgs a) {
                 for (int it = 0; it < C::ITEMS; ++it) {
                     const int b = bq + 16 * it;
                     const int row = row0 + sub * NBS + b;
-                    const int tk = toks[(sub * NBS + b) * L + t];
                     const float4 pr = ld4(P + b * G3 + j0), pz = ld4(P + b * G3 + HP + j0), pn = ld4(P + b * G3 + 2 * HP + j0);
-                    const float* trow = tabg + tk * G3 + j0;
-                    float4 tr, tz, tn;
-                    if (C::DEC) { tr = ldg4(trow); tz = ldg4(trow + HP); tn = ldg4(trow + 2 * HP); }
-                    else { tr = ld4(trow); tz = ld4(trow + HP); tn = ld4(trow + 2 * HP); }
+                    const float4 tr = tin[it][0], tz = tin[it][1], tn = tin[it][2];
                     float gr[4] = {tr.x + pr.x, tr.y + pr.y, tr.z + pr.z, tr.w + pr.w};
                     float gz[4] = {tz.x + pz.x, tz.y + pz.y, tz.z + pz.z, tz.w + pz.w};
                     float gn[4] = {tn.x, tn.y, tn.z, tn.w};
@@ -385,8 +389,7 @@ template <class C>
 __global__ void __launch_bounds__(C::NTHREADS, 1)
 k_gru_bwd_tc(BwdArgs a) {
     constexpr int HP = C::HP, NQ = C::NQ, NSUB = C::NSUB, KC = C::KC, K3 = C::K3;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    extern __shared__ __align__(1024) unsigned char smem[];   // used directly: keeps every access an LDS/STS
     unsigned char* Ab = smem;                                            // W_hh^T: [2 terms][KC][HP/8][128 B]
     unsigned char* Xb = Ab + 2 * C::A_SPLIT;                             // [NSUB][2 terms][KC][X_LBO]
     float* Pb = reinterpret_cast<float*>(Xb + NSUB * 2 * C::X_SPLIT);    // [NSUB][NBS][HP]
@@ -400,7 +403,7 @@ k_gru_bwd_tc(BwdArgs a) {
 
     // ---- one-time setup: A[j][k] = W_hh[k][j] as two bf16 terms; operand tiles zeroed (K padding stays 0)
     {
-        const float* whh = a.whh[dir];
+        const float* whh = (dir ? a.whh[1] : a.whh[0]);
         for (int idx = tid; idx < KC * HP; idx += C::NTHREADS) {
             const int kc = idx / HP, j = idx % HP;
             float x[8];
@@ -463,9 +466,9 @@ k_gru_bwd_tc(BwdArgs a) {
     } else {
         // ---------------- epilogue
         const int quad = tid % NQ, j0 = quad * 4, bq = tid / NQ;
-        const float* hs_g = a.hs[dir];
-        const float* gates_g = a.gates[dir];
-        float* dg_g = a.dg[dir];
+        const float* hs_g = (dir ? a.hs[1] : a.hs[0]);
+        const float* gates_g = (dir ? a.gates[1] : a.gates[0]);
+        float* dg_g = (dir ? a.dg[1] : a.dg[0]);
         float carry[NSUB][C::ITEMS][4];
         float rs[C::DEC ? C::ITEMS : 1][3][4];
 #pragma unroll
