@@ -27,6 +27,17 @@
 #include <cuda_bf16.h>
 #include "tc_common.cuh"
 
+#ifdef CPG_GRU_TIMELINE
+// developer-only: clock64() stamps of one CTA / one step (tools/gru_timeline.py); never in the product build
+__device__ long long g_gru_tl[64];
+#define CPG_TL(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && s == 12) g_gru_tl[slot] = clock64(); } while (0)
+#define CPG_TL0(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_gru_tl[slot] = clock64(); } while (0)
+extern "C" int cpg_debug_gru_timeline(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_gru_tl, sizeof(g_gru_tl)); }
+#else
+#define CPG_TL(slot) do { } while (0)
+#define CPG_TL0(slot) do { } while (0)
+#endif
+
 namespace cpg {
 int check_launch(const char* where);
 
@@ -43,39 +54,61 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, A operand resident in tensor memory (lane = M row, one 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // kind::f16 with bf16 operands, fp32 accumulate, both operands K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// one lane of a converged warp (the form the compiler keeps on the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 template <int N>
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 lo, __nv_bfloat16 hi) {
-    return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+// (x0, x1) -> packed bf16 leading terms (x0 in the low half) and packed bf16 remainders
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float f0 = __uint_as_float(hi << 16), f1 = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - f0, x1 - f1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // 4 fp32 -> 4 bf16 leading terms + 4 bf16 remainders
 __device__ __forceinline__ void split4(const float (&x)[4], uint2& hi, uint2& lo) {
-    __nv_bfloat16 a[4], b[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        a[e] = __float2bfloat16_rn(x[e]);
-        b[e] = __float2bfloat16_rn(x[e] - __bfloat162float(a[e]));
-    }
-    hi = make_uint2(pack2(a[0], a[1]), pack2(a[2], a[3]));
-    lo = make_uint2(pack2(b[0], b[1]), pack2(b[2], b[3]));
+    split2(x[0], x[1], hi.x, lo.x);
+    split2(x[2], x[3], hi.y, lo.y);
 }
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
-    __nv_bfloat16 a[8], b[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        a[e] = __float2bfloat16_rn(x[e]);
-        b[e] = __float2bfloat16_rn(x[e] - __bfloat162float(a[e]));
-    }
-    hi = make_uint4(pack2(a[0], a[1]), pack2(a[2], a[3]), pack2(a[4], a[5]), pack2(a[6], a[7]));
-    lo = make_uint4(pack2(b[0], b[1]), pack2(b[2], b[3]), pack2(b[4], b[5]), pack2(b[6], b[7]));
+    split2(x[0], x[1], hi.x, lo.x);
+    split2(x[2], x[3], hi.y, lo.y);
+    split2(x[4], x[5], hi.z, lo.z);
+    split2(x[6], x[7], hi.w, lo.w);
 }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+// Gate non-linearities straight on the SFU (ex2.approx + rcp.approx, flush-to-zero forms: no denormal
+// fix-up code around them); absolute error <= ~6e-7 like the SIMT kernels' versions.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.0f, rcp_ftz(1.0f + ex2_ftz(2.8853900817779268f * x)), 1.0f); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // (operand-tile term, weight term) of the three accumulated products
@@ -95,17 +128,18 @@ struct FwdCfg {
     static constexpr int NW_EPI = NT_EPI / 32;
     static constexpr int NTHREADS = NT_EPI + 32;
     static constexpr int KC = KP / 8, KSTEPS = KP / 16;
-    static constexpr int W_LBO = (G3 / 8) * 128;
-    static constexpr int W_SPLIT = KC * W_LBO;
     static constexpr int X_SPLIT = KC * X_LBO;
     static constexpr int P_FLOATS = NBS * G3;
-    static constexpr uint32_t TMEM_COLS = 128;
-    static_assert(NSUB * MT * NBS <= 128, "TMEM columns");
+    // tensor memory: accumulators [NSUB][MT] x 32 columns, then W_hh as the A operand: [MT][2 terms][KP/2] columns
+    static constexpr int WCOL0 = NSUB * MT * NBS;
+    static constexpr int WCOLS = KP / 2;
+    static constexpr uint32_t TMEM_COLS = 512;
+    static_assert(WCOL0 + MT * 2 * WCOLS <= 512, "TMEM columns");
     static_assert(NT_EPI % 32 == 0 && NT_EPI % NQ == 0 && MT * 4 <= NW_EPI, "thread mapping");
     static_assert(HP % 8 == 0 && KP % 16 == 0 && G3 % 8 == 0, "core-matrix geometry");
     static size_t smem_bytes(int V, int L) {
-        return 2 * (size_t)W_SPLIT + (size_t)NSUB * 2 * X_SPLIT + (size_t)NSUB * P_FLOATS * 4 +
-               (DEC ? 0 : (size_t)V * G3 * 4) + (size_t)NSUB * NBS * L + 128;
+        return (size_t)NSUB * 2 * X_SPLIT + (size_t)NSUB * P_FLOATS * 4 + (DEC ? 0 : (size_t)V * G3 * 4) +
+               (size_t)NSUB * NBS * L + 128;
     }
 };
 
@@ -127,8 +161,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1)
 k_gru_fwd_tc(FwdArgs a) {
     constexpr int HP = C::HP, G3 = C::G3, MT = C::MT, NQ = C::NQ, NSUB = C::NSUB, KC = C::KC;
     extern __shared__ __align__(1024) unsigned char smem[];   // used directly: keeps every access an LDS/STS
-    unsigned char* Wb = smem;                                            // [2 terms][KC][G3/8][128 B]
-    unsigned char* Xb = Wb + 2 * C::W_SPLIT;                             // [NSUB][2 terms][KC][X_LBO]
+    unsigned char* Xb = smem;                                            // [NSUB][2 terms][KC][X_LBO]
     float* Pb = reinterpret_cast<float*>(Xb + NSUB * 2 * C::X_SPLIT);    // [NSUB][NBS][G3]
     float* tab = Pb + NSUB * C::P_FLOATS;                                // encoder: [V][G3]
     uint8_t* toks = reinterpret_cast<uint8_t*>(tab + (C::DEC ? 0 : a.V * G3));   // [NSUB*NBS][L]
@@ -139,26 +172,10 @@ k_gru_fwd_tc(FwdArgs a) {
     const int dir = blockIdx.y;
     const int row0 = blockIdx.x * (NSUB * NBS);
     const int B = a.B, L = a.L;
+    CPG_TL0(50);
 
     // ---- one-time setup
     {
-        constexpr int WLD = HP;                                          // row stride of the natural weights
-        const float* whh = (dir ? a.whh[1] : a.whh[0]);
-        for (int idx = tid; idx < G3 * KC; idx += C::NTHREADS) {
-            const int m = idx / KC, kc = idx % KC;
-            float x[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = 0.f;
-            if (kc * 8 + 8 <= WLD) {
-                const float4 f0 = ldg4(whh + (size_t)m * WLD + kc * 8), f1 = ldg4(whh + (size_t)m * WLD + kc * 8 + 4);
-                x[0] = f0.x; x[1] = f0.y; x[2] = f0.z; x[3] = f0.w; x[4] = f1.x; x[5] = f1.y; x[6] = f1.z; x[7] = f1.w;
-            }
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const int off = kc * C::W_LBO + (m >> 3) * W_SBO + (m & 7) * 16;
-            *reinterpret_cast<uint4*>(Wb + off) = hi;
-            *reinterpret_cast<uint4*>(Wb + C::W_SPLIT + off) = lo;
-        }
         for (int idx = tid; idx < NSUB * NBS * KC; idx += C::NTHREADS) {
             const int bb = idx / KC, kc = idx % KC, sub = bb / NBS, b = bb % NBS;
             float x[8];
@@ -199,18 +216,56 @@ k_gru_fwd_tc(FwdArgs a) {
     tc::tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
 
-    if (warp == C::NW_EPI) {
-        // ---------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, NBS);
-            const uint32_t w0 = tc::smem_u32(Wb), x0 = tc::smem_u32(Xb);
-            for (int s = 0; s < L; ++s) {
+    // W_hh -> tensor memory (A operand of every MMA of this CTA): warp q fills lane quadrant q of each M tile,
+    // lane = gate row, 16 K elements (8 packed columns) per store, leading and remainder bf16 terms side by side
+    if (warp < 4) {
+        const float* whh = (dir ? a.whh[1] : a.whh[0]);
+#pragma unroll 1
+        for (int t = 0; t < MT; ++t) {
+            const int m = t * 128 + warp * 32 + lane;
+            const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(C::WCOL0 + t * 2 * C::WCOLS);
+#pragma unroll 1
+            for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                float x[16];
 #pragma unroll
-                for (int sub = 0; sub < NSUB; ++sub) {
-                    if (s > 0) {
-                        tc::mbar_wait(&bar_x[sub], (s - 1) & 1);
-                        tc::tc_fence_after();
+                for (int e = 0; e < 16; ++e) x[e] = 0.f;
+                if (m < G3) {
+#pragma unroll
+                    for (int e4 = 0; e4 < 4; ++e4) {
+                        const int k = ks * 16 + e4 * 4;
+                        if (k + 4 <= HP) {
+                            const float4 f = ldg4(whh + (size_t)m * HP + k);
+                            x[e4 * 4 + 0] = f.x; x[e4 * 4 + 1] = f.y; x[e4 * 4 + 2] = f.z; x[e4 * 4 + 3] = f.w;
+                        }
                     }
+                }
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split2(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
+                tmem_st_32x8(lane_addr + (uint32_t)(ks * 8), hi);
+                tmem_st_32x8(lane_addr + (uint32_t)(C::WCOLS + ks * 8), lo);
+            }
+        }
+        tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    CPG_TL0(51);
+
+    if (warp == C::NW_EPI) {
+        // ---------------- MMA issuer (whole warp converged; one elected lane issues)
+        constexpr uint32_t idesc = make_idesc_bf16(128, NBS);
+        const uint32_t x0 = tc::smem_u32(Xb);
+        for (int s = 0; s < L; ++s) {
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+                if (s > 0) {
+                    tc::mbar_wait(&bar_x[sub], (s - 1) & 1);
+                    tc::tc_fence_after();
+                }
+                if (elect_one()) {
+                    CPG_TL(0 + sub);
 #pragma unroll
                     for (int t = 0; t < MT; ++t) {
                         uint32_t acc = 0;
@@ -218,17 +273,17 @@ k_gru_fwd_tc(FwdArgs a) {
                         for (int p = 0; p < 3; ++p) {
 #pragma unroll
                             for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                                const uint64_t da = tc::make_smem_desc(w0 + WS[p] * C::W_SPLIT + t * 16 * W_SBO + ks * 2 * C::W_LBO,
-                                                                       C::W_LBO, W_SBO, 0);
+                                const uint32_t ta = tmem_d + (uint32_t)(C::WCOL0 + (t * 2 + WS[p]) * C::WCOLS + ks * 8);
                                 const uint64_t db = tc::make_smem_desc(x0 + (sub * 2 + XS[p]) * C::X_SPLIT + ks * 2 * X_LBO,
                                                                        X_LBO, X_SBO, 0);
-                                umma_bf16(tmem_d + (uint32_t)((sub * MT + t) * NBS), da, db, idesc, acc);
+                                umma_bf16_ts(tmem_d + (uint32_t)((sub * MT + t) * NBS), ta, db, idesc, acc);
                                 acc = 1;
                             }
                         }
                     }
                     tc::umma_commit(&bar_d[sub]);
                 }
+                __syncwarp();
             }
         }
         __syncwarp();
@@ -274,8 +329,10 @@ k_gru_fwd_tc(FwdArgs a) {
                     if (C::DEC) { tin[it][0] = ldg4(trow); tin[it][1] = ldg4(trow + HP); tin[it][2] = ldg4(trow + 2 * HP); }
                     else { tin[it][0] = ld4(trow); tin[it][1] = ld4(trow + HP); tin[it][2] = ld4(trow + 2 * HP); }
                 }
+                if (lane == 0 && (warp == 0 || warp == C::NW_EPI - 1)) CPG_TL(8 + 16 * sub + (warp ? 8 : 0));
                 tc::mbar_wait(&bar_d[sub], s & 1);
                 tc::tc_fence_after();
+                if (lane == 0 && (warp == 0 || warp == C::NW_EPI - 1)) CPG_TL(9 + 16 * sub + (warp ? 8 : 0));
                 // phase 1: accumulator (lane = gate row, 32 batch columns) -> P[batch][gate]
                 if (warp < MT * 4) {
                     const int tq = warp >> 2, q = warp & 3;
@@ -288,7 +345,9 @@ k_gru_fwd_tc(FwdArgs a) {
                     }
                 }
                 tc::tc_fence_before();
+                if (lane == 0 && (warp == 0 || warp == C::NW_EPI - 1)) CPG_TL(10 + 16 * sub + (warp ? 8 : 0));
                 epi_bar_sync<C::NT_EPI>();
+                if (lane == 0 && (warp == 0 || warp == C::NW_EPI - 1)) CPG_TL(11 + 16 * sub + (warp ? 8 : 0));
                 // phase 2: gates for (row, 4 units)
 #pragma unroll
                 for (int it = 0; it < C::ITEMS; ++it) {
@@ -320,6 +379,7 @@ k_gru_fwd_tc(FwdArgs a) {
                     const int off = (j0 >> 3) * X_LBO + (b >> 3) * X_SBO + (b & 7) * 16 + (j0 & 7) * 2;
                     *reinterpret_cast<uint2*>(Xb + (sub * 2 + 0) * C::X_SPLIT + off) = hi;
                     *reinterpret_cast<uint2*>(Xb + (sub * 2 + 1) * C::X_SPLIT + off) = lo;
+                    if (tid == 0 && sub == 0) CPG_TL(40 + 2 * it);
                     if (row < B) {
                         const size_t bs = (size_t)row * L + s;
                         if (hs_g != nullptr) st4(hs_g + bs * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
@@ -333,14 +393,18 @@ k_gru_fwd_tc(FwdArgs a) {
                         if (!C::DEC && s == L - 1)
                             st4(a.hfin + (size_t)row * (2 * HP) + dir * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
                     }
+                    if (tid == 0 && sub == 0) CPG_TL(41 + 2 * it);
                 }
+                if (lane == 0 && (warp == 0 || warp == C::NW_EPI - 1)) CPG_TL(12 + 16 * sub + (warp ? 8 : 0));
                 tc::fence_proxy_async();                         // operand-tile stores -> visible to the tensor core
                 tc::mbar_arrive(&bar_x[sub]);
+                if (lane == 0 && (warp == 0 || warp == C::NW_EPI - 1)) CPG_TL(13 + 16 * sub + (warp ? 8 : 0));
             }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
+    CPG_TL0(52);
     if (warp == C::NW_EPI) tc::tmem_dealloc<C::TMEM_COLS>(tmem_d);
 }
 
@@ -361,15 +425,15 @@ struct BwdCfg {
     static constexpr int NT_EPI = NBS * NQ / ITEMS;
     static constexpr int NW_EPI = NT_EPI / 32;
     static constexpr int NTHREADS = NT_EPI + 32;
-    static constexpr int A_LBO = (HP / 8) * 128;
-    static constexpr int A_SPLIT = KC * A_LBO;
     static constexpr int X_SPLIT = KC * X_LBO;
     static constexpr int P_FLOATS = NBS * HP;
-    static constexpr uint32_t TMEM_COLS = NSUB * NBS < 32 ? 32 : NSUB * NBS;
+    // tensor memory: accumulators [NSUB] x 32 columns, then W_hh^T as the A operand: [2 terms][KPAD/2] columns
+    static constexpr int WCOL0 = NSUB * NBS;
+    static constexpr int WCOLS = KPAD / 2;
+    static constexpr uint32_t TMEM_COLS = 512;
+    static_assert(WCOL0 + 2 * WCOLS <= 512, "TMEM columns");
     static_assert(HP <= 128 && NT_EPI % NQ == 0 && NW_EPI >= 4, "thread mapping");
-    // the M = 128 tile reads 16 core-matrix rows per K chunk; rows >= HP alias the next chunk / the
-    // operand tiles that follow (finite garbage in accumulator rows nobody reads)
-    static size_t smem_bytes() { return 2 * (size_t)A_SPLIT + (size_t)NSUB * 2 * X_SPLIT + (size_t)NSUB * P_FLOATS * 4 + 128; }
+    static size_t smem_bytes() { return (size_t)NSUB * 2 * X_SPLIT + (size_t)NSUB * P_FLOATS * 4 + 128; }
 };
 
 struct BwdArgs {
@@ -390,8 +454,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1)
 k_gru_bwd_tc(BwdArgs a) {
     constexpr int HP = C::HP, NQ = C::NQ, NSUB = C::NSUB, KC = C::KC, K3 = C::K3;
     extern __shared__ __align__(1024) unsigned char smem[];   // used directly: keeps every access an LDS/STS
-    unsigned char* Ab = smem;                                            // W_hh^T: [2 terms][KC][HP/8][128 B]
-    unsigned char* Xb = Ab + 2 * C::A_SPLIT;                             // [NSUB][2 terms][KC][X_LBO]
+    unsigned char* Xb = smem;                                            // [NSUB][2 terms][KC][X_LBO]
     float* Pb = reinterpret_cast<float*>(Xb + NSUB * 2 * C::X_SPLIT);    // [NSUB][NBS][HP]
     __shared__ __align__(8) uint64_t bar_x[NSUB], bar_d[NSUB];
     __shared__ uint32_t tmem_slot;
@@ -401,23 +464,8 @@ k_gru_bwd_tc(BwdArgs a) {
     const int row0 = blockIdx.x * (NSUB * NBS);
     const int B = a.B, L = a.L;
 
-    // ---- one-time setup: A[j][k] = W_hh[k][j] as two bf16 terms; operand tiles zeroed (K padding stays 0)
+    // ---- one-time setup: operand tiles zeroed (K padding stays 0)
     {
-        const float* whh = (dir ? a.whh[1] : a.whh[0]);
-        for (int idx = tid; idx < KC * HP; idx += C::NTHREADS) {
-            const int kc = idx / HP, j = idx % HP;
-            float x[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int k = kc * 8 + e;
-                x[e] = k < K3 ? __ldg(whh + (size_t)k * HP + j) : 0.f;
-            }
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const int off = kc * C::A_LBO + (j >> 3) * W_SBO + (j & 7) * 16;
-            *reinterpret_cast<uint4*>(Ab + off) = hi;
-            *reinterpret_cast<uint4*>(Ab + C::A_SPLIT + off) = lo;
-        }
         for (int i = tid; i < NSUB * 2 * C::X_SPLIT / 16; i += C::NTHREADS) reinterpret_cast<uint4*>(Xb)[i] = make_uint4(0, 0, 0, 0);
     }
     if (warp == C::NW_EPI) {
@@ -437,29 +485,55 @@ k_gru_bwd_tc(BwdArgs a) {
     tc::tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
 
+    // W_hh^T -> tensor memory: lane = hidden unit j, K index = gate row k, A[j][k] = W_hh[k][j]
+    if (warp < 4) {
+        const float* whh = (dir ? a.whh[1] : a.whh[0]);
+        const int j = warp * 32 + lane;
+        const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)C::WCOL0;
+#pragma unroll 1
+        for (int ks = 0; ks < C::KSTEPS; ++ks) {
+            float x[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int k = ks * 16 + e;
+                x[e] = (j < HP && k < K3) ? __ldg(whh + (size_t)k * HP + j) : 0.f;
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split2(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
+            tmem_st_32x8(lane_addr + (uint32_t)(ks * 8), hi);
+            tmem_st_32x8(lane_addr + (uint32_t)(C::WCOLS + ks * 8), lo);
+        }
+        tmem_st_wait();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+
     if (warp == C::NW_EPI) {
         // ---------------- MMA issuer: iteration i handles step s = L-1-i
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, NBS);
-            const uint32_t a0 = tc::smem_u32(Ab), x0 = tc::smem_u32(Xb);
-            for (int i = 0; i < L; ++i) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, NBS);
+        const uint32_t x0 = tc::smem_u32(Xb);
+        for (int i = 0; i < L; ++i) {
 #pragma unroll
-                for (int sub = 0; sub < NSUB; ++sub) {
-                    tc::mbar_wait(&bar_x[sub], i & 1);
-                    tc::tc_fence_after();
+            for (int sub = 0; sub < NSUB; ++sub) {
+                tc::mbar_wait(&bar_x[sub], i & 1);
+                tc::tc_fence_after();
+                if (elect_one()) {
                     uint32_t acc = 0;
 #pragma unroll
                     for (int p = 0; p < 3; ++p) {
-#pragma unroll 5
+#pragma unroll
                         for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                            const uint64_t da = tc::make_smem_desc(a0 + WS[p] * C::A_SPLIT + ks * 2 * C::A_LBO, C::A_LBO, W_SBO, 0);
+                            const uint32_t ta = tmem_d + (uint32_t)(C::WCOL0 + WS[p] * C::WCOLS + ks * 8);
                             const uint64_t db = tc::make_smem_desc(x0 + (sub * 2 + XS[p]) * C::X_SPLIT + ks * 2 * X_LBO, X_LBO, X_SBO, 0);
-                            umma_bf16(tmem_d + (uint32_t)(sub * NBS), da, db, idesc, acc);
+                            umma_bf16_ts(tmem_d + (uint32_t)(sub * NBS), ta, db, idesc, acc);
                             acc = 1;
                         }
                     }
                     tc::umma_commit(&bar_d[sub]);
                 }
+                __syncwarp();
             }
         }
         __syncwarp();
