@@ -62,6 +62,7 @@ struct Bump {
 static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, int R, char* base) {
     Bump a{base, 0};
     const size_t BL = (size_t)B * L;
+    const size_t BL32 = (size_t)(ceil_div(B, 32) * 32) * L;     // gate stash of the tcgen05 recurrences: 32-row tiles
     const int sm = ctx->sm_count;
     w.B = B; w.L = L; w.V = V; w.R = R;
     // derived weights
@@ -81,7 +82,7 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
     // encoder
     for (int d = 0; d < 2; ++d) {
         w.enc_hs[d] = a.take<float>(BL * ENC_H);
-        w.enc_gates[d] = a.take<float>(BL * 4 * ENC_H);
+        w.enc_gates[d] = a.take<float>(BL32 * 4 * ENC_H);
         w.enc_dg[d] = a.take<float>(BL * 4 * ENC_H);
     }
     w.hfin = a.take<float>((size_t)B * 2 * ENC_H);
@@ -90,7 +91,7 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
     w.rowbias = a.take<float>((size_t)B * 3 * DEC_HP);
     // decoder
     w.dec_hs = a.take<float>(BL * DEC_HP);
-    w.dec_gates = a.take<float>(BL * 4 * DEC_HP);
+    w.dec_gates = a.take<float>(BL32 * 4 * DEC_HP);
     w.dec_dg = a.take<float>(BL * 4 * DEC_HP);
     w.dec_dh_out = a.take<float>(BL * DEC_HP);
     w.drow = a.take<float>((size_t)B * 3 * DEC_HP);

@@ -27,11 +27,18 @@
 #include <cuda_bf16.h>
 #include "tc_common.cuh"
 
+#ifndef CPG_ENC_FWD_NWG
+#define CPG_ENC_FWD_NWG 10
+#endif
+#ifndef CPG_ENC_BWD_NWG
+#define CPG_ENC_BWD_NWG 7
+#endif
+
 #ifdef CPG_GRU_TIMELINE
 // developer-only: clock64() stamps of one CTA / one step (tools/gru_timeline.py); never in the product build
-__device__ long long g_gru_tl[64];
-#define CPG_TL(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && s == 12) g_gru_tl[slot] = clock64(); } while (0)
-#define CPG_TL0(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_gru_tl[slot] = clock64(); } while (0)
+__device__ long long g_gru_tl[256];
+#define CPG_TL(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && s == 12) g_gru_tl[C::KID * 64 + (slot)] = clock64(); } while (0)
+#define CPG_TL0(slot) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_gru_tl[C::KID * 64 + (slot)] = clock64(); } while (0)
 extern "C" int cpg_debug_gru_timeline(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_gru_tl, sizeof(g_gru_tl)); }
 #else
 #define CPG_TL(slot) do { } while (0)
@@ -42,19 +49,10 @@ namespace cpg {
 int check_launch(const char* where);
 
 namespace {
-constexpr int NBS = 32;                               // batch rows per sub-tile = MMA N
-constexpr int X_LBO = (NBS / 8) * 128 + 16;           // K-adjacent core matrices of an operand tile (padded)
-constexpr int X_SBO = 128;                            // N-adjacent core matrices
-constexpr int W_SBO = 128;                            // M-adjacent core matrices of the weight tile
+constexpr int X_SBO = 128;                            // N-adjacent core matrices of an operand tile
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-// same, A operand resident in tensor memory (lane = M row, one 32-bit column = two consecutive K elements)
+// D[tmem] (+)= A[tmem] * B[smem desc]: kind::f16 (bf16 operands), fp32 accumulate; the A operand is resident
+// in tensor memory (lane = M row, one 32-bit column = two consecutive K elements, even K in the low half)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -67,7 +65,34 @@ __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// kind::f16 with bf16 operands, fp32 accumulate, both operands K-major
+// 32 lanes x N consecutive fp32 columns (N = 16 | 32): thread = TMEM lane of this warp's quadrant
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[N]) {
+    static_assert(N == 16 || N == 32, "column count");
+    uint32_t r[N];
+    if constexpr (N == 32) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr) : "memory");
+    } else {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr) : "memory");
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r[i]);
+}
+// kind::f16 with bf16 operands, fp32 accumulate, B operand K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -81,8 +106,8 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
-template <int N>
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
+// named barrier of one chain's epilogue warps
+__device__ __forceinline__ void group_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // (x0, x1) -> packed bf16 leading terms (x0 in the low half) and packed bf16 remainders
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
@@ -92,7 +117,6 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
     const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - f0, x1 - f1);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-// 4 fp32 -> 4 bf16 leading terms + 4 bf16 remainders
 __device__ __forceinline__ void split4(const float (&x)[4], uint2& hi, uint2& lo) {
     split2(x[0], x[1], hi.x, lo.x);
     split2(x[2], x[3], hi.y, lo.y);
@@ -110,36 +134,67 @@ __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.0f, rcp_ftz(1.0f + ex2_ftz(2.8853900817779268f * x)), 1.0f); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// streaming 16-byte load of stash data read exactly once: no L1 allocation
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 
 // (operand-tile term, weight term) of the three accumulated products
 __device__ constexpr int XS[3] = {0, 0, 1};
 __device__ constexpr int WS[3] = {0, 1, 0};
 
+// 1-D bulk copy global -> shared through the TMA engine, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+
+// Gate stash (r, z, n, hn) private to this file's forward/backward pair: 32-row tiles, step-major inside a
+// tile, [tile][step][plane][row in tile][HP] -- a chain streams through one contiguous region (whole DRAM
+// pages per step) instead of 320-byte pieces 8 KB apart as in the row-major [B][L][4][HP] of the SIMT kernels.
+template <int HP>
+__device__ __forceinline__ size_t gate_stash_offset(int row, int s, int L) {
+    return (((size_t)(row >> 5) * L + s) * 4 * 32 + (row & 31)) * HP;
+}
+
+// Which warp of a chain's group serves TMEM lane quadrant (warp % 4) for task number `task` of that quadrant:
+// the group's warps with equal quadrant are wl, wl+4, ...; tasks are dealt round-robin over them.
+__device__ __forceinline__ bool quadrant_task_is_mine(int wl, int nwg, int task) {
+    const int cnt = (nwg - (wl & 3) + 3) >> 2;
+    return task % cnt == (wl >> 2);
+}
+
 // ------------------------------------------------------------------------------------- forward
-template <int HP_, int KP_, int NSUB_, bool DEC_>
+template <int HP_, int KP_, int NB_, int NCH_, int NWG_, bool DEC_>
 struct FwdCfg {
-    static constexpr int HP = HP_, KP = KP_, NSUB = NSUB_;
+    static constexpr int HP = HP_, KP = KP_, NB = NB_, NCH = NCH_, NWG = NWG_;
     static constexpr bool DEC = DEC_;
+    static constexpr int KID = DEC ? 1 : 0;                 // timeline-probe slot
     static constexpr int G3 = 3 * HP;                       // gate rows (M)
     static constexpr int MT = (G3 + 127) / 128;             // M tiles
     static constexpr int NQ = HP / 4;                       // unit quads per row
-    static constexpr int ITEMS = 2;                         // (row, quad) items per thread and sub-tile
-    static constexpr int NT_EPI = NBS * NQ / ITEMS;         // 320 | 416
-    static constexpr int NW_EPI = NT_EPI / 32;
-    static constexpr int NTHREADS = NT_EPI + 32;
+    static constexpr int NITEMS = NB * NQ;                  // (row, quad) items per chain and step
+    static constexpr int NT_G = NWG * 32;                   // epilogue threads of one chain
+    static constexpr int ITEMS = (NITEMS + NT_G - 1) / NT_G;
+    static constexpr int NW_EPI = NCH * NWG;
+    static constexpr int NTHREADS = (NW_EPI + NCH) * 32;    // + one MMA warp per chain
     static constexpr int KC = KP / 8, KSTEPS = KP / 16;
+    static constexpr int X_LBO = (NB / 8) * 128 + 16;       // K-adjacent core matrices (padded: conflict-free stores)
     static constexpr int X_SPLIT = KC * X_LBO;
-    static constexpr int P_FLOATS = NBS * G3;
-    // tensor memory: accumulators [NSUB][MT] x 32 columns, then W_hh as the A operand: [MT][2 terms][KP/2] columns
-    static constexpr int WCOL0 = NSUB * MT * NBS;
+    static constexpr int P_FLOATS = NB * G3;
+    // tensor memory: accumulators [NCH][MT] x NB columns, then W_hh as the A operand: [MT][2 terms][KP/2] columns
+    static constexpr int WCOL0 = NCH * MT * NB;
     static constexpr int WCOLS = KP / 2;
     static constexpr uint32_t TMEM_COLS = 512;
     static_assert(WCOL0 + MT * 2 * WCOLS <= 512, "TMEM columns");
-    static_assert(NT_EPI % 32 == 0 && NT_EPI % NQ == 0 && MT * 4 <= NW_EPI, "thread mapping");
-    static_assert(HP % 8 == 0 && KP % 16 == 0 && G3 % 8 == 0, "core-matrix geometry");
+    static_assert(NWG >= 4, "every lane quadrant needs a warp in each group");
+    static_assert(HP % 8 == 0 && KP % 16 == 0 && G3 % 8 == 0 && (NB == 16 || NB == 32), "geometry");
     static size_t smem_bytes(int V, int L) {
-        return (size_t)NSUB * 2 * X_SPLIT + (size_t)NSUB * P_FLOATS * 4 + (DEC ? 0 : (size_t)V * G3 * 4) +
-               (size_t)NSUB * NBS * L + 128;
+        return (size_t)NCH * 2 * X_SPLIT + (size_t)NCH * P_FLOATS * 4 + (DEC ? 0 : (size_t)V * G3 * 4) +
+               (size_t)NCH * NB * L + 128;
     }
 };
 
@@ -151,7 +206,7 @@ struct FwdArgs {
     const float* rowbias;      // decoder: [B][3*HP]
     const float* h0;           // decoder: [B][HP]
     float* hs[2];              // [B][L][HP] by step (nullable)
-    float* gates[2];           // [B][L][4][HP] (nullable)
+    float* gates[2];           // [ceil(B/32)][L][4][32][HP] tiled gate stash (nullable)
     float* hfin;               // encoder: [B][2*HP]
     int B, L, V;
 };
@@ -159,50 +214,50 @@ struct FwdArgs {
 template <class C>
 __global__ void __launch_bounds__(C::NTHREADS, 1)
 k_gru_fwd_tc(FwdArgs a) {
-    constexpr int HP = C::HP, G3 = C::G3, MT = C::MT, NQ = C::NQ, NSUB = C::NSUB, KC = C::KC;
+    constexpr int HP = C::HP, G3 = C::G3, MT = C::MT, NQ = C::NQ, NCH = C::NCH, KC = C::KC, NB = C::NB;
     extern __shared__ __align__(1024) unsigned char smem[];   // used directly: keeps every access an LDS/STS
-    unsigned char* Xb = smem;                                            // [NSUB][2 terms][KC][X_LBO]
-    float* Pb = reinterpret_cast<float*>(Xb + NSUB * 2 * C::X_SPLIT);    // [NSUB][NBS][G3]
-    float* tab = Pb + NSUB * C::P_FLOATS;                                // encoder: [V][G3]
-    uint8_t* toks = reinterpret_cast<uint8_t*>(tab + (C::DEC ? 0 : a.V * G3));   // [NSUB*NBS][L]
-    __shared__ __align__(8) uint64_t bar_x[NSUB], bar_d[NSUB];
+    unsigned char* Xb = smem;                                            // [NCH][2 terms][KC][X_LBO]
+    float* Pb = reinterpret_cast<float*>(Xb + NCH * 2 * C::X_SPLIT);     // [NCH][NB][G3]
+    float* tab = Pb + NCH * C::P_FLOATS;                                 // encoder: [V][G3]
+    uint8_t* toks = reinterpret_cast<uint8_t*>(tab + (C::DEC ? 0 : a.V * G3));   // [NCH*NB][L]
+    __shared__ __align__(8) uint64_t bar_x[NCH], bar_d[NCH];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
-    const int row0 = blockIdx.x * (NSUB * NBS);
+    const int row0 = blockIdx.x * (NCH * NB);
     const int B = a.B, L = a.L;
     CPG_TL0(50);
 
     // ---- one-time setup
-    {
-        for (int idx = tid; idx < NSUB * NBS * KC; idx += C::NTHREADS) {
-            const int bb = idx / KC, kc = idx % KC, sub = bb / NBS, b = bb % NBS;
-            float x[8];
+    for (int idx = tid; idx < NCH * NB * KC; idx += C::NTHREADS) {
+        const int bb = idx / KC, kc = idx % KC, ch = bb / NB, b = bb % NB;
+        float x[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = 0.f;
-            if (C::DEC && kc * 8 + 8 <= HP) {
-                const int row = min(row0 + bb, B - 1);
-                const float4 f0 = ldg4(a.h0 + (size_t)row * HP + kc * 8), f1 = ldg4(a.h0 + (size_t)row * HP + kc * 8 + 4);
-                x[0] = f0.x; x[1] = f0.y; x[2] = f0.z; x[3] = f0.w; x[4] = f1.x; x[5] = f1.y; x[6] = f1.z; x[7] = f1.w;
-            }
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            const int off = kc * X_LBO + (b >> 3) * X_SBO + (b & 7) * 16;
-            *reinterpret_cast<uint4*>(Xb + (sub * 2 + 0) * C::X_SPLIT + off) = hi;
-            *reinterpret_cast<uint4*>(Xb + (sub * 2 + 1) * C::X_SPLIT + off) = lo;
+        for (int e = 0; e < 8; ++e) x[e] = 0.f;
+        if (C::DEC && kc * 8 + 8 <= HP) {
+            const int row = min(row0 + bb, B - 1);
+            const float4 f0 = ldg4(a.h0 + (size_t)row * HP + kc * 8), f1 = ldg4(a.h0 + (size_t)row * HP + kc * 8 + 4);
+            x[0] = f0.x; x[1] = f0.y; x[2] = f0.z; x[3] = f0.w; x[4] = f1.x; x[5] = f1.y; x[6] = f1.z; x[7] = f1.w;
         }
-        if (!C::DEC)
-            for (int i = tid; i < a.V * G3; i += C::NTHREADS) tab[i] = (dir ? a.table[1] : a.table[0])[i];
-        for (int i = tid; i < NSUB * NBS * L; i += C::NTHREADS) {
-            const int row = min(row0 + i / L, B - 1);
-            toks[i] = a.tok[(size_t)row * L + i % L];
-        }
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const int off = kc * C::X_LBO + (b >> 3) * X_SBO + (b & 7) * 16;
+        *reinterpret_cast<uint4*>(Xb + (ch * 2 + 0) * C::X_SPLIT + off) = hi;
+        *reinterpret_cast<uint4*>(Xb + (ch * 2 + 1) * C::X_SPLIT + off) = lo;
+    }
+    if (!C::DEC) {
+        const float* tsrc = (dir ? a.table[1] : a.table[0]);
+        for (int i = tid; i < a.V * G3; i += C::NTHREADS) tab[i] = __ldg(tsrc + i);
+    }
+    for (int i = tid; i < NCH * NB * L; i += C::NTHREADS) {
+        const int row = min(row0 + i / L, B - 1);
+        toks[i] = a.tok[(size_t)row * L + i % L];
     }
     if (warp == C::NW_EPI) {
         if (lane == 0) {
-            for (int i = 0; i < NSUB; ++i) {
-                tc::mbar_init(&bar_x[i], C::NT_EPI);
+            for (int i = 0; i < NCH; ++i) {
+                tc::mbar_init(&bar_x[i], C::NT_G);
                 tc::mbar_init(&bar_d[i], 1);
             }
             tc::fence_barrier_init();
@@ -216,35 +271,36 @@ k_gru_fwd_tc(FwdArgs a) {
     tc::tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
 
-    // W_hh -> tensor memory (A operand of every MMA of this CTA): warp q fills lane quadrant q of each M tile,
-    // lane = gate row, 16 K elements (8 packed columns) per store, leading and remainder bf16 terms side by side
-    if (warp < 4) {
+    // W_hh -> tensor memory (A operand of every MMA of this CTA).  Task = (M tile, 16-wide K slice) of the lane
+    // quadrant warp % 4; every warp of the CTA takes its share.  lane = gate row; leading and remainder bf16
+    // terms side by side.
+    {
         const float* whh = (dir ? a.whh[1] : a.whh[0]);
-#pragma unroll 1
-        for (int t = 0; t < MT; ++t) {
-            const int m = t * 128 + warp * 32 + lane;
-            const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(C::WCOL0 + t * 2 * C::WCOLS);
-#pragma unroll 1
-            for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                float x[16];
+        constexpr int NWARPS = C::NTHREADS / 32;
+        const int q = warp & 3;
+        const int cnt = (NWARPS - q + 3) >> 2;
+        for (int task = warp >> 2; task < MT * C::KSTEPS; task += cnt) {
+            const int t = task / C::KSTEPS, ks = task % C::KSTEPS;
+            const int m = t * 128 + q * 32 + lane;
+            float x[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) x[e] = 0.f;
-                if (m < G3) {
+            for (int e = 0; e < 16; ++e) x[e] = 0.f;
+            if (m < G3) {
 #pragma unroll
-                    for (int e4 = 0; e4 < 4; ++e4) {
-                        const int k = ks * 16 + e4 * 4;
-                        if (k + 4 <= HP) {
-                            const float4 f = ldg4(whh + (size_t)m * HP + k);
-                            x[e4 * 4 + 0] = f.x; x[e4 * 4 + 1] = f.y; x[e4 * 4 + 2] = f.z; x[e4 * 4 + 3] = f.w;
-                        }
+                for (int e4 = 0; e4 < 4; ++e4) {
+                    const int k = ks * 16 + e4 * 4;
+                    if (k + 4 <= HP) {
+                        const float4 f = ldg4(whh + (size_t)m * HP + k);
+                        x[e4 * 4 + 0] = f.x; x[e4 * 4 + 1] = f.y; x[e4 * 4 + 2] = f.z; x[e4 * 4 + 3] = f.w;
                     }
                 }
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) split2(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
-                tmem_st_32x8(lane_addr + (uint32_t)(ks * 8), hi);
-                tmem_st_32x8(lane_addr + (uint32_t)(C::WCOLS + ks * 8), lo);
             }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split2(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
+            const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(C::WCOL0 + t * 2 * C::WCOLS + ks * 8);
+            tmem_st_32x8(lane_addr, hi);
+            tmem_st_32x8(lane_addr + (uint32_t)C::WCOLS, lo);
         }
         tmem_st_wait();
     }
@@ -253,153 +309,162 @@ k_gru_fwd_tc(FwdArgs a) {
     tc::tc_fence_after();
     CPG_TL0(51);
 
-    if (warp == C::NW_EPI) {
-        // ---------------- MMA issuer (whole warp converged; one elected lane issues)
-        constexpr uint32_t idesc = make_idesc_bf16(128, NBS);
-        const uint32_t x0 = tc::smem_u32(Xb);
+    if (warp >= C::NW_EPI) {
+        // ---------------- MMA issuer of chain ch (whole warp converged; one elected lane issues)
+        const int ch = warp - C::NW_EPI;
+        constexpr uint32_t idesc = make_idesc_bf16(128, NB);
+        const uint32_t x0 = tc::smem_u32(Xb) + (uint32_t)(ch * 2 * C::X_SPLIT);
+        const uint32_t d0 = tmem_d + (uint32_t)(ch * MT * NB);
         for (int s = 0; s < L; ++s) {
+            if (s > 0) {
+                tc::mbar_wait(&bar_x[ch], (s - 1) & 1);
+                tc::tc_fence_after();
+            }
+            if (elect_one()) {
+                CPG_TL(0 + ch);
 #pragma unroll
-            for (int sub = 0; sub < NSUB; ++sub) {
-                if (s > 0) {
-                    tc::mbar_wait(&bar_x[sub], (s - 1) & 1);
-                    tc::tc_fence_after();
-                }
-                if (elect_one()) {
-                    CPG_TL(0 + sub);
+                for (int t = 0; t < MT; ++t) {
+                    uint32_t acc = 0;
 #pragma unroll
-                    for (int t = 0; t < MT; ++t) {
-                        uint32_t acc = 0;
+                    for (int p = 0; p < 3; ++p) {
 #pragma unroll
-                        for (int p = 0; p < 3; ++p) {
-#pragma unroll
-                            for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                                const uint32_t ta = tmem_d + (uint32_t)(C::WCOL0 + (t * 2 + WS[p]) * C::WCOLS + ks * 8);
-                                const uint64_t db = tc::make_smem_desc(x0 + (sub * 2 + XS[p]) * C::X_SPLIT + ks * 2 * X_LBO,
-                                                                       X_LBO, X_SBO, 0);
-                                umma_bf16_ts(tmem_d + (uint32_t)((sub * MT + t) * NBS), ta, db, idesc, acc);
-                                acc = 1;
-                            }
+                        for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                            const uint32_t ta = tmem_d + (uint32_t)(C::WCOL0 + (t * 2 + WS[p]) * C::WCOLS + ks * 8);
+                            const uint64_t db = tc::make_smem_desc(x0 + XS[p] * C::X_SPLIT + ks * 2 * C::X_LBO, C::X_LBO, X_SBO, 0);
+                            umma_bf16_ts(d0 + (uint32_t)(t * NB), ta, db, idesc, acc);
+                            acc = 1;
                         }
                     }
-                    tc::umma_commit(&bar_d[sub]);
                 }
-                __syncwarp();
+                tc::umma_commit(&bar_d[ch]);
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else {
-        // ---------------- epilogue
-        const int quad = tid % NQ, j0 = quad * 4, bq = tid / NQ;        // item it -> batch row bq + 16 it
-        const float4 bhn4 = ldg4((dir ? a.bhn[1] : a.bhn[0]) + j0);
-        const float bhn[4] = {bhn4.x, bhn4.y, bhn4.z, bhn4.w};
-        float hprev[NSUB][C::ITEMS][4];
-        float rb[C::DEC ? C::ITEMS : 1][3][4];
-#pragma unroll
-        for (int sub = 0; sub < NSUB; ++sub)
-#pragma unroll
-            for (int it = 0; it < C::ITEMS; ++it) {
-                const int row = min(row0 + sub * NBS + bq + 16 * it, B - 1);
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (C::DEC) {
-                    v = ldg4(a.h0 + (size_t)row * HP + j0);
-#pragma unroll
-                    for (int g = 0; g < 3; ++g) {
-                        const float4 r4 = ldg4(a.rowbias + (size_t)row * G3 + g * HP + j0);
-                        rb[C::DEC ? it : 0][g][0] = r4.x; rb[C::DEC ? it : 0][g][1] = r4.y;
-                        rb[C::DEC ? it : 0][g][2] = r4.z; rb[C::DEC ? it : 0][g][3] = r4.w;
-                    }
-                }
-                hprev[sub][it][0] = v.x; hprev[sub][it][1] = v.y; hprev[sub][it][2] = v.z; hprev[sub][it][3] = v.w;
-            }
-        const float* tabg = C::DEC ? (dir ? a.table[1] : a.table[0]) : tab;
+        // ---------------- epilogue of chain ch
+        const int ch = warp / C::NWG, wl = warp % C::NWG, tl = tid - ch * C::NT_G;
+        unsigned char* X0 = Xb + (ch * 2 + 0) * C::X_SPLIT;
+        unsigned char* X1 = Xb + (ch * 2 + 1) * C::X_SPLIT;
+        float* P = Pb + ch * C::P_FLOATS;
+        const uint8_t* tks = toks + ch * NB * L;
+        const uint32_t d0 = tmem_d + (uint32_t)(ch * MT * NB);
+        const int rowc0 = row0 + ch * NB;
+        const float* bhn_g = (dir ? a.bhn[1] : a.bhn[0]);
+        const float* tabg = C::DEC ? a.table[0] : tab;
         float* hs_g = (dir ? a.hs[1] : a.hs[0]);
         float* gates_g = (dir ? a.gates[1] : a.gates[0]);
 
+        int ib[C::ITEMS], ij[C::ITEMS];                      // item -> (row in tile, first unit); row < 0: no item
+        float bhn[C::ITEMS][4];
+        float hprev[C::ITEMS][4];
+        float rb[C::DEC ? C::ITEMS : 1][3][4];
+#pragma unroll
+        for (int it = 0; it < C::ITEMS; ++it) {
+            const int idx = tl + it * C::NT_G;
+            const bool valid = idx < C::NITEMS;
+            ib[it] = valid ? idx / NQ : -1;
+            ij[it] = valid ? (idx % NQ) * 4 : 0;
+            const int row = min(rowc0 + max(ib[it], 0), B - 1);
+            const float4 b4 = ldg4(bhn_g + ij[it]);
+            bhn[it][0] = b4.x; bhn[it][1] = b4.y; bhn[it][2] = b4.z; bhn[it][3] = b4.w;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (C::DEC) {
+                v = ldg4(a.h0 + (size_t)row * HP + ij[it]);
+#pragma unroll
+                for (int g = 0; g < 3; ++g) {
+                    const float4 r4 = ldg4(a.rowbias + (size_t)row * G3 + g * HP + ij[it]);
+                    rb[C::DEC ? it : 0][g][0] = r4.x; rb[C::DEC ? it : 0][g][1] = r4.y;
+                    rb[C::DEC ? it : 0][g][2] = r4.z; rb[C::DEC ? it : 0][g][3] = r4.w;
+                }
+            }
+            hprev[it][0] = v.x; hprev[it][1] = v.y; hprev[it][2] = v.z; hprev[it][3] = v.w;
+        }
+
         for (int s = 0; s < L; ++s) {
             const int t = dir ? (L - 1 - s) : s;
+            // input-side pre-activations do not depend on the MMA: fetch them before waiting on it
+            float4 tin[C::ITEMS][3];
 #pragma unroll
-            for (int sub = 0; sub < NSUB; ++sub) {
-                float* P = Pb + sub * C::P_FLOATS;
-                // input-side pre-activations do not depend on the MMA: fetch them before waiting on it
-                float4 tin[C::ITEMS][3];
-#pragma unroll
-                for (int it = 0; it < C::ITEMS; ++it) {
-                    const int tk = toks[(sub * NBS + bq + 16 * it) * L + t];
-                    const float* trow = tabg + tk * G3 + j0;
-                    if (C::DEC) { tin[it][0] = ldg4(trow); tin[it][1] = ldg4(trow + HP); tin[it][2] = ldg4(trow + 2 * HP); }
-                    else { tin[it][0] = ld4(trow); tin[it][1] = ld4(trow + HP); tin[it][2] = ld4(trow + 2 * HP); }
-                }
-                if (lane == 0 && (warp == 0 || warp == C::NW_EPI - 1)) CPG_TL(8 + 16 * sub + (warp ? 8 : 0));
-                tc::mbar_wait(&bar_d[sub], s & 1);
-                tc::tc_fence_after();
-                if (lane == 0 && (warp == 0 || warp == C::NW_EPI - 1)) CPG_TL(9 + 16 * sub + (warp ? 8 : 0));
-                // phase 1: accumulator (lane = gate row, 32 batch columns) -> P[batch][gate]
-                if (warp < MT * 4) {
-                    const int tq = warp >> 2, q = warp & 3;
-                    float v[32];
-                    tc::tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((sub * MT + tq) * NBS), v);
-                    const int m = tq * 128 + q * 32 + lane;
-                    if (m < G3) {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) P[c * G3 + m] = v[c];
-                    }
-                }
-                tc::tc_fence_before();
-                if (lane == 0 && (warp == 0 || warp == C::NW_EPI - 1)) CPG_TL(10 + 16 * sub + (warp ? 8 : 0));
-                epi_bar_sync<C::NT_EPI>();
-                if (lane == 0 && (warp == 0 || warp == C::NW_EPI - 1)) CPG_TL(11 + 16 * sub + (warp ? 8 : 0));
-                // phase 2: gates for (row, 4 units)
-#pragma unroll
-                for (int it = 0; it < C::ITEMS; ++it) {
-                    const int b = bq + 16 * it;
-                    const int row = row0 + sub * NBS + b;
-                    const float4 pr = ld4(P + b * G3 + j0), pz = ld4(P + b * G3 + HP + j0), pn = ld4(P + b * G3 + 2 * HP + j0);
-                    const float4 tr = tin[it][0], tz = tin[it][1], tn = tin[it][2];
-                    float gr[4] = {tr.x + pr.x, tr.y + pr.y, tr.z + pr.z, tr.w + pr.w};
-                    float gz[4] = {tz.x + pz.x, tz.y + pz.y, tz.z + pz.z, tz.w + pz.w};
-                    float gn[4] = {tn.x, tn.y, tn.z, tn.w};
-                    const float pnv[4] = {pn.x, pn.y, pn.z, pn.w};
-                    float rr[4], zz[4], nn[4], hh[4], hn[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (C::DEC) {
-                            gr[e] += rb[C::DEC ? it : 0][0][e];
-                            gz[e] += rb[C::DEC ? it : 0][1][e];
-                            gn[e] += rb[C::DEC ? it : 0][2][e];
-                        }
-                        rr[e] = sigmoid_fast(gr[e]);
-                        zz[e] = sigmoid_fast(gz[e]);
-                        hh[e] = pnv[e] + bhn[e];
-                        nn[e] = tanh_fast(gn[e] + rr[e] * hh[e]);
-                        hn[e] = (1.0f - zz[e]) * nn[e] + zz[e] * hprev[sub][it][e];
-                        hprev[sub][it][e] = hn[e];
-                    }
-                    uint2 hi, lo;
-                    split4(hn, hi, lo);
-                    const int off = (j0 >> 3) * X_LBO + (b >> 3) * X_SBO + (b & 7) * 16 + (j0 & 7) * 2;
-                    *reinterpret_cast<uint2*>(Xb + (sub * 2 + 0) * C::X_SPLIT + off) = hi;
-                    *reinterpret_cast<uint2*>(Xb + (sub * 2 + 1) * C::X_SPLIT + off) = lo;
-                    if (tid == 0 && sub == 0) CPG_TL(40 + 2 * it);
-                    if (row < B) {
-                        const size_t bs = (size_t)row * L + s;
-                        if (hs_g != nullptr) st4(hs_g + bs * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
-                        if (gates_g != nullptr) {
-                            float* g = gates_g + bs * 4 * HP + j0;
-                            st4(g, make_float4(rr[0], rr[1], rr[2], rr[3]));
-                            st4(g + HP, make_float4(zz[0], zz[1], zz[2], zz[3]));
-                            st4(g + 2 * HP, make_float4(nn[0], nn[1], nn[2], nn[3]));
-                            st4(g + 3 * HP, make_float4(hh[0], hh[1], hh[2], hh[3]));
-                        }
-                        if (!C::DEC && s == L - 1)
-                            st4(a.hfin + (size_t)row * (2 * HP) + dir * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
-                    }
-                    if (tid == 0 && sub == 0) CPG_TL(41 + 2 * it);
-                }
-                if (lane == 0 && (warp == 0 || warp == C::NW_EPI - 1)) CPG_TL(12 + 16 * sub + (warp ? 8 : 0));
-                tc::fence_proxy_async();                         // operand-tile stores -> visible to the tensor core
-                tc::mbar_arrive(&bar_x[sub]);
-                if (lane == 0 && (warp == 0 || warp == C::NW_EPI - 1)) CPG_TL(13 + 16 * sub + (warp ? 8 : 0));
+            for (int it = 0; it < C::ITEMS; ++it) {
+                const int tk = tks[max(ib[it], 0) * L + t];
+                const float* trow = tabg + tk * G3 + ij[it];
+                if (C::DEC) { tin[it][0] = ldg4(trow); tin[it][1] = ldg4(trow + HP); tin[it][2] = ldg4(trow + 2 * HP); }
+                else { tin[it][0] = ld4(trow); tin[it][1] = ld4(trow + HP); tin[it][2] = ld4(trow + 2 * HP); }
             }
+            if (lane == 0 && wl == 0) CPG_TL(8 + 16 * ch);
+            tc::mbar_wait(&bar_d[ch], s & 1);
+            tc::tc_fence_after();
+            if (lane == 0 && wl == 0) CPG_TL(9 + 16 * ch);
+            // phase 1: accumulator (lane = gate row, NB batch columns) -> P[batch][gate]
+#pragma unroll
+            for (int tq = 0; tq < MT; ++tq) {
+                if (quadrant_task_is_mine(wl, C::NWG, tq)) {
+                    const int q = warp & 3;
+                    const int m = tq * 128 + q * 32 + lane;
+                    if (tq * 128 + q * 32 < G3) {            // warp-uniform: skip quadrants that hold no gate row
+                        float v[NB];
+                        tmem_ld_cols<NB>(d0 + ((uint32_t)(q * 32) << 16) + (uint32_t)(tq * NB), v);
+                        if (m < G3) {
+#pragma unroll
+                            for (int c = 0; c < NB; ++c) P[c * G3 + m] = v[c];
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            if (lane == 0 && wl == 0) CPG_TL(10 + 16 * ch);
+            group_bar_sync(1 + ch, C::NT_G);
+            if (lane == 0 && wl == 0) CPG_TL(11 + 16 * ch);
+            // phase 2: gates for (row, 4 units)
+#pragma unroll
+            for (int it = 0; it < C::ITEMS; ++it) {
+                const int b = ib[it], j0 = ij[it];
+                if (b < 0) continue;
+                const int row = rowc0 + b;
+                const float4 pr = ld4(P + b * G3 + j0), pz = ld4(P + b * G3 + HP + j0), pn = ld4(P + b * G3 + 2 * HP + j0);
+                const float4 tr = tin[it][0], tz = tin[it][1], tn = tin[it][2];
+                float gr[4] = {tr.x + pr.x, tr.y + pr.y, tr.z + pr.z, tr.w + pr.w};
+                float gz[4] = {tz.x + pz.x, tz.y + pz.y, tz.z + pz.z, tz.w + pz.w};
+                float gn[4] = {tn.x, tn.y, tn.z, tn.w};
+                const float pnv[4] = {pn.x, pn.y, pn.z, pn.w};
+                float rr[4], zz[4], nn[4], hh[4], hn[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (C::DEC) {
+                        gr[e] += rb[C::DEC ? it : 0][0][e];
+                        gz[e] += rb[C::DEC ? it : 0][1][e];
+                        gn[e] += rb[C::DEC ? it : 0][2][e];
+                    }
+                    rr[e] = sigmoid_fast(gr[e]);
+                    zz[e] = sigmoid_fast(gz[e]);
+                    hh[e] = pnv[e] + bhn[it][e];
+                    nn[e] = tanh_fast(gn[e] + rr[e] * hh[e]);
+                    hn[e] = (1.0f - zz[e]) * nn[e] + zz[e] * hprev[it][e];
+                    hprev[it][e] = hn[e];
+                }
+                uint2 hi, lo;
+                split4(hn, hi, lo);
+                const int off = (j0 >> 3) * C::X_LBO + (b >> 3) * X_SBO + (b & 7) * 16 + (j0 & 7) * 2;
+                *reinterpret_cast<uint2*>(X0 + off) = hi;
+                *reinterpret_cast<uint2*>(X1 + off) = lo;
+                if (row < B) {
+                    const size_t bs = (size_t)row * L + s;
+                    if (hs_g != nullptr) st4(hs_g + bs * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
+                    if (gates_g != nullptr) {
+                        float* g = gates_g + gate_stash_offset<HP>(row, s, L) + j0;
+                        st4(g, make_float4(rr[0], rr[1], rr[2], rr[3]));
+                        st4(g + 32 * HP, make_float4(zz[0], zz[1], zz[2], zz[3]));
+                        st4(g + 2 * 32 * HP, make_float4(nn[0], nn[1], nn[2], nn[3]));
+                        st4(g + 3 * 32 * HP, make_float4(hh[0], hh[1], hh[2], hh[3]));
+                    }
+                    if (!C::DEC && s == L - 1)
+                        st4(a.hfin + (size_t)row * (2 * HP) + dir * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
+                }
+            }
+            if (lane == 0 && wl == 0) CPG_TL(12 + 16 * ch);
+            tc::fence_proxy_async();                         // operand-tile stores -> visible to the tensor core
+            tc::mbar_arrive(&bar_x[ch]);
+            if (lane == 0 && wl == 0) CPG_TL(13 + 16 * ch);
         }
     }
     tc::tc_fence_before();
@@ -413,33 +478,37 @@ k_gru_fwd_tc(FwdArgs a) {
 //   dht = dh + dh_out[s];  dn = dht (1-z); dz = dht (h_prev - n); carry = dht z
 //   dn_pre = dn (1-n^2); dr = dn_pre hn; dhn = dn_pre r; dr_pre = dr r (1-r); dz_pre = dz z (1-z)
 //   dh = carry + W_hh^T [dr_pre, dz_pre, dhn]
-template <int HP_, int NSUB_, bool DEC_>
+template <int HP_, int NB_, int NCH_, int NWG_, bool DEC_>
 struct BwdCfg {
-    static constexpr int HP = HP_, NSUB = NSUB_;
+    static constexpr int HP = HP_, NB = NB_, NCH = NCH_, NWG = NWG_;
     static constexpr bool DEC = DEC_;
+    static constexpr int KID = DEC ? 2 : 3;
     static constexpr int K3 = 3 * HP;
     static constexpr int KPAD = (K3 + 15) / 16 * 16;        // 240 | 320
     static constexpr int KC = KPAD / 8, KSTEPS = KPAD / 16;
     static constexpr int NQ = HP / 4;
-    static constexpr int ITEMS = 2;
-    static constexpr int NT_EPI = NBS * NQ / ITEMS;
-    static constexpr int NW_EPI = NT_EPI / 32;
-    static constexpr int NTHREADS = NT_EPI + 32;
+    static constexpr int NITEMS = NB * NQ;
+    static constexpr int NT_G = NWG * 32;
+    static constexpr int ITEMS = (NITEMS + NT_G - 1) / NT_G;
+    static constexpr int NW_EPI = NCH * NWG;
+    static constexpr int NTHREADS = (NW_EPI + NCH) * 32;
+    static constexpr int X_LBO = (NB / 8) * 128 + 16;
     static constexpr int X_SPLIT = KC * X_LBO;
-    static constexpr int P_FLOATS = NBS * HP;
-    // tensor memory: accumulators [NSUB] x 32 columns, then W_hh^T as the A operand: [2 terms][KPAD/2] columns
-    static constexpr int WCOL0 = NSUB * NBS;
+    static constexpr int P_FLOATS = NB * HP;
+    // tensor memory: accumulators [NCH] x NB columns, then W_hh^T as the A operand: [2 terms][KPAD/2] columns
+    static constexpr int WCOL0 = NCH * NB < 32 ? 32 : NCH * NB;
     static constexpr int WCOLS = KPAD / 2;
     static constexpr uint32_t TMEM_COLS = 512;
     static_assert(WCOL0 + 2 * WCOLS <= 512, "TMEM columns");
-    static_assert(HP <= 128 && NT_EPI % NQ == 0 && NW_EPI >= 4, "thread mapping");
-    static size_t smem_bytes() { return (size_t)NSUB * 2 * X_SPLIT + (size_t)NSUB * P_FLOATS * 4 + 128; }
+    static_assert(HP <= 128 && NWG >= 4 && (NB == 16 || NB == 32), "geometry");
+    static constexpr int G_PLANE = NB * HP * 4;              // bytes of one gate plane of one chain and step
+    static size_t smem_bytes() { return (size_t)NCH * 2 * X_SPLIT + (size_t)NCH * P_FLOATS * 4 + (size_t)NCH * 4 * G_PLANE + 128; }
 };
 
 struct BwdArgs {
     const float* whh[2];       // [3*HP][HP] natural
     const float* hs[2];        // [B][L][HP]
-    const float* gates[2];     // [B][L][4][HP]
+    const float* gates[2];     // [ceil(B/32)][L][4][32][HP] tiled gate stash
     const float* h0;           // decoder: [B][HP] (null = zeros)
     const float* dh_out;       // decoder: [B][L][HP]
     const float* dh_fin;       // encoder: [B][2*HP]
@@ -452,27 +521,28 @@ struct BwdArgs {
 template <class C>
 __global__ void __launch_bounds__(C::NTHREADS, 1)
 k_gru_bwd_tc(BwdArgs a) {
-    constexpr int HP = C::HP, NQ = C::NQ, NSUB = C::NSUB, KC = C::KC, K3 = C::K3;
+    constexpr int HP = C::HP, NQ = C::NQ, NCH = C::NCH, K3 = C::K3, NB = C::NB;
     extern __shared__ __align__(1024) unsigned char smem[];   // used directly: keeps every access an LDS/STS
-    unsigned char* Xb = smem;                                            // [NSUB][2 terms][KC][X_LBO]
-    float* Pb = reinterpret_cast<float*>(Xb + NSUB * 2 * C::X_SPLIT);    // [NSUB][NBS][HP]
-    __shared__ __align__(8) uint64_t bar_x[NSUB], bar_d[NSUB];
+    unsigned char* Xb = smem;                                            // [NCH][2 terms][KC][X_LBO]
+    float* Pb = reinterpret_cast<float*>(Xb + NCH * 2 * C::X_SPLIT);     // [NCH][NB][HP]
+    float* Gb = Pb + NCH * C::P_FLOATS;                                  // [NCH][4 planes][NB][HP]: gate stash of the current step
+    __shared__ __align__(8) uint64_t bar_x[NCH], bar_d[NCH], bar_g[NCH];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.y;
-    const int row0 = blockIdx.x * (NSUB * NBS);
+    const int row0 = blockIdx.x * (NCH * NB);
     const int B = a.B, L = a.L;
+    CPG_TL0(50);
 
     // ---- one-time setup: operand tiles zeroed (K padding stays 0)
-    {
-        for (int i = tid; i < NSUB * 2 * C::X_SPLIT / 16; i += C::NTHREADS) reinterpret_cast<uint4*>(Xb)[i] = make_uint4(0, 0, 0, 0);
-    }
+    for (int i = tid; i < NCH * 2 * C::X_SPLIT / 16; i += C::NTHREADS) reinterpret_cast<uint4*>(Xb)[i] = make_uint4(0, 0, 0, 0);
     if (warp == C::NW_EPI) {
         if (lane == 0) {
-            for (int i = 0; i < NSUB; ++i) {
-                tc::mbar_init(&bar_x[i], C::NT_EPI);
+            for (int i = 0; i < NCH; ++i) {
+                tc::mbar_init(&bar_x[i], C::NT_G);
                 tc::mbar_init(&bar_d[i], 1);
+                tc::mbar_init(&bar_g[i], 1);
             }
             tc::fence_barrier_init();
         }
@@ -485,208 +555,242 @@ k_gru_bwd_tc(BwdArgs a) {
     tc::tc_fence_after();
     const uint32_t tmem_d = tmem_slot;
 
-    // W_hh^T -> tensor memory: lane = hidden unit j, K index = gate row k, A[j][k] = W_hh[k][j]
-    if (warp < 4) {
+    // W_hh^T -> tensor memory: lane = hidden unit j, K index = gate row k, A[j][k] = W_hh[k][j].
+    // Task = 16-wide K slice of the lane quadrant warp % 4, dealt over all warps of the CTA.
+    {
         const float* whh = (dir ? a.whh[1] : a.whh[0]);
-        const int j = warp * 32 + lane;
-        const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)C::WCOL0;
-#pragma unroll 1
-        for (int ks = 0; ks < C::KSTEPS; ++ks) {
-            float x[16];
+        constexpr int NWARPS = C::NTHREADS / 32;
+        const int q = warp & 3;
+        const int cnt = (NWARPS - q + 3) >> 2;
+        const int j = q * 32 + lane;
+        if (q * 32 < HP) {
+            for (int ks = warp >> 2; ks < C::KSTEPS; ks += cnt) {
+                float x[16];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int k = ks * 16 + e;
-                x[e] = (j < HP && k < K3) ? __ldg(whh + (size_t)k * HP + j) : 0.f;
+                for (int e = 0; e < 16; ++e) {
+                    const int k = ks * 16 + e;
+                    x[e] = (j < HP && k < K3) ? __ldg(whh + (size_t)k * HP + j) : 0.f;
+                }
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split2(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
+                const uint32_t lane_addr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(C::WCOL0 + ks * 8);
+                tmem_st_32x8(lane_addr, hi);
+                tmem_st_32x8(lane_addr + (uint32_t)C::WCOLS, lo);
             }
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) split2(x[2 * e], x[2 * e + 1], hi[e], lo[e]);
-            tmem_st_32x8(lane_addr + (uint32_t)(ks * 8), hi);
-            tmem_st_32x8(lane_addr + (uint32_t)(C::WCOLS + ks * 8), lo);
+            tmem_st_wait();
         }
-        tmem_st_wait();
     }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    CPG_TL0(51);
 
-    if (warp == C::NW_EPI) {
-        // ---------------- MMA issuer: iteration i handles step s = L-1-i
-        constexpr uint32_t idesc = make_idesc_bf16(128, NBS);
-        const uint32_t x0 = tc::smem_u32(Xb);
-        for (int i = 0; i < L; ++i) {
+    if (warp >= C::NW_EPI) {
+        // ---------------- MMA issuer of chain ch: iteration i handles step s = L-1-i
+        const int ch = warp - C::NW_EPI;
+        constexpr uint32_t idesc = make_idesc_bf16(128, NB);
+        const uint32_t x0 = tc::smem_u32(Xb) + (uint32_t)(ch * 2 * C::X_SPLIT);
+        const uint32_t d0 = tmem_d + (uint32_t)(ch * NB);
+        // gate stash of (this chain, step s) -> shared memory: one bulk copy per plane through the TMA engine
+        const float* gates_src = (dir ? a.gates[1] : a.gates[0]);
+        float* G = Gb + ch * 4 * NB * HP;
+        auto load_gates = [&](int s) {
+            tc::mbar_expect_tx(&bar_g[ch], 4 * C::G_PLANE);
 #pragma unroll
-            for (int sub = 0; sub < NSUB; ++sub) {
-                tc::mbar_wait(&bar_x[sub], i & 1);
-                tc::tc_fence_after();
-                if (elect_one()) {
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int p = 0; p < 3; ++p) {
-#pragma unroll
-                        for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                            const uint32_t ta = tmem_d + (uint32_t)(C::WCOL0 + WS[p] * C::WCOLS + ks * 8);
-                            const uint64_t db = tc::make_smem_desc(x0 + (sub * 2 + XS[p]) * C::X_SPLIT + ks * 2 * X_LBO, X_LBO, X_SBO, 0);
-                            umma_bf16_ts(tmem_d + (uint32_t)(sub * NBS), ta, db, idesc, acc);
-                            acc = 1;
-                        }
-                    }
-                    tc::umma_commit(&bar_d[sub]);
-                }
-                __syncwarp();
-            }
-        }
+            for (int pl = 0; pl < 4; ++pl)
+                bulk_load(G + pl * NB * HP, gates_src + gate_stash_offset<HP>(row0 + ch * NB, s, L) + (size_t)pl * 32 * HP,
+                          C::G_PLANE, &bar_g[ch]);
+        };
+        if (elect_one()) load_gates(L - 1);
         __syncwarp();
+        for (int i = 0; i < L; ++i) {
+            tc::mbar_wait(&bar_x[ch], i & 1);          // phase 2 of iteration i is over: X tile ready, G buffer free
+            tc::tc_fence_after();
+            if (elect_one()) {
+                { const int s = L - 1 - i; CPG_TL(0 + ch); }
+                if (i + 1 < L) load_gates(L - 2 - i);
+                uint32_t acc = 0;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+#pragma unroll
+                    for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                        const uint32_t ta = tmem_d + (uint32_t)(C::WCOL0 + WS[p] * C::WCOLS + ks * 8);
+                        const uint64_t db = tc::make_smem_desc(x0 + XS[p] * C::X_SPLIT + ks * 2 * C::X_LBO, C::X_LBO, X_SBO, 0);
+                        umma_bf16_ts(d0, ta, db, idesc, acc);
+                        acc = 1;
+                    }
+                }
+                tc::umma_commit(&bar_d[ch]);
+            }
+            __syncwarp();
+        }
     } else {
-        // ---------------- epilogue
-        const int quad = tid % NQ, j0 = quad * 4, bq = tid / NQ;
+        // ---------------- epilogue of chain ch
+        const int ch = warp / C::NWG, wl = warp % C::NWG, tl = tid - ch * C::NT_G;
+        unsigned char* X0 = Xb + (ch * 2 + 0) * C::X_SPLIT;
+        unsigned char* X1 = Xb + (ch * 2 + 1) * C::X_SPLIT;
+        float* P = Pb + ch * C::P_FLOATS;
+        const uint32_t d0 = tmem_d + (uint32_t)(ch * NB);
+        const int rowc0 = row0 + ch * NB;
         const float* hs_g = (dir ? a.hs[1] : a.hs[0]);
-        const float* gates_g = (dir ? a.gates[1] : a.gates[0]);
         float* dg_g = (dir ? a.dg[1] : a.dg[0]);
-        float carry[NSUB][C::ITEMS][4];
+
+        int ib[C::ITEMS], ij[C::ITEMS];
+        float carry[C::ITEMS][4];
         float rs[C::DEC ? C::ITEMS : 1][3][4];
 #pragma unroll
-        for (int sub = 0; sub < NSUB; ++sub)
+        for (int it = 0; it < C::ITEMS; ++it) {
+            const int idx = tl + it * C::NT_G;
+            const bool valid = idx < C::NITEMS;
+            ib[it] = valid ? idx / NQ : -1;
+            ij[it] = valid ? (idx % NQ) * 4 : 0;
 #pragma unroll
-            for (int it = 0; it < C::ITEMS; ++it)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) carry[sub][it][e] = 0.f;
-        if (C::DEC) {
-#pragma unroll
-            for (int it = 0; it < C::ITEMS; ++it)
+            for (int e = 0; e < 4; ++e) carry[it][e] = 0.f;
+            if (C::DEC) {
 #pragma unroll
                 for (int g = 0; g < 3; ++g)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) rs[C::DEC ? it : 0][g][e] = 0.f;
+            }
         }
         // prefetch registers for the step about to be processed: gates (r,z,n,hn), h_prev, dh_out
-        float4 pg[NSUB][C::ITEMS][4], ph[NSUB][C::ITEMS], pd[NSUB][C::ITEMS];
-        auto prefetch = [&](int sub, int s) {
+        float4 ph[C::ITEMS], pd[C::ITEMS];
+        const float* G = Gb + ch * 4 * NB * HP;
+        auto prefetch = [&](int s) {
 #pragma unroll
             for (int it = 0; it < C::ITEMS; ++it) {
-                const int row = min(row0 + sub * NBS + bq + 16 * it, B - 1);
+                if (ib[it] < 0) continue;
+                const int j0 = ij[it];
+                const int row = min(rowc0 + ib[it], B - 1);
                 const size_t bs = (size_t)row * L + s;
                 const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int pl = 0; pl < 4; ++pl) pg[sub][it][pl] = ldg4(gates_g + (bs * 4 + pl) * HP + j0);
-                if (s > 0) ph[sub][it] = ldg4(hs_g + (bs - 1) * HP + j0);
-                else ph[sub][it] = (C::DEC && a.h0 != nullptr) ? ldg4(a.h0 + (size_t)row * HP + j0) : zero;
-                if (C::DEC) pd[sub][it] = ldg4(a.dh_out + bs * HP + j0);
-                else pd[sub][it] = (s == L - 1) ? ldg4(a.dh_fin + (size_t)row * (2 * HP) + dir * HP + j0) : zero;
+                if (s > 0) ph[it] = ld_stream4(hs_g + (bs - 1) * HP + j0);
+                else ph[it] = (C::DEC && a.h0 != nullptr) ? ldg4(a.h0 + (size_t)row * HP + j0) : zero;
+                if (C::DEC) pd[it] = ld_stream4(a.dh_out + bs * HP + j0);
+                else pd[it] = (s == L - 1) ? ldg4(a.dh_fin + (size_t)row * (2 * HP) + dir * HP + j0) : zero;
             }
         };
-#pragma unroll
-        for (int sub = 0; sub < NSUB; ++sub) prefetch(sub, L - 1);
+        prefetch(L - 1);
 
         for (int i = 0; i <= L; ++i) {
             const int s = L - 1 - i;                             // i == L: only collects the last contraction (dh0)
+            if (i > 0) {
+                if (lane == 0 && wl == 0) CPG_TL(8 + 16 * ch);
+                tc::mbar_wait(&bar_d[ch], (i - 1) & 1);
+                tc::tc_fence_after();
+                if (lane == 0 && wl == 0) CPG_TL(9 + 16 * ch);
+                const int q = warp & 3;
+                if ((wl >> 2) == 0 && q * 32 < HP) {             // first warp of each quadrant; lane = hidden unit j
+                    float v[NB];
+                    tmem_ld_cols<NB>(d0 + ((uint32_t)(q * 32) << 16), v);
+                    const int j = q * 32 + lane;
+                    if (j < HP) {
 #pragma unroll
-            for (int sub = 0; sub < NSUB; ++sub) {
-                float* P = Pb + sub * C::P_FLOATS;
+                        for (int c = 0; c < NB; ++c) P[c * HP + j] = v[c];
+                    }
+                }
+                tc::tc_fence_before();
+                if (lane == 0 && wl == 0) CPG_TL(10 + 16 * ch);
+                group_bar_sync(1 + ch, C::NT_G);
+                if (lane == 0 && wl == 0) CPG_TL(11 + 16 * ch);
+            }
+            if (i < L) tc::mbar_wait(&bar_g[ch], i & 1);         // this step's gate planes have landed in G
+#pragma unroll
+            for (int it = 0; it < C::ITEMS; ++it) {
+                const int b = ib[it], j0 = ij[it];
+                if (b < 0) continue;
+                const int row = rowc0 + b;
+                float dh[4] = {carry[it][0], carry[it][1], carry[it][2], carry[it][3]};
                 if (i > 0) {
-                    tc::mbar_wait(&bar_d[sub], (i - 1) & 1);
-                    tc::tc_fence_after();
-                    if (warp < 4) {                              // lane = hidden unit j (rows >= HP unused)
-                        float v[32];
-                        tc::tmem_ld_32x32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sub * NBS), v);
-                        const int j = warp * 32 + lane;
-                        if (j < HP) {
+                    const float4 p4 = ld4(P + b * HP + j0);
+                    dh[0] += p4.x; dh[1] += p4.y; dh[2] += p4.z; dh[3] += p4.w;
+                }
+                if (i == L) {
+                    if (C::DEC && row < B) {
+                        if (a.dh0 != nullptr) st4(a.dh0 + (size_t)row * HP + j0, make_float4(dh[0], dh[1], dh[2], dh[3]));
+                        if (a.drow != nullptr) {
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) P[c * HP + j] = v[c];
+                            for (int g = 0; g < 3; ++g)
+                                st4(a.drow + (size_t)row * K3 + g * HP + j0,
+                                    make_float4(rs[C::DEC ? it : 0][g][0], rs[C::DEC ? it : 0][g][1],
+                                                rs[C::DEC ? it : 0][g][2], rs[C::DEC ? it : 0][g][3]));
                         }
                     }
-                    tc::tc_fence_before();
-                    epi_bar_sync<C::NT_EPI>();
+                    continue;
                 }
+                const float4 g_r = ld4(G + b * HP + j0), g_z = ld4(G + (NB + b) * HP + j0);
+                const float4 g_n = ld4(G + (2 * NB + b) * HP + j0), g_hn = ld4(G + (3 * NB + b) * HP + j0);
+                const float r4[4] = {g_r.x, g_r.y, g_r.z, g_r.w};
+                const float z4[4] = {g_z.x, g_z.y, g_z.z, g_z.w};
+                const float n4[4] = {g_n.x, g_n.y, g_n.z, g_n.w};
+                const float hn4[4] = {g_hn.x, g_hn.y, g_hn.z, g_hn.w};
+                const float hp4[4] = {ph[it].x, ph[it].y, ph[it].z, ph[it].w};
+                const float do4[4] = {pd[it].x, pd[it].y, pd[it].z, pd[it].w};
+                float o_r[4], o_z[4], o_n[4], o_hn[4];
 #pragma unroll
-                for (int it = 0; it < C::ITEMS; ++it) {
-                    const int b = bq + 16 * it;
-                    const int row = row0 + sub * NBS + b;
-                    float dh[4] = {carry[sub][it][0], carry[sub][it][1], carry[sub][it][2], carry[sub][it][3]};
-                    if (i > 0) {
-                        const float4 p4 = ld4(P + b * HP + j0);
-                        dh[0] += p4.x; dh[1] += p4.y; dh[2] += p4.z; dh[3] += p4.w;
-                    }
-                    if (i == L) {
-                        if (C::DEC && row < B) {
-                            if (a.dh0 != nullptr) st4(a.dh0 + (size_t)row * HP + j0, make_float4(dh[0], dh[1], dh[2], dh[3]));
-                            if (a.drow != nullptr) {
-#pragma unroll
-                                for (int g = 0; g < 3; ++g)
-                                    st4(a.drow + (size_t)row * K3 + g * HP + j0,
-                                        make_float4(rs[C::DEC ? it : 0][g][0], rs[C::DEC ? it : 0][g][1],
-                                                    rs[C::DEC ? it : 0][g][2], rs[C::DEC ? it : 0][g][3]));
-                            }
-                        }
-                        continue;
-                    }
-                    const float r4[4] = {pg[sub][it][0].x, pg[sub][it][0].y, pg[sub][it][0].z, pg[sub][it][0].w};
-                    const float z4[4] = {pg[sub][it][1].x, pg[sub][it][1].y, pg[sub][it][1].z, pg[sub][it][1].w};
-                    const float n4[4] = {pg[sub][it][2].x, pg[sub][it][2].y, pg[sub][it][2].z, pg[sub][it][2].w};
-                    const float hn4[4] = {pg[sub][it][3].x, pg[sub][it][3].y, pg[sub][it][3].z, pg[sub][it][3].w};
-                    const float hp4[4] = {ph[sub][it].x, ph[sub][it].y, ph[sub][it].z, ph[sub][it].w};
-                    const float do4[4] = {pd[sub][it].x, pd[sub][it].y, pd[sub][it].z, pd[sub][it].w};
-                    float o_r[4], o_z[4], o_n[4], o_hn[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float dht = dh[e] + do4[e];
-                        const float dn = dht * (1.0f - z4[e]);
-                        const float dz = dht * (hp4[e] - n4[e]);
-                        carry[sub][it][e] = dht * z4[e];
-                        const float dn_pre = dn * (1.0f - n4[e] * n4[e]);
-                        const float dr = dn_pre * hn4[e];
-                        o_hn[e] = dn_pre * r4[e];
-                        o_r[e] = dr * r4[e] * (1.0f - r4[e]);
-                        o_z[e] = dz * z4[e] * (1.0f - z4[e]);
-                        o_n[e] = dn_pre;
-                        if (C::DEC) {
-                            rs[C::DEC ? it : 0][0][e] += o_r[e];
-                            rs[C::DEC ? it : 0][1][e] += o_z[e];
-                            rs[C::DEC ? it : 0][2][e] += o_n[e];
-                        }
-                    }
-                    // operand tile: K index = g*HP + j for (dr_pre, dz_pre, dhn)
-                    const int boff = (b >> 3) * X_SBO + (b & 7) * 16;
-                    uint2 hi, lo;
-                    unsigned char* X0 = Xb + (sub * 2 + 0) * C::X_SPLIT;
-                    unsigned char* X1 = Xb + (sub * 2 + 1) * C::X_SPLIT;
-                    split4(o_r, hi, lo);
-                    int k = j0;
-                    *reinterpret_cast<uint2*>(X0 + (k >> 3) * X_LBO + boff + (k & 7) * 2) = hi;
-                    *reinterpret_cast<uint2*>(X1 + (k >> 3) * X_LBO + boff + (k & 7) * 2) = lo;
-                    split4(o_z, hi, lo);
-                    k = HP + j0;
-                    *reinterpret_cast<uint2*>(X0 + (k >> 3) * X_LBO + boff + (k & 7) * 2) = hi;
-                    *reinterpret_cast<uint2*>(X1 + (k >> 3) * X_LBO + boff + (k & 7) * 2) = lo;
-                    split4(o_hn, hi, lo);
-                    k = 2 * HP + j0;
-                    *reinterpret_cast<uint2*>(X0 + (k >> 3) * X_LBO + boff + (k & 7) * 2) = hi;
-                    *reinterpret_cast<uint2*>(X1 + (k >> 3) * X_LBO + boff + (k & 7) * 2) = lo;
-                    if (row < B) {
-                        float* gp = dg_g + ((size_t)row * L + s) * 4 * HP + j0;
-                        st4(gp, make_float4(o_r[0], o_r[1], o_r[2], o_r[3]));
-                        st4(gp + HP, make_float4(o_z[0], o_z[1], o_z[2], o_z[3]));
-                        st4(gp + 2 * HP, make_float4(o_n[0], o_n[1], o_n[2], o_n[3]));
-                        st4(gp + 3 * HP, make_float4(o_hn[0], o_hn[1], o_hn[2], o_hn[3]));
+                for (int e = 0; e < 4; ++e) {
+                    const float dht = dh[e] + do4[e];
+                    const float dn = dht * (1.0f - z4[e]);
+                    const float dz = dht * (hp4[e] - n4[e]);
+                    carry[it][e] = dht * z4[e];
+                    const float dn_pre = dn * (1.0f - n4[e] * n4[e]);
+                    const float dr = dn_pre * hn4[e];
+                    o_hn[e] = dn_pre * r4[e];
+                    o_r[e] = dr * r4[e] * (1.0f - r4[e]);
+                    o_z[e] = dz * z4[e] * (1.0f - z4[e]);
+                    o_n[e] = dn_pre;
+                    if (C::DEC) {
+                        rs[C::DEC ? it : 0][0][e] += o_r[e];
+                        rs[C::DEC ? it : 0][1][e] += o_z[e];
+                        rs[C::DEC ? it : 0][2][e] += o_n[e];
                     }
                 }
-                if (i < L) {
-                    tc::fence_proxy_async();
-                    tc::mbar_arrive(&bar_x[sub]);
-                    if (s > 0) prefetch(sub, s - 1);             // in flight under the other sub-tile / the MMAs
+                // operand tile: K index = g*HP + j for (dr_pre, dz_pre, dhn)
+                const int boff = (b >> 3) * X_SBO + (b & 7) * 16;
+                uint2 hi, lo;
+                split4(o_r, hi, lo);
+                int k = j0;
+                *reinterpret_cast<uint2*>(X0 + (k >> 3) * C::X_LBO + boff + (k & 7) * 2) = hi;
+                *reinterpret_cast<uint2*>(X1 + (k >> 3) * C::X_LBO + boff + (k & 7) * 2) = lo;
+                split4(o_z, hi, lo);
+                k = HP + j0;
+                *reinterpret_cast<uint2*>(X0 + (k >> 3) * C::X_LBO + boff + (k & 7) * 2) = hi;
+                *reinterpret_cast<uint2*>(X1 + (k >> 3) * C::X_LBO + boff + (k & 7) * 2) = lo;
+                split4(o_hn, hi, lo);
+                k = 2 * HP + j0;
+                *reinterpret_cast<uint2*>(X0 + (k >> 3) * C::X_LBO + boff + (k & 7) * 2) = hi;
+                *reinterpret_cast<uint2*>(X1 + (k >> 3) * C::X_LBO + boff + (k & 7) * 2) = lo;
+                if (row < B) {
+                    float* gp = dg_g + ((size_t)row * L + s) * 4 * HP + j0;
+                    st4(gp, make_float4(o_r[0], o_r[1], o_r[2], o_r[3]));
+                    st4(gp + HP, make_float4(o_z[0], o_z[1], o_z[2], o_z[3]));
+                    st4(gp + 2 * HP, make_float4(o_n[0], o_n[1], o_n[2], o_n[3]));
+                    st4(gp + 3 * HP, make_float4(o_hn[0], o_hn[1], o_hn[2], o_hn[3]));
                 }
+            }
+            if (i < L) {
+                if (lane == 0 && wl == 0) CPG_TL(12 + 16 * ch);
+                tc::fence_proxy_async();
+                tc::mbar_arrive(&bar_x[ch]);
+                if (lane == 0 && wl == 0) CPG_TL(13 + 16 * ch);
+                if (s > 0) prefetch(s - 1);                      // in flight under the MMAs / the other chain
+                if (lane == 0 && wl == 0) CPG_TL(14 + 16 * ch);
             }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
+    CPG_TL0(52);
     if (warp == C::NW_EPI) tc::tmem_dealloc<C::TMEM_COLS>(tmem_d);
 }
 
-using EncFwd = FwdCfg<ENC_H, ENC_H, 2, false>;
-using DecFwd = FwdCfg<DEC_HP, 112, 1, true>;
-using EncBwd = BwdCfg<ENC_H, 2, false>;
-using DecBwd = BwdCfg<DEC_HP, 1, true>;
+// chains per CTA x batch rows per chain: 64 rows per CTA (encoder, 2 directions -> 128 CTAs at B = 4096),
+// 32 rows per CTA (decoder -> 128 CTAs)
+using EncFwd = FwdCfg<ENC_H, ENC_H, 32, 2, CPG_ENC_FWD_NWG, false>;     // KID 0 | 1 (forward), 2 | 3 (backward)
+using DecFwd = FwdCfg<DEC_HP, 112, 16, 2, 7, true>;
+using EncBwd = BwdCfg<ENC_H, 32, 2, CPG_ENC_BWD_NWG, false>;
+using DecBwd = BwdCfg<DEC_HP, 16, 2, 7, true>;
 
 template <class K>
 int set_smem(K kfn, size_t bytes, size_t& set_for) {
@@ -714,7 +818,7 @@ int launch_gru_fwd_enc_tc(cudaStream_t s, const GruSeq* two, int B, int L, int V
     const size_t smem = EncFwd::smem_bytes(V, L);
     static size_t set_for = 0;
     if (set_smem(k_gru_fwd_tc<EncFwd>, smem, set_for)) return CPG_ECUDA;
-    CPG_LAUNCH_NAMED("k_gru_fwd_enc_tc", k_gru_fwd_tc<EncFwd>, dim3(ceil_div(B, EncFwd::NSUB * NBS), 2), EncFwd::NTHREADS, smem, s, a);
+    CPG_LAUNCH_NAMED("k_gru_fwd_enc_tc", k_gru_fwd_tc<EncFwd>, dim3(ceil_div(B, EncFwd::NCH * EncFwd::NB), 2), EncFwd::NTHREADS, smem, s, a);
     return CPG_OK;
 }
 
@@ -727,7 +831,7 @@ int launch_gru_fwd_dec_tc(cudaStream_t s, const GruSeq& q, int B, int L, int V) 
     const size_t smem = DecFwd::smem_bytes(V, L);
     static size_t set_for = 0;
     if (set_smem(k_gru_fwd_tc<DecFwd>, smem, set_for)) return CPG_ECUDA;
-    CPG_LAUNCH_NAMED("k_gru_fwd_dec_tc", k_gru_fwd_tc<DecFwd>, dim3(ceil_div(B, DecFwd::NSUB * NBS), 1), DecFwd::NTHREADS, smem, s, a);
+    CPG_LAUNCH_NAMED("k_gru_fwd_dec_tc", k_gru_fwd_tc<DecFwd>, dim3(ceil_div(B, DecFwd::NCH * DecFwd::NB), 1), DecFwd::NTHREADS, smem, s, a);
     return CPG_OK;
 }
 
@@ -742,7 +846,7 @@ int launch_gru_bwd_enc_tc(cudaStream_t s, const GruSeq* two, int B, int L) {
     const size_t smem = EncBwd::smem_bytes();
     static size_t set_for = 0;
     if (set_smem(k_gru_bwd_tc<EncBwd>, smem, set_for)) return CPG_ECUDA;
-    CPG_LAUNCH_NAMED("k_gru_bwd_enc_tc", k_gru_bwd_tc<EncBwd>, dim3(ceil_div(B, EncBwd::NSUB * NBS), 2), EncBwd::NTHREADS, smem, s, a);
+    CPG_LAUNCH_NAMED("k_gru_bwd_enc_tc", k_gru_bwd_tc<EncBwd>, dim3(ceil_div(B, EncBwd::NCH * EncBwd::NB), 2), EncBwd::NTHREADS, smem, s, a);
     return CPG_OK;
 }
 
@@ -755,7 +859,7 @@ int launch_gru_bwd_dec_tc(cudaStream_t s, const GruSeq& q, int B, int L) {
     const size_t smem = DecBwd::smem_bytes();
     static size_t set_for = 0;
     if (set_smem(k_gru_bwd_tc<DecBwd>, smem, set_for)) return CPG_ECUDA;
-    CPG_LAUNCH_NAMED("k_gru_bwd_dec_tc", k_gru_bwd_tc<DecBwd>, dim3(ceil_div(B, DecBwd::NSUB * NBS), 1), DecBwd::NTHREADS, smem, s, a);
+    CPG_LAUNCH_NAMED("k_gru_bwd_dec_tc", k_gru_bwd_tc<DecBwd>, dim3(ceil_div(B, DecBwd::NCH * DecBwd::NB), 1), DecBwd::NTHREADS, smem, s, a);
     return CPG_OK;
 }
 
