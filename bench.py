@@ -33,6 +33,16 @@ METRIC, UNIT = 'wae_train_seq_per_s', 'seq/s'
 WORKLOAD = 'WAE phase-1 full config, batch=4096 len<=25, fp32 (BASELINE.json configs[1])'
 
 
+def load_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu summary."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    try:
+        with open(path) as f:
+            return json.load(f).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
@@ -77,22 +87,35 @@ class ClockSampler(threading.Thread):
 
 
 # per-kernel algorithmic work of ONE launch at batch B: (flops, bytes)
-def kernel_work(B, L=SEQ_LEN, V=N_VOCAB):
-    He, Hd, HP = 80, 102, 104
+def kernel_work(B, L=SEQ_LEN, V=N_VOCAB, R=500):
+    He, Hd, HP, Z = 80, 102, 104, 100
     f4 = 4
+    fwd_enc = (2 * 2 * B * L * He * 3 * He, 2 * B * L * (5 * He) * f4)           # writes h + (r, z, n, hn), both directions
+    fwd_dec = (2 * B * L * Hd * 3 * Hd, B * L * (5 * HP) * f4)
+    bwd_enc = (2 * 2 * B * L * He * 3 * He, 2 * B * L * (5 * He + 4 * He) * f4)  # reads 4 gate planes + h_prev, writes 4 dg planes
+    bwd_dec = (2 * B * L * Hd * 3 * Hd, B * L * (6 * HP + 4 * HP) * f4)          # + dh_out
+    # the twelve small dense products of one iteration (heads, [z;c] projection, RF map and their transposes): (M, N, K)
+    gemms = [(B, Z, 2 * He)] * 2 + [(B, 3 * HP, HP)] + [(B, R, Z)] * 2 + [(B, HP, 3 * HP), (3 * HP, HP, B)] + \
+            [(B, 2 * He, Z)] * 2 + [(Z, 2 * He, B)] * 2 + [(B, Z, R)]
+    g_flops = sum(2 * m * n * k for m, n, k in gemms)
+    g_bytes = sum((m * k + k * n + m * n) * f4 for m, n, k in gemms)
     return {
-        'k_gru_fwd_enc': (2 * 2 * B * L * He * 3 * He, 2 * B * L * (5 * He) * f4),
-        'k_gru_fwd_dec': (2 * B * L * Hd * 3 * Hd, B * L * (5 * HP) * f4),
-        'k_gru_bwd_enc': (2 * 2 * B * L * He * 3 * He, 2 * B * L * (5 * He + 4 * He) * f4),
-        'k_gru_bwd_dec': (2 * B * L * Hd * 3 * Hd, B * L * (6 * HP + 4 * HP) * f4),
+        'k_gru_fwd_enc': fwd_enc, 'k_gru_fwd_enc_tc': fwd_enc,
+        'k_gru_fwd_dec': fwd_dec, 'k_gru_fwd_dec_tc': fwd_dec,
+        'k_gru_bwd_enc': bwd_enc, 'k_gru_bwd_enc_tc': bwd_enc,
+        'k_gru_bwd_dec': bwd_dec, 'k_gru_bwd_dec_tc': bwd_dec,
         'k_wgrad_hh_enc': (2 * B * L * He * 3 * He, B * L * (4 * He) * f4),
         'k_wgrad_hh_dec': (2 * B * L * Hd * 3 * Hd, B * L * (4 * HP) * f4),
-        'k_wgrad_hh_tc_enc': (2 * B * L * He * 3 * He, B * L * (4 * He) * f4),      # 3 gate planes + h read once
-        'k_wgrad_hh_tc_dec': (2 * B * L * Hd * 3 * Hd, B * L * (4 * HP) * f4),
+        # one pass over the 4 dg planes + h: dW_hh (3 planes x H) and the token-table gradient (4 planes x 32 one-hot columns)
+        'k_wgrad_tc_enc': (2 * B * L * (3 * He * He + 4 * He * 32), B * L * (5 * He) * f4),
+        'k_wgrad_tc_dec': (2 * B * L * (3 * HP * HP + 4 * HP * 32), B * L * (5 * HP) * f4),
         'k_mmd_gram_tc': (3 * 2 * B * B * 100, 2 * B * 128 * f4),
+        'k_mmd_gram_tc2': (3 * 2 * B * B * 100, 2 * B * 128 * f4),
         'k_dec_out': (2 * 3 * B * L * Hd * V, B * L * (2 * HP * f4 + Hd)),
         'k_mmd_gram': (3 * 2 * B * B * 100, 2 * B * 100 * f4),
         'k_dtable': (B * L * 4 * HP, B * L * 4 * HP * f4),
+        'k_sgemm': (g_flops / len(gemms), g_bytes / len(gemms)),                  # average of the 12 launches of one iteration
+        'k_input_grads': (2 * V * 150 * (2 * 3 * He + 3 * HP), V * (2 * 4 * He + 4 * HP) * f4),
     }
 
 
@@ -202,9 +225,11 @@ def run_ours(args):
                                      'frac_tensor': round(f / (kms / 1e3) / 1e12 / peaks['bf16_tflops_sustained'], 4),
                                      'frac_hbm': round(nb / (kms / 1e3) / 1e9 / peaks['hbm_gbs'], 4)}
     roof.update({'per_kernel': per_kernel_roof, 'kernel': dom, 'kernel_ms': round(per_kernel[dom][0], 4), 'launches_per_step': per_kernel[dom][1],
-                 'share_of_step': round(step_share[dom] / sum(step_share.values()), 4), 'traffic': None,
+                 'share_of_step': round(step_share[dom] / sum(step_share.values()), 4), 'traffic': load_traffic(dom),
                  'peak_source': peak_src + ' (MEASURED_PEAKS.json, sustained)' if peak_src == 'measured' else peak_src,
-                 'note': 'fp32 SIMT kernel: FLOP/s shown against the bf16 tensor peak; see DESIGN.md',
+                 'note': 'dominant kernel = largest share of the step by CUDA events; per_kernel lists every kernel with a work model '
+                         '(FLOP/s against the bf16 tensor peak, bytes against the HBM copy peak); traffic = dram bytes of one launch from '
+                         'the committed ncu --set full capture (profiles/), null if that kernel was not captured',
                  'top_kernels_ms_per_step': {k: round(v, 4) for k, v in sorted(step_share.items(), key=lambda x: -x[1])[:8]}})
 
     # ---- end to end through the reference-facing API: host tokens -> train_vae.train_vae -> host scalars
