@@ -113,6 +113,124 @@ k_sgemm(int M, int N, int K, float alpha, const float* __restrict__ A, int64_t s
     }
 }
 
+// ---- pipelined variant for 16-byte-aligned operands (every product of the training step) -------------
+// 64x64x16 tiles (B = 4096 gives 128..512 CTAs for the step's shapes instead of 64..256), 4x4 register
+// tile, and a 4-stage cp.async pipeline so that three k-tiles of global latency are always in flight
+// (the K loops here are only 7..32 tiles long: with one tile of prefetch the kernel was latency-bound).
+// Each operand keeps its own fastest axis in shared memory (16-byte cp.async chunks along it); the FMA
+// loop consumes four k's at a time so that either orientation is read with float4.
+constexpr int PM = 64, PN = 64, PK = 16, PST = 4, PPAD = 4;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool A_KFAST, bool B_KFAST>
+__global__ void __launch_bounds__(256)
+k_sgemm_pipe(int M, int N, int K, float alpha, const float* __restrict__ A, int64_t lda,
+             const float* __restrict__ Bm, int64_t ldb, float beta, float* __restrict__ C, int64_t ldc,
+             const float* __restrict__ bias, int kchunk, float* __restrict__ ws) {
+    // A_KFAST: A(m,k) = A[m*lda + k] -> As[m][k]   else A(m,k) = A[k*lda + m] -> As[k][m]
+    // B_KFAST: B(k,n) = B[n*ldb + k] -> Bs[n][k]   else B(k,n) = B[k*ldb + n] -> Bs[k][n]
+    constexpr int AROWS = A_KFAST ? PM : PK, ACOLS = (A_KFAST ? PK : PM) + PPAD;
+    constexpr int BROWS = B_KFAST ? PN : PK, BCOLS = (B_KFAST ? PK : PN) + PPAD;
+    __shared__ __align__(16) float As[PST][AROWS][ACOLS];
+    __shared__ __align__(16) float Bs[PST][BROWS][BCOLS];
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    const int m0 = blockIdx.y * PM, n0 = blockIdx.x * PN;
+    const int kbeg = blockIdx.z * kchunk;
+    const int kend = min(K, kbeg + kchunk);
+    const int ntile = kend > kbeg ? (kend - kbeg + PK - 1) / PK : 0;
+
+    auto issue = [&](int t) {                                  // k-tile t of this CTA -> stage t % PST
+        const int st = t % PST, k0 = kbeg + t * PK;
+        {   // one 16-byte chunk of A per thread
+            int r, c, gm, gk, valid;
+            if (A_KFAST) { r = tid / 4; c = (tid % 4) * 4; gm = m0 + r; gk = k0 + c; valid = gm < M ? (kend - gk) : 0; }
+            else { r = tid / 16; c = (tid % 16) * 4; gk = k0 + r; gm = m0 + c; valid = gk < kend ? (M - gm) : 0; }
+            valid = max(0, min(4, valid));
+            const float* src = valid > 0 ? (A_KFAST ? A + (int64_t)gm * lda + gk : A + (int64_t)gk * lda + gm) : A;
+            cp_async16(&As[st][r][c], src, valid * 4);
+        }
+        {
+            int r, c, gn, gk, valid;
+            if (B_KFAST) { r = tid / 4; c = (tid % 4) * 4; gn = n0 + r; gk = k0 + c; valid = gn < N ? (kend - gk) : 0; }
+            else { r = tid / 16; c = (tid % 16) * 4; gk = k0 + r; gn = n0 + c; valid = gk < kend ? (N - gn) : 0; }
+            valid = max(0, min(4, valid));
+            const float* src = valid > 0 ? (B_KFAST ? Bm + (int64_t)gn * ldb + gk : Bm + (int64_t)gk * ldb + gn) : Bm;
+            cp_async16(&Bs[st][r][c], src, valid * 4);
+        }
+    };
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+    for (int t = 0; t < PST - 1; ++t) {
+        if (t < ntile) issue(t);
+        cp_async_commit();
+    }
+    for (int t = 0; t < ntile; ++t) {
+        cp_async_wait<PST - 2>();
+        __syncthreads();                                       // tile t landed; everyone is done with tile t-1's stage
+        if (t + PST - 1 < ntile) issue(t + PST - 1);
+        cp_async_commit();
+        const int st = t % PST;
+#pragma unroll
+        for (int kq = 0; kq < PK / 4; ++kq) {
+            float a[4][4], b[4][4];                            // [row i | col j][k within the group of 4]
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                if (A_KFAST) {
+                    const float4 v = ld4(&As[st][ty * 4 + x][kq * 4]);
+                    a[x][0] = v.x; a[x][1] = v.y; a[x][2] = v.z; a[x][3] = v.w;
+                } else {
+                    const float4 v = ld4(&As[st][kq * 4 + x][ty * 4]);
+                    a[0][x] = v.x; a[1][x] = v.y; a[2][x] = v.z; a[3][x] = v.w;
+                }
+                if (B_KFAST) {                                 // columns tx + 16 j: conflict-free with the 20-float row stride
+                    const float4 v = ld4(&Bs[st][tx + 16 * x][kq * 4]);
+                    b[x][0] = v.x; b[x][1] = v.y; b[x][2] = v.z; b[x][3] = v.w;
+                } else {                                       // columns 4 tx + j
+                    const float4 v = ld4(&Bs[st][kq * 4 + x][tx * 4]);
+                    b[0][x] = v.x; b[1][x] = v.y; b[2][x] = v.z; b[3][x] = v.w;
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i][kk], b[j][kk], acc[i][j]);
+        }
+    }
+    const bool split = gridDim.z > 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + (B_KFAST ? tx + 16 * j : tx * 4 + j);
+            if (gn >= N) continue;
+            if (split) {
+                ws[((size_t)blockIdx.z * M + gm) * N + gn] = acc[i][j];
+            } else {
+                float v = alpha * acc[i][j];
+                if (bias != nullptr) v += bias[gn];
+                if (beta != 0.f) v += beta * C[gm * ldc + gn];
+                C[gm * ldc + gn] = v;
+            }
+        }
+    }
+}
+
 __global__ void k_splitk_reduce(int M, int N, int splits, float alpha, const float* __restrict__ ws, float beta,
                                 float* __restrict__ C, int64_t ldc, const float* __restrict__ bias) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,6 +250,23 @@ void launch_sgemm(cudaStream_t s, int M, int N, int K, float alpha, const float*
     if (split_k < 1 || ws == nullptr) split_k = 1;
     int kchunk = ceil_div(ceil_div(K, split_k), GK) * GK;
     split_k = ceil_div(K, kchunk);
+    // pipelined kernel: one operand axis has unit stride, the other a multiple of 4 floats, bases 16-byte aligned
+    const bool a_k = sak == 1, a_m = sam == 1, b_k = sbk == 1, b_n = sbn == 1;
+    const int64_t lda = a_k ? sam : sak, ldb = b_k ? sbn : sbk;
+    const bool aligned = (a_k || a_m) && (b_k || b_n) && lda % 4 == 0 && ldb % 4 == 0 &&
+                         ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0;
+    if (aligned) {
+        dim3 grid(ceil_div(N, PN), ceil_div(M, PM), split_k);
+#define CPG_PIPE(AK, BK) CPG_LAUNCH_NAMED("k_sgemm", (k_sgemm_pipe<AK, BK>), grid, 256, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, kchunk, ws)
+        if (a_k && !b_k) CPG_PIPE(true, false);
+        else if (a_k && b_k) CPG_PIPE(true, true);
+        else if (!a_k && !b_k) CPG_PIPE(false, false);
+        else CPG_PIPE(false, true);
+#undef CPG_PIPE
+        if (split_k > 1)
+            CPG_LAUNCH(k_splitk_reduce, ceil_div(M * N, 256), 256, 0, s, M, N, split_k, alpha, ws, beta, C, ldc, bias);
+        return;
+    }
     dim3 grid(ceil_div(N, GN), ceil_div(M, GM), split_k);
     CPG_LAUNCH(k_sgemm, grid, 256, 0, s, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc, bias, kchunk, ws);
     if (split_k > 1)
