@@ -77,6 +77,37 @@ __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + e
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// ---- ordered reduction of split partials:  sum_p part[p * pstride + off]
+// Block = (32 outputs) x (RED_Y split lanes).  Lane y accumulates partials y, y + RED_Y, ... with four
+// independent loads in flight, then the RED_Y lane sums are added in lane order from shared memory: the
+// result is bit-reproducible run to run (no atomics) and the serial chain is nsplit / RED_Y long instead of nsplit.
+constexpr int RED_X = 32, RED_Y = 8;
+__device__ __forceinline__ float block_split_sum(const float* __restrict__ part, size_t pstride, int nsplit, size_t off, bool active) {
+    __shared__ float red_s[RED_Y][RED_X + 1];
+    const int y = threadIdx.y;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (active) {
+        int p = y;
+        for (; p + 3 * RED_Y < nsplit; p += 4 * RED_Y) {
+            s0 += part[(size_t)p * pstride + off];
+            s1 += part[(size_t)(p + RED_Y) * pstride + off];
+            s2 += part[(size_t)(p + 2 * RED_Y) * pstride + off];
+            s3 += part[(size_t)(p + 3 * RED_Y) * pstride + off];
+        }
+        for (; p < nsplit; p += RED_Y) s0 += part[(size_t)p * pstride + off];
+    }
+    red_s[y][threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    float s = 0.f;
+    if (y == 0) {
+#pragma unroll
+        for (int q = 0; q < RED_Y; ++q) s += red_s[q][threadIdx.x];
+    }
+    return s;                                                  // valid on threadIdx.y == 0
+}
+#define CPG_RED_GRID(n) cpg::ceil_div((n), cpg::RED_X)
+#define CPG_RED_BLOCK dim3(cpg::RED_X, cpg::RED_Y)
+
 // ---- Philox4x32-10 counter RNG (Salmon et al. 2011), used by the perf-mode noise
 // generators; key = (seed lo, seed hi), counter = (index lo, index hi, stream, 0).
 struct Philox {

@@ -215,21 +215,20 @@ k_dec_out(DecOutArgs a) {
 __global__ void k_dec_out_reduce(const float* __restrict__ part_w, const float* __restrict__ part_b,
                                  const float* __restrict__ part_nll, int nparts, int V,
                                  float* __restrict__ dW, float* __restrict__ db, float* __restrict__ nll_sum) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < V * DEC_H) {
-        int v = i / DEC_H, j = i % DEC_H;
-        float s = 0.f;
-        for (int p = 0; p < nparts; ++p) s += part_w[((size_t)p * VMAX + v) * DEC_HP + j];
-        dW[i] = s;
-    } else if (i < V * DEC_H + V) {
-        int v = i - V * DEC_H;
-        float s = 0.f;
-        for (int p = 0; p < nparts; ++p) s += part_b[(size_t)p * VMAX + v];
-        db[v] = s;
-    } else if (i == V * DEC_H + V && nll_sum != nullptr) {
-        double s = 0.0;
-        for (int p = 0; p < nparts; ++p) s += (double)part_nll[p];
-        *nll_sum = (float)s;
+    const int i = blockIdx.x * RED_X + threadIdx.x;
+    const int nW = V * DEC_H;
+    const bool isW = i < nW, isB = !isW && i - nW < V;
+    const float* src = isW ? part_w : part_b;
+    const size_t stride = isW ? (size_t)VMAX * DEC_HP : (size_t)VMAX;
+    const size_t off = isW ? (size_t)(i / DEC_H) * DEC_HP + i % DEC_H : (size_t)(isB ? i - nW : 0);
+    const float s = block_split_sum(src, stride, nparts, off, isW || isB);      // one uniform call per block
+    if (threadIdx.y != 0) return;
+    if (isW) dW[i] = s;
+    else if (isB) db[i - nW] = s;
+    else if (i - nW == V && nll_sum != nullptr) {
+        double t = 0.0;
+        for (int p = 0; p < nparts; ++p) t += (double)part_nll[p];
+        *nll_sum = (float)t;
     }
 }
 
@@ -247,7 +246,7 @@ void launch_dec_out(cudaStream_t s, const DecOutArgs& a, int sm_count) {
 void launch_dec_out_reduce(cudaStream_t s, const DecOutArgs& a, int sm_count, float* dW, float* db, float* nll_sum) {
     int parts = dec_out_parts(a.B, a.L, sm_count);
     int n = a.V * DEC_H + a.V + 1;
-    CPG_LAUNCH(k_dec_out_reduce, ceil_div(n, 128), 128, 0, s, a.part_w, a.part_b, a.part_nll, parts, a.V, dW, db, nll_sum);
+    CPG_LAUNCH(k_dec_out_reduce, CPG_RED_GRID(n), CPG_RED_BLOCK, 0, s, a.part_w, a.part_b, a.part_nll, parts, a.V, dW, db, nll_sum);
 }
 
 }  // namespace cpg

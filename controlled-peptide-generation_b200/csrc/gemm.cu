@@ -233,11 +233,11 @@ k_sgemm_pipe(int M, int N, int K, float alpha, const float* __restrict__ A, int6
 
 __global__ void k_splitk_reduce(int M, int N, int splits, float alpha, const float* __restrict__ ws, float beta,
                                 float* __restrict__ C, int64_t ldc, const float* __restrict__ bias) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M * N) return;
+    const int i = blockIdx.x * RED_X + threadIdx.x;
+    const bool ok = i < M * N;
+    const float s = block_split_sum(ws, (size_t)M * N, splits, (size_t)(ok ? i : 0), ok);
+    if (!ok || threadIdx.y != 0) return;
     int m = i / N, n = i % N;
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += ws[(size_t)z * M * N + i];
     float v = alpha * s;
     if (bias != nullptr) v += bias[n];
     if (beta != 0.f) v += beta * C[m * ldc + n];
@@ -264,13 +264,13 @@ void launch_sgemm(cudaStream_t s, int M, int N, int K, float alpha, const float*
         else CPG_PIPE(false, true);
 #undef CPG_PIPE
         if (split_k > 1)
-            CPG_LAUNCH(k_splitk_reduce, ceil_div(M * N, 256), 256, 0, s, M, N, split_k, alpha, ws, beta, C, ldc, bias);
+            CPG_LAUNCH(k_splitk_reduce, CPG_RED_GRID(M * N), CPG_RED_BLOCK, 0, s, M, N, split_k, alpha, ws, beta, C, ldc, bias);
         return;
     }
     dim3 grid(ceil_div(N, GN), ceil_div(M, GM), split_k);
     CPG_LAUNCH(k_sgemm, grid, 256, 0, s, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc, bias, kchunk, ws);
     if (split_k > 1)
-        CPG_LAUNCH(k_splitk_reduce, ceil_div(M * N, 256), 256, 0, s, M, N, split_k, alpha, ws, beta, C, ldc, bias);
+        CPG_LAUNCH(k_splitk_reduce, CPG_RED_GRID(M * N), CPG_RED_BLOCK, 0, s, M, N, split_k, alpha, ws, beta, C, ldc, bias);
 }
 
 // column sums, two deterministic stages: partial[chunk][n] then ordered sum over chunks
@@ -285,11 +285,10 @@ __global__ void k_colsum_partial(const float* __restrict__ A, int M, int N, int6
     part[(size_t)c * N + n] = s;
 }
 __global__ void k_colsum_final(const float* __restrict__ part, int nchunk, int N, float* __restrict__ out) {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float s = 0.f;
-    for (int c = 0; c < nchunk; ++c) s += part[(size_t)c * N + n];
-    out[n] = s;
+    const int n = blockIdx.x * RED_X + threadIdx.x;
+    const bool ok = n < N;
+    const float s = block_split_sum(part, (size_t)N, nchunk, (size_t)(ok ? n : 0), ok);
+    if (ok && threadIdx.y == 0) out[n] = s;
 }
 
 void launch_colsum(cudaStream_t s, const float* A, int M, int N, int64_t lda, float* out, float* ws, int nchunk) {
@@ -297,7 +296,7 @@ void launch_colsum(cudaStream_t s, const float* A, int M, int N, int64_t lda, fl
     int rpc = ceil_div(M, nchunk);
     nchunk = ceil_div(M, rpc);
     CPG_LAUNCH(k_colsum_partial, dim3(ceil_div(N, 128), nchunk), 128, 0, s, A, M, N, lda, rpc, ws);
-    CPG_LAUNCH(k_colsum_final, ceil_div(N, 128), 128, 0, s, ws, nchunk, N, out);
+    CPG_LAUNCH(k_colsum_final, CPG_RED_GRID(N), CPG_RED_BLOCK, 0, s, ws, nchunk, N, out);
 }
 
 }  // namespace cpg

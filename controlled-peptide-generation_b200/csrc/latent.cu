@@ -129,11 +129,10 @@ __global__ void k_rf_colsum_partial(const float* __restrict__ pre, const float* 
     part[(size_t)c * R + r] = s;
 }
 __global__ void k_rf_colsum_final(const float* __restrict__ part, int nchunk, int R, float* __restrict__ out) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    float s = 0.f;
-    for (int c = 0; c < nchunk; ++c) s += part[(size_t)c * R + r];
-    out[r] = s;
+    const int r = blockIdx.x * RED_X + threadIdx.x;
+    const bool ok = r < R;
+    const float s = block_split_sum(part, (size_t)R, nchunk, (size_t)(ok ? r : 0), ok);
+    if (ok && threadIdx.y == 0) out[r] = s;
 }
 void launch_rf_colsum(cudaStream_t s, const float* pre, const float* rf_b, int B, int R, float sigma, float* part,
                       int nchunk, float* out) {
@@ -141,7 +140,7 @@ void launch_rf_colsum(cudaStream_t s, const float* pre, const float* rf_b, int B
     int rpc = ceil_div(B, nchunk);
     nchunk = ceil_div(B, rpc);
     CPG_LAUNCH(k_rf_colsum_partial, dim3(ceil_div(R, 128), nchunk), 128, 0, s, pre, rf_b, B, R, sigma, rpc, part);
-    CPG_LAUNCH(k_rf_colsum_final, ceil_div(R, 128), 128, 0, s, part, nchunk, R, out);
+    CPG_LAUNCH(k_rf_colsum_final, CPG_RED_GRID(R), CPG_RED_BLOCK, 0, s, part, nchunk, R, out);
 }
 
 // loss = sum_r (mean1 - mean2)^2 from the GLOBAL feature sums; also

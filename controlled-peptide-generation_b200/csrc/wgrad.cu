@@ -71,12 +71,11 @@ k_wgrad_hh(const float* __restrict__ dg, const float* __restrict__ hs, const flo
 
 // dW_hh [3H][H] (unpadded) = ordered sum of the split partials [split][3HP][HP]
 __global__ void k_wgrad_hh_reduce(const float* __restrict__ part, int nsplit, int HP, int H, float* __restrict__ dW) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 3 * H * H) return;
-    int g = i / H, k = i % H, pl = g / H, j = g % H;
-    float s = 0.f;
-    for (int p = 0; p < nsplit; ++p) s += part[((size_t)p * 3 * HP + pl * HP + j) * HP + k];
-    dW[i] = s;
+    const int i = blockIdx.x * RED_X + threadIdx.x;
+    const bool ok = i < 3 * H * H;
+    const int g = ok ? i / H : 0, k = ok ? i % H : 0, pl = g / H, j = g % H;
+    const float s = block_split_sum(part, (size_t)3 * HP * HP, nsplit, (size_t)(pl * HP + j) * HP + k, ok);
+    if (ok && threadIdx.y == 0) dW[i] = s;
 }
 
 int wgrad_splits(int B, int L, int sm_count) {
@@ -104,8 +103,8 @@ bool launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float
     if ((g_opt_wgrad_tc == 1 && nrows >= 8192) || g_opt_wgrad_tc == 2) {
         int nsplit = 0;
         if (launch_wgrad_tc(s, HP, dg, hs, h0, tok, reverse, B, L, V, sm_count, part, dt_part, &nsplit) == 0) {
-            CPG_LAUNCH(k_wgrad_hh_reduce, ceil_div(3 * H * H, 256), 256, 0, s, part, nsplit, HP, H, dW);
-            CPG_LAUNCH(k_dtable_reduce, ceil_div(V * 4 * HP, 256), 256, 0, s, dt_part, nsplit, V * 4 * HP, dT);
+            CPG_LAUNCH(k_wgrad_hh_reduce, CPG_RED_GRID(3 * H * H), CPG_RED_BLOCK, 0, s, part, nsplit, HP, H, dW);
+            CPG_LAUNCH(k_dtable_reduce, CPG_RED_GRID(V * 4 * HP), CPG_RED_BLOCK, 0, s, dt_part, nsplit, V * 4 * HP, dT);
             return true;                               // W_hh gradient (h0 rows included) and dT both done
         }
     }
@@ -125,7 +124,7 @@ void launch_wgrad_hh_simt(cudaStream_t s, int HP, int H, const float* dg, const 
     } else {
         CPG_LAUNCH_NAMED("k_wgrad_hh_dec", k_wgrad_hh<DEC_HP>, dim3(3, nsplit), (DEC_HP / 4) * (DEC_HP / 8), 0, s, dg, hs, h0, B, L, rps, part);
     }
-    CPG_LAUNCH(k_wgrad_hh_reduce, ceil_div(3 * H * H, 256), 256, 0, s, part, nsplit, HP, H, dW);
+    CPG_LAUNCH(k_wgrad_hh_reduce, CPG_RED_GRID(3 * H * H), CPG_RED_BLOCK, 0, s, part, nsplit, HP, H, dW);
 }
 
 // token-table gradient: thread c owns column c of the 4*HP planes; accumulators [V][4HP] in smem
@@ -157,11 +156,10 @@ __global__ void k_dtable(const float* __restrict__ dg, const uint8_t* __restrict
     for (int v = 0; v < V; ++v) out[v * HP4 + c] = acc[v * HP4 + c];
 }
 __global__ void k_dtable_reduce(const float* __restrict__ part, int nsplit, int n, float* __restrict__ dT) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float s = 0.f;
-    for (int p = 0; p < nsplit; ++p) s += part[(size_t)p * n + i];
-    dT[i] = s;
+    const int i = blockIdx.x * RED_X + threadIdx.x;
+    const bool ok = i < n;
+    const float s = block_split_sum(part, (size_t)n, nsplit, (size_t)(ok ? i : 0), ok);
+    if (ok && threadIdx.y == 0) dT[i] = s;
 }
 int dtable_splits(int B, int L, int sm_count) { return max(1, min(B * L, 2 * sm_count)); }
 void launch_dtable(cudaStream_t s, int HP, const float* dg, const uint8_t* tok, int B, int L, int reverse, int V,
@@ -174,7 +172,7 @@ void launch_dtable(cudaStream_t s, int HP, const float* dg, const uint8_t* tok, 
     size_t smem = (size_t)V * HP4 * sizeof(float);
     CPG_SET_MAX_SMEM(k_dtable, smem);
     CPG_LAUNCH(k_dtable, nsplit, HP4, smem, s, dg, tok, B, L, reverse, HP4, V, rps, part);
-    CPG_LAUNCH(k_dtable_reduce, ceil_div(V * HP4, 256), 256, 0, s, part, nsplit, V * HP4, dT);
+    CPG_LAUNCH(k_dtable_reduce, CPG_RED_GRID(V * HP4), CPG_RED_BLOCK, 0, s, part, nsplit, V * HP4, dT);
 }
 
 // input-side parameter gradients from the three table gradients
@@ -224,27 +222,43 @@ __global__ void k_input_grads(InputGradArgs a) {
             a.g_dec_bih[g] = si;
             a.g_dec_bhh[g] = sh;
         }
-    } else {                                // embedding gradient [V][150]; <pad> row stays 0 (model.py:47)
-        for (int i = t0; i < V * EMB; i += stride) {
-            int v = i / EMB, e = i % EMB;
-            float s = 0.f;
-            if (v != PAD) {
-                for (int d = 0; d < 2; ++d) {
-                    const float* dT = a.dT_enc[d] + v * 4 * ENC_H;
-                    const float* w = a.enc_wih[d];
-                    for (int g = 0; g < 3 * ENC_H; ++g) s = fmaf(dT[g], w[g * EMB + e], s);
-                }
-                const float* dT = a.dT_dec + v * 4 * DEC_HP;
-                for (int gate = 0; gate < 3; ++gate)
-                    for (int j = 0; j < DEC_H; ++j)
-                        s = fmaf(dT[gate * DEC_HP + j], a.dec_wih[(size_t)(gate * DEC_H + j) * DEC_IN + e], s);
+    }
+}
+// embedding gradient [V][150] = sum over the three tables' gate rows of dT[v][g] * W_ih[g][e]; <pad> row stays 0
+// (model.py:47).  786-long contraction per output: 8 slices of g per output, summed in slice order.
+__global__ void k_emb_grad(InputGradArgs a) {
+    __shared__ float red_s[RED_Y][RED_X + 1];
+    const int i = blockIdx.x * RED_X + threadIdx.x, y = threadIdx.y;
+    const bool ok = i < a.V * EMB;
+    const int v = ok ? i / EMB : 0, e = ok ? i % EMB : 0;
+    float s0 = 0.f, s1 = 0.f;
+    if (ok && v != PAD) {
+        for (int d = 0; d < 2; ++d) {
+            const float* dT = a.dT_enc[d] + v * 4 * ENC_H;
+            const float* w = a.enc_wih[d];
+            for (int g = y; g < 3 * ENC_H; g += 2 * RED_Y) {
+                s0 = fmaf(dT[g], w[g * EMB + e], s0);
+                s1 = fmaf(dT[g + RED_Y], w[(g + RED_Y) * EMB + e], s1);      // 240 = 15 * 16: no tail
             }
-            a.g_emb[i] = s;
         }
+        const float* dT = a.dT_dec + v * 4 * DEC_HP;
+        for (int g = y; g < 3 * DEC_H; g += RED_Y) {
+            const int gate = g / DEC_H, j = g % DEC_H;
+            s0 = fmaf(dT[gate * DEC_HP + j], a.dec_wih[(size_t)g * DEC_IN + e], s0);
+        }
+    }
+    red_s[y][threadIdx.x] = s0 + s1;
+    __syncthreads();
+    if (y == 0 && ok) {
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < RED_Y; ++q) s += red_s[q][threadIdx.x];
+        a.g_emb[i] = s;
     }
 }
 void launch_input_grads(cudaStream_t s, const InputGradArgs& a) {
-    CPG_LAUNCH(k_input_grads, dim3(32, 4), 256, 0, s, a);
+    CPG_LAUNCH(k_input_grads, dim3(32, 3), 256, 0, s, a);
+    CPG_LAUNCH(k_emb_grad, CPG_RED_GRID(a.V * EMB), CPG_RED_BLOCK, 0, s, a);
 }
 
 }  // namespace cpg
