@@ -13,6 +13,7 @@
 // partial per CTA (ordered reduction afterwards, no float atomics).
 #include "kernels.h"
 #include "dec_out.h"
+#include "../../include/cpg_b200.h"
 
 namespace cpg {
 
@@ -237,14 +238,23 @@ int dec_out_parts(int B, int L, int sm_count) {
     return max(1, min(tiles, 2 * max(1, sm_count)));
 }
 
+int g_opt_dec_out_tc = 1;
+static int g_last_parts = 0;       // partials written by the most recent launch_dec_out (consumed by the reduce that follows it)
+
 void launch_dec_out(cudaStream_t s, const DecOutArgs& a, int sm_count) {
+#ifndef CPG_EMU
+    if (g_opt_dec_out_tc == 2 || (g_opt_dec_out_tc == 1 && a.B * a.L >= 8192)) {
+        if (launch_dec_out_tc(s, a, sm_count, &g_last_parts) == CPG_OK) return;
+    }
+#endif
     const size_t smem = (size_t)(VMAX * DSTR + DT * DSTR + DT * LSTR) * sizeof(float) + DT * DEC_HP;
     CPG_SET_MAX_SMEM(k_dec_out, smem);
-    CPG_LAUNCH(k_dec_out, dec_out_parts(a.B, a.L, sm_count), DO_THREADS, smem, s, a);
+    g_last_parts = dec_out_parts(a.B, a.L, sm_count);
+    CPG_LAUNCH(k_dec_out, g_last_parts, DO_THREADS, smem, s, a);
 }
 
 void launch_dec_out_reduce(cudaStream_t s, const DecOutArgs& a, int sm_count, float* dW, float* db, float* nll_sum) {
-    int parts = dec_out_parts(a.B, a.L, sm_count);
+    int parts = g_last_parts > 0 ? g_last_parts : dec_out_parts(a.B, a.L, sm_count);
     int n = a.V * DEC_H + a.V + 1;
     CPG_LAUNCH(k_dec_out_reduce, CPG_RED_GRID(n), CPG_RED_BLOCK, 0, s, a.part_w, a.part_b, a.part_nll, parts, a.V, dW, db, nll_sum);
 }

@@ -23,6 +23,9 @@ struct DecOutArgs {
 
 int dec_out_parts(int B, int L, int sm_count);
 void launch_dec_out(cudaStream_t s, const DecOutArgs& a, int sm_count);
+// tcgen05 variant (dec_out_tc.cu): one persistent CTA per SM; *parts_out = number of per-CTA partials written
+int launch_dec_out_tc(cudaStream_t s, const DecOutArgs& a, int sm_count, int* parts_out);
+extern int g_opt_dec_out_tc;      // 0 = never, 1 = auto (rows >= 8192), 2 = always
 void launch_dec_out_reduce(cudaStream_t s, const DecOutArgs& a, int sm_count, float* dW, float* db, float* nll_sum);
 
 }  // namespace cpg

@@ -1,0 +1,407 @@
+// Decoder output layer on the 5th-gen tensor cores: out-dropout -> Linear(102 -> V) -> softmax cross-entropy,
+// forward and backward fused over 128-row tiles of the [B*L, 104] hidden-state matrix (same contract as
+// dec_out.cu, which stays the path for small batches; models/decoder.py:43-45,83 and losses.py:27-30).
+//
+// Per tile three contractions run as tcgen05.mma (kind::f16, bf16 operand terms, fp32 accumulation in TMEM).
+// The logits are compared element-wise at 1e-4 relative, also where they pass through zero, so that product
+// uses three bf16 terms per operand (x = x1 + x2 + x3, the six products of weight >= 2^-16: fp32-level);
+// dh and dW use two terms (three products, 2^-16):
+//     logits[128 x 32]   = hd[128 x 104]  . W^T              (M = rows,  N = classes, K = hidden)
+//     dh[128 x 104]      = dl[128 x 32]   . W                (M = rows,  N = hidden,  K = classes)
+//     dW^T[104 x 32]    += hd^T[104 x 128] . dl[128 x 32]    (M = hidden, N = classes, K = rows; accumulates in
+//                                                             TMEM over all tiles of the persistent CTA)
+// All operand tiles are K-major no-swizzle core-matrix tiles in shared memory; hd and dl are therefore
+// staged twice (row-major-K and transposed).  Softmax / CE run with thread = row straight out of TMEM
+// (all 32 class logits of a row in one thread's registers: no shuffles).
+// One persistent CTA per SM, 256 threads: all 8 warps stage, warps 0-3 own the TMEM epilogues, an
+// elected lane of warp 4 issues the MMAs.  Per-CTA partials (dW, db, nll) feed the ordered reduction of dec_out.cu.
+#include "ctx.h"
+#ifndef CPG_EMU
+#include <cuda_bf16.h>
+#include "tc_common.cuh"
+
+namespace cpg {
+
+namespace {
+constexpr int TR = 128;                    // rows per tile
+constexpr int KH = 112;                    // hidden padded to a multiple of 16
+constexpr int NF4 = DEC_HP / 4;            // 26 float4 per hidden row
+constexpr int NTH = 256;
+// K-major no-swizzle tiles: offset(row, k) = (k >> 3) * LBO + (row >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2
+constexpr int LBO_R = (TR / 8) * 128 + 16;         // 128-row tiles (padded: conflict-free stores)
+constexpr int LBO_V = (VMAX / 8) * 128;            // 32-row weight tile (written once)
+constexpr int LBO_VT = (VMAX / 8) * 128 + 16;      // 32-row dl^T tile
+constexpr int LBO_H = (KH / 8) * 128;              // 112-row W^T tile (written once)
+constexpr int HD_SPLIT = (KH / 8) * LBO_R;         // hd   : 128 rows x K = 112
+constexpr int WK_SPLIT = (KH / 8) * LBO_V;         // W    : 32 classes x K = 112
+constexpr int DL_SPLIT = (VMAX / 8) * LBO_R;       // dl   : 128 rows x K = 32
+constexpr int WT_SPLIT = (VMAX / 8) * LBO_H;       // W^T  : 112 hidden x K = 32
+constexpr int HDT_SPLIT = (TR / 8) * LBO_R;        // hd^T : 128 hidden (104 used) x K = 128 rows
+constexpr int DLT_SPLIT = (TR / 8) * LBO_VT;       // dl^T : 32 classes x K = 128 rows
+constexpr int OFF_HD = 0;
+constexpr int OFF_WK = OFF_HD + 3 * HD_SPLIT;
+constexpr int OFF_DL = OFF_WK + 3 * WK_SPLIT;
+constexpr int OFF_WT = OFF_DL + 2 * DL_SPLIT;
+constexpr int OFF_HDT = OFF_WT + 2 * WT_SPLIT;
+constexpr int OFF_DLT = OFF_HDT + 2 * HDT_SPLIT;
+constexpr int OFF_KEEP = OFF_DLT + 2 * DLT_SPLIT;  // [128][26] keep nibbles (one byte per 4 hidden units)
+constexpr int SMEM_TOTAL = OFF_KEEP + TR * NF4 + 128;
+// tensor-memory columns
+constexpr int TC_LG = 0, TC_DH = 32, TC_DW = 160;
+constexpr uint32_t TMEM_COLS = 256;
+
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float f0 = __uint_as_float(hi << 16), f1 = __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - f0, x1 - f1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// (x0, x1) -> three packed bf16 terms
+__device__ __forceinline__ void split2x3(float x0, float x1, uint32_t& t1, uint32_t& t2, uint32_t& t3) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(x0, x1);
+    t1 = *reinterpret_cast<const uint32_t*>(&a);
+    const float r0 = x0 - __uint_as_float(t1 << 16), r1 = x1 - __uint_as_float(t1 & 0xffff0000u);
+    const __nv_bfloat162 b = __floats2bfloat162_rn(r0, r1);
+    t2 = *reinterpret_cast<const uint32_t*>(&b);
+    const __nv_bfloat162 c = __floats2bfloat162_rn(r0 - __uint_as_float(t2 << 16), r1 - __uint_as_float(t2 & 0xffff0000u));
+    t3 = *reinterpret_cast<const uint32_t*>(&c);
+}
+// contraction over `ksteps` K slices of 16 as a sum of `np` (A term, B term) products; the terms of a tile
+// lie `a_split` / `b_split` bytes apart
+__device__ __forceinline__ void mma_terms(uint32_t tmem_d, uint32_t a0, int a_split, int a_lbo, uint32_t b0, int b_split, int b_lbo,
+                                          int ksteps, uint32_t idesc, uint32_t acc, const int* xa, const int* xb, int np) {
+    for (int p = 0; p < np; ++p)
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t da = tc::make_smem_desc(a0 + xa[p] * a_split + ks * 2 * a_lbo, a_lbo, 128, 0);
+            const uint64_t db = tc::make_smem_desc(b0 + xb[p] * b_split + ks * 2 * b_lbo, b_lbo, 128, 0);
+            umma_bf16_ss(tmem_d, da, db, idesc, acc);
+            acc = 1;
+        }
+}
+// three-product split-bf16 contraction over `ksteps` K slices of 16: A and B tiles with their two terms
+// `a_split` / `b_split` bytes apart
+__device__ __forceinline__ void mma_split3(uint32_t tmem_d, uint32_t a0, int a_split, int a_lbo, uint32_t b0, int b_split, int b_lbo,
+                                           int ksteps, uint32_t idesc, uint32_t acc) {
+    const int xs[3] = {0, 0, 1}, ws[3] = {0, 1, 0};
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t da = tc::make_smem_desc(a0 + xs[p] * a_split + ks * 2 * a_lbo, a_lbo, 128, 0);
+            const uint64_t db = tc::make_smem_desc(b0 + ws[p] * b_split + ks * 2 * b_lbo, b_lbo, 128, 0);
+            umma_bf16_ss(tmem_d, da, db, idesc, acc);
+            acc = 1;
+        }
+}
+}  // namespace
+
+__global__ void __launch_bounds__(NTH, 1)
+k_dec_out_tc(DecOutArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* HD = smem + OFF_HD;
+    unsigned char* WK = smem + OFF_WK;
+    unsigned char* DL = smem + OFF_DL;
+    unsigned char* WT = smem + OFF_WT;
+    unsigned char* HDT = smem + OFF_HDT;
+    unsigned char* DLT = smem + OFF_DLT;
+    unsigned char* keep_s = smem + OFF_KEEP;
+    __shared__ __align__(8) uint64_t bar_m;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float red_b[4][VMAX];
+    __shared__ float red_n[4];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int V = a.V;
+    const int nrows = a.B * a.L;
+    const bool want_grad = a.dh_out != nullptr;
+    const bool has_mask = a.out_keep != nullptr;
+    const float sc = has_mask ? a.keep_scale : 1.0f;
+    const float inv_ntok = (a.ntok != nullptr && *a.ntok > 0.f) ? 1.0f / *a.ntok : 0.f;
+
+    // ---- one-time setup: zero every operand tile (K / M padding stays zero), then the two weight tiles
+    for (int i = tid; i < OFF_KEEP / 16; i += NTH) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int idx = tid; idx < VMAX * DEC_HP; idx += NTH) {
+        const int v = idx / DEC_HP, j = idx % DEC_HP;
+        const float w = a.fc_w[idx];
+        const __nv_bfloat16 h = __float2bfloat16_rn(w);
+        const float wr = w - __bfloat162float(h);
+        const __nv_bfloat16 l = __float2bfloat16_rn(wr);
+        const __nv_bfloat16 l3 = __float2bfloat16_rn(wr - __bfloat162float(l));
+        // W as [class][k = hidden] and W^T as [hidden][k = class]
+        const int o1 = (j >> 3) * LBO_V + (v >> 3) * 128 + (v & 7) * 16 + (j & 7) * 2;
+        const int o2 = (v >> 3) * LBO_H + (j >> 3) * 128 + (j & 7) * 16 + (v & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(WK + o1) = h;
+        *reinterpret_cast<__nv_bfloat16*>(WK + WK_SPLIT + o1) = l;
+        *reinterpret_cast<__nv_bfloat16*>(WK + 2 * WK_SPLIT + o1) = l3;
+        *reinterpret_cast<__nv_bfloat16*>(WT + o2) = h;
+        *reinterpret_cast<__nv_bfloat16*>(WT + WT_SPLIT + o2) = l;
+    }
+    if (warp == 4) {
+        if (lane == 0) {
+            tc::mbar_init(&bar_m, 1);
+            tc::fence_barrier_init();
+        }
+        __syncwarp();
+        tc::tmem_alloc<TMEM_COLS>(&tmem_slot);
+    }
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t s_hd = tc::smem_u32(HD), s_wk = tc::smem_u32(WK), s_dl = tc::smem_u32(DL), s_wt = tc::smem_u32(WT);
+    const uint32_t s_hdt = tc::smem_u32(HDT), s_dlt = tc::smem_u32(DLT);
+
+    // epilogue threads (warps 0-3): thread = row of the tile = TMEM lane
+    const int rl = tid;                                        // valid for tid < 128
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float accb[VMAX];
+#pragma unroll
+    for (int v = 0; v < VMAX; ++v) accb[v] = 0.f;
+    float accn = 0.f;
+    uint32_t mphase = 0;
+    bool dw_started = false;
+
+    const int ntiles = ceil_div(nrows, TR);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row0 = tile * TR;
+        // ---- S1) hd = h * keep * scale -> HD (K-major, two bf16 terms) + keep bytes; coalesced over (row, quad)
+        for (int idx = tid; idx < TR * NF4; idx += NTH) {
+            const int r = idx / NF4, f = idx % NF4, row = row0 + r;
+            float hv[4] = {0.f, 0.f, 0.f, 0.f};
+            unsigned char k4[4] = {0, 0, 0, 0};
+            if (row < nrows) {
+                const float4 h = ld4(a.hs + (size_t)row * DEC_HP + f * 4);
+                const float hh[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int j = f * 4 + c;
+                    const unsigned char k = j < DEC_H ? (has_mask ? a.out_keep[(size_t)row * DEC_H + j] : 1) : 0;
+                    k4[c] = k;
+                    hv[c] = k ? hh[c] * sc : 0.f;
+                }
+            }
+            uint2 t1, t2, t3;
+            split2x3(hv[0], hv[1], t1.x, t2.x, t3.x);
+            split2x3(hv[2], hv[3], t1.y, t2.y, t3.y);
+            const int j0 = f * 4;
+            const int off = (j0 >> 3) * LBO_R + (r >> 3) * 128 + (r & 7) * 16 + (j0 & 7) * 2;
+            *reinterpret_cast<uint2*>(HD + off) = t1;
+            *reinterpret_cast<uint2*>(HD + HD_SPLIT + off) = t2;
+            *reinterpret_cast<uint2*>(HD + 2 * HD_SPLIT + off) = t3;
+            keep_s[r * NF4 + f] = (unsigned char)((k4[0] ? 1 : 0) | (k4[1] ? 2 : 0) | (k4[2] ? 4 : 0) | (k4[3] ? 8 : 0));
+        }
+        __syncthreads();
+        // ---- S2) transposed copy HD -> HDT (lanes along rows: conflict-free 2-byte stores)
+        if (want_grad) {
+            for (int idx = tid; idx < TR * (DEC_HP / 8); idx += NTH) {
+                const int r = idx % TR, kc = idx / TR;             // kc: 8 hidden units
+                const int src = kc * LBO_R + (r >> 3) * 128 + (r & 7) * 16;
+#pragma unroll
+                for (int sp = 0; sp < 2; ++sp) {                                   // the two leading terms
+                    const uint4 v = *reinterpret_cast<const uint4*>(HD + sp * HD_SPLIT + src);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int j = kc * 8 + e;
+                        const uint16_t bits = (uint16_t)(w[e >> 1] >> ((e & 1) * 16));
+                        *reinterpret_cast<uint16_t*>(HDT + sp * HDT_SPLIT + (r >> 3) * LBO_R + (j >> 3) * 128 + (j & 7) * 16 + (r & 7) * 2) = bits;
+                    }
+                }
+            }
+        }
+        tc::fence_proxy_async();
+        __syncthreads();
+        // ---- M1) logits
+        if (warp == 4) {
+            tc::tc_fence_after();
+            if (elect_one()) {
+                const int xa[6] = {0, 0, 1, 1, 2, 0}, xb[6] = {0, 1, 0, 1, 0, 2};
+                mma_terms(tmem + TC_LG, s_hd, HD_SPLIT, LBO_R, s_wk, WK_SPLIT, LBO_V, KH / 16, idesc_bf16(128, VMAX), 0, xa, xb, 6);
+                tc::umma_commit(&bar_m);
+            }
+            __syncwarp();
+        }
+        // ---- E1) softmax / CE, thread = row
+        if (warp < 4) {
+            tc::mbar_wait(&bar_m, mphase & 1);
+            tc::tc_fence_after();
+            float lg[VMAX];
+            tc::tmem_ld_32x32(lane_addr + TC_LG, lg);
+            const int row = row0 + rl;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int v = 0; v < VMAX; ++v) {
+                lg[v] = v < V ? lg[v] + a.fc_b[v] : -INFINITY;
+                mx = fmaxf(mx, lg[v]);
+            }
+            if (row < nrows && a.logits_out != nullptr) {
+#pragma unroll
+                for (int v = 0; v < VMAX; ++v)
+                    if (v < V) a.logits_out[(size_t)row * V + v] = lg[v];
+            }
+            float dl[VMAX];
+#pragma unroll
+            for (int v = 0; v < VMAX; ++v) dl[v] = 0.f;
+            if (a.fused_ce) {
+                const int tg = row < nrows ? a.tgt[row] : PAD;
+                if (tg != PAD) {
+                    float e[VMAX], se = 0.f, lt = 0.f;
+#pragma unroll
+                    for (int v = 0; v < VMAX; ++v) {
+                        e[v] = v < V ? expf(lg[v] - mx) : 0.f;
+                        se += e[v];
+                        if (v == tg) lt = lg[v];
+                    }
+                    accn += (mx + logf(se)) - lt;
+                    const float inv = 1.0f / se;
+#pragma unroll
+                    for (int v = 0; v < VMAX; ++v) dl[v] = v < V ? (e[v] * inv - (v == tg ? 1.f : 0.f)) * inv_ntok : 0.f;
+                }
+            } else if (a.dlogits_in != nullptr && row < nrows) {
+#pragma unroll
+                for (int v = 0; v < VMAX; ++v)
+                    if (v < V) dl[v] = a.dlogits_in[(size_t)row * V + v];
+            }
+            if (want_grad) {
+#pragma unroll
+                for (int v = 0; v < VMAX; ++v) accb[v] += dl[v];
+                // dl -> DL (K = class, K-major) and DLT (class x rows)
+#pragma unroll
+                for (int kc = 0; kc < VMAX / 8; ++kc) {
+                    uint4 hi, lo;
+                    split2(dl[kc * 8 + 0], dl[kc * 8 + 1], hi.x, lo.x);
+                    split2(dl[kc * 8 + 2], dl[kc * 8 + 3], hi.y, lo.y);
+                    split2(dl[kc * 8 + 4], dl[kc * 8 + 5], hi.z, lo.z);
+                    split2(dl[kc * 8 + 6], dl[kc * 8 + 7], hi.w, lo.w);
+                    const int off = kc * LBO_R + (rl >> 3) * 128 + (rl & 7) * 16;
+                    *reinterpret_cast<uint4*>(DL + off) = hi;
+                    *reinterpret_cast<uint4*>(DL + DL_SPLIT + off) = lo;
+                    const uint32_t wh[4] = {hi.x, hi.y, hi.z, hi.w}, wl[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int v = kc * 8 + e;
+                        const int o = (rl >> 3) * LBO_VT + (v >> 3) * 128 + (v & 7) * 16 + (rl & 7) * 2;
+                        *reinterpret_cast<uint16_t*>(DLT + o) = (uint16_t)(wh[e >> 1] >> ((e & 1) * 16));
+                        *reinterpret_cast<uint16_t*>(DLT + DLT_SPLIT + o) = (uint16_t)(wl[e >> 1] >> ((e & 1) * 16));
+                    }
+                }
+            }
+            tc::tc_fence_before();
+        }
+        ++mphase;
+        if (!want_grad) { __syncthreads(); continue; }
+        tc::fence_proxy_async();
+        __syncthreads();
+        // ---- M2) dh = dl W  and  dW^T += hd^T dl
+        if (warp == 4) {
+            tc::tc_fence_after();
+            if (elect_one()) {
+                mma_split3(tmem + TC_DH, s_dl, DL_SPLIT, LBO_R, s_wt, WT_SPLIT, LBO_H, VMAX / 16, idesc_bf16(128, KH), 0);
+                mma_split3(tmem + TC_DW, s_hdt, HDT_SPLIT, LBO_R, s_dlt, DLT_SPLIT, LBO_VT, TR / 16, idesc_bf16(128, VMAX),
+                           dw_started ? 1u : 0u);
+                tc::umma_commit(&bar_m);
+            }
+            __syncwarp();
+        }
+        dw_started = true;
+        // ---- E2) dh_out = dh * keep * scale, thread = row
+        if (warp < 4) {
+            tc::mbar_wait(&bar_m, mphase & 1);
+            tc::tc_fence_after();
+            const int row = row0 + rl;
+#pragma unroll 1
+            for (int c0 = 0; c0 < DEC_HP; c0 += 32) {
+                float v[32];
+                tc::tmem_ld_32x32(lane_addr + TC_DH + c0, v);     // columns 104..127 of the last chunk: K padding, unused
+                if (row < nrows) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int j = c0 + q * 4;
+                        if (j < DEC_HP) {
+                            const unsigned k = keep_s[rl * NF4 + (j >> 2)];
+                            st4(a.dh_out + (size_t)row * DEC_HP + j,
+                                make_float4((k & 1) ? v[q * 4] * sc : 0.f, (k & 2) ? v[q * 4 + 1] * sc : 0.f,
+                                            (k & 4) ? v[q * 4 + 2] * sc : 0.f, (k & 8) ? v[q * 4 + 3] * sc : 0.f));
+                        }
+                    }
+                }
+            }
+            tc::tc_fence_before();
+        }
+        ++mphase;
+        __syncthreads();                                       // both MMAs are done with HD / HDT / DL / DLT
+    }
+
+    // ---- per-CTA partials
+    tc::tc_fence_after();
+    if (want_grad) {
+        float* pw = a.part_w + (size_t)blockIdx.x * VMAX * DEC_HP;
+        if (warp < 4) {
+            float dw[VMAX];
+            if (dw_started) tc::tmem_ld_32x32(lane_addr + TC_DW, dw);      // lane = hidden unit j, columns = classes
+            const int j = tid;
+            if (j < DEC_HP) {
+#pragma unroll
+                for (int v = 0; v < VMAX; ++v) pw[v * DEC_HP + j] = dw_started ? dw[v] : 0.f;
+            }
+#pragma unroll
+            for (int v = 0; v < VMAX; ++v) {
+                const float s = warp_sum(accb[v]);
+                if (lane == 0) red_b[warp][v] = s;
+            }
+        }
+        __syncthreads();
+        if (tid < VMAX) a.part_b[(size_t)blockIdx.x * VMAX + tid] = (red_b[0][tid] + red_b[1][tid]) + (red_b[2][tid] + red_b[3][tid]);
+    }
+    if (a.part_nll != nullptr) {
+        if (warp < 4) {
+            const float s = warp_sum(accn);
+            if (lane == 0) red_n[warp] = s;
+        }
+        __syncthreads();
+        if (tid == 0) a.part_nll[blockIdx.x] = (red_n[0] + red_n[1]) + (red_n[2] + red_n[3]);
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+int launch_dec_out_tc(cudaStream_t s, const DecOutArgs& a, int sm_count, int* parts_out) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute((const void*)k_dec_out_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess) {
+            cudaGetLastError();
+            return CPG_ECUDA;
+        }
+        attr_set = true;
+    }
+    const int ntiles = ceil_div(a.B * a.L, TR);
+    const int grid = max(1, min(ntiles, sm_count));
+    CPG_LAUNCH_NAMED("k_dec_out_tc", k_dec_out_tc, grid, NTH, SMEM_TOTAL, s, a);
+    *parts_out = grid;
+    return CPG_OK;
+}
+
+}  // namespace cpg
+#endif  // CPG_EMU

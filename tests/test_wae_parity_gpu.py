@@ -53,9 +53,11 @@ def test_forward_tensor_core_recurrences_match_oracle(eng, batch):
     from cpg_b200 import _lib
     try:
         _lib.set_option('gru_tensor_core', 2)
+        _lib.set_option('dec_out_tensor_core', 2)
         test_forward_matches_oracle(eng, batch)
     finally:
         _lib.set_option('gru_tensor_core', 1)
+        _lib.set_option('dec_out_tensor_core', 1)
 
 
 def test_inference_forward_matches_reference_golden(eng):
@@ -144,9 +146,11 @@ def test_train_step_tensor_core_recurrences_match_oracle(eng, batch, z_regu):
     from cpg_b200 import _lib
     try:
         _lib.set_option('gru_tensor_core', 2)
+        _lib.set_option('dec_out_tensor_core', 2)
         test_train_step_matches_oracle(eng, batch, z_regu, max_outliers=3)
     finally:
         _lib.set_option('gru_tensor_core', 1)
+        _lib.set_option('dec_out_tensor_core', 1)
 
 
 def test_full_batch_4096_matches_reference_golden(eng):
