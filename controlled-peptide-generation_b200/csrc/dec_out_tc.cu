@@ -186,30 +186,53 @@ k_dec_out_tc(DecOutArgs a) {
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int row0 = tile * TR;
         // ---- S1) hd = h * keep * scale -> HD (K-major, two bf16 terms) + keep bytes; coalesced over (row, quad)
-        for (int idx = tid; idx < TR * NF4; idx += NTH) {
-            const int r = idx / NF4, f = idx % NF4, row = row0 + r;
-            float hv[4] = {0.f, 0.f, 0.f, 0.f};
-            unsigned char k4[4] = {0, 0, 0, 0};
-            if (row < nrows) {
-                const float4 h = ld4(a.hs + (size_t)row * DEC_HP + f * 4);
-                const float hh[4] = {h.x, h.y, h.z, h.w};
+        {
+            constexpr int NIT = TR * NF4 / NTH;                  // 13 (row, quad) items per thread, exactly
+            static_assert(TR * NF4 % NTH == 0, "staging items");
+            float4 hq[NIT];
+            unsigned short k0[NIT], k1[NIT];                     // raw keep bytes (units 4f, 4f+1 | 4f+2, 4f+3)
+            // all global loads of the tile first: unconditional (clamped) addresses and no use of the loaded values
+            // in this loop, so that the 39 loads of a thread are in flight together ...
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int j = f * 4 + c;
-                    const unsigned char k = j < DEC_H ? (has_mask ? a.out_keep[(size_t)row * DEC_H + j] : 1) : 0;
-                    k4[c] = k;
-                    hv[c] = k ? hh[c] * sc : 0.f;
+            for (int it = 0; it < NIT; ++it) {
+                const int idx = tid + it * NTH;
+                const int r = idx / NF4, f = idx % NF4;
+                const int row = min(row0 + r, nrows - 1);
+                hq[it] = ld4(a.hs + (size_t)row * DEC_HP + f * 4);
+                k0[it] = 0x0101; k1[it] = 0x0101;
+                if (has_mask) {
+                    // row * 102 + 4 f is even: two aligned 2-byte loads (the last quad's second pair is clamped, masked below)
+                    const unsigned short* kp = reinterpret_cast<const unsigned short*>(a.out_keep + (size_t)row * DEC_H + f * 4);
+                    k0[it] = kp[0];
+                    k1[it] = kp[f * 4 + 2 < DEC_H ? 1 : 0];
                 }
             }
-            uint2 t1, t2, t3;
-            split2x3(hv[0], hv[1], t1.x, t2.x, t3.x);
-            split2x3(hv[2], hv[3], t1.y, t2.y, t3.y);
-            const int j0 = f * 4;
-            const int off = (j0 >> 3) * LBO_R + (r >> 3) * 128 + (r & 7) * 16 + (j0 & 7) * 2;
-            *reinterpret_cast<uint2*>(HD + off) = t1;
-            *reinterpret_cast<uint2*>(HD + HD_SPLIT + off) = t2;
-            *reinterpret_cast<uint2*>(HD + 2 * HD_SPLIT + off) = t3;
-            keep_s[r * NF4 + f] = (unsigned char)((k4[0] ? 1 : 0) | (k4[1] ? 2 : 0) | (k4[2] ? 4 : 0) | (k4[3] ? 8 : 0));
+            // ... then mask, split and store
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int idx = tid + it * NTH;
+                const int r = idx / NF4, f = idx % NF4;
+                const float hh[4] = {hq[it].x, hq[it].y, hq[it].z, hq[it].w};
+                const bool in_rows = row0 + r < nrows;
+                const uint32_t kq = (uint32_t)k0[it] | ((f * 4 + 2 < DEC_H) ? (uint32_t)k1[it] << 16 : 0u);
+                float hv[4];
+                unsigned kb = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const bool k = in_rows && ((kq >> (8 * c)) & 0xff) != 0;
+                    hv[c] = k ? hh[c] * sc : 0.f;
+                    kb |= k ? (1u << c) : 0u;
+                }
+                uint2 t1, t2, t3;
+                split2x3(hv[0], hv[1], t1.x, t2.x, t3.x);
+                split2x3(hv[2], hv[3], t1.y, t2.y, t3.y);
+                const int j0 = f * 4;
+                const int off = (j0 >> 3) * LBO_R + (r >> 3) * 128 + (r & 7) * 16 + (j0 & 7) * 2;
+                *reinterpret_cast<uint2*>(HD + off) = t1;
+                *reinterpret_cast<uint2*>(HD + HD_SPLIT + off) = t2;
+                *reinterpret_cast<uint2*>(HD + 2 * HD_SPLIT + off) = t3;
+                keep_s[r * NF4 + f] = (unsigned char)kb;
+            }
         }
         __syncthreads();
         // ---- S2) transposed copy HD -> HDT (lanes along rows: conflict-free 2-byte stores)
@@ -325,21 +348,23 @@ k_dec_out_tc(DecOutArgs a) {
             __syncwarp();
         }
         dw_started = true;
-        // ---- E2) dh_out = dh * keep * scale, thread = row
-        if (warp < 4) {
+        // ---- E2) dh_out = dh * keep * scale, thread = row; warps w and w + 4 share a lane quadrant and split the columns
+        {
             tc::mbar_wait(&bar_m, mphase & 1);
             tc::tc_fence_after();
-            const int row = row0 + rl;
+            const int r2 = (warp & 3) * 32 + lane;
+            const int row = row0 + r2;
+            const int cbeg = warp < 4 ? 0 : 64, cend = warp < 4 ? 64 : DEC_HP;
 #pragma unroll 1
-            for (int c0 = 0; c0 < DEC_HP; c0 += 32) {
+            for (int c0 = cbeg; c0 < cend; c0 += 32) {
                 float v[32];
-                tc::tmem_ld_32x32(lane_addr + TC_DH + c0, v);     // columns 104..127 of the last chunk: K padding, unused
+                tc::tmem_ld_32x32(lane_addr + TC_DH + c0, v);     // columns >= 104 of the last chunk: padding, unused
                 if (row < nrows) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int j = c0 + q * 4;
                         if (j < DEC_HP) {
-                            const unsigned k = keep_s[rl * NF4 + (j >> 2)];
+                            const unsigned k = keep_s[r2 * NF4 + (j >> 2)];
                             st4(a.dh_out + (size_t)row * DEC_HP + j,
                                 make_float4((k & 1) ? v[q * 4] * sc : 0.f, (k & 2) ? v[q * 4 + 1] * sc : 0.f,
                                             (k & 4) ? v[q * 4 + 2] * sc : 0.f, (k & 8) ? v[q * 4 + 3] * sc : 0.f));
