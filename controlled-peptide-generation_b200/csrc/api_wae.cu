@@ -162,13 +162,51 @@ static int check_dims(int V, int B, int L) {
     return CPG_OK;
 }
 
+// -------------------------------------------------------------------------------- side stream
+// g_opt_side_stream: 1 = overlap the loss kernels with the decoder path (default), 0 = everything on one stream
+int g_opt_side_stream = 1;
+#ifndef CPG_EMU
+static bool side_ready(cpg_ctx* ctx) {
+    if (!g_opt_side_stream) return false;
+    if (ctx->side_stream == nullptr) {
+        cudaStream_t q;
+        cudaEvent_t e0, e1;
+        if (cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e0, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        ctx->side_stream = q; ctx->ev_fork = e0; ctx->ev_join = e1;
+    }
+    return true;
+}
+// everything enqueued on `s` so far happens-before what is then enqueued on the returned stream
+static void side_mark(cpg_ctx* ctx, cudaStream_t s) { cudaEventRecord((cudaEvent_t)ctx->ev_fork, s); }
+static cudaStream_t side_enter(cpg_ctx* ctx) {
+    cudaStreamWaitEvent((cudaStream_t)ctx->side_stream, (cudaEvent_t)ctx->ev_fork, 0);
+    return (cudaStream_t)ctx->side_stream;
+}
+static void side_leave(cpg_ctx* ctx) { cudaEventRecord((cudaEvent_t)ctx->ev_join, (cudaStream_t)ctx->side_stream); ctx->join_pending = true; }
+static void side_join(cpg_ctx* ctx, cudaStream_t s) {
+    if (ctx->join_pending) { cudaStreamWaitEvent(s, (cudaEvent_t)ctx->ev_join, 0); ctx->join_pending = false; }
+}
+#else
+static bool side_ready(cpg_ctx*) { return false; }
+static void side_mark(cpg_ctx*, cudaStream_t) {}
+static cudaStream_t side_enter(cpg_ctx*) { return nullptr; }
+static void side_leave(cpg_ctx*) {}
+static void side_join(cpg_ctx*, cudaStream_t) {}
+#endif
+
 // ------------------------------------------------------------------------------------ forward
 // Tensor-core recurrences pay off once a 128-row tile per CTA fills a good part of the chip;
 // tiny batches stay on the 32-row fp32 SIMT kernels.  g_opt_gru_tc: 0 = never, 1 = auto, 2 = always.
 int g_opt_gru_tc = 1;
 static bool use_gru_tc(int B) { return g_opt_gru_tc == 2 || (g_opt_gru_tc == 1 && B >= 1024); }
 static void forward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, const ParamLayout& lay, int V, int B, int L,
-                         const cpg_wae_inputs* in, float* mu, float* logvar, float* z, bool stash, bool encoder_only) {
+                         const cpg_wae_inputs* in, float* mu, float* logvar, float* z, bool stash, bool encoder_only,
+                         bool mark_after_reparam = false) {
     Workspace& w = ctx->ws;
     launch_prep_tokens(s, in->tokens, in->word_drop, B, L, V, w.tok, w.tokd, w.tgt, ctx->ints, ctx->ints + 1);
     launch_prep_weights(s, params, lay, V, w.d);
@@ -196,6 +234,7 @@ static void forward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, cons
                  logvar, ZD, params + lay.off[P_QLV_B], 1, nullptr);
     if (encoder_only) return;
     launch_reparam(s, mu, logvar, in->eps, in->c, B, z, w.zc);
+    if (mark_after_reparam) side_mark(ctx, s);      // mu, logvar, z are final: the loss statistics may start
     // per-row input projection of [z;c] (the non-embedding columns of decoder W_ih)
     launch_sgemm(s, B, 3 * DEC_HP, DEC_HP, 1.f, w.zc, DEC_HP, 1, w.d.wizc_t, 3 * DEC_HP, 1, 0.f, w.rowbias,
                  3 * DEC_HP, nullptr, 1, nullptr);
@@ -248,6 +287,7 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     LatentBwdArgs la = lat_in;
     la.mu = w.mu; la.logvar = w.logvar; la.eps = in->eps; la.dzc = w.dh0; la.B = B;
     la.dmu = w.dmu; la.dlv = w.dlv;
+    side_join(ctx, s);                              // dz_rf / loss scalars produced on the side stream
     launch_latent_bwd(s, la);
     // heads
     const float* wmu = params + lay.off[P_QMU_W];
@@ -363,6 +403,14 @@ int cpg_destroy(cpg_ctx* c) {
     if (c == nullptr) return CPG_OK;
     if (c->base) dev_free(c->base);
     if (c->ints) dev_free(c->ints);
+#ifndef CPG_EMU
+    if (c->side_stream) {
+        cudaStreamSynchronize((cudaStream_t)c->side_stream);
+        cudaStreamDestroy((cudaStream_t)c->side_stream);
+        cudaEventDestroy((cudaEvent_t)c->ev_fork);
+        cudaEventDestroy((cudaEvent_t)c->ev_join);
+    }
+#endif
     delete c;
     return CPG_OK;
 }
@@ -467,14 +515,20 @@ int cpg_wae_step_phase1(cpg_ctx* ctx, cpg_stream stream, const float* params, in
     if ((rc = ensure_workspace(ctx, B, L, V, R, s))) return rc;
     Workspace& w = ctx->ws;
     ParamLayout lay = make_layout(V);
-    forward_impl(ctx, s, params, lay, V, B, L, in, w.mu, w.logvar, w.z, true, false);
-    // local statistics that couple the batch: token count, latent sums, RF feature sums
-    launch_int_to_float(s, ctx->ints, coupled + 0, 1);
-    launch_latent_stats(s, w.mu, w.logvar, B, w.lat_part, w.lat_nparts, coupled + 2);
-    launch_sgemm(s, B, R, ZD, 1.f, w.z, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre1, R, nullptr, 1, nullptr);
-    launch_sgemm(s, B, R, ZD, 1.f, nz->z_prior_rf, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre2, R, nullptr, 1, nullptr);
-    launch_rf_colsum(s, w.rf_pre1, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8);
-    launch_rf_colsum(s, w.rf_pre2, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8 + R);
+    const bool side = side_ready(ctx);
+    forward_impl(ctx, s, params, lay, V, B, L, in, w.mu, w.logvar, w.z, true, false, side);
+    // local statistics that couple the batch: token count, latent sums, RF feature sums -- they depend on
+    // (mu, logvar, z) only and run on the side stream under the decoder recurrence
+    {
+        cudaStream_t q = side ? side_enter(ctx) : s;
+        launch_int_to_float(q, ctx->ints, coupled + 0, 1);
+        launch_latent_stats(q, w.mu, w.logvar, B, w.lat_part, w.lat_nparts, coupled + 2);
+        launch_sgemm(q, B, R, ZD, 1.f, w.z, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre1, R, nullptr, 1, nullptr);
+        launch_sgemm(q, B, R, ZD, 1.f, nz->z_prior_rf, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre2, R, nullptr, 1, nullptr);
+        launch_rf_colsum(q, w.rf_pre1, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8);
+        launch_rf_colsum(q, w.rf_pre2, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8 + R);
+        if (side) { side_leave(ctx); side_join(ctx, s); }
+    }
     if (mu) dev_copy(mu, w.mu, (size_t)B * ZD * 4, s);
     if (logvar) dev_copy(logvar, w.logvar, (size_t)B * ZD * 4, s);
     if (z) dev_copy(z, w.z, (size_t)B * ZD * 4, s);
@@ -499,6 +553,24 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
     const int Bg = hp->global_batch > 0 ? hp->global_batch : B;
     ParamLayout lay = make_layout(V);
     dev_memset(grads, 0, (size_t)lay.total * 4, s);
+    // RF-MMD from the global feature sums and the (logged) full-kernel MMD: side stream, joined in
+    // backward_impl right before the latent backward that consumes dz_rf
+    const bool side = side_ready(ctx);
+    if (side) side_mark(ctx, s);
+    const float w_rf = hp->z_regu == CPG_ZREGU_MMDRF ? hp->beta : 0.f;
+    const float* dz_rf = nullptr;
+    {
+        cudaStream_t q = side ? side_enter(ctx) : s;
+        launch_rf_loss(q, coupled + 8, coupled + 8 + R, R, Bg, hp->mmd_sigma, w_rf, w.rf_coef, w.mmdrf_out);
+        if (w_rf != 0.f) {
+            launch_rf_grad_prep(q, w.rf_pre1, nz->rf_b, w.rf_coef, B, R, hp->mmd_sigma);
+            launch_sgemm(q, B, ZD, R, 1.f, w.rf_pre1, R, 1, nz->rf_w, 1, R, 0.f, w.dz_rf, ZD, nullptr, 1, nullptr);
+            dz_rf = w.dz_rf;
+        }
+        if (hp->compute_full_mmd && nz->z_prior_full)
+            if ((rc = launch_mmd_full(q, w.z, nz->z_prior_full, B, hp->mmd_sigma, w.mmd_ws, w.mmd_out))) return rc;
+        if (side) side_leave(ctx);
+    }
     // reconstruction loss fwd+bwd with the global token count (coupled[0])
     DecOutArgs a = dec_out_args(ctx, in, V, B, L);
     a.ntok = coupled + 0;
@@ -507,17 +579,6 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
     a.dh_out = w.dec_dh_out;
     launch_dec_out(s, a, ctx->sm_count);
     launch_dec_out_reduce(s, a, ctx->sm_count, grads + lay.off[P_FC_W], grads + lay.off[P_FC_B], w.nll_sum);
-    // RF-MMD from the global feature sums
-    const float w_rf = hp->z_regu == CPG_ZREGU_MMDRF ? hp->beta : 0.f;
-    launch_rf_loss(s, coupled + 8, coupled + 8 + R, R, Bg, hp->mmd_sigma, w_rf, w.rf_coef, w.mmdrf_out);
-    const float* dz_rf = nullptr;
-    if (w_rf != 0.f) {
-        launch_rf_grad_prep(s, w.rf_pre1, nz->rf_b, w.rf_coef, B, R, hp->mmd_sigma);
-        launch_sgemm(s, B, ZD, R, 1.f, w.rf_pre1, R, 1, nz->rf_w, 1, R, 0.f, w.dz_rf, ZD, nullptr, 1, nullptr);
-        dz_rf = w.dz_rf;
-    }
-    if (hp->compute_full_mmd && nz->z_prior_full)
-        if ((rc = launch_mmd_full(s, w.z, nz->z_prior_full, B, hp->mmd_sigma, w.mmd_ws, w.mmd_out))) return rc;
     LatentBwdArgs la;
     memset(&la, 0, sizeof(la));
     la.dz_rf = dz_rf;

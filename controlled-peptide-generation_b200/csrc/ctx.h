@@ -40,6 +40,12 @@ struct cpg_ctx {
     cpg::Workspace ws;
     bool have_stash = false;
     int64_t launches = 0;
+    // side stream for the latency-bound loss kernels that only depend on (mu, logvar, z): they run under the
+    // decoder recurrence / decoder-output kernels of the main stream (fork / join with events; api_wae.cu)
+    void* side_stream = nullptr;
+    void* ev_fork = nullptr;
+    void* ev_join = nullptr;
+    bool join_pending = false;
 };
 
 namespace cpg {

@@ -74,6 +74,7 @@ int launch_gru_fwd_dec_tc(cudaStream_t s, const GruSeq& seq, int B, int L, int V
 int launch_gru_bwd_enc_tc(cudaStream_t s, const GruSeq* two_dirs, int B, int L);
 int launch_gru_bwd_dec_tc(cudaStream_t s, const GruSeq& seq, int B, int L);
 extern int g_opt_gru_tc;
+extern int g_opt_side_stream;
 
 // C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C ; generic strides (elements):
 // A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn], C(m,n) = C[m*ldc + n]; optional bias[n].
