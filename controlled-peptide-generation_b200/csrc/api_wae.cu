@@ -118,6 +118,8 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
     w.wg_part = a.take<float>((size_t)ws_ * 3 * DEC_HP * DEC_HP);
     int ds_ = dtable_splits(B, L, sm);
     w.dt_part = a.take<float>((size_t)ds_ * V * 4 * DEC_HP);
+    w.wg_part_dec = a.take<float>((size_t)ws_ * 3 * DEC_HP * DEC_HP);     // own partials: runs concurrently with the encoder's
+    w.dt_part_dec = a.take<float>((size_t)ds_ * V * 4 * DEC_HP);
     for (int d = 0; d < 2; ++d) w.dT_enc[d] = a.take<float>((size_t)V * 4 * ENC_H);
     w.dT_dec = a.take<float>((size_t)V * 4 * DEC_HP);
     w.dwizc = a.take<float>((size_t)3 * DEC_HP * DEC_HP);
@@ -170,33 +172,34 @@ static bool side_ready(cpg_ctx* ctx) {
     if (!g_opt_side_stream) return false;
     if (ctx->side_stream == nullptr) {
         cudaStream_t q;
-        cudaEvent_t e0, e1;
-        if (cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&e0, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess) {
-            cudaGetLastError();
-            return false;
-        }
-        ctx->side_stream = q; ctx->ev_fork = e0; ctx->ev_join = e1;
+        cudaEvent_t e[4];
+        bool ok = cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); return false; }
+        ctx->side_stream = q;
+        ctx->ev_fork[0] = e[0]; ctx->ev_join[0] = e[1]; ctx->ev_fork[1] = e[2]; ctx->ev_join[1] = e[3];
     }
     return true;
 }
 // everything enqueued on `s` so far happens-before what is then enqueued on the returned stream
-static void side_mark(cpg_ctx* ctx, cudaStream_t s) { cudaEventRecord((cudaEvent_t)ctx->ev_fork, s); }
-static cudaStream_t side_enter(cpg_ctx* ctx) {
-    cudaStreamWaitEvent((cudaStream_t)ctx->side_stream, (cudaEvent_t)ctx->ev_fork, 0);
+static void side_mark(cpg_ctx* ctx, cudaStream_t s, int k = 0) { cudaEventRecord((cudaEvent_t)ctx->ev_fork[k], s); }
+static cudaStream_t side_enter(cpg_ctx* ctx, int k = 0) {
+    cudaStreamWaitEvent((cudaStream_t)ctx->side_stream, (cudaEvent_t)ctx->ev_fork[k], 0);
     return (cudaStream_t)ctx->side_stream;
 }
-static void side_leave(cpg_ctx* ctx) { cudaEventRecord((cudaEvent_t)ctx->ev_join, (cudaStream_t)ctx->side_stream); ctx->join_pending = true; }
-static void side_join(cpg_ctx* ctx, cudaStream_t s) {
-    if (ctx->join_pending) { cudaStreamWaitEvent(s, (cudaEvent_t)ctx->ev_join, 0); ctx->join_pending = false; }
+static void side_leave(cpg_ctx* ctx, int k = 0) {
+    cudaEventRecord((cudaEvent_t)ctx->ev_join[k], (cudaStream_t)ctx->side_stream);
+    ctx->join_pending[k] = true;
+}
+static void side_join(cpg_ctx* ctx, cudaStream_t s, int k = 0) {
+    if (ctx->join_pending[k]) { cudaStreamWaitEvent(s, (cudaEvent_t)ctx->ev_join[k], 0); ctx->join_pending[k] = false; }
 }
 #else
 static bool side_ready(cpg_ctx*) { return false; }
-static void side_mark(cpg_ctx*, cudaStream_t) {}
-static cudaStream_t side_enter(cpg_ctx*) { return nullptr; }
-static void side_leave(cpg_ctx*) {}
-static void side_join(cpg_ctx*, cudaStream_t) {}
+static void side_mark(cpg_ctx*, cudaStream_t, int = 0) {}
+static cudaStream_t side_enter(cpg_ctx*, int = 0) { return nullptr; }
+static void side_leave(cpg_ctx*, int = 0) {}
+static void side_join(cpg_ctx*, cudaStream_t, int = 0) {}
 #endif
 
 // ------------------------------------------------------------------------------------ forward
@@ -277,6 +280,17 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     q.dh_out = w.dec_dh_out; q.dg = w.dec_dg; q.dh0 = w.dh0; q.drow = w.drow;
     if (use_gru_tc(B)) launch_gru_bwd_dec_tc(s, q, B, L);
     else launch_gru_bwd_dec(s, q, B, L);
+    // decoder W_hh / token-table gradients only need the decoder's dg: side stream, under the dense layers and
+    // the encoder BPTT of the main stream (joined before the input-side gradients)
+    const bool side = side_ready(ctx);
+    {
+        cudaStream_t qs = s;
+        if (side) { side_mark(ctx, s, 1); qs = side_enter(ctx, 1); }
+        const bool t2 = launch_wgrad_hh(qs, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, w.tokd, 0, V, B, L, sm, w.wg_part_dec,
+                                        w.dt_part_dec, grads + lay.off[P_DEC_WHH], w.dT_dec);
+        if (!t2) launch_dtable(qs, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part_dec, w.dT_dec);
+        if (side) side_leave(ctx, 1);
+    }
     // gradient at [z;c]:  dh0 + drow @ W_ih[:,150:]   (in place on dh0)
     launch_sgemm(s, B, DEC_HP, 3 * DEC_HP, 1.f, w.drow, 3 * DEC_HP, 1, w.d.wizc, DEC_HP, 1, 1.f, w.dh0, DEC_HP,
                  nullptr, 1, nullptr);
@@ -320,9 +334,7 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     const bool t1 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[1], w.enc_hs[1], nullptr, w.tok, 1, V, B, L, sm, w.wg_part,
                                     w.dt_part, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1]);
     if (!t1) launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part, w.dT_enc[1]);
-    const bool t2 = launch_wgrad_hh(s, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, w.tokd, 0, V, B, L, sm, w.wg_part,
-                                    w.dt_part, grads + lay.off[P_DEC_WHH], w.dT_dec);
-    if (!t2) launch_dtable(s, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part, w.dT_dec);
+    side_join(ctx, s, 1);                           // decoder weight / table gradients from the side stream
     InputGradArgs ia;
     memset(&ia, 0, sizeof(ia));
     ia.emb = params + lay.off[P_EMB];
@@ -407,8 +419,10 @@ int cpg_destroy(cpg_ctx* c) {
     if (c->side_stream) {
         cudaStreamSynchronize((cudaStream_t)c->side_stream);
         cudaStreamDestroy((cudaStream_t)c->side_stream);
-        cudaEventDestroy((cudaEvent_t)c->ev_fork);
-        cudaEventDestroy((cudaEvent_t)c->ev_join);
+        for (int k = 0; k < 2; ++k) {
+            cudaEventDestroy((cudaEvent_t)c->ev_fork[k]);
+            cudaEventDestroy((cudaEvent_t)c->ev_join[k]);
+        }
     }
 #endif
     delete c;

@@ -23,7 +23,7 @@ struct Workspace {
     float *lat_part, *lat_sums;
     float *mmd_ws, *mmd_out, *mmdrf_out;
     float *do_part_w, *do_part_b, *do_part_nll, *nll_sum;
-    float *wg_part, *dt_part, *dT_enc[2], *dT_dec, *dwizc;
+    float *wg_part, *dt_part, *wg_part_dec, *dt_part_dec, *dT_enc[2], *dT_dec, *dwizc;
     float *gemm_ws, *colsum_ws;
     float *norm_part, *clip_coef, *scalars, *ntok_f, *coupled;
     int lat_nparts, rf_nchunk, gemm_splits;
@@ -43,9 +43,9 @@ struct cpg_ctx {
     // side stream for the latency-bound loss kernels that only depend on (mu, logvar, z): they run under the
     // decoder recurrence / decoder-output kernels of the main stream (fork / join with events; api_wae.cu)
     void* side_stream = nullptr;
-    void* ev_fork = nullptr;
-    void* ev_join = nullptr;
-    bool join_pending = false;
+    void* ev_fork[2] = {nullptr, nullptr};          // [0] loss kernels, [1] decoder weight gradients
+    void* ev_join[2] = {nullptr, nullptr};
+    bool join_pending[2] = {false, false};
 };
 
 namespace cpg {
