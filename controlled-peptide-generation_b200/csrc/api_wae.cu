@@ -286,6 +286,9 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     {
         cudaStream_t qs = s;
         if (side) { side_mark(ctx, s, 1); qs = side_enter(ctx, 1); }
+        // dW_ih[:,150:] = drow^T @ [z;c]  (a weight gradient: nothing on the BPTT chain waits for it)
+        launch_sgemm(qs, 3 * DEC_HP, DEC_HP, B, 1.f, w.drow, 1, 3 * DEC_HP, w.zc, DEC_HP, 1, 0.f, w.dwizc, DEC_HP,
+                     nullptr, w.gemm_splits, w.gemm_ws);
         const bool t2 = launch_wgrad_hh(qs, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, w.tokd, 0, V, B, L, sm, w.wg_part_dec,
                                         w.dt_part_dec, grads + lay.off[P_DEC_WHH], w.dT_dec);
         if (!t2) launch_dtable(qs, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part_dec, w.dT_dec);
@@ -294,9 +297,6 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     // gradient at [z;c]:  dh0 + drow @ W_ih[:,150:]   (in place on dh0)
     launch_sgemm(s, B, DEC_HP, 3 * DEC_HP, 1.f, w.drow, 3 * DEC_HP, 1, w.d.wizc, DEC_HP, 1, 1.f, w.dh0, DEC_HP,
                  nullptr, 1, nullptr);
-    // dW_ih[:,150:] = drow^T @ [z;c]
-    launch_sgemm(s, 3 * DEC_HP, DEC_HP, B, 1.f, w.drow, 1, 3 * DEC_HP, w.zc, DEC_HP, 1, 0.f, w.dwizc, DEC_HP,
-                 nullptr, w.gemm_splits, w.gemm_ws);
     // latent
     LatentBwdArgs la = lat_in;
     la.mu = w.mu; la.logvar = w.logvar; la.eps = in->eps; la.dzc = w.dh0; la.B = B;
@@ -308,12 +308,18 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     const float* wlv = params + lay.off[P_QLV_W];
     launch_sgemm(s, B, 2 * ENC_H, ZD, 1.f, w.dmu, ZD, 1, wmu, 2 * ENC_H, 1, 0.f, w.dhfin, 2 * ENC_H, nullptr, 1, nullptr);
     launch_sgemm(s, B, 2 * ENC_H, ZD, 1.f, w.dlv, ZD, 1, wlv, 2 * ENC_H, 1, 1.f, w.dhfin, 2 * ENC_H, nullptr, 1, nullptr);
-    launch_sgemm(s, ZD, 2 * ENC_H, B, 1.f, w.dmu, 1, ZD, w.hfin, 2 * ENC_H, 1, 0.f, grads + lay.off[P_QMU_W],
-                 2 * ENC_H, nullptr, w.gemm_splits, w.gemm_ws);
-    launch_sgemm(s, ZD, 2 * ENC_H, B, 1.f, w.dlv, 1, ZD, w.hfin, 2 * ENC_H, 1, 0.f, grads + lay.off[P_QLV_W],
-                 2 * ENC_H, nullptr, w.gemm_splits, w.gemm_ws);
-    launch_colsum(s, w.dmu, B, ZD, ZD, grads + lay.off[P_QMU_B], w.colsum_ws, 64);
-    launch_colsum(s, w.dlv, B, ZD, ZD, grads + lay.off[P_QLV_B], w.colsum_ws, 64);
+    // head weight / bias gradients: side stream (after the decoder weight gradients), under the encoder BPTT
+    {
+        cudaStream_t qs = s;
+        if (side) { side_mark(ctx, s, 0); qs = side_enter(ctx, 0); }
+        launch_sgemm(qs, ZD, 2 * ENC_H, B, 1.f, w.dmu, 1, ZD, w.hfin, 2 * ENC_H, 1, 0.f, grads + lay.off[P_QMU_W],
+                     2 * ENC_H, nullptr, w.gemm_splits, w.gemm_ws);
+        launch_sgemm(qs, ZD, 2 * ENC_H, B, 1.f, w.dlv, 1, ZD, w.hfin, 2 * ENC_H, 1, 0.f, grads + lay.off[P_QLV_W],
+                     2 * ENC_H, nullptr, w.gemm_splits, w.gemm_ws);
+        launch_colsum(qs, w.dmu, B, ZD, ZD, grads + lay.off[P_QMU_B], w.colsum_ws, 64);
+        launch_colsum(qs, w.dlv, B, ZD, ZD, grads + lay.off[P_QLV_B], w.colsum_ws, 64);
+        if (side) side_leave(ctx, 0);
+    }
     // encoder BPTT
     GruSeq enc[2];
     for (int d = 0; d < 2; ++d) {
@@ -335,6 +341,7 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
                                     w.dt_part, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1]);
     if (!t1) launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part, w.dT_enc[1]);
     side_join(ctx, s, 1);                           // decoder weight / table gradients from the side stream
+    side_join(ctx, s, 0);                           // head weight gradients
     InputGradArgs ia;
     memset(&ia, 0, sizeof(ia));
     ia.emb = params + lay.off[P_EMB];
