@@ -120,6 +120,8 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
     w.dt_part = a.take<float>((size_t)ds_ * V * 4 * DEC_HP);
     w.wg_part_dec = a.take<float>((size_t)ws_ * 3 * DEC_HP * DEC_HP);     // own partials: runs concurrently with the encoder's
     w.dt_part_dec = a.take<float>((size_t)ds_ * V * 4 * DEC_HP);
+    w.wg_part_enc1 = a.take<float>((size_t)ws_ * 3 * ENC_H * ENC_H);
+    w.dt_part_enc1 = a.take<float>((size_t)ds_ * V * 4 * ENC_H);
     for (int d = 0; d < 2; ++d) w.dT_enc[d] = a.take<float>((size_t)V * 4 * ENC_H);
     w.dT_dec = a.take<float>((size_t)V * 4 * DEC_HP);
     w.dwizc = a.take<float>((size_t)3 * DEC_HP * DEC_HP);
@@ -334,14 +336,18 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     else launch_gru_bwd_enc(s, enc, B, L);
     // recurrent weight gradients
     // (the tensor-core path produces the token-table gradient in the same pass over dg)
+    // (each direction has its own partials, and the ordered reductions of the partials run on the side stream
+    //  while the main stream already contracts the next direction)
+    cudaStream_t rs = side ? (cudaStream_t)ctx->side_stream : nullptr;
     const bool t0 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[0], w.enc_hs[0], nullptr, w.tok, 0, V, B, L, sm, w.wg_part,
-                                    w.dt_part, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0]);
+                                    w.dt_part, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0], rs, side ? ctx->ev_fork[1] : nullptr);
     if (!t0) launch_dtable(s, ENC_H, w.enc_dg[0], w.tok, B, L, 0, V, sm, w.dt_part, w.dT_enc[0]);
-    const bool t1 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[1], w.enc_hs[1], nullptr, w.tok, 1, V, B, L, sm, w.wg_part,
-                                    w.dt_part, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1]);
-    if (!t1) launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part, w.dT_enc[1]);
-    side_join(ctx, s, 1);                           // decoder weight / table gradients from the side stream
-    side_join(ctx, s, 0);                           // head weight gradients
+    const bool t1 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[1], w.enc_hs[1], nullptr, w.tok, 1, V, B, L, sm, w.wg_part_enc1,
+                                    w.dt_part_enc1, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1], rs, side ? ctx->ev_fork[1] : nullptr);
+    if (!t1) launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part_enc1, w.dT_enc[1]);
+    if (side) side_leave(ctx, 1);                   // covers everything enqueued on the (in-order) side stream so far
+    side_join(ctx, s, 1);
+    ctx->join_pending[0] = false;                   // (already implied by the join above)
     InputGradArgs ia;
     memset(&ia, 0, sizeof(ia));
     ia.emb = params + lay.off[P_EMB];

@@ -94,7 +94,7 @@ __global__ void k_dtable_reduce(const float* __restrict__ part, int nsplit, int 
 
 bool launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0,
                      const uint8_t* tok, int reverse, int V, int B, int L, int sm_count, float* part, float* dt_part,
-                     float* dW, float* dT) {
+                     float* dW, float* dT, cudaStream_t reduce_stream, void* reduce_event) {
     int nrows = B * L;
 #ifndef CPG_EMU
     // tf32 operands (round-to-nearest, fp32 accumulate): the rounding noise averages out over the
@@ -103,8 +103,14 @@ bool launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float
     if ((g_opt_wgrad_tc == 1 && nrows >= 8192) || g_opt_wgrad_tc == 2) {
         int nsplit = 0;
         if (launch_wgrad_tc(s, HP, dg, hs, h0, tok, reverse, B, L, V, sm_count, part, dt_part, &nsplit) == 0) {
-            CPG_LAUNCH(k_wgrad_hh_reduce, CPG_RED_GRID(3 * H * H), CPG_RED_BLOCK, 0, s, part, nsplit, HP, H, dW);
-            CPG_LAUNCH(k_dtable_reduce, CPG_RED_GRID(V * 4 * HP), CPG_RED_BLOCK, 0, s, dt_part, nsplit, V * 4 * HP, dT);
+            cudaStream_t rs = s;
+            if (reduce_stream != nullptr && reduce_event != nullptr) {
+                cudaEventRecord((cudaEvent_t)reduce_event, s);
+                cudaStreamWaitEvent(reduce_stream, (cudaEvent_t)reduce_event, 0);
+                rs = reduce_stream;
+            }
+            CPG_LAUNCH(k_wgrad_hh_reduce, CPG_RED_GRID(3 * H * H), CPG_RED_BLOCK, 0, rs, part, nsplit, HP, H, dW);
+            CPG_LAUNCH(k_dtable_reduce, CPG_RED_GRID(V * 4 * HP), CPG_RED_BLOCK, 0, rs, dt_part, nsplit, V * 4 * HP, dT);
             return true;                               // W_hh gradient (h0 rows included) and dT both done
         }
     }

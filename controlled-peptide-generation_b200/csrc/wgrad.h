@@ -21,7 +21,8 @@ int dtable_splits(int B, int L, int sm_count);
 // dW_hh (and, on the tensor-core path, the token-table gradient dT as well: returns true then).
 bool launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0,
                      const uint8_t* tok, int reverse, int V, int B, int L, int sm_count, float* part, float* dt_part,
-                     float* dW, float* dT);
+                     float* dW, float* dT,
+                     cudaStream_t reduce_stream = nullptr, void* reduce_event = nullptr);   // reductions on another stream (event-ordered)
 void launch_wgrad_hh_simt(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0, int B, int L,
                           int sm_count, float* part, float* dW);
 // tcgen05 version (wgrad_tc.cu): partials part_w [nsplit][3*HP][HP] and part_t [nsplit][V][4*HP]
