@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(192, 1)
 k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ CUtensorMap tmap_hs, WgTcArgs a) {
     constexpr int NCH = (HP + 31) / 32;                 // 32-float chunks holding valid columns
     constexpr int N_MMA = (HP + 15) / 16 * 16;          // UMMA N for the W_hh tiles
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char smem[];   // 1024-byte aligned window (SWIZZLE_128B atoms); used
+                                                              // directly so that every access stays an LDS/STS
     __shared__ __align__(8) uint64_t bar_full[WT_STAGES], bar_conv[WT_STAGES], bar_empty[WT_STAGES], bar_done;
     __shared__ uint32_t tmem_slot;
 
