@@ -27,6 +27,9 @@
 #include <cuda_bf16.h>
 #include "tc_common.cuh"
 
+#ifndef CPG_CHAIN_SKEW_NS
+#define CPG_CHAIN_SKEW_NS 900
+#endif
 #ifndef CPG_ENC_FWD_NWG
 #define CPG_ENC_FWD_NWG 10
 #endif
@@ -133,6 +136,17 @@ __device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz
 __device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.0f, rcp_ftz(1.0f + ex2_ftz(2.8853900817779268f * x)), 1.0f); }
+// r = sigmoid(a), z = sigmoid(b) with ONE reciprocal: 1/((1+e^-a)(1+e^-b)) feeds both (the SFU, at 16 ops/clk/SM,
+// is what bounds the forward gate math: 5 instead of 6 SFU ops per hidden unit).  The exponents are clamped
+// so that the product of the two denominators stays finite.
+__device__ __forceinline__ void sigmoid_pair(float a, float b, float& r, float& z) {
+    const float ea = ex2_ftz(fminf(-1.4426950408889634f * a, 60.0f));
+    const float eb = ex2_ftz(fminf(-1.4426950408889634f * b, 60.0f));
+    const float pa = 1.0f + ea, pb = 1.0f + eb;
+    const float inv = rcp_ftz(pa * pb);
+    r = pb * inv;
+    z = pa * inv;
+}
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 // streaming 16-byte load of stash data read exactly once: no L1 allocation
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
@@ -315,6 +329,9 @@ k_gru_fwd_tc(FwdArgs a) {
         constexpr uint32_t idesc = make_idesc_bf16(128, NB);
         const uint32_t x0 = tc::smem_u32(Xb) + (uint32_t)(ch * 2 * C::X_SPLIT);
         const uint32_t d0 = tmem_d + (uint32_t)(ch * MT * NB);
+        // start the chains half a step apart: the SFU-bound gate math of one then runs under the MMA / TMEM
+        // read-out of the other instead of both phases coinciding
+        if (ch > 0) __nanosleep(CPG_CHAIN_SKEW_NS);
         for (int s = 0; s < L; ++s) {
             if (s > 0) {
                 tc::mbar_wait(&bar_x[ch], (s - 1) & 1);
@@ -435,8 +452,7 @@ k_gru_fwd_tc(FwdArgs a) {
                         gz[e] += rb[C::DEC ? it : 0][1][e];
                         gn[e] += rb[C::DEC ? it : 0][2][e];
                     }
-                    rr[e] = sigmoid_fast(gr[e]);
-                    zz[e] = sigmoid_fast(gz[e]);
+                    sigmoid_pair(gr[e], gz[e], rr[e], zz[e]);
                     hh[e] = pnv[e] + bhn[it][e];
                     nn[e] = tanh_fast(gn[e] + rr[e] * hh[e]);
                     hn[e] = (1.0f - zz[e]) * nn[e] + zz[e] * hprev[it][e];
