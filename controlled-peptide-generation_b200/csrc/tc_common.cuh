@@ -123,11 +123,11 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, i
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float to_tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// fp32 -> tf32, round to nearest (ties away): add half a tf32 ulp to the magnitude and clear the 13 low bits
+// (callers also use the rounded value in fp32 arithmetic, e.g. the norms of the MMD Gram).  Two integer ops
+// instead of the multi-instruction cvt.rna.tf32 sequence (identical for finite values; the operand-conversion
+// warps of wgrad_tc / mmd_tc were bound by that sequence).
+__device__ __forceinline__ float to_tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 }  // namespace tc
 

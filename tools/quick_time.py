@@ -14,6 +14,7 @@ st = engine.FlatState(V, dev); st.load(p)
 tokens = ow.synthetic_tokens(B, V, seed=2).to(dev)
 noise = engine.alloc_noise(B, L, dev)
 hp = engine.make_hparams()
+SIDE = int(sys.argv[2]) if len(sys.argv) > 2 else 1      # 0: everything on one stream (per-kernel times are then each kernel's own)
 def step(i):
     engine.fill_step_noise(noise, 1238, i)
     return engine.train_step(st, tokens, noise, hp)
@@ -26,10 +27,12 @@ for i in range(K): s, _ = step(3 + i)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
 print('B=%d step %.3f ms -> %.0f seq/s ; loss %.4f' % (B, ms, B / ms * 1e3, float(s[0])))
+_lib.set_option('side_stream', SIDE)
 _lib.profile_enable(True)
 for i in range(5): step(30 + i)
 rows = _lib.profile_read()
 _lib.profile_enable(False)
+_lib.set_option('side_stream', 1)
 tot = sum(r[1] for r in rows)
 for name, t, n in sorted(rows, key=lambda r: -r[1]):
     print('  %-28s %8.3f ms/step  x%-3d %5.1f%%' % (name, t / 5, n // 5, 100 * t / tot))
