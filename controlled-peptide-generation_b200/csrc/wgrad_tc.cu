@@ -4,7 +4,7 @@
 //     dW_hh[g][k]   = sum_r dgh[r][g] * h_prev[r][k]            (3 gate planes, N = H)
 //     dT[v][pl][j]  = sum_r [tok_r == v] * dg[r][pl][j]          (4 planes, N = 32 one-hot columns)
 // The range is split over one persistent CTA per SM; each CTA streams its rows through a
-// TMA -> convert -> tcgen05.mma pipeline (2 stages of 32 rows) with all seven accumulator tiles
+// TMA -> convert -> tcgen05.mma pipeline (4 stages of 16 rows) with all seven accumulator tiles
 // (3 x [128 x H] + 4 x [128 x 32]) resident in TMEM for the whole range, so dg is read from HBM once.
 //
 // Operands are "MN-major" for UMMA: a row of `dg` ([B*L][4*HP]) holds the M index (gate column)
@@ -16,18 +16,31 @@
 // operand to tf32 (round-to-nearest: unbiased products; the tensor core itself truncates) and build the
 // one-hot token tile in the same swizzled layout.
 //
-// Warp roles (192 threads): warp 4 = TMA producer, warp 5 = MMA issuer (+ TMEM owner),
-// warps 0-3 = conversion per stage, then the TMEM -> global epilogue.
+// Warp roles (320 threads): warp 4 = TMA producer, warp 5 = MMA issuer (+ TMEM owner), warps 0-3 and 6-9 =
+// conversion per stage; warps 0-3 then run the TMEM -> global epilogue.
 #include "ctx.h"
 #ifndef CPG_EMU
 #include "tc_common.cuh"
 
+#ifdef CPG_GRU_TIMELINE
+// developer-only probe (tools/wgrad_timeline.py): cycles each warp role of CTA 0 spends waiting / working
+__device__ long long g_wg_tl[32];
+extern "C" int cpg_debug_wgrad_timeline(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_wg_tl, sizeof(g_wg_tl)); }
+#define WG_T0() const long long _t0 = clock64()
+#define WG_ACC(var) var += clock64() - _t0
+#define WG_OUT(slot, v) do { if (blockIdx.x == 0) g_wg_tl[slot] = (v); } while (0)
+#else
+#define WG_T0() do { } while (0)
+#define WG_ACC(var) do { } while (0)
+#define WG_OUT(slot, v) do { } while (0)
+#endif
+
 namespace cpg {
 int check_launch(const char* where);
 
-constexpr int WT_RK = 32;                 // reduction rows per pipeline stage
-constexpr int WT_CHUNK = WT_RK * 128;     // bytes of one {32 floats x 32 rows} box
-constexpr int WT_STAGES = 2;
+constexpr int WT_RK = 16;                 // reduction rows per pipeline stage (two K = 8 MMAs per tile)
+constexpr int WT_CHUNK = WT_RK * 128;     // bytes of one {32 floats x WT_RK rows} box
+constexpr int WT_STAGES = 4;              // 4 x 42 KB: the TMA latency of three stages hides under the fourth's conversion + MMAs
 constexpr int WT_A_BYTES = 4 * 4 * WT_CHUNK;      // 4 planes x 4 chunks (M = 128 lanes per plane)
 constexpr int WT_B_BYTES = 4 * WT_CHUNK;          // h_prev: up to 128 columns
 constexpr int WT_O_BYTES = WT_CHUNK;              // one-hot tokens: 32 columns
@@ -47,7 +60,7 @@ struct WgTcArgs {
 __device__ __forceinline__ int wt_unit_off(int i, int u) { return i * 128 + ((((u >> 1) ^ (i & 3))) << 5) + ((u & 1) << 4); }
 
 template <int HP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ CUtensorMap tmap_hs, WgTcArgs a) {
     constexpr int NCH = (HP + 31) / 32;                 // 32-float chunks holding valid columns
     constexpr int N_MMA = (HP + 15) / 16 * 16;          // UMMA N for the W_hh tiles
@@ -66,7 +79,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ 
         if (lane == 0) {
             for (int s = 0; s < WT_STAGES; ++s) {
                 tc::mbar_init(&bar_full[s], 1);
-                tc::mbar_init(&bar_conv[s], 128);
+                tc::mbar_init(&bar_conv[s], 256);
                 tc::mbar_init(&bar_empty[s], 1);
             }
             tc::mbar_init(&bar_done, 1);
@@ -85,9 +98,12 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ 
         if (lane == 0) {
             tc::tma_prefetch_desc(&tmap_dg);
             tc::tma_prefetch_desc(&tmap_hs);
+            long long w_empty = 0, w_issue = 0;
+            const long long tstart = clock64();
             for (int it = 0; it < n_iters; ++it) {
                 const int st = it % WT_STAGES, u = it / WT_STAGES;
-                if (u >= 1) tc::mbar_wait(&bar_empty[st], (u - 1) & 1);
+                { WG_T0(); if (u >= 1) tc::mbar_wait(&bar_empty[st], (u - 1) & 1); WG_ACC(w_empty); }
+                WG_T0();
                 unsigned char* sa = smem + (size_t)st * WT_STAGE_BYTES;
                 unsigned char* sb = sa + WT_A_BYTES;
                 const int r0 = r_begin + it * WT_RK;
@@ -97,7 +113,9 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ 
                         tc::tma_load_2d(sa + (pl * 4 + c) * WT_CHUNK, &tmap_dg, &bar_full[st], pl * HP + c * 32, r0);
                 for (int c = 0; c < NCH; ++c)
                     tc::tma_load_2d(sb + c * WT_CHUNK, &tmap_hs, &bar_full[st], c * 32, r0 - 1);
+                WG_ACC(w_issue);
             }
+            WG_OUT(0, w_empty); WG_OUT(1, w_issue); WG_OUT(2, clock64() - tstart); WG_OUT(3, (long long)n_iters);
         }
         __syncwarp();
     } else if (warp == 5) {
@@ -108,10 +126,13 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ 
             // MN-major SWIZZLE_128B_BASE32B: next 32 floats of M/N one 4 KB box further (LBO),
             // 4-row K groups 512 B apart (SBO); one K = 8 MMA spans two such groups
             constexpr uint32_t lbo = WT_CHUNK, sbo = 512u;
+            long long w_conv = 0, w_mma = 0;
+            const long long tstart = clock64();
             for (int it = 0; it < n_iters; ++it) {
                 const int st = it % WT_STAGES, u = it / WT_STAGES;
-                tc::mbar_wait(&bar_conv[st], u & 1);
+                { WG_T0(); tc::mbar_wait(&bar_conv[st], u & 1); WG_ACC(w_conv); }
                 tc::tc_fence_after();
+                WG_T0();
                 const uint32_t sa = tc::smem_u32(smem + (size_t)st * WT_STAGE_BYTES);
                 const uint32_t sb = sa + WT_A_BYTES, so = sb + WT_B_BYTES;
 #pragma unroll
@@ -127,42 +148,54 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ 
                     }
                 }
                 tc::umma_commit(&bar_empty[st]);          // stage reusable once these MMAs have read it
+                WG_ACC(w_mma);
             }
             tc::umma_commit(&bar_done);
+            WG_OUT(4, w_conv); WG_OUT(5, w_mma); WG_OUT(6, clock64() - tstart);
         }
         __syncwarp();
     } else {
-        // ---------------- conversion (in place), 128 threads:
-        // thread -> 16-byte unit (tid & 7) of rows (tid >> 3) and (tid >> 3) + 16 of every 4 KB box
+        // ---------------- conversion (in place), 256 threads = warps 0-3 and 6-9 (two warps per scheduler: the
+        // single-warp version was latency-bound and paced the whole pipeline).  Converter ci -> 16-byte unit
+        // (ci & 7) of row (ci >> 3) & 15 of every box; group ci >> 7 takes the boxes of its parity.  Group 0 also
+        // rounds h_prev (and rewrites it for first steps), group 1 builds the one-hot token tile.
+        const int ci = warp < 4 ? tid : tid - 64;
+        const int grp = ci >> 7, slot = ci & 127, row = slot >> 3, un = slot & 7;
+        auto rnd4 = [](float4 v) {          // tf32 round-to-nearest = add half an ulp; the tensor core drops the low bits
+            v.x = __uint_as_float(__float_as_uint(v.x) + 0x1000u); v.y = __uint_as_float(__float_as_uint(v.y) + 0x1000u);
+            v.z = __uint_as_float(__float_as_uint(v.z) + 0x1000u); v.w = __uint_as_float(__float_as_uint(v.w) + 0x1000u);
+            return v;
+        };
+        static_assert(WT_RK == 16, "one row per converter slot");
+        long long w_full = 0, w_work = 0;
+        const long long tstart = clock64();
         for (int it = 0; it < n_iters; ++it) {
             const int st = it % WT_STAGES, u_it = it / WT_STAGES;
-            tc::mbar_wait(&bar_full[st], u_it & 1);
+            const int r0 = r_begin + it * WT_RK;
+            const int r = r0 + row;
+            const bool dead = r >= r_end;                     // rows of the next CTA's range (or past the end)
+            const int rr = dead ? r_begin : r;
+            const int b = rr / L, s = rr % L;
+            // token of this row: fetched before the wait so that its latency hides under the TMA's
+            int tk = 0;
+            if (grp == 1) {
+                const int t = a.reverse ? (L - 1 - s) : s;
+                tk = a.tok[(size_t)b * L + t];
+            }
+            { WG_T0(); tc::mbar_wait(&bar_full[st], u_it & 1); WG_ACC(w_full); }
+            WG_T0();
             unsigned char* sa = smem + (size_t)st * WT_STAGE_BYTES;
             unsigned char* sb = sa + WT_A_BYTES;
             unsigned char* so = sb + WT_B_BYTES;
-            const int r0 = r_begin + it * WT_RK;
-            const int un = tid & 7;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int row = (tid >> 3) + 16 * half;
-                const int r = r0 + row;
-                const bool dead = r >= r_end;                 // rows of the next CTA's range (or past the end)
-                const int rr = dead ? r_begin : r;
-                const int b = rr / L, s = rr % L;
-                const int slot = row * 8 + un;                // unit index in box-linear order (swizzle agnostic)
+            for (int pl = 0; pl < 4; ++pl)
 #pragma unroll
-                for (int pl = 0; pl < 4; ++pl)
-#pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        float4* p = reinterpret_cast<float4*>(sa + (pl * 4 + c) * WT_CHUNK) + slot;
-                        float4 v = *p;
-                        if (dead) {
-                            v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        } else {
-                            v.x = tc::to_tf32_rn(v.x); v.y = tc::to_tf32_rn(v.y); v.z = tc::to_tf32_rn(v.z); v.w = tc::to_tf32_rn(v.w);
-                        }
-                        *p = v;
-                    }
+                for (int c = 0; c < NCH; ++c) {
+                    if (((pl * NCH + c) & 1) != grp) continue;
+                    float4* p = reinterpret_cast<float4*>(sa + (pl * 4 + c) * WT_CHUNK) + slot;   // box-linear: swizzle agnostic
+                    *p = dead ? make_float4(0.f, 0.f, 0.f, 0.f) : rnd4(*p);
+                }
+            if (grp == 0) {
                 if (s == 0) {
                     // h_prev of a first step is h0, not the row above: rewrite it (swizzle-aware addressing)
 #pragma unroll
@@ -170,21 +203,17 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ 
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         const int col = c * 32 + un * 4;
                         if (a.h0 != nullptr && col < HP) v = ld4(a.h0 + (size_t)b * HP + col);
-                        v.x = tc::to_tf32_rn(v.x); v.y = tc::to_tf32_rn(v.y); v.z = tc::to_tf32_rn(v.z); v.w = tc::to_tf32_rn(v.w);
-                        *reinterpret_cast<float4*>(sb + c * WT_CHUNK + wt_unit_off(row, un)) = v;
+                        *reinterpret_cast<float4*>(sb + c * WT_CHUNK + wt_unit_off(row, un)) = rnd4(v);
                     }
                 } else {
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
                         float4* p = reinterpret_cast<float4*>(sb + c * WT_CHUNK) + slot;
-                        float4 v = *p;
-                        v.x = tc::to_tf32_rn(v.x); v.y = tc::to_tf32_rn(v.y); v.z = tc::to_tf32_rn(v.z); v.w = tc::to_tf32_rn(v.w);
-                        *p = v;
+                        *p = rnd4(*p);
                     }
                 }
+            } else {
                 // one-hot row of the token that fed step s (time L-1-s for the reverse direction)
-                const int t = a.reverse ? (L - 1 - s) : s;
-                const int tk = a.tok[(size_t)b * L + t];
                 float4 oh = make_float4(0.f, 0.f, 0.f, 0.f);
                 if ((tk >> 2) == un) {
                     const int k = tk & 3;
@@ -194,48 +223,58 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ 
             }
             tc::fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core
             tc::mbar_arrive(&bar_conv[st]);
+            WG_ACC(w_work);
         }
-        // ---------------- epilogue: TMEM -> per-CTA partials
-        if (n_iters > 0) {
-            tc::mbar_wait(&bar_done, 0);
-            tc::tc_fence_after();
-        }
-        float* out_w = a.part_w + (size_t)blockIdx.x * 3 * HP * HP;
-        float* out_t = a.part_t + (size_t)blockIdx.x * a.V * 4 * HP;
-        const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
-        for (int g = 0; g < 3; ++g) {
+        if (tid == 0) { WG_OUT(8, w_full); WG_OUT(9, w_work); WG_OUT(10, clock64() - tstart); }
+        const long long tepi = clock64();
+        // ---------------- epilogue (warps 0-3): TMEM -> per-CTA partials
+        if (warp < 4) {
+            if (n_iters > 0) {
+                tc::mbar_wait(&bar_done, 0);
+                tc::tc_fence_after();
+            }
+            float* out_w = a.part_w + (size_t)blockIdx.x * 3 * HP * HP;
+            float* out_t = a.part_t + (size_t)blockIdx.x * a.V * 4 * HP;
+            const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+            for (int g = 0; g < 3; ++g) {
 #pragma unroll 1
-            for (int c = 0; c < NCH; ++c) {
+                for (int c = 0; c < NCH; ++c) {
+                    float v[32];
+                    if (n_iters > 0) {
+                        tc::tmem_ld_32x32(lane_addr + (uint32_t)(g * 128 + c * 32), v);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) v[q] = 0.f;
+                    }
+                    if (tid < HP) {
+                        float* o = out_w + ((size_t)g * HP + tid) * HP + c * 32;      // 16-byte aligned: HP % 4 == 0
+#pragma unroll
+                        for (int q = 0; q < 32; q += 4)
+                            if (c * 32 + q < HP) st4(o + q, make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]));
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int pl = 0; pl < 4; ++pl) {
                 float v[32];
                 if (n_iters > 0) {
-                    tc::tmem_ld_32x32(lane_addr + (uint32_t)(g * 128 + c * 32), v);
+                    tc::tmem_ld_32x32(lane_addr + (uint32_t)(WT_TCOL + pl * 32), v);
                 } else {
 #pragma unroll
                     for (int q = 0; q < 32; ++q) v[q] = 0.f;
                 }
                 if (tid < HP) {
-                    float* o = out_w + ((size_t)g * HP + tid) * HP + c * 32;
 #pragma unroll
                     for (int q = 0; q < 32; ++q)
-                        if (c * 32 + q < HP) o[q] = v[q];
+                        if (q < a.V) out_t[(size_t)q * 4 * HP + pl * HP + tid] = v[q];
                 }
             }
         }
-#pragma unroll 1
-        for (int pl = 0; pl < 4; ++pl) {
-            float v[32];
-            if (n_iters > 0) {
-                tc::tmem_ld_32x32(lane_addr + (uint32_t)(WT_TCOL + pl * 32), v);
-            } else {
-#pragma unroll
-                for (int q = 0; q < 32; ++q) v[q] = 0.f;
-            }
-            if (tid < HP) {
-#pragma unroll
-                for (int q = 0; q < 32; ++q)
-                    if (q < a.V) out_t[(size_t)q * 4 * HP + pl * HP + tid] = v[q];
-            }
-        }
+#ifdef CPG_GRU_TIMELINE
+        if (tid == 0) WG_OUT(11, clock64() - tepi);
+#else
+        (void)tepi;
+#endif
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -264,12 +303,12 @@ int launch_wgrad_tc(cudaStream_t s, int HP, const float* dg, const float* hs, co
         auto kfn = k_wgrad_tc<ENC_H>;
         static bool once = false;
         if (!once) { cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM); once = true; }
-        CPG_LAUNCH_NAMED("k_wgrad_tc_enc", kfn, nsplit, 192, WT_SMEM, s, tm_dg, tm_hs, a);
+        CPG_LAUNCH_NAMED("k_wgrad_tc_enc", kfn, nsplit, 320, WT_SMEM, s, tm_dg, tm_hs, a);
     } else {
         auto kfn = k_wgrad_tc<DEC_HP>;
         static bool once = false;
         if (!once) { cudaFuncSetAttribute((const void*)kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WT_SMEM); once = true; }
-        CPG_LAUNCH_NAMED("k_wgrad_tc_dec", kfn, nsplit, 192, WT_SMEM, s, tm_dg, tm_hs, a);
+        CPG_LAUNCH_NAMED("k_wgrad_tc_dec", kfn, nsplit, 320, WT_SMEM, s, tm_dg, tm_hs, a);
     }
     return CPG_OK;
 }
