@@ -280,7 +280,9 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     memset(&q, 0, sizeof(q));
     q.whh = w.d.whh_dec; q.h0 = w.zc; q.hs = w.dec_hs; q.gates = w.dec_gates;
     q.dh_out = w.dec_dh_out; q.dg = w.dec_dg; q.dh0 = w.dh0; q.drow = w.drow;
-    if (use_gru_tc(B)) launch_gru_bwd_dec_tc(s, q, B, L);
+    // the tcgen05 BPTT kernels hand dg to the tf32 weight-gradient kernel already rounded
+    const int dg_rounded = (use_gru_tc(B) && wgrad_uses_tc(B * L)) ? 1 : 0;
+    if (use_gru_tc(B)) launch_gru_bwd_dec_tc(s, q, B, L, dg_rounded);
     else launch_gru_bwd_dec(s, q, B, L);
     // decoder W_hh / token-table gradients only need the decoder's dg: side stream, under the dense layers and
     // the encoder BPTT of the main stream (joined before the input-side gradients)
@@ -292,7 +294,7 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
         launch_sgemm(qs, 3 * DEC_HP, DEC_HP, B, 1.f, w.drow, 1, 3 * DEC_HP, w.zc, DEC_HP, 1, 0.f, w.dwizc, DEC_HP,
                      nullptr, w.gemm_splits, w.gemm_ws);
         const bool t2 = launch_wgrad_hh(qs, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, w.tokd, 0, V, B, L, sm, w.wg_part_dec,
-                                        w.dt_part_dec, grads + lay.off[P_DEC_WHH], w.dT_dec);
+                                        w.dt_part_dec, grads + lay.off[P_DEC_WHH], w.dT_dec, nullptr, nullptr, dg_rounded);
         if (!t2) launch_dtable(qs, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part_dec, w.dT_dec);
         if (side) side_leave(ctx, 1);
     }
@@ -332,7 +334,7 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
         e.dh_fin = w.dhfin + d * ENC_H; e.dh_fin_stride = 2 * ENC_H;
         e.dg = w.enc_dg[d];
     }
-    if (use_gru_tc(B)) launch_gru_bwd_enc_tc(s, enc, B, L);
+    if (use_gru_tc(B)) launch_gru_bwd_enc_tc(s, enc, B, L, dg_rounded);
     else launch_gru_bwd_enc(s, enc, B, L);
     // recurrent weight gradients
     // (the tensor-core path produces the token-table gradient in the same pass over dg)
@@ -340,10 +342,10 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     //  while the main stream already contracts the next direction)
     cudaStream_t rs = side ? (cudaStream_t)ctx->side_stream : nullptr;
     const bool t0 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[0], w.enc_hs[0], nullptr, w.tok, 0, V, B, L, sm, w.wg_part,
-                                    w.dt_part, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0], rs, side ? ctx->ev_fork[1] : nullptr);
+                                    w.dt_part, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0], rs, side ? ctx->ev_fork[1] : nullptr, dg_rounded);
     if (!t0) launch_dtable(s, ENC_H, w.enc_dg[0], w.tok, B, L, 0, V, sm, w.dt_part, w.dT_enc[0]);
     const bool t1 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[1], w.enc_hs[1], nullptr, w.tok, 1, V, B, L, sm, w.wg_part_enc1,
-                                    w.dt_part_enc1, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1], rs, side ? ctx->ev_fork[1] : nullptr);
+                                    w.dt_part_enc1, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1], rs, side ? ctx->ev_fork[1] : nullptr, dg_rounded);
     if (!t1) launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part_enc1, w.dT_enc[1]);
     if (side) side_leave(ctx, 1);                   // covers everything enqueued on the (in-order) side stream so far
     side_join(ctx, s, 1);

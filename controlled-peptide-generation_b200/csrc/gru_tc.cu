@@ -532,6 +532,7 @@ struct BwdArgs {
     float* dh0;                // decoder: [B][HP]
     float* drow;               // decoder: [B][3*HP]
     int B, L;
+    int round_dg;              // 1: store dg rounded to tf32 (its consumer is k_wgrad_tc)
 };
 
 template <class C>
@@ -779,10 +780,18 @@ k_gru_bwd_tc(BwdArgs a) {
                 *reinterpret_cast<uint2*>(X1 + (k >> 3) * C::X_LBO + boff + (k & 7) * 2) = lo;
                 if (row < B) {
                     float* gp = dg_g + ((size_t)row * L + s) * 4 * HP + j0;
-                    st4(gp, make_float4(o_r[0], o_r[1], o_r[2], o_r[3]));
-                    st4(gp + HP, make_float4(o_z[0], o_z[1], o_z[2], o_z[3]));
-                    st4(gp + 2 * HP, make_float4(o_n[0], o_n[1], o_n[2], o_n[3]));
-                    st4(gp + 3 * HP, make_float4(o_hn[0], o_hn[1], o_hn[2], o_hn[3]));
+                    // dg's only reader on this path is the tf32 weight-gradient kernel: when it asks for it, the
+                    // planes leave already rounded to tf32 (add half an ulp; the tensor core drops the low bits),
+                    // which removes four of its five operand-conversion passes
+                    const uint32_t rb = a.round_dg ? 0x1000u : 0u;
+                    auto r4 = [rb](const float (&x)[4]) {
+                        return make_float4(__uint_as_float(__float_as_uint(x[0]) + rb), __uint_as_float(__float_as_uint(x[1]) + rb),
+                                           __uint_as_float(__float_as_uint(x[2]) + rb), __uint_as_float(__float_as_uint(x[3]) + rb));
+                    };
+                    st4(gp, r4(o_r));
+                    st4(gp + HP, r4(o_z));
+                    st4(gp + 2 * HP, r4(o_n));
+                    st4(gp + 3 * HP, r4(o_hn));
                 }
             }
             if (i < L) {
@@ -851,14 +860,14 @@ int launch_gru_fwd_dec_tc(cudaStream_t s, const GruSeq& q, int B, int L, int V) 
     return CPG_OK;
 }
 
-int launch_gru_bwd_enc_tc(cudaStream_t s, const GruSeq* two, int B, int L) {
+int launch_gru_bwd_enc_tc(cudaStream_t s, const GruSeq* two, int B, int L, int round_dg) {
     BwdArgs a;
     memset(&a, 0, sizeof(a));
     for (int d = 0; d < 2; ++d) {
         a.whh[d] = two[d].whh; a.hs[d] = two[d].hs; a.gates[d] = two[d].gates; a.dg[d] = two[d].dg;
     }
     a.dh_fin = two[0].dh_fin;
-    a.B = B; a.L = L;
+    a.B = B; a.L = L; a.round_dg = round_dg;
     const size_t smem = EncBwd::smem_bytes();
     static size_t set_for = 0;
     if (set_smem(k_gru_bwd_tc<EncBwd>, smem, set_for)) return CPG_ECUDA;
@@ -866,12 +875,12 @@ int launch_gru_bwd_enc_tc(cudaStream_t s, const GruSeq* two, int B, int L) {
     return CPG_OK;
 }
 
-int launch_gru_bwd_dec_tc(cudaStream_t s, const GruSeq& q, int B, int L) {
+int launch_gru_bwd_dec_tc(cudaStream_t s, const GruSeq& q, int B, int L, int round_dg) {
     BwdArgs a;
     memset(&a, 0, sizeof(a));
     a.whh[0] = q.whh; a.hs[0] = q.hs; a.gates[0] = q.gates; a.dg[0] = q.dg;
     a.h0 = q.h0; a.dh_out = q.dh_out; a.dh0 = q.dh0; a.drow = q.drow;
-    a.B = B; a.L = L;
+    a.B = B; a.L = L; a.round_dg = round_dg;
     const size_t smem = DecBwd::smem_bytes();
     static size_t set_for = 0;
     if (set_smem(k_gru_bwd_tc<DecBwd>, smem, set_for)) return CPG_ECUDA;

@@ -71,8 +71,8 @@ void launch_gru_bwd_dec(cudaStream_t s, const GruSeq& seq, int B, int L);
 // tcgen05 recurrences (gru_tc.cu); GruSeq::whh must hold the natural [3H][H] recurrent weights
 int launch_gru_fwd_enc_tc(cudaStream_t s, const GruSeq* two_dirs, int B, int L, int V);
 int launch_gru_fwd_dec_tc(cudaStream_t s, const GruSeq& seq, int B, int L, int V);
-int launch_gru_bwd_enc_tc(cudaStream_t s, const GruSeq* two_dirs, int B, int L);
-int launch_gru_bwd_dec_tc(cudaStream_t s, const GruSeq& seq, int B, int L);
+int launch_gru_bwd_enc_tc(cudaStream_t s, const GruSeq* two_dirs, int B, int L, int round_dg);   // round_dg: dg stored as tf32
+int launch_gru_bwd_dec_tc(cudaStream_t s, const GruSeq& seq, int B, int L, int round_dg);
 extern int g_opt_gru_tc;
 extern int g_opt_side_stream;
 

@@ -86,6 +86,11 @@ int wgrad_splits(int B, int L, int sm_count) {
 }
 
 int g_opt_wgrad_tc = 1;
+#ifndef CPG_EMU
+bool wgrad_uses_tc(int nrows) { return (g_opt_wgrad_tc == 1 && nrows >= 8192) || g_opt_wgrad_tc == 2; }
+#else
+bool wgrad_uses_tc(int) { return false; }
+#endif
 #ifdef CPG_EMU
 int wgrad_tc_splits(int) { return 1; }      // the tcgen05 kernel is compiled out of the CPU emulation
 #endif
@@ -94,15 +99,15 @@ __global__ void k_dtable_reduce(const float* __restrict__ part, int nsplit, int 
 
 bool launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0,
                      const uint8_t* tok, int reverse, int V, int B, int L, int sm_count, float* part, float* dt_part,
-                     float* dW, float* dT, cudaStream_t reduce_stream, void* reduce_event) {
+                     float* dW, float* dT, cudaStream_t reduce_stream, void* reduce_event, int dg_rounded) {
     int nrows = B * L;
 #ifndef CPG_EMU
     // tf32 operands (round-to-nearest, fp32 accumulate): the rounding noise averages out over the
     // B*L-long reduction, so the tensor-core path is used where the reduction is long (>= 8192 rows);
     // short reductions (tiny batches) stay on the exact fp32 SIMT kernels.  g_opt_wgrad_tc = 2 forces it.
-    if ((g_opt_wgrad_tc == 1 && nrows >= 8192) || g_opt_wgrad_tc == 2) {
+    if (wgrad_uses_tc(nrows)) {
         int nsplit = 0;
-        if (launch_wgrad_tc(s, HP, dg, hs, h0, tok, reverse, B, L, V, sm_count, part, dt_part, &nsplit) == 0) {
+        if (launch_wgrad_tc(s, HP, dg, hs, h0, tok, reverse, B, L, V, sm_count, part, dt_part, &nsplit, dg_rounded) == 0) {
             cudaStream_t rs = s;
             if (reduce_stream != nullptr && reduce_event != nullptr) {
                 cudaEventRecord((cudaEvent_t)reduce_event, s);

@@ -22,14 +22,16 @@ int dtable_splits(int B, int L, int sm_count);
 bool launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0,
                      const uint8_t* tok, int reverse, int V, int B, int L, int sm_count, float* part, float* dt_part,
                      float* dW, float* dT,
-                     cudaStream_t reduce_stream = nullptr, void* reduce_event = nullptr);   // reductions on another stream (event-ordered)
+                     cudaStream_t reduce_stream = nullptr, void* reduce_event = nullptr,
+                     int dg_rounded = 0);   // reductions on another stream (event-ordered)
 void launch_wgrad_hh_simt(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0, int B, int L,
                           int sm_count, float* part, float* dW);
 // tcgen05 version (wgrad_tc.cu): partials part_w [nsplit][3*HP][HP] and part_t [nsplit][V][4*HP]
 int wgrad_tc_splits(int sm_count);
 int launch_wgrad_tc(cudaStream_t s, int HP, const float* dg, const float* hs, const float* h0, const uint8_t* tok,
-                    int reverse, int B, int L, int V, int sm_count, float* part_w, float* part_t, int* nsplit_out);
+                    int reverse, int B, int L, int V, int sm_count, float* part_w, float* part_t, int* nsplit_out, int dg_rounded);
 extern int g_opt_wgrad_tc;
+bool wgrad_uses_tc(int nrows);      // would launch_wgrad_hh take the tensor-core path for this many rows?
 void launch_dtable(cudaStream_t s, int HP, const float* dg, const uint8_t* tok, int B, int L, int reverse, int V,
                    int sm_count, float* part, float* dT);
 void launch_input_grads(cudaStream_t s, const InputGradArgs& a);

@@ -54,6 +54,7 @@ struct WgTcArgs {
     float* part_w;           // [nsplit][3*HP][HP]
     float* part_t;           // [nsplit][V][4*HP]
     int nrows, L, V, reverse, rows_per_cta;
+    int dg_rounded;          // dg arrives already rounded to tf32 (k_gru_bwd_tc): its boxes need no conversion pass
 };
 
 // byte offset of 16-byte unit u (columns 4u..4u+3) of row i inside one swizzled 4 KB box
@@ -187,6 +188,9 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ 
             unsigned char* sa = smem + (size_t)st * WT_STAGE_BYTES;
             unsigned char* sb = sa + WT_A_BYTES;
             unsigned char* so = sb + WT_B_BYTES;
+            // (rows past the end of the reduction are zero-filled by the TMA itself; rows past this CTA's range
+            //  only exist when the range is not a multiple of the tile, i.e. never with pre-rounded dg)
+            if (!a.dg_rounded || dead)
 #pragma unroll
             for (int pl = 0; pl < 4; ++pl)
 #pragma unroll
@@ -285,7 +289,7 @@ int wgrad_tc_splits(int sm_count) { return sm_count > 0 ? sm_count : 1; }
 
 // Fills part_w ([nsplit][3*HP][HP]) and part_t ([nsplit][V][4*HP]); the caller reduces them.
 int launch_wgrad_tc(cudaStream_t s, int HP, const float* dg, const float* hs, const float* h0, const uint8_t* tok,
-                    int reverse, int B, int L, int V, int sm_count, float* part_w, float* part_t, int* nsplit_out) {
+                    int reverse, int B, int L, int V, int sm_count, float* part_w, float* part_t, int* nsplit_out, int dg_rounded) {
     const int nrows = B * L;
     int nsplit = std::min(wgrad_tc_splits(sm_count), ceil_div(nrows, WT_RK));
     int rpc = ceil_div(ceil_div(nrows, nsplit), WT_RK) * WT_RK;
@@ -298,7 +302,7 @@ int launch_wgrad_tc(cudaStream_t s, int HP, const float* dg, const float* hs, co
     if (rc) return rc;
     WgTcArgs a;
     a.tok = tok; a.h0 = h0; a.part_w = part_w; a.part_t = part_t;
-    a.nrows = nrows; a.L = L; a.V = V; a.reverse = reverse; a.rows_per_cta = rpc;
+    a.nrows = nrows; a.L = L; a.V = V; a.reverse = reverse; a.rows_per_cta = rpc; a.dg_rounded = dg_rounded;
     if (HP == ENC_H) {
         auto kfn = k_wgrad_tc<ENC_H>;
         static bool once = false;
