@@ -57,6 +57,17 @@ struct WgTcArgs {
     int dg_rounded;          // dg arrives already rounded to tf32 (k_gru_bwd_tc): its boxes need no conversion pass
 };
 
+// one lane of a converged warp (keeps the single-thread TMA / MMA issue loops on the uniform datapath)
+__device__ __forceinline__ bool wt_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // byte offset of 16-byte unit u (columns 4u..4u+3) of row i inside one swizzled 4 KB box
 __device__ __forceinline__ int wt_unit_off(int i, int u) { return i * 128 + ((((u >> 1) ^ (i & 3))) << 5) + ((u & 1) << 4); }
 
@@ -95,46 +106,53 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ 
     const uint32_t tmem_d = tmem_slot;
 
     if (warp == 4) {
-        // ---------------- TMA producer
+        // ---------------- TMA producer (whole warp converged, one elected lane issues)
         if (lane == 0) {
             tc::tma_prefetch_desc(&tmap_dg);
             tc::tma_prefetch_desc(&tmap_hs);
-            long long w_empty = 0, w_issue = 0;
-            const long long tstart = clock64();
-            for (int it = 0; it < n_iters; ++it) {
-                const int st = it % WT_STAGES, u = it / WT_STAGES;
-                { WG_T0(); if (u >= 1) tc::mbar_wait(&bar_empty[st], (u - 1) & 1); WG_ACC(w_empty); }
-                WG_T0();
+        }
+        __syncwarp();
+        long long w_empty = 0, w_issue = 0;
+        const long long tstart = clock64();
+        for (int it = 0; it < n_iters; ++it) {
+            const int st = it % WT_STAGES, u = it / WT_STAGES;
+            { WG_T0(); if (u >= 1) tc::mbar_wait(&bar_empty[st], (u - 1) & 1); WG_ACC(w_empty); }
+            WG_T0();
+            if (wt_elect_one()) {
                 unsigned char* sa = smem + (size_t)st * WT_STAGE_BYTES;
                 unsigned char* sb = sa + WT_A_BYTES;
                 const int r0 = r_begin + it * WT_RK;
                 tc::mbar_expect_tx(&bar_full[st], (4 * NCH + NCH) * WT_CHUNK);
+#pragma unroll
                 for (int pl = 0; pl < 4; ++pl)
+#pragma unroll
                     for (int c = 0; c < NCH; ++c)
                         tc::tma_load_2d(sa + (pl * 4 + c) * WT_CHUNK, &tmap_dg, &bar_full[st], pl * HP + c * 32, r0);
+#pragma unroll
                 for (int c = 0; c < NCH; ++c)
                     tc::tma_load_2d(sb + c * WT_CHUNK, &tmap_hs, &bar_full[st], c * 32, r0 - 1);
-                WG_ACC(w_issue);
             }
-            WG_OUT(0, w_empty); WG_OUT(1, w_issue); WG_OUT(2, clock64() - tstart); WG_OUT(3, (long long)n_iters);
+            __syncwarp();
+            WG_ACC(w_issue);
         }
-        __syncwarp();
+        if (lane == 0) { WG_OUT(0, w_empty); WG_OUT(1, w_issue); WG_OUT(2, clock64() - tstart); WG_OUT(3, (long long)n_iters); }
     } else if (warp == 5) {
-        // ---------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc_w = tc::make_idesc_tf32(128, N_MMA, 1, 1);
-            constexpr uint32_t idesc_t = tc::make_idesc_tf32(128, 32, 1, 1);
-            // MN-major SWIZZLE_128B_BASE32B: next 32 floats of M/N one 4 KB box further (LBO),
-            // 4-row K groups 512 B apart (SBO); one K = 8 MMA spans two such groups
-            constexpr uint32_t lbo = WT_CHUNK, sbo = 512u;
-            long long w_conv = 0, w_mma = 0;
-            const long long tstart = clock64();
-            for (int it = 0; it < n_iters; ++it) {
-                const int st = it % WT_STAGES, u = it / WT_STAGES;
-                { WG_T0(); tc::mbar_wait(&bar_conv[st], u & 1); WG_ACC(w_conv); }
-                tc::tc_fence_after();
-                WG_T0();
-                const uint32_t sa = tc::smem_u32(smem + (size_t)st * WT_STAGE_BYTES);
+        // ---------------- MMA issuer (whole warp converged, one elected lane issues)
+        constexpr uint32_t idesc_w = tc::make_idesc_tf32(128, N_MMA, 1, 1);
+        constexpr uint32_t idesc_t = tc::make_idesc_tf32(128, 32, 1, 1);
+        // MN-major SWIZZLE_128B_BASE32B: next 32 floats of M/N one box further (LBO),
+        // 4-row K groups 512 B apart (SBO); one K = 8 MMA spans two such groups
+        constexpr uint32_t lbo = WT_CHUNK, sbo = 512u;
+        long long w_conv = 0, w_mma = 0;
+        const long long tstart = clock64();
+        const uint32_t s0 = tc::smem_u32(smem);
+        for (int it = 0; it < n_iters; ++it) {
+            const int st = it % WT_STAGES, u = it / WT_STAGES;
+            { WG_T0(); tc::mbar_wait(&bar_conv[st], u & 1); WG_ACC(w_conv); }
+            tc::tc_fence_after();
+            WG_T0();
+            if (wt_elect_one()) {
+                const uint32_t sa = s0 + (uint32_t)st * WT_STAGE_BYTES;
                 const uint32_t sb = sa + WT_A_BYTES, so = sb + WT_B_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < WT_RK / 8; ++ks) {
@@ -149,12 +167,13 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmap_dg, const __grid_constant__ 
                     }
                 }
                 tc::umma_commit(&bar_empty[st]);          // stage reusable once these MMAs have read it
-                WG_ACC(w_mma);
             }
-            tc::umma_commit(&bar_done);
-            WG_OUT(4, w_conv); WG_OUT(5, w_mma); WG_OUT(6, clock64() - tstart);
+            __syncwarp();
+            WG_ACC(w_mma);
         }
+        if (wt_elect_one()) tc::umma_commit(&bar_done);
         __syncwarp();
+        if (lane == 0) { WG_OUT(4, w_conv); WG_OUT(5, w_mma); WG_OUT(6, clock64() - tstart); }
     } else {
         // ---------------- conversion (in place), 256 threads = warps 0-3 and 6-9 (two warps per scheduler: the
         // single-warp version was latency-bound and paced the whole pipeline).  Converter ci -> 16-byte unit
