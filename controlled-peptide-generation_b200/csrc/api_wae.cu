@@ -233,10 +233,8 @@ static void forward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, cons
         launch_gru_fwd_enc(s, enc, B, L);
     }
     // q_mu / q_logvar heads (models/encoder.py:50-51)
-    launch_sgemm(s, B, ZD, 2 * ENC_H, 1.f, w.hfin, 2 * ENC_H, 1, params + lay.off[P_QMU_W], 1, 2 * ENC_H, 0.f,
-                 mu, ZD, params + lay.off[P_QMU_B], 1, nullptr);
-    launch_sgemm(s, B, ZD, 2 * ENC_H, 1.f, w.hfin, 2 * ENC_H, 1, params + lay.off[P_QLV_W], 1, 2 * ENC_H, 0.f,
-                 logvar, ZD, params + lay.off[P_QLV_B], 1, nullptr);
+    launch_sgemm_pair(s, B, ZD, 2 * ENC_H, 1.f, w.hfin, 2 * ENC_H, 1, params + lay.off[P_QMU_W], params + lay.off[P_QLV_W],
+                      1, 2 * ENC_H, mu, logvar, ZD, params + lay.off[P_QMU_B], params + lay.off[P_QLV_B]);
     if (encoder_only) return;
     launch_reparam(s, mu, logvar, in->eps, in->c, B, z, w.zc);
     if (mark_after_reparam) side_mark(ctx, s);      // mu, logvar, z are final: the loss statistics may start
@@ -310,8 +308,7 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     // heads
     const float* wmu = params + lay.off[P_QMU_W];
     const float* wlv = params + lay.off[P_QLV_W];
-    launch_sgemm(s, B, 2 * ENC_H, ZD, 1.f, w.dmu, ZD, 1, wmu, 2 * ENC_H, 1, 0.f, w.dhfin, 2 * ENC_H, nullptr, 1, nullptr);
-    launch_sgemm(s, B, 2 * ENC_H, ZD, 1.f, w.dlv, ZD, 1, wlv, 2 * ENC_H, 1, 1.f, w.dhfin, 2 * ENC_H, nullptr, 1, nullptr);
+    launch_sgemm_sum2(s, B, 2 * ENC_H, ZD, 1.f, w.dmu, w.dlv, ZD, 1, wmu, wlv, 2 * ENC_H, 1, 0.f, w.dhfin, 2 * ENC_H);
     // head weight / bias gradients: side stream (after the decoder weight gradients), under the encoder BPTT
     {
         cudaStream_t qs = s;
@@ -364,7 +361,15 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     ia.g_dec_wih = grads + lay.off[P_DEC_WIH]; ia.g_dec_bih = grads + lay.off[P_DEC_BIH];
     ia.g_dec_bhh = grads + lay.off[P_DEC_BHH];
     ia.V = V;
-    launch_input_grads(s, ia);
+    if (side) {                                     // the two input-side kernels are independent: run them side by side
+        side_mark(ctx, s, 0);
+        cudaStream_t qs = side_enter(ctx, 0);
+        launch_input_grads(s, ia, qs);
+        side_leave(ctx, 0);
+        side_join(ctx, s, 0);
+    } else {
+        launch_input_grads(s, ia);
+    }
 }
 
 static AdamHyper adam_hyper(const cpg_train_hparams* hp) {

@@ -128,11 +128,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+struct GemmSecond { const float* A; const float* B; const float* bias; float* C; int mode; };
+
 template <bool A_KFAST, bool B_KFAST>
 __global__ void __launch_bounds__(256)
 k_sgemm_pipe(int M, int N, int K, float alpha, const float* __restrict__ A, int64_t lda,
              const float* __restrict__ Bm, int64_t ldb, float beta, float* __restrict__ C, int64_t ldc,
-             const float* __restrict__ bias, int kchunk, float* __restrict__ ws) {
+             const float* __restrict__ bias, int kchunk, float* __restrict__ ws, GemmSecond sec) {
+    // second operand set (same shapes and strides): sec.mode 1 -> C = alpha (A B + A2 B2) + ..., one pass more over K;
+    // sec.mode 2 -> blockIdx.z == 1 computes the independent product C2 = alpha A2 B2 + bias2 (no split-K)
+    if (sec.mode == 2 && blockIdx.z == 1) { A = sec.A; Bm = sec.B; C = sec.C; bias = sec.bias; }
+    const int npass = sec.mode == 1 ? 2 : 1;
     // A_KFAST: A(m,k) = A[m*lda + k] -> As[m][k]   else A(m,k) = A[k*lda + m] -> As[k][m]
     // B_KFAST: B(k,n) = B[n*ldb + k] -> Bs[n][k]   else B(k,n) = B[k*ldb + n] -> Bs[k][n]
     constexpr int AROWS = A_KFAST ? PM : PK, ACOLS = (A_KFAST ? PK : PM) + PPAD;
@@ -142,7 +148,7 @@ k_sgemm_pipe(int M, int N, int K, float alpha, const float* __restrict__ A, int6
     const int tid = threadIdx.x;
     const int tx = tid % 16, ty = tid / 16;
     const int m0 = blockIdx.y * PM, n0 = blockIdx.x * PN;
-    const int kbeg = blockIdx.z * kchunk;
+    const int kbeg = sec.mode == 2 ? 0 : blockIdx.z * kchunk;
     const int kend = min(K, kbeg + kchunk);
     const int ntile = kend > kbeg ? (kend - kbeg + PK - 1) / PK : 0;
 
@@ -171,6 +177,12 @@ k_sgemm_pipe(int M, int N, int K, float alpha, const float* __restrict__ A, int6
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int pass = 0; pass < npass; ++pass) {
+    if (pass == 1) {
+        cp_async_wait<0>();
+        __syncthreads();                                       // every stage of the first pass consumed
+        A = sec.A; Bm = sec.B;
+    }
 #pragma unroll
     for (int t = 0; t < PST - 1; ++t) {
         if (t < ntile) issue(t);
@@ -210,7 +222,8 @@ k_sgemm_pipe(int M, int N, int K, float alpha, const float* __restrict__ A, int6
                     for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i][kk], b[j][kk], acc[i][j]);
         }
     }
-    const bool split = gridDim.z > 1;
+    }   // pass
+    const bool split = gridDim.z > 1 && sec.mode != 2;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int gm = m0 + ty * 4 + i;
@@ -244,9 +257,33 @@ __global__ void k_splitk_reduce(int M, int N, int splits, float alpha, const flo
     C[m * ldc + n] = v;
 }
 
+static void launch_sgemm_impl(cudaStream_t s, int M, int N, int K, float alpha, const float* A, int64_t sam, int64_t sak,
+                              const float* B, int64_t sbk, int64_t sbn, float beta, float* C, int64_t ldc,
+                              const float* bias, int split_k, float* ws, GemmSecond sec);
+
 void launch_sgemm(cudaStream_t s, int M, int N, int K, float alpha, const float* A, int64_t sam, int64_t sak,
                   const float* B, int64_t sbk, int64_t sbn, float beta, float* C, int64_t ldc,
                   const float* bias, int split_k, float* ws) {
+    GemmSecond none{nullptr, nullptr, nullptr, nullptr, 0};
+    launch_sgemm_impl(s, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc, bias, split_k, ws, none);
+}
+// C = alpha (A B + A2 B2) + beta C (+ bias): two products of equal shape and strides in one launch
+void launch_sgemm_sum2(cudaStream_t s, int M, int N, int K, float alpha, const float* A, const float* A2, int64_t sam, int64_t sak,
+                       const float* B, const float* B2, int64_t sbk, int64_t sbn, float beta, float* C, int64_t ldc) {
+    GemmSecond sec{A2, B2, nullptr, nullptr, 1};
+    launch_sgemm_impl(s, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc, nullptr, 1, nullptr, sec);
+}
+// C = alpha A B + bias and C2 = alpha A B2 + bias2 (shared A, equal shapes and strides) in one launch
+void launch_sgemm_pair(cudaStream_t s, int M, int N, int K, float alpha, const float* A, int64_t sam, int64_t sak,
+                       const float* B, const float* B2, int64_t sbk, int64_t sbn, float* C, float* C2, int64_t ldc,
+                       const float* bias, const float* bias2) {
+    GemmSecond sec{A, B2, bias2, C2, 2};
+    launch_sgemm_impl(s, M, N, K, alpha, A, sam, sak, B, sbk, sbn, 0.f, C, ldc, bias, 1, nullptr, sec);
+}
+
+static void launch_sgemm_impl(cudaStream_t s, int M, int N, int K, float alpha, const float* A, int64_t sam, int64_t sak,
+                              const float* B, int64_t sbk, int64_t sbn, float beta, float* C, int64_t ldc,
+                              const float* bias, int split_k, float* ws, GemmSecond sec) {
     if (split_k < 1 || ws == nullptr) split_k = 1;
     int kchunk = ceil_div(ceil_div(K, split_k), GK) * GK;
     split_k = ceil_div(K, kchunk);
@@ -254,10 +291,19 @@ void launch_sgemm(cudaStream_t s, int M, int N, int K, float alpha, const float*
     const bool a_k = sak == 1, a_m = sam == 1, b_k = sbk == 1, b_n = sbn == 1;
     const int64_t lda = a_k ? sam : sak, ldb = b_k ? sbn : sbk;
     const bool aligned = (a_k || a_m) && (b_k || b_n) && lda % 4 == 0 && ldb % 4 == 0 &&
-                         ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0;
+                         ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 &&
+                         (sec.mode == 0 || (((uintptr_t)sec.A & 15) == 0 && ((uintptr_t)sec.B & 15) == 0));
+    if (!aligned && sec.mode != 0) {
+        // unaligned operands: two plain launches with the same meaning
+        GemmSecond none{nullptr, nullptr, nullptr, nullptr, 0};
+        launch_sgemm_impl(s, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc, bias, 1, nullptr, none);
+        if (sec.mode == 1) launch_sgemm_impl(s, M, N, K, alpha, sec.A, sam, sak, sec.B, sbk, sbn, 1.f, C, ldc, nullptr, 1, nullptr, none);
+        else launch_sgemm_impl(s, M, N, K, alpha, sec.A, sam, sak, sec.B, sbk, sbn, 0.f, sec.C, ldc, sec.bias, 1, nullptr, none);
+        return;
+    }
     if (aligned) {
-        dim3 grid(ceil_div(N, PN), ceil_div(M, PM), split_k);
-#define CPG_PIPE(AK, BK) CPG_LAUNCH_NAMED("k_sgemm", (k_sgemm_pipe<AK, BK>), grid, 256, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, kchunk, ws)
+        dim3 grid(ceil_div(N, PN), ceil_div(M, PM), sec.mode == 2 ? 2 : split_k);
+#define CPG_PIPE(AK, BK) CPG_LAUNCH_NAMED("k_sgemm", (k_sgemm_pipe<AK, BK>), grid, 256, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, kchunk, ws, sec)
         if (a_k && !b_k) CPG_PIPE(true, false);
         else if (a_k && b_k) CPG_PIPE(true, true);
         else if (!a_k && !b_k) CPG_PIPE(false, false);

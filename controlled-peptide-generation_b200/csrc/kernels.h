@@ -82,6 +82,13 @@ extern int g_opt_side_stream;
 void launch_sgemm(cudaStream_t s, int M, int N, int K, float alpha, const float* A, int64_t sam, int64_t sak,
                   const float* B, int64_t sbk, int64_t sbn, float beta, float* C, int64_t ldc,
                   const float* bias, int split_k, float* ws);
+// C = alpha (A B + A2 B2) + beta C: two products of equal shape / strides accumulated in one launch
+void launch_sgemm_sum2(cudaStream_t s, int M, int N, int K, float alpha, const float* A, const float* A2, int64_t sam, int64_t sak,
+                       const float* B, const float* B2, int64_t sbk, int64_t sbn, float beta, float* C, int64_t ldc);
+// C = alpha A B + bias and C2 = alpha A B2 + bias2 (shared A) in one launch
+void launch_sgemm_pair(cudaStream_t s, int M, int N, int K, float alpha, const float* A, int64_t sam, int64_t sak,
+                       const float* B, const float* B2, int64_t sbk, int64_t sbn, float* C, float* C2, int64_t ldc,
+                       const float* bias, const float* bias2);
 // out[n] = sum_m A[m*lda + n], deterministic two-stage
 void launch_colsum(cudaStream_t s, const float* A, int M, int N, int64_t lda, float* out, float* ws, int nchunk);
 

@@ -267,9 +267,9 @@ __global__ void k_emb_grad(InputGradArgs a) {
         a.g_emb[i] = s;
     }
 }
-void launch_input_grads(cudaStream_t s, const InputGradArgs& a) {
+void launch_input_grads(cudaStream_t s, const InputGradArgs& a, cudaStream_t s_emb) {
     CPG_LAUNCH(k_input_grads, dim3(32, 3), 256, 0, s, a);
-    CPG_LAUNCH(k_emb_grad, CPG_RED_GRID(a.V * EMB), CPG_RED_BLOCK, 0, s, a);
+    CPG_LAUNCH(k_emb_grad, CPG_RED_GRID(a.V * EMB), CPG_RED_BLOCK, 0, s_emb ? s_emb : s, a);   // independent of the kernel above
 }
 
 }  // namespace cpg
