@@ -161,7 +161,7 @@ def run_ours(args):
         it = counter['it']
         counter['it'] += 1
         hp.beta = float(ow.anneal_beta(it))
-        engine.fill_step_noise(noise, seed, it)
+        engine.fill_step_noise(noise, seed, it, overlap=True)      # next reader is the train step below
         if world > 1:
             return parallel.dp_train_step(st, tokens, noise, hp, global_batch=gb)
         return engine.train_step(st, tokens, noise, hp)[0]

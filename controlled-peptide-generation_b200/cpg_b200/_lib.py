@@ -82,6 +82,7 @@ def _signatures(L):
         'cpg_mmd_full': (I, [P, P, P, P, I, F, P]),
         'cpg_mmd_rf': (I, [P, P, P, P, P, P, I, I, F, P, P]),
         'cpg_fill_step_noise': (I, [P, P, c_uint64, c_uint32, I, I, F, F, P, P, P, P, P, P]),
+        'cpg_fill_step_noise_overlapped': (I, [P, P, c_uint64, c_uint32, I, I, F, F, P, P, P, P, P, P]),
         'cpg_fill_normal': (I, [P, P, c_uint64, c_uint32, I64, P]),
         'cpg_fill_uniform': (I, [P, P, c_uint64, c_uint32, F, I64, P]),
         'cpg_beam_decode': (I, [P, P, P, I, I, I, P, P, I, I, P, P, P]),

@@ -240,11 +240,14 @@ def mmd_rf(z, z_prior, rf_w, rf_b, sigma, want_grad=False):
 
 
 # ------------------------------------------------------------------ perf-mode noise + trainer
-def fill_step_noise(noise, seed, step, p_word=0.3, p_out=0.3):
-    """Regenerate the per-iteration noise tensors in place (Philox; pure function of seed/step)."""
+def fill_step_noise(noise, seed, step, p_word=0.3, p_out=0.3, overlap=False):
+    """Regenerate the per-iteration noise tensors in place (Philox; pure function of seed/step).
+    overlap=True: the late-use tensors (z_prior x2, out-dropout mask) are generated on the library's side stream
+    and joined inside the train-step entry points -- only when the next reader IS a train step."""
     B, L = noise['word_drop'].shape
     dev = noise['eps'].device
-    check(lib().cpg_fill_step_noise(context(dev), stream_ptr(), int(seed), int(step), B, L, float(p_word),
+    fn = lib().cpg_fill_step_noise_overlapped if overlap else lib().cpg_fill_step_noise
+    check(fn(context(dev), stream_ptr(), int(seed), int(step), B, L, float(p_word),
                                     float(p_out), ptr(noise['eps']), ptr(noise['c']), ptr(noise['word_drop']),
                                     ptr(noise['out_keep']), ptr(noise.get('z_prior_full')),
                                     ptr(noise['z_prior_rf'])), 'cpg_fill_step_noise')
@@ -309,8 +312,8 @@ class FusedStepper:
             self._tokens = tokens
             self._inp = _inputs(tokens, n['eps'], n['c'], n['word_drop'], n['out_keep'], self.p_out)
         s = stream_ptr()
-        check(self.lib.cpg_fill_step_noise(self.ctx, s, self.seed, int(it), self.B, self.L, self.p_word, self.p_out,
-                                           *self._noise_args), 'cpg_fill_step_noise')
+        check(self.lib.cpg_fill_step_noise_overlapped(self.ctx, s, self.seed, int(it), self.B, self.L, self.p_word,
+                                                      self.p_out, *self._noise_args), 'cpg_fill_step_noise_overlapped')
         st.step += 1
         hp.adam_step = st.step
         hp.beta = float(beta)

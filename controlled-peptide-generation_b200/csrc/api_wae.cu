@@ -174,12 +174,12 @@ static bool side_ready(cpg_ctx* ctx) {
     if (!g_opt_side_stream) return false;
     if (ctx->side_stream == nullptr) {
         cudaStream_t q;
-        cudaEvent_t e[4];
+        cudaEvent_t e[6];
         bool ok = cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking) == cudaSuccess;
-        for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { cudaGetLastError(); return false; }
         ctx->side_stream = q;
-        ctx->ev_fork[0] = e[0]; ctx->ev_join[0] = e[1]; ctx->ev_fork[1] = e[2]; ctx->ev_join[1] = e[3];
+        for (int k = 0; k < 3; ++k) { ctx->ev_fork[k] = e[2 * k]; ctx->ev_join[k] = e[2 * k + 1]; }
     }
     return true;
 }
@@ -439,7 +439,7 @@ int cpg_destroy(cpg_ctx* c) {
     if (c->side_stream) {
         cudaStreamSynchronize((cudaStream_t)c->side_stream);
         cudaStreamDestroy((cudaStream_t)c->side_stream);
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < 3; ++k) {
             cudaEventDestroy((cudaEvent_t)c->ev_fork[k]);
             cudaEventDestroy((cudaEvent_t)c->ev_join[k]);
         }
@@ -490,6 +490,7 @@ int cpg_wae_forward(cpg_ctx* ctx, cpg_stream stream, const float* params, int V,
     if (!ctx || !params || !in || !in->tokens || !in->c) { set_error("cpg_wae_forward: null argument"); return CPG_EINVAL; }
     if (in->out_keep && !(in->p_out_dropout >= 0.f && in->p_out_dropout < 1.f)) { set_error("p_out_dropout must be in [0,1)"); return CPG_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
+    side_join(ctx, s, 2);                           // late noise of cpg_fill_step_noise_overlapped, if any
     if ((rc = ensure_workspace(ctx, B, L, V, ctx->ws.R > 0 ? ctx->ws.R : 500, s))) return rc;
     Workspace& w = ctx->ws;
     ParamLayout lay = make_layout(V);
@@ -518,6 +519,7 @@ int cpg_wae_backward(cpg_ctx* ctx, cpg_stream stream, const float* params, int V
         return CPG_EINVAL;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    side_join(ctx, s, 2);
     ParamLayout lay = make_layout(V);
     dev_memset(grads, 0, (size_t)lay.total * 4, s);
     DecOutArgs a = dec_out_args(ctx, in, V, B, L);
@@ -532,6 +534,27 @@ int cpg_wae_backward(cpg_ctx* ctx, cpg_stream stream, const float* params, int V
     la.B_global = B;
     backward_impl(ctx, s, params, lay, grads, V, B, L, in, la);
     return check_launch("cpg_wae_backward");
+}
+
+int cpg_fill_step_noise_overlapped(cpg_ctx* ctx, cpg_stream stream, uint64_t seed, uint32_t step, int B, int L, float p_word,
+                                   float p_out, float* eps, float* c, uint8_t* word_drop, uint8_t* out_keep,
+                                   float* z_prior_full, float* z_prior_rf) {
+    if (!ctx || B < 1 || L < 1) { set_error("cpg_fill_step_noise_overlapped: bad argument"); return CPG_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    StepNoiseArgs a;
+    a.seed = seed; a.step = step; a.B = B; a.L = L; a.p_word = p_word; a.p_out = p_out;
+    a.eps = eps; a.c = c; a.word_drop = word_drop; a.out_keep = out_keep; a.zp_full = z_prior_full; a.zp_rf = z_prior_rf;
+    if (!side_ready(ctx)) {
+        launch_step_noise(s, a, 3);
+        return check_launch("cpg_fill_step_noise_overlapped");
+    }
+    side_join(ctx, s, 2);                           // a previous late part nobody consumed yet
+    side_mark(ctx, s, 2);                           // earlier readers of these buffers (previous iteration) are on `s`
+    cudaStream_t q = side_enter(ctx, 2);
+    launch_step_noise(q, a, 2);                     // z_prior x2 + out-dropout mask: under prep / encoder recurrence
+    side_leave(ctx, 2);
+    launch_step_noise(s, a, 1);                     // eps, c, word dropout: needed right away
+    return check_launch("cpg_fill_step_noise_overlapped");
 }
 
 int64_t cpg_coupled_count(int rf_dim) { return 8 + 2 * (int64_t)rf_dim; }
@@ -611,6 +634,7 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
     a.fused_ce = 1;
     a.logits_out = logits;
     a.dh_out = w.dec_dh_out;
+    side_join(ctx, s, 2);                           // out-dropout mask generated on the side stream
     launch_dec_out(s, a, ctx->sm_count);
     launch_dec_out_reduce(s, a, ctx->sm_count, grads + lay.off[P_FC_W], grads + lay.off[P_FC_B], w.nll_sum);
     LatentBwdArgs la;

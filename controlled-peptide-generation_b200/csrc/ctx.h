@@ -43,9 +43,9 @@ struct cpg_ctx {
     // side stream for the latency-bound loss kernels that only depend on (mu, logvar, z): they run under the
     // decoder recurrence / decoder-output kernels of the main stream (fork / join with events; api_wae.cu)
     void* side_stream = nullptr;
-    void* ev_fork[2] = {nullptr, nullptr};          // [0] loss kernels, [1] decoder weight gradients
-    void* ev_join[2] = {nullptr, nullptr};
-    bool join_pending[2] = {false, false};
+    void* ev_fork[3] = {nullptr, nullptr, nullptr};  // [0] loss kernels, [1] decoder weight gradients, [2] late noise
+    void* ev_join[3] = {nullptr, nullptr, nullptr};
+    bool join_pending[3] = {false, false, false};
 };
 
 namespace cpg {

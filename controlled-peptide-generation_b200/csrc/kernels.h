@@ -60,6 +60,15 @@ struct GruSeq {            // one recurrence (a direction of the encoder, or the
     float* drow;           // [B][3*HP] sum over steps of (dr_pre,dz_pre,dn_pre), or null
 };
 
+// per-iteration noise (noise.cu); part bit 0 = eps / c / word dropout, bit 1 = z_prior x2 / out-dropout mask
+struct StepNoiseArgs {
+    uint64_t seed; uint32_t step;
+    int B, L;
+    float p_word, p_out;
+    float* eps; float* c; uint8_t* word_drop; uint8_t* out_keep; float* zp_full; float* zp_rf;
+};
+void launch_step_noise(cudaStream_t s, const StepNoiseArgs& a, int part);
+
 void launch_prep_tokens(cudaStream_t s, const int64_t* tokens, const uint8_t* word_drop, int B, int L, int V,
                         uint8_t* tok, uint8_t* tokd, uint8_t* tgt, int* ntok, int* err);
 void launch_prep_weights(cudaStream_t s, const float* params, const ParamLayout& lay, int V, const Derived& d);

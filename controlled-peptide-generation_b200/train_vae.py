@@ -84,7 +84,7 @@ def _train_fused(cfgv, model, dataset):
         hp.compute_full_mmd = 1 if (it % every == 0 or log_it) else 0
         if distributed:
             hp.beta = beta
-            engine.fill_step_noise(stepper.noise, rank_seed, it, p_word, p_out)
+            engine.fill_step_noise(stepper.noise, rank_seed, it, p_word, p_out, overlap=True)
             scal = parallel.dp_train_step(st, tok, stepper.noise, hp, p_out=p_out, global_batch=global_batch)
         else:
             scal = stepper.step(tok, it, beta)

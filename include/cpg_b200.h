@@ -181,6 +181,13 @@ int cpg_mmd_rf(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* z_p
 int cpg_fill_step_noise(cpg_ctx* ctx, cpg_stream stream, uint64_t seed, uint32_t step, int B, int L, float p_word,
                         float p_out, float* eps, float* c, uint8_t* word_drop, uint8_t* out_keep,
                         float* z_prior_full, float* z_prior_rf);
+/* Same tensors, same values; the parts the step only needs late (z_prior x2, out-dropout mask) are generated on the
+ * context's side stream and joined inside the cpg_wae_* entry points that consume them.  ONLY for callers whose
+ * next use of these buffers is cpg_wae_step_phase1/2, cpg_wae_train_step, cpg_wae_forward or cpg_wae_backward on
+ * the same context and stream (anything else must use cpg_fill_step_noise). */
+int cpg_fill_step_noise_overlapped(cpg_ctx* ctx, cpg_stream stream, uint64_t seed, uint32_t step, int B, int L,
+                                   float p_word, float p_out, float* eps, float* c, uint8_t* word_drop,
+                                   uint8_t* out_keep, float* z_prior_full, float* z_prior_rf);
 /* N(0,1) / U[0,1)*scale fills, e.g. rf_w = randn(100,R), rf_b = 2*pi*rand(R) (losses.py:75-76) */
 int cpg_fill_normal(cpg_ctx* ctx, cpg_stream stream, uint64_t seed, uint32_t stream_id, int64_t n, float* out);
 int cpg_fill_uniform(cpg_ctx* ctx, cpg_stream stream, uint64_t seed, uint32_t stream_id, float scale, int64_t n,
@@ -234,7 +241,14 @@ int cpg_gmm_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, c
 int cpg_prior_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, double* out);
 
 /* ---- options ------------------------------------------------------------------------------------
- * "mmd_tensor_core" (default 1): full-kernel MMD Gram tiles on tcgen05 (tf32) instead of the fp32 SIMT kernel. */
+ * Which flavour of a kernel runs (the defaults pick the tcgen05 paths where the batch is large enough to
+ * fill the chip; the fp32 SIMT kernels stay for small batches and are what the parity tests compare with):
+ *   "mmd_tensor_core"     1 (default) persistent tcgen05 Gram kernel (tf32), 3 one tile per CTA, 0 fp32 SIMT
+ *   "wgrad_tensor_core"   1 (default) tf32 tcgen05 weight / token-table gradients when B*L >= 8192, 2 always, 0 never
+ *   "gru_tensor_core"     1 (default) split-bf16 tcgen05 recurrences (forward + BPTT) when B >= 1024, 2 always, 0 never
+ *   "dec_out_tensor_core" 1 (default) tcgen05 decoder-output layer when B*L >= 8192, 2 always, 0 never
+ *   "side_stream"         1 (default) loss / weight-gradient kernels overlap the recurrences on an internal stream
+ *                         (event fork/join inside each call; results identical), 0 everything on the caller's stream */
 int cpg_set_option(const char* name, int value);
 
 /* ---- per-kernel timing (CUDA events on the launching stream; off by default) ------------------ */

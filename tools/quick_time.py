@@ -16,7 +16,7 @@ noise = engine.alloc_noise(B, L, dev)
 hp = engine.make_hparams()
 SIDE = int(sys.argv[2]) if len(sys.argv) > 2 else 1      # 0: everything on one stream (per-kernel times are then each kernel's own)
 def step(i):
-    engine.fill_step_noise(noise, 1238, i)
+    engine.fill_step_noise(noise, 1238, i, overlap=True)
     return engine.train_step(st, tokens, noise, hp)
 for i in range(3): step(i)
 torch.cuda.synchronize()
