@@ -166,6 +166,15 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                  ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
 }
 
+// 1-D bulk copy shared -> global through the TMA engine (bulk async-group completion)
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(tc::smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Gate stash (r, z, n, hn) private to this file's forward/backward pair: 32-row tiles, step-major inside a
 // tile, [tile][step][plane][row in tile][HP] -- a chain streams through one contiguous region (whole DRAM
 // pages per step) instead of 320-byte pieces 8 KB apart as in the row-major [B][L][4][HP] of the SIMT kernels.
@@ -208,8 +217,12 @@ struct FwdCfg {
     static_assert(HP % 8 == 0 && KP % 16 == 0 && G3 % 8 == 0 && (NB == 16 || NB == 32), "geometry");
     static size_t smem_bytes(int V, int L) {
         return (size_t)NCH * 2 * X_SPLIT + (size_t)NCH * P_FLOATS * 4 + (DEC ? 0 : (size_t)V * G3 * 4) +
-               (size_t)NCH * NB * L + 128;
+               (((size_t)NCH * NB * L + 15) & ~(size_t)15) + (STAGE_G ? (size_t)NCH * 4 * G_PLANE : 0) + 128;
     }
+    static constexpr int G_PLANE = NB * HP * 4;             // bytes of one gate plane of one chain and step (staging)
+    // gate planes through a shared-memory staging tile + TMA bulk stores (measured: decoder 80 -> 72 us; the encoder's
+    // 40 KB per chain-step read-out would sit on the MMA completion signal, 110 -> 118 us, so it stores directly)
+    static constexpr bool STAGE_G = DEC;
 };
 
 struct FwdArgs {
@@ -234,6 +247,7 @@ k_gru_fwd_tc(FwdArgs a) {
     float* Pb = reinterpret_cast<float*>(Xb + NCH * 2 * C::X_SPLIT);     // [NCH][NB][G3]
     float* tab = Pb + NCH * C::P_FLOATS;                                 // encoder: [V][G3]
     uint8_t* toks = reinterpret_cast<uint8_t*>(tab + (C::DEC ? 0 : a.V * G3));   // [NCH*NB][L]
+    float* Gs = reinterpret_cast<float*>(toks + ((NCH * NB * a.L + 15) & ~15));     // [NCH][4 planes][NB][HP]: gate stash staging
     __shared__ __align__(8) uint64_t bar_x[NCH], bar_d[NCH];
     __shared__ uint32_t tmem_slot;
 
@@ -332,6 +346,18 @@ k_gru_fwd_tc(FwdArgs a) {
         // start the chains half a step apart: the SFU-bound gate math of one then runs under the MMA / TMEM
         // read-out of the other instead of both phases coinciding
         if (ch > 0) __nanosleep(CPG_CHAIN_SKEW_NS);
+        // gate planes of a finished step leave through the TMA engine: the epilogue only writes them to the staging
+        // tile in shared memory (its arrival on bar_x says they are there), this lane streams the four 10 KB planes out
+        float* gates_dst = (dir ? a.gates[1] : a.gates[0]);
+        const float* Gch = Gs + ch * 4 * NB * HP;
+        auto store_gates = [&](int s_done) {
+            if (!C::STAGE_G || gates_dst == nullptr || row0 + ch * NB >= B) return;   // no stash wanted / chain entirely past the batch
+#pragma unroll
+            for (int pl = 0; pl < 4; ++pl)
+                bulk_store(gates_dst + gate_stash_offset<HP>(row0 + ch * NB, s_done, L) + (size_t)pl * 32 * HP,
+                           Gch + pl * NB * HP, C::G_PLANE);
+            bulk_commit();
+        };
         for (int s = 0; s < L; ++s) {
             if (s > 0) {
                 tc::mbar_wait(&bar_x[ch], (s - 1) & 1);
@@ -339,6 +365,7 @@ k_gru_fwd_tc(FwdArgs a) {
             }
             if (elect_one()) {
                 CPG_TL(0 + ch);
+                if (s > 0) store_gates(s - 1);
 #pragma unroll
                 for (int t = 0; t < MT; ++t) {
                     uint32_t acc = 0;
@@ -353,16 +380,26 @@ k_gru_fwd_tc(FwdArgs a) {
                         }
                     }
                 }
+                // the staging tile is rewritten by the gate math that follows these MMAs: its read-out must be over
+                // before their completion is signalled (it runs under the MMAs, so this does not add latency)
+                if (C::STAGE_G && s > 0) bulk_wait_read();
                 tc::umma_commit(&bar_d[ch]);
             }
             __syncwarp();
         }
+        tc::mbar_wait(&bar_x[ch], (L - 1) & 1);
+        if (elect_one()) {
+            store_gates(L - 1);
+            bulk_wait_all();
+        }
+        __syncwarp();
     } else {
         // ---------------- epilogue of chain ch
         const int ch = warp / C::NWG, wl = warp % C::NWG, tl = tid - ch * C::NT_G;
         unsigned char* X0 = Xb + (ch * 2 + 0) * C::X_SPLIT;
         unsigned char* X1 = Xb + (ch * 2 + 1) * C::X_SPLIT;
         float* P = Pb + ch * C::P_FLOATS;
+        float* Gch = Gs + ch * 4 * NB * HP;
         const uint8_t* tks = toks + ch * NB * L;
         const uint32_t d0 = tmem_d + (uint32_t)(ch * MT * NB);
         const int rowc0 = row0 + ch * NB;
@@ -463,10 +500,17 @@ k_gru_fwd_tc(FwdArgs a) {
                 const int off = (j0 >> 3) * C::X_LBO + (b >> 3) * X_SBO + (b & 7) * 16 + (j0 & 7) * 2;
                 *reinterpret_cast<uint2*>(X0 + off) = hi;
                 *reinterpret_cast<uint2*>(X1 + off) = lo;
+                if (C::STAGE_G && gates_g != nullptr) {          // staging tile [plane][row in chain][HP] (linear: conflict-free)
+                    float* g = Gch + b * HP + j0;
+                    st4(g, make_float4(rr[0], rr[1], rr[2], rr[3]));
+                    st4(g + NB * HP, make_float4(zz[0], zz[1], zz[2], zz[3]));
+                    st4(g + 2 * NB * HP, make_float4(nn[0], nn[1], nn[2], nn[3]));
+                    st4(g + 3 * NB * HP, make_float4(hh[0], hh[1], hh[2], hh[3]));
+                }
                 if (row < B) {
                     const size_t bs = (size_t)row * L + s;
                     if (hs_g != nullptr) st4(hs_g + bs * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
-                    if (gates_g != nullptr) {
+                    if (!C::STAGE_G && gates_g != nullptr) {
                         float* g = gates_g + gate_stash_offset<HP>(row, s, L) + j0;
                         st4(g, make_float4(rr[0], rr[1], rr[2], rr[3]));
                         st4(g + 32 * HP, make_float4(zz[0], zz[1], zz[2], zz[3]));
