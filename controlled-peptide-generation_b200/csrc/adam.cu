@@ -50,10 +50,29 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
     p = p - st.step_size * (m / denom);                  // addcdiv_(exp_avg, denom, value=-step_size)
 }
 
-__global__ void k_clip_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            int64_t n, int64_t dup_off, int64_t dup_n, const float* __restrict__ coef_ptr,
-                            AdamHyper h) {
-    const float coef = *coef_ptr;
+// The total norm is finished here, by every block on its own (the same ordered sum of the same partials: identical
+// in every block and run to run), instead of in a one-thread kernel between the two passes.
+__global__ void __launch_bounds__(NORM_THREADS)
+k_clip_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            int64_t n, int64_t dup_off, int64_t dup_n, const float* __restrict__ part, int nparts, float max_norm,
+            float* __restrict__ norm_out, float* __restrict__ coef_out, AdamHyper h) {
+    __shared__ float coef_s;
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nparts; i += 32) s += (double)part[i];
+        s = warp_sum(s);
+        if (threadIdx.x == 0) {
+            const float total = (float)sqrt(s);
+            const float c = max_norm / (total + 1e-6f);           // torch: clamp(max_norm / (total + 1e-6), max=1)
+            coef_s = c < 1.0f ? c : 1.0f;
+            if (blockIdx.x == 0) {
+                if (norm_out != nullptr) *norm_out = total;
+                if (coef_out != nullptr) *coef_out = coef_s;
+            }
+        }
+    }
+    __syncthreads();
+    const float coef = coef_s;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const bool dup = (i >= dup_off && i < dup_off + dup_n);
         float gi = g[i] * coef;
@@ -83,10 +102,14 @@ void launch_grad_norm(cudaStream_t s, const float* g, int64_t n, int64_t dup_off
     CPG_LAUNCH(k_norm_final, 1, 32, 0, s, part, parts, max_norm, norm_out, coef_out);
 }
 
-void launch_clip_adam(cudaStream_t s, float* p, float* g, float* m, float* v, int64_t n, int64_t dup_off,
-                      int64_t dup_n, const float* coef, const AdamHyper& h, int sm_count) {
+// sum-of-squares partials + (norm, clip, Adam) in two launches
+void launch_clip_adam_fused(cudaStream_t s, float* p, float* g, float* m, float* v, int64_t n, int64_t dup_off,
+                            int64_t dup_n, float max_norm, float* part, float* norm_out, float* coef_out,
+                            const AdamHyper& h, int sm_count) {
     int parts = adam_norm_parts(n, sm_count);
-    CPG_LAUNCH(k_clip_adam, parts, NORM_THREADS, 0, s, p, g, m, v, n, dup_off, dup_n, coef, h);
+    CPG_LAUNCH(k_sumsq_partial, parts, NORM_THREADS, 0, s, g, n, dup_off, dup_n, part);
+    CPG_LAUNCH(k_clip_adam, parts, NORM_THREADS, 0, s, p, g, m, v, n, dup_off, dup_n, part, parts, max_norm, norm_out,
+               coef_out, h);
 }
 
 }  // namespace cpg

@@ -668,10 +668,8 @@ int cpg_clip_adam_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* gr
     if (ctx->base == nullptr && (rc = ensure_workspace(ctx, 1, 2, V, 500, s))) return rc;
     Workspace& w = ctx->ws;
     ParamLayout lay = make_layout(V);
-    launch_grad_norm(s, grads, lay.total, lay.off[P_EMB], lay.size[P_EMB], hp->clip_norm, ctx->sm_count, w.norm_part,
-                     grad_norm_out, w.clip_coef);
-    launch_clip_adam(s, params, grads, m, v, lay.total, lay.off[P_EMB], lay.size[P_EMB], w.clip_coef, adam_hyper(hp),
-                     ctx->sm_count);
+    launch_clip_adam_fused(s, params, grads, m, v, lay.total, lay.off[P_EMB], lay.size[P_EMB], hp->clip_norm, w.norm_part,
+                           grad_norm_out, w.clip_coef, adam_hyper(hp), ctx->sm_count);
     return check_launch("cpg_clip_adam_step");
 }
 

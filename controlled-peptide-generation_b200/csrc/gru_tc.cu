@@ -34,7 +34,7 @@
 #define CPG_ENC_FWD_NWG 10
 #endif
 #ifndef CPG_ENC_BWD_NWG
-#define CPG_ENC_BWD_NWG 7
+#define CPG_ENC_BWD_NWG 10
 #endif
 
 #ifdef CPG_GRU_TIMELINE

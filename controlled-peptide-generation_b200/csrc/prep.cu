@@ -89,32 +89,40 @@ __global__ void k_prep_weights(PrepArgs a) {
     const int stride = gridDim.x * blockDim.x;
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int V = a.V;
+    // token tables: one warp per output, lanes over the 150 embedding columns (both operands read coalesced; the
+    // one-thread-per-output version walked W_ih rows with a 600-byte stride and took 22 us for 3 MFLOP)
+    const int lane = threadIdx.x & 31;
+    const int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = stride >> 5;
     if (task < 2) {                     // encoder token tables
         const int d = task, G = 3 * ENC_H;
-        for (int i = t0; i < V * G; i += stride) {
+        for (int i = warp_g; i < V * G; i += nwarp) {
             int v = i / G, g = i % G;
             const float* e = a.emb + (size_t)v * EMB;
             const float* w = a.enc_wih[d] + (size_t)g * EMB;
             float acc = 0.f;
-            for (int k = 0; k < EMB; ++k) acc = fmaf(e[k], w[k], acc);
-            acc += a.enc_bih[d][g];
-            if (g < 2 * ENC_H) acc += a.enc_bhh[d][g];      // b_hr, b_hz fold into the table; b_hn cannot
-            a.d.t_enc[d][i] = acc;
+            for (int k = lane; k < EMB; k += 32) acc = fmaf(e[k], w[k], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                acc += a.enc_bih[d][g];
+                if (g < 2 * ENC_H) acc += a.enc_bhh[d][g];      // b_hr, b_hz fold into the table; b_hn cannot
+                a.d.t_enc[d][i] = acc;
+            }
         }
     } else if (task == 2) {             // decoder token table (embedding columns of W_ih only)
         const int G = 3 * DEC_HP;
-        for (int i = t0; i < V * G; i += stride) {
+        for (int i = warp_g; i < V * G; i += nwarp) {
             int v = i / G, gp = i % G, gate = gp / DEC_HP, j = gp % DEC_HP;
             float acc = 0.f;
             if (j < DEC_H) {
                 int g = gate * DEC_H + j;
                 const float* e = a.emb + (size_t)v * EMB;
                 const float* w = a.dec_wih + (size_t)g * DEC_IN;
-                for (int k = 0; k < EMB; ++k) acc = fmaf(e[k], w[k], acc);
+                for (int k = lane; k < EMB; k += 32) acc = fmaf(e[k], w[k], acc);
+                acc = warp_sum(acc);
                 acc += a.dec_bih[g];
                 if (gate < 2) acc += a.dec_bhh[g];
             }
-            a.d.t_dec[i] = acc;
+            if (lane == 0) a.d.t_dec[i] = acc;
         }
     } else if (task < 5) {              // encoder W_hh^T  [k][g]
         const int d = task - 3, G = 3 * ENC_H;
@@ -163,7 +171,7 @@ void launch_prep_weights(cudaStream_t s, const float* p, const ParamLayout& l, i
     a.fc_w = p + l.off[P_FC_W]; a.fc_b = p + l.off[P_FC_B];
     a.d = d;
     a.V = V;
-    CPG_LAUNCH(k_prep_weights, dim3(24, 8), 256, 0, s, a);
+    CPG_LAUNCH(k_prep_weights, dim3(120, 8), 256, 0, s, a);      // 960 warps per table task: ~8 outputs per warp
 }
 
 }  // namespace cpg
