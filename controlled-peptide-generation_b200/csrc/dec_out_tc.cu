@@ -20,6 +20,15 @@
 #include <cuda_bf16.h>
 #include "tc_common.cuh"
 
+#ifdef CPG_GRU_TIMELINE
+// developer-only probe: cycles thread 0 of CTA 0 spends in each phase (includes the waits at the phase's barrier)
+__device__ long long g_do_tl[16];
+extern "C" int cpg_debug_dec_out_timeline(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_do_tl, sizeof(g_do_tl)); }
+#define DO_MARK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long _n = clock64(); g_do_acc[slot] += _n - g_do_last; g_do_last = _n; } } while (0)
+#else
+#define DO_MARK(slot) do { } while (0)
+#endif
+
 namespace cpg {
 
 namespace {
@@ -69,6 +78,7 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
     hi = *reinterpret_cast<const uint32_t*>(&h);
@@ -98,6 +108,18 @@ __device__ __forceinline__ void mma_terms(uint32_t tmem_d, uint32_t a0, int a_sp
             acc = 1;
         }
 }
+__device__ __forceinline__ void tmem_ld_16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 // three-product split-bf16 contraction over `ksteps` K slices of 16: A and B tiles with their two terms
 // `a_split` / `b_split` bytes apart
 __device__ __forceinline__ void mma_split3(uint32_t tmem_d, uint32_t a0, int a_split, int a_lbo, uint32_t b0, int b_split, int b_lbo,
@@ -126,8 +148,9 @@ k_dec_out_tc(DecOutArgs a) {
     unsigned char* keep_s = smem + OFF_KEEP;
     __shared__ __align__(8) uint64_t bar_m;
     __shared__ uint32_t tmem_slot;
-    __shared__ float red_b[4][VMAX];
+    __shared__ float red_b[8][VMAX / 2];
     __shared__ float red_n[4];
+    __shared__ float ex_s[3][2][TR];                           // row max / sum / target logit of each class half
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int V = a.V;
@@ -175,16 +198,21 @@ k_dec_out_tc(DecOutArgs a) {
     // epilogue threads (warps 0-3): thread = row of the tile = TMEM lane
     const int rl = tid;                                        // valid for tid < 128
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float accb[VMAX];
+    float accb[VMAX / 2];                                      // db partial of this thread's half of the classes
 #pragma unroll
-    for (int v = 0; v < VMAX; ++v) accb[v] = 0.f;
+    for (int v = 0; v < VMAX / 2; ++v) accb[v] = 0.f;
     float accn = 0.f;
     uint32_t mphase = 0;
     bool dw_started = false;
 
+#ifdef CPG_GRU_TIMELINE
+    long long g_do_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long g_do_last = clock64();
+#endif
     const int ntiles = ceil_div(nrows, TR);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int row0 = tile * TR;
+        DO_MARK(7);
         // ---- S1) hd = h * keep * scale -> HD (K-major, two bf16 terms) + keep bytes; coalesced over (row, quad)
         {
             constexpr int NIT = TR * NF4 / NTH;                  // 13 (row, quad) items per thread, exactly
@@ -235,6 +263,7 @@ k_dec_out_tc(DecOutArgs a) {
             }
         }
         __syncthreads();
+        DO_MARK(0);
         // ---- S2) transposed copy HD -> HDT (lanes along rows: conflict-free 2-byte stores)
         if (want_grad) {
             for (int idx = tid; idx < TR * (DEC_HP / 8); idx += NTH) {
@@ -255,6 +284,7 @@ k_dec_out_tc(DecOutArgs a) {
         }
         tc::fence_proxy_async();
         __syncthreads();
+        DO_MARK(1);
         // ---- M1) logits
         if (warp == 4) {
             tc::tc_fence_after();
@@ -265,68 +295,81 @@ k_dec_out_tc(DecOutArgs a) {
             }
             __syncwarp();
         }
-        // ---- E1) softmax / CE, thread = row
-        if (warp < 4) {
+        // ---- E1) softmax / CE: thread = (row, half of the classes); warps w and w + 4 share TMEM lane quadrant w & 3
+        // and exchange their row maxima / sums through shared memory
+        {
+            constexpr int HV = VMAX / 2;
+            const int half = warp >> 2, v0 = half * HV;
+            const int r2 = (warp & 3) * 32 + lane;
+            const int row = row0 + r2;
             tc::mbar_wait(&bar_m, mphase & 1);
             tc::tc_fence_after();
-            float lg[VMAX];
-            tc::tmem_ld_32x32(lane_addr + TC_LG, lg);
-            const int row = row0 + rl;
+            float lg[HV];
+            tmem_ld_16(lane_addr + TC_LG + v0, lg);
             float mx = -INFINITY;
 #pragma unroll
-            for (int v = 0; v < VMAX; ++v) {
-                lg[v] = v < V ? lg[v] + a.fc_b[v] : -INFINITY;
-                mx = fmaxf(mx, lg[v]);
+            for (int i = 0; i < HV; ++i) {
+                lg[i] = v0 + i < V ? lg[i] + a.fc_b[v0 + i] : -INFINITY;
+                mx = fmaxf(mx, lg[i]);
             }
             if (row < nrows && a.logits_out != nullptr) {
 #pragma unroll
-                for (int v = 0; v < VMAX; ++v)
-                    if (v < V) a.logits_out[(size_t)row * V + v] = lg[v];
+                for (int i = 0; i < HV; ++i)
+                    if (v0 + i < V) a.logits_out[(size_t)row * V + v0 + i] = lg[i];
             }
-            float dl[VMAX];
+            float dl[HV];
 #pragma unroll
-            for (int v = 0; v < VMAX; ++v) dl[v] = 0.f;
+            for (int i = 0; i < HV; ++i) dl[i] = 0.f;
             if (a.fused_ce) {
                 const int tg = row < nrows ? a.tgt[row] : PAD;
+                ex_s[0][half][r2] = mx;
+                __syncthreads();
+                mx = fmaxf(ex_s[0][0][r2], ex_s[0][1][r2]);
+                float e[HV], se = 0.f, lt = 0.f;
+#pragma unroll
+                for (int i = 0; i < HV; ++i) {
+                    e[i] = v0 + i < V ? ex2_fast((lg[i] - mx) * 1.4426950408889634f) : 0.f;     // SFU exp2: 2^-22 relative
+                    se += e[i];
+                    if (v0 + i == tg) lt = lg[i];
+                }
+                ex_s[1][half][r2] = se;
+                ex_s[2][half][r2] = lt;
+                __syncthreads();
+                se = ex_s[1][0][r2] + ex_s[1][1][r2];
+                lt = ex_s[2][0][r2] + ex_s[2][1][r2];
                 if (tg != PAD) {
-                    float e[VMAX], se = 0.f, lt = 0.f;
+                    if (half == 0) accn += (mx + __logf(se)) - lt;
+                    const float inv = inv_ntok / se;
 #pragma unroll
-                    for (int v = 0; v < VMAX; ++v) {
-                        e[v] = v < V ? expf(lg[v] - mx) : 0.f;
-                        se += e[v];
-                        if (v == tg) lt = lg[v];
-                    }
-                    accn += (mx + logf(se)) - lt;
-                    const float inv = 1.0f / se;
-#pragma unroll
-                    for (int v = 0; v < VMAX; ++v) dl[v] = v < V ? (e[v] * inv - (v == tg ? 1.f : 0.f)) * inv_ntok : 0.f;
+                    for (int i = 0; i < HV; ++i) dl[i] = v0 + i < V ? e[i] * inv - (v0 + i == tg ? inv_ntok : 0.f) : 0.f;
                 }
             } else if (a.dlogits_in != nullptr && row < nrows) {
 #pragma unroll
-                for (int v = 0; v < VMAX; ++v)
-                    if (v < V) dl[v] = a.dlogits_in[(size_t)row * V + v];
+                for (int i = 0; i < HV; ++i)
+                    if (v0 + i < V) dl[i] = a.dlogits_in[(size_t)row * V + v0 + i];
             }
             if (want_grad) {
 #pragma unroll
-                for (int v = 0; v < VMAX; ++v) accb[v] += dl[v];
+                for (int i = 0; i < HV; ++i) accb[i] += dl[i];
                 // dl -> DL (K = class, K-major) and DLT (class x rows)
 #pragma unroll
-                for (int kc = 0; kc < VMAX / 8; ++kc) {
+                for (int kq = 0; kq < HV / 8; ++kq) {
+                    const int kc = half * (HV / 8) + kq;
                     uint4 hi, lo;
-                    split2(dl[kc * 8 + 0], dl[kc * 8 + 1], hi.x, lo.x);
-                    split2(dl[kc * 8 + 2], dl[kc * 8 + 3], hi.y, lo.y);
-                    split2(dl[kc * 8 + 4], dl[kc * 8 + 5], hi.z, lo.z);
-                    split2(dl[kc * 8 + 6], dl[kc * 8 + 7], hi.w, lo.w);
-                    const int off = kc * LBO_R + (rl >> 3) * 128 + (rl & 7) * 16;
+                    split2(dl[kq * 8 + 0], dl[kq * 8 + 1], hi.x, lo.x);
+                    split2(dl[kq * 8 + 2], dl[kq * 8 + 3], hi.y, lo.y);
+                    split2(dl[kq * 8 + 4], dl[kq * 8 + 5], hi.z, lo.z);
+                    split2(dl[kq * 8 + 6], dl[kq * 8 + 7], hi.w, lo.w);
+                    const int off = kc * LBO_R + (r2 >> 3) * 128 + (r2 & 7) * 16;
                     *reinterpret_cast<uint4*>(DL + off) = hi;
                     *reinterpret_cast<uint4*>(DL + DL_SPLIT + off) = lo;
                     const uint32_t wh[4] = {hi.x, hi.y, hi.z, hi.w}, wl[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int v = kc * 8 + e;
-                        const int o = (rl >> 3) * LBO_VT + (v >> 3) * 128 + (v & 7) * 16 + (rl & 7) * 2;
-                        *reinterpret_cast<uint16_t*>(DLT + o) = (uint16_t)(wh[e >> 1] >> ((e & 1) * 16));
-                        *reinterpret_cast<uint16_t*>(DLT + DLT_SPLIT + o) = (uint16_t)(wl[e >> 1] >> ((e & 1) * 16));
+                    for (int e8 = 0; e8 < 8; ++e8) {
+                        const int v = kc * 8 + e8;
+                        const int o = (r2 >> 3) * LBO_VT + (v >> 3) * 128 + (v & 7) * 16 + (r2 & 7) * 2;
+                        *reinterpret_cast<uint16_t*>(DLT + o) = (uint16_t)(wh[e8 >> 1] >> ((e8 & 1) * 16));
+                        *reinterpret_cast<uint16_t*>(DLT + DLT_SPLIT + o) = (uint16_t)(wl[e8 >> 1] >> ((e8 & 1) * 16));
                     }
                 }
             }
@@ -336,6 +379,7 @@ k_dec_out_tc(DecOutArgs a) {
         if (!want_grad) { __syncthreads(); continue; }
         tc::fence_proxy_async();
         __syncthreads();
+        DO_MARK(2);
         // ---- M2) dh = dl W  and  dW^T += hd^T dl
         if (warp == 4) {
             tc::tc_fence_after();
@@ -376,8 +420,12 @@ k_dec_out_tc(DecOutArgs a) {
         }
         ++mphase;
         __syncthreads();                                       // both MMAs are done with HD / HDT / DL / DLT
+        DO_MARK(3);
     }
 
+#ifdef CPG_GRU_TIMELINE
+    if (blockIdx.x == 0 && threadIdx.x == 0) for (int i = 0; i < 8; ++i) g_do_tl[i] = g_do_acc[i];
+#endif
     // ---- per-CTA partials
     tc::tc_fence_after();
     if (want_grad) {
@@ -390,14 +438,18 @@ k_dec_out_tc(DecOutArgs a) {
 #pragma unroll
                 for (int v = 0; v < VMAX; ++v) pw[v * DEC_HP + j] = dw_started ? dw[v] : 0.f;
             }
+        }
 #pragma unroll
-            for (int v = 0; v < VMAX; ++v) {
-                const float s = warp_sum(accb[v]);
-                if (lane == 0) red_b[warp][v] = s;
-            }
+        for (int v = 0; v < VMAX / 2; ++v) {
+            const float sv = warp_sum(accb[v]);
+            if (lane == 0) red_b[warp][v] = sv;
         }
         __syncthreads();
-        if (tid < VMAX) a.part_b[(size_t)blockIdx.x * VMAX + tid] = (red_b[0][tid] + red_b[1][tid]) + (red_b[2][tid] + red_b[3][tid]);
+        if (tid < VMAX) {
+            const int hf = tid / (VMAX / 2), v = tid % (VMAX / 2);
+            a.part_b[(size_t)blockIdx.x * VMAX + tid] =
+                (red_b[hf * 4 + 0][v] + red_b[hf * 4 + 1][v]) + (red_b[hf * 4 + 2][v] + red_b[hf * 4 + 3][v]);
+        }
     }
     if (a.part_nll != nullptr) {
         if (warp < 4) {
