@@ -392,31 +392,39 @@ k_dec_out_tc(DecOutArgs a) {
             __syncwarp();
         }
         dw_started = true;
-        // ---- E2) dh_out = dh * keep * scale, thread = row; warps w and w + 4 share a lane quadrant and split the columns
+        // ---- E2) dh_out = dh * keep * scale.  TMEM read-out with thread = row (warps w and w + 4 share a lane quadrant and
+        // split the columns) into a padded fp32 tile that reuses the hd^T operand space (its reader, the dW MMA, has
+        // completed; its never-rewritten M-padding rows only feed accumulator rows nobody reads -- unlike HD, whose
+        // K padding must stay zero), then a row-contiguous masked copy to HBM by all 256 threads.
         {
+            constexpr int SST = DEC_HP + 4;                    // 108 floats: conflict-free float4 rows
+            float* stage = reinterpret_cast<float*>(HDT);
+            static_assert((DEC_HP + 4) * TR * 4 <= 2 * HDT_SPLIT, "staging tile fits the hd^T operand space");
             tc::mbar_wait(&bar_m, mphase & 1);
             tc::tc_fence_after();
             const int r2 = (warp & 3) * 32 + lane;
-            const int row = row0 + r2;
             const int cbeg = warp < 4 ? 0 : 64, cend = warp < 4 ? 64 : DEC_HP;
 #pragma unroll 1
             for (int c0 = cbeg; c0 < cend; c0 += 32) {
                 float v[32];
                 tc::tmem_ld_32x32(lane_addr + TC_DH + c0, v);     // columns >= 104 of the last chunk: padding, unused
-                if (row < nrows) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int j = c0 + q * 4;
-                        if (j < DEC_HP) {
-                            const unsigned k = keep_s[r2 * NF4 + (j >> 2)];
-                            st4(a.dh_out + (size_t)row * DEC_HP + j,
-                                make_float4((k & 1) ? v[q * 4] * sc : 0.f, (k & 2) ? v[q * 4 + 1] * sc : 0.f,
-                                            (k & 4) ? v[q * 4 + 2] * sc : 0.f, (k & 8) ? v[q * 4 + 3] * sc : 0.f));
-                        }
-                    }
-                }
+                for (int q = 0; q < 8; ++q)
+                    if (c0 + q * 4 < DEC_HP) st4(stage + r2 * SST + c0 + q * 4, make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]));
             }
             tc::tc_fence_before();
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < TR * NF4 / NTH; ++it) {
+                const int idx = tid + it * NTH;
+                const int r = idx / NF4, f = idx % NF4, row = row0 + r;
+                if (row < nrows) {
+                    const float4 d = ld4(stage + r * SST + f * 4);
+                    const unsigned k = keep_s[r * NF4 + f];
+                    st4(a.dh_out + (size_t)row * DEC_HP + f * 4,
+                        make_float4((k & 1) ? d.x * sc : 0.f, (k & 2) ? d.y * sc : 0.f, (k & 4) ? d.z * sc : 0.f, (k & 8) ? d.w * sc : 0.f));
+                }
+            }
         }
         ++mphase;
         __syncthreads();                                       // both MMAs are done with HD / HDT / DL / DLT
