@@ -210,32 +210,37 @@ k_dec_out_tc(DecOutArgs a) {
     long long g_do_last = clock64();
 #endif
     const int ntiles = ceil_div(nrows, TR);
+    // Raw inputs of a tile ((row, quad) items: 13 per thread): fetched one tile ahead -- the loads of tile t+1 are issued
+    // right after the second MMA batch of tile t and land under its dh epilogue.  Unconditional (clamped) addresses
+    // and no use of the loaded values at the issue point, so that the 39 loads of a thread are in flight together.
+    constexpr int NIT = TR * NF4 / NTH;
+    static_assert(TR * NF4 % NTH == 0, "staging items");
+    float4 hq[NIT];
+    unsigned short k0[NIT], k1[NIT];                             // raw keep bytes (units 4f, 4f+1 | 4f+2, 4f+3)
+    auto load_tile = [&](int tile) {
+        const int row0 = tile * TR;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int idx = tid + it * NTH;
+            const int r = idx / NF4, f = idx % NF4;
+            const int row = min(row0 + r, nrows - 1);
+            hq[it] = ld4(a.hs + (size_t)row * DEC_HP + f * 4);
+            k0[it] = 0x0101; k1[it] = 0x0101;
+            if (has_mask) {
+                // row * 102 + 4 f is even: two aligned 2-byte loads (the last quad's second pair is clamped, masked below)
+                const unsigned short* kp = reinterpret_cast<const unsigned short*>(a.out_keep + (size_t)row * DEC_H + f * 4);
+                k0[it] = kp[0];
+                k1[it] = kp[f * 4 + 2 < DEC_H ? 1 : 0];
+            }
+        }
+    };
+    if ((int)blockIdx.x < ntiles) load_tile(blockIdx.x);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int row0 = tile * TR;
         DO_MARK(7);
-        // ---- S1) hd = h * keep * scale -> HD (K-major, two bf16 terms) + keep bytes; coalesced over (row, quad)
+        // ---- S1) hd = h * keep * scale -> HD (K-major, three bf16 terms) + keep nibbles; coalesced over (row, quad)
         {
-            constexpr int NIT = TR * NF4 / NTH;                  // 13 (row, quad) items per thread, exactly
-            static_assert(TR * NF4 % NTH == 0, "staging items");
-            float4 hq[NIT];
-            unsigned short k0[NIT], k1[NIT];                     // raw keep bytes (units 4f, 4f+1 | 4f+2, 4f+3)
-            // all global loads of the tile first: unconditional (clamped) addresses and no use of the loaded values
-            // in this loop, so that the 39 loads of a thread are in flight together ...
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                const int idx = tid + it * NTH;
-                const int r = idx / NF4, f = idx % NF4;
-                const int row = min(row0 + r, nrows - 1);
-                hq[it] = ld4(a.hs + (size_t)row * DEC_HP + f * 4);
-                k0[it] = 0x0101; k1[it] = 0x0101;
-                if (has_mask) {
-                    // row * 102 + 4 f is even: two aligned 2-byte loads (the last quad's second pair is clamped, masked below)
-                    const unsigned short* kp = reinterpret_cast<const unsigned short*>(a.out_keep + (size_t)row * DEC_H + f * 4);
-                    k0[it] = kp[0];
-                    k1[it] = kp[f * 4 + 2 < DEC_H ? 1 : 0];
-                }
-            }
-            // ... then mask, split and store
+            if (!want_grad && tile != (int)blockIdx.x) load_tile(tile);     // forward-only: no second MMA batch to hide under
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int idx = tid + it * NTH;
@@ -392,6 +397,7 @@ k_dec_out_tc(DecOutArgs a) {
             __syncwarp();
         }
         dw_started = true;
+        if (tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x);      // next tile's inputs: in flight under E2
         // ---- E2) dh_out = dh * keep * scale.  TMEM read-out with thread = row (warps w and w + 4 share a lane quadrant and
         // split the columns) into a padded fp32 tile that reuses the hd^T operand space (its reader, the dW MMA, has
         // completed; its never-rewritten M-padding rows only feed accumulator rows nobody reads -- unlike HD, whose
