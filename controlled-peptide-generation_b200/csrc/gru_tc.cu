@@ -345,7 +345,7 @@ k_gru_fwd_tc(FwdArgs a) {
         const uint32_t d0 = tmem_d + (uint32_t)(ch * MT * NB);
         // start the chains half a step apart: the SFU-bound gate math of one then runs under the MMA / TMEM
         // read-out of the other instead of both phases coinciding
-        if (ch > 0) __nanosleep(CPG_CHAIN_SKEW_NS);
+        if (ch > 0) __nanosleep(CPG_CHAIN_SKEW_NS * 2 * ch / NCH);
         // gate planes of a finished step leave through the TMA engine: the epilogue only writes them to the staging
         // tile in shared memory (its arrival on bar_x says they are there), this lane streams the four 10 KB planes out
         float* gates_dst = (dir ? a.gates[1] : a.gates[0]);
@@ -854,11 +854,20 @@ k_gru_bwd_tc(BwdArgs a) {
     if (warp == C::NW_EPI) tc::tmem_dealloc<C::TMEM_COLS>(tmem_d);
 }
 
-// chains per CTA x batch rows per chain: 64 rows per CTA (encoder, 2 directions -> 128 CTAs at B = 4096),
-// 32 rows per CTA (decoder -> 128 CTAs)
-using EncFwd = FwdCfg<ENC_H, ENC_H, 32, 2, CPG_ENC_FWD_NWG, false>;     // KID 0 | 1 (forward), 2 | 3 (backward)
+// chains per CTA x batch rows per chain: 4 x 16 = 64 rows per CTA (encoder, 2 directions -> 128 CTAs at B = 4096),
+// 2 x 16 = 32 rows per CTA (decoder -> 128 CTAs).  More, thinner chains per SM hide each other's MMA -> TMEM ->
+// shared-memory -> gate-math latency chain better than fewer, fatter ones.
+#ifndef CPG_ENC_2CHAINS
+using EncFwd = FwdCfg<ENC_H, ENC_H, 16, 4, 5, false>;      // four 16-row chains per CTA: 107 -> 97 us vs two 32-row chains
+#else
+using EncFwd = FwdCfg<ENC_H, ENC_H, 32, 2, CPG_ENC_FWD_NWG, false>;
+#endif     // KID 0 | 1 (forward), 2 | 3 (backward)
 using DecFwd = FwdCfg<DEC_HP, 112, 16, 2, 7, true>;
+#ifndef CPG_ENC_2CHAINS
+using EncBwd = BwdCfg<ENC_H, 16, 4, 5, false>;             // 127 -> 119 us
+#else
 using EncBwd = BwdCfg<ENC_H, 32, 2, CPG_ENC_BWD_NWG, false>;
+#endif
 using DecBwd = BwdCfg<DEC_HP, 16, 2, 7, true>;
 
 template <class K>
