@@ -87,16 +87,29 @@ k_class_sample(GmmSpec g, ClfSpec cs, uint64_t seed, int64_t offset, int64_t n, 
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long local_acc = 0;
-    for (int64_t i = (int64_t)blockIdx.x * CS_WARPS + warp; i < n; i += (int64_t)gridDim.x * CS_WARPS) {
+    // A warp takes 32 consecutive draws at a time: lane l first does the per-draw scalar work (Philox stream 0 ->
+    // component by binary search + acceptance uniform) of draw base + l, then the warp walks the 32 draws with
+    // lanes over the 100 dimensions and the scalars broadcast by shuffle -- the scalar part used to be recomputed by
+    // all 32 lanes of every draw (a third of the kernel's instructions).  Same streams, same values as before.
+    for (int64_t base = ((int64_t)blockIdx.x * CS_WARPS + warp) * 32; base < n; base += (int64_t)gridDim.x * CS_WARPS * 32) {
+        int k_mine = 0;
+        double ua_mine = 2.0;
+        if (base + lane < n) {
+            uint32_t r0[4];
+            Philox::gen(seed, (uint64_t)(offset + base + lane), 0u, r0);
+            const float uc = (float)(r0[0] >> 8) * (1.0f / 16777216.0f);
+            ua_mine = u64_to_unit(r0[2], r0[3]);
+            int lo = 0, hi = g.K - 1;                            // first k with cdf[k] > uc
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf_s[mid] > uc) hi = mid; else lo = mid + 1; }
+            k_mine = lo;
+        }
+        const int ndraw = (int)min((int64_t)32, n - base);
+        for (int jd = 0; jd < ndraw; ++jd) {
+        const int64_t i = base + jd;
         const uint64_t gid = (uint64_t)(offset + i);
+        const int k = __shfl_sync(0xffffffffu, k_mine, jd);
+        const double ua = __shfl_sync(0xffffffffu, ua_mine, jd);
         uint32_t r[4];
-        // stream 0: component + acceptance uniform (same for every lane), stream 1+lane: normals
-        Philox::gen(seed, gid, 0u, r);
-        const float uc = (float)(r[0] >> 8) * (1.0f / 16777216.0f);
-        const double ua = u64_to_unit(r[2], r[3]);
-        int lo = 0, hi = g.K - 1;                            // first k with cdf[k] > uc
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf_s[mid] > uc) hi = mid; else lo = mid + 1; }
-        const int k = lo;
         Philox::gen(seed, gid, 1u + (uint32_t)lane, r);
         float nrm[4];
         {
@@ -139,6 +152,7 @@ k_class_sample(GmmSpec g, ClfSpec cs, uint64_t seed, int64_t offset, int64_t n, 
             if (comp_out != nullptr) comp_out[i] = k;
             local_acc += acc;
         }
+        }   // draws of this group of 32
     }
     if (n_accepted != nullptr && lane == 0 && local_acc) atomicAdd(n_accepted, local_acc);
 }
@@ -229,8 +243,8 @@ int cpg_class_sample(cpg_ctx* ctx, cpg_stream stream, const float* gmm_mean, con
     int rc = fill_clf(cs, n_clf, coef, intercept, target_col, f32);
     if (rc) return rc;
     GmmSpec g{gmm_mean, gmm_sd, gmm_cdf, K};
-    int64_t want = (n + CS_WARPS - 1) / CS_WARPS;
-    int grid = (int)std::min<int64_t>(want, (int64_t)ctx->sm_count * 8);
+    int64_t want = (n + CS_WARPS * 32 - 1) / (CS_WARPS * 32);
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * 8));
     CPG_LAUNCH(k_class_sample, grid, CS_WARPS * 32, 0, (cudaStream_t)stream, g, cs, seed, offset, n, z_out, probs, accum,
                accept, comp_out, n_accepted);
     return check_launch("cpg_class_sample");
