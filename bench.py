@@ -317,7 +317,8 @@ def run_ours(args):
                    'l2_policy': 'per-step working set (activation stash ~1.1 GB) exceeds the 126 MB L2; no flush needed',
                    'noise': 'Philox in-kernel, regenerated every step'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * L * 8, 'd2h_bytes_per_step': 16 * 4 + 8,
-                'api': 'train_vae.train_vae(cfgv, model, dataset) with pinned host tokens, scalars read every step'},
+                'api': 'train_vae.train_vae(cfgv, model, dataset): pinned host tokens copied H2D every step (one step ahead, copy stream), '
+                  'scalar block copied D2H every step (collected after the next step is enqueued)'},
         'gpu_launches': launches, 'launches_per_step': launches / K,
         'profiled_ms_per_step': prof_ms / K,
         'roofline': roof, 'cpu_baseline': cpu, 'clocks': clock_summary, 'class': class_block,

@@ -65,21 +65,45 @@ def _train_fused(cfgv, model, dataset):
     if distributed:
         # rank-distinct noise rows; rf_w / rf_b come from the shared seed inside alloc_noise
         rank_seed = (seed + 0x9E3779B97F4A7C15 * (1 + parallel.dist.get_rank())) % (1 << 63)
-    stepper, tok_dev, global_batch = None, None, None
+    stepper, global_batch = None, None
     it_range, write = _progress(range(cfgv.s_iter, cfgv.s_iter + cfgv.n_iter + 1))
-    for it in it_range:
+    last_it = cfgv.s_iter + cfgv.n_iter
+    # Host batches go to the device one iteration ahead, on a copy stream, into one of two buffers: the H2D copy of
+    # batch i+1 runs under the kernels of iteration i (same number of next_batch calls as the reference loop).
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs, used_ev = [None, None], [None, None]       # device token buffers / "last reader has been enqueued" events
+    staged = None                                     # (host tokens, slot or None, copy event or None) of the next iteration
+    pinned_scal, pending_read = None, None
+
+    def stage(tokens, slot):
+        if engine._lib._on_device(tokens):
+            return tokens, None, None
+        Bn, Ln = tokens.shape
+        if bufs[slot] is None or bufs[slot].shape != (Bn, Ln):
+            bufs[slot] = torch.empty(Bn, Ln, dtype=torch.int64, device=dev)
+            used_ev[slot] = None
+        with torch.cuda.stream(copy_stream):
+            if used_ev[slot] is not None:
+                copy_stream.wait_event(used_ev[slot])                    # its previous reader (two iterations ago)
+            bufs[slot].copy_(tokens, non_blocking=True)                  # async when the loader pins its batches
+            ev = copy_stream.record_event()
+        return tokens, slot, ev
+
+    for n_done, it in enumerate(it_range):
         log_it = it % cfgv.cheaplog_every == 0 or it % cfgv.expsvlog_every == 0
-        tokens = dataset.next_batch('train_vae').text
+        if staged is None:
+            staged = stage(dataset.next_batch('train_vae').text, n_done % 2)
+        tokens, slot, ev = staged
+        staged = None
         B, L = tokens.shape
         if stepper is None or stepper.B != B or stepper.L != L:
             stepper = engine.FusedStepper(st, B, L, hp, seed=seed, p_word=p_word, p_out=p_out, rf_dim=wm.rf_dim)
-            tok_dev = torch.empty(B, L, dtype=torch.int64, device=dev)
             global_batch = parallel.global_batch_size(B, dev) if distributed else B
-        if engine._lib._on_device(tokens):
+        if slot is None:
             tok = tokens if tokens.is_contiguous() else tokens.contiguous()
         else:
-            tok_dev.copy_(tokens, non_blocking=True)                 # H2D (async when the loader pins its batches)
-            tok = tok_dev
+            torch.cuda.current_stream(dev).wait_event(ev)
+            tok = bufs[slot]
         beta = float(utils.anneal(cfgv.beta, it))
         hp.compute_full_mmd = 1 if (it % every == 0 or log_it) else 0
         if distributed:
@@ -88,8 +112,24 @@ def _train_fused(cfgv, model, dataset):
             scal = parallel.dp_train_step(st, tok, stepper.noise, hp, p_out=p_out, global_batch=global_batch)
         else:
             scal = stepper.step(tok, it, beta)
-        if log_it or (sync_every > 0 and it % sync_every == 0):
-            last_scalars = vals = scal.cpu()                         # the only device->host read
+        if slot is not None:
+            used_ev[slot] = torch.cuda.current_stream(dev).record_event()
+        if it != last_it:                                                # next batch: fetch + H2D under this iteration
+            staged = stage(dataset.next_batch('train_vae').text, (n_done + 1) % 2)
+        # device -> host read of the scalar block.  Iterations that print need it now; the periodic read
+        # (cfg.b200.sync_scalars_every) is pipelined: copied to pinned memory asynchronously and collected after the
+        # NEXT iteration has been enqueued, so the GPU never idles behind the host round trip.
+        if pending_read is not None:
+            pending_read[1].synchronize()
+            last_scalars = pending_read[0].clone()
+            pending_read = None
+        if log_it:
+            last_scalars = vals = scal.cpu()
+        elif sync_every > 0 and it % sync_every == 0:
+            if pinned_scal is None:
+                pinned_scal = torch.empty(scal.shape, dtype=scal.dtype, pin_memory=True)
+            pinned_scal.copy_(scal, non_blocking=True)
+            pending_read = (pinned_scal, torch.cuda.current_stream(dev).record_event())
         if log_it:
             for name, slot in _SCALAR_LOG:
                 log_value('train_' + name, float(vals[engine.SC[slot]]), it)
@@ -102,6 +142,9 @@ def _train_fused(cfgv, model, dataset):
             _log_sample(model, dataset, write)
         if it % cfgv.expsvlog_every == 0 and it > 0:
             save_model(model, cfgv.chkpt_path.format(it))
+    if pending_read is not None:
+        pending_read[1].synchronize()
+        last_scalars = pending_read[0].clone()
     return st
 
 
