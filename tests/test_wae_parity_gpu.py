@@ -330,3 +330,37 @@ def test_module_level_backward_matches_oracle(eng):
             want[ow.PAD_IDX] = 0
         scale = float(want.abs().max()) + 1e-12
         np.testing.assert_allclose(got[k].cpu().numpy(), want.numpy(), rtol=1e-3, atol=1e-4 * scale, err_msg=k)
+
+
+def test_side_stream_and_overlapped_noise_change_nothing(eng):
+    """The internal side stream (loss / weight-gradient kernels overlapped with the recurrences) and the overlapped
+    noise generation are scheduling choices only: parameters, gradients and scalars after two iterations are
+    bit-identical with everything serialised on one stream."""
+    from cpg_b200 import _lib
+    dev = torch.device('cuda')
+    B = 1536                                       # large enough for the tcgen05 paths (auto mode)
+    p = ow.random_params(V, seed=21)
+    tokens = ow.synthetic_tokens(B, V, seed=22).to(dev)
+    results = []
+    try:
+        for side, overlap in ((0, False), (1, True)):
+            _lib.set_option('side_stream', side)
+            st = eng.FlatState(V, dev)
+            st.load(p)
+            noise = eng.alloc_noise(B, 25, dev, seed=99)
+            hp = eng.make_hparams(beta=0.7)
+            scal = None
+            for it in range(2):
+                eng.fill_step_noise(noise, 1234, it, overlap=overlap)
+                scal, _ = eng.train_step(st, tokens, noise, hp)
+            torch.cuda.synchronize()
+            results.append((st.params.clone(), st.grads.clone(), scal.clone(),
+                            {k: v.clone() for k, v in noise.items() if torch.is_tensor(v)}))
+    finally:
+        _lib.set_option('side_stream', 1)
+    (p0, g0, s0, n0), (p1, g1, s1, n1) = results
+    for k in n0:
+        assert torch.equal(n0[k], n1[k]), 'noise ' + k
+    assert torch.equal(g0, g1)
+    assert torch.equal(p0, p1)
+    assert torch.equal(s0, s1)
