@@ -30,6 +30,9 @@
 #ifndef CPG_CHAIN_SKEW_NS
 #define CPG_CHAIN_SKEW_NS 900
 #endif
+#ifndef CPG_DEC_NWG
+#define CPG_DEC_NWG 7
+#endif
 #ifndef CPG_ENC_FWD_NWG
 #define CPG_ENC_FWD_NWG 10
 #endif
@@ -862,13 +865,13 @@ using EncFwd = FwdCfg<ENC_H, ENC_H, 16, 4, 5, false>;      // four 16-row chains
 #else
 using EncFwd = FwdCfg<ENC_H, ENC_H, 32, 2, CPG_ENC_FWD_NWG, false>;
 #endif     // KID 0 | 1 (forward), 2 | 3 (backward)
-using DecFwd = FwdCfg<DEC_HP, 112, 16, 2, 7, true>;
+using DecFwd = FwdCfg<DEC_HP, 112, 16, 2, CPG_DEC_NWG, true>;
 #ifndef CPG_ENC_2CHAINS
 using EncBwd = BwdCfg<ENC_H, 16, 4, 5, false>;             // 127 -> 119 us
 #else
 using EncBwd = BwdCfg<ENC_H, 32, 2, CPG_ENC_BWD_NWG, false>;
 #endif
-using DecBwd = BwdCfg<DEC_HP, 16, 2, 7, true>;
+using DecBwd = BwdCfg<DEC_HP, 16, 2, CPG_DEC_NWG, true>;
 
 template <class K>
 int set_smem(K kfn, size_t bytes, size_t& set_for) {
