@@ -30,18 +30,6 @@ k_sumsq_partial(const float* __restrict__ g, int64_t n, int64_t dup_off, int64_t
     }
 }
 
-// total norm, clip coefficient (torch: clamp(max_norm / (total + 1e-6), max=1))
-__global__ void k_norm_final(const float* __restrict__ part, int nparts, float max_norm, float* __restrict__ norm_out,
-                             float* __restrict__ coef_out) {
-    if (threadIdx.x != 0) return;
-    double s = 0.0;
-    for (int i = 0; i < nparts; ++i) s += (double)part[i];
-    float total = (float)sqrt(s);
-    if (norm_out != nullptr) *norm_out = total;
-    float c = max_norm / (total + 1e-6f);
-    *coef_out = c < 1.0f ? c : 1.0f;
-}
-
 __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamStep& st, float b1,
                                             float b2, float eps) {
     m = m + (g - m) * (1.0f - b1);                       // exp_avg.lerp_(grad, 1 - beta1)
@@ -93,13 +81,6 @@ int adam_norm_parts(int64_t n, int sm_count) {
     int64_t want = (n + NORM_THREADS * 4 - 1) / (NORM_THREADS * 4);
     int cap = 2 * (sm_count > 0 ? sm_count : 1);
     return (int)(want < 1 ? 1 : (want > cap ? cap : want));
-}
-
-void launch_grad_norm(cudaStream_t s, const float* g, int64_t n, int64_t dup_off, int64_t dup_n, float max_norm,
-                      int sm_count, float* part, float* norm_out, float* coef_out) {
-    int parts = adam_norm_parts(n, sm_count);
-    CPG_LAUNCH(k_sumsq_partial, parts, NORM_THREADS, 0, s, g, n, dup_off, dup_n, part);
-    CPG_LAUNCH(k_norm_final, 1, 32, 0, s, part, parts, max_norm, norm_out, coef_out);
 }
 
 // sum-of-squares partials + (norm, clip, Adam) in two launches

@@ -12,8 +12,6 @@ struct AdamHyper {
 };
 
 int adam_norm_parts(int64_t n, int sm_count);
-void launch_grad_norm(cudaStream_t s, const float* g, int64_t n, int64_t dup_off, int64_t dup_n, float max_norm,
-                      int sm_count, float* part, float* norm_out, float* coef_out);
 // partial sums of squares, then one kernel that finishes the norm, clips and applies Adam (norm_out / coef_out nullable)
 void launch_clip_adam_fused(cudaStream_t s, float* p, float* g, float* m, float* v, int64_t n, int64_t dup_off,
                             int64_t dup_n, float max_norm, float* part, float* norm_out, float* coef_out,
