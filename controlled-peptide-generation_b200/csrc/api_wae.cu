@@ -208,7 +208,11 @@ static void side_join(cpg_ctx*, cudaStream_t, int = 0) {}
 // Tensor-core recurrences pay off once a 128-row tile per CTA fills a good part of the chip;
 // tiny batches stay on the 32-row fp32 SIMT kernels.  g_opt_gru_tc: 0 = never, 1 = auto, 2 = always.
 int g_opt_gru_tc = 1;
+#ifndef CPG_EMU
 static bool use_gru_tc(int B) { return g_opt_gru_tc == 2 || (g_opt_gru_tc == 1 && B >= 1024); }
+#else
+static bool use_gru_tc(int) { return false; }
+#endif
 static void forward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, const ParamLayout& lay, int V, int B, int L,
                          const cpg_wae_inputs* in, float* mu, float* logvar, float* z, bool stash, bool encoder_only,
                          bool mark_after_reparam = false) {

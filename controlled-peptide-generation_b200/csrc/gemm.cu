@@ -113,6 +113,9 @@ k_sgemm(int M, int N, int K, float alpha, const float* __restrict__ A, int64_t s
     }
 }
 
+struct GemmSecond { const float* A; const float* B; const float* bias; float* C; int mode; };   // second operand set of a launch
+
+#ifndef CPG_EMU   // cp.async pipeline: GPU build only (the CPU emulation of tools/cuda_emu keeps the plain kernel above)
 // ---- pipelined variant for 16-byte-aligned operands (every product of the training step) -------------
 // 64x64x16 tiles (B = 4096 gives 128..512 CTAs for the step's shapes instead of 64..256), 4x4 register
 // tile, and a 4-stage cp.async pipeline so that three k-tiles of global latency are always in flight
@@ -128,7 +131,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-struct GemmSecond { const float* A; const float* B; const float* bias; float* C; int mode; };
 
 template <bool A_KFAST, bool B_KFAST>
 __global__ void __launch_bounds__(256)
@@ -244,6 +246,8 @@ k_sgemm_pipe(int M, int N, int K, float alpha, const float* __restrict__ A, int6
     }
 }
 
+#endif  // CPG_EMU
+
 __global__ void k_splitk_reduce(int M, int N, int splits, float alpha, const float* __restrict__ ws, float beta,
                                 float* __restrict__ C, int64_t ldc, const float* __restrict__ bias) {
     const int i = blockIdx.x * RED_X + threadIdx.x;
@@ -293,7 +297,12 @@ static void launch_sgemm_impl(cudaStream_t s, int M, int N, int K, float alpha, 
     const bool aligned = (a_k || a_m) && (b_k || b_n) && lda % 4 == 0 && ldb % 4 == 0 &&
                          ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 &&
                          (sec.mode == 0 || (((uintptr_t)sec.A & 15) == 0 && ((uintptr_t)sec.B & 15) == 0));
-    if (!aligned && sec.mode != 0) {
+#ifdef CPG_EMU
+    const bool use_pipe = false;
+#else
+    const bool use_pipe = aligned;
+#endif
+    if (!use_pipe && sec.mode != 0) {
         // unaligned operands: two plain launches with the same meaning
         GemmSecond none{nullptr, nullptr, nullptr, nullptr, 0};
         launch_sgemm_impl(s, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc, bias, 1, nullptr, none);
@@ -301,7 +310,8 @@ static void launch_sgemm_impl(cudaStream_t s, int M, int N, int K, float alpha, 
         else launch_sgemm_impl(s, M, N, K, alpha, sec.A, sam, sak, sec.B, sbk, sbn, 0.f, sec.C, ldc, sec.bias, 1, nullptr, none);
         return;
     }
-    if (aligned) {
+#ifndef CPG_EMU
+    if (use_pipe) {
         dim3 grid(ceil_div(N, PN), ceil_div(M, PM), sec.mode == 2 ? 2 : split_k);
 #define CPG_PIPE(AK, BK) CPG_LAUNCH_NAMED("k_sgemm", (k_sgemm_pipe<AK, BK>), grid, 256, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, kchunk, ws, sec)
         if (a_k && !b_k) CPG_PIPE(true, false);
@@ -313,6 +323,7 @@ static void launch_sgemm_impl(cudaStream_t s, int M, int N, int K, float alpha, 
             CPG_LAUNCH(k_splitk_reduce, CPG_RED_GRID(M * N), CPG_RED_BLOCK, 0, s, M, N, split_k, alpha, ws, beta, C, ldc, bias);
         return;
     }
+#endif
     dim3 grid(ceil_div(N, GN), ceil_div(M, GM), split_k);
     CPG_LAUNCH(k_sgemm, grid, 256, 0, s, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc, bias, kchunk, ws);
     if (split_k > 1)

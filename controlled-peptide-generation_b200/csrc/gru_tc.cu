@@ -945,4 +945,11 @@ int launch_gru_bwd_dec_tc(cudaStream_t s, const GruSeq& q, int B, int L, int rou
 }
 
 }  // namespace cpg
+#else   // CPG_EMU: tcgen05 kernels do not exist in the CPU emulation; the selection logic never picks them there
+namespace cpg {
+int launch_gru_fwd_enc_tc(cudaStream_t, const GruSeq*, int, int, int) { return CPG_ECUDA; }
+int launch_gru_fwd_dec_tc(cudaStream_t, const GruSeq&, int, int, int) { return CPG_ECUDA; }
+int launch_gru_bwd_enc_tc(cudaStream_t, const GruSeq*, int, int, int) { return CPG_ECUDA; }
+int launch_gru_bwd_dec_tc(cudaStream_t, const GruSeq&, int, int, int) { return CPG_ECUDA; }
+}  // namespace cpg
 #endif  // CPG_EMU
