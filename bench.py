@@ -301,7 +301,7 @@ def run_ours(args):
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cb.time_wae_cpu(B, N_VOCAB, steps=2, warmup=1, budget_s=90.0)
+        r = cb.time_wae_cpu(B, N_VOCAB, steps=5, warmup=1, budget_s=90.0)      # ~13 s of CPU work on 16 host threads
         cpu = {'value': r['seq_per_s'], 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'],
                'sample': '%d full iterations at batch %d after 1 warm-up (%.0f ms/step)' % (
                    r['steps_timed'], B, r['ms_per_step'])}
@@ -315,7 +315,10 @@ def run_ours(args):
         'config': {'workload': WORKLOAD, 'per_gpu_batch': B, 'global_batch': gb, 'seq_len': L, 'n_vocab': N_VOCAB,
                    'parallelism': 'dp%d' % world if world > 1 else 'single',
                    'l2_policy': 'per-step working set (activation stash ~1.1 GB) exceeds the 126 MB L2; no flush needed',
-                   'noise': 'Philox in-kernel, regenerated every step'},
+                   'noise': 'Philox in-kernel, regenerated every step',
+                   'arithmetic': 'fp32 storage and accumulation; recurrence / decoder-output contractions as split-bf16 '
+                                 '(x1+x2, 3 products; logits 3 terms) tcgen05 MMAs, weight-gradient and MMD Gram contractions tf32, '
+                                 'dense layers fp32 SIMT'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * L * 8, 'd2h_bytes_per_step': 16 * 4 + 8,
                 'api': 'train_vae.train_vae(cfgv, model, dataset): pinned host tokens copied H2D every step (one step ahead, copy stream), '
                   'scalar block copied D2H every step (collected after the next step is enqueued)'},
