@@ -1,27 +1,29 @@
 // GRU recurrences (forward with activation stash, and BPTT) on the 5th-gen tensor cores, with
-// fp32-grade accuracy.  Same math and the same HBM stash layouts as the fp32 SIMT kernels of gru.cu
-// (models/encoder.py:25-30,42 and models/decoder.py:40,77; gate order r,z,n; h' = (1-z) n + z h),
-// so either flavour of forward pairs with either flavour of backward.
+// fp32-grade accuracy.  Same math as the fp32 SIMT kernels of gru.cu (models/encoder.py:25-30,42 and
+// models/decoder.py:40,77; gate order r,z,n; h' = (1-z) n + z h) and the same row-major h / dg layouts;
+// the gate stash (r, z, n, hn) is private to this file's forward/backward pair and tile-major.
 //
 // Formulation.  The batch is the N side of the MMA and the weights are the M side ("transposed"):
 //     forward   G^T[3H x nb] = W_hh[3H x H]   . h^T[H x nb]          (M tiles of 128 gate rows)
 //     backward  dh^T[H x nb] = W_hh^T[H x 3H] . (dr,dz,dhn)^T[3H x nb]
-// N = 32 batch rows per MMA, so B = 4096 gives 128 CTAs whatever the hidden size (the row-major
-// variant is stuck at M = 128 rows per tile, i.e. 32..64 CTAs on 148 SMs).  tcgen05.mma kind::f16 with
-// bf16 operands and fp32 accumulation in TMEM; every fp32 operand x is split x = x1 + x2 (two bf16
-// terms, 16 mantissa bits) and the three products x1 w1 + x1 w2 + x2 w1 are accumulated: relative
-// error 2^-16 per term, well inside the 1e-4 parity bar of the path (a single bf16/tf32 pass is not).
+// N = nb = 16 batch rows per MMA ("chain"), so B = 4096 gives 512 / 256 independent chains on 128 CTAs
+// whatever the hidden size (with the batch on M a tile is 128 rows: 32..64 CTAs on 148 SMs).
+// tcgen05.mma kind::f16 with bf16 operands and fp32 accumulation in TMEM; every fp32 operand x is split
+// x = x1 + x2 (two bf16 terms, 16 mantissa bits) and the three products x1 w1 + x1 w2 + x2 w1 are
+// accumulated: relative error 2^-16 per term, inside the 1e-4 parity bar (a single bf16/tf32 pass is not).
+// W_hh (both terms) lives in TENSOR MEMORY as the A operand for all L steps (tcgen05.st once per CTA):
+// from shared memory every N = 16..32 MMA re-read 4 KB of weights and ran at 43 clk instead of 16.
 //
-// One CTA = NSUB sub-tiles of 32 batch rows of one direction, all L steps:
-//   warp NW (last) : TMEM owner; one elected thread issues the MMAs of a sub-tile as soon as that
-//                    sub-tile's operand tile of the previous step is complete (mbarrier bar_x)
-//   warps 0..NW-1  : per sub-tile and step
-//        phase 1  tcgen05.ld (lane = gate row, 32 batch columns) -> P[batch][gate] in shared memory
-//        phase 2  thread = (batch row, 4 consecutive hidden units): gate math, fp32 stash to HBM with
-//                 row-contiguous float4 stores, next operand tile (bf16 split, K-major core matrices)
-//   With NSUB = 2 the MMAs of one sub-tile run under the epilogue of the other (ping-pong).
-// W_hh (both bf16 terms) stays in shared memory for all L steps; operand tiles use the no-swizzle
-// K-major core-matrix layout with a 16-byte pad on the K stride (bank-conflict-free 8-byte stores).
+// One CTA = NCH chains of one direction (encoder 4, decoder 2), all L steps.  Per chain:
+//   one MMA warp    : waits for the chain's operand tile of the previous step (mbarrier bar_x), an elected
+//                     lane issues the step's MMAs and commits to bar_d; in the backward kernel it also streams the
+//                     next step's gate planes in with cp.async.bulk (forward, decoder: streams the finished ones out)
+//   NWG warps       : phase 1  tcgen05.ld (lane = gate row, nb batch columns) -> P[batch][gate] in shared memory
+//                     phase 2  thread = (batch row, 4 consecutive hidden units): gate math, fp32 stash with
+//                              row-contiguous float4 stores, next operand tile (bf16 split, K-major core matrices,
+//                              16-byte pad on the K stride: bank-conflict-free 8-byte stores), arrive on bar_x
+//   The chains of a CTA are independent: the MMA -> TMEM -> shared memory -> gate math latency chain of one runs
+//   under the others' (named barrier 1 + chain for the phase 1 -> 2 hand-over, no CTA-wide barrier in the loop).
 #include "ctx.h"
 #ifndef CPG_EMU
 #include <cuda_bf16.h>
