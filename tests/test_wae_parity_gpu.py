@@ -364,3 +364,38 @@ def test_side_stream_and_overlapped_noise_change_nothing(eng):
     assert torch.equal(g0, g1)
     assert torch.equal(p0, p1)
     assert torch.equal(s0, s1)
+
+
+@pytest.mark.parametrize('batch', [1025, 2500])
+def test_auto_tensor_core_paths_match_simt_at_ragged_large_batches(eng, batch):
+    """Auto mode at batches that are not multiples of any tile (16-row chains, 128-row decoder-output tiles, 16-row
+    weight-gradient stages, pre-rounded dg): every tcgen05 path on vs every path on the exact fp32 SIMT kernels."""
+    from cpg_b200 import _lib
+    dev = torch.device('cuda')
+    p = ow.random_params(V, seed=31)
+    tokens = ow.synthetic_tokens(batch, V, seed=32).to(dev)
+    noise = dev_noise(ow.draw_noise(batch, seed=33), dev)
+    opts = ('gru_tensor_core', 'dec_out_tensor_core', 'wgrad_tensor_core', 'mmd_tensor_core')
+    out = {}
+    try:
+        for flag in (0, 1):
+            for o in opts:
+                _lib.set_option(o, flag)
+            st = eng.FlatState(V, dev)
+            st.load(p)
+            scal, ex = eng.train_step(st, tokens, noise, eng.make_hparams(beta=1.3, clip_norm=1e9), want=('mu', 'logits'))
+            out[flag] = (scal.cpu(), {k: v.cpu() for k, v in ex.items() if v is not None},
+                         {k: v.clone().cpu() for k, v in st.views(st.grads).items()})
+    finally:
+        for o in opts:
+            _lib.set_option(o, 1)
+    (s0, e0, g0), (s1, e1, g1) = out[0], out[1]
+    for k in ('loss', 'recon', 'mmd', 'mmdrf', 'grad_norm'):
+        assert float(s1[eng.SC[k]]) == pytest.approx(float(s0[eng.SC[k]]), rel=1e-4, abs=1e-7), k
+    # two fp32-grade evaluations compared with each other (each is held to 1e-4 / 2e-6 against the oracle in the tests
+    # above): the absolute floor is twice the oracle tests' (logits passing through zero)
+    for k in e0:
+        np.testing.assert_allclose(e1[k].numpy(), e0[k].numpy(), rtol=1e-4, atol=4e-6, err_msg=k)
+    for k in ow.UNIQUE_VAE_PARAMS:
+        scale = float(g0[k].abs().max()) + 1e-12
+        np.testing.assert_allclose(g1[k].numpy(), g0[k].numpy(), rtol=1e-3, atol=1e-4 * scale, err_msg=k)
