@@ -664,11 +664,15 @@ k_gru_bwd_tc(BwdArgs a) {
         // gate stash of (this chain, step s) -> shared memory: one bulk copy per plane through the TMA engine
         const float* gates_src = (dir ? a.gates[1] : a.gates[0]);
         float* G = Gb + ch * 4 * NB * HP;
+        // a chain entirely past the batch (ragged last CTA) has no stash tile of its own: it reads tile 0 instead
+        // (its results are never stored), so that no copy leaves the stash allocation of ceil(B/32) tiles
+        const int first_row = row0 + ch * NB;
+        const int src_row = first_row < ((B + 31) & ~31) ? first_row : (first_row & 31);
         auto load_gates = [&](int s) {
             tc::mbar_expect_tx(&bar_g[ch], 4 * C::G_PLANE);
 #pragma unroll
             for (int pl = 0; pl < 4; ++pl)
-                bulk_load(G + pl * NB * HP, gates_src + gate_stash_offset<HP>(row0 + ch * NB, s, L) + (size_t)pl * 32 * HP,
+                bulk_load(G + pl * NB * HP, gates_src + gate_stash_offset<HP>(src_row, s, L) + (size_t)pl * 32 * HP,
                           C::G_PLANE, &bar_g[ch]);
         };
         if (elect_one()) load_gates(L - 1);
