@@ -159,3 +159,21 @@ def test_shard_bounds():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_bench_work_model_and_traffic_table():
+    """bench.py's roofline inputs: every kernel that can dominate the step has an algorithmic-work entry, the byte counts
+    follow the stash layout (planes x hidden x rows x 4 B), and the committed ncu traffic table is readable."""
+    import bench
+    B, L = 4096, 25
+    work = bench.kernel_work(B)
+    for name in ('k_gru_fwd_enc_tc', 'k_gru_fwd_dec_tc', 'k_gru_bwd_enc_tc', 'k_gru_bwd_dec_tc', 'k_wgrad_tc_enc',
+                 'k_wgrad_tc_dec', 'k_dec_out_tc', 'k_sgemm'):
+        assert name in work and work[name][1] > 0, name
+    assert work['k_gru_fwd_enc_tc'][1] == 2 * B * L * 5 * 80 * 4          # h + 4 gate planes, two directions
+    assert work['k_gru_bwd_enc_tc'][1] == 2 * B * L * 9 * 80 * 4          # 5 planes in, 4 dg planes out
+    assert work['k_gru_bwd_dec_tc'][1] == B * L * 10 * 104 * 4            # + dh_out
+    assert work['k_gru_fwd_enc_tc'] == work['k_gru_fwd_enc']              # SIMT and tcgen05 flavours move the same bytes
+    t = bench.load_traffic('k_gru_bwd_enc_tc')
+    assert t is None or (0.5 < t / work['k_gru_bwd_enc_tc'][1] < 1.5)     # ncu DRAM bytes ~ algorithmic bytes
+    assert bench.load_traffic('no_such_kernel') is None
