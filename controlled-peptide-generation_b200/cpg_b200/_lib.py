@@ -62,6 +62,7 @@ def _signatures(L):
         'cpg_sm_count': (I, [P]),
         'cpg_workspace_bytes': (I64, [P]),
         'cpg_launch_count': (I64, [P]),
+        'cpg_stash_generation': (I64, [P]),
         'cpg_check_errors': (I, [P, P]),
         'cpg_vae_param_count': (I64, [I]),
         'cpg_vae_param_layout': (I, [I, POINTER(I64), POINTER(I64)]),
@@ -77,6 +78,10 @@ def _signatures(L):
         'cpg_wae_step_phase2': (I, [P, P, P, P, I, I, I, POINTER(WaeInputs), POINTER(LossNoise),
                                     POINTER(TrainHparams), P, P, P]),
         'cpg_clip_adam_step': (I, [P, P, P, P, P, P, I, POINTER(TrainHparams), P]),
+        'cpg_side_stream': (P, [P]),
+        'cpg_dp_tail_count': (I, []),
+        'cpg_dp_pack_tail': (I, [P, P, P]),
+        'cpg_dp_apply_tail': (I, [P, P, P, P]),
         'cpg_softmax_xent': (I, [P, P, P, P, I, I, I, P, P]),
         'cpg_latent_stats': (I, [P, P, P, P, I, P]),
         'cpg_mmd_full': (I, [P, P, P, P, I, F, P]),

@@ -2,6 +2,7 @@
 backward / fused-step calls and the individual loss ops.  All tensors are torch
 CUDA tensors owned by the caller; this module only marshals pointers.
 """
+import contextlib
 import math
 from collections import OrderedDict
 from ctypes import byref, c_void_p
@@ -23,6 +24,8 @@ PARAM_NAMES = (
     'decoder.fc.1.weight', 'decoder.fc.1.bias',
 )
 EMB, ENC_H, ZD, CD, DEC_H = 150, 80, 100, 2, 102
+DP_TAIL = 8          # == cpg_dp_tail_count()
+STATIC_STREAM = 0x80000000
 
 
 def param_shapes(n_vocab):
@@ -45,7 +48,17 @@ class FlatState:
         self.offsets, self.sizes, self.total = _lib.param_layout(self.n_vocab)
         self.shapes = param_shapes(self.n_vocab)
         z = lambda: torch.zeros(self.total, dtype=torch.float32, device=self.device)
-        self.params, self.grads, self.adam_m, self.adam_v = z(), z(), z(), z()
+        self.params, self.adam_m, self.adam_v = z(), z(), z()
+        # the flat gradient is followed by a few floats that ride along in the data-parallel gradient all-reduce
+        # (parallel.py): one buffer, `grads` is the view the kernels and nn.Parameter.grad see
+        self.grads_ext = torch.zeros(self.total + DP_TAIL, dtype=torch.float32, device=self.device)
+        self.grads = self.grads_ext[:self.total]
+        self.step = 0
+
+    def reset_optimizer(self):
+        """Fresh Adam state, as a newly constructed optim.Adam (train_vae.py:15 builds one per call)."""
+        self.adam_m.zero_()
+        self.adam_v.zero_()
         self.step = 0
 
     def views(self, flat):
@@ -103,10 +116,19 @@ def wae_forward(params, n_vocab, tokens, eps, c, word_drop=None, out_keep=None, 
     return mu, logvar, z, logits
 
 
+def stash_generation(device):
+    """Id of the BPTT stash the context holds right now (-1: none); see cpg_stash_generation."""
+    return int(lib().cpg_stash_generation(context(device)))
+
+
 def wae_backward(params, n_vocab, tokens, eps, c, word_drop, out_keep, p_out, d_mu, d_logvar, d_z, d_logits,
-                 grads_out=None):
+                 grads_out=None, expect_generation=None):
     B, L = _check_shapes(tokens, eps, c, word_drop, out_keep)
     dev = tokens.device
+    if expect_generation is not None and stash_generation(dev) != expect_generation:
+        raise _lib.CpgLibraryError(
+            'backward of a forward whose activation stash is gone: another forward / decode / encode ran on this '
+            'device in between (the context keeps ONE stash; run forward -> backward pairs one at a time)')
     if grads_out is None:
         grads_out = torch.empty_like(params)
     inp = _inputs(tokens, eps, c, word_drop, out_keep, p_out)
@@ -195,12 +217,38 @@ def step_phase2(state, tokens, noise, hp, coupled, p_out=0.3):
     return scalars
 
 
-def clip_adam(state, hp):
+def clip_adam(state, hp, out=None):
+    """clip_grad_norm_ + Adam on the flat buffers; the pre-clip norm goes to `out` (1 float, device)."""
     dev = state.params.device
-    gn = torch.zeros(1, device=dev)
+    gn = torch.zeros(1, device=dev) if out is None else out
     check(lib().cpg_clip_adam_step(context(dev), stream_ptr(), ptr(state.params), ptr(state.grads), ptr(state.adam_m),
                                    ptr(state.adam_v), state.n_vocab, byref(hp), ptr(gn)), 'cpg_clip_adam_step')
     return gn
+
+
+# ------------------------------------------------------------------ data-parallel plumbing (parallel.py)
+def dp_tail_count():
+    return DP_TAIL
+
+
+def side_stream(device):
+    """The library's internal side stream as a torch stream (None when option side_stream = 0)."""
+    p = lib().cpg_side_stream(context(device))
+    return torch.cuda.ExternalStream(p, device=device) if p else None
+
+
+def stats_stream(device):
+    """Context manager: work enqueued inside is ordered behind the stream that produced phase 1's `coupled`."""
+    s = side_stream(device)
+    return torch.cuda.stream(s) if s is not None else contextlib.nullcontext()
+
+
+def dp_pack_tail(tail):
+    check(lib().cpg_dp_pack_tail(context(tail.device), stream_ptr(), ptr(tail)), 'cpg_dp_pack_tail')
+
+
+def dp_apply_tail(tail, scalars):
+    check(lib().cpg_dp_apply_tail(context(tail.device), stream_ptr(), ptr(tail), ptr(scalars)), 'cpg_dp_apply_tail')
 
 
 # ------------------------------------------------------------------ losses.py ops
@@ -279,8 +327,9 @@ def alloc_noise(B, L, device, rf_dim=500, seed=1238, full_mmd=True):
     }
     if full_mmd:
         noise['z_prior_full'] = torch.empty(B, ZD, device=dev)
-    fill_normal(noise['rf_w'], seed, 0xF001)
-    fill_uniform(noise['rf_b'], seed, 0xF002, scale=2 * math.pi)
+    # static draws live in the upper half of the Philox stream-id space; the per-step noise uses 16*step + k < 2**31
+    fill_normal(noise['rf_w'], seed, STATIC_STREAM | 0xF001)
+    fill_uniform(noise['rf_b'], seed, STATIC_STREAM | 0xF002, scale=2 * math.pi)
     return noise
 
 

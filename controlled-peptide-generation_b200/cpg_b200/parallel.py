@@ -1,22 +1,32 @@
-"""Data-parallel WAE iteration: one process per GPU, batch sharded by sample, and the three exchange
-points of SURVEY.md 8(e) done with torch.distributed (NCCL over NVLink on the GPU box, gloo in the
-CPU tests of the host logic):
+"""Data-parallel WAE iteration: one process per GPU, batch sharded by sample, exchanges done with
+torch.distributed (NCCL over NVLink on the GPU box; gloo in the CPU tests of this host logic).
 
-  phase 1 (local)  forward through the decoder GRU + local statistics
-  all-reduce SUM   `coupled` = [n_tok, -, 5 latent sums, RF feature sums of z, of z_prior]  (~4 KB)
-  phase 2 (local)  CE with the GLOBAL token count, RF-MMD gradient from the GLOBAL feature means,
-                   BPTT, weight gradients (each rank's share of the global-batch gradient)
-  all-reduce SUM   flat gradient buffer (1.03 MB)
-  clip + Adam      identical on every rank (weights stay replicated bit-for-bit)
+  phase 1 (local)     forward through the decoder GRU; the local statistics that couple the batch
+                      (`coupled` = [n_tok, -, 5 latent sums, RF feature sums of z, of z_prior], ~4 KB) are
+                      produced on the library's side stream while the decoder recurrence runs
+  all-reduce #1 SUM   of `coupled`, ASYNC, enqueued behind the side stream: it runs under the decoder
+                      recurrence; the main stream waits for it only when phase 2 starts
+  phase 2 (local)     CE with the GLOBAL token count, RF-MMD gradient from the GLOBAL feature means, BPTT,
+                      weight gradients (this rank's share of the global-batch gradient)
+  all-reduce #2 SUM   flat gradient (1.03 MB) + an 8-float tail carrying the local NLL sum (and the
+                      partial sums of the distributed full-kernel MMD) -- one collective, no third one
+  clip + Adam         identical on every rank (weights stay replicated bit-for-bit)
 
 The reference has no distributed code; the contract is "N ranks on shards == one process on the
-concatenated batch".  The log-only full-kernel MMD is evaluated on the local shard unless
-`full_mmd='global'` (all-gather of z and z_prior, then every rank computes the global value).
+concatenated batch" (SURVEY.md 8e).  Replicas are made identical at start-up (`sync_replicas`: broadcast
+of params / Adam moments / step from rank 0) and can be verified at any time (`check_replicas`).
+Each rank's loader must yield ITS shard of the global batch (`assert_distinct_shards` warns when two
+ranks present the same token batch).
+
+The log-only full-kernel MMD: full_mmd='local' evaluates it on the local shard (cheap; a per-shard
+value), 'global' all-gathers z / z_prior (ragged shards are padded) and evaluates the global-batch value.
 """
+import warnings
+
 import torch
 import torch.distributed as dist
 
-from . import engine
+from . import engine as _engine
 
 
 def is_distributed():
@@ -36,12 +46,69 @@ def global_batch_size(local_batch, device, group=None):
     return int(sizes.item())
 
 
-def dp_train_step(state, tokens, noise, hp, p_out=0.3, group=None, full_mmd='local', global_batch=None):
-    """One data-parallel iteration on this rank's shard.  Returns the scalar block (device); after the
-    call scalars hold GLOBAL recon / KL / RF-MMD values (the kernels compose them from the reduced
-    statistics), the full-kernel MMD slot is local unless full_mmd == 'global'.  Pass `global_batch`
-    (sum of the shard sizes) when it is constant to avoid one tiny all-reduce + host sync per step."""
+def sync_replicas(state, group=None, src=0):
+    """Start-up broadcast: parameters, Adam moments and the step count of rank `src` to every rank."""
+    for t in (state.params, state.adam_m, state.adam_v):
+        dist.broadcast(t, src, group=group)
+    step = torch.tensor([state.step], device=state.params.device, dtype=torch.int64)
+    dist.broadcast(step, src, group=group)
+    state.step = int(step.item())
+    return state
+
+
+def check_replicas(state, group=None):
+    """Raise if the replicas' parameters / Adam moments / step differ (bit-level checksums, min == max)."""
+    def chk(t):
+        b = t.detach().contiguous().view(torch.int32).to(torch.int64)
+        return torch.stack([b.sum(), (b * (torch.arange(b.numel(), device=b.device) % 8191 + 1)).sum()])
+    sums = torch.cat([chk(state.params), chk(state.adam_m), chk(state.adam_v),
+                      torch.tensor([state.step], device=state.params.device, dtype=torch.int64)])
+    lo, hi = sums.clone(), sums.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    if not torch.equal(lo, hi):
+        raise RuntimeError('data-parallel replicas have diverged (params / Adam state / step checksums differ '
+                           'across ranks); call sync_replicas() after loading weights')
+
+
+def assert_distinct_shards(tokens, group=None):
+    """Same-seed loaders would train N copies of one batch: warn when two ranks hold identical tokens."""
+    t = tokens.detach().to(torch.int64).reshape(-1)
+    w = torch.arange(t.numel(), device=t.device, dtype=torch.int64) % 1021 + 1
+    h = torch.stack([(t * w).sum(), t.sum()]).reshape(1, 2)
     world = dist.get_world_size(group)
+    hs = [torch.empty_like(h) for _ in range(world)]
+    dist.all_gather(hs, h, group=group)
+    keys = [tuple(x.reshape(-1).tolist()) for x in hs]
+    if len(set(keys)) < world:
+        warnings.warn('data-parallel ranks received identical token batches: give every rank its own shard of the '
+                      'global batch (rank-sharded loader / distinct sampler seeds)')
+        return False
+    return True
+
+
+def all_gather_ragged(t, group=None):
+    """Concatenation over ranks of [n_r, ...] tensors whose n_r may differ (padded exchange)."""
+    world = dist.get_world_size(group)
+    n = torch.tensor([t.shape[0]], device=t.device, dtype=torch.int64)
+    ns = [torch.empty_like(n) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    ns = [int(x.item()) for x in ns]
+    nmax = max(ns)
+    pad = t.contiguous()
+    if pad.shape[0] < nmax:
+        pad = torch.cat([pad, pad.new_zeros((nmax - pad.shape[0],) + tuple(pad.shape[1:]))])
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    return torch.cat([o[:k] for o, k in zip(outs, ns)])
+
+
+def dp_train_step(state, tokens, noise, hp, p_out=0.3, group=None, full_mmd='local', global_batch=None, eng=None):
+    """One data-parallel iteration on this rank's shard.  Returns the scalar block (device): recon / KL /
+    RF-MMD / loss are GLOBAL values; the full-kernel MMD slot is the local-shard value unless
+    full_mmd == 'global'.  Pass `global_batch` (sum of the shard sizes) when it is constant to avoid one
+    tiny all-reduce + host sync per step.  `eng` (default: cpg_b200.engine) provides the local phases."""
+    eng = eng or _engine
     hp.global_batch = int(global_batch) if global_batch else global_batch_size(tokens.shape[0], tokens.device, group)
     state.step += 1
     hp.adam_step = state.step
@@ -50,24 +117,22 @@ def dp_train_step(state, tokens, noise, hp, p_out=0.3, group=None, full_mmd='loc
     if full_mmd != 'local':
         local_noise = dict(noise)
         local_noise.pop('z_prior_full', None)            # phase 2 must not compute the local value
-    coupled, z = engine.step_phase1(state, tokens, local_noise, hp, p_out)
-    dist.all_reduce(coupled, group=group)
-    scalars = engine.step_phase2(state, tokens, local_noise, hp, coupled, p_out)
-    # recon needs the global sum of NLL: the local sum sits in SC_NLL_SUM
-    dist.all_reduce(state.grads, group=group)
-    gn = engine.clip_adam(state, hp)
-    fix = scalars[engine.SC['nll_sum']:engine.SC['nll_sum'] + 1].clone()
-    dist.all_reduce(fix, group=group)
-    ntok = scalars[engine.SC['ntok']]
-    recon_global = fix[0] / torch.clamp(ntok, min=1.0)
-    delta = recon_global - scalars[engine.SC['recon']]
-    scalars[engine.SC['recon']] = recon_global
-    scalars[engine.SC['loss']] += delta
-    scalars[engine.SC['grad_norm']] = gn[0]
+    gext = state.grads_ext
+    tail = gext[state.grads.numel():]
+    coupled, z = eng.step_phase1(state, tokens, local_noise, hp, p_out)
+    # exchange 1, asynchronous: ordered behind the side stream that produced `coupled`, overlapped with the decoder
+    # recurrence already enqueued on the main stream
+    with eng.stats_stream(tokens.device):
+        work = dist.all_reduce(coupled, group=group, async_op=True)
+    work.wait()                                          # stream-level wait (no host block with NCCL)
+    scalars = eng.step_phase2(state, tokens, local_noise, hp, coupled, p_out)
+    eng.dp_pack_tail(tail)
+    dist.all_reduce(gext, group=group)                   # exchange 2: gradients + NLL sum
+    g = eng.SC['grad_norm']
+    eng.clip_adam(state, hp, out=scalars[g:g + 1])
+    eng.dp_apply_tail(tail, scalars)
     if full_mmd == 'global' and z_prior_full is not None:
-        zs = [torch.empty_like(z) for _ in range(world)]
-        zp = [torch.empty_like(z_prior_full) for _ in range(world)]
-        dist.all_gather(zs, z.contiguous(), group=group)
-        dist.all_gather(zp, z_prior_full.contiguous(), group=group)
-        scalars[engine.SC['mmd']] = engine.mmd_full(torch.cat(zs), torch.cat(zp), hp.mmd_sigma)[0]
+        zs = all_gather_ragged(z, group)
+        zp = all_gather_ragged(z_prior_full, group)
+        scalars[eng.SC['mmd']] = eng.mmd_full(zs, zp, hp.mmd_sigma)[0]
     return scalars

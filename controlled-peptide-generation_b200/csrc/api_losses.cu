@@ -108,10 +108,8 @@ int cpg_mmd_full(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* z
     if (!ctx || !z || !zp || !out || B < 2) { set_error("cpg_mmd_full: bad argument"); return CPG_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if ((ctx->base == nullptr || ctx->ws.B < B) && (rc = ensure_workspace(ctx, B, ctx->ws.L > 0 ? ctx->ws.L : 2,
-                                                                      ctx->ws.V > 0 ? ctx->ws.V : 4,
-                                                                      ctx->ws.R > 0 ? ctx->ws.R : 500, s))) return rc;
-    if ((rc = launch_mmd_full(s, z, zp, B, sigma, ctx->ws.mmd_ws, out))) return rc;
+    if ((rc = ensure_aux(ctx, mmd_ws_floats(B) * sizeof(float), s))) return rc;
+    if ((rc = launch_mmd_full(s, z, zp, B, sigma, (float*)ctx->aux, out))) return rc;
     return check_launch("cpg_mmd_full");
 }
 
@@ -120,17 +118,24 @@ int cpg_mmd_rf(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* zp,
     if (!ctx || !z || !zp || !rf_w || !rf_b || !loss_out || B < 1 || R < 1) { set_error("cpg_mmd_rf: bad argument"); return CPG_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if ((ctx->base == nullptr || ctx->ws.B < B || ctx->ws.R != R) &&
-        (rc = ensure_workspace(ctx, B, ctx->ws.L > 0 ? ctx->ws.L : 2, ctx->ws.V > 0 ? ctx->ws.V : 4, R, s))) return rc;
-    Workspace& w = ctx->ws;
-    launch_sgemm(s, B, R, ZD, 1.f, z, ZD, 1, rf_w, R, 1, 0.f, w.rf_pre1, R, nullptr, 1, nullptr);
-    launch_sgemm(s, B, R, ZD, 1.f, zp, ZD, 1, rf_w, R, 1, 0.f, w.rf_pre2, R, nullptr, 1, nullptr);
-    launch_rf_colsum(s, w.rf_pre1, rf_b, B, R, sigma, w.rf_part, w.rf_nchunk, w.rf_sum1);
-    launch_rf_colsum(s, w.rf_pre2, rf_b, B, R, sigma, w.rf_part, w.rf_nchunk, w.rf_sum2);
-    launch_rf_loss(s, w.rf_sum1, w.rf_sum2, R, B, sigma, 1.0f, w.rf_coef, loss_out);
+    // own scratch (never the step workspace: a loss evaluated between forward and backward must not touch the stash)
+    const int nchunk = std::max(1, std::min(B, 2 * ctx->sm_count));
+    const size_t nB = align_up((size_t)B * R, 64), nC = align_up((size_t)nchunk * R, 64), nR = align_up((size_t)R, 64);
+    if ((rc = ensure_aux(ctx, (2 * nB + nC + 3 * nR) * sizeof(float), s))) return rc;
+    float* pre1 = (float*)ctx->aux;
+    float* pre2 = pre1 + nB;
+    float* part = pre2 + nB;
+    float* sum1 = part + nC;
+    float* sum2 = sum1 + nR;
+    float* coef = sum2 + nR;
+    launch_sgemm(s, B, R, ZD, 1.f, z, ZD, 1, rf_w, R, 1, 0.f, pre1, R, nullptr, 1, nullptr);
+    launch_sgemm(s, B, R, ZD, 1.f, zp, ZD, 1, rf_w, R, 1, 0.f, pre2, R, nullptr, 1, nullptr);
+    launch_rf_colsum(s, pre1, rf_b, B, R, sigma, part, nchunk, sum1);
+    launch_rf_colsum(s, pre2, rf_b, B, R, sigma, part, nchunk, sum2);
+    launch_rf_loss(s, sum1, sum2, R, B, sigma, 1.0f, coef, loss_out);
     if (dz != nullptr) {
-        launch_rf_grad_prep(s, w.rf_pre1, rf_b, w.rf_coef, B, R, sigma);
-        launch_sgemm(s, B, ZD, R, 1.f, w.rf_pre1, R, 1, rf_w, 1, R, 0.f, dz, ZD, nullptr, 1, nullptr);
+        launch_rf_grad_prep(s, pre1, rf_b, coef, B, R, sigma);
+        launch_sgemm(s, B, ZD, R, 1.f, pre1, R, 1, rf_w, 1, R, 0.f, dz, ZD, nullptr, 1, nullptr);
     }
     return check_launch("cpg_mmd_rf");
 }

@@ -138,7 +138,8 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
 
 int ensure_workspace(cpg_ctx* ctx, int B, int L, int V, int R, cudaStream_t stream) {
     Workspace& w = ctx->ws;
-    if (w.B == B && w.L == L && w.V == V && w.R == R && ctx->base != nullptr) return CPG_OK;
+    if (w.B == B && w.L == L && w.V == V && w.R >= R && ctx->base != nullptr) return CPG_OK;
+    if (w.R > R) R = w.R;                           // never shrink the random-feature scratch
     Workspace probe;
     size_t need = layout_workspace(ctx, probe, B, L, V, R, nullptr);
     if (need > ctx->capacity) {
@@ -156,6 +157,23 @@ int ensure_workspace(cpg_ctx* ctx, int B, int L, int V, int R, cudaStream_t stre
     }
     layout_workspace(ctx, w, B, L, V, R, (char*)ctx->base);
     ctx->have_stash = false;
+    return CPG_OK;
+}
+
+int ensure_aux(cpg_ctx* ctx, size_t bytes, cudaStream_t stream) {
+    if (bytes <= ctx->aux_capacity && ctx->aux != nullptr) return CPG_OK;
+    dev_sync(stream);
+    if (ctx->aux) dev_free(ctx->aux);
+    ctx->aux = nullptr;
+    ctx->aux_capacity = 0;
+    void* p = nullptr;
+    bytes = align_up(bytes, 1 << 20);
+    if (dev_alloc(&p, bytes) != 0) {
+        set_error("scratch allocation of " + std::to_string(bytes) + " bytes failed");
+        return CPG_ENOMEM;
+    }
+    ctx->aux = p;
+    ctx->aux_capacity = bytes;
     return CPG_OK;
 }
 
@@ -438,6 +456,7 @@ int cpg_create(cpg_ctx** out, int device) {
 int cpg_destroy(cpg_ctx* c) {
     if (c == nullptr) return CPG_OK;
     if (c->base) dev_free(c->base);
+    if (c->aux) dev_free(c->aux);
     if (c->ints) dev_free(c->ints);
 #ifndef CPG_EMU
     if (c->side_stream) {
@@ -456,6 +475,7 @@ int cpg_destroy(cpg_ctx* c) {
 int cpg_sm_count(const cpg_ctx* c) { return c ? c->sm_count : 0; }
 int64_t cpg_workspace_bytes(const cpg_ctx* c) { return c ? (int64_t)c->capacity : 0; }
 int64_t cpg_launch_count(const cpg_ctx*) { return (int64_t)g_launch_count; }
+int64_t cpg_stash_generation(const cpg_ctx* c) { return (c && c->have_stash) ? c->stash_gen : -1; }
 
 int cpg_check_errors(cpg_ctx* c, cpg_stream stream) {
     int host[2] = {0, 0};
@@ -509,6 +529,7 @@ int cpg_wae_forward(cpg_ctx* ctx, cpg_stream stream, const float* params, int V,
         launch_dec_out(s, a, ctx->sm_count);
     }
     ctx->have_stash = keep != 0;
+    if (keep) ctx->stash_gen++;
     return check_launch("cpg_wae_forward");
 }
 
@@ -594,6 +615,7 @@ int cpg_wae_step_phase1(cpg_ctx* ctx, cpg_stream stream, const float* params, in
     if (logvar) dev_copy(logvar, w.logvar, (size_t)B * ZD * 4, s);
     if (z) dev_copy(z, w.z, (size_t)B * ZD * 4, s);
     ctx->have_stash = true;
+    ctx->stash_gen++;
     return check_launch("cpg_wae_step_phase1");
 }
 
@@ -604,7 +626,7 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
     if (rc) return rc;
     if (!ctx || !params || !grads || !in || !nz || !hp || !coupled) { set_error("cpg_wae_step_phase2: null argument"); return CPG_EINVAL; }
     Workspace& w = ctx->ws;
-    if (!ctx->have_stash || w.B != B || w.L != L || w.V != V || w.R != hp->rf_dim) {
+    if (!ctx->have_stash || w.B != B || w.L != L || w.V != V || w.R < hp->rf_dim) {
         set_error("cpg_wae_step_phase2: phase1 was not run for this shape");
         return CPG_EINVAL;
     }
@@ -690,6 +712,26 @@ int cpg_wae_train_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* gr
     if ((rc = cpg_wae_step_phase2(ctx, stream, params, grads, V, B, L, in, nz, &h, cpl, scalars, logits))) return rc;
     float* gn = scalars ? scalars + SC_GRAD_NORM : nullptr;
     return cpg_clip_adam_step(ctx, stream, params, grads, m, v, V, &h, gn);
+}
+
+// ---- data-parallel helpers (cpg_b200/parallel.py) ----------------------------------------------------------
+void* cpg_side_stream(cpg_ctx* ctx) {
+    if (!ctx || !side_ready(ctx)) return nullptr;
+    return ctx->side_stream;
+}
+
+int cpg_dp_tail_count(void) { return DP_TAIL; }
+
+int cpg_dp_pack_tail(cpg_ctx* ctx, cpg_stream stream, float* tail) {
+    if (!ctx || !tail || ctx->base == nullptr) { set_error("cpg_dp_pack_tail: null argument / no step was run"); return CPG_EINVAL; }
+    launch_dp_pack_tail((cudaStream_t)stream, ctx->ws.nll_sum, tail);
+    return check_launch("cpg_dp_pack_tail");
+}
+
+int cpg_dp_apply_tail(cpg_ctx* ctx, cpg_stream stream, const float* tail, float* scalars) {
+    if (!ctx || !tail || !scalars) { set_error("cpg_dp_apply_tail: null argument"); return CPG_EINVAL; }
+    launch_dp_apply_tail((cudaStream_t)stream, tail, scalars);
+    return check_launch("cpg_dp_apply_tail");
 }
 
 int cpg_wae_decode_teacher(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int B, int L,

@@ -39,6 +39,11 @@ struct cpg_ctx {
     int* ints = nullptr;           // [0] ntok (int), [1] sticky token-range error flag
     cpg::Workspace ws;
     bool have_stash = false;
+    int64_t stash_gen = 0;         // bumped by every call that (re)writes the BPTT stash: a backward names the one it expects
+    // scratch of the stand-alone loss ops (cpg_mmd_rf / cpg_mmd_full): separate from the step workspace so that a
+    // loss evaluated between a forward and its backward can neither re-lay-out nor overwrite the stash
+    void* aux = nullptr;
+    size_t aux_capacity = 0;
     int64_t launches = 0;
     // side stream for the latency-bound loss kernels that only depend on (mu, logvar, z): they run under the
     // decoder recurrence / decoder-output kernels of the main stream (fork / join with events; api_wae.cu)
@@ -51,4 +56,5 @@ struct cpg_ctx {
 namespace cpg {
 void set_error(const std::string& msg);
 int ensure_workspace(cpg_ctx* ctx, int B, int L, int V, int R, cudaStream_t stream);
+int ensure_aux(cpg_ctx* ctx, size_t bytes, cudaStream_t stream);
 }

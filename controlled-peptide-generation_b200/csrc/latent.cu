@@ -354,6 +354,22 @@ __global__ void k_compose_scalars(ComposeArgs a) {
 }
 void launch_compose_scalars(cudaStream_t s, const ComposeArgs& a) { CPG_LAUNCH(k_compose_scalars, 1, 32, 0, s, a); }
 
+// Data-parallel bookkeeping: the local NLL sum rides behind the flat gradient through the gradient all-reduce
+// (no third collective); afterwards the logged reconstruction loss / total loss are re-based on the global sum.
+__global__ void k_dp_pack_tail(const float* __restrict__ nll_sum, float* __restrict__ tail) {
+    if (threadIdx.x < DP_TAIL) tail[threadIdx.x] = threadIdx.x == 0 ? *nll_sum : 0.f;
+}
+__global__ void k_dp_apply_tail(const float* __restrict__ tail, float* __restrict__ o) {
+    if (threadIdx.x != 0) return;
+    const float ntok = o[SC_NTOK];
+    const float recon = ntok > 0.f ? tail[0] / ntok : 0.f;
+    o[SC_LOSS] += recon - o[SC_RECON];
+    o[SC_RECON] = recon;
+    o[SC_NLL_SUM] = tail[0];
+}
+void launch_dp_pack_tail(cudaStream_t s, const float* nll_sum, float* tail) { CPG_LAUNCH(k_dp_pack_tail, 1, 32, 0, s, nll_sum, tail); }
+void launch_dp_apply_tail(cudaStream_t s, const float* tail, float* scalars) { CPG_LAUNCH(k_dp_apply_tail, 1, 32, 0, s, tail, scalars); }
+
 __global__ void k_int_to_float(const int* __restrict__ src, float* __restrict__ dst, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = (float)src[i];

@@ -53,6 +53,10 @@ int launch_mmd_full_tc2(cudaStream_t s, const float* z, const float* zp, int N, 
 extern int g_opt_mmd_tc;     // 0 = fp32 SIMT, 1 = persistent tcgen05 (default), 3 = one-tile-per-CTA tcgen05
 extern int g_sm_count;
 void launch_compose_scalars(cudaStream_t s, const ComposeArgs& a);
+// data-parallel tail: extra floats all-reduced together with the flat gradient ([0] = NLL sum; rest reserved)
+constexpr int DP_TAIL = 8;
+void launch_dp_pack_tail(cudaStream_t s, const float* nll_sum, float* tail);
+void launch_dp_apply_tail(cudaStream_t s, const float* tail, float* scalars);
 void launch_int_to_float(cudaStream_t s, const int* src, float* dst, int n);
 
 }  // namespace cpg

@@ -42,6 +42,7 @@ class _WaeFunction(torch.autograd.Function):
         mu, logvar, z, logits = engine.wae_forward(flat.params, flat.n_vocab, tokens, eps, c, word_drop, out_keep,
                                                    p_out, want_logits=True, keep_for_backward=need_grad)
         ctx.model, ctx.p_out = model, p_out
+        ctx.stash_gen = engine.stash_generation(tokens.device) if need_grad else None
         ctx.save_for_backward(tokens, eps, c, word_drop, out_keep)
         ctx.n_params = len(params)
         return mu, logvar, z, logits
@@ -52,7 +53,8 @@ class _WaeFunction(torch.autograd.Function):
         flat = ctx.model._flat
         cont = lambda t: None if t is None else t.contiguous()
         g = engine.wae_backward(flat.params, flat.n_vocab, tokens, eps, c, word_drop, out_keep, ctx.p_out,
-                                cont(d_mu), cont(d_logvar), cont(d_z), cont(d_logits))
+                                cont(d_mu), cont(d_logvar), cont(d_z), cont(d_logits),
+                                expect_generation=ctx.stash_gen)
         views = flat.views(g)
         return (None,) * 7 + tuple(views[name] for name in engine.PARAM_NAMES)
 

@@ -51,6 +51,10 @@ def _train_fused(cfgv, model, dataset):
     global last_scalars
     st = model.bind_grads()
     dev = st.device
+    if not model.word_emb.weight.requires_grad:
+        raise NotImplementedError('freeze_embeddings=True: the fused clip+Adam updates every VAE tensor; train with '
+                                  'cfg.b200.fused_step = False (autograd path, optim.Adam over vae_params())')
+    st.reset_optimizer()                             # the reference builds a fresh optim.Adam per call (train_vae.py:15)
     wm = cfg.losses.wae_mmd
     if wm.kernel != 'gaussian':
         raise NotImplementedError("only the gaussian MMD kernel is built")
@@ -63,6 +67,7 @@ def _train_fused(cfgv, model, dataset):
     sync_every = int(getattr(cfg.b200, 'sync_scalars_every', 0))
     distributed = parallel.is_distributed()
     if distributed:
+        parallel.sync_replicas(st)                   # rank 0's weights everywhere; moments / step were just reset
         # rank-distinct noise rows; rf_w / rf_b come from the shared seed inside alloc_noise
         rank_seed = (seed + 0x9E3779B97F4A7C15 * (1 + parallel.dist.get_rank())) % (1 << 63)
     stepper, global_batch = None, None
@@ -82,6 +87,9 @@ def _train_fused(cfgv, model, dataset):
         if bufs[slot] is None or bufs[slot].shape != (Bn, Ln):
             bufs[slot] = torch.empty(Bn, Ln, dtype=torch.int64, device=dev)
             used_ev[slot] = None
+            # the caching allocator may hand back a block whose last readers are still queued on the compute
+            # stream (a previous token buffer, noise of a replaced stepper): order the copy behind them
+            copy_stream.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(copy_stream):
             if used_ev[slot] is not None:
                 copy_stream.wait_event(used_ev[slot])                    # its previous reader (two iterations ago)
@@ -99,6 +107,8 @@ def _train_fused(cfgv, model, dataset):
         if stepper is None or stepper.B != B or stepper.L != L:
             stepper = engine.FusedStepper(st, B, L, hp, seed=seed, p_word=p_word, p_out=p_out, rf_dim=wm.rf_dim)
             global_batch = parallel.global_batch_size(B, dev) if distributed else B
+            if distributed:
+                parallel.assert_distinct_shards(tokens.to(dev))          # warns when every rank feeds the same batch
         if slot is None:
             tok = tokens if tokens.is_contiguous() else tokens.contiguous()
         else:
@@ -109,7 +119,8 @@ def _train_fused(cfgv, model, dataset):
         if distributed:
             hp.beta = beta
             engine.fill_step_noise(stepper.noise, rank_seed, it, p_word, p_out, overlap=True)
-            scal = parallel.dp_train_step(st, tok, stepper.noise, hp, p_out=p_out, global_batch=global_batch)
+            scal = parallel.dp_train_step(st, tok, stepper.noise, hp, p_out=p_out, global_batch=global_batch,
+                                          full_mmd=str(getattr(cfg.b200, 'dp_full_mmd', 'local')))
         else:
             scal = stepper.step(tok, it, beta)
         if slot is not None:

@@ -47,6 +47,10 @@ int cpg_sm_count(const cpg_ctx* ctx);
 int64_t cpg_workspace_bytes(const cpg_ctx* ctx);
 /* number of kernel launches enqueued by this context since creation */
 int64_t cpg_launch_count(const cpg_ctx* ctx);
+/* Generation of the activation stash held by the context: changes with every cpg_wae_forward(keep_for_backward=1)
+ * / cpg_wae_step_phase1, -1 when no stash is valid (an inference call or a re-layout dropped it).  A caller that
+ * defers cpg_wae_backward (autograd) records it after the forward and compares before the backward. */
+int64_t cpg_stash_generation(const cpg_ctx* ctx);
 /* device->host check of the sticky token-range flag (synchronises `stream`) */
 int cpg_check_errors(cpg_ctx* ctx, cpg_stream stream);
 
@@ -157,6 +161,18 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
                         const float* coupled, float* scalars, float* logits);
 int cpg_clip_adam_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* adam_m, float* adam_v,
                        int n_vocab, const cpg_train_hparams* hp, float* grad_norm_out);
+
+/* Data-parallel plumbing (no reference counterpart: the reference is single-process).
+ * cpg_side_stream: the context's internal side stream (cudaStream_t; NULL when option side_stream = 0).  phase1
+ *   produces `coupled` on it, so a caller that enqueues its collective on that stream starts the exchange as soon
+ *   as the statistics exist, under the decoder recurrence of the main stream.
+ * cpg_dp_pack_tail: after phase2, writes float[cpg_dp_tail_count()] = {local NLL sum, 0...}; the caller appends
+ *   it to the flat gradient so that ONE all-reduce carries both.
+ * cpg_dp_apply_tail: after the all-reduce, re-bases scalars[RECON], [LOSS], [NLL_SUM] on the global NLL sum. */
+void* cpg_side_stream(cpg_ctx* ctx);
+int cpg_dp_tail_count(void);
+int cpg_dp_pack_tail(cpg_ctx* ctx, cpg_stream stream, float* tail);
+int cpg_dp_apply_tail(cpg_ctx* ctx, cpg_stream stream, const float* tail_reduced, float* scalars);
 
 /* ---- individual losses (losses.py) ---------------------------------------------------------- */
 /* recon_dec (losses.py:18-31): mean NLL over non-<pad> next-token targets; optional d_logits.

@@ -1,10 +1,15 @@
-"""Two real GPUs, NCCL: the data-parallel iteration (phase1 -> all-reduce -> phase2 -> all-reduce ->
-clip+Adam) on two shards equals the single-GPU fused iteration on the whole batch, and the replicas
-stay bit-identical.  Skipped on boxes with fewer than 2 GPUs."""
+"""The product's data-parallel iteration (cpg_b200.parallel.dp_train_step: CUDA phases + torch.distributed
+exchanges) on shards equals the single-GPU fused iteration on the whole batch, and the replicas stay
+bit-identical.  Three launch shapes so that the path is exercised on whatever box runs the suite:
+
+  * world 1, NCCL, one process                       -- always (1 GPU)
+  * world 2, two processes sharing cuda:0, gloo       -- always (1 GPU; gloo moves CUDA tensors through the host,
+                                                         NCCL refuses two ranks on one device)
+  * world 2, NCCL, one process per GPU                -- boxes with >= 2 GPUs (skipped with that reason otherwise)
+"""
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 
@@ -23,59 +28,103 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, ret):
-    import sys
-    from conftest import PKG
-    sys.path.insert(0, PKG)
+def _run_rank(rank, world, backend, device_index, full_mmd='global'):
+    """Two iterations of dp_train_step on this rank's shard; -> (scalars [2, SC], flat params)."""
     import torch.distributed as dist
     from cpg_b200 import engine, parallel
-    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
-    torch.cuda.set_device(rank)
-    dev = torch.device('cuda', rank)
-    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    dev = torch.device('cuda', device_index)
     p = ow.random_params(V, seed=5)
     tokens = ow.synthetic_tokens(B, V, seed=6)
     noise = ow.draw_noise(B, seed=7)
     lo, hi = parallel.shard_bounds(B, rank, world)
     st = engine.FlatState(V, dev)
-    st.load(p)
+    if rank == 0:
+        st.load(p)                                     # the other ranks get the weights from the start-up broadcast
+    parallel.sync_replicas(st)
     nz = {k: (v[lo:hi] if v.shape[0] == B else v).to(dev).contiguous() for k, v in noise.items()}
     out = []
     for it in range(2):
         hp = engine.make_hparams(beta=1.0 + 0.5 * it)
-        sc = parallel.dp_train_step(st, tokens[lo:hi].to(dev).contiguous(), nz, hp, full_mmd='global')
+        sc = parallel.dp_train_step(st, tokens[lo:hi].to(dev).contiguous(), nz, hp, full_mmd=full_mmd)
         out.append(sc.cpu())
     flat = st.params.clone()
     gathered = [torch.empty_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
-    if rank == 0:
-        ret['scalars'] = torch.stack(out)
-        ret['params'] = flat.cpu()
-        ret['replicas_equal'] = all(torch.equal(gathered[0], g) for g in gathered[1:])
-    dist.destroy_process_group()
+    parallel.check_replicas(st)                        # raises if any replica drifted
+    return torch.stack(out), flat.cpu(), all(torch.equal(gathered[0], g) for g in gathered[1:])
 
 
-def test_two_gpu_nccl_equals_single_gpu():
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs 2 GPUs')
-    import torch.multiprocessing as mp
+def _worker(rank, world, port, backend, same_device, ret):
+    import sys
+    from conftest import PKG
+    sys.path.insert(0, PKG)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    di = 0 if same_device else rank
+    torch.cuda.set_device(di)
+    kw = {'device_id': torch.device('cuda', di)} if backend == 'nccl' else {}
+    dist.init_process_group(backend, rank=rank, world_size=world, **kw)
+    try:
+        scal, flat, same = _run_rank(rank, world, backend, di)
+        if rank == 0:
+            ret['scalars'], ret['params'], ret['replicas_equal'] = scal, flat, same
+    finally:
+        dist.destroy_process_group()
+
+
+def _single_gpu_reference():
     from cpg_b200 import engine
-    world = 2
-    mgr = mp.Manager()
-    ret = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
-    assert ret['replicas_equal']
     dev = torch.device('cuda', 0)
     p = ow.random_params(V, seed=5)
     tokens = ow.synthetic_tokens(B, V, seed=6).to(dev)
     noise = {k: v.to(dev) for k, v in ow.draw_noise(B, seed=7).items()}
     st = engine.FlatState(V, dev)
     st.load(p)
+    scal = []
     for it in range(2):
         sc, _ = engine.train_step(st, tokens, noise, engine.make_hparams(beta=1.0 + 0.5 * it))
+        scal.append(sc.cpu())
+    return engine, st, scal
+
+
+def _compare(ret):
+    engine, st, scal = _single_gpu_reference()
+    assert ret['replicas_equal']
+    for it in range(2):
         got = ret['scalars'][it]
         for k in ('loss', 'recon', 'kl', 'mmd', 'mmdrf', 'logvar_kl', 'grad_norm'):
-            assert float(got[engine.SC[k]]) == pytest.approx(float(sc[engine.SC[k]]), rel=1e-4, abs=1e-7), (it, k)
+            assert float(got[engine.SC[k]]) == pytest.approx(float(scal[it][engine.SC[k]]), rel=1e-4, abs=1e-7), (it, k)
     single = st.views(st.params)
-    multi = st.views(ret['params'].to(dev))
-    assert_params_close(multi, single, st.views(st.grads), 'dp2', max_outliers=3)
+    multi = st.views(ret['params'].to(st.device))
+    assert_params_close(multi, single, st.views(st.grads), 'dp', max_outliers=3)
+
+
+def _spawn(world, backend, same_device):
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), backend, same_device, ret), nprocs=world, join=True)
+    return ret
+
+
+def test_world1_nccl_equals_fused_step():
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(_free_port()))
+    torch.cuda.set_device(0)
+    dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda', 0))
+    try:
+        scal, flat, same = _run_rank(0, 1, 'nccl', 0)
+    finally:
+        dist.destroy_process_group()
+    _compare({'scalars': scal, 'params': flat, 'replicas_equal': same})
+
+
+def test_two_ranks_on_one_gpu_gloo_equal_single_gpu():
+    _compare(_spawn(2, 'gloo', True))
+
+
+def test_two_gpu_nccl_equals_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('box has %d GPU; the same ranks-vs-single check runs above over gloo on one GPU, and the 2-GPU '
+                    'NCCL result of this test is recorded in profiles/ (gpurun --gpus 2)' % torch.cuda.device_count())
+    _compare(_spawn(2, 'nccl', False))

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from conftest import load_golden
-from helpers import assert_params_close, clipped
+from helpers import assert_params_close, clipped, compare_beam
 from oracle import class_sampling as oc
 from oracle import decode as od
 from oracle import wae as ow
@@ -150,9 +150,7 @@ def test_generate_sentences_modes(model):
     c = torch.from_numpy(fx['trained/c'])
     hyps, zz, c_ix = model.generate_sentences(z.shape[0], z, c, sample_mode='beam', beam_size=5)
     ref, margins = fx['trained/beam_hyps'], fx['trained/beam_margin']
-    for j, hs in enumerate(hyps):
-        if margins[j] >= 1e-4:
-            assert hs[0] == [int(t) for t in ref[j, 0] if t >= 0]
+    compare_beam(hyps, [[[int(t) for t in h if t >= 0] for h in hs] for hs in ref], margins, 'generate_sentences', n_hyps=1)
     assert np.array_equal(c_ix.cpu().numpy(), fx['trained/c'].argmax(1))
     g, _, _ = model.generate_sentences(z.shape[0], z, c, sample_mode='greedy')
     assert np.array_equal(g.cpu().numpy(), fx['trained/greedy'])
@@ -193,3 +191,42 @@ def test_mogQ_rejection_sample_and_pipeline(model):
     assert 0.1 < df['accept'].mean() < 0.5
     out = sp.run_sampling(model, ds, Q, n_samples_per_round=200, n_samples_acc=20, max_rounds=20)
     assert out['accept'].sum() >= 20 and out['peptide'].is_unique
+
+
+def test_stale_stash_raises_and_losses_do_not_touch_the_stash(model):
+    """The context keeps ONE activation stash: a backward whose stash was replaced by another forward must raise
+    (not silently use the wrong activations); stand-alone loss ops between forward and backward use their own
+    scratch, whatever rf_dim is."""
+    import losses
+    from cpg_b200 import _lib
+    dev = torch.device('cuda')
+    B = 9
+    t1 = ow.synthetic_tokens(B, V, seed=3).to(dev)
+    t2 = ow.synthetic_tokens(B, V, seed=4).to(dev)
+    model.train()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    (mu1, lv1), (z1, _), lg1 = model(t1)
+    (mu2, lv2), (z2, _), lg2 = model(t2)                     # replaces the stash of the first forward
+    l1, l2 = losses.recon_dec(t1, lg1), losses.recon_dec(t2, lg2)
+    with pytest.raises(_lib.CpgLibraryError, match='stash'):
+        (l1 + l2).backward()
+    # forward -> RF-MMD with a non-default rf_dim (own scratch) -> encode of another batch size is NOT allowed in
+    # between (it would drop the stash) but loss ops are: backward works and matches a run without them
+    model.zero_grad()
+    losses.rf.clear()
+    torch.manual_seed(1)
+    np.random.seed(1)
+    (mu, lv), (z, _), lg = model(t1)
+    extra = losses.mmd_rf(z, torch.randn_like(z), sigma=7.0, kernel='gaussian', rf_dim=300)
+    full = losses.mmd_full_kernel(z.detach(), torch.randn_like(z), sigma=7.0, kernel='gaussian')
+    assert torch.isfinite(full)
+    (losses.recon_dec(t1, lg) + 0.0 * extra).backward()
+    g_a = model.decoder.fc[1].weight.grad.clone()
+    model.zero_grad()
+    torch.manual_seed(1)
+    np.random.seed(1)
+    (mu, lv), (z, _), lg = model(t1)
+    losses.recon_dec(t1, lg).backward()
+    assert torch.equal(g_a, model.decoder.fc[1].weight.grad)
+    losses.rf.clear()

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from conftest import load_golden
-from helpers import (assert_params_close, clipped, dev_noise, digest, rel_err)
+from helpers import (GRAD_NOISE, PARAM_ATOL, assert_params_close, clipped, dev_noise, digest, rel_err)
 from oracle import wae as ow
 
 pytestmark = pytest.mark.gpu
@@ -154,27 +154,52 @@ def test_train_step_tensor_core_recurrences_match_oracle(eng, batch, z_regu):
 
 
 def test_full_batch_4096_matches_reference_golden(eng):
-    """BASELINE config 2 (B=4096): inputs regenerated from the recorded seeds; scalars and
-    gradient / parameter digests from the live reference."""
+    """BASELINE config 2 (B=4096).  Inputs are regenerated from the recorded seeds.
+    (i) logged scalars, forward / gradient / post-Adam parameter digests of the LIVE reference (golden);
+    (ii) every element of mu, logvar, z, logits, of every gradient and of the post-Adam parameters against the
+    oracle evaluated in-test on the same inputs (the oracle itself is pinned to the reference by the goldens)."""
     dev = torch.device('cuda')
     fx = load_golden('wae_b4096.npz')
     B = int(fx['batch'])
+    p0 = _params()
     st = eng.FlatState(V, dev)
-    st.load(_params())
+    st.load(p0)
     tokens = ow.synthetic_tokens(B, V, seed=int(fx['token_seeds'][0]))
     noise = ow.draw_noise(B, seed=int(fx['noise_seeds'][0]))
-    hp = eng.make_hparams(beta=float(fx['betas'][0]))
-    scal, ex = eng.train_step(st, tokens.to(dev), dev_noise(noise, dev), hp, want=('mu', 'logvar', 'logits'))
+    beta = float(fx['betas'][0])
+    hp = eng.make_hparams(beta=beta)
+    scal, ex = eng.train_step(st, tokens.to(dev), dev_noise(noise, dev), hp, want=('mu', 'logvar', 'z', 'logits'))
     scal = scal.cpu()
     keys = [str(k) for k in fx['logged_keys']]
     for j, k in enumerate(keys):
         assert float(scal[eng.SC[LOG_TO_SC[k]]]) == pytest.approx(float(fx['logged'][0][j]), rel=1e-4, abs=1e-7), k
     for k in ('mu', 'logvar', 'logits'):
         np.testing.assert_allclose(digest(k, ex[k]), fx['it0/%s_digest' % k], rtol=2e-4, atol=2e-5, err_msg=k)
+    got_p = st.views(st.params)
     for k in ow.UNIQUE_VAE_PARAMS:
         ref = fx['it0/grad_digest/' + k]
         np.testing.assert_allclose(digest(k, st.views(st.grads)[k]), ref, rtol=2e-3, atol=2e-4 * abs(ref[1]) + 1e-7,
                                    err_msg='grad ' + k)
+        # post-Adam parameters of the reference: L2 norm, and the 32 sampled entries to 2 % of an Adam step (entries
+        # whose reference gradient is rounding noise are decided by that noise: set aside, see helpers.py)
+        pref = fx['it0/param_digest/' + k]
+        pd_ = digest(k, got_p[k])
+        assert pd_[1] == pytest.approx(pref[1], rel=1e-5), 'param L2 ' + k
+        n = got_p[k].numel()
+        assert abs(pd_[0] - pref[0]) <= PARAM_ATOL * n ** 0.5 * 4 + 1e-6 * abs(pref[0]), 'param sum ' + k
+        live = np.abs(ref[2:]) > GRAD_NOISE
+        np.testing.assert_allclose(pd_[2:][live], pref[2:][live], rtol=2e-4, atol=PARAM_ATOL, err_msg='param ' + k)
+    # ---- element-wise against the oracle on the same inputs (CPU, a few seconds)
+    p = {k: v.clone() for k, v in p0.items()}
+    oscal, ograds, aux = ow.train_step(p, {}, tokens, noise, it=0, beta=beta, with_full_mmd=False)
+    for k in ('mu', 'logvar', 'z', 'logits'):
+        np.testing.assert_allclose(ex[k].cpu().numpy(), aux[k].detach().numpy(), rtol=1e-4, atol=2e-6, err_msg=k)
+    want = clipped(ograds, oscal['grad_norm'])
+    got = st.views(st.grads)
+    for k in ow.UNIQUE_VAE_PARAMS:
+        scale = float(want[k].abs().max()) + 1e-12
+        np.testing.assert_allclose(got[k].cpu().numpy(), want[k].numpy(), rtol=1e-3, atol=1e-4 * scale, err_msg=k)
+    assert_params_close(got_p, p, want, 'B=4096 post-Adam', max_outliers=3)
 
 
 def test_loss_ops_match_oracle(eng):
