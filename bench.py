@@ -33,16 +33,6 @@ METRIC, UNIT = 'wae_train_seq_per_s', 'seq/s'
 WORKLOAD = 'WAE phase-1 full config, batch=4096 len<=25, fp32 (BASELINE.json configs[1])'
 
 
-def load_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu summary."""
-    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
-    try:
-        with open(path) as f:
-            return json.load(f).get(kernel)
-    except (OSError, ValueError):
-        return None
-
-
 def load_peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
@@ -86,38 +76,111 @@ class ClockSampler(threading.Thread):
                 'samples': len(self.rows), 'power_w_max': max(float(r[2]) for r in self.rows)}
 
 
-# per-kernel algorithmic work of ONE launch at batch B: (flops, bytes)
+# ---- roofline model ---------------------------------------------------------------------------
+# ALGORITHMIC work of one launch at per-GPU batch B: the bytes / FLOPs the path needs whatever the implementation
+# moves -- h-stash written once by the forward recurrences and read once by BPTT (25*(160+102)*4 B/seq each way),
+# tokens, logits only when materialised, mu/logvar/z/eps, parameters + gradients + Adam state once per step; FLOPs of
+# the genuine contractions (recurrent, [z;c] projection, heads, fc, RF map, full-kernel MMD Gram).  `frac` in the
+# bench line is this figure / event time / measured peak; what the kernel ACTUALLY moves (ncu dram bytes,
+# profiles/ncu_traffic.json) is reported next to it as frac_dram and traffic_ratio = dram / algorithmic.
 def kernel_work(B, L=SEQ_LEN, V=N_VOCAB, R=500):
-    He, Hd, HP, Z = 80, 102, 104, 100
+    He, Hd, Z, E = 80, 102, 100, 150
     f4 = 4
-    fwd_enc = (2 * 2 * B * L * He * 3 * He, 2 * B * L * (5 * He) * f4)           # writes h + (r, z, n, hn), both directions
-    fwd_dec = (2 * B * L * Hd * 3 * Hd, B * L * (5 * HP) * f4)
-    bwd_enc = (2 * 2 * B * L * He * 3 * He, 2 * B * L * (5 * He + 4 * He) * f4)  # reads 4 gate planes + h_prev, writes 4 dg planes
-    bwd_dec = (2 * B * L * Hd * 3 * Hd, B * L * (6 * HP + 4 * HP) * f4)          # + dh_out
-    # the twelve small dense products of one iteration (heads, [z;c] projection, RF map and their transposes): (M, N, K)
-    gemms = [(B, Z, 2 * He)] * 2 + [(B, 3 * HP, HP)] + [(B, R, Z)] * 2 + [(B, HP, 3 * HP), (3 * HP, HP, B)] + \
-            [(B, 2 * He, Z)] * 2 + [(Z, 2 * He, B)] * 2 + [(B, Z, R)]
-    g_flops = sum(2 * m * n * k for m, n, k in gemms)
-    g_bytes = sum((m * k + k * n + m * n) * f4 for m, n, k in gemms)
-    return {
-        'k_gru_fwd_enc': fwd_enc, 'k_gru_fwd_enc_tc': fwd_enc,
-        'k_gru_fwd_dec': fwd_dec, 'k_gru_fwd_dec_tc': fwd_dec,
-        'k_gru_bwd_enc': bwd_enc, 'k_gru_bwd_enc_tc': bwd_enc,
-        'k_gru_bwd_dec': bwd_dec, 'k_gru_bwd_dec_tc': bwd_dec,
-        'k_wgrad_hh_enc': (2 * B * L * He * 3 * He, B * L * (4 * He) * f4),
-        'k_wgrad_hh_dec': (2 * B * L * Hd * 3 * Hd, B * L * (4 * HP) * f4),
-        # one pass over the 4 dg planes + h: dW_hh (3 planes x H) and the token-table gradient (4 planes x 32 one-hot columns)
-        'k_wgrad_tc_enc': (2 * B * L * (3 * He * He + 4 * He * 32), B * L * (5 * He) * f4),
-        'k_wgrad_tc_dec': (2 * B * L * (3 * HP * HP + 4 * HP * 32), B * L * (5 * HP) * f4),
-        'k_mmd_gram_tc': (3 * 2 * B * B * 100, 2 * B * 128 * f4),
-        'k_mmd_gram_tc2': (3 * 2 * B * B * 100, 2 * B * 128 * f4),
-        'k_dec_out': (2 * 3 * B * L * Hd * V, B * L * (2 * HP * f4 + Hd)),
-        'k_dec_out_tc': (2 * 3 * B * L * Hd * V, B * L * (2 * HP * f4 + Hd)),
-        'k_mmd_gram': (3 * 2 * B * B * 100, 2 * B * 100 * f4),
-        'k_dtable': (B * L * 4 * HP, B * L * 4 * HP * f4),
-        'k_sgemm': (g_flops / len(gemms), g_bytes / len(gemms)),                  # average of the 12 launches of one iteration
-        'k_input_grads': (2 * V * 150 * (2 * 3 * He + 3 * HP), V * (2 * 4 * He + 4 * HP) * f4),
+    rec_enc = 2 * 2 * B * L * He * 3 * He            # both directions
+    rec_dec = 2 * B * L * Hd * 3 * Hd
+    h_enc, h_dec = 2 * B * L * He * f4, B * L * Hd * f4
+    n_par = 258568
+    w = {
+        'k_gru_fwd_enc': (rec_enc, h_enc + B * L), 'k_gru_fwd_dec': (rec_dec, h_dec + B * L),
+        # BPTT: W_hh^T dg contraction + (when fused) the dW_hh / token-table contractions; reads the h stash
+        'k_gru_bwd_enc': (2 * rec_enc, h_enc), 'k_gru_bwd_dec': (2 * rec_dec, h_dec),
+        'k_wgrad_tc_enc': (rec_enc // 2, 0), 'k_wgrad_tc_dec': (rec_dec, 0),     # part of BPTT algorithmically: no bytes of their own
+        'k_wgrad_hh_enc': (rec_enc // 2, 0), 'k_wgrad_hh_dec': (rec_dec, 0),
+        'k_dec_out': (2 * 3 * B * L * Hd * V, 0),      # fc fwd + 2 bwd products; h already counted with the recurrences
+        'k_mmd_gram': (3 * 2 * B * B * Z, 2 * B * Z * f4),
+        'k_clip_adam': (0, 7 * n_par * f4), 'k_sumsq_partial': (0, n_par * f4),
+        'k_prep_tokens': (0, B * L * 8), 'k_step_noise': (0, B * (3 * Z * f4 + L * Hd + L + 8)),
+        'k_input_grads': (2 * V * E * (2 * 3 * He + 3 * Hd) * 2, 0),
+        'k_prep_weights': (2 * V * E * (2 * 3 * He + 3 * Hd), 2 * n_par * f4),
     }
+    # the dense layers, by shape label "MxNxK": heads (B x 100 x 160, x2 + transposes), [z;c] projection, RF map
+    return w
+
+
+def work_for(label, work, B):
+    """(flops, bytes) of one launch of kernel `label`; dense products carry their shape in the label."""
+    import re
+    m = re.match(r'k_(?:sgemm|gemm_tc)\w*\[(\d+)x(\d+)x(\d+)(?:x(\d+))?\]', label)
+    if m:
+        M, N, K = int(m.group(1)), int(m.group(2)), int(m.group(3))
+        n = int(m.group(4) or 1)
+        return 2 * M * N * K * n, 0                 # operands are activations already counted (mu/z/h) or parameters
+    for k in sorted(work, key=len, reverse=True):
+        if label.startswith(k):
+            return work[k]
+    return None
+
+
+def step_work(B, L=SEQ_LEN, V=N_VOCAB):
+    """60 KB/seq + params/grads/Adam once; 11.8 MFLOP/seq + the MMD Gram."""
+    seq_bytes = 200 + 2 * L * (160 + 102) * 4 + 2 * L * V * 4 + 3200
+    return {'alg_bytes': B * seq_bytes + 6.2e6, 'alg_flops': B * 11.8e6 + 3 * 2 * B * B * 100}
+
+
+def build_roofline(rows, K, B, ms_per_step, peaks, peak_src):
+    """rows: (label, total ms, launches) over K serialised steps -> the `roofline` object of the bench line."""
+    work = kernel_work(B)
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            traffic = json.load(f)
+    except (OSError, ValueError):
+        traffic = {}
+    hbm, tens = peaks['hbm_gbs'] * 1e9, peaks['bf16_tflops_sustained'] * 1e12
+    tot_ms = sum(ms for _, ms, _ in rows) / K
+    per, dram_known = {}, 0.0
+    for label, ms, cnt in rows:
+        kms = ms / max(cnt, 1)
+        wk = work_for(label, work, B)
+        tr = traffic.get(label)
+        ent = {'ms': round(kms, 4), 'launches_per_step': cnt / K, 'share_of_step': round(ms / K / tot_ms, 4)}
+        if wk is not None and kms > 0:
+            fl, by = wk
+            ent.update({'alg_flops': fl, 'alg_bytes': by,
+                        'frac_hbm_algorithmic': round(by / (kms / 1e3) / hbm, 4),
+                        'frac_tensor_algorithmic': round(fl / (kms / 1e3) / tens, 4)})
+        if tr is not None and kms > 0:
+            ent.update({'traffic': tr, 'frac_dram': round(tr / (kms / 1e3) / hbm, 4)})
+            if wk is not None and wk[1] > 0:
+                ent['traffic_ratio'] = round(tr / wk[1], 2)
+            dram_known += tr * cnt / K
+        per[label] = ent
+    dom = max(per, key=lambda k: per[k]['share_of_step'] )
+    d = per[dom]
+    fh, ft = d.get('frac_hbm_algorithmic', 0.0), d.get('frac_tensor_algorithmic', 0.0)
+    kms = d['ms'] / 1e3
+    if ft > fh:
+        roof = {'bound': 'tensor', 'achieved': round(d.get('alg_flops', 0) / kms / 1e12, 3), 'peak': peaks['bf16_tflops_sustained'],
+                'unit': 'TFLOP/s', 'frac': ft}
+    else:
+        roof = {'bound': 'hbm', 'achieved': round(d.get('alg_bytes', 0) / kms / 1e9, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': fh}
+    sw = step_work(B)
+    step = {'ms': round(ms_per_step, 4), 'alg_bytes': sw['alg_bytes'], 'alg_flops': sw['alg_flops'],
+            'frac_hbm_algorithmic': round(sw['alg_bytes'] / (ms_per_step / 1e3) / hbm, 4),
+            'frac_tensor_algorithmic': round(sw['alg_flops'] / (ms_per_step / 1e3) / tens, 4),
+            'dram_bytes_captured_kernels': dram_known,
+            'frac_hbm_dram': round(dram_known / (ms_per_step / 1e3) / hbm, 4) if dram_known else None,
+            'traffic_ratio': round(dram_known / sw['alg_bytes'], 2) if dram_known else None}
+    roof.update({'kernel': dom, 'kernel_ms': d['ms'], 'launches_per_step': d['launches_per_step'],
+                 'share_of_step': d['share_of_step'], 'frac_algorithmic': roof['frac'], 'frac_dram': d.get('frac_dram'),
+                 'traffic': d.get('traffic'), 'traffic_ratio': d.get('traffic_ratio'), 'step': step,
+                 'per_kernel': dict(sorted(per.items(), key=lambda kv: -kv[1]['share_of_step'])),
+                 'peak_source': peak_src + (' (MEASURED_PEAKS.json: HBM copy GB/s, bf16 sustained TFLOP/s)' if peak_src == 'measured' else ''),
+                 'note': 'dominant kernel = largest share of the step by CUDA events (serialised pass); frac = ALGORITHMIC bytes or '
+                         'FLOPs of that kernel (SURVEY 8d: h-stash once each way, genuine contractions) / event time / measured peak; '
+                         'frac_dram = ncu dram bytes of one launch (profiles/ncu_traffic.json) / event time / HBM peak; '
+                         'traffic_ratio = dram / algorithmic bytes; step = whole iteration against 60 KB/seq + 11.8 MFLOP/seq'})
+    return roof
 
 
 def setup_model(device):
@@ -142,13 +205,13 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     from cpg_b200 import _lib, engine, parallel, sampling
-    from oracle import wae as ow
-    from oracle import cpu_baseline as cb
+    import utils
+    from cpg_b200 import synth
 
     cfg, model = setup_model(dev)
     st = model.bind_grads()
     B, L, K, W = args.batch, SEQ_LEN, args.steps, args.warmup
-    tokens_host = ow.synthetic_tokens(B, N_VOCAB, seed=1238 + rank).pin_memory()
+    tokens_host = synth.synthetic_tokens(B, N_VOCAB, seed=1238 + rank).pin_memory()
     tokens = tokens_host.to(dev)
     noise = engine.alloc_noise(B, L, dev, seed=cfg.seed)
     hp = engine.make_hparams(lr=cfg.vae.lr, z_regu=cfg.vae.z_regu_loss, mmd_sigma=cfg.losses.wae_mmd.sigma,
@@ -160,7 +223,7 @@ def run_ours(args):
     def step():
         it = counter['it']
         counter['it'] += 1
-        hp.beta = float(ow.anneal_beta(it))
+        hp.beta = float(utils.anneal(cfg.vae.beta, it))
         engine.fill_step_noise(noise, seed, it, overlap=True)      # next reader is the train step below
         if world > 1:
             return parallel.dp_train_step(st, tokens, noise, hp, global_batch=gb)
@@ -204,42 +267,8 @@ def run_ours(args):
     rows = _lib.profile_read()
     _lib.profile_enable(False)
     _lib.set_option('side_stream', 1)
-    per_kernel = {name: (ms / max(cnt, 1), cnt / K) for name, ms, cnt in rows}
-    step_share = {name: ms / K for name, ms, cnt in rows}
-    # dominant kernel = largest share among single-launch kernels with a work model (k_sgemm is 12 different small
-    # products, listed in per_kernel with its average)
-    work_names = set(kernel_work(B).keys()) - {'k_sgemm'}
-    cand = {k: v for k, v in step_share.items() if k in work_names} or step_share
-    dom = max(cand, key=cand.get)
     peaks, peak_src = load_peaks()
-    work = kernel_work(B)
-    flops, nbytes = work.get(dom, (0, 0))
-    dur_s = per_kernel[dom][0] / 1e3
-    tf = flops / dur_s / 1e12 if dur_s > 0 else 0.0
-    gbs = nbytes / dur_s / 1e9 if dur_s > 0 else 0.0
-    tensor_frac = tf / peaks['bf16_tflops_sustained']
-    hbm_frac = gbs / peaks['hbm_gbs']
-    if tensor_frac >= hbm_frac:
-        roof = {'bound': 'tensor', 'achieved': round(tf, 3), 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                'frac': round(tensor_frac, 5)}
-    else:
-        roof = {'bound': 'hbm', 'achieved': round(gbs, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': round(hbm_frac, 5)}
-    per_kernel_roof = {}
-    for name, (kms, per_step) in per_kernel.items():
-        if name in work and kms > 0:
-            f, nb = work[name]
-            per_kernel_roof[name] = {'ms': round(kms, 4), 'launches_per_step': per_step,
-                                     'tflops': round(f / (kms / 1e3) / 1e12, 2), 'gbs': round(nb / (kms / 1e3) / 1e9, 1),
-                                     'frac_tensor': round(f / (kms / 1e3) / 1e12 / peaks['bf16_tflops_sustained'], 4),
-                                     'frac_hbm': round(nb / (kms / 1e3) / 1e9 / peaks['hbm_gbs'], 4)}
-    roof.update({'per_kernel': per_kernel_roof, 'kernel': dom, 'kernel_ms': round(per_kernel[dom][0], 4), 'launches_per_step': per_kernel[dom][1],
-                 'share_of_step': round(step_share[dom] / sum(step_share.values()), 4), 'traffic': load_traffic(dom),
-                 'peak_source': peak_src + ' (MEASURED_PEAKS.json, sustained)' if peak_src == 'measured' else peak_src,
-                 'note': 'dominant kernel = largest share of the step by CUDA events; per_kernel lists every kernel with a work model '
-                         '(FLOP/s against the bf16 tensor peak, bytes against the HBM copy peak); traffic = dram bytes of one launch from '
-                         'the committed ncu --set full capture (profiles/), null if that kernel was not captured',
-                 'top_kernels_ms_per_step': {k: round(v, 4) for k, v in sorted(step_share.items(), key=lambda x: -x[1])[:8]}})
+    roof = build_roofline(rows, K, B, ms_per_step, peaks, peak_src)
 
     # ---- end to end through the reference-facing API: host tokens -> train_vae.train_vae -> host scalars
     import tb_json_logger
@@ -272,7 +301,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     # ---- CLaSS (secondary metric of BASELINE.json): accepted samples/s, Philox draws + scores + accept
-    w, means, covs, clfs = cb.synthetic_class_setup()
+    w, means, covs, clfs = synth.synthetic_class_setup()
     gmm = sampling.GmmDevice(w, means, covs, dev)
     spec = sampling.ClassifierSpec(clfs, dev)
     n_draws = 10_000_000
@@ -301,6 +330,7 @@ def run_ours(args):
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline as cb          # the ONLY use of oracle/ by this arm: the CPU baseline leg
         r = cb.time_wae_cpu(B, N_VOCAB, steps=5, warmup=1, budget_s=90.0)      # ~13 s of CPU work on 16 host threads
         cpu = {'value': r['seq_per_s'], 'unit': UNIT, 'cores': r['cores'], 'kind': r['kind'],
                'sample': '%d full iterations at batch %d after 1 warm-up (%.0f ms/step)' % (

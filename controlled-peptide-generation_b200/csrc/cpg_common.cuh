@@ -34,6 +34,7 @@ namespace cpg {
 extern long long g_launch_count;      // kernels enqueued by this library (reported by cpg_launch_count)
 // optional per-kernel CUDA-event timing (cpg_profile_*): off by default, one branch per launch
 extern bool g_profile_on;
+const char* shape_label(const char* name, int M, int N, int K, int nprod);
 #ifndef CPG_EMU
 void prof_begin(const char* label, cudaStream_t s);
 void prof_end(cudaStream_t s);

@@ -313,7 +313,8 @@ static void launch_sgemm_impl(cudaStream_t s, int M, int N, int K, float alpha, 
 #ifndef CPG_EMU
     if (use_pipe) {
         dim3 grid(ceil_div(N, PN), ceil_div(M, PM), sec.mode == 2 ? 2 : split_k);
-#define CPG_PIPE(AK, BK) CPG_LAUNCH_NAMED("k_sgemm", (k_sgemm_pipe<AK, BK>), grid, 256, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, kchunk, ws, sec)
+        const char* lbl = g_profile_on ? shape_label("k_sgemm", M, N, K, sec.mode ? 2 : 1) : "k_sgemm";
+#define CPG_PIPE(AK, BK) CPG_LAUNCH_NAMED(lbl, (k_sgemm_pipe<AK, BK>), grid, 256, 0, s, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, kchunk, ws, sec)
         if (a_k && !b_k) CPG_PIPE(true, false);
         else if (a_k && b_k) CPG_PIPE(true, true);
         else if (!a_k && !b_k) CPG_PIPE(false, false);

@@ -4,11 +4,24 @@
 #include <string>
 #include <vector>
 #include <string.h>
+#include <stdio.h>
 #include "ctx.h"
 
 namespace cpg {
 
 bool g_profile_on = false;
+
+// "name[MxNxK]" / "name[MxNxKxn]" (n products in one launch) with static storage: the per-kernel timing keeps dense
+// products of different shapes apart
+const char* shape_label(const char* name, int M, int N, int K, int nprod) {
+    static std::map<std::string, std::string> pool;
+    char buf[96];
+    if (nprod > 1) snprintf(buf, sizeof(buf), "%s[%dx%dx%dx%d]", name, M, N, K, nprod);
+    else snprintf(buf, sizeof(buf), "%s[%dx%dx%d]", name, M, N, K);
+    auto it = pool.find(buf);
+    if (it == pool.end()) it = pool.emplace(buf, buf).first;
+    return it->second.c_str();
+}
 
 #ifndef CPG_EMU
 struct ProfRec { const char* label; cudaEvent_t a, b; };
