@@ -115,8 +115,9 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
     w.nll_sum = a.take<float>(4);
     // weight-gradient partials
     int ws_ = std::max(wgrad_splits(B, L, sm), wgrad_tc_splits(sm));
+    ws_ = std::max(ws_, std::max(bptt_fused_ctas_enc(B), bptt_fused_ctas_dec(B)));   // fused BPTT: one partial per CTA
     w.wg_part = a.take<float>((size_t)ws_ * 3 * DEC_HP * DEC_HP);
-    int ds_ = dtable_splits(B, L, sm);
+    int ds_ = std::max(dtable_splits(B, L, sm), std::max(bptt_fused_ctas_enc(B), bptt_fused_ctas_dec(B)));
     w.dt_part = a.take<float>((size_t)ds_ * V * 4 * DEC_HP);
     w.wg_part_dec = a.take<float>((size_t)ws_ * 3 * DEC_HP * DEC_HP);     // own partials: runs concurrently with the encoder's
     w.dt_part_dec = a.take<float>((size_t)ds_ * V * 4 * DEC_HP);
@@ -231,6 +232,9 @@ static bool use_gru_tc(int B) { return g_opt_gru_tc == 2 || (g_opt_gru_tc == 1 &
 #else
 static bool use_gru_tc(int) { return false; }
 #endif
+// g_opt_bptt_fused: 1 (default) = on the tcgen05 path the BPTT kernels also contract dW_hh / the token-table
+// gradient (no dg planes in HBM, no separate weight-gradient kernel); 0 = k_gru_bwd_tc + k_wgrad_tc
+int g_opt_bptt_fused = 1;
 static void forward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, const ParamLayout& lay, int V, int B, int L,
                          const cpg_wae_inputs* in, float* mu, float* logvar, float* z, bool stash, bool encoder_only,
                          bool mark_after_reparam = false) {
@@ -302,10 +306,12 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     q.dh_out = w.dec_dh_out; q.dg = w.dec_dg; q.dh0 = w.dh0; q.drow = w.drow;
     // the tcgen05 BPTT kernels hand dg to the tf32 weight-gradient kernel already rounded
     const int dg_rounded = (use_gru_tc(B) && wgrad_uses_tc(B * L)) ? 1 : 0;
-    if (use_gru_tc(B)) launch_gru_bwd_dec_tc(s, q, B, L, dg_rounded);
+    const bool fused = use_gru_tc(B) && g_opt_bptt_fused != 0;
+    if (fused) launch_gru_bwd_dec_fused(s, q, w.tokd, B, L, V, w.wg_part_dec, w.dt_part_dec);
+    else if (use_gru_tc(B)) launch_gru_bwd_dec_tc(s, q, B, L, dg_rounded);
     else launch_gru_bwd_dec(s, q, B, L);
-    // decoder W_hh / token-table gradients only need the decoder's dg: side stream, under the dense layers and
-    // the encoder BPTT of the main stream (joined before the input-side gradients)
+    // decoder W_hh / token-table gradients only need the decoder BPTT's output: side stream, under the dense layers
+    // and the encoder BPTT of the main stream (joined before the input-side gradients)
     const bool side = side_ready(ctx);
     {
         cudaStream_t qs = s;
@@ -313,9 +319,14 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
         // dW_ih[:,150:] = drow^T @ [z;c]  (a weight gradient: nothing on the BPTT chain waits for it)
         launch_sgemm(qs, 3 * DEC_HP, DEC_HP, B, 1.f, w.drow, 1, 3 * DEC_HP, w.zc, DEC_HP, 1, 0.f, w.dwizc, DEC_HP,
                      nullptr, w.gemm_splits, w.gemm_ws);
-        const bool t2 = launch_wgrad_hh(qs, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, w.tokd, 0, V, B, L, sm, w.wg_part_dec,
-                                        w.dt_part_dec, grads + lay.off[P_DEC_WHH], w.dT_dec, nullptr, nullptr, dg_rounded);
-        if (!t2) launch_dtable(qs, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part_dec, w.dT_dec);
+        if (fused) {
+            launch_wgrad_partial_reduce(qs, DEC_HP, DEC_H, V, w.wg_part_dec, w.dt_part_dec, bptt_fused_ctas_dec(B),
+                                        grads + lay.off[P_DEC_WHH], w.dT_dec);
+        } else {
+            const bool t2 = launch_wgrad_hh(qs, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, w.tokd, 0, V, B, L, sm, w.wg_part_dec,
+                                            w.dt_part_dec, grads + lay.off[P_DEC_WHH], w.dT_dec, nullptr, nullptr, dg_rounded);
+            if (!t2) launch_dtable(qs, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part_dec, w.dT_dec);
+        }
         if (side) side_leave(ctx, 1);
     }
     // gradient at [z;c]:  dh0 + drow @ W_ih[:,150:]   (in place on dh0)
@@ -353,19 +364,33 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
         e.dh_fin = w.dhfin + d * ENC_H; e.dh_fin_stride = 2 * ENC_H;
         e.dg = w.enc_dg[d];
     }
+    cudaStream_t rs = side ? (cudaStream_t)ctx->side_stream : nullptr;
+    if (fused) {
+        float* const pw[2] = {w.wg_part, w.wg_part_enc1};
+        float* const pt[2] = {w.dt_part, w.dt_part_enc1};
+        launch_gru_bwd_enc_fused(s, enc, w.tok, B, L, V, pw, pt);
+        // ordered reductions of the per-CTA partials: one direction on the side stream, the other on the main stream
+        const int nc = bptt_fused_ctas_enc(B);
+        if (side) {
+            cudaEventRecord((cudaEvent_t)ctx->ev_fork[1], s);
+            cudaStreamWaitEvent(rs, (cudaEvent_t)ctx->ev_fork[1], 0);
+        }
+        launch_wgrad_partial_reduce(side ? rs : s, ENC_H, ENC_H, V, pw[0], pt[0], nc, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0]);
+        launch_wgrad_partial_reduce(s, ENC_H, ENC_H, V, pw[1], pt[1], nc, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1]);
+    } else {
     if (use_gru_tc(B)) launch_gru_bwd_enc_tc(s, enc, B, L, dg_rounded);
     else launch_gru_bwd_enc(s, enc, B, L);
     // recurrent weight gradients
     // (the tensor-core path produces the token-table gradient in the same pass over dg)
     // (each direction has its own partials, and the ordered reductions of the partials run on the side stream
     //  while the main stream already contracts the next direction)
-    cudaStream_t rs = side ? (cudaStream_t)ctx->side_stream : nullptr;
     const bool t0 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[0], w.enc_hs[0], nullptr, w.tok, 0, V, B, L, sm, w.wg_part,
                                     w.dt_part, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0], rs, side ? ctx->ev_fork[1] : nullptr, dg_rounded);
     if (!t0) launch_dtable(s, ENC_H, w.enc_dg[0], w.tok, B, L, 0, V, sm, w.dt_part, w.dT_enc[0]);
     const bool t1 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[1], w.enc_hs[1], nullptr, w.tok, 1, V, B, L, sm, w.wg_part_enc1,
                                     w.dt_part_enc1, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1], rs, side ? ctx->ev_fork[1] : nullptr, dg_rounded);
     if (!t1) launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part_enc1, w.dT_enc[1]);
+    }
     if (side) side_leave(ctx, 1);                   // covers everything enqueued on the (in-order) side stream so far
     side_join(ctx, s, 1);
     ctx->join_pending[0] = false;                   // (already implied by the join above)

@@ -82,7 +82,16 @@ int launch_gru_fwd_enc_tc(cudaStream_t s, const GruSeq* two_dirs, int B, int L, 
 int launch_gru_fwd_dec_tc(cudaStream_t s, const GruSeq& seq, int B, int L, int V);
 int launch_gru_bwd_enc_tc(cudaStream_t s, const GruSeq* two_dirs, int B, int L, int round_dg);   // round_dg: dg stored as tf32
 int launch_gru_bwd_dec_tc(cudaStream_t s, const GruSeq& seq, int B, int L, int round_dg);
+// BPTT with the dW_hh / token-table gradient contractions fused in (gru_bwd_fused.cu): no dg planes in HBM.
+// part_w: [ctas][3*HP][HP], part_t: [ctas][V][4*HP] per direction, ctas = bptt_fused_ctas_*(B).
+int bptt_fused_ctas_enc(int B);
+int bptt_fused_ctas_dec(int B);
+int launch_gru_bwd_enc_fused(cudaStream_t s, const GruSeq* two_dirs, const uint8_t* tok, int B, int L, int V,
+                             float* const part_w[2], float* const part_t[2]);
+int launch_gru_bwd_dec_fused(cudaStream_t s, const GruSeq& seq, const uint8_t* tok, int B, int L, int V, float* part_w,
+                             float* part_t);
 extern int g_opt_gru_tc;
+extern int g_opt_bptt_fused;
 extern int g_opt_side_stream;
 
 // C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C ; generic strides (elements):

@@ -124,6 +124,12 @@ bool launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float
     return false;
 }
 
+void launch_wgrad_partial_reduce(cudaStream_t s, int HP, int H, int V, const float* part_w, const float* part_t, int nsplit,
+                                 float* dW, float* dT) {
+    CPG_LAUNCH(k_wgrad_hh_reduce, CPG_RED_GRID(3 * H * H), CPG_RED_BLOCK, 0, s, part_w, nsplit, HP, H, dW);
+    CPG_LAUNCH(k_dtable_reduce, CPG_RED_GRID(V * 4 * HP), CPG_RED_BLOCK, 0, s, part_t, nsplit, V * 4 * HP, dT);
+}
+
 void launch_wgrad_hh_simt(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0, int B, int L,
                           int sm_count, float* part, float* dW) {
     int nrows = B * L;

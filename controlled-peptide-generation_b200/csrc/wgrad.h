@@ -30,6 +30,9 @@ void launch_wgrad_hh_simt(cudaStream_t s, int HP, int H, const float* dg, const 
 int wgrad_tc_splits(int sm_count);
 int launch_wgrad_tc(cudaStream_t s, int HP, const float* dg, const float* hs, const float* h0, const uint8_t* tok,
                     int reverse, int B, int L, int V, int sm_count, float* part_w, float* part_t, int* nsplit_out, int dg_rounded);
+// ordered sums of per-CTA partials in the layouts above -> dW_hh [3H][H] (unpadded) and dT [V][4*HP]
+void launch_wgrad_partial_reduce(cudaStream_t s, int HP, int H, int V, const float* part_w, const float* part_t, int nsplit,
+                                 float* dW, float* dT);
 extern int g_opt_wgrad_tc;
 bool wgrad_uses_tc(int nrows);      // would launch_wgrad_hh take the tensor-core path for this many rows?
 void launch_dtable(cudaStream_t s, int HP, const float* dg, const uint8_t* tok, int B, int L, int reverse, int V,

@@ -263,6 +263,8 @@ int cpg_prior_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n,
  *   "wgrad_tensor_core"   1 (default) tf32 tcgen05 weight / token-table gradients when B*L >= 8192, 2 always, 0 never
  *   "gru_tensor_core"     1 (default) split-bf16 tcgen05 recurrences (forward + BPTT) when B >= 1024, 2 always, 0 never
  *   "dec_out_tensor_core" 1 (default) tcgen05 decoder-output layer when B*L >= 8192, 2 always, 0 never
+ *   "bptt_fused"          1 (default) on the tcgen05 path the BPTT kernels also contract dW_hh and the token-table gradient
+ *                         (the gate-gradient planes never reach HBM), 0 = separate tf32 weight-gradient kernels
  *   "side_stream"         1 (default) loss / weight-gradient kernels overlap the recurrences on an internal stream
  *                         (event fork/join inside each call; results identical), 0 everything on the caller's stream */
 int cpg_set_option(const char* name, int value);

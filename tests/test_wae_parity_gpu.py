@@ -424,3 +424,32 @@ def test_auto_tensor_core_paths_match_simt_at_ragged_large_batches(eng, batch):
     for k in ow.UNIQUE_VAE_PARAMS:
         scale = float(g0[k].abs().max()) + 1e-12
         np.testing.assert_allclose(g1[k].numpy(), g0[k].numpy(), rtol=1e-3, atol=1e-4 * scale, err_msg=k)
+
+
+@pytest.mark.parametrize('batch', [1, 33, 100, 1100])
+def test_fused_bptt_weight_gradients_vs_separate_kernels(eng, batch):
+    """BPTT with dW_hh / token-table gradient contracted in the same kernel (split-bf16 tcgen05, accumulators in TMEM
+    over all steps, one partial per CTA) vs the fp32 SIMT BPTT + SIMT weight-gradient kernels: every gradient."""
+    from cpg_b200 import _lib
+    dev = torch.device('cuda')
+    p = ow.random_params(V, seed=81)
+    tokens = ow.synthetic_tokens(batch, V, seed=82).to(dev)
+    noise = dev_noise(ow.draw_noise(batch, seed=83), dev)
+    grads = {}
+    try:
+        for name, tcflag, fused in (('simt', 0, 0), ('fused', 2, 1), ('tc_separate', 2, 0)):
+            _lib.set_option('gru_tensor_core', tcflag)
+            _lib.set_option('wgrad_tensor_core', 0 if name == 'simt' else 2)
+            _lib.set_option('bptt_fused', fused)
+            st = eng.FlatState(V, dev)
+            st.load(p)
+            eng.train_step(st, tokens, noise, eng.make_hparams(clip_norm=1e9))
+            grads[name] = {k: v.clone().cpu() for k, v in st.views(st.grads).items()}
+    finally:
+        _lib.set_option('gru_tensor_core', 1)
+        _lib.set_option('wgrad_tensor_core', 1)
+        _lib.set_option('bptt_fused', 1)
+    for k in ow.UNIQUE_VAE_PARAMS:
+        ref = grads['simt'][k].numpy()
+        scale = float(np.abs(ref).max()) + 1e-12
+        np.testing.assert_allclose(grads['fused'][k].numpy(), ref, rtol=1e-3, atol=1e-4 * scale, err_msg='fused ' + k)
