@@ -155,6 +155,8 @@ _DEFAULTS = {
         'full_mmd_every': 1,       # the reference evaluates the (log-only) full-kernel MMD every iteration
         'sync_scalars_every': 0,   # > 0: also read the 16-float scalar block back every n-th iteration
                                    # (train_vae.last_scalars; e.g. for a NaN watchdog); 0 = log iterations only
+        'decode_accepted_only': False,   # sample_pipeline: True = compact the accepted z on the device and decode only those
+                                         # (rows of the round table = unique accepted peptides); False = decode every draw
         'dp_full_mmd': 'local',    # under torch.distributed: 'local' = the log-only full-kernel MMD of this rank's shard,
                                    # 'global' = all-gather z / z_prior and evaluate the global-batch value
     },

@@ -95,6 +95,11 @@ def _signatures(L):
         'cpg_cnn_classifier_fwd': (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P, P, P]),
         'cpg_class_score_accept': (I, [P, P, P, P, I64, I, P, P, P, P, P, P, P]),
         'cpg_class_sample': (I, [P, P, P, P, P, I, I, P, P, P, P, c_uint64, I64, I64, P, P, P, P, P, P]),
+        'cpg_class_regen': (I, [P, P, P, P, P, I, I, P, P, P, P, c_uint64, P, I64, P, P, P]),
+        'cpg_compact_accepted': (I, [P, P, P, I64, I64, I64, P, P]),
+        'cpg_gather_rows': (I, [P, P, P, P, I64, I64, I, P]),
+        'cpg_dedup_rows': (I, [P, P, P, I64, I, P, P]),
+        'cpg_peptide_descriptors': (I, [P, P, P, I64, I, P, I, P, P, ctypes.c_double, F, P, P, P, P]),
         'cpg_gmm_logpdf': (I, [P, P, P, I64, P, P, P, I, P]),
         'cpg_prior_logpdf': (I, [P, P, P, I64, P]),
         'cpg_set_option': (I, [c_char_p, I]),

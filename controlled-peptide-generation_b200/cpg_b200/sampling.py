@@ -133,6 +133,43 @@ def class_sample(gmm, spec, n, seed, offset=0, want_z=True, want_scores=True):
     return out
 
 
+def compact_accepted(accept, first_index=0, cap=None):
+    """Ascending global indices (first_index + position) of the accepted draws -> (idx int64 [cap] device,
+    count device uint64 scalar).  Only the first `count` entries of idx are meaningful."""
+    n = accept.shape[0]
+    dev = accept.device
+    cap = n if cap is None else int(cap)
+    idx = torch.empty(max(cap, 1), dtype=torch.int64, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(lib().cpg_compact_accepted(context(dev), stream_ptr(), ptr(accept, torch.uint8), n, int(first_index), cap, ptr(idx),
+                                     ptr(count)), 'cpg_compact_accepted')
+    return idx, count
+
+
+def gather_rows(src, idx, index_base=0):
+    m, D = idx.shape[0], src.shape[1]
+    dst = torch.empty(m, D, dtype=torch.float32, device=src.device)
+    if m:
+        check(lib().cpg_gather_rows(context(src.device), stream_ptr(), ptr(src, torch.float32), ptr(idx, torch.int64),
+                                    int(index_base), m, D, ptr(dst)), 'cpg_gather_rows')
+    return dst
+
+
+def class_regen(gmm, spec, seed, draw_index, want_scores=False):
+    """z (and optionally scores) of the listed draws, bit-identical to class_sample(seed) at those indices."""
+    m = draw_index.shape[0]
+    dev = gmm.device
+    z = torch.empty(m, ZD, dtype=torch.float32, device=dev)
+    probs = torch.empty(max(spec.n, 1), m, dtype=torch.float64, device=dev) if want_scores else None
+    accum = torch.empty(m, dtype=torch.float64, device=dev) if want_scores else None
+    if m:
+        n_clf, coef, icpt, tgt, f32 = spec.args()
+        check(lib().cpg_class_regen(context(dev), stream_ptr(), ptr(gmm.mean32), ptr(gmm.sd32), ptr(gmm.cdf32), gmm.K, n_clf,
+                                    coef, icpt, tgt, f32, int(seed), ptr(draw_index.contiguous(), torch.int64), m, ptr(z),
+                                    ptr(probs), ptr(accum)), 'cpg_class_regen')
+    return z, probs, accum
+
+
 def gmm_logpdf(gmm, x):
     n = x.shape[0]
     out = torch.empty(n, dtype=torch.float64, device=x.device)

@@ -371,10 +371,12 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
         launch_gru_bwd_enc_fused(s, enc, w.tok, B, L, V, pw, pt);
         // ordered reductions of the per-CTA partials: one direction on the side stream, the other on the main stream
         const int nc = bptt_fused_ctas_enc(B);
+#ifndef CPG_EMU
         if (side) {
             cudaEventRecord((cudaEvent_t)ctx->ev_fork[1], s);
             cudaStreamWaitEvent(rs, (cudaEvent_t)ctx->ev_fork[1], 0);
         }
+#endif
         launch_wgrad_partial_reduce(side ? rs : s, ENC_H, ENC_H, V, pw[0], pt[0], nc, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0]);
         launch_wgrad_partial_reduce(s, ENC_H, ENC_H, V, pw[1], pt[1], nc, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1]);
     } else {

@@ -77,9 +77,9 @@ struct GmmSpec {
 };
 constexpr int CS_WARPS = 8;
 __global__ void __launch_bounds__(CS_WARPS * 32)
-k_class_sample(GmmSpec g, ClfSpec cs, uint64_t seed, int64_t offset, int64_t n, float* __restrict__ z_out,
-               double* __restrict__ probs, double* __restrict__ accum_out, uint8_t* __restrict__ accept,
-               int* __restrict__ comp_out, unsigned long long* __restrict__ n_accepted) {
+k_class_sample(GmmSpec g, ClfSpec cs, uint64_t seed, int64_t offset, const int64_t* __restrict__ gid_list, int64_t n,
+               float* __restrict__ z_out, double* __restrict__ probs, double* __restrict__ accum_out,
+               uint8_t* __restrict__ accept, int* __restrict__ comp_out, unsigned long long* __restrict__ n_accepted) {
     __shared__ float coef_s[MAX_CLF][ZD + 28];
     __shared__ float cdf_s[1024];
     for (int i = threadIdx.x; i < cs.n_clf * ZD; i += blockDim.x) coef_s[i / ZD][i % ZD] = (float)cs.coef[i / ZD][i % ZD];
@@ -96,7 +96,9 @@ k_class_sample(GmmSpec g, ClfSpec cs, uint64_t seed, int64_t offset, int64_t n, 
         double ua_mine = 2.0;
         if (base + lane < n) {
             uint32_t r0[4];
-            Philox::gen(seed, (uint64_t)(offset + base + lane), 0u, r0);
+            // draw number: consecutive from `offset`, or (re-generation of selected draws) taken from a list
+            const uint64_t gid0 = gid_list != nullptr ? (uint64_t)gid_list[base + lane] : (uint64_t)(offset + base + lane);
+            Philox::gen(seed, gid0, 0u, r0);
             const float uc = (float)(r0[0] >> 8) * (1.0f / 16777216.0f);
             ua_mine = u64_to_unit(r0[2], r0[3]);
             int lo = 0, hi = g.K - 1;                            // first k with cdf[k] > uc
@@ -106,7 +108,7 @@ k_class_sample(GmmSpec g, ClfSpec cs, uint64_t seed, int64_t offset, int64_t n, 
         const int ndraw = (int)min((int64_t)32, n - base);
         for (int jd = 0; jd < ndraw; ++jd) {
         const int64_t i = base + jd;
-        const uint64_t gid = (uint64_t)(offset + i);
+        const uint64_t gid = gid_list != nullptr ? (uint64_t)gid_list[i] : (uint64_t)(offset + i);
         const int k = __shfl_sync(0xffffffffu, k_mine, jd);
         const double ua = __shfl_sync(0xffffffffu, ua_mine, jd);
         uint32_t r[4];
@@ -147,7 +149,7 @@ k_class_sample(GmmSpec g, ClfSpec cs, uint64_t seed, int64_t offset, int64_t n, 
         }
         if (lane == 0) {
             const int acc = ua < (double)accf ? 1 : 0;
-            accept[i] = (uint8_t)acc;
+            if (accept != nullptr) accept[i] = (uint8_t)acc;
             if (accum_out != nullptr) accum_out[i] = (double)accf;
             if (comp_out != nullptr) comp_out[i] = k;
             local_acc += acc;
@@ -245,9 +247,27 @@ int cpg_class_sample(cpg_ctx* ctx, cpg_stream stream, const float* gmm_mean, con
     GmmSpec g{gmm_mean, gmm_sd, gmm_cdf, K};
     int64_t want = (n + CS_WARPS * 32 - 1) / (CS_WARPS * 32);
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * 8));
-    CPG_LAUNCH(k_class_sample, grid, CS_WARPS * 32, 0, (cudaStream_t)stream, g, cs, seed, offset, n, z_out, probs, accum,
-               accept, comp_out, n_accepted);
+    CPG_LAUNCH(k_class_sample, grid, CS_WARPS * 32, 0, (cudaStream_t)stream, g, cs, seed, offset, (const int64_t*)nullptr, n, z_out,
+               probs, accum, accept, comp_out, n_accepted);
     return check_launch("cpg_class_sample");
+}
+
+int cpg_class_regen(cpg_ctx* ctx, cpg_stream stream, const float* gmm_mean, const float* gmm_sd, const float* gmm_cdf,
+                    int K, int n_clf, const double* const* coef, const double* intercept, const int* target_col,
+                    const int* f32, uint64_t seed, const int64_t* draw_index, int64_t m, float* z_out, double* probs,
+                    double* accum) {
+    if (!ctx || !gmm_mean || !gmm_sd || !gmm_cdf || !draw_index || !z_out || m < 0) { set_error("cpg_class_regen: bad argument"); return CPG_EINVAL; }
+    if (m == 0) return CPG_OK;
+    if (K < 1 || K > 1024) { set_error("cpg_class_regen: 1 <= n_components <= 1024"); return CPG_EINVAL; }
+    ClfSpec cs;
+    int rc = fill_clf(cs, n_clf, coef, intercept, target_col, f32);
+    if (rc) return rc;
+    GmmSpec g{gmm_mean, gmm_sd, gmm_cdf, K};
+    int64_t want = (m + CS_WARPS * 32 - 1) / (CS_WARPS * 32);
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * 8));
+    CPG_LAUNCH_NAMED("k_class_regen", k_class_sample, grid, CS_WARPS * 32, 0, (cudaStream_t)stream, g, cs, seed, (int64_t)0, draw_index, m,
+                     z_out, probs, accum, (uint8_t*)nullptr, (int*)nullptr, (unsigned long long*)nullptr);
+    return check_launch("cpg_class_regen");
 }
 
 int cpg_gmm_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, const double* mean_t,

@@ -80,6 +80,53 @@ class RejSampleBase:
         return z.cpu(), scores_z, accept.cpu().numpy().astype(bool)
 
 
+    def rejection_sample_decode(self, n_samples, model, dataset, prefix='clfZ', device=None, n_best=3, return_device=False):
+        """One sampling round with everything after the draw kept on the GPU (BASELINE.json config 5: "beam decode of
+        accepted z"): Philox draws + scores + accept (no z in HBM for rejected draws) -> stream compaction of the
+        accept mask -> re-generation of the accepted z -> beam decode -> duplicate removal -> H / uH / charge.
+        Only the unique accepted peptides cross PCIe.  Returns a DataFrame with one row per unique accepted peptide
+        (columns of the reference's round table + draw_index, H, uH, charge) and sets self.last_round_stats."""
+        import pandas as pd
+        from cpg_b200 import peptides
+        dev = _device(device)
+        spec = self._clf_spec(dev)
+        gmm = self._gmm_device(dev)
+        off = self._draw_offset
+        out = sampling.class_sample(gmm, spec, n_samples, self.seed, off, want_z=False, want_scores=False)
+        self._draw_offset += n_samples
+        n_acc = int(out['n_accepted'].item())                       # the one host sync of the round (8 bytes)
+        idx, _ = sampling.compact_accepted(out['accept'], first_index=off, cap=max(n_acc, 1))
+        idx = idx[:n_acc]
+        z, probs, accum = sampling.class_regen(gmm, spec, self.seed, idx, want_scores=True)
+        st = model.flat_state()
+        c = model.sample_c_prior(n_acc) if n_acc else torch.zeros(0, 2, device=dev)
+        stats = {'n_draws': n_samples, 'n_accepted': n_acc, 'n_unique': 0}
+        if n_acc == 0:
+            self.last_round_stats = stats
+            return pd.DataFrame(columns=['peptide', 'z', 'accept_z', 'draw_index', 'H', 'uH', 'charge'])
+        toks, lens, _ = sampling.beam_decode(st.params, model.n_vocab, z, c.to(dev), model.MAX_SEQ_LEN, 5, n_best)
+        hyp0 = toks[:, 0, :].contiguous()
+        _, is_first = peptides.dedup_rows(hyp0)
+        keep = torch.nonzero(is_first, as_tuple=False).squeeze(1)
+        a2t = peptides.token_to_residue(lambda t: dataset.idx2sentences([[t]], print_special_tokens=True)[0], model.n_vocab)
+        H, uH, ch, _ = peptides.descriptors_from_tokens(hyp0, a2t)
+        stats['n_unique'] = int(keep.numel())
+        self.last_round_stats = stats
+        if return_device:
+            return {'tokens': hyp0, 'keep': keep, 'z': z, 'idx': idx, 'H': H, 'uH': uH, 'charge': ch, 'accum': accum}
+        # device -> host: the unique accepted rows only
+        kt, kl = hyp0[keep].cpu().tolist(), lens[keep, 0].cpu().tolist()
+        seqs = dataset.idx2sentences([row[:n] for row, n in zip(kt, kl)], print_special_tokens=False)
+        cast = (lambda a: a.astype(np.float32)) if spec.all_f32 else (lambda a: a)
+        df = {'peptide': seqs, 'z': [tuple(r) for r in z[keep].cpu().tolist()], 'accept_z': np.ones(len(seqs), dtype=bool),
+              'draw_index': idx[keep].cpu().numpy()}
+        for i, name in enumerate(spec.names):
+            df['{}_{}={}'.format(prefix, name, spec.target[i])] = cast(probs[i][keep].cpu().numpy())
+        df[prefix + '_prob_accum'] = cast(accum[keep].cpu().numpy())
+        df['H'], df['uH'], df['charge'] = H[keep].cpu().numpy(), uH[keep].cpu().numpy(), ch[keep].cpu().numpy()
+        return pd.DataFrame(df)
+
+
 class mogQ(RejSampleBase):
     def __init__(self, mu, logvar, n_components=10, z_num_samples=10, **mog_kwargs):
         import sklearn.mixture

@@ -249,6 +249,33 @@ int cpg_class_sample(cpg_ctx* ctx, cpg_stream stream, const float* gmm_mean, con
                      int K, int n_clf, const double* const* coef, const double* intercept, const int* target_col,
                      const int* f32, uint64_t seed, int64_t offset, int64_t n, float* z_out, double* probs,
                      double* accum, uint8_t* accept, int* comp_out, unsigned long long* n_accepted);
+/* Re-generation of selected draws: z (and optionally the scores) of the draws whose global indices are listed in
+ * draw_index[m] -- bit-identical to what cpg_class_sample(seed, ...) produced / would produce for those indices (every
+ * draw is a pure function of (seed, index)).  With it a sampling round needs no z in HBM for the rejected draws:
+ * cpg_class_sample(z_out = NULL) -> cpg_compact_accepted -> cpg_class_regen. */
+int cpg_class_regen(cpg_ctx* ctx, cpg_stream stream, const float* gmm_mean, const float* gmm_sd, const float* gmm_cdf,
+                    int K, int n_clf, const double* const* coef, const double* intercept, const int* target_col,
+                    const int* f32, uint64_t seed, const int64_t* draw_index, int64_t m, float* z_out, double* probs,
+                    double* accum);
+/* ---- after the accept test (sample_pipeline.py:195-218,312-316) --------------------------------
+ * cpg_compact_accepted: ascending indices (first_index + position) of the non-zero entries of accept[n] -> idx_out
+ *   (at most `cap` are written), their number -> *count (device).  Stable: boolean-mask indexing of the reference.
+ * cpg_gather_rows: dst[r][:] = src[idx[r] - index_base][:] for r < m (rows of D floats).
+ * cpg_dedup_rows: rows int32 [n][width] (decoded token rows, -1 padded): first_index[i] = lowest row index with the
+ *   same content, is_first[i] = (first_index[i] == i) -- pandas drop_duplicates() keeps exactly those rows.  Exact.
+ * cpg_peptide_descriptors: per token row, over the residues only (aa_of_token[t] in 0..19, -1 = not a residue; HOST
+ *   array of n_tokens entries): H = mean hydrophobicity, uH = |sum_i h_i exp(i * pos_i * angle)| / len (hydrophobic
+ *   moment over the whole sequence: modlamp calculate_moment with window >= len), charge = charge_ends + sum of the
+ *   side-chain partial charges, rounded to 3 decimals.  hydrophobicity20 / side_chain_charge20: HOST tables indexed by
+ *   residue code.  length (residues per row) may be NULL. */
+int cpg_compact_accepted(cpg_ctx* ctx, cpg_stream stream, const uint8_t* accept, int64_t n, int64_t first_index, int64_t cap,
+                         int64_t* idx_out, unsigned long long* count);
+int cpg_gather_rows(cpg_ctx* ctx, cpg_stream stream, const float* src, const int64_t* idx, int64_t index_base, int64_t m, int D,
+                    float* dst);
+int cpg_dedup_rows(cpg_ctx* ctx, cpg_stream stream, const int* rows, int64_t n, int width, int* first_index, uint8_t* is_first);
+int cpg_peptide_descriptors(cpg_ctx* ctx, cpg_stream stream, const int* tokens, int64_t n, int width, const int8_t* aa_of_token,
+                            int n_tokens, const float* hydrophobicity20, const double* side_chain_charge20, double charge_ends,
+                            float angle_deg, float* H, float* uH, float* charge, int* length);
 /* mogQ.logpdf batched (density_modeling.py:75-77): mean_t, prec_t fp64 [100][K] (component fastest),
  * logw_norm[k] = log w_k - 50 log(2 pi) + 0.5 sum_d log prec_kd; out fp64 [n]. */
 int cpg_gmm_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, const double* mean_t,

@@ -196,3 +196,71 @@ def test_package_synthetic_workload_equals_oracle_generator():
     a, b = synth.synthetic_class_setup(), cb.synthetic_class_setup()
     assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3]))
     assert all(np.array_equal(x[1], y[1]) and x[3] == y[3] for x, y in zip(a[3], b[3]))
+
+
+def test_states_files_round_trip_float16(tmp_path):
+    """states_{split}_{n_iter}: same datasets / dtypes as vis/scripts/build_index.py:30-66 (float16 encodings)."""
+    from cpg_b200 import states
+    rs = np.random.RandomState(0)
+    n = 37
+    mu, lv = rs.randn(n, 100).astype(np.float32), rs.randn(n, 100).astype(np.float32) - 2
+    src = rs.randint(0, 24, (n, 25))
+    lab = rs.randint(-1, 2, (n, 3))
+    base = states.states_basename(str(tmp_path), 'val', 5)
+    path = states.write_states(base, src, mu, mu, lv, lab, np.full((n, 1), 1))
+    assert os.path.isfile(path)
+    st = states.read_states(base)
+    assert set(st) == set(states.KEYS)
+    assert st['mu'].dtype == np.float16 and st['logvar'].dtype == np.float16 and st['z'].dtype == np.float16
+    assert np.array_equal(st['mu'], mu.astype(np.float16)) and np.array_equal(st['src'], src)
+    assert st['label'].dtype.kind == 'i' and st['split'].shape == (n, 1)
+    with pytest.raises(FileNotFoundError):
+        states.read_states(states.states_basename(str(tmp_path), 'test', 5))
+
+
+def test_sample_pipeline_surface_matches_the_reference_names():
+    """Function names / CLI flags of the reference's sample_pipeline.py (:41-361) and api.py are present."""
+    import inspect
+    sp = importlib.import_module('sample_pipeline')
+    for name, params in (('get_encodings', ['query', 'split', 'model', 'dataloader']),
+                         ('get_encodings_from_dataloader', ['query', 'split', 'model', 'dataloader']),
+                         ('get_encodings_from_states', ['query', 'split']),
+                         ('fitQ_and_test', ['QClass', 'QKwargs', 'Q_select', 'negative_select', 'model', 'dataloader']),
+                         ('decode_from_z', ['z', 'model', 'dataset']), ('save_csv_pkl', ['samples', 'fn']),
+                         ('save_samples', ['samples', 'basedir', 'fn_prefix']), ('score_clfZ', ['clf', 'z']),
+                         ('build_clfZ', ['attr']), ('get_new_samples', ['model', 'dataset', 'Q', 'n_samples']),
+                         ('compute_modlamp', ['df']), ('one_sampling_round', ['model', 'dataset', 'Q', 'n_samples_per_round']),
+                         ('get_sample_source_str', []), ('main', ['args'])):
+        fn = getattr(sp, name)
+        got = list(inspect.signature(fn).parameters)
+        assert got[:len(params)] == params, (name, got)
+    flags = {a.option_strings[0] for a in sp.build_parser()._actions if a.option_strings}
+    for f in ('--QClass', '--Q_n_components', '--Q_covariance_type', '--n_samples_per_round', '--n_samples_acc',
+              '--samples_outfn_prefix', '--Q_select_amppos', '--Q_from_full_dataloader', '--vae.batch_size', '--seed'):
+        assert f in flags, f
+    assert sp.Q_CLASS.__name__ == 'mogQ' and set(sp.Q_KWARGS) == {'n_components', 'z_num_samples', 'covariance_type'}
+    api = importlib.import_module('api')
+    for name in ('Vocab', 'load_trained_model', 'encode_sequence', 'sample_from_model', 'get_model_and_vocab_path',
+                 'get_result_for_model', 'main'):
+        assert hasattr(api, name), name
+
+
+def test_vocab_and_peptide_formula_known_answers(tmp_path):
+    api = importlib.import_module('api')
+    fn = tmp_path / 'vocab.dict'
+    words = ['<unk>', '<pad>', '<start>', '<eos>'] + list('ACDEFGHIKLMNPQRSTVWY')
+    fn.write_text(''.join('%s %d\n' % (w, i) for i, w in enumerate(words)))
+    v = api.Vocab(str(fn))
+    assert v.size() == 24 and v.special_tokens_ix == {0, 1, 2, 3}
+    ix = v.to_ix('K L A')
+    assert ix.shape == (1, 25) and ix[0, :5].tolist() == [2, 12, 13, 4, 3] and int(ix[0, -1]) == 1
+    assert v.to_word(ix[0], print_special_tokens=False) == ['K', 'L', 'A']
+    from oracle import peptides as op
+    # hand-computed: one lysine, amidated C-terminus, pH 7
+    q = 10 ** 9.38 / (10 ** 9.38 + 1e7) + 10 ** 10.67 / (10 ** 10.67 + 1e7) - 1e7 / (1e15 + 1e7)
+    assert op.charge('K') == round(q, 3) == 1.996
+    assert op.descriptors('K')[:2] == (-1.5, 1.5)
+    h = [0.62, 1.06]                                             # 'AL': moment of two residues 100 degrees apart
+    want = (((h[0] + h[1] * np.cos(np.deg2rad(100))) ** 2 + (h[1] * np.sin(np.deg2rad(100))) ** 2) ** 0.5) / 2
+    assert op.descriptors('AL')[1] == pytest.approx(want, rel=1e-12)
+    assert op.drop_duplicates_first(['a', 'b', 'a', 'c', 'b']) == ([0, 1, 0, 3, 1], [1, 1, 0, 1, 0])

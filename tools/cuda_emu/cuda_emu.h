@@ -238,6 +238,7 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 template <typename T> static inline T atomicMax(T* p, T v) { T o = *p; *p = std::max(o, v); return o; }
 template <typename T> static inline T atomicMin(T* p, T v) { T o = *p; *p = std::min(o, v); return o; }
 template <typename T> static inline T atomicExch(T* p, T v) { T o = *p; *p = v; return o; }
+template <typename T> static inline T atomicCAS(T* p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 
