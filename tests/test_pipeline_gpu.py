@@ -118,7 +118,7 @@ def test_sample_pipeline_main_end_to_end(accepted_only, tmp_path):
     from cpg_b200 import states, synth
     model = _trained_model()
     ds = Dataset()
-    old = (cfg.savepath, cfg.attributes, cfg.vae.n_iter, cfg.b200.decode_accepted_only)
+    old = (getattr(cfg, 'savepath', None), cfg.attributes, cfg.vae.n_iter, cfg.b200.decode_accepted_only)
     cfg.savepath, cfg.attributes, cfg.vae.n_iter = str(tmp_path), [('amp', 1), ('tox', 1), ('sol', 1)], 77
     cfg.b200.decode_accepted_only = accepted_only
     try:
