@@ -194,6 +194,160 @@ def setup_model(device):
     return cfg, model
 
 
+def run_strong(args, cfg, model, st, dev, world, rank, timed, hp):
+    """Global batch 4096 split over the ranks (512 per GPU at N = 8); the log-only full-kernel MMD is the GLOBAL-batch
+    value (all-gather of z).  Both kernel families are timed: the fp32 SIMT kernels the library picks by
+    itself below 1024 rows per GPU, and the tcgen05 kernels forced on."""
+    import torch
+    import utils
+    from cpg_b200 import _lib, engine, parallel, synth
+    Bs = max(1, BATCH // world)
+    tok = synth.synthetic_tokens(Bs, N_VOCAB, seed=4242 + rank).to(dev)
+    noise = engine.alloc_noise(Bs, SEQ_LEN, dev, seed=cfg.seed)
+    seed = cfg.b200.noise_seed + 7919 * rank
+    out = {'global_batch': Bs * world, 'per_gpu_batch': Bs, 'full_mmd': 'global', 'steps': args.steps}
+    it = {'n': 0}
+
+    def step():
+        it['n'] += 1
+        hp.beta = float(utils.anneal(cfg.vae.beta, it['n']))
+        engine.fill_step_noise(noise, seed, it['n'], overlap=True)
+        return parallel.dp_train_step(st, tok, noise, hp, global_batch=Bs * world, full_mmd='global')
+    try:
+        for name, flag in (('auto', 1), ('tcgen05_forced', 2)):
+            for o in ('gru_tensor_core', 'dec_out_tensor_core', 'wgrad_tensor_core'):
+                _lib.set_option(o, flag)
+            for _ in range(3):
+                step()
+            ms = timed(step, args.steps) / args.steps
+            out[name] = {'ms_per_step': ms, 'seq_per_s': Bs * world / (ms / 1e3)}
+    finally:
+        for o in ('gru_tensor_core', 'dec_out_tensor_core', 'wgrad_tensor_core'):
+            _lib.set_option(o, 1)
+    best = max(('auto', 'tcgen05_forced'), key=lambda k: out[k]['seq_per_s'])
+    out.update({'value': out[best]['seq_per_s'], 'unit': UNIT, 'kernels': best, 'scaling': 'strong'})
+    return out
+
+
+def run_class(args, st, dev, world, rank, barrier, model):
+    """CLaSS sampling, sharded by Philox offset: rank r draws n per-GPU samples with global indices [r n, (r+1) n); no
+    data-path collective, the accepted counts are summed at the end of the round.  Three measurements:
+      value     device-resident rejection sampling with the reference's full return contract in HBM (z fp32, 3 score
+                arrays fp64, mask: 425 B/draw), all ranks, max time over ranks
+      e2e       through density_modeling.mogQ.rejection_sample(n): the same plus the copies to host tensors it returns
+      pipeline  one device round of config 5: flags only -> compaction -> re-generation of accepted z -> beam decode ->
+                dedup -> descriptors -> unique accepted peptides to the host (mogQ.rejection_sample_decode)."""
+    import numpy as np
+    import sklearn.mixture
+    import torch
+    import torch.distributed as dist
+    import density_modeling as dm
+    from cpg_b200 import sampling, synth
+    w, means, covs, clfs = synth.synthetic_class_setup()
+    gmm = sampling.GmmDevice(w, means, covs, dev)
+    spec = sampling.ClassifierSpec(clfs, dev)
+    n = args.class_draws or (10_000_000 if world == 1 else 12_500_000)
+    peaks, _ = load_peaks()
+
+    def reduce_max(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t)
+        return float(t.item())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # (1) device-resident, full contract
+    sampling.class_sample(gmm, spec, n, 1, offset=rank * n)
+    barrier()
+    e0.record()
+    out = sampling.class_sample(gmm, spec, n, 2, offset=rank * n)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_local = e0.elapsed_time(e1)
+    cms = reduce_max(ms_local)
+    acc = reduce_sum(float(out['n_accepted'].item()))
+    del out
+    # flags only (what the device pipeline runs)
+    sampling.class_sample(gmm, spec, n, 3, offset=rank * n, want_z=False, want_scores=False)
+    barrier()
+    e0.record()
+    sampling.class_sample(gmm, spec, n, 4, offset=rank * n, want_z=False, want_scores=False)
+    e1.record()
+    torch.cuda.synchronize()
+    fms = reduce_max(e0.elapsed_time(e1))
+    torch.cuda.empty_cache()
+    # (2) end to end through the reference-facing call (host outputs), bounded sample
+    mog = sklearn.mixture.GaussianMixture(n_components=len(w), covariance_type='diag')
+    mog.weights_, mog.means_, mog.covariances_ = w, means, covs
+    mog.precisions_cholesky_ = 1.0 / np.sqrt(covs)
+    Q = dm.mogQ.from_fitted(mog)
+    mk = lambda c: types.SimpleNamespace(coef_=np.asarray(c[1])[None, :], intercept_=np.asarray([c[2]]))
+    Q.init_attr_classifiers({c[0]: mk(c) for c in clfs}, {c[0]: c[3] for c in clfs})
+    Q._draw_offset = rank * (1 << 40)
+    n_e2e = min(n, 2_000_000)
+    Q.rejection_sample(100_000)
+    barrier()
+    t0 = time.perf_counter()
+    z_h, scores_h, accepted = Q.rejection_sample(n_e2e)
+    d2h = (z_h.numel() * z_h.element_size() + sum(v.nbytes for v in scores_h.values()) + accepted.nbytes) / n_e2e
+    torch.cuda.synchronize()
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    e2e_acc = reduce_sum(float(accepted.sum()))
+    # (3) device round with decode of the accepted z
+    aa = ['<unk>', '<pad>', '<start>', '<eos>'] + list('ACDEFGHIKLMNPQRSTVWY')
+    ds = types.SimpleNamespace(idx2sentences=lambda seqs, print_special_tokens=True: [
+        ' '.join(aa[int(i)] for i in s_ if print_special_tokens or int(i) > 3) for s_ in seqs])
+    n_pipe = min(n, 2_000_000)
+    Q.rejection_sample_decode(100_000, model, ds)
+    barrier()
+    t0 = time.perf_counter()
+    df = Q.rejection_sample_decode(n_pipe, model, ds)
+    torch.cuda.synchronize()
+    pipe_s = reduce_max(time.perf_counter() - t0)
+    stats = Q.last_round_stats
+    pipe_acc, pipe_unique = reduce_sum(stats['n_accepted']), reduce_sum(stats['n_unique'])
+    # device-only timing of the same round (no host tables)
+    barrier()
+    e0.record()
+    Q.rejection_sample_decode(n_pipe, model, ds, return_device=True)
+    e1.record()
+    torch.cuda.synchronize()
+    pipe_dev_ms = reduce_max(e0.elapsed_time(e1))
+    # beam decode alone
+    zb = torch.randn(8192, 100, device=dev)
+    cbm = torch.eye(2, device=dev)[torch.arange(8192, device=dev) % 2]
+    sampling.beam_decode(st.params, N_VOCAB, zb, cbm)
+    barrier()
+    e0.record()
+    sampling.beam_decode(st.params, N_VOCAB, zb, cbm)
+    e1.record()
+    torch.cuda.synchronize()
+    bms = reduce_max(e0.elapsed_time(e1))
+    tot = n * world
+    gbs_rank = 425 * n / (ms_local / 1e3) / 1e9
+    return {'metric': 'class_accepted_samples_per_s', 'value': acc / (cms / 1e3), 'unit': 'samples/s', 'n_gpus': world,
+            'scaling': 'weak' if world > 1 else None, 'sharding': 'Philox offset = rank * n_draws_per_gpu, no collective on the data path',
+            'draws_per_s': tot / (cms / 1e3), 'accept_rate': acc / tot, 'n_draws': tot, 'n_draws_per_gpu': n,
+            'flags_only_draws_per_s': tot / (fms / 1e3),
+            'roofline': {'kernel': 'k_class_sample', 'bound': 'hbm', 'achieved': round(gbs_rank, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                         'frac': round(gbs_rank / peaks['hbm_gbs'], 4), 'bytes_per_draw': 425,
+                         'note': 'algorithmic bytes = the reference return contract (z fp32 + 3 fp64 score arrays + mask) written once'},
+            'e2e': {'value': e2e_acc / e2e_s, 'unit': 'samples/s', 'draws_per_s': n_e2e * world / e2e_s, 'n_draws': n_e2e * world,
+                    'd2h_bytes_per_draw': d2h, 'h2d_bytes_per_draw': 0,
+                    'api': 'density_modeling.mogQ.rejection_sample(n): z, 3 score arrays and the mask returned as host arrays'},
+            'pipeline': {'accepted_decoded_per_s': pipe_acc / pipe_s, 'unique_peptides_per_s': pipe_unique / pipe_s,
+                         'draws_per_s': n_pipe * world / pipe_s, 'n_draws': n_pipe * world, 'n_accepted': pipe_acc,
+                         'n_unique': pipe_unique, 'device_only_accepted_decoded_per_s': pipe_acc / (pipe_dev_ms / 1e3),
+                         'api': 'mogQ.rejection_sample_decode(n, model, dataset): flags -> compaction -> re-generation -> beam decode '
+                                '-> dedup -> H/uH/charge on the device, unique accepted peptides to a host table'},
+            'beam_decode_seq_per_s': 8192 * world / (bms / 1e3)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -296,37 +450,18 @@ def run_ours(args):
     e2e_value = gb * K / float(e2e_s.item())
     clock_summary = clocks.summary() if clocks else None
 
+    # ---- strong scaling (BASELINE.json configs[2]: global batch 4096 over the N GPUs), N > 1 only
+    strong = None
+    if world > 1 and not args.no_strong:
+        strong = run_strong(args, cfg, model, st, dev, world, rank, timed, hp)
+
+    # ---- CLaSS (second metric of BASELINE.json: accepted samples/s; configs[3] at N = 1, configs[4] sharded)
+    class_block = run_class(args, st, dev, world, rank, barrier, model)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- CLaSS (secondary metric of BASELINE.json): accepted samples/s, Philox draws + scores + accept
-    w, means, covs, clfs = synth.synthetic_class_setup()
-    gmm = sampling.GmmDevice(w, means, covs, dev)
-    spec = sampling.ClassifierSpec(clfs, dev)
-    n_draws = 10_000_000
-    sampling.class_sample(gmm, spec, n_draws, 1)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    out = sampling.class_sample(gmm, spec, n_draws, 2)
-    e1.record()
-    torch.cuda.synchronize()
-    cms = e0.elapsed_time(e1)
-    acc = int(out['n_accepted'].item())
-    zb = torch.randn(8192, 100, device=dev)
-    cbm = torch.eye(2, device=dev)[torch.arange(8192, device=dev) % 2]
-    sampling.beam_decode(st.params, N_VOCAB, zb, cbm)
-    torch.cuda.synchronize()
-    e0.record()
-    sampling.beam_decode(st.params, N_VOCAB, zb, cbm)
-    e1.record()
-    torch.cuda.synchronize()
-    class_block = {'metric': 'class_accepted_samples_per_s', 'value': acc / (cms / 1e3), 'unit': 'samples/s',
-                   'draws_per_s': n_draws / (cms / 1e3), 'accept_rate': acc / n_draws, 'n_draws': n_draws,
-                   'bytes_written_per_draw': 425, 'hbm_gbs': 425 * n_draws / (cms / 1e3) / 1e9,
-                   'beam_decode_seq_per_s': 8192 / (e0.elapsed_time(e1) / 1e3)}
-
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -338,6 +473,9 @@ def run_ours(args):
         rc = cb.time_class_cpu(1_000_000)
         class_block['cpu_baseline'] = {'value': rc['accepted_per_s'], 'unit': 'samples/s', 'cores': 1, 'kind': rc['kind'],
                                        'sample': 'rejection_sample(1e6): %.2f s, accept rate %.3f' % (rc['seconds'], rc['accept_rate'])}
+        rb = cb.time_beam_cpu({k: v.detach().cpu() for k, v in st.views(st.params).items()}, 192)
+        class_block['beam_cpu_baseline'] = {'value': rb['seq_per_s'], 'unit': 'seq/s', 'cores': rb['cores'], 'kind': rb['kind'],
+                                            'sample': 'beam decode (beam 5, n_best 3) of %d z: %.2f s' % (rb['n'], rb['seconds'])}
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -354,7 +492,7 @@ def run_ours(args):
                   'scalar block copied D2H every step (collected after the next step is enqueued)'},
         'gpu_launches': launches, 'launches_per_step': launches / K,
         'profiled_ms_per_step': prof_ms / K,
-        'roofline': roof, 'cpu_baseline': cpu, 'clocks': clock_summary, 'class': class_block,
+        'roofline': roof, 'cpu_baseline': cpu, 'clocks': clock_summary, 'class': class_block, 'strong_scaling': strong,
     }
     print(json.dumps(line))
     if world > 1:
@@ -395,6 +533,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling arm at N > 1')
+    ap.add_argument('--class-draws', type=int, default=0, help='CLaSS draws per GPU (default 10M at N=1, 12.5M at N>1)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

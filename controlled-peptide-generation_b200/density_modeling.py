@@ -72,13 +72,21 @@ class RejSampleBase:
             out = sampling.class_sample(self._gmm_device(dev), spec, n_samples, self.seed, self._draw_offset)
             self._draw_offset += n_samples
             z, probs, accum, accept = out['z'], out['probs'], out['accum'], out['accept']
-        cast = (lambda a: a.astype(np.float32)) if spec.all_f32 else (lambda a: a)
+        # device -> host through pinned staging (one async copy per array, one synchronise): the reference's return
+        # contract is host data -- z as a CPU tensor, scores / mask as numpy arrays
+        def to_host(t):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            return h
+        if spec.all_f32:                                 # float32 classifiers score in float32 (see the class docstring)
+            probs, accum = probs.float(), accum.float()
+        hz, hp, ha, hm = to_host(z), to_host(probs), to_host(accum), to_host(accept)
+        torch.cuda.current_stream(dev).synchronize()
         scores_z = {}
         for i, name in enumerate(spec.names):
-            scores_z['{}_{}={}'.format(prefix, name, spec.target[i])] = cast(probs[i].cpu().numpy())
-        scores_z[prefix + '_prob_accum'] = cast(accum.cpu().numpy())
-        return z.cpu(), scores_z, accept.cpu().numpy().astype(bool)
-
+            scores_z['{}_{}={}'.format(prefix, name, spec.target[i])] = hp[i].numpy()
+        scores_z[prefix + '_prob_accum'] = ha.numpy()
+        return hz, scores_z, hm.numpy().astype(bool)
 
     def rejection_sample_decode(self, n_samples, model, dataset, prefix='clfZ', device=None, n_best=3, return_device=False):
         """One sampling round with everything after the draw kept on the GPU (BASELINE.json config 5: "beam decode of
@@ -118,7 +126,7 @@ class RejSampleBase:
         kt, kl = hyp0[keep].cpu().tolist(), lens[keep, 0].cpu().tolist()
         seqs = dataset.idx2sentences([row[:n] for row, n in zip(kt, kl)], print_special_tokens=False)
         cast = (lambda a: a.astype(np.float32)) if spec.all_f32 else (lambda a: a)
-        df = {'peptide': seqs, 'z': [tuple(r) for r in z[keep].cpu().tolist()], 'accept_z': np.ones(len(seqs), dtype=bool),
+        df = {'peptide': seqs, 'z': list(z[keep].cpu().numpy()), 'accept_z': np.ones(len(seqs), dtype=bool),
               'draw_index': idx[keep].cpu().numpy()}
         for i, name in enumerate(spec.names):
             df['{}_{}={}'.format(prefix, name, spec.target[i])] = cast(probs[i][keep].cpu().numpy())

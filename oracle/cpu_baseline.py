@@ -213,3 +213,26 @@ def time_class_cpu(n_draws=1_000_000, repeats=1):
         acc = float(np.mean(a))
     return {'draws_per_s': n_draws / best, 'accepted_per_s': acc * n_draws / best, 'accept_rate': acc, 'seconds': best,
             'kind': kind, 'cores': cores, 'n_draws': n_draws}
+
+
+def time_beam_cpu(params, n=192):
+    """Beam decode (beam 5, n_best 3) of n latent points on the host: the reference's own generate_sentences when its
+    tree is present (Python loop per sample and step, models/model.py:258-328), else the oracle restatement."""
+    import torch
+    from . import decode as od
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(n, 100, generator=g)
+    c = torch.eye(2)[torch.randint(0, 2, (n,), generator=g)]
+    kind = 'port'
+    if rh.reference_available():
+        kind = 'reference'
+        model = rh.build_model(params['word_emb.weight'].shape[0])
+        model.load_state_dict({k: v for k, v in params.items() if k in model.state_dict()}, strict=False)
+        model.eval()
+        run = lambda: model.generate_sentences(n, z, c, sample_mode='beam', beam_size=5)
+    else:
+        run = lambda: od.beam_decode(params, z, c)
+    t0 = time.perf_counter()
+    run()
+    dt = time.perf_counter() - t0
+    return {'seq_per_s': n / dt, 'seconds': dt, 'n': n, 'kind': kind, 'cores': host_threads()}
