@@ -269,8 +269,8 @@ def latent_stats(mu, logvar):
     return out
 
 
-def mmd_full(z, z_prior, sigma):
-    out = torch.empty(1, device=z.device)
+def mmd_full(z, z_prior, sigma, out=None):
+    out = torch.empty(1, device=z.device) if out is None else out
     check(lib().cpg_mmd_full(context(z.device), stream_ptr(), ptr(z.contiguous(), torch.float32),
                              ptr(z_prior.contiguous(), torch.float32), z.shape[0], float(sigma), ptr(out)),
           'cpg_mmd_full')

@@ -87,6 +87,17 @@ def assert_distinct_shards(tokens, group=None):
     return True
 
 
+def all_gather_rows(t, group=None, even=False):
+    """Concatenation over ranks of [n_r, ...] tensors.  even=True: every rank holds the same n (one collective, no
+    host synchronisation); else the sizes are exchanged first and the rows padded (ragged shards)."""
+    world = dist.get_world_size(group)
+    if even:
+        out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        return out
+    return all_gather_ragged(t, group)
+
+
 def all_gather_ragged(t, group=None):
     """Concatenation over ranks of [n_r, ...] tensors whose n_r may differ (padded exchange)."""
     world = dist.get_world_size(group)
@@ -132,7 +143,10 @@ def dp_train_step(state, tokens, noise, hp, p_out=0.3, group=None, full_mmd='loc
     eng.clip_adam(state, hp, out=scalars[g:g + 1])
     eng.dp_apply_tail(tail, scalars)
     if full_mmd == 'global' and z_prior_full is not None:
-        zs = all_gather_ragged(z, group)
-        zp = all_gather_ragged(z_prior_full, group)
-        scalars[eng.SC['mmd']] = eng.mmd_full(zs, zp, hp.mmd_sigma)[0]
+        world = dist.get_world_size(group)
+        even = hp.global_batch == world * tokens.shape[0]
+        zs = all_gather_rows(z, group, even)
+        zp = all_gather_rows(z_prior_full, group, even)
+        m = eng.SC['mmd']
+        eng.mmd_full(zs, zp, hp.mmd_sigma, out=scalars[m:m + 1])
     return scalars

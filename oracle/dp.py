@@ -125,5 +125,8 @@ class OracleEngine:
             out[0] = gn
         return torch.tensor([float(gn)])
 
-    def mmd_full(self, z, zp, sigma):
-        return torch.tensor([float(ow.mmd_full_kernel(z, zp, sigma))])
+    def mmd_full(self, z, zp, sigma, out=None):
+        v = torch.tensor([float(ow.mmd_full_kernel(z, zp, sigma))])
+        if out is not None:
+            out.copy_(v)
+        return v
