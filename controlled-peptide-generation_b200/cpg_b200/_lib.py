@@ -92,6 +92,8 @@ def _signatures(L):
         'cpg_fill_uniform': (I, [P, P, c_uint64, c_uint32, F, I64, P]),
         'cpg_beam_decode': (I, [P, P, P, I, I, I, P, P, I, I, P, P, P]),
         'cpg_sample_decode': (I, [P, P, P, I, I, I, P, P, I, F, c_uint64, P, P]),
+        'cpg_soft_decode': (I, [P, P, P, I, I, I, P, P, I, F, c_uint64, P, P, P]),
+        'cpg_flow_forward': (I, [P, P, P, I, I, P, P, P, P, P, I, P, P]),
         'cpg_cnn_classifier_fwd': (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, P, P, P]),
         'cpg_class_score_accept': (I, [P, P, P, P, I64, I, P, P, P, P, P, P, P]),
         'cpg_class_sample': (I, [P, P, P, P, P, I, I, P, P, P, P, c_uint64, I64, I64, P, P, P, P, P, P]),
@@ -100,6 +102,7 @@ def _signatures(L):
         'cpg_gather_rows': (I, [P, P, P, P, I64, I64, I, P]),
         'cpg_dedup_rows': (I, [P, P, P, I64, I, P, P]),
         'cpg_peptide_descriptors': (I, [P, P, P, I64, I, P, I, P, P, ctypes.c_double, F, P, P, P, P]),
+        'cpg_feed_batch': (I, [P, P, P, P, I64, I, c_uint64, c_uint64, I, P, P]),
         'cpg_gmm_logpdf': (I, [P, P, P, I64, P, P, P, I, P]),
         'cpg_prior_logpdf': (I, [P, P, P, I64, P]),
         'cpg_set_option': (I, [c_char_p, I]),

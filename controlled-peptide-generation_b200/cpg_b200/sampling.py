@@ -11,6 +11,7 @@ from ._lib import check, context, lib, ptr, stream_ptr
 
 ZD, CD = 100, 2
 MODE_GREEDY, MODE_CATEGORICAL = 1, 2
+SOFT_MODES = {'none_softmax': 3, 'greedy_softmax': 4, 'categorical_softmax': 5}
 
 
 # ------------------------------------------------------------------------------------- decode
@@ -38,6 +39,21 @@ def sample_decode(params, n_vocab, z, c, mode, max_len=25, temp=1.0, seed=0):
                                   float(temp), int(seed), ptr(toks), ptr(steps)), 'cpg_sample_decode')
     k = int(steps.item())
     return toks[:, :k + 1].to(torch.int64)
+
+
+def soft_decode(params, n_vocab, z, c, mode, max_len=25, temp=1.0, seed=0):
+    """Soft sampling (models/model.py:330-359, forward only): -> (seqIx int64 [n, 1 + steps], seqSoftIx float32
+    [n, 1 + steps, V]): per step softmax(logits / temp), zeroed from the <eos> step on, fed back as a soft embedding."""
+    n = z.shape[0]
+    dev = z.device
+    toks = torch.empty(n, max_len + 1, dtype=torch.int32, device=dev)
+    soft = torch.empty(n, max_len + 1, n_vocab, dtype=torch.float32, device=dev)
+    steps = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib().cpg_soft_decode(context(dev), stream_ptr(), ptr(params), n_vocab, n, max_len,
+                                ptr(z.contiguous(), torch.float32), ptr(c.contiguous(), torch.float32), int(SOFT_MODES[mode]),
+                                float(temp), int(seed), ptr(toks), ptr(soft), ptr(steps)), 'cpg_soft_decode')
+    k = int(steps.item())
+    return toks[:, :k + 1].to(torch.int64), soft[:, :k + 1].contiguous()
 
 
 # ---------------------------------------------------------------------------------------- CNN

@@ -24,7 +24,9 @@ constexpr float NEG_SENT = -1e20f;
 constexpr int D_NU = DEC_HP / 4, D_NT = D_NU * (DR / 4), D_G = 3 * DEC_HP;
 constexpr int FSTR = DEC_HP + 1;
 
-enum DecodeMode { MODE_BEAM = 0, MODE_GREEDY = 1, MODE_CATEGORICAL = 2 };
+// 3..5: soft sampling (models/model.py:330-341): the softmax of every step is returned and fed back as a SOFT embedding
+enum DecodeMode { MODE_BEAM = 0, MODE_GREEDY = 1, MODE_CATEGORICAL = 2, MODE_NONE_SOFTMAX = 3, MODE_GREEDY_SOFTMAX = 4,
+                  MODE_CATEGORICAL_SOFTMAX = 5 };
 
 struct DecodeArgs {
     const float* table;     // [V][312]
@@ -40,6 +42,7 @@ struct DecodeArgs {
     int* out_len;           // beam: [n][n_best]
     float* out_score;       // beam: [n][n_best]
     int* out_steps;         // sampling: max over samples of steps executed (atomicMax)
+    float* out_soft;        // soft sampling: [n][L+1][V] softmax(logits / temp) per step (0 after <eos>), one-hot <start> first
 };
 
 template <int R>
@@ -79,6 +82,7 @@ k_decode(DecodeArgs a) {
     const bool full_warp = warp < nwarps;
     const int tx = tid % D_NU, ty = tid / D_NU;
     const int j0 = 4 * tx, r0 = 4 * ty;
+    constexpr bool SOFT = MODE >= MODE_NONE_SOFTMAX;
     const int V = a.V, L = a.L;
     const int spc = MODE == MODE_BEAM ? BEAM_S : R;          // samples per CTA
     const int samp0 = blockIdx.x * spc;
@@ -124,6 +128,28 @@ k_decode(DecodeArgs a) {
             int sm_ = row_valid(row) ? row_sample(row) : 0;
             const float* base = a.table + (size_t)rtok[row] * G + j0;
             const float* rb = a.rowbias + (size_t)sm_ * G + j0;
+            if (SOFT && s > 0) {
+                // soft embedding of the previous step's (masked) softmax: sum_v p_v T[v]; the table rows carry the input
+                // biases, so the missing mass 1 - sum_v p_v (all of it after <eos>) takes the <pad> row = biases only
+                float4 acc3[3];
+                float rest = 1.0f;
+#pragma unroll
+                for (int g = 0; g < 3; ++g) acc3[g] = __ldg(reinterpret_cast<const float4*>(rb + g * HP));
+                for (int v = 0; v <= V; ++v) {
+                    const float p = v < V ? cand[row * VMAX + v] : rest;
+                    rest -= p;
+                    const float* tv = a.table + (size_t)(v < V ? v : PAD) * G + j0;
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+                        const float4 t4 = __ldg(reinterpret_cast<const float4*>(tv + g * HP));
+                        acc3[g].x = fmaf(p, t4.x, acc3[g].x); acc3[g].y = fmaf(p, t4.y, acc3[g].y);
+                        acc3[g].z = fmaf(p, t4.z, acc3[g].z); acc3[g].w = fmaf(p, t4.w, acc3[g].w);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < 3; ++g) { gi[i][g][0] = acc3[g].x; gi[i][g][1] = acc3[g].y; gi[i][g][2] = acc3[g].z; gi[i][g][3] = acc3[g].w; }
+                continue;
+            }
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
                 float4 v = __ldg(reinterpret_cast<const float4*>(base + g * HP));
@@ -196,7 +222,16 @@ k_decode(DecodeArgs a) {
                 cand[row * VMAX + lane] = lane < V ? v : -INFINITY;
             } else {
                 int nxt;
-                if (MODE == MODE_GREEDY) {
+                float psoft = 0.f;
+                if (SOFT) {                                              // F.softmax(logits / temp, dim=1)
+                    const float sc = logit / a.temp;
+                    const float mx = warp_max(sc);
+                    const float e = lane < V ? expf(sc - mx) : 0.f;
+                    psoft = e / warp_sum(e);
+                }
+                if (MODE == MODE_NONE_SOFTMAX) {
+                    nxt = rtok[row];                                     // the reference never updates sampleIx in this mode
+                } else if (MODE == MODE_GREEDY || MODE == MODE_GREEDY_SOFTMAX) {
                     // torch.argmax: first maximal index
                     float best = logit; int bi = lane;
 #pragma unroll
@@ -224,12 +259,21 @@ k_decode(DecodeArgs a) {
                     unsigned m = __ballot_sync(0xffffffffu, lane < V && cum >= u);
                     nxt = m ? (__ffs((int)m) - 1) : (V - 1);
                 }
-                if (lane == 0) {
-                    int fin = rfin[row];
+                {
+                    const int fin = rfin[row];
                     if (fin) nxt = PAD;                                  // model.py:349 masked_fill_(finished, PAD)
-                    if (nxt == EOS) rfin[row] = 1;                       // model.py:350
-                    rtok[row] = nxt;
-                    if (row_valid(row)) a.out_tok[(size_t)row_sample(row) * (L + 1) + s + 1] = nxt;
+                    const int fin_now = fin || nxt == EOS;               // model.py:350
+                    if (SOFT) {
+                        if (fin_now) psoft = 0.f;                        // model.py:354: zeroed from the <eos> step on
+                        cand[row * VMAX + lane] = lane < V ? psoft : 0.f;
+                        if (lane < V && row_valid(row)) a.out_soft[((size_t)row_sample(row) * (L + 1) + s + 1) * V + lane] = psoft;
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        rfin[row] = fin_now;
+                        rtok[row] = nxt;
+                        if (row_valid(row)) a.out_tok[(size_t)row_sample(row) * (L + 1) + s + 1] = nxt;
+                    }
                 }
             }
         }
@@ -336,6 +380,11 @@ k_decode(DecodeArgs a) {
             int* o = a.out_tok + (size_t)row_sample(row) * (L + 1);
             if (lane == 0) o[0] = START;
             for (int c = steps_done + 1 + lane; c <= L; c += 32) o[c] = PAD;
+            if (SOFT) {
+                float* os = a.out_soft + (size_t)row_sample(row) * (L + 1) * V;
+                if (lane < V) os[lane] = lane == START ? 1.f : 0.f;      // onehot_embed(<start>) (model.py:293)
+                for (int c = (steps_done + 1) * V + lane; c < (L + 1) * V; c += 32) os[c] = 0.f;
+            }
         }
         if (tid == 0 && a.out_steps != nullptr) atomicMax(a.out_steps, steps_done);
         return;
@@ -445,6 +494,38 @@ int cpg_sample_decode(cpg_ctx* ctx, cpg_stream stream, const float* params, int 
         CPG_LAUNCH_NAMED("k_decode_categorical", kfn, ceil_div(n, DR), D_NT, smem, s, a);
     }
     return check_launch("cpg_sample_decode");
+}
+
+int cpg_soft_decode(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int n, int L, const float* z, const float* c,
+                    int mode, float temp, uint64_t seed, int* out_tokens, float* out_soft, int* out_steps) {
+    if (mode < MODE_NONE_SOFTMAX || mode > MODE_CATEGORICAL_SOFTMAX) { set_error("cpg_soft_decode: mode must be 3 (none_softmax), 4 (greedy_softmax) or 5 (categorical_softmax)"); return CPG_EINVAL; }
+    if (!out_tokens || !out_soft || !out_steps) { set_error("cpg_soft_decode: null output"); return CPG_EINVAL; }
+    if (!(temp > 0.f)) { set_error("cpg_soft_decode: temp must be > 0"); return CPG_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    DecodeArgs a;
+    int rc = decode_prepare(ctx, s, params, V, n, L, z, c, a);
+    if (rc) return rc;
+    a.temp = temp; a.seed = seed; a.out_tok = out_tokens; a.out_steps = out_steps; a.out_soft = out_soft;
+#ifdef CPG_EMU
+    *out_steps = 0;
+#else
+    cudaMemsetAsync(out_steps, 0, sizeof(int), s);
+#endif
+    size_t smem = decode_smem_bytes();
+    if (mode == MODE_NONE_SOFTMAX) {
+        auto kfn = k_decode<MODE_NONE_SOFTMAX>;
+        CPG_SET_MAX_SMEM(kfn, smem);
+        CPG_LAUNCH_NAMED("k_decode_none_softmax", kfn, ceil_div(n, DR), D_NT, smem, s, a);
+    } else if (mode == MODE_GREEDY_SOFTMAX) {
+        auto kfn = k_decode<MODE_GREEDY_SOFTMAX>;
+        CPG_SET_MAX_SMEM(kfn, smem);
+        CPG_LAUNCH_NAMED("k_decode_greedy_softmax", kfn, ceil_div(n, DR), D_NT, smem, s, a);
+    } else {
+        auto kfn = k_decode<MODE_CATEGORICAL_SOFTMAX>;
+        CPG_SET_MAX_SMEM(kfn, smem);
+        CPG_LAUNCH_NAMED("k_decode_categorical_softmax", kfn, ceil_div(n, DR), D_NT, smem, s, a);
+    }
+    return check_launch("cpg_soft_decode");
 }
 
 }  // extern "C"

@@ -184,6 +184,29 @@ __global__ void k_peptide_descriptors(const int* __restrict__ tok, int64_t n, in
     if (length != nullptr) length[i] = len;
 }
 
+// ------------------------------------------------------------------------------------- data feed
+// One batch of the weighted random iterator (data_processing/dataset.py:60-77: torch.multinomial(weights, B,
+// replacement=True), then the padded token rows of the chosen examples): row i of the batch takes a Philox uniform,
+// finds its example by binary search in the cumulative sampling weights and copies the example's token row.
+__global__ void k_feed_batch(const uint8_t* __restrict__ tokens, const double* __restrict__ cdf, int64_t n_examples, int L,
+                             uint64_t seed, uint64_t step, int B, int64_t* __restrict__ out, int64_t* __restrict__ out_index) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);          // one warp per batch row
+    const int lane = threadIdx.x & 31;
+    if (i >= B) return;
+    int64_t ex = 0;
+    if (lane == 0) {
+        uint32_t r[4];
+        Philox::gen(seed, step * (uint64_t)B + (uint64_t)i, 0x80000001u, r);
+        const double u = u64_to_unit(r[0], r[1]) * cdf[n_examples - 1];
+        int64_t lo = 0, hi = n_examples - 1;                                    // first example with cdf > u
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (cdf[mid] > u) hi = mid; else lo = mid + 1; }
+        ex = lo;
+        if (out_index != nullptr) out_index[i] = ex;
+    }
+    ex = __shfl_sync(0xffffffffu, ex, 0);
+    for (int t = lane; t < L; t += 32) out[(size_t)i * L + t] = (int64_t)tokens[ex * L + t];
+}
+
 }  // namespace cpg
 
 using namespace cpg;
@@ -253,6 +276,13 @@ int cpg_peptide_descriptors(cpg_ctx* ctx, cpg_stream stream, const int* tokens, 
     for (int t = 0; t < 64; ++t) T.aa_of_token[t] = t < n_tokens ? aa_of_token[t] : (int8_t)-1;
     CPG_LAUNCH(k_peptide_descriptors, (unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream, tokens, n, width, T, H, uH, charge, length);
     return check_launch("cpg_peptide_descriptors");
+}
+
+int cpg_feed_batch(cpg_ctx* ctx, cpg_stream stream, const uint8_t* tokens, const double* cdf, int64_t n_examples, int L,
+                   uint64_t seed, uint64_t step, int B, int64_t* out_tokens, int64_t* out_index) {
+    if (!ctx || !tokens || !cdf || !out_tokens || n_examples < 1 || L < 1 || B < 1) { set_error("cpg_feed_batch: bad argument"); return CPG_EINVAL; }
+    CPG_LAUNCH(k_feed_batch, (unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream, tokens, cdf, n_examples, L, seed, step, B, out_tokens, out_index);
+    return check_launch("cpg_feed_batch");
 }
 
 }  // extern "C"

@@ -13,8 +13,10 @@ What runs where
   forward_decoder()         cpg_wae_decode_teacher (inference)
   forward_classifier()      cpg_cnn_classifier_fwd (inference, eval-mode dropout)
   sample_G / generate_sentences   cpg_beam_decode / cpg_sample_decode
-Not on the B200 hot path (raise NotImplementedError): flow > 0, soft sampling modes, soft (3-D)
-inputs, prevent_empty, the deconv decoder -- phase-2 / optional features of the reference.
+  flow_model (flow > 0)     cpg_flow_forward (models/flow.py), applied in generate_sentences like the reference
+  soft sampling modes       cpg_soft_decode (none_softmax | greedy_softmax | categorical_softmax), forward only
+Not built (raise NotImplementedError): soft (3-D) encoder / classifier inputs, prevent_empty, the deconv decoder, the
+gumbel_* modes (placeholder strings in the reference as well) -- phase-2 training features of the reference.
 """
 from itertools import chain
 
@@ -63,8 +65,6 @@ class RNN_VAE(nn.Module):
     def __init__(self, n_vocab, max_seq_len, z_dim, c_dim, emb_dim, pretrained_emb, freeze_embeddings, flow,
                  flow_type, E_args, G_args, C_args):
         super().__init__()
-        if flow > 0:
-            raise NotImplementedError('flow > 0 is dead on the reference hot path (cfg.py:267) and not built here')
         if not (z_dim == 100 and c_dim == 2 and emb_dim == 150):
             raise NotImplementedError('cpg_b200 kernels are built for z_dim=100, c_dim=2, emb_dim=150')
         if not 4 <= n_vocab <= 32:
@@ -83,7 +83,10 @@ class RNN_VAE(nn.Module):
         self.decoder = build_decoder(embedding=self.word_emb, emb_dim=emb_dim + z_dim + c_dim, output_dim=n_vocab,
                                      h_dim=z_dim + c_dim, **G_args)
         self.classifier = build_classifier('cnn', emb_dim, **C_args)
-        self.use_flow = False
+        self.use_flow = flow > 0                                  # reference models/model.py:70-73
+        if self.use_flow:
+            from models.flow import build_flow
+            self.flow_model = build_flow(flow_type, flow, z_dim)
         self._flat = None
         self._decode_seed = 0
 
@@ -135,12 +138,17 @@ class RNN_VAE(nn.Module):
         return filter(lambda p: p.requires_grad, self.decoder.parameters())
 
     def encoder_params(self):
-        return filter(lambda p: p.requires_grad, chain(self.word_emb.parameters(), self.encoder.parameters()))
+        params = [self.word_emb.parameters(), self.encoder.parameters()]
+        if self.use_flow:
+            params.append(self.flow_model.parameters())
+        return filter(lambda p: p.requires_grad, chain(*params))
 
     def vae_params(self):
         # word_emb is yielded twice (decoder.emb is word_emb), exactly like the reference
-        return filter(lambda p: p.requires_grad,
-                      chain(self.word_emb.parameters(), self.encoder.parameters(), self.decoder.parameters()))
+        params = [self.word_emb.parameters(), self.encoder.parameters(), self.decoder.parameters()]
+        if self.use_flow:
+            params.append(self.flow_model.parameters())
+        return filter(lambda p: p.requires_grad, chain(*params))
 
     # ------------------------------------------------------------------ noise (reference RNG call sites)
     def sample_z(self, mu, logvar):
@@ -194,6 +202,9 @@ class RNN_VAE(nn.Module):
 
     def forward(self, sequences, q_c='prior', sample_z=1):
         """-> ((mu, logvar), (z, c), dec_logits), reference models/model.py:146-195."""
+        if self.use_flow:
+            raise ValueError('Hmm if we properly want to do this, we need to compute flow and return flow-kl loss out of '
+                             'function.')                            # as the reference, models/model.py:173-176
         mbsize, L = sequences.shape
         dev = sequences.device
         st = self.flat_state()
@@ -223,16 +234,21 @@ class RNN_VAE(nn.Module):
             z = self.sample_z_prior(mbsize)
         if c is None:
             c = self.sample_c_prior(mbsize)
-        if not eval_mode:
-            raise NotImplementedError('eval_mode=False is only used for phase-2 soft sampling; not built here')
+        if self.use_flow:                                         # reference :210-214 (train flag = eval_mode)
+            z = z.to(self._param_device())
+            z = self.flow_model(z, train=eval_mode)
+            if eval_mode:
+                z = z[0]
         sentences = self.sample_G(mbsize, z, c, **sample_kwargs)
         return sentences, z, c.argmax(dim=1)
 
     def sample_G(self, mbsize, z, c, sample_mode='categorical', temp=1.0, gumbel_temp=1.0, prepend_start_idx=True,
                  prevent_empty=False, min_length=1, beam_size=5, n_best=3):
-        if sample_mode in _SOFT_MODES or sample_mode == 'gumbel_max':
-            raise NotImplementedError("sample_mode '%s' (soft / gumbel sampling) belongs to phase 2; the B200 path "
-                                      'provides categorical | greedy | beam' % sample_mode)
+        if sample_mode in ('gumbel_soft', 'gumbel_ST', 'gumbel_max'):
+            raise NotImplementedError("sample_mode '%s' is a placeholder string in the reference too (models/model.py:313,"
+                                      '331-335); implemented: categorical | greedy | beam | none_softmax | greedy_softmax | '
+                                      'categorical_softmax' % sample_mode)
+        assert not (sample_mode in _SOFT_MODES and prevent_empty), 'cant prevent_empty when soft sampling'
         if prevent_empty or min_length != 1:
             raise NotImplementedError('prevent_empty / min_length != 1 are not built into the decode kernels')
         assert beam_size >= n_best, "Can't return more than max hypothesis"
@@ -245,6 +261,11 @@ class RNN_VAE(nn.Module):
             toks, lens, _ = sampling.beam_decode(st.params, self.n_vocab, z, c, L, beam_size, n_best)
             toks, lens = toks.cpu().tolist(), lens.cpu().tolist()
             return [[toks[j][i][:lens[j][i]] for i in range(n_best)] for j in range(mbsize)]
+        if sample_mode in sampling.SOFT_MODES:
+            # forward only: the soft samples are not differentiated (phase-2 training is outside this package)
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if sample_mode == 'categorical_softmax' else 0
+            seq, soft = sampling.soft_decode(st.params, self.n_vocab, z, c, sample_mode, L, temp, seed)
+            return (seq, soft) if prepend_start_idx else (seq[:, 1:], soft[:, 1:])
         if sample_mode == 'greedy':
             seq = sampling.sample_decode(st.params, self.n_vocab, z, c, sampling.MODE_GREEDY, L)
         elif sample_mode == 'categorical':

@@ -224,6 +224,22 @@ int cpg_beam_decode(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_
 int cpg_sample_decode(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_vocab, int n, int L, const float* z,
                       const float* c, int mode, float temp, uint64_t seed, int* out_tokens, int* out_steps);
 
+/* Soft sampling modes of sample_G (models/model.py:330-359), forward only: mode 3 = none_softmax (the hard token is never
+ * updated, as in the reference), 4 = greedy_softmax, 5 = categorical_softmax.  out_soft: float [n][L+1][n_vocab] =
+ * softmax(logits / temp) of every step (one-hot <start> first, zeros from the <eos> step on); each step's softmax is fed
+ * back as a soft embedding (decoder.py:86-92, mutils.soft_embed).  out_tokens / out_steps as cpg_sample_decode. */
+int cpg_soft_decode(cpg_ctx* ctx, cpg_stream stream, const float* params, int n_vocab, int n, int L, const float* z,
+                    const float* c, int mode, float temp, uint64_t seed, int* out_tokens, float* out_soft, int* out_steps);
+
+/* ---- normalising flow on the latent code (models/flow.py:30-160) ------------------------------
+ * All layers in one launch.  kind[l]: 0 planar, 1 radial (HOST array).  vec_a / vec_b: HOST arrays of DEVICE pointers to
+ * [100] floats -- planar (weight, scale), radial (initial point, unused).  scalar_a / scalar_b: HOST arrays -- planar
+ * (bias, weight.scale), radial (alpha, beta).  train != 0 also writes loss_out = mean_b sum_l log(|det J_l| + 1e-7) with
+ * the radial determinant exactly as the reference evaluates it (batch-wide Frobenius norm of the radii, flow.py:87). */
+int cpg_flow_forward(cpg_ctx* ctx, cpg_stream stream, const float* z_in, int B, int n_layers, const int* kind,
+                     const float* const* vec_a, const float* const* vec_b, const float* scalar_a, const float* scalar_b,
+                     int train, float* z_out, float* loss_out);
+
 /* ---- CNN attribute classifier forward (models/classifier.py:39-60, eval mode) ---------------- */
 /* conv weights [100][1][w][150] for w = 3,4,5; fc [2][300]; table_ws: 12*n_vocab*100 floats scratch. */
 int cpg_cnn_classifier_fwd(cpg_ctx* ctx, cpg_stream stream, const float* emb, const float* conv_w3, const float* conv_b3,
@@ -276,6 +292,13 @@ int cpg_dedup_rows(cpg_ctx* ctx, cpg_stream stream, const int* rows, int64_t n, 
 int cpg_peptide_descriptors(cpg_ctx* ctx, cpg_stream stream, const int* tokens, int64_t n, int width, const int8_t* aa_of_token,
                             int n_tokens, const float* hydrophobicity20, const double* side_chain_charge20, double charge_ends,
                             float angle_deg, float* H, float* uH, float* charge, int* length);
+/* ---- data feed (data_processing/dataset.py:60-77,242-244,285-286) -----------------------------
+ * The dataset lives on the device as padded token rows uint8 [n_examples][L] (Field(init_token, eos_token, fix_length)
+ * layout) with the cumulative sampling weights cdf fp64 [n_examples].  One call draws a batch of the weighted random
+ * iterator: B examples i.i.d. ~ weights with replacement (Philox(seed, step * B + row)), out_tokens int64 [B][L] in
+ * `batch.text` form; out_index (chosen example per row) may be NULL. */
+int cpg_feed_batch(cpg_ctx* ctx, cpg_stream stream, const uint8_t* tokens, const double* cdf, int64_t n_examples, int L,
+                   uint64_t seed, uint64_t step, int B, int64_t* out_tokens, int64_t* out_index);
 /* mogQ.logpdf batched (density_modeling.py:75-77): mean_t, prec_t fp64 [100][K] (component fastest),
  * logw_norm[k] = log w_k - 50 log(2 pi) + 0.5 sum_d log prec_kd; out fp64 [n]. */
 int cpg_gmm_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, const double* mean_t,
