@@ -85,6 +85,7 @@ def _signatures(L):
         'cpg_softmax_xent': (I, [P, P, P, P, I, I, I, P, P]),
         'cpg_latent_stats': (I, [P, P, P, P, I, P]),
         'cpg_mmd_full': (I, [P, P, P, P, I, F, P]),
+        'cpg_mmd_full_grad': (I, [P, P, P, P, I, F, P]),
         'cpg_mmd_rf': (I, [P, P, P, P, P, P, I, I, F, P, P]),
         'cpg_fill_step_noise': (I, [P, P, c_uint64, c_uint32, I, I, F, F, P, P, P, P, P, P]),
         'cpg_fill_step_noise_overlapped': (I, [P, P, c_uint64, c_uint32, I, I, F, F, P, P, P, P, P, P]),

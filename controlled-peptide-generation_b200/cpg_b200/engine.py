@@ -277,6 +277,13 @@ def mmd_full(z, z_prior, sigma, out=None):
     return out
 
 
+def mmd_full_grad(z, z_prior, sigma):
+    dz = torch.empty_like(z, dtype=torch.float32)
+    check(lib().cpg_mmd_full_grad(context(z.device), stream_ptr(), ptr(z.contiguous(), torch.float32),
+                                  ptr(z_prior.contiguous(), torch.float32), z.shape[0], float(sigma), ptr(dz)), 'cpg_mmd_full_grad')
+    return dz
+
+
 def mmd_rf(z, z_prior, rf_w, rf_b, sigma, want_grad=False):
     out = torch.empty(1, device=z.device)
     dz = torch.empty_like(z) if want_grad else None

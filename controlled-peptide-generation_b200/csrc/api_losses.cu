@@ -113,6 +113,12 @@ int cpg_mmd_full(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* z
     return check_launch("cpg_mmd_full");
 }
 
+int cpg_mmd_full_grad(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* zp, int B, float sigma, float* dz) {
+    if (!ctx || !z || !zp || !dz || B < 2) { set_error("cpg_mmd_full_grad: bad argument"); return CPG_EINVAL; }
+    launch_mmd_full_grad((cudaStream_t)stream, z, zp, B, sigma, 1.0f, dz);
+    return check_launch("cpg_mmd_full_grad");
+}
+
 int cpg_mmd_rf(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* zp, const float* rf_w, const float* rf_b,
                int B, int R, float sigma, float* loss_out, float* dz) {
     if (!ctx || !z || !zp || !rf_w || !rf_b || !loss_out || B < 1 || R < 1) { set_error("cpg_mmd_rf: bad argument"); return CPG_EINVAL; }

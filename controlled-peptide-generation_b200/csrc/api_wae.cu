@@ -657,7 +657,11 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
         set_error("cpg_wae_step_phase2: phase1 was not run for this shape");
         return CPG_EINVAL;
     }
-    if (hp->z_regu == CPG_ZREGU_MMD) { set_error("z_regu_loss='mmd' (full-kernel MMD in the loss) has no backward here; use mmdrf or kl"); return CPG_EINVAL; }
+    if (hp->z_regu == CPG_ZREGU_MMD && (!nz->z_prior_full || (hp->global_batch > 0 && hp->global_batch != B))) {
+        set_error("z_regu_loss='mmd' differentiates the full-kernel MMD of the whole batch: it needs z_prior_full and runs on one GPU "
+                  "(under data parallelism use mmdrf, whose coupling is two R-float sums)");
+        return CPG_EINVAL;
+    }
     cudaStream_t s = (cudaStream_t)stream;
     const int R = hp->rf_dim;
     const int Bg = hp->global_batch > 0 ? hp->global_batch : B;
@@ -677,8 +681,12 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
             launch_sgemm(q, B, ZD, R, 1.f, w.rf_pre1, R, 1, nz->rf_w, 1, R, 0.f, w.dz_rf, ZD, nullptr, 1, nullptr);
             dz_rf = w.dz_rf;
         }
-        if (hp->compute_full_mmd && nz->z_prior_full)
+        if ((hp->compute_full_mmd || hp->z_regu == CPG_ZREGU_MMD) && nz->z_prior_full)
             if ((rc = launch_mmd_full(q, w.z, nz->z_prior_full, B, hp->mmd_sigma, w.mmd_ws, w.mmd_out))) return rc;
+        if (hp->z_regu == CPG_ZREGU_MMD) {                          // the full-kernel MMD is the regulariser: its gradient at z
+            launch_mmd_full_grad(q, w.z, nz->z_prior_full, B, hp->mmd_sigma, hp->beta, w.dz_rf);
+            dz_rf = w.dz_rf;
+        }
         if (side) side_leave(ctx);
     }
     // reconstruction loss fwd+bwd with the global token count (coupled[0])
@@ -702,7 +710,7 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
         ComposeArgs c;
         memset(&c, 0, sizeof(c));
         c.ntok = coupled + 0; c.nll_sum = w.nll_sum; c.lat_sums = coupled + 2;
-        c.mmd = (hp->compute_full_mmd && nz->z_prior_full) ? w.mmd_out : nullptr;
+        c.mmd = ((hp->compute_full_mmd || hp->z_regu == CPG_ZREGU_MMD) && nz->z_prior_full) ? w.mmd_out : nullptr;
         c.mmdrf = w.mmdrf_out;
         c.beta = hp->beta; c.lambda_l1 = hp->lambda_logvar_l1; c.lambda_kl = hp->lambda_logvar_kl;
         c.z_regu = hp->z_regu; c.B_global = Bg; c.out = scalars;

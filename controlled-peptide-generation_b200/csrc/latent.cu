@@ -310,6 +310,65 @@ void launch_mmd_full_simt(cudaStream_t s, const float* z, const float* zp, int N
     CPG_LAUNCH(k_mmd_final, 1, 256, 0, s, part, nt * nt, diag_part, ndiag, N, out);
 }
 
+// ---- gradient of the full-kernel MMD wrt z (z_regu_loss = 'mmd': losses.py:47-56 under loss.backward()).
+// With H = K11 + K22 - 2 K12 and the reference's row-broadcast `H - diag(H)`:
+//   L N (N-1) = sum_ij K11_ij - 2 sum_ij K12_ij + 2 N sum_j K12_jj + const
+//   dL/dz_i   = 4 / (sigma^2 N (N-1)) * [ -sum_j K11_ij (z_i - z_j) + sum_j K12_ij (z_i - y_j) - N K12_ii (z_i - y_i) ]
+// fp32 SIMT (exact distances): 16 rows per CTA, 16 lanes per row over the 100 dimensions, columns staged through
+// shared memory.  A differentiated full-kernel MMD is outside the reference's default configuration.
+constexpr int MG_ROWS = 16, MG_LPR = 16, MG_COLS = 32, MG_D = 7;       // 7 * 16 >= 100
+__global__ void __launch_bounds__(MG_ROWS * MG_LPR)
+k_mmd_full_grad(const float* __restrict__ z, const float* __restrict__ y, int N, float sigma, float w, float* __restrict__ dz) {
+    __shared__ float xs[MG_COLS][ZD + 1];
+    const int r = threadIdx.x / MG_LPR, l = threadIdx.x % MG_LPR;
+    const int i = blockIdx.x * MG_ROWS + r;
+    const bool live = i < N;
+    const float inv_s2 = 1.0f / (sigma * sigma);
+    float zi[MG_D], acc[MG_D];
+#pragma unroll
+    for (int q = 0; q < MG_D; ++q) {
+        const int d = l + MG_LPR * q;
+        zi[q] = (live && d < ZD) ? z[(size_t)i * ZD + d] : 0.f;
+        acc[q] = 0.f;
+    }
+    for (int pass = 0; pass < 2; ++pass) {                         // 0: columns z (K11, sign -), 1: columns y (K12, sign +)
+        const float* X = pass == 0 ? z : y;
+        const float sign = pass == 0 ? -1.0f : 1.0f;
+        for (int j0 = 0; j0 < N; j0 += MG_COLS) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < MG_COLS * ZD; t += MG_ROWS * MG_LPR) {
+                const int c = t / ZD, d = t % ZD;
+                xs[c][d] = (j0 + c < N) ? X[(size_t)(j0 + c) * ZD + d] : 0.f;
+            }
+            __syncthreads();
+            const int nc = min(MG_COLS, N - j0);
+            for (int c = 0; c < nc; ++c) {
+                float df[MG_D], d2 = 0.f;
+#pragma unroll
+                for (int q = 0; q < MG_D; ++q) {
+                    const int d = l + MG_LPR * q;
+                    df[q] = d < ZD ? zi[q] - xs[c][d] : 0.f;
+                    d2 = fmaf(df[q], df[q], d2);
+                }
+#pragma unroll
+                for (int o = MG_LPR / 2; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+                float k = sign * expf(-d2 * inv_s2);
+                if (pass == 1 && j0 + c == i) k -= (float)N * expf(-d2 * inv_s2);      // the -N K12_ii (z_i - y_i) term
+#pragma unroll
+                for (int q = 0; q < MG_D; ++q) acc[q] = fmaf(k, df[q], acc[q]);
+            }
+        }
+    }
+    if (live) {
+        const float coef = w * 4.0f * inv_s2 / ((float)N * (float)(N - 1));
+#pragma unroll
+        for (int q = 0; q < MG_D; ++q) { const int d = l + MG_LPR * q; if (d < ZD) dz[(size_t)i * ZD + d] = coef * acc[q]; }
+    }
+}
+void launch_mmd_full_grad(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float w, float* dz) {
+    CPG_LAUNCH(k_mmd_full_grad, ceil_div(N, MG_ROWS), MG_ROWS * MG_LPR, 0, s, z, zp, N, sigma, w, dz);
+}
+
 int g_opt_mmd_tc = 1;
 int g_sm_count = 148;
 size_t mmd_ws_floats(int N) {

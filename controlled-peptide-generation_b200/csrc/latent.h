@@ -50,6 +50,8 @@ size_t mmd_ws_floats(int N);
 int launch_mmd_full(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float* ws, float* out);
 int launch_mmd_full_tc2(cudaStream_t s, const float* z, const float* zp, int N, float sigma, int sm_count, float* ws,
                         float* out);
+// dz = w * d mmd_full_kernel(z, zp) / dz   (fp32 SIMT)
+void launch_mmd_full_grad(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float w, float* dz);
 extern int g_opt_mmd_tc;     // 0 = fp32 SIMT, 1 = persistent tcgen05 (default), 3 = one-tile-per-CTA tcgen05
 extern int g_sm_count;
 void launch_compose_scalars(cudaStream_t s, const ComposeArgs& a);

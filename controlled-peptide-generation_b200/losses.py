@@ -72,12 +72,14 @@ def wae_mmd_gaussianprior(z, method='full_kernel'):
 class _MmdFull(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z1, z2, sigma):
+        ctx.save_for_backward(z1.detach(), z2.detach())
+        ctx.sigma = sigma
         return engine.mmd_full(z1.detach(), z2.detach(), sigma)[0].clone()
 
     @staticmethod
     def backward(ctx, g):
-        raise NotImplementedError("the full-kernel MMD is forward-only on the B200 path (the reference default "
-                                  "z_regu_loss='mmdrf' only logs it); use 'mmdrf' or 'kl' in the loss")
+        z1, z2 = ctx.saved_tensors
+        return engine.mmd_full_grad(z1, z2, ctx.sigma) * g, None, None       # gradient wrt z1 only (z2 is the prior sample)
 
 
 def mmd_full_kernel(z1, z2, **mmd_kwargs):

@@ -172,11 +172,10 @@ def _train_modular(cfgv, model, dataset):
         (z_mu, z_logvar), (z, c), dec_logits = model(tokens, q_c='prior', sample_z=1)
         recon_loss = losses.recon_dec(tokens, dec_logits)
         kl_loss = losses.kl_gaussianprior(z_mu, z_logvar)
-        wae_mmd_loss = losses.wae_mmd_gaussianprior(z.detach(), method='full_kernel')
+        # the full-kernel MMD is differentiated only when it is the regulariser (same draw order as the reference)
+        wae_mmd_loss = losses.wae_mmd_gaussianprior(z if cfgv.z_regu_loss == 'mmd' else z.detach(), method='full_kernel')
         wae_mmdrf_loss = losses.wae_mmd_gaussianprior(z, method='rf')
-        if cfgv.z_regu_loss == 'mmd':
-            raise NotImplementedError("z_regu_loss='mmd' needs the full-kernel MMD backward; use mmdrf or kl")
-        z_regu_loss = {'kl': kl_loss, 'mmdrf': wae_mmdrf_loss}[cfgv.z_regu_loss]
+        z_regu_loss = {'kl': kl_loss, 'mmd': wae_mmd_loss, 'mmdrf': wae_mmdrf_loss}[cfgv.z_regu_loss]
         z_logvar_L1 = z_logvar.abs().sum(1).mean(0)
         z_logvar_KL_penalty = losses.kl_gaussian_sharedmu(z_mu, z_logvar)
         loss = recon_loss + beta * z_regu_loss + cfgv.lambda_logvar_L1 * z_logvar_L1 \

@@ -185,6 +185,9 @@ int cpg_latent_stats(cpg_ctx* ctx, cpg_stream stream, const float* mu, const flo
 /* mmd_full_kernel (losses.py:47-56,96-108), gaussian kernel, as executed by the reference */
 int cpg_mmd_full(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* z_prior, int B, float sigma,
                  float* loss_out);
+/* d mmd_full_kernel / d z: what loss.backward() propagates when cfg.vae.z_regu_loss = 'mmd' (the reference default
+ * 'mmdrf' only logs the full-kernel value); dz: [B,100] */
+int cpg_mmd_full_grad(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* z_prior, int B, float sigma, float* dz);
 /* mmd_rf (losses.py:59-93); dz may be NULL; dz = d loss / d z */
 int cpg_mmd_rf(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* z_prior, const float* rf_w,
                const float* rf_b, int B, int rf_dim, float sigma, float* loss_out, float* dz);

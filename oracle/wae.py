@@ -271,8 +271,11 @@ def wae_forward_losses(p, tokens, noise, beta=1.0, lambda_l1=0.0, lambda_kl=1e-3
     out['recon'] = recon_dec(tokens, logits)
     out['kl'] = kl_gaussianprior(mu, logvar)
     if with_full_mmd:
-        with torch.no_grad():
-            out['mmd'] = mmd_full_kernel(z.detach(), noise['z_prior_full'], sigma)
+        if z_regu == 'mmd':                    # train_vae.py:29-31: the full-kernel MMD is in the loss and differentiated
+            out['mmd'] = mmd_full_kernel(z, noise['z_prior_full'], sigma)
+        else:
+            with torch.no_grad():
+                out['mmd'] = mmd_full_kernel(z.detach(), noise['z_prior_full'], sigma)
     out['mmdrf'] = mmd_rf(z, noise['z_prior_rf'], noise['rf_w'], noise['rf_b'], sigma, rf_dim)
     out['logvar_l1'] = logvar.abs().sum(1).mean(0)
     out['logvar_kl'] = kl_gaussian_sharedmu(mu, logvar)

@@ -110,7 +110,7 @@ def test_train_iterations_match_reference_golden(eng, batch):
     assert_params_close(st.views(st.params), final, g0, 'final', max_outliers=3)
 
 
-@pytest.mark.parametrize('batch,z_regu', [(6, 'mmdrf'), (40, 'mmdrf'), (40, 'kl'), (131, 'mmdrf')])
+@pytest.mark.parametrize('batch,z_regu', [(6, 'mmdrf'), (40, 'mmdrf'), (40, 'kl'), (131, 'mmdrf'), (40, 'mmd'), (131, 'mmd')])
 def test_train_step_matches_oracle(eng, batch, z_regu, max_outliers=0):
     dev = torch.device('cuda')
     p = ow.random_params(V, seed=11)
@@ -453,3 +453,20 @@ def test_fused_bptt_weight_gradients_vs_separate_kernels(eng, batch):
         ref = grads['simt'][k].numpy()
         scale = float(np.abs(ref).max()) + 1e-12
         np.testing.assert_allclose(grads['fused'][k].numpy(), ref, rtol=1e-3, atol=1e-4 * scale, err_msg='fused ' + k)
+
+
+def test_full_kernel_mmd_gradient_matches_autograd(eng):
+    """d mmd_full_kernel / dz (z_regu_loss='mmd') against autograd through the oracle's restatement of losses.py:47-56,96-108."""
+    import losses
+    dev = torch.device('cuda')
+    for n in (2, 33, 300):
+        g = torch.Generator().manual_seed(n)
+        z = (torch.randn(n, 100, generator=g) * 0.9 + 0.1).requires_grad_(True)
+        y = torch.randn(n, 100, generator=g)
+        ow.mmd_full_kernel(z, y, 7.0).backward()
+        dz = eng.mmd_full_grad(z.detach().to(dev), y.to(dev), 7.0).cpu()
+        np.testing.assert_allclose(dz.numpy(), z.grad.numpy(), rtol=1e-4, atol=1e-6 * float(z.grad.abs().max()))
+        zd = z.detach().to(dev).requires_grad_(True)
+        losses.mmd_full_kernel(zd, y.to(dev), sigma=7.0, kernel='gaussian').backward()      # module-level autograd path
+        np.testing.assert_allclose(zd.grad.cpu().numpy(), z.grad.numpy(), rtol=1e-4, atol=1e-6 * float(z.grad.abs().max()))
+        z.grad = None
