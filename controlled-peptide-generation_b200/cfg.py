@@ -157,6 +157,8 @@ _DEFAULTS = {
                                    # (train_vae.last_scalars; e.g. for a NaN watchdog); 0 = log iterations only
         'decode_accepted_only': False,   # sample_pipeline: True = compact the accepted z on the device and decode only those
                                          # (rows of the round table = unique accepted peptides); False = decode every draw
+        'q_fit': 'sklearn',        # mogQ fit: 'sklearn' (reference: host GaussianMixture.fit) | 'device' (EM kernels, cpg_b200.fit)
+        'clf_fit': 'sklearn',      # z-space classifiers: 'sklearn' (LogisticRegression lbfgs) | 'device' (Newton, GPU statistics)
         'dp_full_mmd': 'local',    # under torch.distributed: 'local' = the log-only full-kernel MMD of this rank's shard,
                                    # 'global' = all-gather z / z_prior and evaluate the global-batch value
     },

@@ -106,6 +106,9 @@ def _signatures(L):
         'cpg_feed_batch': (I, [P, P, P, P, I64, I, c_uint64, c_uint64, I, P, P]),
         'cpg_gmm_logpdf': (I, [P, P, P, I64, P, P, P, I, P]),
         'cpg_prior_logpdf': (I, [P, P, P, I64, P]),
+        'cpg_gmm_em_step': (I, [P, P, P, I64, I, P, P, P, ctypes.c_double, P, P, P, P, P]),
+        'cpg_logreg_newton_stats': (I, [P, P, P, P, I64, P, P]),
+        'cpg_logreg_stats_len': (I, []),
         'cpg_set_option': (I, [c_char_p, I]),
         'cpg_profile_enable': (I, [I]),
         'cpg_profile_read': (I, [P, I, P, P, I]),

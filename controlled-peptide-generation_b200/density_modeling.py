@@ -144,8 +144,17 @@ class mogQ(RejSampleBase):
         self.N, self.D = mu.shape
         self.z = torch.cat([mu + (0.5 * logvar).exp() * torch.randn_like(logvar) for _ in range(z_num_samples)], dim=0)
         self.n_components = n_components
-        self.mog = sklearn.mixture.GaussianMixture(n_components=n_components, **mog_kwargs)
-        self.mog.fit(self.z.cpu().numpy())
+        import cfg
+        if str(getattr(cfg.b200, 'q_fit', 'sklearn')) == 'device':
+            # EM on the GPU (cpg_b200.fit: sklearn's EM arithmetic in fp64; started from K data points instead of
+            # sklearn's host k-means, so it reaches a different local optimum of the same likelihood)
+            from cpg_b200 import fit
+            self.mog = fit.gmm_fit_diag(self.z.float().to(_device()), n_components, tol=mog_kwargs.get('tol', 1e-3),
+                                        max_iter=mog_kwargs.get('max_iter', 100), reg_covar=mog_kwargs.get('reg_covar', 1e-6),
+                                        seed=int(cfg.seed))
+        else:
+            self.mog = sklearn.mixture.GaussianMixture(n_components=n_components, **mog_kwargs)
+            self.mog.fit(self.z.cpu().numpy())
         self._gmm = None
         print('mog-{}. Converged: {} in {} iters, log likelihood lower bound: {:.4f}'.format(
             n_components, self.mog.converged_, self.mog.n_iter_, self.mog.lower_bound_))
@@ -173,6 +182,12 @@ class mogQ(RejSampleBase):
 
     def sample(self, n_samples):
         """Host draw through sklearn / numpy's global RNG (reference density_modeling.py:79-80)."""
+        if not hasattr(self.mog, 'sample'):                 # fitted on the device: same draw procedure, numpy global stream
+            m = self.mog
+            n_k = np.random.multinomial(n_samples, m.weights_)
+            X = np.vstack([mean + np.random.standard_normal((int(k), mean.shape[0])) * np.sqrt(cov)
+                           for mean, cov, k in zip(m.means_, m.covariances_, n_k)])
+            return torch.from_numpy(X).float()
         return torch.from_numpy(self.mog.sample(n_samples)[0]).float()
 
 

@@ -130,10 +130,14 @@ def score_clfZ(clf, z):
 
 def fit_clfZ(zpos_mu, zneg_mu):
     """LogisticRegression(lbfgs, 200) between attr=1 and attr=0 encodings (the fit inside build_clfZ)."""
-    from sklearn.linear_model import LogisticRegression
     X = torch.cat([zpos_mu, zneg_mu], dim=0).numpy()
     Y = torch.cat([torch.ones(zpos_mu.shape[0]), torch.zeros(zneg_mu.shape[0])], dim=0).numpy()
-    clf = LogisticRegression(solver='lbfgs', max_iter=200)
+    if str(getattr(cfg.b200, 'clf_fit', 'sklearn')) == 'device':
+        from cpg_b200.fit import DeviceLogisticRegression       # same objective, Newton steps with GPU statistics
+        clf = DeviceLogisticRegression()
+    else:
+        from sklearn.linear_model import LogisticRegression
+        clf = LogisticRegression(solver='lbfgs', max_iter=200)
     clf.fit(X, Y)
     LOG.info('num samples: {} pos, {} neg. train accuracy={:.5f}'.format(zpos_mu.shape[0], zneg_mu.shape[0], clf.score(X, Y)))
     return clf

@@ -309,6 +309,21 @@ int cpg_gmm_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, c
 /* prior_logpdf batched (density_modeling.py:11-14) */
 int cpg_prior_logpdf(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t n, double* out);
 
+/* ---- fitting Q(z) and the z-space classifiers on the device (density_modeling.py:64-73, sample_pipeline.py:169-192) ----
+ * cpg_gmm_em_step: one EM iteration of a diagonal Gaussian mixture in fp64 (sklearn's arithmetic).  x fp32 [N][100];
+ *   mean_in / prec_in fp64 [K][100] (prec = 1 / cov), logw_norm_in[k] = log w_k - 50 log(2 pi) + 0.5 sum_d log prec_kd;
+ *   resp_ws: fp64 [N][K] scratch (responsibilities); outputs: weights_out[k] = n_k / N (un-normalised), mean_out, cov_out
+ *   (incl. reg_covar), loglik_out fp64 [N] = log-likelihood of every point under the INPUT parameters.
+ * cpg_logreg_newton_stats: for w fp64 [101] (100 coefficients + intercept) and labels y in {0,1} (fp32 [N]):
+ *   out fp64 [cpg_logreg_stats_len()] = [sum_i log-loss | gradient (101) | Hessian upper triangle, row-major (5151)],
+ *   WITHOUT the L2 penalty (the caller adds it). */
+int cpg_gmm_em_step(cpg_ctx* ctx, cpg_stream stream, const float* x, int64_t N, int K, const double* mean_in, const double* prec_in,
+                    const double* logw_norm_in, double reg_covar, double* resp_ws, double* weights_out, double* mean_out,
+                    double* cov_out, double* loglik_out);
+int cpg_logreg_newton_stats(cpg_ctx* ctx, cpg_stream stream, const float* x, const float* y01, int64_t N, const double* w101,
+                            double* out);
+int cpg_logreg_stats_len(void);
+
 /* ---- options ------------------------------------------------------------------------------------
  * Which flavour of a kernel runs (the defaults pick the tcgen05 paths where the batch is large enough to
  * fill the chip; the fp32 SIMT kernels stay for small batches and are what the parity tests compare with):

@@ -109,8 +109,8 @@ def _trained_model():
     return m
 
 
-@pytest.mark.parametrize('accepted_only', [False, True])
-def test_sample_pipeline_main_end_to_end(accepted_only, tmp_path):
+@pytest.mark.parametrize('accepted_only,backend', [(False, 'sklearn'), (True, 'sklearn'), (True, 'device')])
+def test_sample_pipeline_main_end_to_end(accepted_only, backend, tmp_path):
     """sample_pipeline.main(args) as the reference runs it: states files -> Q fit -> z classifiers -> rounds of
     rejection sampling + decode + dedup -> samples written to cfg.savepath."""
     import cfg
@@ -121,6 +121,7 @@ def test_sample_pipeline_main_end_to_end(accepted_only, tmp_path):
     old = (getattr(cfg, 'savepath', None), cfg.attributes, cfg.vae.n_iter, cfg.b200.decode_accepted_only)
     cfg.savepath, cfg.attributes, cfg.vae.n_iter = str(tmp_path), [('amp', 1), ('tox', 1), ('sol', 1)], 77
     cfg.b200.decode_accepted_only = accepted_only
+    cfg.b200.q_fit = cfg.b200.clf_fit = backend              # 'device': EM / Newton fits on the GPU
     try:
         rs = np.random.RandomState(0)
         for split, n in (('train', 900), ('test', 200)):
@@ -139,6 +140,7 @@ def test_sample_pipeline_main_end_to_end(accepted_only, tmp_path):
         samples = sp.main(args, model=model, dataset=ds)
     finally:
         cfg.savepath, cfg.attributes, cfg.vae.n_iter, cfg.b200.decode_accepted_only = old
+        cfg.b200.q_fit = cfg.b200.clf_fit = 'sklearn'
     assert samples['accept'].sum() >= 30 and samples['peptide'].is_unique
     for col in ('peptide', 'z', 'accept_z', 'accept', 'clfZ_amp=1', 'clfZ_tox=0', 'clfZ_prob_accum', 'H', 'uH', 'charge'):
         assert col in samples.columns, col
@@ -193,3 +195,46 @@ def test_device_round_equals_reference_style_round(mods):
 
 def pd_dup(model, ds, acc_rows):
     return acc_rows.peptide.duplicated().to_numpy()
+
+
+def test_device_em_matches_sklearn_from_the_same_start():
+    """EM iterations of the diagonal mixture on the GPU == sklearn's, given sklearn's own initial parameters."""
+    import warnings
+    import sklearn.mixture
+    from cpg_b200 import fit
+    rs = np.random.RandomState(1)
+    N, K = 6000, 8
+    cent = rs.randn(K, 100) * 0.35                                     # overlapping components: EM moves for many iterations
+    x = (cent[rs.randint(0, K, N)] + rs.randn(N, 100) * (0.5 + rs.rand(1, 100))).astype(np.float32)
+    mi = x[rs.choice(N, K, replace=False)].astype(np.float64)
+    wi = rs.dirichlet(np.ones(K) * 5)
+    ci = np.tile(x.var(0), (K, 1)).astype(np.float64) * (0.5 + rs.rand(K, 1))
+    for iters in (1, 7):
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            sk = sklearn.mixture.GaussianMixture(K, covariance_type='diag', means_init=mi, weights_init=wi, precisions_init=1 / ci,
+                                                 max_iter=iters, tol=0.0).fit(x.astype(np.float64))
+        me = fit.gmm_fit_diag(torch.from_numpy(x).cuda(), K, mi, wi, ci, tol=0.0, max_iter=iters)
+        np.testing.assert_allclose(me.weights_, sk.weights_, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(me.means_, sk.means_, rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(me.covariances_, sk.covariances_, rtol=1e-8, atol=1e-10)
+        assert me.lower_bound_ == pytest.approx(sk.lower_bound_, rel=1e-10) and me.n_iter_ == iters
+    free = fit.gmm_fit_diag(torch.from_numpy(x).cuda(), K, tol=1e-3, max_iter=100, seed=3)   # own start: converges, likelihood as good
+    assert free.converged_ and free.lower_bound_ > sk.lower_bound_ - 1.0
+
+
+def test_device_logistic_regression_reaches_sklearns_optimum():
+    import sklearn.linear_model
+    from cpg_b200 import fit
+    rs = np.random.RandomState(2)
+    X = (rs.randn(3000, 100) * 0.8).astype(np.float32)
+    w = rs.randn(100) * 0.25
+    Y = ((X @ w + 0.4 + rs.logistic(size=3000)) > 0).astype(np.float64)
+    sk = sklearn.linear_model.LogisticRegression(solver='lbfgs', max_iter=5000, tol=1e-12).fit(X.astype(np.float64), Y)
+    me = fit.DeviceLogisticRegression().fit(X, Y)
+    np.testing.assert_allclose(me.coef_, sk.coef_, rtol=1e-4, atol=2e-6)
+    assert me.intercept_[0] == pytest.approx(sk.intercept_[0], rel=1e-4, abs=2e-6)
+    np.testing.assert_allclose(me.predict_proba(X), sk.predict_proba(X.astype(np.float64)), atol=1e-6)
+    ref = sklearn.linear_model.LogisticRegression(solver='lbfgs', max_iter=200).fit(X.astype(np.float64), Y)   # the reference's settings
+    assert np.abs(me.predict_proba(X) - ref.predict_proba(X.astype(np.float64))).max() < 2e-3
+    assert me.coef_.dtype == np.float64 and me.coef_.shape == (1, 100)
