@@ -187,8 +187,11 @@ def test_mogQ_rejection_sample_and_pipeline(model):
     # one pipeline round on Philox draws, decode accepted only
     ds = Dataset([])
     df = sp.one_sampling_round(model, ds, Q, 300, decode_accepted_only=True)
-    assert len(df) == 300 and df['accept'].sum() == df['peptide'].notna().sum()
-    assert 0.1 < df['accept'].mean() < 0.5
+    st = Q.last_round_stats                       # device round: one row per UNIQUE accepted peptide
+    assert st['n_draws'] == 300 and len(df) == st['n_unique'] <= st['n_accepted'] and bool(df['accept'].all())
+    assert 0.1 < st['n_accepted'] / 300 < 0.5 and df['peptide'].is_unique
+    full = sp.one_sampling_round(model, ds, Q, 300)                 # reference behaviour: every draw decoded
+    assert len(full) == 300 and 0.1 < full['accept'].mean() < 0.5 and full['peptide'].notna().all()
     out = sp.run_sampling(model, ds, Q, n_samples_per_round=200, n_samples_acc=20, max_rounds=20)
     assert out['accept'].sum() >= 20 and out['peptide'].is_unique
 
