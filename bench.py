@@ -374,14 +374,17 @@ def run_ours(args):
     gb = B * world
     counter = {'it': 0}
 
+    stepper = engine.FusedStepper(st, B, L, hp, seed=seed, rf_dim=cfg.losses.wae_mmd.rf_dim) if world == 1 else None
+
     def step():
         it = counter['it']
         counter['it'] += 1
-        hp.beta = float(utils.anneal(cfg.vae.beta, it))
+        beta = float(utils.anneal(cfg.vae.beta, it))
+        if world == 1:                                             # what train_vae issues per iteration: noise + step, one C call
+            return stepper.step(tokens, it, beta)                  # (captured CUDA graph from the third call on)
+        hp.beta = beta
         engine.fill_step_noise(noise, seed, it, overlap=True)      # next reader is the train step below
-        if world > 1:
-            return parallel.dp_train_step(st, tokens, noise, hp, global_batch=gb)
-        return engine.train_step(st, tokens, noise, hp)[0]
+        return parallel.dp_train_step(st, tokens, noise, hp, global_batch=gb)
 
     def barrier():
         if world > 1:
@@ -484,6 +487,7 @@ def run_ours(args):
                    'parallelism': 'dp%d' % world if world > 1 else 'single',
                    'l2_policy': 'per-step working set (activation stash ~1.1 GB) exceeds the 126 MB L2; no flush needed',
                    'noise': 'Philox in-kernel, regenerated every step',
+                   'launch': 'single GPU: one captured CUDA graph per iteration (cpg_wae_train_step_philox); N > 1: eager launches around the NCCL exchanges',
                    'arithmetic': 'fp32 storage and accumulation; recurrence / decoder-output contractions as split-bf16 '
                                  '(x1+x2, 3 products; logits 3 terms) tcgen05 MMAs, weight-gradient and MMD Gram contractions tf32, '
                                  'dense layers fp32 SIMT'},

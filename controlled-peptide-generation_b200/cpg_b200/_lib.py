@@ -41,6 +41,11 @@ class TrainHparams(Structure):
                 ('compute_full_mmd', c_int), ('adam_step', c_int), ('global_batch', c_int)]
 
 
+class StepNoiseBuffers(Structure):
+    _fields_ = [('eps', c_void_p), ('c', c_void_p), ('word_drop', c_void_p), ('out_keep', c_void_p),
+                ('z_prior_full', c_void_p), ('z_prior_rf', c_void_p), ('rf_w', c_void_p), ('rf_b', c_void_p)]
+
+
 class LossNoise(Structure):
     _fields_ = [('z_prior_full', c_void_p), ('z_prior_rf', c_void_p), ('rf_w', c_void_p), ('rf_b', c_void_p)]
 
@@ -72,6 +77,8 @@ def _signatures(L):
         'cpg_wae_backward': (I, [P, P, P, I, I, I, POINTER(WaeInputs), P, P, P, P, P]),
         'cpg_wae_train_step': (I, [P, P, P, P, P, P, I, I, I, POINTER(WaeInputs), POINTER(LossNoise),
                                    POINTER(TrainHparams), P, P, P, P, P]),
+        'cpg_wae_train_step_philox': (I, [P, P, P, P, P, P, I, I, I, P, POINTER(StepNoiseBuffers), POINTER(TrainHparams),
+                                          c_uint64, c_uint32, F, F, P]),
         'cpg_coupled_count': (I64, [I]),
         'cpg_wae_step_phase1': (I, [P, P, P, I, I, I, POINTER(WaeInputs), POINTER(LossNoise),
                                     POINTER(TrainHparams), P, P, P, P]),

@@ -10,7 +10,7 @@ from ctypes import byref, c_void_p
 import torch
 
 from . import _lib
-from ._lib import (SC, SC_COUNT, ZREGU, LossNoise, TrainHparams, WaeInputs, check, context, lib, ptr,
+from ._lib import (SC, SC_COUNT, ZREGU, LossNoise, StepNoiseBuffers, TrainHparams, WaeInputs, check, context, lib, ptr,
                    stream_ptr)
 
 # layout order of cpg_vae_param_layout (== unique tensors of RNN_VAE.vae_params(), models/model.py:88-94)
@@ -353,8 +353,7 @@ class FusedStepper:
         self.scalars = torch.zeros(SC_COUNT, device=dev)
         self.ctx, self.lib = context(dev), lib()
         self.nz = _loss_noise(self.noise)
-        self._tokens = None
-        self._inp = None
+        self._nb = None
         n = self.noise
         self._noise_args = (ptr(n['eps']), ptr(n['c']), ptr(n['word_drop']), ptr(n['out_keep']),
                             ptr(n.get('z_prior_full')), ptr(n['z_prior_rf']))
@@ -362,19 +361,20 @@ class FusedStepper:
         self._null = c_void_p(None)
 
     def step(self, tokens, it, beta):
-        """tokens: contiguous int64 [B, L] on the device.  Returns the device scalar block (not synchronised)."""
+        """tokens: contiguous int64 [B, L] on the device.  Returns the device scalar block (not synchronised).
+        One C call: Philox noise + the fused iteration, replayed from a captured CUDA graph after two eager steps."""
         st, hp, n = self.state, self.hp, self.noise
-        if self._tokens is None or self._tokens.data_ptr() != tokens.data_ptr():
-            self._tokens = tokens
-            self._inp = _inputs(tokens, n['eps'], n['c'], n['word_drop'], n['out_keep'], self.p_out)
-        s = stream_ptr()
-        check(self.lib.cpg_fill_step_noise_overlapped(self.ctx, s, self.seed, int(it), self.B, self.L, self.p_word,
-                                                      self.p_out, *self._noise_args), 'cpg_fill_step_noise_overlapped')
+        if self._nb is None:
+            nb = StepNoiseBuffers()
+            nb.eps, nb.c, nb.word_drop, nb.out_keep = ptr(n['eps']), ptr(n['c']), ptr(n['word_drop']), ptr(n['out_keep'])
+            nb.z_prior_full, nb.z_prior_rf = ptr(n.get('z_prior_full')), ptr(n['z_prior_rf'])
+            nb.rf_w, nb.rf_b = ptr(n['rf_w']), ptr(n['rf_b'])
+            self._nb = nb
         st.step += 1
         hp.adam_step = st.step
         hp.beta = float(beta)
         p, g, m, v, sc = self._bufs
-        check(self.lib.cpg_wae_train_step(self.ctx, s, p, g, m, v, st.n_vocab, self.B, self.L, byref(self._inp),
-                                          byref(self.nz), byref(hp), sc, self._null, self._null, self._null, self._null),
-              'cpg_wae_train_step')
+        check(self.lib.cpg_wae_train_step_philox(self.ctx, stream_ptr(), p, g, m, v, st.n_vocab, self.B, self.L,
+                                                 ptr(tokens, torch.int64, allow_none=False), byref(self._nb), byref(hp), self.seed,
+                                                 int(it), self.p_word, self.p_out, sc), 'cpg_wae_train_step_philox')
         return self.scalars

@@ -43,8 +43,13 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
 __global__ void __launch_bounds__(NORM_THREADS)
 k_clip_adam(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             int64_t n, int64_t dup_off, int64_t dup_n, const float* __restrict__ part, int nparts, float max_norm,
-            float* __restrict__ norm_out, float* __restrict__ coef_out, AdamHyper h) {
+            float* __restrict__ norm_out, float* __restrict__ coef_out, AdamHyper h, const StepDyn* __restrict__ dyn) {
     __shared__ float coef_s;
+    if (dyn != nullptr) {
+        h.single = AdamStep{dyn->step_size[0], dyn->bc2_sqrt[0]};
+        h.dup_first = AdamStep{dyn->step_size[1], dyn->bc2_sqrt[1]};
+        h.dup_second = AdamStep{dyn->step_size[2], dyn->bc2_sqrt[2]};
+    }
     if (threadIdx.x < 32) {
         double s = 0.0;
         for (int i = threadIdx.x; i < nparts; i += 32) s += (double)part[i];
@@ -90,7 +95,7 @@ void launch_clip_adam_fused(cudaStream_t s, float* p, float* g, float* m, float*
     int parts = adam_norm_parts(n, sm_count);
     CPG_LAUNCH(k_sumsq_partial, parts, NORM_THREADS, 0, s, g, n, dup_off, dup_n, part);
     CPG_LAUNCH(k_clip_adam, parts, NORM_THREADS, 0, s, p, g, m, v, n, dup_off, dup_n, part, parts, max_norm, norm_out,
-               coef_out, h);
+               coef_out, h, g_dyn);
 }
 
 }  // namespace cpg

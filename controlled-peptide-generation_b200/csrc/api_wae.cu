@@ -3,6 +3,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string>
+#include <vector>
+#include <stdio.h>
 #include "ctx.h"
 
 namespace cpg {
@@ -438,6 +440,51 @@ static AdamHyper adam_hyper(const cpg_train_hparams* hp) {
     return h;
 }
 
+// ------------------------------------------------------------------------------- captured iteration
+const StepDyn* g_dyn = nullptr;
+int g_opt_graph = 1;                  // 1: cpg_wae_train_step_philox replays a captured CUDA graph of the iteration
+__global__ void k_set_dyn(StepDyn v, StepDyn* __restrict__ dst) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v;
+}
+
+static StepDyn make_dyn(const cpg_train_hparams* hp, uint32_t noise_step) {
+    const AdamHyper h = adam_hyper(hp);
+    StepDyn d;
+    d.beta = hp->beta;
+    d.step_size[0] = h.single.step_size; d.bc2_sqrt[0] = h.single.bc2_sqrt;
+    d.step_size[1] = h.dup_first.step_size; d.bc2_sqrt[1] = h.dup_first.bc2_sqrt;
+    d.step_size[2] = h.dup_second.step_size; d.bc2_sqrt[2] = h.dup_second.bc2_sqrt;
+    d.noise_step = noise_step;
+    return d;
+}
+
+#ifndef CPG_EMU
+struct StepGraph {
+    std::string key;
+    int seen = 0;                     // eager runs of this key so far (the first one sizes every workspace)
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t dyn_node = nullptr;
+    long long launches = 0;           // kernels inside the graph (for cpg_launch_count)
+    long long last_use = 0;
+};
+constexpr int MAX_GRAPHS = 8;
+static StepGraph g_graphs[MAX_GRAPHS];
+static long long g_graph_clock = 0;
+
+static StepGraph* find_graph(const std::string& key) {
+    StepGraph* lru = &g_graphs[0];
+    for (auto& g : g_graphs) {
+        if (g.key == key) { g.last_use = ++g_graph_clock; return &g; }
+        if (g.last_use < lru->last_use) lru = &g;
+    }
+    if (lru->exec) { cudaGraphExecDestroy(lru->exec); }
+    *lru = StepGraph();
+    lru->key = key;
+    lru->last_use = ++g_graph_clock;
+    return lru;
+}
+#endif
+
 }  // namespace cpg
 
 using namespace cpg;
@@ -472,9 +519,9 @@ int cpg_create(cpg_ctx** out, int device) {
     g_sm_count = c->sm_count;
 #endif
     void* p = nullptr;
-    if (dev_alloc(&p, 64) != 0) { set_error("cpg_create: allocation failed"); delete c; return CPG_ENOMEM; }
-    c->ints = (int*)p;
-    dev_memset(c->ints, 0, 64, nullptr);
+    if (dev_alloc(&p, 256) != 0) { set_error("cpg_create: allocation failed"); delete c; return CPG_ENOMEM; }
+    c->ints = (int*)p;                         // [0..15] ints, [32..] StepDyn of the captured iteration
+    dev_memset(c->ints, 0, 256, nullptr);
     dev_sync(nullptr);
     *out = c;
     return CPG_OK;
@@ -747,6 +794,99 @@ int cpg_wae_train_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* gr
     if ((rc = cpg_wae_step_phase2(ctx, stream, params, grads, V, B, L, in, nz, &h, cpl, scalars, logits))) return rc;
     float* gn = scalars ? scalars + SC_GRAD_NORM : nullptr;
     return cpg_clip_adam_step(ctx, stream, params, grads, m, v, V, &h, gn);
+}
+
+// Philox noise + the whole iteration as ONE call; from the third call with the same buffers and settings on, a replay
+// of a captured CUDA graph (the ~50 kernels, memsets and the fork / join of the side stream) whose per-step scalars
+// (beta, Adam bias corrections, noise counter) are refreshed by one kernel-node parameter update.
+int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* m, float* v, int V, int B,
+                              int L, const int64_t* tokens, const cpg_step_noise_buffers* nb, const cpg_train_hparams* hp,
+                              uint64_t seed, uint32_t noise_step, float p_word, float p_out, float* scalars) {
+    if (!ctx || !hp || !nb || !tokens || !params || !grads || !m || !v) { set_error("cpg_wae_train_step_philox: null argument"); return CPG_EINVAL; }
+    if (!nb->eps || !nb->c || !nb->word_drop || !nb->out_keep || !nb->z_prior_rf || !nb->rf_w || !nb->rf_b) {
+        set_error("cpg_wae_train_step_philox: noise buffers missing"); return CPG_EINVAL;
+    }
+    cpg_wae_inputs in;
+    in.tokens = tokens; in.eps = nb->eps; in.c = nb->c; in.word_drop = nb->word_drop; in.out_keep = nb->out_keep;
+    in.p_out_dropout = p_out;
+    cpg_loss_noise nz;
+    nz.z_prior_full = nb->z_prior_full; nz.z_prior_rf = nb->z_prior_rf; nz.rf_w = nb->rf_w; nz.rf_b = nb->rf_b;
+    auto body = [&]() -> int {
+        int rc = cpg_fill_step_noise_overlapped(ctx, stream, seed, noise_step, B, L, p_word, p_out, nb->eps, nb->c, nb->word_drop,
+                                                nb->out_keep, nb->z_prior_full, nb->z_prior_rf);
+        if (rc) return rc;
+        return cpg_wae_train_step(ctx, stream, params, grads, m, v, V, B, L, &in, &nz, hp, scalars, nullptr, nullptr, nullptr, nullptr);
+    };
+#ifdef CPG_EMU
+    return body();
+#else
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!g_opt_graph || g_profile_on) return body();
+    char kb[512];
+    snprintf(kb, sizeof(kb), "%p|%p|%p|%p|%p|%p|%d|%d|%d|%p|%p|%p|%p|%p|%p|%p|%p|%p|%g|%g|%g|%g|%g|%g|%g|%d|%g|%d|%d|%d|%llu|%g|%g|%d|%d|%d|%d|%d",
+             (void*)ctx, (void*)s, (void*)params, (void*)grads, (void*)m, (void*)v, V, B, L, (const void*)tokens, (void*)nb->eps, (void*)nb->c,
+             (void*)nb->word_drop, (void*)nb->out_keep, (void*)nb->z_prior_full, (void*)nb->z_prior_rf, (void*)nb->rf_w, (void*)nb->rf_b,
+             hp->lr, hp->beta1, hp->beta2, hp->adam_eps, hp->clip_norm, hp->lambda_logvar_l1, hp->lambda_logvar_kl, hp->z_regu,
+             hp->mmd_sigma, hp->rf_dim, hp->compute_full_mmd, hp->beta != 0.f ? 1 : 0, (unsigned long long)seed, p_word, p_out,
+             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc);
+    StepGraph* g = find_graph(kb + std::string(scalars ? std::to_string((uintptr_t)scalars) : ""));
+    StepDyn* dyn_dev = reinterpret_cast<StepDyn*>(ctx->ints + 32);
+    const StepDyn dv = make_dyn(hp, noise_step);
+    if (g->exec == nullptr) {
+        if (g->seen < 1) { g->seen++; return body(); }          // first sight: eager (allocations, attribute set-up)
+        // capture
+        ctx->join_pending[0] = ctx->join_pending[1] = ctx->join_pending[2] = false;
+        const long long l0 = g_launch_count;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return body(); }
+        k_set_dyn<<<1, 32, 0, s>>>(dv, dyn_dev);
+        g_dyn = dyn_dev;
+        int rc = body();
+        g_dyn = nullptr;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        const long long captured = g_launch_count - l0 + 1;
+        g_launch_count = l0;
+        if (rc || ce != cudaSuccess || graph == nullptr) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            g->seen = -1000000;                                  // do not try again for this key
+            return rc ? rc : body();
+        }
+        size_t nn = 0;
+        cudaGraphGetNodes(graph, nullptr, &nn);
+        std::vector<cudaGraphNode_t> nodes(nn);
+        cudaGraphGetNodes(graph, nodes.data(), &nn);
+        for (auto nd : nodes) {
+            cudaGraphNodeType ty;
+            if (cudaGraphNodeGetType(nd, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+            cudaKernelNodeParams kp;
+            if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess && kp.func == (void*)k_set_dyn) { g->dyn_node = nd; break; }
+        }
+        cudaGraphExec_t ex = nullptr;
+        if (g->dyn_node == nullptr || cudaGraphInstantiate(&ex, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            cudaGraphDestroy(graph);
+            g->seen = -1000000;
+            return body();
+        }
+        cudaGraphDestroy(graph);
+        g->exec = ex;
+        g->launches = captured;
+    }
+    if (g->seen < 0) return body();
+    // replay: refresh the per-step scalars through the head node's arguments, then launch
+    StepDyn hv = dv;
+    void* kargs[2] = {&hv, &dyn_dev};
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = (void*)k_set_dyn; kp.gridDim = dim3(1); kp.blockDim = dim3(32); kp.sharedMemBytes = 0; kp.kernelParams = kargs; kp.extra = nullptr;
+    if (cudaGraphExecKernelNodeSetParams(g->exec, g->dyn_node, &kp) != cudaSuccess || cudaGraphLaunch(g->exec, s) != cudaSuccess) {
+        set_error(std::string("cpg_wae_train_step_philox: graph replay failed: ") + cudaGetErrorString(cudaGetLastError()));
+        return CPG_ECUDA;
+    }
+    g_launch_count += g->launches;
+    return CPG_OK;
+#endif
 }
 
 // ---- data-parallel helpers (cpg_b200/parallel.py) ----------------------------------------------------------

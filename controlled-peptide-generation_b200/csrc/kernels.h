@@ -60,6 +60,16 @@ struct GruSeq {            // one recurrence (a direction of the encoder, or the
     float* drow;           // [B][3*HP] sum over steps of (dr_pre,dz_pre,dn_pre), or null
 };
 
+// Per-step scalars that change between replays of a captured iteration (CUDA graph): they live in device memory and one
+// tiny kernel at the head of the graph refreshes them; g_dyn is non-null while such an iteration is being enqueued, and
+// the kernels that take these values by argument then read them from there instead.
+struct StepDyn {
+    float beta;
+    float step_size[3], bc2_sqrt[3];      // Adam: ordinary tensors, first / second update of the duplicated embedding
+    uint32_t noise_step;
+};
+extern const StepDyn* g_dyn;
+
 // per-iteration noise (noise.cu); part bit 0 = eps / c / word dropout, bit 1 = z_prior x2 / out-dropout mask
 struct StepNoiseArgs {
     uint64_t seed; uint32_t step;
@@ -92,6 +102,7 @@ int launch_gru_bwd_dec_fused(cudaStream_t s, const GruSeq& seq, const uint8_t* t
                              float* part_t);
 extern int g_opt_gru_tc;
 extern int g_opt_bptt_fused;
+extern int g_opt_graph;
 extern int g_opt_side_stream;
 
 // C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C ; generic strides (elements):

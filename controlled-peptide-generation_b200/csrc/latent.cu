@@ -102,8 +102,9 @@ __global__ void k_latent_bwd(LatentBwdArgs a) {
     const float m = a.mu[i], lv = a.logvar[i];
     const float e = expf(lv);
     const float invB = 1.0f / (float)a.B_global;
-    float dmu = dz + a.w_kl * m * invB;
-    float dlv = (a.w_kl + a.w_klsm) * 0.5f * (e - 1.0f) * invB;
+    const float w_kl = (a.dyn != nullptr && a.w_kl != 0.f) ? a.dyn->beta : a.w_kl;
+    float dmu = dz + w_kl * m * invB;
+    float dlv = (w_kl + a.w_klsm) * 0.5f * (e - 1.0f) * invB;
     dlv += a.w_l1 * (lv > 0.f ? 1.f : (lv < 0.f ? -1.f : 0.f)) * invB;
     if (a.eps != nullptr) dlv += dz * a.eps[i] * 0.5f * expf(lv / 2);
     if (a.dmu_ext != nullptr) dmu += a.dmu_ext[i];
@@ -111,7 +112,9 @@ __global__ void k_latent_bwd(LatentBwdArgs a) {
     a.dmu[i] = dmu;
     a.dlv[i] = dlv;
 }
-void launch_latent_bwd(cudaStream_t s, const LatentBwdArgs& a) {
+void launch_latent_bwd(cudaStream_t s, const LatentBwdArgs& a_in) {
+    LatentBwdArgs a = a_in;
+    a.dyn = g_dyn;
     CPG_LAUNCH(k_latent_bwd, ceil_div(a.B * ZD, 256), 256, 0, s, a);
 }
 
@@ -146,8 +149,10 @@ void launch_rf_colsum(cudaStream_t s, const float* pre, const float* rf_b, int B
 // loss = sum_r (mean1 - mean2)^2 from the GLOBAL feature sums; also
 // coef[r] = w * 2 (mean1 - mean2) * sqrt(2/R) / (B_global * sigma) for the backward pass.
 __global__ void k_rf_loss(const float* __restrict__ sum1, const float* __restrict__ sum2, int R, int B_global,
-                          float sigma, float w, float* __restrict__ coef, float* __restrict__ loss_out) {
+                          float sigma, float w, float* __restrict__ coef, float* __restrict__ loss_out,
+                          const StepDyn* __restrict__ dyn) {
     __shared__ float red[32];
+    if (dyn != nullptr && w != 0.f) w = dyn->beta;
     const float invB = 1.0f / (float)B_global;
     const float scale = sqrtf(2.0f / (float)R);
     float acc = 0.f;
@@ -167,7 +172,7 @@ __global__ void k_rf_loss(const float* __restrict__ sum1, const float* __restric
 }
 void launch_rf_loss(cudaStream_t s, const float* sum1, const float* sum2, int R, int B_global, float sigma, float w,
                     float* coef, float* loss_out) {
-    CPG_LAUNCH(k_rf_loss, 1, 256, 0, s, sum1, sum2, R, B_global, sigma, w, coef, loss_out);
+    CPG_LAUNCH(k_rf_loss, 1, 256, 0, s, sum1, sum2, R, B_global, sigma, w, coef, loss_out, g_dyn);
 }
 // G[b][r] = coef[r] * (-sin(pre/sigma + b)) in place; then dz = G @ rf_w^T (gemm)
 __global__ void k_rf_grad_prep(float* __restrict__ pre, const float* __restrict__ rf_b,
@@ -318,7 +323,9 @@ void launch_mmd_full_simt(cudaStream_t s, const float* z, const float* zp, int N
 // shared memory.  A differentiated full-kernel MMD is outside the reference's default configuration.
 constexpr int MG_ROWS = 16, MG_LPR = 16, MG_COLS = 32, MG_D = 7;       // 7 * 16 >= 100
 __global__ void __launch_bounds__(MG_ROWS * MG_LPR)
-k_mmd_full_grad(const float* __restrict__ z, const float* __restrict__ y, int N, float sigma, float w, float* __restrict__ dz) {
+k_mmd_full_grad(const float* __restrict__ z, const float* __restrict__ y, int N, float sigma, float w, float* __restrict__ dz,
+                const StepDyn* __restrict__ dyn) {
+    if (dyn != nullptr && w != 0.f) w = dyn->beta;
     __shared__ float xs[MG_COLS][ZD + 1];
     const int r = threadIdx.x / MG_LPR, l = threadIdx.x % MG_LPR;
     const int i = blockIdx.x * MG_ROWS + r;
@@ -366,7 +373,7 @@ k_mmd_full_grad(const float* __restrict__ z, const float* __restrict__ y, int N,
     }
 }
 void launch_mmd_full_grad(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float w, float* dz) {
-    CPG_LAUNCH(k_mmd_full_grad, ceil_div(N, MG_ROWS), MG_ROWS * MG_LPR, 0, s, z, zp, N, sigma, w, dz);
+    CPG_LAUNCH(k_mmd_full_grad, ceil_div(N, MG_ROWS), MG_ROWS * MG_LPR, 0, s, z, zp, N, sigma, w, dz, g_dyn);
 }
 
 int g_opt_mmd_tc = 1;
@@ -390,6 +397,7 @@ int launch_mmd_full(cudaStream_t s, const float* z, const float* zp, int N, floa
 // total loss and logging scalars (train_vae.py:31-37,44-53) from the reduced sums (single-rank view)
 __global__ void k_compose_scalars(ComposeArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (a.dyn != nullptr) a.beta = a.dyn->beta;
     const float invB = 1.0f / (float)a.B_global;
     float ntok = *a.ntok;
     float recon = ntok > 0.f ? *a.nll_sum / ntok : 0.f;
@@ -411,7 +419,11 @@ __global__ void k_compose_scalars(ComposeArgs a) {
     o[SC_NTOK] = ntok;
     o[SC_NLL_SUM] = *a.nll_sum;
 }
-void launch_compose_scalars(cudaStream_t s, const ComposeArgs& a) { CPG_LAUNCH(k_compose_scalars, 1, 32, 0, s, a); }
+void launch_compose_scalars(cudaStream_t s, const ComposeArgs& a_in) {
+    ComposeArgs a = a_in;
+    a.dyn = g_dyn;
+    CPG_LAUNCH(k_compose_scalars, 1, 32, 0, s, a);
+}
 
 // Data-parallel bookkeeping: the local NLL sum rides behind the flat gradient through the gradient all-reduce
 // (no third collective); afterwards the logged reconstruction loss / total loss are re-based on the global sum.

@@ -1,5 +1,6 @@
 #pragma once
 #include "cpg_common.cuh"
+#include "kernels.h"
 
 namespace cpg {
 
@@ -21,6 +22,7 @@ struct LatentBwdArgs {
     float w_l1;             // lambda_logvar_L1
     int B, B_global;
     float* dmu; float* dlv; // [B][100] out
+    const StepDyn* dyn;     // set by the launcher (see kernels.h)
 };
 
 struct ComposeArgs {
@@ -28,6 +30,7 @@ struct ComposeArgs {
     float beta, lambda_l1, lambda_kl;
     int z_regu, B_global;
     float* out;
+    const StepDyn* dyn;     // set by the launcher
 };
 
 void launch_reparam(cudaStream_t s, const float* mu, const float* logvar, const float* eps, const float* c, int B,

@@ -22,12 +22,12 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 // stream ids: 16*step + {0: normals, 1: c, 2: word dropout, 3: out dropout}
 // part: bit 0 = what the forward needs first (eps, c, word dropout), bit 1 = what is only needed later (z_prior x2,
 // out-dropout mask -- the bulk of the work)
-__global__ void k_step_noise(StepNoiseArgs a, int part) {
+__global__ void k_step_noise(StepNoiseArgs a, int part, const StepDyn* __restrict__ dyn) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_lat = (int64_t)a.B * ZD;
     const int64_t n_tok = (int64_t)a.B * a.L;
     const int64_t n_out4 = ((int64_t)a.B * a.L * DEC_H + 3) / 4;
-    const uint32_t base = a.step * 16u;
+    const uint32_t base = (dyn != nullptr ? dyn->noise_step : a.step) * 16u;
     uint32_t r[4];
     if (i < n_lat) {
         Philox::gen(a.seed, (uint64_t)i, base + 0, r);
@@ -82,7 +82,7 @@ void launch_step_noise(cudaStream_t s, const StepNoiseArgs& a, int part) {
     int64_t n = (int64_t)a.B * ZD;                                         // normals (both parts)
     if (part & 1) n = std::max<int64_t>(n, (int64_t)a.B * a.L);
     if (part & 2) n = std::max<int64_t>(n, ((int64_t)a.B * a.L * DEC_H + 3) / 4);
-    CPG_LAUNCH(k_step_noise, (unsigned)((n + 255) / 256), 256, 0, s, a, part);
+    CPG_LAUNCH(k_step_noise, (unsigned)((n + 255) / 256), 256, 0, s, a, part, g_dyn);
 }
 
 }  // namespace cpg

@@ -145,6 +145,20 @@ int cpg_wae_train_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* gr
                        const cpg_train_hparams* hp, float* scalars, float* mu, float* logvar, float* z,
                        float* logits);
 
+/* The iteration with its Philox noise as ONE call (what train_vae's default loop issues per step): the per-step noise
+ * buffers are regenerated from (seed, noise_step) and the step of cpg_wae_train_step runs on them.  From the third call
+ * with the same buffers / shapes / settings on, the whole step is a replay of a captured CUDA graph (option "cuda_graph");
+ * only hp->beta, hp->adam_step and noise_step may change between replays without a re-capture. */
+typedef struct {
+    float* eps; float* c; uint8_t* word_drop; uint8_t* out_keep;      /* per-step noise, regenerated every call   */
+    float* z_prior_full; float* z_prior_rf;                            /* (z_prior_full may be NULL)               */
+    const float* rf_w; const float* rf_b;                              /* cached random features (losses.py:75-76) */
+} cpg_step_noise_buffers;
+int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* adam_m, float* adam_v,
+                              int n_vocab, int B, int L, const int64_t* tokens, const cpg_step_noise_buffers* noise,
+                              const cpg_train_hparams* hp, uint64_t seed, uint32_t noise_step, float p_word, float p_out,
+                              float* scalars);
+
 /* The same iteration split at its data-parallel exchange points:
  *   phase1: forward through the decoder GRU + local loss statistics.  Writes `coupled`
  *           (device float[cpg_coupled_count(rf_dim)]) = [n_tok, nll placeholder, 5 latent sums,
@@ -333,6 +347,7 @@ int cpg_logreg_stats_len(void);
  *   "dec_out_tensor_core" 1 (default) tcgen05 decoder-output layer when B*L >= 8192, 2 always, 0 never
  *   "bptt_fused"          1 (default) on the tcgen05 path the BPTT kernels also contract dW_hh and the token-table gradient
  *                         (the gate-gradient planes never reach HBM), 0 = separate tf32 weight-gradient kernels
+ *   "cuda_graph"          1 (default) cpg_wae_train_step_philox replays a captured CUDA graph of the iteration, 0 = eager launches
  *   "side_stream"         1 (default) loss / weight-gradient kernels overlap the recurrences on an internal stream
  *                         (event fork/join inside each call; results identical), 0 everything on the caller's stream */
 int cpg_set_option(const char* name, int value);
