@@ -68,95 +68,144 @@ k_score_accept(const float* __restrict__ z, const double* __restrict__ u, int64_
     accept[i] = u[i] < accum ? 1 : 0;
 }
 
-// ---- perf mode: everything drawn in-kernel (Philox), one warp per draw ------------------------
+// ---- perf mode: everything drawn in-kernel (Philox), ONE LANE PER DRAW ---------------------------------------
+// A thread owns a draw from the component choice to the accept test: 1 + 25 Philox4x32-10 calls (stream 0: component
+// and acceptance uniforms; stream 1 + q: the four normals of dimensions 4q .. 4q+3), Box-Muller, z = mean_k + sd_k n,
+// the classifier dots accumulated in registers.  No shuffles, no warp reductions, no idle lanes (the first version
+// spread one draw over a warp: 32 Philox calls for 100 normals and a reduction tree per classifier -- 3x the
+// instructions).  mean / sd of all components sit in shared memory as interleaved (mean, sd) pairs with an odd row
+// stride (lanes read different components: rows land in different banks); classifier coefficients are broadcast reads.
+// z rows leave through a per-warp staging tile in shared memory, 20 dimensions at a time: the warp then writes 80-byte
+// row pieces with consecutive lanes on consecutive 16 bytes (lane-per-row 16-byte stores 400 bytes apart cost twice the
+// L2 transactions: measured 2.8 -> see DESIGN.md); scores and the mask are lane-contiguous.
 struct GmmSpec {
     const float* mean;      // [K][D] fp32
     const float* sd;        // [K][D] sqrt(cov), fp32
     const float* cdf;       // [K] cumulative weights (last = 1)
     int K;
 };
-constexpr int CS_WARPS = 8;
-__global__ void __launch_bounds__(CS_WARPS * 32)
+constexpr int CS_THREADS = 256;
+constexpr int CS_STRIDE = ZD + 1;                 // float2 per row, odd
+constexpr int CS_KMAX_SMEM = 128;                 // components whose tables fit in shared memory
+constexpr int CS_ZCH = 20;                        // dimensions per staged piece of a z row (80 bytes)
+template <bool TAB_SMEM>
+__global__ void __launch_bounds__(CS_THREADS)
 k_class_sample(GmmSpec g, ClfSpec cs, uint64_t seed, int64_t offset, const int64_t* __restrict__ gid_list, int64_t n,
                float* __restrict__ z_out, double* __restrict__ probs, double* __restrict__ accum_out,
                uint8_t* __restrict__ accept, int* __restrict__ comp_out, unsigned long long* __restrict__ n_accepted) {
-    __shared__ float coef_s[MAX_CLF][ZD + 28];
-    __shared__ float cdf_s[1024];
-    for (int i = threadIdx.x; i < cs.n_clf * ZD; i += blockDim.x) coef_s[i / ZD][i % ZD] = (float)cs.coef[i / ZD][i % ZD];
+    CPG_DYN_SMEM(float, dsm);
+    float2* tab_s = reinterpret_cast<float2*>(dsm);                       // [K][CS_STRIDE] (mean, sd)   (TAB_SMEM)
+    float* coef_s = dsm + (TAB_SMEM ? ((2 * (size_t)g.K * CS_STRIDE + 3) & ~(size_t)3) : 0);  // [MAX_CLF][ZD]
+    float* cdf_s = coef_s + MAX_CLF * ZD;                                 // [K]
+    float* stage = cdf_s + ((g.K + 3) & ~3) + (threadIdx.x >> 5) * (32 * CS_ZCH);   // this warp's [32 draws][CS_ZCH] tile
+    const int lane = threadIdx.x & 31;
+    __shared__ unsigned long long acc_s;
+    if (TAB_SMEM)
+        for (int i = threadIdx.x; i < g.K * ZD; i += blockDim.x)
+            tab_s[(i / ZD) * CS_STRIDE + (i % ZD)] = make_float2(g.mean[i], g.sd[i]);
+    for (int i = threadIdx.x; i < MAX_CLF * ZD; i += blockDim.x) coef_s[i] = i < cs.n_clf * ZD ? (float)cs.coef[i / ZD][i % ZD] : 0.f;
     for (int i = threadIdx.x; i < g.K; i += blockDim.x) cdf_s[i] = g.cdf[i];
+    if (threadIdx.x == 0) acc_s = 0ull;
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long local_acc = 0;
-    // A warp takes 32 consecutive draws at a time: lane l first does the per-draw scalar work (Philox stream 0 ->
-    // component by binary search + acceptance uniform) of draw base + l, then the warp walks the 32 draws with
-    // lanes over the 100 dimensions and the scalars broadcast by shuffle -- the scalar part used to be recomputed by
-    // all 32 lanes of every draw (a third of the kernel's instructions).  Same streams, same values as before.
-    for (int64_t base = ((int64_t)blockIdx.x * CS_WARPS + warp) * 32; base < n; base += (int64_t)gridDim.x * CS_WARPS * 32) {
-        int k_mine = 0;
-        double ua_mine = 2.0;
-        if (base + lane < n) {
-            uint32_t r0[4];
-            // draw number: consecutive from `offset`, or (re-generation of selected draws) taken from a list
-            const uint64_t gid0 = gid_list != nullptr ? (uint64_t)gid_list[base + lane] : (uint64_t)(offset + base + lane);
-            Philox::gen(seed, gid0, 0u, r0);
-            const float uc = (float)(r0[0] >> 8) * (1.0f / 16777216.0f);
-            ua_mine = u64_to_unit(r0[2], r0[3]);
-            int lo = 0, hi = g.K - 1;                            // first k with cdf[k] > uc
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf_s[mid] > uc) hi = mid; else lo = mid + 1; }
-            k_mine = lo;
-        }
-        const int ndraw = (int)min((int64_t)32, n - base);
-        for (int jd = 0; jd < ndraw; ++jd) {
-        const int64_t i = base + jd;
-        const uint64_t gid = gid_list != nullptr ? (uint64_t)gid_list[i] : (uint64_t)(offset + i);
-        const int k = __shfl_sync(0xffffffffu, k_mine, jd);
-        const double ua = __shfl_sync(0xffffffffu, ua_mine, jd);
+    // whole warps iterate together (the staged z write-out is warp-collective); lanes past n idle through the math
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + lane;
+        const bool live = i < n;
+        // draw number: consecutive from `offset`, or (re-generation of selected draws) taken from a list
+        const uint64_t gid = !live ? 0ull : (gid_list != nullptr ? (uint64_t)gid_list[i] : (uint64_t)(offset + i));
         uint32_t r[4];
-        Philox::gen(seed, gid, 1u + (uint32_t)lane, r);
-        float nrm[4];
-        {
-            float u1 = u32_to_unit_open(r[0]), u2 = u32_to_unit_open(r[1]);
-            float rad = sqrtf(-2.0f * __logf(u1)); float sn, cn; __sincosf(6.283185307179586f * u2, &sn, &cn);
-            nrm[0] = rad * cn; nrm[1] = rad * sn;
-            u1 = u32_to_unit_open(r[2]); u2 = u32_to_unit_open(r[3]);
-            rad = sqrtf(-2.0f * __logf(u1)); __sincosf(6.283185307179586f * u2, &sn, &cn);
-            nrm[2] = rad * cn; nrm[3] = rad * sn;
-        }
-        float zv[4];
+        Philox::gen(seed, gid, 0u, r);
+        const float uc = (float)(r[0] >> 8) * (1.0f / 16777216.0f);
+        const double ua = u64_to_unit(r[2], r[3]);
+        int lo = 0, hi = g.K - 1;                                          // first k with cdf[k] > uc
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf_s[mid] > uc) hi = mid; else lo = mid + 1; }
+        const int k = lo;
         float dots[MAX_CLF] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 5
+        for (int q = 0; q < ZD / 4; ++q) {
+            Philox::gen(seed, gid, 1u + (uint32_t)q, r);
+            float nrm[4];
+            {
+                float u1 = u32_to_unit_open(r[0]), u2 = u32_to_unit_open(r[1]);
+                float rad = sqrtf(-2.0f * __logf(u1)); float sn, cn; __sincosf(6.283185307179586f * u2, &sn, &cn);
+                nrm[0] = rad * cn; nrm[1] = rad * sn;
+                u1 = u32_to_unit_open(r[2]); u2 = u32_to_unit_open(r[3]);
+                rad = sqrtf(-2.0f * __logf(u1)); __sincosf(6.283185307179586f * u2, &sn, &cn);
+                nrm[2] = rad * cn; nrm[3] = rad * sn;
+            }
+            float zv[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            int d = lane + 32 * q;
-            zv[q] = 0.f;
-            if (d < ZD) {
-                zv[q] = fmaf(nrm[q], __ldg(g.sd + (size_t)k * ZD + d), __ldg(g.mean + (size_t)k * ZD + d));
-                if (z_out != nullptr) z_out[(size_t)i * ZD + d] = zv[q];
+            for (int e = 0; e < 4; ++e) {
+                const int d = 4 * q + e;
+                float2 ms;
+                if (TAB_SMEM) ms = tab_s[k * CS_STRIDE + d];
+                else ms = make_float2(__ldg(g.mean + (size_t)k * ZD + d), __ldg(g.sd + (size_t)k * ZD + d));
+                zv[e] = fmaf(nrm[e], ms.y, ms.x);
 #pragma unroll
-                for (int a = 0; a < MAX_CLF; ++a)
-                    if (a < cs.n_clf) dots[a] = fmaf(zv[q], coef_s[a][d], dots[a]);
+                for (int a = 0; a < MAX_CLF; ++a) dots[a] = fmaf(zv[e], coef_s[a * ZD + d], dots[a]);
+            }
+            if (z_out != nullptr) {
+                constexpr int QPC = CS_ZCH / 4;                               // quads per staged piece
+                *reinterpret_cast<float4*>(stage + lane * CS_ZCH + (q % QPC) * 4) = make_float4(zv[0], zv[1], zv[2], zv[3]);
+                if (q % QPC == QPC - 1) {
+                    __syncwarp();
+                    const int d0 = (q / QPC) * CS_ZCH;
+#pragma unroll
+                    for (int j = 0; j < QPC; ++j) {                           // 32 * QPC float4 of the tile, lane-linear
+                        const int idx = j * 32 + lane, row = idx / QPC, pc = idx % QPC;
+                        if (i0 + row < n)
+                            *reinterpret_cast<float4*>(z_out + (size_t)(i0 + row) * ZD + d0 + pc * 4) =
+                                *reinterpret_cast<const float4*>(stage + row * CS_ZCH + pc * 4);
+                    }
+                    __syncwarp();
+                }
             }
         }
+        if (!live) continue;
         float accf = 1.0f;
 #pragma unroll
         for (int a = 0; a < MAX_CLF; ++a) {
             if (a < cs.n_clf) {
-                float s = warp_sum(dots[a]) + (float)cs.intercept[a];
-                float p1 = expit_f(s);
-                float p = cs.target_col[a] == 1 ? p1 : 1.0f - p1;
+                const float sc = dots[a] + (float)cs.intercept[a];
+                const float p1 = expit_f(sc);
+                const float p = cs.target_col[a] == 1 ? p1 : 1.0f - p1;
                 accf *= p;
-                if (probs != nullptr && lane == 0) probs[(size_t)a * n + i] = (double)p;
+                if (probs != nullptr) probs[(size_t)a * n + i] = (double)p;
             }
         }
-        if (lane == 0) {
-            const int acc = ua < (double)accf ? 1 : 0;
-            if (accept != nullptr) accept[i] = (uint8_t)acc;
-            if (accum_out != nullptr) accum_out[i] = (double)accf;
-            if (comp_out != nullptr) comp_out[i] = k;
-            local_acc += acc;
-        }
-        }   // draws of this group of 32
+        const int acc = ua < (double)accf ? 1 : 0;
+        if (accept != nullptr) accept[i] = (uint8_t)acc;
+        if (accum_out != nullptr) accum_out[i] = (double)accf;
+        if (comp_out != nullptr) comp_out[i] = k;
+        local_acc += acc;
     }
-    if (n_accepted != nullptr && lane == 0 && local_acc) atomicAdd(n_accepted, local_acc);
+    if (n_accepted != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local_acc += __shfl_xor_sync(0xffffffffu, local_acc, o);
+        if ((threadIdx.x & 31) == 0 && local_acc) atomicAdd(&acc_s, local_acc);
+        __syncthreads();
+        if (threadIdx.x == 0 && acc_s) atomicAdd(n_accepted, acc_s);
+    }
+}
+
+static int launch_class_sample(cpg_ctx* ctx, cudaStream_t s, const char* label, const GmmSpec& g, const ClfSpec& cs, uint64_t seed,
+                               int64_t offset, const int64_t* gid_list, int64_t n, float* z_out, double* probs, double* accum,
+                               uint8_t* accept, int* comp_out, unsigned long long* n_accepted) {
+    const bool tab = g.K <= CS_KMAX_SMEM;
+    const size_t smem = ((tab ? ((2 * (size_t)g.K * CS_STRIDE + 3) & ~(size_t)3) : 0) + MAX_CLF * ZD + ((g.K + 3) & ~3) + (CS_THREADS / 32) * 32 * CS_ZCH) * sizeof(float);
+    const int64_t want = (n + CS_THREADS - 1) / CS_THREADS;
+    const int per_sm = tab ? 2 : 4;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * per_sm));
+    if (tab) {
+        auto kfn = k_class_sample<true>;
+        CPG_SET_MAX_SMEM(kfn, smem);
+        CPG_LAUNCH_NAMED(label, kfn, grid, CS_THREADS, smem, s, g, cs, seed, offset, gid_list, n, z_out, probs, accum, accept, comp_out, n_accepted);
+    } else {
+        auto kfn = k_class_sample<false>;
+        CPG_LAUNCH_NAMED(label, kfn, grid, CS_THREADS, smem, s, g, cs, seed, offset, gid_list, n, z_out, probs, accum, accept, comp_out, n_accepted);
+    }
+    return CPG_OK;
 }
 
 // ---- log densities (fp64) -----------------------------------------------------------------------
@@ -245,10 +294,7 @@ int cpg_class_sample(cpg_ctx* ctx, cpg_stream stream, const float* gmm_mean, con
     int rc = fill_clf(cs, n_clf, coef, intercept, target_col, f32);
     if (rc) return rc;
     GmmSpec g{gmm_mean, gmm_sd, gmm_cdf, K};
-    int64_t want = (n + CS_WARPS * 32 - 1) / (CS_WARPS * 32);
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * 8));
-    CPG_LAUNCH(k_class_sample, grid, CS_WARPS * 32, 0, (cudaStream_t)stream, g, cs, seed, offset, (const int64_t*)nullptr, n, z_out,
-               probs, accum, accept, comp_out, n_accepted);
+    launch_class_sample(ctx, (cudaStream_t)stream, "k_class_sample", g, cs, seed, offset, nullptr, n, z_out, probs, accum, accept, comp_out, n_accepted);
     return check_launch("cpg_class_sample");
 }
 
@@ -263,10 +309,7 @@ int cpg_class_regen(cpg_ctx* ctx, cpg_stream stream, const float* gmm_mean, cons
     int rc = fill_clf(cs, n_clf, coef, intercept, target_col, f32);
     if (rc) return rc;
     GmmSpec g{gmm_mean, gmm_sd, gmm_cdf, K};
-    int64_t want = (m + CS_WARPS * 32 - 1) / (CS_WARPS * 32);
-    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->sm_count * 8));
-    CPG_LAUNCH_NAMED("k_class_regen", k_class_sample, grid, CS_WARPS * 32, 0, (cudaStream_t)stream, g, cs, seed, (int64_t)0, draw_index, m,
-                     z_out, probs, accum, (uint8_t*)nullptr, (int*)nullptr, (unsigned long long*)nullptr);
+    launch_class_sample(ctx, (cudaStream_t)stream, "k_class_regen", g, cs, seed, 0, draw_index, m, z_out, probs, accum, nullptr, nullptr, nullptr);
     return check_launch("cpg_class_regen");
 }
 
