@@ -119,6 +119,7 @@ def _signatures(L):
         'cpg_set_option': (I, [c_char_p, I]),
         'cpg_profile_enable': (I, [I]),
         'cpg_profile_read': (I, [P, I, P, P, I]),
+        'cpg_profile_timeline': (I, [P, I, P, P, I]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -232,6 +233,17 @@ def profile_read(cap=128):
         label = names.raw[i * stride:(i + 1) * stride].split(b'\0', 1)[0].decode()
         out.append((label, float(ms[i]), int(cnt[i])))
     return out
+
+
+def profile_timeline(cap=4096):
+    """-> list of (kernel label, start ms, duration ms) of the launches covered by the last profile_read()."""
+    stride = 64
+    names = ctypes.create_string_buffer(cap * stride)
+    t0 = (c_float * cap)()
+    dt = (c_float * cap)()
+    n = lib().cpg_profile_timeline(ctypes.cast(names, c_void_p), stride, ctypes.cast(t0, c_void_p),
+                                   ctypes.cast(dt, c_void_p), cap)
+    return [(names.raw[i * stride:(i + 1) * stride].split(b'\0', 1)[0].decode(), float(t0[i]), float(dt[i])) for i in range(n)]
 
 
 def set_option(name, value):

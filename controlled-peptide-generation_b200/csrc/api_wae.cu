@@ -79,6 +79,11 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
     w.d.bhn_dec = a.take<float>(DEC_HP);
     w.d.fc_w = a.take<float>((size_t)VMAX * DEC_HP);
     w.d.fc_b = a.take<float>(VMAX);
+#ifndef CPG_EMU
+    w.d.lat_tiles = a.take<unsigned char>(LT_TILES_BYTES);
+#else
+    w.d.lat_tiles = nullptr;
+#endif
     // tokens
     w.tok = a.take<uint8_t>(BL); w.tokd = a.take<uint8_t>(BL); w.tgt = a.take<uint8_t>(BL);
     // encoder
@@ -187,42 +192,70 @@ static int check_dims(int V, int B, int L) {
     return CPG_OK;
 }
 
-// -------------------------------------------------------------------------------- side stream
-// g_opt_side_stream: 1 = overlap the loss kernels with the decoder path (default), 0 = everything on one stream
+// -------------------------------------------------------------------------------- internal streams
+// g_opt_side_stream: 1 = the loss / reduction / weight-gradient kernels overlap the recurrences on two internal streams
+// (default), 0 = everything on the caller's stream.  Lanes: m = the caller's stream (the dependent chain of the
+// iteration), s = loss statistics, RF-MMD, full-kernel MMD, t = derived weight forms, ordered reductions of partials,
+// weight-gradient products.  A dependency is an event recorded on the producer's lane (`mark`) and waited for on the
+// consumer's (`wait_mark`); events come from a rotating pool (a wait binds to the record made before it was issued, so
+// an event may be re-recorded once all waits on the earlier record have been ISSUED: far fewer than NEV per call).
 int g_opt_side_stream = 1;
+typedef void* Mark;
+struct Lanes { cudaStream_t m, s, t; bool on; };
 #ifndef CPG_EMU
+constexpr int NEV = 32;
 static bool side_ready(cpg_ctx* ctx) {
     if (!g_opt_side_stream) return false;
     if (ctx->side_stream == nullptr) {
-        cudaStream_t q;
-        cudaEvent_t e[6];
-        bool ok = cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking) == cudaSuccess;
-        for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) == cudaSuccess;
+        cudaStream_t q[2];
+        cudaEvent_t e[NEV + 1];
+        bool ok = cudaStreamCreateWithFlags(&q[0], cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&q[1], cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i <= NEV && ok; ++i) ok = cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { cudaGetLastError(); return false; }
-        ctx->side_stream = q;
-        for (int k = 0; k < 3; ++k) { ctx->ev_fork[k] = e[2 * k]; ctx->ev_join[k] = e[2 * k + 1]; }
+        ctx->side_stream = q[0];
+        ctx->aux_stream = q[1];
+        for (int i = 0; i < NEV; ++i) ctx->ev_pool[i] = e[i];
+        ctx->ev_noise = e[NEV];
     }
     return true;
 }
-// everything enqueued on `s` so far happens-before what is then enqueued on the returned stream
-static void side_mark(cpg_ctx* ctx, cudaStream_t s, int k = 0) { cudaEventRecord((cudaEvent_t)ctx->ev_fork[k], s); }
-static cudaStream_t side_enter(cpg_ctx* ctx, int k = 0) {
-    cudaStreamWaitEvent((cudaStream_t)ctx->side_stream, (cudaEvent_t)ctx->ev_fork[k], 0);
-    return (cudaStream_t)ctx->side_stream;
+static Lanes lanes(cpg_ctx* ctx, cudaStream_t m) {
+    if (!side_ready(ctx)) return Lanes{m, m, m, false};
+    return Lanes{m, (cudaStream_t)ctx->side_stream, (cudaStream_t)ctx->aux_stream, true};
 }
-static void side_leave(cpg_ctx* ctx, int k = 0) {
-    cudaEventRecord((cudaEvent_t)ctx->ev_join[k], (cudaStream_t)ctx->side_stream);
-    ctx->join_pending[k] = true;
+// everything enqueued on `s` so far
+static Mark mark(cpg_ctx* ctx, const Lanes& l, cudaStream_t s) {
+    if (!l.on) return nullptr;
+    cudaEvent_t e = (cudaEvent_t)ctx->ev_pool[ctx->ev_next];
+    ctx->ev_next = (ctx->ev_next + 1) % NEV;
+    cudaEventRecord(e, s);
+    return e;
 }
-static void side_join(cpg_ctx* ctx, cudaStream_t s, int k = 0) {
-    if (ctx->join_pending[k]) { cudaStreamWaitEvent(s, (cudaEvent_t)ctx->ev_join[k], 0); ctx->join_pending[k] = false; }
+static void wait_mark(cudaStream_t s, Mark m) { if (m != nullptr) cudaStreamWaitEvent(s, (cudaEvent_t)m, 0); }
+// an event of the pool for a callee that records and waits by itself
+static void* pool_event(cpg_ctx* ctx, const Lanes& l) {
+    if (!l.on) return nullptr;
+    void* e = ctx->ev_pool[ctx->ev_next];
+    ctx->ev_next = (ctx->ev_next + 1) % NEV;
+    return e;
+}
+// what is enqueued on `to` from now on runs after everything enqueued on `from` so far
+static void order(cpg_ctx* ctx, const Lanes& l, cudaStream_t from, cudaStream_t to) {
+    if (l.on && from != to) wait_mark(to, mark(ctx, l, from));
+}
+// noise produced on the side stream by cpg_fill_step_noise_overlapped: its first reader on another stream joins it
+static void noise_join(cpg_ctx* ctx, cudaStream_t s) {
+    if (ctx->noise_pending) { cudaStreamWaitEvent(s, (cudaEvent_t)ctx->ev_noise, 0); ctx->noise_pending = false; }
 }
 #else
 static bool side_ready(cpg_ctx*) { return false; }
-static void side_mark(cpg_ctx*, cudaStream_t, int = 0) {}
-static cudaStream_t side_enter(cpg_ctx*, int = 0) { return nullptr; }
-static void side_leave(cpg_ctx*, int = 0) {}
-static void side_join(cpg_ctx*, cudaStream_t, int = 0) {}
+static Lanes lanes(cpg_ctx*, cudaStream_t m) { return Lanes{m, m, m, false}; }
+static Mark mark(cpg_ctx*, const Lanes&, cudaStream_t) { return nullptr; }
+static void wait_mark(cudaStream_t, Mark) {}
+static void* pool_event(cpg_ctx*, const Lanes&) { return nullptr; }
+static void order(cpg_ctx*, const Lanes&, cudaStream_t, cudaStream_t) {}
+static void noise_join(cpg_ctx*, cudaStream_t) {}
 #endif
 
 // ------------------------------------------------------------------------------------ forward
@@ -237,12 +270,18 @@ static bool use_gru_tc(int) { return false; }
 // g_opt_bptt_fused: 1 (default) = on the tcgen05 path the BPTT kernels also contract dW_hh / the token-table
 // gradient (no dg planes in HBM, no separate weight-gradient kernel); 0 = k_gru_bwd_tc + k_wgrad_tc
 int g_opt_bptt_fused = 1;
-static void forward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, const ParamLayout& lay, int V, int B, int L,
-                         const cpg_wae_inputs* in, float* mu, float* logvar, float* z, bool stash, bool encoder_only,
-                         bool mark_after_reparam = false) {
+// Returns the mark "mu, logvar, z are final" (made on the caller's lane right after the latent layers) for the loss
+// statistics of the training step; null when the lanes are off.
+static Mark forward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, const ParamLayout& lay, int V, int B, int L,
+                         const cpg_wae_inputs* in, float* mu, float* logvar, float* z, bool stash, bool encoder_only) {
     Workspace& w = ctx->ws;
+    cudaStream_t s = ln.m;
+    // the derived weight forms only depend on the parameters: their lane runs beside the token preparation
+    order(ctx, ln, s, ln.t);
+    launch_prep_weights(ln.t, params, lay, V, w.d);
+    const Mark weights_ready = mark(ctx, ln, ln.t);
     launch_prep_tokens(s, in->tokens, in->word_drop, B, L, V, w.tok, w.tokd, w.tgt, ctx->ints, ctx->ints + 1);
-    launch_prep_weights(s, params, lay, V, w.d);
+    wait_mark(s, weights_ready);
     GruSeq enc[2];
     for (int d = 0; d < 2; ++d) {
         GruSeq& q = enc[d];
@@ -260,15 +299,26 @@ static void forward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, cons
     } else {
         launch_gru_fwd_enc(s, enc, B, L);
     }
-    // q_mu / q_logvar heads (models/encoder.py:50-51)
-    launch_sgemm_pair(s, B, ZD, 2 * ENC_H, 1.f, w.hfin, 2 * ENC_H, 1, params + lay.off[P_QMU_W], params + lay.off[P_QLV_W],
-                      1, 2 * ENC_H, mu, logvar, ZD, params + lay.off[P_QMU_B], params + lay.off[P_QLV_B]);
-    if (encoder_only) return;
-    launch_reparam(s, mu, logvar, in->eps, in->c, B, z, w.zc);
-    if (mark_after_reparam) side_mark(ctx, s);      // mu, logvar, z are final: the loss statistics may start
-    // per-row input projection of [z;c] (the non-embedding columns of decoder W_ih)
-    launch_sgemm(s, B, 3 * DEC_HP, DEC_HP, 1.f, w.zc, DEC_HP, 1, w.d.wizc_t, 3 * DEC_HP, 1, 0.f, w.rowbias,
-                 3 * DEC_HP, nullptr, 1, nullptr);
+    noise_join(ctx, s);                             // eps, c (and the out-dropout mask) of cpg_fill_step_noise_overlapped
+    if (latent_uses_tc(B)) {
+        // heads -> reparameterisation -> [z;c] -> its input projection, one tcgen05 kernel (latent_tc.cu)
+        launch_latent_fwd_tc(s, w.hfin, params + lay.off[P_QMU_B], params + lay.off[P_QLV_B], encoder_only ? nullptr : in->eps,
+                             encoder_only ? nullptr : in->c, w.d.lat_tiles, B, mu, logvar, encoder_only ? nullptr : z, w.zc,
+                             encoder_only ? nullptr : w.rowbias);
+        if (encoder_only) return nullptr;
+    } else {
+        // q_mu / q_logvar heads (models/encoder.py:50-51)
+        launch_sgemm_pair(s, B, ZD, 2 * ENC_H, 1.f, w.hfin, 2 * ENC_H, 1, params + lay.off[P_QMU_W], params + lay.off[P_QLV_W],
+                          1, 2 * ENC_H, mu, logvar, ZD, params + lay.off[P_QMU_B], params + lay.off[P_QLV_B]);
+        if (encoder_only) return nullptr;
+        launch_reparam(s, mu, logvar, in->eps, in->c, B, z, w.zc);
+    }
+    const Mark latent_ready = mark(ctx, ln, s);     // mu, logvar, z are final: the loss statistics may start
+    if (!latent_uses_tc(B)) {
+        // per-row input projection of [z;c] (the non-embedding columns of decoder W_ih)
+        launch_sgemm(s, B, 3 * DEC_HP, DEC_HP, 1.f, w.zc, DEC_HP, 1, w.d.wizc_t, 3 * DEC_HP, 1, 0.f, w.rowbias,
+                     3 * DEC_HP, nullptr, 1, nullptr);
+    }
     GruSeq q;
     memset(&q, 0, sizeof(q));
     q.tok = w.tokd; q.table = w.d.t_dec; q.rowbias = w.rowbias; q.whh_t = w.d.whh_t_dec; q.bhn = w.d.bhn_dec;
@@ -279,6 +329,7 @@ static void forward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, cons
     } else {
         launch_gru_fwd_dec(s, q, B, L);
     }
+    return latent_ready;
 }
 
 static DecOutArgs dec_out_args(cpg_ctx* ctx, const cpg_wae_inputs* in, int V, int B, int L) {
@@ -295,12 +346,14 @@ static DecOutArgs dec_out_args(cpg_ctx* ctx, const cpg_wae_inputs* in, int V, in
 }
 
 // ----------------------------------------------------------------------------------- backward
-// Everything after the decoder-output layer has produced dec_dh_out.  dz_rf / external latent
-// gradients are optional.
-static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, const ParamLayout& lay, float* grads,
-                          int V, int B, int L, const cpg_wae_inputs* in, const LatentBwdArgs& lat_in) {
+// Everything after the decoder-output layer has produced dec_dh_out.  dz_rf / external latent gradients are optional;
+// `dz_ready` = the mark after which lat_in.dz_rf may be read (null: it is already ordered before the caller's lane).
+// On return every gradient is complete on the caller's lane (the other lanes are joined).
+static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, const ParamLayout& lay, float* grads,
+                          int V, int B, int L, const cpg_wae_inputs* in, const LatentBwdArgs& lat_in, Mark dz_ready) {
     Workspace& w = ctx->ws;
     const int sm = ctx->sm_count;
+    cudaStream_t s = ln.m;
     // decoder BPTT
     GruSeq q;
     memset(&q, 0, sizeof(q));
@@ -312,49 +365,49 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     if (fused) launch_gru_bwd_dec_fused(s, q, w.tokd, B, L, V, w.wg_part_dec, w.dt_part_dec);
     else if (use_gru_tc(B)) launch_gru_bwd_dec_tc(s, q, B, L, dg_rounded);
     else launch_gru_bwd_dec(s, q, B, L);
-    // decoder W_hh / token-table gradients only need the decoder BPTT's output: side stream, under the dense layers
-    // and the encoder BPTT of the main stream (joined before the input-side gradients)
-    const bool side = side_ready(ctx);
+    // decoder W_hh / token-table gradients only need the decoder BPTT's output: lane t, under the dense layers and the
+    // encoder BPTT of the caller's lane (joined before the input-side gradients)
     {
-        cudaStream_t qs = s;
-        if (side) { side_mark(ctx, s, 1); qs = side_enter(ctx, 1); }
+        order(ctx, ln, s, ln.t);
         // dW_ih[:,150:] = drow^T @ [z;c]  (a weight gradient: nothing on the BPTT chain waits for it)
-        launch_sgemm(qs, 3 * DEC_HP, DEC_HP, B, 1.f, w.drow, 1, 3 * DEC_HP, w.zc, DEC_HP, 1, 0.f, w.dwizc, DEC_HP,
+        launch_sgemm(ln.t, 3 * DEC_HP, DEC_HP, B, 1.f, w.drow, 1, 3 * DEC_HP, w.zc, DEC_HP, 1, 0.f, w.dwizc, DEC_HP,
                      nullptr, w.gemm_splits, w.gemm_ws);
         if (fused) {
-            launch_wgrad_partial_reduce(qs, DEC_HP, DEC_H, V, w.wg_part_dec, w.dt_part_dec, bptt_fused_ctas_dec(B),
+            launch_wgrad_partial_reduce(ln.t, DEC_HP, DEC_H, V, w.wg_part_dec, w.dt_part_dec, bptt_fused_ctas_dec(B),
                                         grads + lay.off[P_DEC_WHH], w.dT_dec);
         } else {
-            const bool t2 = launch_wgrad_hh(qs, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, w.tokd, 0, V, B, L, sm, w.wg_part_dec,
+            const bool t2 = launch_wgrad_hh(ln.t, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, w.tokd, 0, V, B, L, sm, w.wg_part_dec,
                                             w.dt_part_dec, grads + lay.off[P_DEC_WHH], w.dT_dec, nullptr, nullptr, dg_rounded);
-            if (!t2) launch_dtable(qs, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part_dec, w.dT_dec);
+            if (!t2) launch_dtable(ln.t, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part_dec, w.dT_dec);
         }
-        if (side) side_leave(ctx, 1);
     }
-    // gradient at [z;c]:  dh0 + drow @ W_ih[:,150:]   (in place on dh0)
-    launch_sgemm(s, B, DEC_HP, 3 * DEC_HP, 1.f, w.drow, 3 * DEC_HP, 1, w.d.wizc, DEC_HP, 1, 1.f, w.dh0, DEC_HP,
-                 nullptr, 1, nullptr);
-    // latent
+    const float* wmu = params + lay.off[P_QMU_W];
+    const float* wlv = params + lay.off[P_QLV_W];
     LatentBwdArgs la = lat_in;
     la.mu = w.mu; la.logvar = w.logvar; la.eps = in->eps; la.dzc = w.dh0; la.B = B;
     la.dmu = w.dmu; la.dlv = w.dlv;
-    side_join(ctx, s);                              // dz_rf / loss scalars produced on the side stream
-    launch_latent_bwd(s, la);
-    // heads
-    const float* wmu = params + lay.off[P_QMU_W];
-    const float* wlv = params + lay.off[P_QLV_W];
-    launch_sgemm_sum2(s, B, 2 * ENC_H, ZD, 1.f, w.dmu, w.dlv, ZD, 1, wmu, wlv, 2 * ENC_H, 1, 0.f, w.dhfin, 2 * ENC_H);
-    // head weight / bias gradients: side stream (after the decoder weight gradients), under the encoder BPTT
+    if (latent_uses_tc(B)) {
+        // gradient at [z;c] -> latent backward -> gradient at the encoder's final hidden state, one tcgen05 kernel
+        wait_mark(s, dz_ready);                     // dz_rf produced on lane s
+        launch_latent_bwd_tc(s, w.drow, w.dh0, w.d.lat_tiles, la, w.dhfin);
+    } else {
+        // gradient at [z;c]:  dh0 + drow @ W_ih[:,150:]   (in place on dh0)
+        launch_sgemm(s, B, DEC_HP, 3 * DEC_HP, 1.f, w.drow, 3 * DEC_HP, 1, w.d.wizc, DEC_HP, 1, 1.f, w.dh0, DEC_HP,
+                     nullptr, 1, nullptr);
+        wait_mark(s, dz_ready);
+        launch_latent_bwd(s, la);
+        // heads
+        launch_sgemm_sum2(s, B, 2 * ENC_H, ZD, 1.f, w.dmu, w.dlv, ZD, 1, wmu, wlv, 2 * ENC_H, 1, 0.f, w.dhfin, 2 * ENC_H);
+    }
+    // head weight / bias gradients: lane t (after the decoder weight gradients: same split-K scratch), under the encoder BPTT
     {
-        cudaStream_t qs = s;
-        if (side) { side_mark(ctx, s, 0); qs = side_enter(ctx, 0); }
-        launch_sgemm(qs, ZD, 2 * ENC_H, B, 1.f, w.dmu, 1, ZD, w.hfin, 2 * ENC_H, 1, 0.f, grads + lay.off[P_QMU_W],
+        order(ctx, ln, s, ln.t);
+        launch_sgemm(ln.t, ZD, 2 * ENC_H, B, 1.f, w.dmu, 1, ZD, w.hfin, 2 * ENC_H, 1, 0.f, grads + lay.off[P_QMU_W],
                      2 * ENC_H, nullptr, w.gemm_splits, w.gemm_ws);
-        launch_sgemm(qs, ZD, 2 * ENC_H, B, 1.f, w.dlv, 1, ZD, w.hfin, 2 * ENC_H, 1, 0.f, grads + lay.off[P_QLV_W],
+        launch_sgemm(ln.t, ZD, 2 * ENC_H, B, 1.f, w.dlv, 1, ZD, w.hfin, 2 * ENC_H, 1, 0.f, grads + lay.off[P_QLV_W],
                      2 * ENC_H, nullptr, w.gemm_splits, w.gemm_ws);
-        launch_colsum(qs, w.dmu, B, ZD, ZD, grads + lay.off[P_QMU_B], w.colsum_ws, 64);
-        launch_colsum(qs, w.dlv, B, ZD, ZD, grads + lay.off[P_QLV_B], w.colsum_ws, 64);
-        if (side) side_leave(ctx, 0);
+        launch_colsum(ln.t, w.dmu, B, ZD, ZD, grads + lay.off[P_QMU_B], w.colsum_ws, 64);
+        launch_colsum(ln.t, w.dlv, B, ZD, ZD, grads + lay.off[P_QLV_B], w.colsum_ws, 64);
     }
     // encoder BPTT
     GruSeq enc[2];
@@ -366,38 +419,31 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
         e.dh_fin = w.dhfin + d * ENC_H; e.dh_fin_stride = 2 * ENC_H;
         e.dg = w.enc_dg[d];
     }
-    cudaStream_t rs = side ? (cudaStream_t)ctx->side_stream : nullptr;
     if (fused) {
         float* const pw[2] = {w.wg_part, w.wg_part_enc1};
         float* const pt[2] = {w.dt_part, w.dt_part_enc1};
         launch_gru_bwd_enc_fused(s, enc, w.tok, B, L, V, pw, pt);
-        // ordered reductions of the per-CTA partials: one direction on the side stream, the other on the main stream
+        // ordered reductions of the per-CTA partials: one direction on lane s, the other on the caller's lane
         const int nc = bptt_fused_ctas_enc(B);
-#ifndef CPG_EMU
-        if (side) {
-            cudaEventRecord((cudaEvent_t)ctx->ev_fork[1], s);
-            cudaStreamWaitEvent(rs, (cudaEvent_t)ctx->ev_fork[1], 0);
-        }
-#endif
-        launch_wgrad_partial_reduce(side ? rs : s, ENC_H, ENC_H, V, pw[0], pt[0], nc, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0]);
+        order(ctx, ln, s, ln.s);
+        launch_wgrad_partial_reduce(ln.s, ENC_H, ENC_H, V, pw[0], pt[0], nc, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0]);
         launch_wgrad_partial_reduce(s, ENC_H, ENC_H, V, pw[1], pt[1], nc, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1]);
     } else {
-    if (use_gru_tc(B)) launch_gru_bwd_enc_tc(s, enc, B, L, dg_rounded);
-    else launch_gru_bwd_enc(s, enc, B, L);
-    // recurrent weight gradients
-    // (the tensor-core path produces the token-table gradient in the same pass over dg)
-    // (each direction has its own partials, and the ordered reductions of the partials run on the side stream
-    //  while the main stream already contracts the next direction)
-    const bool t0 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[0], w.enc_hs[0], nullptr, w.tok, 0, V, B, L, sm, w.wg_part,
-                                    w.dt_part, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0], rs, side ? ctx->ev_fork[1] : nullptr, dg_rounded);
-    if (!t0) launch_dtable(s, ENC_H, w.enc_dg[0], w.tok, B, L, 0, V, sm, w.dt_part, w.dT_enc[0]);
-    const bool t1 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[1], w.enc_hs[1], nullptr, w.tok, 1, V, B, L, sm, w.wg_part_enc1,
-                                    w.dt_part_enc1, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1], rs, side ? ctx->ev_fork[1] : nullptr, dg_rounded);
-    if (!t1) launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part_enc1, w.dT_enc[1]);
+        if (use_gru_tc(B)) launch_gru_bwd_enc_tc(s, enc, B, L, dg_rounded);
+        else launch_gru_bwd_enc(s, enc, B, L);
+        // recurrent weight gradients (the tensor-core path produces the token-table gradient in the same pass over dg);
+        // each direction has its own partials, and the ordered reductions of the partials run on lane s while the caller's
+        // lane already contracts the next direction
+        cudaStream_t rs = ln.on ? ln.s : nullptr;
+        const bool t0 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[0], w.enc_hs[0], nullptr, w.tok, 0, V, B, L, sm, w.wg_part,
+                                        w.dt_part, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0], rs, pool_event(ctx, ln), dg_rounded);
+        if (!t0) launch_dtable(s, ENC_H, w.enc_dg[0], w.tok, B, L, 0, V, sm, w.dt_part, w.dT_enc[0]);
+        const bool t1 = launch_wgrad_hh(s, ENC_H, ENC_H, w.enc_dg[1], w.enc_hs[1], nullptr, w.tok, 1, V, B, L, sm, w.wg_part_enc1,
+                                        w.dt_part_enc1, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1], rs, pool_event(ctx, ln), dg_rounded);
+        if (!t1) launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part_enc1, w.dT_enc[1]);
     }
-    if (side) side_leave(ctx, 1);                   // covers everything enqueued on the (in-order) side stream so far
-    side_join(ctx, s, 1);
-    ctx->join_pending[0] = false;                   // (already implied by the join above)
+    order(ctx, ln, ln.t, s);                        // every lane's gradients / partial reductions are complete
+    order(ctx, ln, ln.s, s);
     InputGradArgs ia;
     memset(&ia, 0, sizeof(ia));
     ia.emb = params + lay.off[P_EMB];
@@ -412,12 +458,10 @@ static void backward_impl(cpg_ctx* ctx, cudaStream_t s, const float* params, con
     ia.g_dec_wih = grads + lay.off[P_DEC_WIH]; ia.g_dec_bih = grads + lay.off[P_DEC_BIH];
     ia.g_dec_bhh = grads + lay.off[P_DEC_BHH];
     ia.V = V;
-    if (side) {                                     // the two input-side kernels are independent: run them side by side
-        side_mark(ctx, s, 0);
-        cudaStream_t qs = side_enter(ctx, 0);
-        launch_input_grads(s, ia, qs);
-        side_leave(ctx, 0);
-        side_join(ctx, s, 0);
+    if (ln.on) {                                    // the two input-side kernels are independent: run them side by side
+        order(ctx, ln, s, ln.t);
+        launch_input_grads(s, ia, ln.t);
+        order(ctx, ln, ln.t, s);
     } else {
         launch_input_grads(s, ia);
     }
@@ -535,11 +579,11 @@ int cpg_destroy(cpg_ctx* c) {
 #ifndef CPG_EMU
     if (c->side_stream) {
         cudaStreamSynchronize((cudaStream_t)c->side_stream);
+        cudaStreamSynchronize((cudaStream_t)c->aux_stream);
         cudaStreamDestroy((cudaStream_t)c->side_stream);
-        for (int k = 0; k < 3; ++k) {
-            cudaEventDestroy((cudaEvent_t)c->ev_fork[k]);
-            cudaEventDestroy((cudaEvent_t)c->ev_join[k]);
-        }
+        cudaStreamDestroy((cudaStream_t)c->aux_stream);
+        for (int k = 0; k < NEV; ++k) cudaEventDestroy((cudaEvent_t)c->ev_pool[k]);
+        cudaEventDestroy((cudaEvent_t)c->ev_noise);
     }
 #endif
     delete c;
@@ -576,7 +620,8 @@ int cpg_wae_encode(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, 
     cpg_wae_inputs in;
     memset(&in, 0, sizeof(in));
     in.tokens = tokens;
-    forward_impl(ctx, s, params, make_layout(V), V, B, L, &in, mu, logvar, nullptr, false, true);
+    const Lanes ln = lanes(ctx, s);
+    forward_impl(ctx, ln, params, make_layout(V), V, B, L, &in, mu, logvar, nullptr, false, true);
     ctx->have_stash = false;
     return check_launch("cpg_wae_encode");
 }
@@ -588,11 +633,12 @@ int cpg_wae_forward(cpg_ctx* ctx, cpg_stream stream, const float* params, int V,
     if (!ctx || !params || !in || !in->tokens || !in->c) { set_error("cpg_wae_forward: null argument"); return CPG_EINVAL; }
     if (in->out_keep && !(in->p_out_dropout >= 0.f && in->p_out_dropout < 1.f)) { set_error("p_out_dropout must be in [0,1)"); return CPG_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
-    side_join(ctx, s, 2);                           // late noise of cpg_fill_step_noise_overlapped, if any
     if ((rc = ensure_workspace(ctx, B, L, V, ctx->ws.R > 0 ? ctx->ws.R : 500, s))) return rc;
     Workspace& w = ctx->ws;
     ParamLayout lay = make_layout(V);
-    forward_impl(ctx, s, params, lay, V, B, L, in, w.mu, w.logvar, w.z, keep != 0, false);
+    const Lanes ln = lanes(ctx, s);
+    noise_join(ctx, s);                             // noise of cpg_fill_step_noise_overlapped, if any
+    forward_impl(ctx, ln, params, lay, V, B, L, in, w.mu, w.logvar, w.z, keep != 0, false);
     if (mu) dev_copy(mu, w.mu, (size_t)B * ZD * 4, s);
     if (logvar) dev_copy(logvar, w.logvar, (size_t)B * ZD * 4, s);
     if (z) dev_copy(z, w.z, (size_t)B * ZD * 4, s);
@@ -618,7 +664,8 @@ int cpg_wae_backward(cpg_ctx* ctx, cpg_stream stream, const float* params, int V
         return CPG_EINVAL;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    side_join(ctx, s, 2);
+    noise_join(ctx, s);
+    const Lanes ln = lanes(ctx, s);
     ParamLayout lay = make_layout(V);
     dev_memset(grads, 0, (size_t)lay.total * 4, s);
     DecOutArgs a = dec_out_args(ctx, in, V, B, L);
@@ -631,7 +678,7 @@ int cpg_wae_backward(cpg_ctx* ctx, cpg_stream stream, const float* params, int V
     memset(&la, 0, sizeof(la));
     la.dz_ext = d_z; la.dmu_ext = d_mu; la.dlv_ext = d_logvar;
     la.B_global = B;
-    backward_impl(ctx, s, params, lay, grads, V, B, L, in, la);
+    backward_impl(ctx, ln, params, lay, grads, V, B, L, in, la, nullptr);
     return check_launch("cpg_wae_backward");
 }
 
@@ -643,24 +690,29 @@ int cpg_fill_step_noise_overlapped(cpg_ctx* ctx, cpg_stream stream, uint64_t see
     StepNoiseArgs a;
     a.seed = seed; a.step = step; a.B = B; a.L = L; a.p_word = p_word; a.p_out = p_out;
     a.eps = eps; a.c = c; a.word_drop = word_drop; a.out_keep = out_keep; a.zp_full = z_prior_full; a.zp_rf = z_prior_rf;
-    if (!side_ready(ctx)) {
-        launch_step_noise(s, a, 3);
+    const Lanes ln = lanes(ctx, s);
+    if (!ln.on) {
+        launch_step_noise(s, a, NOISE_ALL);
         return check_launch("cpg_fill_step_noise_overlapped");
     }
-    side_join(ctx, s, 2);                           // a previous late part nobody consumed yet
-    side_mark(ctx, s, 2);                           // earlier readers of these buffers (previous iteration) are on `s`
-    cudaStream_t q = side_enter(ctx, 2);
-    launch_step_noise(q, a, 2);                     // z_prior x2 + out-dropout mask: under prep / encoder recurrence
-    side_leave(ctx, 2);
-    launch_step_noise(s, a, 1);                     // eps, c, word dropout: needed right away
+    noise_join(ctx, s);                             // a previous batch of noise nobody consumed yet
+    order(ctx, ln, s, ln.s);                        // earlier readers of these buffers (previous iteration) are on `s`
+    // eps, c, z_prior x2, out-dropout mask: lane s, under the token preparation / encoder recurrence (first reader: the
+    // latent layers, which join it)
+    launch_step_noise(ln.s, a, NOISE_LATENT | NOISE_LATE);
+    cudaEventRecord((cudaEvent_t)ctx->ev_noise, ln.s);
+    ctx->noise_pending = true;
+    launch_step_noise(s, a, NOISE_WORD);            // word dropout: needed by the token preparation right away
     return check_launch("cpg_fill_step_noise_overlapped");
 }
 
 int64_t cpg_coupled_count(int rf_dim) { return 8 + 2 * (int64_t)rf_dim; }
 
-int cpg_wae_step_phase1(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int B, int L,
-                        const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
-                        float* coupled, float* mu, float* logvar, float* z) {
+// Phase 1.  `join`: the caller's lane waits for the coupled statistics (the public contract of cpg_wae_step_phase1); the
+// fused single-GPU step leaves them on lane s, where everything that consumes them runs.
+static int phase1_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int B, int L,
+                       const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
+                       float* coupled, float* mu, float* logvar, float* z, bool join) {
     int rc = check_dims(V, B, L);
     if (rc) return rc;
     if (!ctx || !params || !in || !nz || !hp || !coupled || !in->tokens || !in->c) { set_error("cpg_wae_step_phase1: null argument"); return CPG_EINVAL; }
@@ -671,20 +723,22 @@ int cpg_wae_step_phase1(cpg_ctx* ctx, cpg_stream stream, const float* params, in
     if ((rc = ensure_workspace(ctx, B, L, V, R, s))) return rc;
     Workspace& w = ctx->ws;
     ParamLayout lay = make_layout(V);
-    const bool side = side_ready(ctx);
-    forward_impl(ctx, s, params, lay, V, B, L, in, w.mu, w.logvar, w.z, true, false, side);
+    const Lanes ln = lanes(ctx, s);
+    cudaStream_t q = ln.s;
+    // the prior's random features do not depend on the batch: lane s, under the encoder recurrence
+    // (z_prior_rf: produced on lane s by cpg_fill_step_noise_overlapped, or an input ordered before the caller's lane)
+    if (!ctx->noise_pending) order(ctx, ln, s, q);
+    launch_sgemm(q, B, R, ZD, 1.f, nz->z_prior_rf, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre2, R, nullptr, 1, nullptr);
+    launch_rf_colsum(q, w.rf_pre2, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8 + R);
+    const Mark latent_ready = forward_impl(ctx, ln, params, lay, V, B, L, in, w.mu, w.logvar, w.z, true, false);
     // local statistics that couple the batch: token count, latent sums, RF feature sums -- they depend on
-    // (mu, logvar, z) only and run on the side stream under the decoder recurrence
-    {
-        cudaStream_t q = side ? side_enter(ctx) : s;
-        launch_int_to_float(q, ctx->ints, coupled + 0, 1);
-        launch_latent_stats(q, w.mu, w.logvar, B, w.lat_part, w.lat_nparts, coupled + 2);
-        launch_sgemm(q, B, R, ZD, 1.f, w.z, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre1, R, nullptr, 1, nullptr);
-        launch_sgemm(q, B, R, ZD, 1.f, nz->z_prior_rf, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre2, R, nullptr, 1, nullptr);
-        launch_rf_colsum(q, w.rf_pre1, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8);
-        launch_rf_colsum(q, w.rf_pre2, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8 + R);
-        if (side) { side_leave(ctx); side_join(ctx, s); }
-    }
+    // (mu, logvar, z) only and run on lane s under the decoder recurrence
+    wait_mark(q, latent_ready);
+    launch_int_to_float(q, ctx->ints, coupled + 0, 1);
+    launch_latent_stats(q, w.mu, w.logvar, B, w.lat_part, w.lat_nparts, coupled + 2);
+    launch_sgemm(q, B, R, ZD, 1.f, w.z, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre1, R, nullptr, 1, nullptr);
+    launch_rf_colsum(q, w.rf_pre1, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8);
+    if (join) order(ctx, ln, q, s);
     if (mu) dev_copy(mu, w.mu, (size_t)B * ZD * 4, s);
     if (logvar) dev_copy(logvar, w.logvar, (size_t)B * ZD * 4, s);
     if (z) dev_copy(z, w.z, (size_t)B * ZD * 4, s);
@@ -693,9 +747,17 @@ int cpg_wae_step_phase1(cpg_ctx* ctx, cpg_stream stream, const float* params, in
     return check_launch("cpg_wae_step_phase1");
 }
 
-int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, float* grads, int V, int B, int L,
+int cpg_wae_step_phase1(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int B, int L,
                         const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
-                        const float* coupled, float* scalars, float* logits) {
+                        float* coupled, float* mu, float* logvar, float* z) {
+    return phase1_impl(ctx, stream, params, V, B, L, in, nz, hp, coupled, mu, logvar, z, true);
+}
+
+// Phase 2.  `fused` = called by the single-GPU step right after phase1_impl(join = false): the coupled statistics are
+// local and still on lane s (where their consumers run), and the token count is read from the preparation's own counter.
+static int phase2_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, float* grads, int V, int B, int L,
+                       const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
+                       const float* coupled, float* scalars, float* logits, bool fused_step) {
     int rc = check_dims(V, B, L);
     if (rc) return rc;
     if (!ctx || !params || !grads || !in || !nz || !hp || !coupled) { set_error("cpg_wae_step_phase2: null argument"); return CPG_EINVAL; }
@@ -713,38 +775,43 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
     const int R = hp->rf_dim;
     const int Bg = hp->global_batch > 0 ? hp->global_batch : B;
     ParamLayout lay = make_layout(V);
+    const Lanes ln = lanes(ctx, s);
     dev_memset(grads, 0, (size_t)lay.total * 4, s);
-    // RF-MMD from the global feature sums and the (logged) full-kernel MMD: side stream, joined in
-    // backward_impl right before the latent backward that consumes dz_rf
-    const bool side = side_ready(ctx);
-    if (side) side_mark(ctx, s);
+    // RF-MMD from the global feature sums, then the full-kernel MMD: lane s; the caller's lane waits for the RF gradient
+    // right before the latent backward that consumes it, for the (logged) full-kernel MMD only at the end of the step
+    if (!fused_step) order(ctx, ln, s, ln.s);       // `coupled` as the caller left it on its stream (exchange done)
     const float w_rf = hp->z_regu == CPG_ZREGU_MMDRF ? hp->beta : 0.f;
     const float* dz_rf = nullptr;
+    Mark dz_ready = nullptr;
     {
-        cudaStream_t q = side ? side_enter(ctx) : s;
+        cudaStream_t q = ln.s;
         launch_rf_loss(q, coupled + 8, coupled + 8 + R, R, Bg, hp->mmd_sigma, w_rf, w.rf_coef, w.mmdrf_out);
         if (w_rf != 0.f) {
             launch_rf_grad_prep(q, w.rf_pre1, nz->rf_b, w.rf_coef, B, R, hp->mmd_sigma);
             launch_sgemm(q, B, ZD, R, 1.f, w.rf_pre1, R, 1, nz->rf_w, 1, R, 0.f, w.dz_rf, ZD, nullptr, 1, nullptr);
             dz_rf = w.dz_rf;
         }
-        if ((hp->compute_full_mmd || hp->z_regu == CPG_ZREGU_MMD) && nz->z_prior_full)
-            if ((rc = launch_mmd_full(q, w.z, nz->z_prior_full, B, hp->mmd_sigma, w.mmd_ws, w.mmd_out))) return rc;
+        const bool want_mmd = (hp->compute_full_mmd || hp->z_regu == CPG_ZREGU_MMD) && nz->z_prior_full;
         if (hp->z_regu == CPG_ZREGU_MMD) {                          // the full-kernel MMD is the regulariser: its gradient at z
             launch_mmd_full_grad(q, w.z, nz->z_prior_full, B, hp->mmd_sigma, hp->beta, w.dz_rf);
             dz_rf = w.dz_rf;
         }
-        if (side) side_leave(ctx);
+        dz_ready = mark(ctx, ln, q);
+        if (want_mmd)
+            if ((rc = launch_mmd_full(q, w.z, nz->z_prior_full, B, hp->mmd_sigma, w.mmd_ws, w.mmd_out))) return rc;
     }
-    // reconstruction loss fwd+bwd with the global token count (coupled[0])
+    // reconstruction loss fwd+bwd with the global token count
     DecOutArgs a = dec_out_args(ctx, in, V, B, L);
     a.ntok = coupled + 0;
+    a.ntok_i = fused_step ? ctx->ints : nullptr;    // single GPU: the count prep_tokens left on this lane
     a.fused_ce = 1;
     a.logits_out = logits;
     a.dh_out = w.dec_dh_out;
-    side_join(ctx, s, 2);                           // out-dropout mask generated on the side stream
+    noise_join(ctx, s);                             // out-dropout mask generated on lane s (normally joined by the latent layers)
     launch_dec_out(s, a, ctx->sm_count);
-    launch_dec_out_reduce(s, a, ctx->sm_count, grads + lay.off[P_FC_W], grads + lay.off[P_FC_B], w.nll_sum);
+    // the ordered reduction of its partials (fc gradients, NLL sum): lane t, under the decoder BPTT
+    order(ctx, ln, s, ln.t);
+    launch_dec_out_reduce(ln.t, a, ctx->sm_count, grads + lay.off[P_FC_W], grads + lay.off[P_FC_B], w.nll_sum);
     LatentBwdArgs la;
     memset(&la, 0, sizeof(la));
     la.dz_rf = dz_rf;
@@ -752,7 +819,7 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
     la.w_klsm = hp->lambda_logvar_kl;
     la.w_l1 = hp->lambda_logvar_l1;
     la.B_global = Bg;
-    backward_impl(ctx, s, params, lay, grads, V, B, L, in, la);
+    backward_impl(ctx, ln, params, lay, grads, V, B, L, in, la, dz_ready);
     if (scalars) {
         ComposeArgs c;
         memset(&c, 0, sizeof(c));
@@ -764,6 +831,12 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
         launch_compose_scalars(s, c);
     }
     return check_launch("cpg_wae_step_phase2");
+}
+
+int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, float* grads, int V, int B, int L,
+                        const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
+                        const float* coupled, float* scalars, float* logits) {
+    return phase2_impl(ctx, stream, params, grads, V, B, L, in, nz, hp, coupled, scalars, logits, false);
 }
 
 int cpg_clip_adam_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* m, float* v, int V,
@@ -790,8 +863,8 @@ int cpg_wae_train_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* gr
     int rc = ensure_workspace(ctx, B, L, V, h.rf_dim, (cudaStream_t)stream);
     if (rc) return rc;
     float* cpl = ctx->ws.coupled;
-    if ((rc = cpg_wae_step_phase1(ctx, stream, params, V, B, L, in, nz, &h, cpl, mu, logvar, z))) return rc;
-    if ((rc = cpg_wae_step_phase2(ctx, stream, params, grads, V, B, L, in, nz, &h, cpl, scalars, logits))) return rc;
+    if ((rc = phase1_impl(ctx, stream, params, V, B, L, in, nz, &h, cpl, mu, logvar, z, false))) return rc;
+    if ((rc = phase2_impl(ctx, stream, params, grads, V, B, L, in, nz, &h, cpl, scalars, logits, true))) return rc;
     float* gn = scalars ? scalars + SC_GRAD_NORM : nullptr;
     return cpg_clip_adam_step(ctx, stream, params, grads, m, v, V, &h, gn);
 }
@@ -828,14 +901,13 @@ int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, fl
              (void*)nb->word_drop, (void*)nb->out_keep, (void*)nb->z_prior_full, (void*)nb->z_prior_rf, (void*)nb->rf_w, (void*)nb->rf_b,
              hp->lr, hp->beta1, hp->beta2, hp->adam_eps, hp->clip_norm, hp->lambda_logvar_l1, hp->lambda_logvar_kl, hp->z_regu,
              hp->mmd_sigma, hp->rf_dim, hp->compute_full_mmd, hp->beta != 0.f ? 1 : 0, (unsigned long long)seed, p_word, p_out,
-             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc);
+             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows);
     StepGraph* g = find_graph(kb + std::string(scalars ? std::to_string((uintptr_t)scalars) : ""));
     StepDyn* dyn_dev = reinterpret_cast<StepDyn*>(ctx->ints + 32);
     const StepDyn dv = make_dyn(hp, noise_step);
     if (g->exec == nullptr) {
         if (g->seen < 1) { g->seen++; return body(); }          // first sight: eager (allocations, attribute set-up)
         // capture
-        ctx->join_pending[0] = ctx->join_pending[1] = ctx->join_pending[2] = false;
         const long long l0 = g_launch_count;
         if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return body(); }
         k_set_dyn<<<1, 32, 0, s>>>(dv, dyn_dev);

@@ -45,12 +45,15 @@ struct cpg_ctx {
     void* aux = nullptr;
     size_t aux_capacity = 0;
     int64_t launches = 0;
-    // side stream for the latency-bound loss kernels that only depend on (mu, logvar, z): they run under the
-    // decoder recurrence / decoder-output kernels of the main stream (fork / join with events; api_wae.cu)
+    // Two internal streams next to the caller's: the latency-bound loss kernels (statistics, RF-MMD, full-kernel MMD) on
+    // `side_stream`, weight-derived forms / ordered reductions / weight-gradient products on `aux_stream`; they run under
+    // the recurrences of the caller's stream.  Dependencies are events from a small rotating pool (api_wae.cu).
     void* side_stream = nullptr;
-    void* ev_fork[3] = {nullptr, nullptr, nullptr};  // [0] loss kernels, [1] decoder weight gradients, [2] late noise
-    void* ev_join[3] = {nullptr, nullptr, nullptr};
-    bool join_pending[3] = {false, false, false};
+    void* aux_stream = nullptr;
+    void* ev_pool[32] = {nullptr};
+    int ev_next = 0;
+    void* ev_noise = nullptr;      // noise generated on the side stream by cpg_fill_step_noise_overlapped, not yet joined
+    bool noise_pending = false;
 };
 
 namespace cpg {

@@ -36,7 +36,8 @@ k_dec_out(DecOutArgs a) {
     const int nrows = a.B * a.L;
     const bool want_grad = a.dh_out != nullptr;
     const bool has_mask = a.out_keep != nullptr;
-    const float inv_ntok = (a.ntok != nullptr && *a.ntok > 0.f) ? 1.0f / *a.ntok : 0.f;
+    const float ntok_v = a.ntok_i != nullptr ? (float)*a.ntok_i : (a.ntok != nullptr ? *a.ntok : 0.f);
+    const float inv_ntok = ntok_v > 0.f ? 1.0f / ntok_v : 0.f;
 
     for (int i = tid; i < VMAX * DEC_HP; i += DO_THREADS) Ws[(i / DEC_HP) * DSTR + (i % DEC_HP)] = a.fc_w[i];
     // phase B / C mapping: 2 rows x 4 classes per thread

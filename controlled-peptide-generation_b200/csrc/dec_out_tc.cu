@@ -158,7 +158,8 @@ k_dec_out_tc(DecOutArgs a) {
     const bool want_grad = a.dh_out != nullptr;
     const bool has_mask = a.out_keep != nullptr;
     const float sc = has_mask ? a.keep_scale : 1.0f;
-    const float inv_ntok = (a.ntok != nullptr && *a.ntok > 0.f) ? 1.0f / *a.ntok : 0.f;
+    const float ntok_v = a.ntok_i != nullptr ? (float)*a.ntok_i : (a.ntok != nullptr ? *a.ntok : 0.f);
+    const float inv_ntok = ntok_v > 0.f ? 1.0f / ntok_v : 0.f;
 
     // ---- one-time setup: zero every operand tile (K / M padding stays zero), then the two weight tiles
     for (int i = tid; i < OFF_KEEP / 16; i += NTH) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);

@@ -35,6 +35,7 @@ struct Derived {
     float* bhn_dec;       // [104]
     float* fc_w;          // [VMAX][104]  zero padded
     float* fc_b;          // [VMAX]
+    unsigned char* lat_tiles;   // pre-split operand tiles of latent_tc.cu (latent.h: LT_*), or null
 };
 size_t derived_floats(int n_vocab);
 
@@ -77,6 +78,11 @@ struct StepNoiseArgs {
     float p_word, p_out;
     float* eps; float* c; uint8_t* word_drop; uint8_t* out_keep; float* zp_full; float* zp_rf;
 };
+// part bits: what to generate
+constexpr int NOISE_WORD = 1;      // word-dropout mask (the token preparation needs it first)
+constexpr int NOISE_LATE = 2;      // z_prior x2, out-dropout mask (the bulk of the work)
+constexpr int NOISE_LATENT = 4;    // eps, c
+constexpr int NOISE_ALL = 7;
 void launch_step_noise(cudaStream_t s, const StepNoiseArgs& a, int part);
 
 void launch_prep_tokens(cudaStream_t s, const int64_t* tokens, const uint8_t* word_drop, int B, int L, int V,

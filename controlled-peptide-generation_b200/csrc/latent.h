@@ -57,6 +57,23 @@ int launch_mmd_full_tc2(cudaStream_t s, const float* z, const float* zp, int N, 
 void launch_mmd_full_grad(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float w, float* dz);
 extern int g_opt_mmd_tc;     // 0 = fp32 SIMT, 1 = persistent tcgen05 (default), 3 = one-tile-per-CTA tcgen05
 extern int g_sm_count;
+// tcgen05 versions of the dense layers around the latent code, fused with the element-wise work (latent_tc.cu).
+// Their weight operands are pre-split (leading terms | remainders) into the shared-memory tile image once per step by
+// k_prep_weights (prep.cu) and bulk-copied by the kernels; byte offsets inside Derived::lat_tiles:
+constexpr int LT_F1_ROWS = 208, LT_F1_K = 160;       // [q_mu | q_logvar] rows interleaved (n = 2 j | 2 j + 1), K-major, fp16 split
+constexpr int LT_F2_ROWS = 320, LT_F2_K = 112;       // W_ih[:,150:] (row = padded gate index, K = [z;c] index), K-major, fp16 split
+constexpr int LT_B1_ROWS = 112, LT_B1_K = 320;       // its transpose (row = [z;c] index, K = gate index), K-major, bf16 split
+constexpr int LT_B2_N = 160, LT_B2_K = 208;          // heads^T (n = hfin column, k = 2 j | 2 j + 1), MN-major, bf16 split
+constexpr size_t LT_F1_TERM = (size_t)LT_F1_ROWS * LT_F1_K * 2, LT_F2_TERM = (size_t)LT_F2_ROWS * LT_F2_K * 2;
+constexpr size_t LT_B1_TERM = (size_t)LT_B1_ROWS * LT_B1_K * 2, LT_B2_TERM = (size_t)LT_B2_N * LT_B2_K * 2;
+constexpr size_t LT_F1_OFF = 0, LT_F2_OFF = LT_F1_OFF + 2 * LT_F1_TERM, LT_B1_OFF = LT_F2_OFF + 2 * LT_F2_TERM;
+constexpr size_t LT_B2_OFF = LT_B1_OFF + 2 * LT_B1_TERM, LT_TILES_BYTES = LT_B2_OFF + 2 * LT_B2_TERM;
+bool latent_uses_tc(int B);
+extern int g_opt_latent_tc, g_opt_latent_rows;
+int launch_latent_fwd_tc(cudaStream_t s, const float* hfin, const float* bmu, const float* blv, const float* eps, const float* c,
+                         const unsigned char* tiles, int B, float* mu, float* logvar, float* z, float* zc, float* rowbias);
+int launch_latent_bwd_tc(cudaStream_t s, const float* drow, const float* dh0, const unsigned char* tiles, const LatentBwdArgs& lat,
+                         float* dhfin);
 void launch_compose_scalars(cudaStream_t s, const ComposeArgs& a);
 // data-parallel tail: extra floats all-reduced together with the flat gradient ([0] = NLL sum; rest reserved)
 constexpr int DP_TAIL = 8;

@@ -20,8 +20,8 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 
 
 // stream ids: 16*step + {0: normals, 1: c, 2: word dropout, 3: out dropout}
-// part: bit 0 = what the forward needs first (eps, c, word dropout), bit 1 = what is only needed later (z_prior x2,
-// out-dropout mask -- the bulk of the work)
+// part: NOISE_WORD = word dropout (needed first), NOISE_LATENT = eps, c, NOISE_LATE = what is only needed later
+// (z_prior x2, out-dropout mask -- the bulk of the work)
 __global__ void k_step_noise(StepNoiseArgs a, int part, const StepDyn* __restrict__ dyn) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_lat = (int64_t)a.B * ZD;
@@ -29,26 +29,26 @@ __global__ void k_step_noise(StepNoiseArgs a, int part, const StepDyn* __restric
     const int64_t n_out4 = ((int64_t)a.B * a.L * DEC_H + 3) / 4;
     const uint32_t base = (dyn != nullptr ? dyn->noise_step : a.step) * 16u;
     uint32_t r[4];
-    if (i < n_lat) {
+    if (i < n_lat && (part & (NOISE_LATENT | NOISE_LATE))) {
         Philox::gen(a.seed, (uint64_t)i, base + 0, r);
         float n0, n1, n2, n3;
         box_muller(r[0], r[1], n0, n1);
         box_muller(r[2], r[3], n2, n3);
-        if (a.eps && (part & 1)) a.eps[i] = n0;
-        if (a.zp_full && (part & 2)) a.zp_full[i] = n1;
-        if (a.zp_rf && (part & 2)) a.zp_rf[i] = n2;
+        if (a.eps && (part & NOISE_LATENT)) a.eps[i] = n0;
+        if (a.zp_full && (part & NOISE_LATE)) a.zp_full[i] = n1;
+        if (a.zp_rf && (part & NOISE_LATE)) a.zp_rf[i] = n2;
     }
-    if (i < a.B && a.c && (part & 1)) {
+    if (i < a.B && a.c && (part & NOISE_LATENT)) {
         Philox::gen(a.seed, (uint64_t)i, base + 1, r);
         int k = r[0] >> 31;                                 // Cat([.5, .5]) one-hot (model.py:121-126)
         a.c[i * CD + 0] = k == 0 ? 1.f : 0.f;
         a.c[i * CD + 1] = k == 1 ? 1.f : 0.f;
     }
-    if (i < n_tok && a.word_drop && (part & 1)) {
+    if (i < n_tok && a.word_drop && (part & NOISE_WORD)) {
         Philox::gen(a.seed, (uint64_t)i, base + 2, r);
         a.word_drop[i] = u32_to_unit_open(r[0]) < a.p_word ? 1 : 0;      // decoder.py:124-127
     }
-    if (i < n_out4 && a.out_keep && (part & 2)) {
+    if (i < n_out4 && a.out_keep && (part & NOISE_LATE)) {
         Philox::gen(a.seed, (uint64_t)i, base + 3, r);
         const int64_t n_out = (int64_t)a.B * a.L * DEC_H;
 #pragma unroll
@@ -79,9 +79,11 @@ __global__ void k_fill_random(uint64_t seed, uint32_t stream, int kind, float sc
 }
 
 void launch_step_noise(cudaStream_t s, const StepNoiseArgs& a, int part) {
-    int64_t n = (int64_t)a.B * ZD;                                         // normals (both parts)
-    if (part & 1) n = std::max<int64_t>(n, (int64_t)a.B * a.L);
-    if (part & 2) n = std::max<int64_t>(n, ((int64_t)a.B * a.L * DEC_H + 3) / 4);
+    int64_t n = 0;
+    if (part & (NOISE_LATENT | NOISE_LATE)) n = (int64_t)a.B * ZD;         // normals
+    if (part & NOISE_LATENT) n = std::max<int64_t>(n, a.B);
+    if (part & NOISE_WORD) n = std::max<int64_t>(n, (int64_t)a.B * a.L);
+    if (part & NOISE_LATE) n = std::max<int64_t>(n, ((int64_t)a.B * a.L * DEC_H + 3) / 4);
     CPG_LAUNCH(k_step_noise, (unsigned)((n + 255) / 256), 256, 0, s, a, part, g_dyn);
 }
 
@@ -98,7 +100,7 @@ int cpg_fill_step_noise(cpg_ctx* ctx, cpg_stream stream, uint64_t seed, uint32_t
     StepNoiseArgs a;
     a.seed = seed; a.step = step; a.B = B; a.L = L; a.p_word = p_word; a.p_out = p_out;
     a.eps = eps; a.c = c; a.word_drop = word_drop; a.out_keep = out_keep; a.zp_full = z_prior_full; a.zp_rf = z_prior_rf;
-    launch_step_noise((cudaStream_t)stream, a, 3);
+    launch_step_noise((cudaStream_t)stream, a, NOISE_ALL);
     return check_launch("cpg_fill_step_noise");
 }
 

@@ -6,7 +6,10 @@
 // vocabulary is tiny (V <= 32), the embedding gather and the input projection
 // x_t W_ih^T + b_ih collapse into a token -> gate table T = E W_ih[:, :150]^T + b
 // that is rebuilt from the current weights every step (2 V 150 3H flop).
-#include "kernels.h"
+#include "latent.h"
+#ifndef CPG_EMU
+#include "tc_gru.cuh"
+#endif
 
 namespace cpg {
 
@@ -79,6 +82,7 @@ struct PrepArgs {
     const float* enc_wih[2]; const float* enc_whh[2]; const float* enc_bih[2]; const float* enc_bhh[2];
     const float* dec_wih; const float* dec_whh; const float* dec_bih; const float* dec_bhh;
     const float* fc_w; const float* fc_b;
+    const float* wmu; const float* wlv;
     Derived d;
     int V;
 };
@@ -150,13 +154,72 @@ __global__ void k_prep_weights(PrepArgs a) {
             a.d.whh_dec[i] = ok ? a.dec_whh[(size_t)g * DEC_H + k] : 0.f;
             a.d.wizc[i] = ok ? a.dec_wih[(size_t)g * DEC_IN + EMB + k] : 0.f;
         }
-    } else {                            // fc padded [VMAX][104]
+    } else if (task == 7) {             // fc padded [VMAX][104]
         for (int i = t0; i < VMAX * DEC_HP; i += stride) {
             int v = i / DEC_HP, j = i % DEC_HP;
             a.d.fc_w[i] = (v < V && j < DEC_H) ? a.fc_w[(size_t)v * DEC_H + j] : 0.f;
         }
         for (int i = t0; i < VMAX; i += stride) a.d.fc_b[i] = (i < V) ? a.fc_b[i] : 0.f;
     }
+#ifndef CPG_EMU
+    // ---- pre-split operand tiles of the tcgen05 dense layers around the latent code (latent_tc.cu; geometry in latent.h):
+    // one thread per 16-byte chunk (8 consecutive K, or 8 consecutive N of an MN-major tile) of the shared-memory image
+    else if (task == 8) {               // heads, K-major [208][160]: row n = 2 j (q_mu) | 2 j + 1 (q_logvar); fp16 split
+        for (int i = t0; i < LT_F1_ROWS * (LT_F1_K / 8); i += stride) {
+            const int kc = i % (LT_F1_K / 8), r = i / (LT_F1_K / 8), j = r >> 1;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = j < ZD ? ((r & 1) ? a.wlv : a.wmu)[(size_t)j * (2 * ENC_H) + kc * 8 + e] : 0.f;
+            uint4 h, l;
+            split2h(x[0], x[1], h.x, l.x); split2h(x[2], x[3], h.y, l.y); split2h(x[4], x[5], h.z, l.z); split2h(x[6], x[7], h.w, l.w);
+            const size_t off = LT_F1_OFF + (size_t)kc * (LT_F1_ROWS * 16) + (r >> 3) * 128 + (r & 7) * 16;
+            *reinterpret_cast<uint4*>(a.d.lat_tiles + off) = h;
+            *reinterpret_cast<uint4*>(a.d.lat_tiles + off + LT_F1_TERM) = l;
+        }
+    } else if (task == 9) {             // W_ih[:,150:], K-major [320][112]: row = padded gate index, K = [z;c] index; fp16 split
+        for (int i = t0; i < LT_F2_ROWS * (LT_F2_K / 8); i += stride) {
+            const int kc = i % (LT_F2_K / 8), r = i / (LT_F2_K / 8), gate = r / DEC_HP, j = r % DEC_HP;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = kc * 8 + e;
+                x[e] = (gate < 3 && j < DEC_H && k < DEC_H) ? a.dec_wih[(size_t)(gate * DEC_H + j) * DEC_IN + EMB + k] : 0.f;
+            }
+            uint4 h, l;
+            split2h(x[0], x[1], h.x, l.x); split2h(x[2], x[3], h.y, l.y); split2h(x[4], x[5], h.z, l.z); split2h(x[6], x[7], h.w, l.w);
+            const size_t off = LT_F2_OFF + (size_t)kc * (LT_F2_ROWS * 16) + (r >> 3) * 128 + (r & 7) * 16;
+            *reinterpret_cast<uint4*>(a.d.lat_tiles + off) = h;
+            *reinterpret_cast<uint4*>(a.d.lat_tiles + off + LT_F2_TERM) = l;
+        }
+    } else if (task == 10) {            // (W_ih[:,150:])^T, K-major [112][320]: row = [z;c] index, K = padded gate index; bf16 split
+        for (int i = t0; i < LT_B1_ROWS * (LT_B1_K / 8); i += stride) {
+            const int r = i % LT_B1_ROWS, kc = i / LT_B1_ROWS;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int g = kc * 8 + e, gate = g / DEC_HP, j = g % DEC_HP;
+                x[e] = (gate < 3 && j < DEC_H && r < DEC_H) ? a.dec_wih[(size_t)(gate * DEC_H + j) * DEC_IN + EMB + r] : 0.f;
+            }
+            uint4 h, l;
+            split8(x, h, l);
+            const size_t off = LT_B1_OFF + (size_t)kc * (LT_B1_ROWS * 16) + (r >> 3) * 128 + (r & 7) * 16;
+            *reinterpret_cast<uint4*>(a.d.lat_tiles + off) = h;
+            *reinterpret_cast<uint4*>(a.d.lat_tiles + off + LT_B1_TERM) = l;
+        }
+    } else if (task == 11) {            // heads^T, MN-major: element (n = hfin column, k = 2 j | 2 j + 1) = W_mu[j][n] | W_logvar[j][n]; bf16 split
+        for (int i = t0; i < (LT_B2_N / 8) * LT_B2_K; i += stride) {
+            const int nc = i % (LT_B2_N / 8), k = i / (LT_B2_N / 8), j = k >> 1;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = j < ZD ? ((k & 1) ? a.wlv : a.wmu)[(size_t)j * (2 * ENC_H) + nc * 8 + e] : 0.f;
+            uint4 h, l;
+            split8(x, h, l);
+            const size_t off = LT_B2_OFF + (size_t)nc * (LT_B2_K * 16) + (k >> 3) * 128 + (k & 7) * 16;
+            *reinterpret_cast<uint4*>(a.d.lat_tiles + off) = h;
+            *reinterpret_cast<uint4*>(a.d.lat_tiles + off + LT_B2_TERM) = l;
+        }
+    }
+#endif
 }
 
 void launch_prep_weights(cudaStream_t s, const float* p, const ParamLayout& l, int V, const Derived& d) {
@@ -169,9 +232,11 @@ void launch_prep_weights(cudaStream_t s, const float* p, const ParamLayout& l, i
     a.dec_wih = p + l.off[P_DEC_WIH]; a.dec_whh = p + l.off[P_DEC_WHH];
     a.dec_bih = p + l.off[P_DEC_BIH]; a.dec_bhh = p + l.off[P_DEC_BHH];
     a.fc_w = p + l.off[P_FC_W]; a.fc_b = p + l.off[P_FC_B];
+    a.wmu = p + l.off[P_QMU_W]; a.wlv = p + l.off[P_QLV_W];
     a.d = d;
     a.V = V;
-    CPG_LAUNCH(k_prep_weights, dim3(120, 8), 256, 0, s, a);      // 960 warps per table task: ~8 outputs per warp
+    // 960 warps per table task: ~8 outputs per warp; tasks 8-11 (operand tiles of latent_tc.cu) only where they are used
+    CPG_LAUNCH(k_prep_weights, dim3(120, d.lat_tiles != nullptr ? 12 : 8), 256, 0, s, a);
 }
 
 }  // namespace cpg

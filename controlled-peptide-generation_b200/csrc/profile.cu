@@ -24,11 +24,14 @@ const char* shape_label(const char* name, int M, int N, int K, int nprod) {
 }
 
 #ifndef CPG_EMU
-struct ProfRec { const char* label; cudaEvent_t a, b; };
+struct ProfRec { const char* label; cudaEvent_t a, b; cudaStream_t s; };
 static std::vector<ProfRec> g_recs;
 static std::vector<cudaEvent_t> g_pool;
 static cudaEvent_t g_pending_a = nullptr;
 static const char* g_pending_label = nullptr;
+
+struct TlRec { const char* label; float start_ms, dur_ms; int stream; };
+static std::vector<TlRec> g_timeline;
 
 static cudaEvent_t take_event() {
     if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
@@ -44,7 +47,7 @@ void prof_begin(const char* label, cudaStream_t s) {
 void prof_end(cudaStream_t s) {
     cudaEvent_t b = take_event();
     cudaEventRecord(b, s);
-    g_recs.push_back(ProfRec{g_pending_label, g_pending_a, b});
+    g_recs.push_back(ProfRec{g_pending_label, g_pending_a, b, s});
 }
 #endif
 
@@ -78,6 +81,18 @@ int cpg_profile_read(char* names, int name_stride, float* total_ms, int* counts,
         g_pool.push_back(r.a);
         g_pool.push_back(r.b);
     }
+    // keep the raw records (start offset from the first one, duration) for cpg_profile_timeline
+    g_timeline.clear();
+    std::vector<cudaStream_t> streams;
+    for (auto& r : g_recs) {
+        int si = 0;
+        while (si < (int)streams.size() && streams[si] != r.s) ++si;
+        if (si == (int)streams.size()) streams.push_back(r.s);
+        float t0 = 0.f, dt = 0.f;
+        cudaEventElapsedTime(&t0, g_recs.front().a, r.a);
+        cudaEventElapsedTime(&dt, r.a, r.b);
+        g_timeline.push_back(TlRec{r.label, t0, dt, si});
+    }
     g_recs.clear();
     int n = 0;
     for (auto& name : order) {
@@ -86,6 +101,25 @@ int cpg_profile_read(char* names, int name_stride, float* total_ms, int* counts,
         names[(size_t)n * name_stride + name_stride - 1] = 0;
         total_ms[n] = (float)acc[name].first;
         counts[n] = acc[name].second;
+        ++n;
+    }
+    return n;
+#endif
+}
+
+// The raw records of the launches seen by the last cpg_profile_read, in launch order: label, start offset from the first
+// record and duration (ms), both from CUDA events on the launching streams.  Returns the number of records written.
+int cpg_profile_timeline(char* names, int name_stride, float* start_ms, float* dur_ms, int cap) {
+#ifdef CPG_EMU
+    (void)names; (void)name_stride; (void)start_ms; (void)dur_ms; (void)cap;
+    return 0;
+#else
+    int n = 0;
+    for (auto& r : g_timeline) {
+        if (n >= cap) break;
+        snprintf(names + (size_t)n * name_stride, name_stride, "S%d %s", r.stream, r.label);   // S0 = first stream seen
+        start_ms[n] = r.start_ms;
+        dur_ms[n] = r.dur_ms;
         ++n;
     }
     return n;

@@ -3,6 +3,7 @@
 #pragma once
 #ifndef CPG_EMU
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 namespace cpg {
@@ -84,6 +85,14 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
     split2(x[2], x[3], hi.y, lo.y);
     split2(x[4], x[5], hi.z, lo.z);
     split2(x[6], x[7], hi.w, lo.w);
+}
+// fp16 flavour of the split (11 + 11 mantissa bits; for operands of bounded magnitude)
+__device__ __forceinline__ void split2h(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 // Gate non-linearities straight on the SFU (ex2.approx + rcp.approx, flush-to-zero forms: no denormal
 // fix-up code around them); absolute error <= ~6e-7 like the SIMT kernels' versions.

@@ -347,6 +347,9 @@ int cpg_logreg_stats_len(void);
  *   "dec_out_tensor_core" 1 (default) tcgen05 decoder-output layer when B*L >= 8192, 2 always, 0 never
  *   "bptt_fused"          1 (default) on the tcgen05 path the BPTT kernels also contract dW_hh and the token-table gradient
  *                         (the gate-gradient planes never reach HBM), 0 = separate tf32 weight-gradient kernels
+ *   "latent_tensor_core"  1 (default) the dense layers around the latent code (heads, [z;c] projection and their backward) as two
+ *                         fused split-bf16 tcgen05 kernels when B >= 1024, 2 always, 0 fp32 SIMT GEMMs + element-wise kernels
+ *   "latent_tile_rows"    64 (default) | 128: batch rows per CTA of the forward latent kernel
  *   "cuda_graph"          1 (default) cpg_wae_train_step_philox replays a captured CUDA graph of the iteration, 0 = eager launches
  *   "side_stream"         1 (default) loss / weight-gradient kernels overlap the recurrences on an internal stream
  *                         (event fork/join inside each call; results identical), 0 everything on the caller's stream */
@@ -357,6 +360,9 @@ int cpg_profile_enable(int on);
 /* Synchronises the device; fills names[i*name_stride..], total_ms[i], counts[i] per kernel label in first-launch
  * order and clears the records.  Returns the number of labels written (<= cap). */
 int cpg_profile_read(char* names, int name_stride, float* total_ms, int* counts, int cap);
+/* The launches seen by the last cpg_profile_read, unaggregated and in launch order: start offset from the first launch
+ * and duration in ms (events on the launching streams, so overlap between the two streams is visible). */
+int cpg_profile_timeline(char* names, int name_stride, float* start_ms, float* dur_ms, int cap);
 
 #ifdef __cplusplus
 }

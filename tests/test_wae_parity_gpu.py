@@ -54,10 +54,12 @@ def test_forward_tensor_core_recurrences_match_oracle(eng, batch):
     try:
         _lib.set_option('gru_tensor_core', 2)
         _lib.set_option('dec_out_tensor_core', 2)
+        _lib.set_option('latent_tensor_core', 2)
         test_forward_matches_oracle(eng, batch)
     finally:
         _lib.set_option('gru_tensor_core', 1)
         _lib.set_option('dec_out_tensor_core', 1)
+        _lib.set_option('latent_tensor_core', 1)
 
 
 def test_inference_forward_matches_reference_golden(eng):
@@ -111,7 +113,7 @@ def test_train_iterations_match_reference_golden(eng, batch):
 
 
 @pytest.mark.parametrize('batch,z_regu', [(6, 'mmdrf'), (40, 'mmdrf'), (40, 'kl'), (131, 'mmdrf'), (40, 'mmd'), (131, 'mmd')])
-def test_train_step_matches_oracle(eng, batch, z_regu, max_outliers=0):
+def test_train_step_matches_oracle(eng, batch, z_regu, max_outliers=0, resync=False):
     dev = torch.device('cuda')
     p = ow.random_params(V, seed=11)
     st = eng.FlatState(V, dev)
@@ -135,6 +137,14 @@ def test_train_step_matches_oracle(eng, batch, z_regu, max_outliers=0):
             scale = float(want[k].abs().max()) + 1e-12
             np.testing.assert_allclose(got[k].cpu().numpy(), want[k].numpy(), rtol=1e-3, atol=1e-4 * scale, err_msg=k)
         assert_params_close(st.views(st.params), p, want, 'it%d' % it, max_outliers=max_outliers)
+        if resync:
+            # the next iteration is compared from IDENTICAL parameters: Adam turns rounding-level gradient differences of
+            # near-zero gradients into 1e-5-level parameter differences, and the L1 term's sign(logvar) is discontinuous,
+            # so that one flipped element moves grad_norm by more than the 1e-4 bar (seen at B = 131, 2 of 13,100 elements)
+            got_p = st.views(st.params)
+            for k in p:
+                if k in got_p:
+                    p[k] = got_p[k].detach().cpu().clone()
 
 
 @pytest.mark.parametrize('batch,z_regu', [(6, 'mmdrf'), (40, 'kl'), (131, 'mmdrf')])
@@ -147,10 +157,12 @@ def test_train_step_tensor_core_recurrences_match_oracle(eng, batch, z_regu):
     try:
         _lib.set_option('gru_tensor_core', 2)
         _lib.set_option('dec_out_tensor_core', 2)
-        test_train_step_matches_oracle(eng, batch, z_regu, max_outliers=3)
+        _lib.set_option('latent_tensor_core', 2)
+        test_train_step_matches_oracle(eng, batch, z_regu, max_outliers=3, resync=True)
     finally:
         _lib.set_option('gru_tensor_core', 1)
         _lib.set_option('dec_out_tensor_core', 1)
+        _lib.set_option('latent_tensor_core', 1)
 
 
 def test_full_batch_4096_matches_reference_golden(eng):
@@ -400,7 +412,7 @@ def test_auto_tensor_core_paths_match_simt_at_ragged_large_batches(eng, batch):
     p = ow.random_params(V, seed=31)
     tokens = ow.synthetic_tokens(batch, V, seed=32).to(dev)
     noise = dev_noise(ow.draw_noise(batch, seed=33), dev)
-    opts = ('gru_tensor_core', 'dec_out_tensor_core', 'wgrad_tensor_core', 'mmd_tensor_core')
+    opts = ('gru_tensor_core', 'dec_out_tensor_core', 'wgrad_tensor_core', 'mmd_tensor_core', 'latent_tensor_core')
     out = {}
     try:
         for flag in (0, 1):
