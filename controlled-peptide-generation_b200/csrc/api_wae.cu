@@ -207,14 +207,18 @@ constexpr int NEV = 32;
 static bool side_ready(cpg_ctx* ctx) {
     if (!g_opt_side_stream) return false;
     if (ctx->side_stream == nullptr) {
-        cudaStream_t q[2];
+        cudaStream_t q[3];
         cudaEvent_t e[NEV + 1];
-        bool ok = cudaStreamCreateWithFlags(&q[0], cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaStreamCreateWithFlags(&q[1], cudaStreamNonBlocking) == cudaSuccess;
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        bool ok = cudaStreamCreateWithPriority(&q[0], cudaStreamNonBlocking, least) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&q[1], cudaStreamNonBlocking, least) == cudaSuccess &&
+                  cudaStreamCreateWithPriority(&q[2], cudaStreamNonBlocking, greatest) == cudaSuccess;
         for (int i = 0; i <= NEV && ok; ++i) ok = cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) == cudaSuccess;
         if (!ok) { cudaGetLastError(); return false; }
         ctx->side_stream = q[0];
         ctx->aux_stream = q[1];
+        ctx->chain_stream = q[2];
         for (int i = 0; i < NEV; ++i) ctx->ev_pool[i] = e[i];
         ctx->ev_noise = e[NEV];
     }
@@ -273,14 +277,29 @@ int g_opt_bptt_fused = 1;
 // Returns the mark "mu, logvar, z are final" (made on the caller's lane right after the latent layers) for the loss
 // statistics of the training step; null when the lanes are off.
 static Mark forward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, const ParamLayout& lay, int V, int B, int L,
-                         const cpg_wae_inputs* in, float* mu, float* logvar, float* z, bool stash, bool encoder_only) {
+                         const cpg_wae_inputs* in, float* mu, float* logvar, float* z, bool stash, bool encoder_only,
+                         const StepNoiseArgs* gen = nullptr) {
     Workspace& w = ctx->ws;
     cudaStream_t s = ln.m;
     // the derived weight forms only depend on the parameters: their lane runs beside the token preparation
     order(ctx, ln, s, ln.t);
     launch_prep_weights(ln.t, params, lay, V, w.d);
     const Mark weights_ready = mark(ctx, ln, ln.t);
-    launch_prep_tokens(s, in->tokens, in->word_drop, B, L, V, w.tok, w.tokd, w.tgt, ctx->ints, ctx->ints + 1);
+    // gen: this step's noise is drawn here -- the word-dropout mask inside the token preparation, the rest on lane s
+    // once the preparation is through (its first reader, the latent layers, joins it)
+    launch_prep_tokens(s, in->tokens, in->word_drop, B, L, V, w.tok, w.tokd, w.tgt, ctx->ints, ctx->ints + 1, gen);
+    if (gen != nullptr) {
+        if (ln.on) {
+            order(ctx, ln, s, ln.s);                // also: earlier readers of the noise buffers (previous iteration) are on `s`
+            launch_step_noise(ln.s, *gen, NOISE_LATENT | NOISE_LATE);
+#ifndef CPG_EMU
+            cudaEventRecord((cudaEvent_t)ctx->ev_noise, ln.s);
+#endif
+            ctx->noise_pending = true;
+        } else {
+            launch_step_noise(s, *gen, NOISE_LATENT | NOISE_LATE);
+        }
+    }
     wait_mark(s, weights_ready);
     GruSeq enc[2];
     for (int d = 0; d < 2; ++d) {
@@ -486,6 +505,7 @@ static AdamHyper adam_hyper(const cpg_train_hparams* hp) {
 
 // ------------------------------------------------------------------------------- captured iteration
 const StepDyn* g_dyn = nullptr;
+int g_opt_chain_priority = 1;         // 1: the fused step's dependent chain runs on the highest-priority internal stream
 int g_opt_graph = 1;                  // 1: cpg_wae_train_step_philox replays a captured CUDA graph of the iteration
 __global__ void k_set_dyn(StepDyn v, StepDyn* __restrict__ dst) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v;
@@ -580,8 +600,10 @@ int cpg_destroy(cpg_ctx* c) {
     if (c->side_stream) {
         cudaStreamSynchronize((cudaStream_t)c->side_stream);
         cudaStreamSynchronize((cudaStream_t)c->aux_stream);
+        cudaStreamSynchronize((cudaStream_t)c->chain_stream);
         cudaStreamDestroy((cudaStream_t)c->side_stream);
         cudaStreamDestroy((cudaStream_t)c->aux_stream);
+        cudaStreamDestroy((cudaStream_t)c->chain_stream);
         for (int k = 0; k < NEV; ++k) cudaEventDestroy((cudaEvent_t)c->ev_pool[k]);
         cudaEventDestroy((cudaEvent_t)c->ev_noise);
     }
@@ -712,7 +734,7 @@ int64_t cpg_coupled_count(int rf_dim) { return 8 + 2 * (int64_t)rf_dim; }
 // fused single-GPU step leaves them on lane s, where everything that consumes them runs.
 static int phase1_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int B, int L,
                        const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
-                       float* coupled, float* mu, float* logvar, float* z, bool join) {
+                       float* coupled, float* mu, float* logvar, float* z, bool join, const StepNoiseArgs* gen = nullptr) {
     int rc = check_dims(V, B, L);
     if (rc) return rc;
     if (!ctx || !params || !in || !nz || !hp || !coupled || !in->tokens || !in->c) { set_error("cpg_wae_step_phase1: null argument"); return CPG_EINVAL; }
@@ -725,19 +747,22 @@ static int phase1_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, int
     ParamLayout lay = make_layout(V);
     const Lanes ln = lanes(ctx, s);
     cudaStream_t q = ln.s;
+    // explicit noise inputs are ordered before the caller's lane; noise of cpg_fill_step_noise_overlapped / `gen` is
+    // produced on lane s itself
+    if (!ctx->noise_pending && gen == nullptr) order(ctx, ln, s, q);
+    const Mark latent_ready = forward_impl(ctx, ln, params, lay, V, B, L, in, w.mu, w.logvar, w.z, true, false, gen);
     // the prior's random features do not depend on the batch: lane s, under the encoder recurrence
-    // (z_prior_rf: produced on lane s by cpg_fill_step_noise_overlapped, or an input ordered before the caller's lane)
-    if (!ctx->noise_pending) order(ctx, ln, s, q);
     launch_sgemm(q, B, R, ZD, 1.f, nz->z_prior_rf, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre2, R, nullptr, 1, nullptr);
     launch_rf_colsum(q, w.rf_pre2, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8 + R);
-    const Mark latent_ready = forward_impl(ctx, ln, params, lay, V, B, L, in, w.mu, w.logvar, w.z, true, false);
-    // local statistics that couple the batch: token count, latent sums, RF feature sums -- they depend on
+    // local statistics that couple the batch: RF feature sums, token count, latent sums -- they depend on
     // (mu, logvar, z) only and run on lane s under the decoder recurrence
     wait_mark(q, latent_ready);
-    launch_int_to_float(q, ctx->ints, coupled + 0, 1);
-    launch_latent_stats(q, w.mu, w.logvar, B, w.lat_part, w.lat_nparts, coupled + 2);
     launch_sgemm(q, B, R, ZD, 1.f, w.z, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre1, R, nullptr, 1, nullptr);
     launch_rf_colsum(q, w.rf_pre1, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8);
+    if (join) {                                     // (the fused step runs these after the RF gradient chain, see phase2_impl)
+        launch_int_to_float(q, ctx->ints, coupled + 0, 1);
+        launch_latent_stats(q, w.mu, w.logvar, B, w.lat_part, w.lat_nparts, coupled + 2);
+    }
     if (join) order(ctx, ln, q, s);
     if (mu) dev_copy(mu, w.mu, (size_t)B * ZD * 4, s);
     if (logvar) dev_copy(logvar, w.logvar, (size_t)B * ZD * 4, s);
@@ -797,6 +822,10 @@ static int phase2_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, flo
             dz_rf = w.dz_rf;
         }
         dz_ready = mark(ctx, ln, q);
+        if (fused_step) {                           // log-only statistics: after the chain the latent backward waits for
+            launch_int_to_float(q, ctx->ints, const_cast<float*>(coupled) + 0, 1);
+            launch_latent_stats(q, w.mu, w.logvar, B, w.lat_part, w.lat_nparts, const_cast<float*>(coupled) + 2);
+        }
         if (want_mmd)
             if ((rc = launch_mmd_full(q, w.z, nz->z_prior_full, B, hp->mmd_sigma, w.mmd_ws, w.mmd_out))) return rc;
     }
@@ -854,19 +883,36 @@ int cpg_clip_adam_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* gr
     return check_launch("cpg_clip_adam_step");
 }
 
-int cpg_wae_train_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* m, float* v, int V, int B,
-                       int L, const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
-                       float* scalars, float* mu, float* logvar, float* z, float* logits) {
+// The fused single-GPU iteration.  The dependent chain runs on the library's highest-priority stream (forked from and joined
+// to the caller's), so that its kernels are dispatched ahead of the co-running loss / reduction kernels of the other lanes.
+static int train_step_impl(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* m, float* v, int V, int B,
+                           int L, const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
+                           float* scalars, float* mu, float* logvar, float* z, float* logits, const StepNoiseArgs* gen) {
     if (!ctx || !hp) { set_error("cpg_wae_train_step: null argument"); return CPG_EINVAL; }
     cpg_train_hparams h = *hp;
     h.global_batch = B;
     int rc = ensure_workspace(ctx, B, L, V, h.rf_dim, (cudaStream_t)stream);
     if (rc) return rc;
     float* cpl = ctx->ws.coupled;
-    if ((rc = phase1_impl(ctx, stream, params, V, B, L, in, nz, &h, cpl, mu, logvar, z, false))) return rc;
-    if ((rc = phase2_impl(ctx, stream, params, grads, V, B, L, in, nz, &h, cpl, scalars, logits, true))) return rc;
+    cudaStream_t caller = (cudaStream_t)stream, chain = caller;
+    const Lanes l0 = lanes(ctx, caller);
+    if (l0.on && g_opt_chain_priority && ctx->chain_stream != nullptr) {
+        chain = (cudaStream_t)ctx->chain_stream;
+        noise_join(ctx, caller);
+        order(ctx, l0, caller, chain);
+    }
+    if ((rc = phase1_impl(ctx, chain, params, V, B, L, in, nz, &h, cpl, mu, logvar, z, false, gen))) return rc;
+    if ((rc = phase2_impl(ctx, chain, params, grads, V, B, L, in, nz, &h, cpl, scalars, logits, true))) return rc;
     float* gn = scalars ? scalars + SC_GRAD_NORM : nullptr;
-    return cpg_clip_adam_step(ctx, stream, params, grads, m, v, V, &h, gn);
+    rc = cpg_clip_adam_step(ctx, chain, params, grads, m, v, V, &h, gn);
+    order(ctx, l0, chain, caller);
+    return rc;
+}
+
+int cpg_wae_train_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* m, float* v, int V, int B,
+                       int L, const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
+                       float* scalars, float* mu, float* logvar, float* z, float* logits) {
+    return train_step_impl(ctx, stream, params, grads, m, v, V, B, L, in, nz, hp, scalars, mu, logvar, z, logits, nullptr);
 }
 
 // Philox noise + the whole iteration as ONE call; from the third call with the same buffers and settings on, a replay
@@ -884,11 +930,13 @@ int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, fl
     in.p_out_dropout = p_out;
     cpg_loss_noise nz;
     nz.z_prior_full = nb->z_prior_full; nz.z_prior_rf = nb->z_prior_rf; nz.rf_w = nb->rf_w; nz.rf_b = nb->rf_b;
+    if (B < 1 || L < 1) { set_error("cpg_wae_train_step_philox: bad argument"); return CPG_EINVAL; }
+    StepNoiseArgs gen;
+    gen.seed = seed; gen.step = noise_step; gen.B = B; gen.L = L; gen.p_word = p_word; gen.p_out = p_out;
+    gen.eps = nb->eps; gen.c = nb->c; gen.word_drop = nb->word_drop; gen.out_keep = nb->out_keep;
+    gen.zp_full = nb->z_prior_full; gen.zp_rf = nb->z_prior_rf;
     auto body = [&]() -> int {
-        int rc = cpg_fill_step_noise_overlapped(ctx, stream, seed, noise_step, B, L, p_word, p_out, nb->eps, nb->c, nb->word_drop,
-                                                nb->out_keep, nb->z_prior_full, nb->z_prior_rf);
-        if (rc) return rc;
-        return cpg_wae_train_step(ctx, stream, params, grads, m, v, V, B, L, &in, &nz, hp, scalars, nullptr, nullptr, nullptr, nullptr);
+        return train_step_impl(ctx, stream, params, grads, m, v, V, B, L, &in, &nz, hp, scalars, nullptr, nullptr, nullptr, nullptr, &gen);
     };
 #ifdef CPG_EMU
     return body();
@@ -901,7 +949,7 @@ int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, fl
              (void*)nb->word_drop, (void*)nb->out_keep, (void*)nb->z_prior_full, (void*)nb->z_prior_rf, (void*)nb->rf_w, (void*)nb->rf_b,
              hp->lr, hp->beta1, hp->beta2, hp->adam_eps, hp->clip_norm, hp->lambda_logvar_l1, hp->lambda_logvar_kl, hp->z_regu,
              hp->mmd_sigma, hp->rf_dim, hp->compute_full_mmd, hp->beta != 0.f ? 1 : 0, (unsigned long long)seed, p_word, p_out,
-             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows);
+             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority);
     StepGraph* g = find_graph(kb + std::string(scalars ? std::to_string((uintptr_t)scalars) : ""));
     StepDyn* dyn_dev = reinterpret_cast<StepDyn*>(ctx->ints + 32);
     const StepDyn dv = make_dyn(hp, noise_step);
@@ -935,7 +983,7 @@ int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, fl
             if (cudaGraphKernelNodeGetParams(nd, &kp) == cudaSuccess && kp.func == (void*)k_set_dyn) { g->dyn_node = nd; break; }
         }
         cudaGraphExec_t ex = nullptr;
-        if (g->dyn_node == nullptr || cudaGraphInstantiate(&ex, graph, 0) != cudaSuccess) {
+        if (g->dyn_node == nullptr || cudaGraphInstantiate(&ex, graph, cudaGraphInstantiateFlagUseNodePriority) != cudaSuccess) {
             cudaGetLastError();
             cudaGraphDestroy(graph);
             g->seen = -1000000;

@@ -50,6 +50,7 @@ struct cpg_ctx {
     // the recurrences of the caller's stream.  Dependencies are events from a small rotating pool (api_wae.cu).
     void* side_stream = nullptr;
     void* aux_stream = nullptr;
+    void* chain_stream = nullptr;  // highest-priority stream for the dependent chain of the fused step (forked from / joined to the caller's)
     void* ev_pool[32] = {nullptr};
     int ev_next = 0;
     void* ev_noise = nullptr;      // noise generated on the side stream by cpg_fill_step_noise_overlapped, not yet joined

@@ -49,9 +49,13 @@ size_t derived_floats(int V) {
 //   tokd : decoder input after word dropout (mask==1 -> <unk>)
 //   tgt  : next-token targets, <pad> appended (losses.py:25-26)
 //   ntok : number of non-<pad> targets of this batch (CE denominator, losses.py:27-30)
+// gen != 0: the word-dropout mask is drawn here (the arithmetic of k_step_noise, stream id 16 * step + 2) and also
+// written to word_drop_out, instead of being read from word_drop.
 __global__ void k_prep_tokens(const int64_t* __restrict__ tokens, const uint8_t* __restrict__ word_drop,
                               int B, int L, int V, uint8_t* __restrict__ tok, uint8_t* __restrict__ tokd,
-                              uint8_t* __restrict__ tgt, int* __restrict__ ntok, int* __restrict__ err) {
+                              uint8_t* __restrict__ tgt, int* __restrict__ ntok, int* __restrict__ err,
+                              int gen, uint64_t seed, uint32_t step, float p_word, const StepDyn* __restrict__ dyn,
+                              uint8_t* __restrict__ word_drop_out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int n = B * L;
     int cnt = 0;
@@ -61,8 +65,17 @@ __global__ void k_prep_tokens(const int64_t* __restrict__ tokens, const uint8_t*
         int t = i % L;
         int64_t nx = (t + 1 < L) ? tokens[i + 1] : (int64_t)PAD;
         if (nx < 0 || nx >= V) nx = UNK;
+        bool drop;
+        if (gen) {
+            uint32_t r[4];
+            Philox::gen(seed, (uint64_t)i, (dyn != nullptr ? dyn->noise_step : step) * 16u + 2, r);
+            drop = u32_to_unit_open(r[0]) < p_word;      // decoder.py:124-127
+            word_drop_out[i] = drop ? 1 : 0;
+        } else {
+            drop = word_drop != nullptr && word_drop[i];
+        }
         tok[i] = (uint8_t)w;
-        tokd[i] = (word_drop != nullptr && word_drop[i]) ? (uint8_t)UNK : (uint8_t)w;
+        tokd[i] = drop ? (uint8_t)UNK : (uint8_t)w;
         tgt[i] = (uint8_t)nx;
         cnt = (nx != PAD) ? 1 : 0;
     }
@@ -71,10 +84,12 @@ __global__ void k_prep_tokens(const int64_t* __restrict__ tokens, const uint8_t*
 }
 
 void launch_prep_tokens(cudaStream_t s, const int64_t* tokens, const uint8_t* word_drop, int B, int L, int V,
-                        uint8_t* tok, uint8_t* tokd, uint8_t* tgt, int* ntok, int* err) {
+                        uint8_t* tok, uint8_t* tokd, uint8_t* tgt, int* ntok, int* err, const StepNoiseArgs* gen) {
     cudaMemsetAsync(ntok, 0, sizeof(int), s);
     int n = B * L;
-    CPG_LAUNCH(k_prep_tokens, ceil_div(n, 256), 256, 0, s, tokens, word_drop, B, L, V, tok, tokd, tgt, ntok, err);
+    CPG_LAUNCH(k_prep_tokens, ceil_div(n, 256), 256, 0, s, tokens, word_drop, B, L, V, tok, tokd, tgt, ntok, err,
+               gen != nullptr ? 1 : 0, gen != nullptr ? gen->seed : 0ull, gen != nullptr ? gen->step : 0u,
+               gen != nullptr ? gen->p_word : 0.f, g_dyn, gen != nullptr ? gen->word_drop : nullptr);
 }
 
 struct PrepArgs {
