@@ -108,7 +108,10 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
     // random features
     w.rf_nchunk = std::max(1, std::min(B, 2 * sm));
     w.rf_pre1 = a.take<float>((size_t)B * R); w.rf_pre2 = a.take<float>((size_t)B * R);
-    w.rf_part = a.take<float>((size_t)w.rf_nchunk * R);
+    const size_t rf_rows = (size_t)std::max(w.rf_nchunk, rf_tc_parts(B));
+    w.rf_part = a.take<float>(rf_rows * R);
+    w.rf_part2 = a.take<float>(rf_rows * R);
+    w.rf_tiles = a.take<unsigned char>(rf_tc_tile_bytes(R));
     w.rf_sum1 = a.take<float>(R); w.rf_sum2 = a.take<float>(R); w.rf_coef = a.take<float>(R);
     w.dz_rf = a.take<float>((size_t)B * ZD);
     w.lat_nparts = std::max(1, std::min(ceil_div(B, 8), 2 * sm));
@@ -136,6 +139,7 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
     w.gemm_splits = std::max(1, std::min(ceil_div(B, 64), sm / 2));
     w.gemm_ws = a.take<float>((size_t)w.gemm_splits * 3 * DEC_HP * (2 * ENC_H));
     w.colsum_ws = a.take<float>((size_t)64 * 512);
+    w.hg_part = a.take<float>((size_t)latent_bwd_tc_ctas(B) * LT_HG_ROWS * LT_HG_COLS);
     w.norm_part = a.take<float>(2 * sm + 8);
     w.clip_coef = a.take<float>(4);
     w.scalars = a.take<float>(SC_COUNT);
@@ -408,7 +412,11 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
     if (latent_uses_tc(B)) {
         // gradient at [z;c] -> latent backward -> gradient at the encoder's final hidden state, one tcgen05 kernel
         wait_mark(s, dz_ready);                     // dz_rf produced on lane s
-        launch_latent_bwd_tc(s, w.drow, w.dh0, w.d.lat_tiles, la, w.dhfin);
+        launch_latent_bwd_tc(s, w.drow, w.dh0, w.d.lat_tiles, la, w.dhfin, w.hfin, w.hg_part);
+        // ... which also contracted the head weight / bias gradients over its rows: ordered sum of the partials on lane t
+        order(ctx, ln, s, ln.t);
+        launch_head_grad_reduce(ln.t, w.hg_part, B, grads + lay.off[P_QMU_W], grads + lay.off[P_QLV_W], grads + lay.off[P_QMU_B],
+                                grads + lay.off[P_QLV_B]);
     } else {
         // gradient at [z;c]:  dh0 + drow @ W_ih[:,150:]   (in place on dh0)
         launch_sgemm(s, B, DEC_HP, 3 * DEC_HP, 1.f, w.drow, 3 * DEC_HP, 1, w.d.wizc, DEC_HP, 1, 1.f, w.dh0, DEC_HP,
@@ -417,9 +425,7 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
         launch_latent_bwd(s, la);
         // heads
         launch_sgemm_sum2(s, B, 2 * ENC_H, ZD, 1.f, w.dmu, w.dlv, ZD, 1, wmu, wlv, 2 * ENC_H, 1, 0.f, w.dhfin, 2 * ENC_H);
-    }
-    // head weight / bias gradients: lane t (after the decoder weight gradients: same split-K scratch), under the encoder BPTT
-    {
+        // head weight / bias gradients: lane t (after the decoder weight gradients: same split-K scratch), under the encoder BPTT
         order(ctx, ln, s, ln.t);
         launch_sgemm(ln.t, ZD, 2 * ENC_H, B, 1.f, w.dmu, 1, ZD, w.hfin, 2 * ENC_H, 1, 0.f, grads + lay.off[P_QMU_W],
                      2 * ENC_H, nullptr, w.gemm_splits, w.gemm_ws);
@@ -442,10 +448,10 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
         float* const pw[2] = {w.wg_part, w.wg_part_enc1};
         float* const pt[2] = {w.dt_part, w.dt_part_enc1};
         launch_gru_bwd_enc_fused(s, enc, w.tok, B, L, V, pw, pt);
-        // ordered reductions of the per-CTA partials: one direction on lane s, the other on the caller's lane
+        // ordered reductions of the per-CTA partials: one direction on lane t, the other on the caller's lane
         const int nc = bptt_fused_ctas_enc(B);
-        order(ctx, ln, s, ln.s);
-        launch_wgrad_partial_reduce(ln.s, ENC_H, ENC_H, V, pw[0], pt[0], nc, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0]);
+        order(ctx, ln, s, ln.t);
+        launch_wgrad_partial_reduce(ln.t, ENC_H, ENC_H, V, pw[0], pt[0], nc, grads + lay.off[P_ENC_WHH_F], w.dT_enc[0]);
         launch_wgrad_partial_reduce(s, ENC_H, ENC_H, V, pw[1], pt[1], nc, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1]);
     } else {
         if (use_gru_tc(B)) launch_gru_bwd_enc_tc(s, enc, B, L, dg_rounded);
@@ -752,13 +758,25 @@ static int phase1_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, int
     if (!ctx->noise_pending && gen == nullptr) order(ctx, ln, s, q);
     const Mark latent_ready = forward_impl(ctx, ln, params, lay, V, B, L, in, w.mu, w.logvar, w.z, true, false, gen);
     // the prior's random features do not depend on the batch: lane s, under the encoder recurrence
-    launch_sgemm(q, B, R, ZD, 1.f, nz->z_prior_rf, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre2, R, nullptr, 1, nullptr);
-    launch_rf_colsum(q, w.rf_pre2, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8 + R);
+    const bool rf_tc = rf_uses_tc(B, R);
+    if (rf_tc) {
+        launch_prep_rf_tiles(q, nz->rf_w, R, w.rf_tiles);
+        if ((rc = launch_rf_feat_tc(q, nz->z_prior_rf, w.rf_tiles, nz->rf_b, B, R, hp->mmd_sigma, nullptr, w.rf_part2))) return rc;
+        launch_rf_colsum_final(q, w.rf_part2, rf_tc_parts(B), R, coupled + 8 + R);
+    } else {
+        launch_sgemm(q, B, R, ZD, 1.f, nz->z_prior_rf, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre2, R, nullptr, 1, nullptr);
+        launch_rf_colsum(q, w.rf_pre2, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part2, w.rf_nchunk, coupled + 8 + R);
+    }
     // local statistics that couple the batch: RF feature sums, token count, latent sums -- they depend on
     // (mu, logvar, z) only and run on lane s under the decoder recurrence
     wait_mark(q, latent_ready);
-    launch_sgemm(q, B, R, ZD, 1.f, w.z, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre1, R, nullptr, 1, nullptr);
-    launch_rf_colsum(q, w.rf_pre1, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8);
+    if (rf_tc) {
+        if ((rc = launch_rf_feat_tc(q, w.z, w.rf_tiles, nz->rf_b, B, R, hp->mmd_sigma, w.rf_pre1, w.rf_part))) return rc;
+        launch_rf_colsum_final(q, w.rf_part, rf_tc_parts(B), R, coupled + 8);
+    } else {
+        launch_sgemm(q, B, R, ZD, 1.f, w.z, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre1, R, nullptr, 1, nullptr);
+        launch_rf_colsum(q, w.rf_pre1, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8);
+    }
     if (join) {                                     // (the fused step runs these after the RF gradient chain, see phase2_impl)
         launch_int_to_float(q, ctx->ints, coupled + 0, 1);
         launch_latent_stats(q, w.mu, w.logvar, B, w.lat_part, w.lat_nparts, coupled + 2);
@@ -812,8 +830,12 @@ static int phase2_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, flo
         cudaStream_t q = ln.s;
         launch_rf_loss(q, coupled + 8, coupled + 8 + R, R, Bg, hp->mmd_sigma, w_rf, w.rf_coef, w.mmdrf_out);
         if (w_rf != 0.f) {
-            launch_rf_grad_prep(q, w.rf_pre1, nz->rf_b, w.rf_coef, B, R, hp->mmd_sigma);
-            launch_sgemm(q, B, ZD, R, 1.f, w.rf_pre1, R, 1, nz->rf_w, 1, R, 0.f, w.dz_rf, ZD, nullptr, 1, nullptr);
+            if (rf_uses_tc(B, R)) {
+                if ((rc = launch_rf_grad_tc(q, w.rf_pre1, w.rf_tiles, nz->rf_b, w.rf_coef, B, R, hp->mmd_sigma, w.dz_rf))) return rc;
+            } else {
+                launch_rf_grad_prep(q, w.rf_pre1, nz->rf_b, w.rf_coef, B, R, hp->mmd_sigma);
+                launch_sgemm(q, B, ZD, R, 1.f, w.rf_pre1, R, 1, nz->rf_w, 1, R, 0.f, w.dz_rf, ZD, nullptr, 1, nullptr);
+            }
             dz_rf = w.dz_rf;
         }
         const bool want_mmd = (hp->compute_full_mmd || hp->z_regu == CPG_ZREGU_MMD) && nz->z_prior_full;
@@ -949,7 +971,7 @@ int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, fl
              (void*)nb->word_drop, (void*)nb->out_keep, (void*)nb->z_prior_full, (void*)nb->z_prior_rf, (void*)nb->rf_w, (void*)nb->rf_b,
              hp->lr, hp->beta1, hp->beta2, hp->adam_eps, hp->clip_norm, hp->lambda_logvar_l1, hp->lambda_logvar_kl, hp->z_regu,
              hp->mmd_sigma, hp->rf_dim, hp->compute_full_mmd, hp->beta != 0.f ? 1 : 0, (unsigned long long)seed, p_word, p_out,
-             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority);
+             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority + 131072 * g_opt_rf_tc);
     StepGraph* g = find_graph(kb + std::string(scalars ? std::to_string((uintptr_t)scalars) : ""));
     StepDyn* dyn_dev = reinterpret_cast<StepDyn*>(ctx->ints + 32);
     const StepDyn dv = make_dyn(hp, noise_step);

@@ -19,12 +19,13 @@ struct Workspace {
     float *hfin, *mu, *logvar, *z, *zc, *rowbias;
     float *dec_hs, *dec_gates, *dec_dg, *dec_dh_out;
     float *drow, *dh0, *dmu, *dlv, *dhfin;
-    float *rf_pre1, *rf_pre2, *rf_part, *rf_sum1, *rf_sum2, *rf_coef, *dz_rf;
+    float *rf_pre1, *rf_pre2, *rf_part, *rf_part2, *rf_sum1, *rf_sum2, *rf_coef, *dz_rf;
+    unsigned char* rf_tiles;
     float *lat_part, *lat_sums;
     float *mmd_ws, *mmd_out, *mmdrf_out;
     float *do_part_w, *do_part_b, *do_part_nll, *nll_sum;
     float *wg_part, *dt_part, *wg_part_dec, *dt_part_dec, *wg_part_enc1, *dt_part_enc1, *dT_enc[2], *dT_dec, *dwizc;
-    float *gemm_ws, *colsum_ws;
+    float *gemm_ws, *colsum_ws, *hg_part;
     float *norm_part, *clip_coef, *scalars, *ntok_f, *coupled;
     int lat_nparts, rf_nchunk, gemm_splits;
 };

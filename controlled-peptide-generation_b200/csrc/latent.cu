@@ -146,6 +146,10 @@ void launch_rf_colsum(cudaStream_t s, const float* pre, const float* rf_b, int B
     CPG_LAUNCH(k_rf_colsum_final, CPG_RED_GRID(R), CPG_RED_BLOCK, 0, s, part, nchunk, R, out);
 }
 
+void launch_rf_colsum_final(cudaStream_t s, const float* part, int nchunk, int R, float* out) {
+    CPG_LAUNCH(k_rf_colsum_final, CPG_RED_GRID(R), CPG_RED_BLOCK, 0, s, part, nchunk, R, out);
+}
+
 // loss = sum_r (mean1 - mean2)^2 from the GLOBAL feature sums; also
 // coef[r] = w * 2 (mean1 - mean2) * sqrt(2/R) / (B_global * sigma) for the backward pass.
 __global__ void k_rf_loss(const float* __restrict__ sum1, const float* __restrict__ sum2, int R, int B_global,

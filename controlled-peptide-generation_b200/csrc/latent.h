@@ -73,8 +73,24 @@ extern int g_opt_latent_tc, g_opt_latent_rows;
 extern int g_opt_chain_priority;      // api_wae.cu: 1 = the fused step's dependent chain runs on a highest-priority internal stream
 int launch_latent_fwd_tc(cudaStream_t s, const float* hfin, const float* bmu, const float* blv, const float* eps, const float* c,
                          const unsigned char* tiles, int B, float* mu, float* logvar, float* z, float* zc, float* rowbias);
+// hg_part (optional): per-CTA partials [latent_bwd_tc_ctas(B)][LT_HG_ROWS][LT_HG_COLS] of the head weight / bias gradients,
+// contracted in the same kernel; launch_head_grad_reduce sums them in CTA order into the gradient buffers
+constexpr int LT_HG_ROWS = 208, LT_HG_COLS = 176;
+int latent_bwd_tc_ctas(int B);
 int launch_latent_bwd_tc(cudaStream_t s, const float* drow, const float* dh0, const unsigned char* tiles, const LatentBwdArgs& lat,
-                         float* dhfin);
+                         float* dhfin, const float* hfin, float* hg_part);
+void launch_head_grad_reduce(cudaStream_t s, const float* hg_part, int B, float* g_wmu, float* g_wlv, float* g_bmu, float* g_blv);
+// tcgen05 random-feature kernels (rf_tc.cu): pre-split rf_w tiles, feature map + column partials, gradient
+extern int g_opt_rf_tc;
+bool rf_uses_tc(int B, int R);
+size_t rf_tc_tile_bytes(int R);
+int rf_tc_parts(int B);                  // rows of the column-sum partials written by launch_rf_feat_tc
+void launch_prep_rf_tiles(cudaStream_t s, const float* rf_w, int R, unsigned char* tiles);
+int launch_rf_feat_tc(cudaStream_t s, const float* x, const unsigned char* tiles, const float* rf_b, int B, int R, float sigma,
+                      float* pre_out, float* part);
+int launch_rf_grad_tc(cudaStream_t s, const float* pre, const unsigned char* tiles, const float* rf_b, const float* coef, int B, int R,
+                      float sigma, float* dz);
+void launch_rf_colsum_final(cudaStream_t s, const float* part, int nchunk, int R, float* out);
 void launch_compose_scalars(cudaStream_t s, const ComposeArgs& a);
 // data-parallel tail: extra floats all-reduced together with the flat gradient ([0] = NLL sum; rest reserved)
 constexpr int DP_TAIL = 8;

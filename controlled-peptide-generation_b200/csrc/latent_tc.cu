@@ -16,15 +16,12 @@
 // shared memory.
 #include "ctx.h"
 #ifndef CPG_EMU
-#include <cuda_fp16.h>
-#include "tc_gru.cuh"
+#include "tc_dense.cuh"
 
 namespace cpg {
 int check_launch(const char* where);
 
 namespace {
-constexpr int LT_THREADS = 512;
-constexpr int LT_PARTS = LT_THREADS / 128;      // warps per TMEM lane quadrant: they take 16-column slices in turn
 constexpr int KH = 2 * ENC_H;            // 160: K of the heads
 constexpr int NHD = LT_F1_ROWS;          // 2 * 100 head outputs (mu_j, logvar_j interleaved) padded to a multiple of 16
 constexpr int KZ = LT_F2_K;              // [z;c] (102 -> 104) padded to a multiple of 16
@@ -33,92 +30,6 @@ constexpr int KG = LT_B1_K;              // K of the backward's first product
 constexpr int KD = LT_B2_K;              // K of the backward's second product: (dmu_j, dlv_j) interleaved
 constexpr int NHF = LT_B2_N;             // N of the backward's second product (hfin columns)
 static_assert(KH == LT_F1_K && KZ == LT_B1_ROWS && NHF == KH, "tile geometry");
-
-__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__host__ __device__ constexpr uint32_t idesc_16(int M, int N, int a_mn, int b_mn, bool half) {
-    return (1u << 4) | (half ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// fp16 split (x = x1 + x2, 11 + 11 mantissa bits): for operands of bounded magnitude (|x| < 6e4; what falls below the fp16
-// subnormal range is below 6e-8 absolute) the three products are fp32-grade in ABSOLUTE terms -- needed for the forward
-// projections, whose result enters all 25 decoder steps (the bf16 split's 2^-16 left the logits 3e-6 off at zero crossings);
-// gradients (tiny magnitudes) keep the bf16 split, whose exponent range is fp32's.
-template <bool HALF>
-__device__ __forceinline__ void split4x(const float (&x)[4], uint2& hi, uint2& lo) {
-    if (HALF) { split2h(x[0], x[1], hi.x, lo.x); split2h(x[2], x[3], hi.y, lo.y); }
-    else split4(x, hi, lo);
-}
-template <bool HALF>
-__device__ __forceinline__ void split8x(const float (&x)[8], uint4& hi, uint4& lo) {
-    if (HALF) {
-        split2h(x[0], x[1], hi.x, lo.x); split2h(x[2], x[3], hi.y, lo.y);
-        split2h(x[4], x[5], hi.z, lo.z); split2h(x[6], x[7], hi.w, lo.w);
-    } else {
-        split8(x, hi, lo);
-    }
-}
-
-// K-major tile of ROWS rows x K_PAD columns (two 16-bit terms): element (r, k) at (k/8) * ROWS * 16 + (r/8) * 128 +
-// (r%8) * 16 + (k%8) * 2.  Filled from a row-major fp32 matrix `src` (leading dimension ld, k_valid columns, rows past
-// n_rows read as 0): a warp-task = 8 rows x 16 columns, lane = (row in block, float4 of the 64-byte piece) -- full
-// 32-byte sectors on the global side, 8-byte stores that tile 128 contiguous bytes per half-warp on the shared side.
-template <bool HALF, int ROWS, int K_PAD>
-__device__ __forceinline__ void fill_rows_kmajor(unsigned char* hi, unsigned char* lo, const float* __restrict__ src, int ld,
-                                                 int n_rows, int k_valid) {
-    constexpr int NT = (ROWS / 8) * (K_PAD / 16);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rl = lane & 7, fl = lane >> 3;
-#pragma unroll 4
-    for (int t = warp; t < NT; t += LT_THREADS / 32) {
-        const int rb = t % (ROWS / 8), kg = t / (ROWS / 8);
-        const int r = rb * 8 + rl, k0 = kg * 16 + fl * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < n_rows && k0 < k_valid) v = ld_stream4(src + (size_t)r * ld + k0);
-        const float x[4] = {v.x, v.y, v.z, v.w};
-        uint2 h, l;
-        split4x<HALF>(x, h, l);
-        const int off = (k0 >> 3) * (ROWS * 16) + rb * 128 + rl * 16 + (k0 & 7) * 2;
-        *reinterpret_cast<uint2*>(hi + off) = h;
-        *reinterpret_cast<uint2*>(lo + off) = l;
-    }
-}
-
-// three split products over K = k_len: A = K-major tile of a_rows rows, B = K-major rows n0.. of a b_rows-row tile, or an
-// MN-major tile (n fastest) with b_rows K rows; `first` = overwrite the accumulator
-__device__ __forceinline__ void issue_products(uint32_t tmem_d, int M, uint32_t a_hi, uint32_t a_lo, int a_rows, uint32_t b_hi,
-                                               uint32_t b_lo, bool b_mn, int b_rows, int n0, int N, int k_len, bool first, bool half) {
-    const uint32_t idesc = idesc_16(M, N, 0, b_mn ? 1 : 0, half);
-    uint32_t acc = first ? 0u : 1u;
-#pragma unroll 1
-    for (int p = 0; p < 3; ++p) {
-        const uint32_t a0 = XS[p] ? a_lo : a_hi, b0 = WS[p] ? b_lo : b_hi;
-#pragma unroll 1
-        for (int ks = 0; ks < k_len / 16; ++ks) {
-            const uint64_t da = tc::make_smem_desc(a0 + ks * 2 * (a_rows * 16), a_rows * 16, 128, 0);
-            uint64_t db;
-            if (!b_mn) db = tc::make_smem_desc(b0 + ks * 2 * (b_rows * 16) + (n0 >> 3) * 128, b_rows * 16, 128, 0);
-            else db = tc::make_smem_desc(b0 + (n0 >> 3) * (b_rows * 16) + ks * 256, 128, b_rows * 16, 0);
-            umma_ss(tmem_d, da, db, idesc, acc);
-            acc = 1;
-        }
-    }
-}
-
-// row of the tile held by this thread in the epilogue and whether the thread holds one: M = 128 -> TMEM lane = row,
-// M = 64 -> rows 16 q .. 16 q + 15 sit in lanes 0-15 of quadrant q
-template <int M>
-__device__ __forceinline__ int epi_row(int q, int lane, bool& has) {
-    if (M == 128) { has = true; return q * 32 + lane; }
-    has = lane < 16;
-    return q * 16 + (lane & 15);
-}
 
 struct LatFwdArgs {
     const float* hfin;      // [B][160]
@@ -278,14 +189,20 @@ struct LatBwdArgs {
     const unsigned char* tiles;
     LatentBwdArgs lat;      // mu, logvar, eps, dz_rf, dz_ext, dmu_ext, dlv_ext, weights, B, B_global, dmu, dlv
     float* dhfin;           // [B][160]
+    const float* hfin;      // [B][160]
+    float* hg_part;         // [CTAs][LT_HG_ROWS][LT_HG_COLS] per-CTA partials of the head weight / bias gradients, or null
 };
 constexpr int BW_M = 64;
 constexpr int BW_A1 = BW_M * KG * 2;          // bytes per term of the drow tile (full K = 320)
 constexpr int BW_A2 = BW_M * KD * 2;          // bytes per term of the (dmu, dlv) tile
 // stage 1: A1 (2 terms) | B1 = LT_B1; stage 2: A2 (written by the epilogue of stage 1) | B2 = LT_B2
-constexpr size_t BW_S1 = 2 * (size_t)BW_A1 + 2 * LT_B1_TERM, BW_S2 = 2 * (size_t)BW_A2 + 2 * LT_B2_TERM;
+// stage 3 (head weight gradients, contracted over the CTA's 64 batch rows): A = the (dmu, dlv) tile read MN-major,
+// B3 = [hfin | 1 | 0...] rows as an MN-major tile (n fastest) behind B2
+constexpr int BW_B3 = (LT_HG_COLS / 8) * (BW_M * 16);          // bytes per term
+constexpr size_t BW_S1 = 2 * (size_t)BW_A1 + 2 * LT_B1_TERM, BW_S2 = 2 * (size_t)BW_A2 + 2 * LT_B2_TERM + 2 * (size_t)BW_B3;
 constexpr size_t BW_SMEM = BW_S1 > BW_S2 ? BW_S1 : BW_S2;
-static_assert(BW_SMEM <= 227 * 1024, "shared memory");
+static_assert(BW_SMEM + 1024 <= 227 * 1024, "shared memory");
+static_assert(LT_HG_ROWS == KD && LT_HG_COLS % 16 == 0 && LT_HG_COLS > NHF, "head-gradient partial geometry");
 
 __device__ __forceinline__ void ld4_to(const float* p, float* x) {
     const float4 v = ld_stream4(p);
@@ -300,6 +217,7 @@ k_latent_bwd_tc(LatBwdArgs a) {
     unsigned char* B1 = smem + 2 * BW_A1;
     unsigned char* A2 = smem;
     unsigned char* B2 = smem + 2 * BW_A2;
+    unsigned char* B3 = B2 + 2 * LT_B2_TERM;
     __shared__ __align__(8) uint64_t bar_mma, bar_w;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -313,7 +231,7 @@ k_latent_bwd_tc(LatBwdArgs a) {
             bulk_load(B1, a.tiles + LT_B1_OFF, (uint32_t)(2 * LT_B1_TERM), &bar_w);
         }
         __syncwarp();
-        tc::tmem_alloc<256>(&tmem_slot);
+        tc::tmem_alloc<512>(&tmem_slot);
     }
     fill_rows_kmajor<false, M, KG>(A1, A1 + BW_A1, a.drow + (size_t)row0 * (3 * DEC_HP), 3 * DEC_HP, B - row0, 3 * DEC_HP);
     tc::fence_proxy_async();
@@ -332,6 +250,29 @@ k_latent_bwd_tc(LatBwdArgs a) {
     if (tid == 0) {
         tc::mbar_expect_tx(&bar_w, (uint32_t)(2 * LT_B2_TERM));
         bulk_load(B2, a.tiles + LT_B2_OFF, (uint32_t)(2 * LT_B2_TERM), &bar_w);
+    }
+    if (a.hg_part != nullptr) {
+        // B3: element (n, k = batch row b) at (n/8) * M * 16 + (b/8) * 128 + (b%8) * 16 + (n%8) * 2; n < 160: hfin[b][n],
+        // n = 160: 1 (the bias gradients ride as one more column), rest 0
+        for (int i = tid; i < (LT_HG_COLS / 8) * M; i += LT_THREADS) {
+            const int b = i % M, nc = i / M;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = 0.f;
+            if (row0 + b < B) {
+                if (nc < NHF / 8) {
+                    ld4_to(a.hfin + (size_t)(row0 + b) * KH + nc * 8, x);
+                    ld4_to(a.hfin + (size_t)(row0 + b) * KH + nc * 8 + 4, x + 4);
+                } else if (nc == NHF / 8) {
+                    x[0] = 1.f;
+                }
+            }
+            uint4 h, l;
+            split8(x, h, l);
+            const int off = nc * (M * 16) + (b >> 3) * 128 + (b & 7) * 16;
+            *reinterpret_cast<uint4*>(B3 + off) = h;
+            *reinterpret_cast<uint4*>(B3 + BW_B3 + off) = l;
+        }
     }
     const int q = warp & 3, part = warp >> 2;
     bool has;
@@ -416,6 +357,13 @@ k_latent_bwd_tc(LatBwdArgs a) {
         tc::mbar_wait(&bar_w, 1);
         const uint32_t a2 = tc::smem_u32(A2), b2 = tc::smem_u32(B2);
         issue_products(tmem, M, a2, a2 + BW_A2, M, b2, b2 + (uint32_t)LT_B2_TERM, true, KD, 0, NHF, KD, true, false);
+        if (a.hg_part != nullptr) {
+            // stage 3: [dW_mu ; dW_logvar | db] (rows j' = 2 j | 2 j + 1) = (dmu, dlv)^T . [hfin | 1]: the A2 tile read MN-major
+            // (m = j'), two M = 128 tiles (rows 0..127 and 80..207), K = the CTA's 64 batch rows
+            const uint32_t b3 = tc::smem_u32(B3);
+            issue_products(tmem + 160, 128, a2, a2 + BW_A2, M, b3, b3 + BW_B3, true, M, 0, LT_HG_COLS, M, true, false, true, 0);
+            issue_products(tmem + 160 + LT_HG_COLS, 128, a2, a2 + BW_A2, M, b3, b3 + BW_B3, true, M, 0, LT_HG_COLS, M, true, false, true, KD - 128);
+        }
         tc::umma_commit(&bar_mma);
     }
     tc::mbar_wait(&bar_mma, 1);
@@ -428,9 +376,40 @@ k_latent_bwd_tc(LatBwdArgs a) {
             for (int e = 0; e < 16; e += 4) st4(a.dhfin + (size_t)row * KH + c0 + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
         }
     }
+    if (a.hg_part != nullptr) {
+        // partial of this CTA: tile 0 holds rows j' = TMEM lane, tile 1 rows j' = 80 + lane (only j' >= 128 taken from it)
+        float* out = a.hg_part + (size_t)blockIdx.x * LT_HG_ROWS * LT_HG_COLS;
+        constexpr int NCH = LT_HG_COLS / 16;
+        for (int it = part; it < 2 * NCH; it += LT_PARTS) {
+            const int tile = it / NCH, c0 = (it % NCH) * 16;
+            const int jr = tile == 0 ? q * 32 + lane : (KD - 128) + q * 32 + lane;
+            if (tile == 1 && q == 0) continue;                 // rows 80..111: already covered by tile 0
+            float v[16];
+            tmem_ld_cols<16>(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(160 + tile * LT_HG_COLS + c0), v);
+            if (tile == 0 || jr >= 128) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) st4(out + (size_t)jr * LT_HG_COLS + c0 + e, make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
+            }
+        }
+    }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<256>(tmem);
+    if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+// head weight / bias gradients from the per-CTA partials, summed in CTA order: row j' = 2 j (q_mu) | 2 j + 1 (q_logvar),
+// columns 0..159 the weight row, column 160 the bias
+__global__ void k_head_grad_reduce(const float* __restrict__ part, int n_cta, float* __restrict__ g_wmu, float* __restrict__ g_wlv,
+                                   float* __restrict__ g_bmu, float* __restrict__ g_blv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * ZD * (NHF + 1)) return;
+    const int jr = i / (NHF + 1), n = i % (NHF + 1);
+    const float* p = part + (size_t)jr * LT_HG_COLS + n;
+    float acc = 0.f;
+    for (int c = 0; c < n_cta; ++c) acc += p[(size_t)c * LT_HG_ROWS * LT_HG_COLS];
+    const int j = jr >> 1;
+    if (n < NHF) ((jr & 1) ? g_wlv : g_wmu)[(size_t)j * NHF + n] = acc;
+    else ((jr & 1) ? g_blv : g_bmu)[j] = acc;
 }
 
 template <int M>
@@ -458,10 +437,12 @@ int launch_latent_fwd_tc(cudaStream_t s, const float* hfin, const float* bmu, co
     return g_opt_latent_rows == 128 ? launch_fwd<128>(s, a) : launch_fwd<64>(s, a);
 }
 
+int latent_bwd_tc_ctas(int B) { return ceil_div(B, BW_M); }
+
 int launch_latent_bwd_tc(cudaStream_t s, const float* drow, const float* dh0, const unsigned char* tiles, const LatentBwdArgs& lat,
-                         float* dhfin) {
+                         float* dhfin, const float* hfin, float* hg_part) {
     LatBwdArgs a;
-    a.drow = drow; a.dh0 = dh0; a.tiles = tiles; a.lat = lat; a.lat.dyn = g_dyn; a.dhfin = dhfin;
+    a.drow = drow; a.dh0 = dh0; a.tiles = tiles; a.lat = lat; a.lat.dyn = g_dyn; a.dhfin = dhfin; a.hfin = hfin; a.hg_part = hg_part;
     static bool set = false;
     if (!set) {
         if (cudaFuncSetAttribute((const void*)k_latent_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BW_SMEM) != cudaSuccess) { cudaGetLastError(); return CPG_ECUDA; }
@@ -471,6 +452,10 @@ int launch_latent_bwd_tc(cudaStream_t s, const float* drow, const float* dh0, co
     return CPG_OK;
 }
 
+void launch_head_grad_reduce(cudaStream_t s, const float* hg_part, int B, float* g_wmu, float* g_wlv, float* g_bmu, float* g_blv) {
+    CPG_LAUNCH(k_head_grad_reduce, ceil_div(2 * ZD * (NHF + 1), 256), 256, 0, s, hg_part, ceil_div(B, BW_M), g_wmu, g_wlv, g_bmu, g_blv);
+}
+
 }  // namespace cpg
 #else
 namespace cpg {
@@ -478,6 +463,8 @@ int g_opt_latent_tc = 0, g_opt_latent_rows = 64;
 bool latent_uses_tc(int) { return false; }
 int launch_latent_fwd_tc(cudaStream_t, const float*, const float*, const float*, const float*, const float*, const unsigned char*, int,
                          float*, float*, float*, float*, float*) { return CPG_ECUDA; }
-int launch_latent_bwd_tc(cudaStream_t, const float*, const float*, const unsigned char*, const LatentBwdArgs&, float*) { return CPG_ECUDA; }
+int latent_bwd_tc_ctas(int) { return 1; }
+int launch_latent_bwd_tc(cudaStream_t, const float*, const float*, const unsigned char*, const LatentBwdArgs&, float*, const float*, float*) { return CPG_ECUDA; }
+void launch_head_grad_reduce(cudaStream_t, const float*, int, float*, float*, float*, float*) {}
 }  // namespace cpg
 #endif

@@ -350,6 +350,8 @@ int cpg_logreg_stats_len(void);
  *   "latent_tensor_core"  1 (default) the dense layers around the latent code (heads, [z;c] projection and their backward) as two
  *                         fused split-bf16 tcgen05 kernels when B >= 1024, 2 always, 0 fp32 SIMT GEMMs + element-wise kernels
  *   "latent_tile_rows"    64 (default) | 128: batch rows per CTA of the forward latent kernel
+ *   "rf_tensor_core"      1 (default) random-feature map and its gradient (RF-MMD) as split-precision tcgen05 kernels when
+ *                         B >= 1024 (rf_dim a multiple of 4), 2 always, 0 fp32 SIMT GEMMs + element-wise kernels
  *   "chain_priority"      1 (default) the dependent chain of the fused step runs on a highest-priority internal stream
  *                         (forked from / joined to the caller's), 0 = on the caller's stream
  *   "cuda_graph"          1 (default) cpg_wae_train_step_philox replays a captured CUDA graph of the iteration, 0 = eager launches

@@ -55,11 +55,13 @@ def test_forward_tensor_core_recurrences_match_oracle(eng, batch):
         _lib.set_option('gru_tensor_core', 2)
         _lib.set_option('dec_out_tensor_core', 2)
         _lib.set_option('latent_tensor_core', 2)
+        _lib.set_option('rf_tensor_core', 2)
         test_forward_matches_oracle(eng, batch)
     finally:
         _lib.set_option('gru_tensor_core', 1)
         _lib.set_option('dec_out_tensor_core', 1)
         _lib.set_option('latent_tensor_core', 1)
+        _lib.set_option('rf_tensor_core', 1)
 
 
 def test_inference_forward_matches_reference_golden(eng):
@@ -158,11 +160,13 @@ def test_train_step_tensor_core_recurrences_match_oracle(eng, batch, z_regu):
         _lib.set_option('gru_tensor_core', 2)
         _lib.set_option('dec_out_tensor_core', 2)
         _lib.set_option('latent_tensor_core', 2)
+        _lib.set_option('rf_tensor_core', 2)
         test_train_step_matches_oracle(eng, batch, z_regu, max_outliers=3, resync=True)
     finally:
         _lib.set_option('gru_tensor_core', 1)
         _lib.set_option('dec_out_tensor_core', 1)
         _lib.set_option('latent_tensor_core', 1)
+        _lib.set_option('rf_tensor_core', 1)
 
 
 def test_full_batch_4096_matches_reference_golden(eng):
@@ -412,7 +416,7 @@ def test_auto_tensor_core_paths_match_simt_at_ragged_large_batches(eng, batch):
     p = ow.random_params(V, seed=31)
     tokens = ow.synthetic_tokens(batch, V, seed=32).to(dev)
     noise = dev_noise(ow.draw_noise(batch, seed=33), dev)
-    opts = ('gru_tensor_core', 'dec_out_tensor_core', 'wgrad_tensor_core', 'mmd_tensor_core', 'latent_tensor_core')
+    opts = ('gru_tensor_core', 'dec_out_tensor_core', 'wgrad_tensor_core', 'mmd_tensor_core', 'latent_tensor_core', 'rf_tensor_core')
     out = {}
     try:
         for flag in (0, 1):
