@@ -102,6 +102,12 @@ def kernel_work(B, L=SEQ_LEN, V=N_VOCAB, R=500):
         'k_prep_tokens': (0, B * L * 8), 'k_step_noise': (0, B * (3 * Z * f4 + L * Hd + L + 8)),
         'k_input_grads': (2 * V * E * (2 * 3 * He + 3 * Hd) * 2, 0),
         'k_prep_weights': (2 * V * E * (2 * 3 * He + 3 * Hd), 2 * n_par * f4),
+        # dense layers around the latent code (heads, [z;c] projection; their backward + the head weight gradients):
+        # mu / logvar / z written + eps read, resp. mu / logvar / eps read
+        'k_latent_fwd_tc': (2 * B * (2 * Z * 2 * He + 3 * Hd * (Z + 2)), 4 * B * Z * f4),
+        'k_latent_bwd_tc': (2 * B * (3 * Hd * (Z + 2) + 2 * 2 * Z * (2 * He)), 3 * B * Z * f4),
+        # random-feature map (z read) and its gradient (dz written)
+        'k_rf_feat_tc': (2 * B * Z * R, B * Z * f4), 'k_rf_grad_tc': (2 * B * Z * R, B * Z * f4),
     }
     # the dense layers, by shape label "MxNxK": heads (B x 100 x 160, x2 + transposes), [z;c] projection, RF map
     return w
@@ -489,8 +495,9 @@ def run_ours(args):
                    'noise': 'Philox in-kernel, regenerated every step',
                    'launch': 'single GPU: one captured CUDA graph per iteration (cpg_wae_train_step_philox); N > 1: eager launches around the NCCL exchanges',
                    'arithmetic': 'fp32 storage and accumulation; recurrence / decoder-output contractions as split-bf16 '
-                                 '(x1+x2, 3 products; logits 3 terms) tcgen05 MMAs, weight-gradient and MMD Gram contractions tf32, '
-                                 'dense layers fp32 SIMT'},
+                                 '(x1+x2, 3 products; logits 3 terms) tcgen05 MMAs; heads / [z;c] projection / RF map as split-fp16, their '
+                                 'backward as split-bf16 tcgen05 MMAs (3 products); MMD Gram tf32; one remaining fp32 SIMT product '
+                                 '(dW_ih[:,150:], K = batch)'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * L * 8, 'd2h_bytes_per_step': 16 * 4 + 8,
                 'api': 'train_vae.train_vae(cfgv, model, dataset): pinned host tokens copied H2D every step (one step ahead, copy stream), '
                   'scalar block copied D2H every step (collected after the next step is enqueued)'},

@@ -46,9 +46,12 @@ for r in data:
         vals.append(v)
     lines.append('| `%s` | ' % name + ' | '.join(vals) + ' |')
     key = re.match(r'k_\w+', name).group(0) if name.startswith('k_') else name
-    if 'fwd_tc' in key or 'bwd_tc' in key:
-        dec = '104' in name.split('Cfg')[1][:6]
-        key = ('k_gru_fwd' if 'fwd_tc' in key else 'k_gru_bwd') + ('_dec_tc' if dec else '_enc_tc')
+    for stem, fmt in (('k_gru_fwd_tc', 'k_gru_fwd_%s_tc'), ('k_gru_bwd_tc', 'k_gru_bwd_%s_tc'), ('k_gru_bwd_fused', 'k_gru_bwd_%s_fused')):
+        if key.startswith(stem) and 'Cfg' in name:
+            key = fmt % ('dec' if '104' in name.split('Cfg')[1][:6] else 'enc')
+            break
+    if key == 'k_latent_fwd_tc':
+        key = 'k_latent_fwd_tc<M>'
     if 'k_wgrad_tc' in key:
         key += '_dec' if '<104>' in name else '_enc'
     agg.setdefault(key, []).append(to_mb(r[col['dram__bytes_read.sum']], units[col['dram__bytes_read.sum']]) +
