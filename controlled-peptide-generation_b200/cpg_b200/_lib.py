@@ -86,6 +86,7 @@ def _signatures(L):
                                     POINTER(TrainHparams), P, P, P]),
         'cpg_clip_adam_step': (I, [P, P, P, P, P, P, I, POINTER(TrainHparams), P]),
         'cpg_side_stream': (P, [P]),
+        'cpg_aux_stream': (P, [P]),
         'cpg_dp_tail_count': (I, []),
         'cpg_dp_pack_tail': (I, [P, P, P]),
         'cpg_dp_apply_tail': (I, [P, P, P, P]),

@@ -238,9 +238,26 @@ def side_stream(device):
 
 
 def stats_stream(device):
-    """Context manager: work enqueued inside is ordered behind the stream that produced phase 1's `coupled`."""
+    """Context manager: work enqueued inside is ordered behind the stream that produced phase 1's `coupled[1:]`."""
     s = side_stream(device)
     return torch.cuda.stream(s) if s is not None else contextlib.nullcontext()
+
+
+def ntok_stream(device):
+    """Context manager: work enqueued inside is ordered behind the stream that produced phase 1's `coupled[0]`
+    (the token count, available right after the token preparation)."""
+    p = lib().cpg_aux_stream(context(device))
+    return torch.cuda.stream(torch.cuda.ExternalStream(p, device=device)) if p else contextlib.nullcontext()
+
+
+def join_coupled(device):
+    """Make the current stream wait for the library's internal streams: a caller that reads phase 1's `coupled` on its own
+    stream (instead of exchanging it on stats_stream / ntok_stream) calls this first."""
+    cur = torch.cuda.current_stream(device)
+    for getter in (lib().cpg_side_stream, lib().cpg_aux_stream):
+        p = getter(context(device))
+        if p:
+            cur.wait_stream(torch.cuda.ExternalStream(p, device=device))
 
 
 def dp_pack_tail(tail):

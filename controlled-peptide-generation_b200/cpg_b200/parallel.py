@@ -4,8 +4,9 @@ torch.distributed (NCCL over NVLink on the GPU box; gloo in the CPU tests of thi
   phase 1 (local)     forward through the decoder GRU; the local statistics that couple the batch
                       (`coupled` = [n_tok, -, 5 latent sums, RF feature sums of z, of z_prior], ~4 KB) are
                       produced on the library's side stream while the decoder recurrence runs
-  all-reduce #1 SUM   of `coupled`, ASYNC, enqueued behind the side stream: it runs under the decoder
-                      recurrence; the main stream waits for it only when phase 2 starts
+  all-reduce #1 SUM   of `coupled`, ASYNC, in two pieces on the library's internal streams: the token count right
+                      after the token preparation, the latent / RF sums under the decoder recurrence; the main
+                      stream never waits for them directly (phase 2 orders the consumers)
   phase 2 (local)     CE with the GLOBAL token count, RF-MMD gradient from the GLOBAL feature means, BPTT,
                       weight gradients (this rank's share of the global-batch gradient)
   all-reduce #2 SUM   flat gradient (1.03 MB) + an 8-float tail carrying the local NLL sum (and the
@@ -131,11 +132,13 @@ def dp_train_step(state, tokens, noise, hp, p_out=0.3, group=None, full_mmd='loc
     gext = state.grads_ext
     tail = gext[state.grads.numel():]
     coupled, z = eng.step_phase1(state, tokens, local_noise, hp, p_out)
-    # exchange 1, asynchronous: ordered behind the side stream that produced `coupled`, overlapped with the decoder
-    # recurrence already enqueued on the main stream
+    # exchange 1, asynchronous and off the main stream: the token count on the lane that produced it right after the token
+    # preparation (phase 2's decoder-output layer waits for that lane), the latent / RF sums behind the lane that produced
+    # them under the decoder recurrence (the RF-MMD chain of phase 2 continues on that lane)
+    with eng.ntok_stream(tokens.device):
+        dist.all_reduce(coupled[0:1], group=group, async_op=True).wait()     # stream-level wait (no host block with NCCL)
     with eng.stats_stream(tokens.device):
-        work = dist.all_reduce(coupled, group=group, async_op=True)
-    work.wait()                                          # stream-level wait (no host block with NCCL)
+        dist.all_reduce(coupled[1:], group=group, async_op=True).wait()
     scalars = eng.step_phase2(state, tokens, local_noise, hp, coupled, p_out)
     eng.dp_pack_tail(tail)
     dist.all_reduce(gext, group=group)                   # exchange 2: gradients + NLL sum

@@ -15,6 +15,6 @@ int adam_norm_parts(int64_t n, int sm_count);
 // partial sums of squares, then one kernel that finishes the norm, clips and applies Adam (norm_out / coef_out nullable)
 void launch_clip_adam_fused(cudaStream_t s, float* p, float* g, float* m, float* v, int64_t n, int64_t dup_off,
                             int64_t dup_n, float max_norm, float* part, float* norm_out, float* coef_out,
-                            const AdamHyper& h, int sm_count);
+                            const AdamHyper& h, int sm_count, unsigned* bar = nullptr);
 
 }  // namespace cpg

@@ -282,7 +282,7 @@ int g_opt_bptt_fused = 1;
 // statistics of the training step; null when the lanes are off.
 static Mark forward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, const ParamLayout& lay, int V, int B, int L,
                          const cpg_wae_inputs* in, float* mu, float* logvar, float* z, bool stash, bool encoder_only,
-                         const StepNoiseArgs* gen = nullptr) {
+                         const StepNoiseArgs* gen = nullptr, float* ntok_out = nullptr) {
     Workspace& w = ctx->ws;
     cudaStream_t s = ln.m;
     // the derived weight forms only depend on the parameters: their lane runs beside the token preparation
@@ -303,6 +303,10 @@ static Mark forward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, con
         } else {
             launch_step_noise(s, *gen, NOISE_LATENT | NOISE_LATE);
         }
+    }
+    if (ntok_out != nullptr) {                      // data-parallel callers exchange the token count early, on lane t
+        order(ctx, ln, s, ln.t);
+        launch_int_to_float(ln.t, ctx->ints, ntok_out, 1);
     }
     wait_mark(s, weights_ready);
     GruSeq enc[2];
@@ -377,6 +381,20 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
     Workspace& w = ctx->ws;
     const int sm = ctx->sm_count;
     cudaStream_t s = ln.m;
+    InputGradArgs ia;
+    memset(&ia, 0, sizeof(ia));
+    ia.emb = params + lay.off[P_EMB];
+    ia.enc_wih[0] = params + lay.off[P_ENC_WIH_F]; ia.enc_wih[1] = params + lay.off[P_ENC_WIH_R];
+    ia.dec_wih = params + lay.off[P_DEC_WIH];
+    ia.dT_enc[0] = w.dT_enc[0]; ia.dT_enc[1] = w.dT_enc[1]; ia.dT_dec = w.dT_dec; ia.dwizc = w.dwizc;
+    ia.g_emb = grads + lay.off[P_EMB];
+    ia.g_enc_wih[0] = grads + lay.off[P_ENC_WIH_F]; ia.g_enc_bih[0] = grads + lay.off[P_ENC_BIH_F];
+    ia.g_enc_bhh[0] = grads + lay.off[P_ENC_BHH_F];
+    ia.g_enc_wih[1] = grads + lay.off[P_ENC_WIH_R]; ia.g_enc_bih[1] = grads + lay.off[P_ENC_BIH_R];
+    ia.g_enc_bhh[1] = grads + lay.off[P_ENC_BHH_R];
+    ia.g_dec_wih = grads + lay.off[P_DEC_WIH]; ia.g_dec_bih = grads + lay.off[P_DEC_BIH];
+    ia.g_dec_bhh = grads + lay.off[P_DEC_BHH];
+    ia.V = V;
     // decoder BPTT
     GruSeq q;
     memset(&q, 0, sizeof(q));
@@ -403,6 +421,7 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
                                             w.dt_part_dec, grads + lay.off[P_DEC_WHH], w.dT_dec, nullptr, nullptr, dg_rounded);
             if (!t2) launch_dtable(ln.t, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part_dec, w.dT_dec);
         }
+        launch_input_grads(ln.t, ia, nullptr, 2);   // decoder W_ih / bias gradients: their inputs are complete
     }
     const float* wmu = params + lay.off[P_QMU_W];
     const float* wlv = params + lay.off[P_QLV_W];
@@ -467,29 +486,16 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
                                         w.dt_part_enc1, grads + lay.off[P_ENC_WHH_R], w.dT_enc[1], rs, pool_event(ctx, ln), dg_rounded);
         if (!t1) launch_dtable(s, ENC_H, w.enc_dg[1], w.tok, B, L, 1, V, sm, w.dt_part_enc1, w.dT_enc[1]);
     }
-    order(ctx, ln, ln.t, s);                        // every lane's gradients / partial reductions are complete
-    order(ctx, ln, ln.s, s);
-    InputGradArgs ia;
-    memset(&ia, 0, sizeof(ia));
-    ia.emb = params + lay.off[P_EMB];
-    ia.enc_wih[0] = params + lay.off[P_ENC_WIH_F]; ia.enc_wih[1] = params + lay.off[P_ENC_WIH_R];
-    ia.dec_wih = params + lay.off[P_DEC_WIH];
-    ia.dT_enc[0] = w.dT_enc[0]; ia.dT_enc[1] = w.dT_enc[1]; ia.dT_dec = w.dT_dec; ia.dwizc = w.dwizc;
-    ia.g_emb = grads + lay.off[P_EMB];
-    ia.g_enc_wih[0] = grads + lay.off[P_ENC_WIH_F]; ia.g_enc_bih[0] = grads + lay.off[P_ENC_BIH_F];
-    ia.g_enc_bhh[0] = grads + lay.off[P_ENC_BHH_F];
-    ia.g_enc_wih[1] = grads + lay.off[P_ENC_WIH_R]; ia.g_enc_bih[1] = grads + lay.off[P_ENC_BIH_R];
-    ia.g_enc_bhh[1] = grads + lay.off[P_ENC_BHH_R];
-    ia.g_dec_wih = grads + lay.off[P_DEC_WIH]; ia.g_dec_bih = grads + lay.off[P_DEC_BIH];
-    ia.g_dec_bhh = grads + lay.off[P_DEC_BHH];
-    ia.V = V;
-    if (ln.on) {                                    // the two input-side kernels are independent: run them side by side
+    // encoder input-side gradients on the caller's lane, the embedding gradient (all three token-table gradients) beside it
+    order(ctx, ln, ln.t, s);                        // lane t: the other direction's reduction, decoder-side gradients
+    if (ln.on) {
         order(ctx, ln, s, ln.t);
-        launch_input_grads(s, ia, ln.t);
+        launch_input_grads(s, ia, ln.t, 1 | 4);
         order(ctx, ln, ln.t, s);
     } else {
-        launch_input_grads(s, ia);
+        launch_input_grads(s, ia, nullptr, 1 | 4);
     }
+    order(ctx, ln, ln.s, s);                        // lane s: loss scalars (and, in the non-fused BPTT path, a reduction)
 }
 
 static AdamHyper adam_hyper(const cpg_train_hparams* hp) {
@@ -512,6 +518,7 @@ static AdamHyper adam_hyper(const cpg_train_hparams* hp) {
 // ------------------------------------------------------------------------------- captured iteration
 const StepDyn* g_dyn = nullptr;
 int g_opt_chain_priority = 1;         // 1: the fused step's dependent chain runs on the highest-priority internal stream
+int g_opt_adam_fused = 1;             // 1: sum of squares + norm + clip + Adam in one launch (grid barrier), 0: two launches
 int g_opt_graph = 1;                  // 1: cpg_wae_train_step_philox replays a captured CUDA graph of the iteration
 __global__ void k_set_dyn(StepDyn v, StepDyn* __restrict__ dst) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v;
@@ -736,8 +743,10 @@ int cpg_fill_step_noise_overlapped(cpg_ctx* ctx, cpg_stream stream, uint64_t see
 
 int64_t cpg_coupled_count(int rf_dim) { return 8 + 2 * (int64_t)rf_dim; }
 
-// Phase 1.  `join`: the caller's lane waits for the coupled statistics (the public contract of cpg_wae_step_phase1); the
-// fused single-GPU step leaves them on lane s, where everything that consumes them runs.
+// Phase 1.  `join` = the public cpg_wae_step_phase1: every coupled statistic is produced here -- coupled[0] (token count)
+// on lane t right after the token preparation, the rest on lane s -- and NOT joined into the caller's stream: the caller
+// exchanges them on those lanes (cpg_aux_stream / cpg_side_stream) and phase 2 orders its consumers behind them.  The fused
+// single-GPU step (join = false) keeps the log-only statistics for later and reads the token count from the counter.
 static int phase1_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int B, int L,
                        const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
                        float* coupled, float* mu, float* logvar, float* z, bool join, const StepNoiseArgs* gen = nullptr) {
@@ -755,8 +764,10 @@ static int phase1_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, int
     cudaStream_t q = ln.s;
     // explicit noise inputs are ordered before the caller's lane; noise of cpg_fill_step_noise_overlapped / `gen` is
     // produced on lane s itself
-    if (!ctx->noise_pending && gen == nullptr) order(ctx, ln, s, q);
-    const Mark latent_ready = forward_impl(ctx, ln, params, lay, V, B, L, in, w.mu, w.logvar, w.z, true, false, gen);
+    // (also: `coupled` may have been initialised on the caller's stream just before this call)
+    order(ctx, ln, s, q);
+    const Mark latent_ready = forward_impl(ctx, ln, params, lay, V, B, L, in, w.mu, w.logvar, w.z, true, false, gen,
+                                           join ? coupled + 0 : nullptr);
     // the prior's random features do not depend on the batch: lane s, under the encoder recurrence
     const bool rf_tc = rf_uses_tc(B, R);
     if (rf_tc) {
@@ -777,11 +788,8 @@ static int phase1_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, int
         launch_sgemm(q, B, R, ZD, 1.f, w.z, ZD, 1, nz->rf_w, R, 1, 0.f, w.rf_pre1, R, nullptr, 1, nullptr);
         launch_rf_colsum(q, w.rf_pre1, nz->rf_b, B, R, hp->mmd_sigma, w.rf_part, w.rf_nchunk, coupled + 8);
     }
-    if (join) {                                     // (the fused step runs these after the RF gradient chain, see phase2_impl)
-        launch_int_to_float(q, ctx->ints, coupled + 0, 1);
-        launch_latent_stats(q, w.mu, w.logvar, B, w.lat_part, w.lat_nparts, coupled + 2);
-    }
-    if (join) order(ctx, ln, q, s);
+    // (the fused step runs the latent statistics after the RF gradient chain, see phase2_impl)
+    if (join) launch_latent_stats(q, w.mu, w.logvar, B, w.lat_part, w.lat_nparts, coupled + 2);
     if (mu) dev_copy(mu, w.mu, (size_t)B * ZD * 4, s);
     if (logvar) dev_copy(logvar, w.logvar, (size_t)B * ZD * 4, s);
     if (z) dev_copy(z, w.z, (size_t)B * ZD * 4, s);
@@ -793,7 +801,18 @@ static int phase1_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, int
 int cpg_wae_step_phase1(cpg_ctx* ctx, cpg_stream stream, const float* params, int V, int B, int L,
                         const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
                         float* coupled, float* mu, float* logvar, float* z) {
-    return phase1_impl(ctx, stream, params, V, B, L, in, nz, hp, coupled, mu, logvar, z, true);
+    // the dependent chain on the library's highest-priority stream, forked from / joined to the caller's (as the fused step does)
+    if (!ctx) { set_error("cpg_wae_step_phase1: null argument"); return CPG_EINVAL; }
+    cudaStream_t caller = (cudaStream_t)stream, chain = caller;
+    const Lanes l0 = lanes(ctx, caller);
+    if (l0.on && g_opt_chain_priority && ctx->chain_stream != nullptr) {
+        chain = (cudaStream_t)ctx->chain_stream;
+        noise_join(ctx, caller);
+        order(ctx, l0, caller, chain);
+    }
+    const int rc = phase1_impl(ctx, chain, params, V, B, L, in, nz, hp, coupled, mu, logvar, z, true);
+    order(ctx, l0, chain, caller);
+    return rc;
 }
 
 // Phase 2.  `fused` = called by the single-GPU step right after phase1_impl(join = false): the coupled statistics are
@@ -859,6 +878,7 @@ static int phase2_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, flo
     a.logits_out = logits;
     a.dh_out = w.dec_dh_out;
     noise_join(ctx, s);                             // out-dropout mask generated on lane s (normally joined by the latent layers)
+    if (!fused_step) order(ctx, ln, ln.t, s);       // the (exchanged) token count lives on lane t
     launch_dec_out(s, a, ctx->sm_count);
     // the ordered reduction of its partials (fc gradients, NLL sum): lane t, under the decoder BPTT
     order(ctx, ln, s, ln.t);
@@ -870,8 +890,8 @@ static int phase2_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, flo
     la.w_klsm = hp->lambda_logvar_kl;
     la.w_l1 = hp->lambda_logvar_l1;
     la.B_global = Bg;
-    backward_impl(ctx, ln, params, lay, grads, V, B, L, in, la, dz_ready);
-    if (scalars) {
+    if (scalars) {                                  // logging scalars: lane s (after the MMD), once lane t has the NLL sum
+        order(ctx, ln, ln.t, ln.s);
         ComposeArgs c;
         memset(&c, 0, sizeof(c));
         c.ntok = coupled + 0; c.nll_sum = w.nll_sum; c.lat_sums = coupled + 2;
@@ -879,15 +899,25 @@ static int phase2_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, flo
         c.mmdrf = w.mmdrf_out;
         c.beta = hp->beta; c.lambda_l1 = hp->lambda_logvar_l1; c.lambda_kl = hp->lambda_logvar_kl;
         c.z_regu = hp->z_regu; c.B_global = Bg; c.out = scalars;
-        launch_compose_scalars(s, c);
+        launch_compose_scalars(ln.s, c);
     }
+    backward_impl(ctx, ln, params, lay, grads, V, B, L, in, la, dz_ready);
     return check_launch("cpg_wae_step_phase2");
 }
 
 int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, float* grads, int V, int B, int L,
                         const cpg_wae_inputs* in, const cpg_loss_noise* nz, const cpg_train_hparams* hp,
                         const float* coupled, float* scalars, float* logits) {
-    return phase2_impl(ctx, stream, params, grads, V, B, L, in, nz, hp, coupled, scalars, logits, false);
+    if (!ctx) { set_error("cpg_wae_step_phase2: null argument"); return CPG_EINVAL; }
+    cudaStream_t caller = (cudaStream_t)stream, chain = caller;
+    const Lanes l0 = lanes(ctx, caller);
+    if (l0.on && g_opt_chain_priority && ctx->chain_stream != nullptr) {
+        chain = (cudaStream_t)ctx->chain_stream;
+        order(ctx, l0, caller, chain);
+    }
+    const int rc = phase2_impl(ctx, chain, params, grads, V, B, L, in, nz, hp, coupled, scalars, logits, false);
+    order(ctx, l0, chain, caller);
+    return rc;
 }
 
 int cpg_clip_adam_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* m, float* v, int V,
@@ -901,7 +931,8 @@ int cpg_clip_adam_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* gr
     Workspace& w = ctx->ws;
     ParamLayout lay = make_layout(V);
     launch_clip_adam_fused(s, params, grads, m, v, lay.total, lay.off[P_EMB], lay.size[P_EMB], hp->clip_norm, w.norm_part,
-                           grad_norm_out, w.clip_coef, adam_hyper(hp), ctx->sm_count);
+                           grad_norm_out, w.clip_coef, adam_hyper(hp), ctx->sm_count,
+                           g_opt_adam_fused ? reinterpret_cast<unsigned*>(ctx->ints + 8) : nullptr);
     return check_launch("cpg_clip_adam_step");
 }
 
@@ -971,7 +1002,7 @@ int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, fl
              (void*)nb->word_drop, (void*)nb->out_keep, (void*)nb->z_prior_full, (void*)nb->z_prior_rf, (void*)nb->rf_w, (void*)nb->rf_b,
              hp->lr, hp->beta1, hp->beta2, hp->adam_eps, hp->clip_norm, hp->lambda_logvar_l1, hp->lambda_logvar_kl, hp->z_regu,
              hp->mmd_sigma, hp->rf_dim, hp->compute_full_mmd, hp->beta != 0.f ? 1 : 0, (unsigned long long)seed, p_word, p_out,
-             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority + 131072 * g_opt_rf_tc);
+             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority + 131072 * g_opt_rf_tc + 524288 * g_opt_adam_fused);
     StepGraph* g = find_graph(kb + std::string(scalars ? std::to_string((uintptr_t)scalars) : ""));
     StepDyn* dyn_dev = reinterpret_cast<StepDyn*>(ctx->ints + 32);
     const StepDyn dv = make_dyn(hp, noise_step);
@@ -1035,6 +1066,10 @@ int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, fl
 void* cpg_side_stream(cpg_ctx* ctx) {
     if (!ctx || !side_ready(ctx)) return nullptr;
     return ctx->side_stream;
+}
+void* cpg_aux_stream(cpg_ctx* ctx) {
+    if (!ctx || !side_ready(ctx)) return nullptr;
+    return ctx->aux_stream;
 }
 
 int cpg_dp_tail_count(void) { return DP_TAIL; }

@@ -70,6 +70,7 @@ constexpr size_t LT_F1_OFF = 0, LT_F2_OFF = LT_F1_OFF + 2 * LT_F1_TERM, LT_B1_OF
 constexpr size_t LT_B2_OFF = LT_B1_OFF + 2 * LT_B1_TERM, LT_TILES_BYTES = LT_B2_OFF + 2 * LT_B2_TERM;
 bool latent_uses_tc(int B);
 extern int g_opt_latent_tc, g_opt_latent_rows;
+extern int g_opt_adam_fused;          // api_wae.cu
 extern int g_opt_chain_priority;      // api_wae.cu: 1 = the fused step's dependent chain runs on a highest-priority internal stream
 int launch_latent_fwd_tc(cudaStream_t s, const float* hfin, const float* bmu, const float* blv, const float* eps, const float* c,
                          const unsigned char* tiles, int B, float* mu, float* logvar, float* z, float* zc, float* rowbias);

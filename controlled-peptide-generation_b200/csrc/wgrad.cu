@@ -78,6 +78,23 @@ __global__ void k_wgrad_hh_reduce(const float* __restrict__ part, int nsplit, in
     if (ok && threadIdx.y == 0) dW[i] = s;
 }
 
+// both ordered reductions of a fused-BPTT partial set in ONE launch: blocks [0, nbw) the W_hh gradient, the rest the token table
+__global__ void k_wgrad_partial_reduce(const float* __restrict__ part_w, const float* __restrict__ part_t, int nsplit, int HP, int H,
+                                       int nbw, int nt, float* __restrict__ dW, float* __restrict__ dT) {
+    if ((int)blockIdx.x < nbw) {
+        const int i = blockIdx.x * RED_X + threadIdx.x;
+        const bool ok = i < 3 * H * H;
+        const int g = ok ? i / H : 0, k = ok ? i % H : 0, pl = g / H, j = g % H;
+        const float s = block_split_sum(part_w, (size_t)3 * HP * HP, nsplit, (size_t)(pl * HP + j) * HP + k, ok);
+        if (ok && threadIdx.y == 0) dW[i] = s;
+    } else {
+        const int i = (blockIdx.x - nbw) * RED_X + threadIdx.x;
+        const bool ok = i < nt;
+        const float s = block_split_sum(part_t, (size_t)nt, nsplit, (size_t)(ok ? i : 0), ok);
+        if (ok && threadIdx.y == 0) dT[i] = s;
+    }
+}
+
 int wgrad_splits(int B, int L, int sm_count) {
     int nrows = B * L;
     int want = max(1, sm_count / 3);
@@ -126,8 +143,8 @@ bool launch_wgrad_hh(cudaStream_t s, int HP, int H, const float* dg, const float
 
 void launch_wgrad_partial_reduce(cudaStream_t s, int HP, int H, int V, const float* part_w, const float* part_t, int nsplit,
                                  float* dW, float* dT) {
-    CPG_LAUNCH(k_wgrad_hh_reduce, CPG_RED_GRID(3 * H * H), CPG_RED_BLOCK, 0, s, part_w, nsplit, HP, H, dW);
-    CPG_LAUNCH(k_dtable_reduce, CPG_RED_GRID(V * 4 * HP), CPG_RED_BLOCK, 0, s, part_t, nsplit, V * 4 * HP, dT);
+    const int nbw = CPG_RED_GRID(3 * H * H), nt = V * 4 * HP;
+    CPG_LAUNCH(k_wgrad_partial_reduce, nbw + CPG_RED_GRID(nt), CPG_RED_BLOCK, 0, s, part_w, part_t, nsplit, HP, H, nbw, nt, dW, dT);
 }
 
 void launch_wgrad_hh_simt(cudaStream_t s, int HP, int H, const float* dg, const float* hs, const float* h0, int B, int L,
@@ -193,8 +210,8 @@ void launch_dtable(cudaStream_t s, int HP, const float* dg, const uint8_t* tok, 
 }
 
 // input-side parameter gradients from the three table gradients
-__global__ void k_input_grads(InputGradArgs a) {
-    const int task = blockIdx.y;
+__global__ void k_input_grads(InputGradArgs a, int task0) {
+    const int task = blockIdx.y + task0;
     const int stride = gridDim.x * blockDim.x;
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int V = a.V;
@@ -242,40 +259,43 @@ __global__ void k_input_grads(InputGradArgs a) {
     }
 }
 // embedding gradient [V][150] = sum over the three tables' gate rows of dT[v][g] * W_ih[g][e]; <pad> row stays 0
-// (model.py:47).  786-long contraction per output: 8 slices of g per output, summed in slice order.
-__global__ void k_emb_grad(InputGradArgs a) {
-    __shared__ float red_s[RED_Y][RED_X + 1];
+// (model.py:47).  786-long contraction per output: EG_Y slices of g per output (short dependent chains), summed in
+// slice order.
+constexpr int EG_Y = 32;
+__global__ void __launch_bounds__(RED_X * EG_Y)
+k_emb_grad(InputGradArgs a) {
+    __shared__ float red_s[EG_Y][RED_X + 1];
     const int i = blockIdx.x * RED_X + threadIdx.x, y = threadIdx.y;
     const bool ok = i < a.V * EMB;
     const int v = ok ? i / EMB : 0, e = ok ? i % EMB : 0;
-    float s0 = 0.f, s1 = 0.f;
+    float s0 = 0.f;
     if (ok && v != PAD) {
         for (int d = 0; d < 2; ++d) {
             const float* dT = a.dT_enc[d] + v * 4 * ENC_H;
             const float* w = a.enc_wih[d];
-            for (int g = y; g < 3 * ENC_H; g += 2 * RED_Y) {
-                s0 = fmaf(dT[g], w[g * EMB + e], s0);
-                s1 = fmaf(dT[g + RED_Y], w[(g + RED_Y) * EMB + e], s1);      // 240 = 15 * 16: no tail
-            }
+            for (int g = y; g < 3 * ENC_H; g += EG_Y) s0 = fmaf(dT[g], w[g * EMB + e], s0);
         }
         const float* dT = a.dT_dec + v * 4 * DEC_HP;
-        for (int g = y; g < 3 * DEC_H; g += RED_Y) {
+        for (int g = y; g < 3 * DEC_H; g += EG_Y) {
             const int gate = g / DEC_H, j = g % DEC_H;
             s0 = fmaf(dT[gate * DEC_HP + j], a.dec_wih[(size_t)g * DEC_IN + e], s0);
         }
     }
-    red_s[y][threadIdx.x] = s0 + s1;
+    red_s[y][threadIdx.x] = s0;
     __syncthreads();
     if (y == 0 && ok) {
         float s = 0.f;
 #pragma unroll
-        for (int q = 0; q < RED_Y; ++q) s += red_s[q][threadIdx.x];
+        for (int q = 0; q < EG_Y; ++q) s += red_s[q][threadIdx.x];
         a.g_emb[i] = s;
     }
 }
-void launch_input_grads(cudaStream_t s, const InputGradArgs& a, cudaStream_t s_emb) {
-    CPG_LAUNCH(k_input_grads, dim3(32, 3), 256, 0, s, a);
-    CPG_LAUNCH(k_emb_grad, CPG_RED_GRID(a.V * EMB), CPG_RED_BLOCK, 0, s_emb ? s_emb : s, a);   // independent of the kernel above
+// parts: 1 = encoder tasks, 2 = decoder task, 4 = embedding gradient (needs all three token-table gradients)
+void launch_input_grads(cudaStream_t s, const InputGradArgs& a, cudaStream_t s_emb, int parts) {
+    if ((parts & 3) == 3) CPG_LAUNCH(k_input_grads, dim3(148, 3), 256, 0, s, a, 0);
+    else if (parts & 1) CPG_LAUNCH(k_input_grads, dim3(148, 2), 256, 0, s, a, 0);
+    else if (parts & 2) CPG_LAUNCH(k_input_grads, dim3(148, 1), 256, 0, s, a, 2);
+    if (parts & 4) CPG_LAUNCH(k_emb_grad, CPG_RED_GRID(a.V * EMB), dim3(RED_X, EG_Y), 0, s_emb ? s_emb : s, a);   // independent of the kernel above
 }
 
 }  // namespace cpg

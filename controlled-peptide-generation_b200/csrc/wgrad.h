@@ -37,6 +37,7 @@ extern int g_opt_wgrad_tc;
 bool wgrad_uses_tc(int nrows);      // would launch_wgrad_hh take the tensor-core path for this many rows?
 void launch_dtable(cudaStream_t s, int HP, const float* dg, const uint8_t* tok, int B, int L, int reverse, int V,
                    int sm_count, float* part, float* dT);
-void launch_input_grads(cudaStream_t s, const InputGradArgs& a, cudaStream_t s_emb = nullptr);   // s_emb: stream for the embedding gradient
+// s_emb: stream for the embedding gradient; parts: 1 = encoder W_ih / biases, 2 = decoder W_ih / biases, 4 = embedding
+void launch_input_grads(cudaStream_t s, const InputGradArgs& a, cudaStream_t s_emb = nullptr, int parts = 7);
 
 }  // namespace cpg

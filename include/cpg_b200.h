@@ -177,13 +177,19 @@ int cpg_clip_adam_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* gr
                        int n_vocab, const cpg_train_hparams* hp, float* grad_norm_out);
 
 /* Data-parallel plumbing (no reference counterpart: the reference is single-process).
- * cpg_side_stream: the context's internal side stream (cudaStream_t; NULL when option side_stream = 0).  phase1
- *   produces `coupled` on it, so a caller that enqueues its collective on that stream starts the exchange as soon
- *   as the statistics exist, under the decoder recurrence of the main stream.
+ * cpg_side_stream / cpg_aux_stream: the context's two internal streams (cudaStream_t; NULL when option side_stream = 0).
+ *   phase1 produces coupled[1..] on the side stream (under the decoder recurrence of the caller's stream) and coupled[0],
+ *   the token count, on the aux stream right after the token preparation; it does NOT join them into the caller's stream.
+ *   A data-parallel caller enqueues the all-reduce of coupled[0:1] on the aux stream and of coupled[1:] on the side
+ *   stream (so that both exchanges start as soon as their operands exist and stay off the caller's stream); phase2
+ *   orders its consumers behind those streams itself (the decoder-output layer behind the aux stream, the RF-MMD
+ *   chain runs on the side stream, everything is joined before phase2 returns its scalars).  With the streams off
+ *   (NULL) everything happens on the caller's stream.
  * cpg_dp_pack_tail: after phase2, writes float[cpg_dp_tail_count()] = {local NLL sum, 0...}; the caller appends
  *   it to the flat gradient so that ONE all-reduce carries both.
  * cpg_dp_apply_tail: after the all-reduce, re-bases scalars[RECON], [LOSS], [NLL_SUM] on the global NLL sum. */
 void* cpg_side_stream(cpg_ctx* ctx);
+void* cpg_aux_stream(cpg_ctx* ctx);
 int cpg_dp_tail_count(void);
 int cpg_dp_pack_tail(cpg_ctx* ctx, cpg_stream stream, float* tail);
 int cpg_dp_apply_tail(cpg_ctx* ctx, cpg_stream stream, const float* tail_reduced, float* scalars);
@@ -352,6 +358,7 @@ int cpg_logreg_stats_len(void);
  *   "latent_tile_rows"    64 (default) | 128: batch rows per CTA of the forward latent kernel
  *   "rf_tensor_core"      1 (default) random-feature map and its gradient (RF-MMD) as split-precision tcgen05 kernels when
  *                         B >= 1024 (rf_dim a multiple of 4), 2 always, 0 fp32 SIMT GEMMs + element-wise kernels
+ *   "adam_fused"          1 (default) sum of squares, norm, clip and Adam in ONE launch (grid-wide barrier), 0 two launches
  *   "chain_priority"      1 (default) the dependent chain of the fused step runs on a highest-priority internal stream
  *                         (forked from / joined to the caller's), 0 = on the caller's stream
  *   "cuda_graph"          1 (default) cpg_wae_train_step_philox replays a captured CUDA graph of the iteration, 0 = eager launches

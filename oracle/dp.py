@@ -79,6 +79,9 @@ class OracleEngine:
     def stats_stream(self, device):
         return self._null()
 
+    def ntok_stream(self, device):
+        return self._null()
+
     def step_phase1(self, st, tokens, noise, hp, p_out=0.3):
         self._z = ow.reparameterize(*ow.encoder_forward(st.p, tokens), noise['eps']).detach()
         return phase1_coupled(st.p, tokens, noise, rf_dim=hp.rf_dim, sigma=hp.mmd_sigma), self._z

@@ -319,7 +319,11 @@ def test_data_parallel_phases_virtual_ranks(eng):
     st = eng.FlatState(V, dev)
     st.load(p)
     hp2 = eng.make_hparams(beta=1.2, global_batch=B)
-    coupled = sum(eng.step_phase1(st, tk, nz, hp2)[0] for tk, nz in shards)
+    parts = []
+    for tk, nz in shards:
+        parts.append(eng.step_phase1(st, tk, nz, hp2)[0])
+        eng.join_coupled(dev)                                # phase 1 leaves `coupled` on the library's internal streams
+    coupled = sum(parts)
     grads = torch.zeros_like(st.grads)
     nll = 0.0
     for tk, nz in shards:
