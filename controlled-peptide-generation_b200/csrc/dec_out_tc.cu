@@ -10,8 +10,9 @@
 //     dh[128 x 104]      = dl[128 x 32]   . W                (M = rows,  N = hidden,  K = classes)
 //     dW^T[104 x 32]    += hd^T[104 x 128] . dl[128 x 32]    (M = hidden, N = classes, K = rows; accumulates in
 //                                                             TMEM over all tiles of the persistent CTA)
-// All operand tiles are K-major no-swizzle core-matrix tiles in shared memory; hd and dl are therefore
-// staged twice (row-major-K and transposed).  Softmax / CE run with thread = row straight out of TMEM
+// All operand tiles are K-major no-swizzle core-matrix tiles in shared memory; the dW contraction, which needs hd and dl
+// with the tile rows as K, reads the SAME hd / dl tiles through MN-major descriptors (no transposed copies).
+// Softmax / CE run with thread = row straight out of TMEM
 // (all 32 class logits of a row in one thread's registers: no shuffles).
 // One persistent CTA per SM, 256 threads: all 8 warps stage, warps 0-3 own the TMEM epilogues, an
 // elected lane of warp 4 issues the MMAs.  Per-CTA partials (dW, db, nll) feed the ordered reduction of dec_out.cu.
@@ -45,15 +46,13 @@ constexpr int HD_SPLIT = (KH / 8) * LBO_R;         // hd   : 128 rows x K = 112
 constexpr int WK_SPLIT = (KH / 8) * LBO_V;         // W    : 32 classes x K = 112
 constexpr int DL_SPLIT = (VMAX / 8) * LBO_R;       // dl   : 128 rows x K = 32
 constexpr int WT_SPLIT = (VMAX / 8) * LBO_H;       // W^T  : 112 hidden x K = 32
-constexpr int HDT_SPLIT = (TR / 8) * LBO_R;        // hd^T : 128 hidden (104 used) x K = 128 rows
-constexpr int DLT_SPLIT = (TR / 8) * LBO_VT;       // dl^T : 32 classes x K = 128 rows
+constexpr int STAGE_BYTES = TR * (DEC_HP + 4) * 4;  // fp32 read-out tile of dh (padded rows)
 constexpr int OFF_HD = 0;
 constexpr int OFF_WK = OFF_HD + 3 * HD_SPLIT;
 constexpr int OFF_DL = OFF_WK + 3 * WK_SPLIT;
 constexpr int OFF_WT = OFF_DL + 2 * DL_SPLIT;
-constexpr int OFF_HDT = OFF_WT + 2 * WT_SPLIT;
-constexpr int OFF_DLT = OFF_HDT + 2 * HDT_SPLIT;
-constexpr int OFF_KEEP = OFF_DLT + 2 * DLT_SPLIT;  // [128][26] keep nibbles (one byte per 4 hidden units)
+constexpr int OFF_STAGE = OFF_WT + 2 * WT_SPLIT;
+constexpr int OFF_KEEP = OFF_STAGE + STAGE_BYTES;  // [128][26] keep nibbles (one byte per 4 hidden units)
 constexpr int SMEM_TOTAL = OFF_KEEP + TR * NF4 + 128;
 // tensor-memory columns
 constexpr int TC_LG = 0, TC_DH = 32, TC_DW = 160;
@@ -66,8 +65,9 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t da, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
-__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -134,6 +134,20 @@ __device__ __forceinline__ void mma_split3(uint32_t tmem_d, uint32_t a0, int a_s
             acc = 1;
         }
 }
+// the same, both operands read MN-major from K-major tiles whose rows are this contraction's K: element (mn, k) of a tile
+// with chunk stride `lbo` sits at (mn >> 3) * lbo + (k >> 3) * 128 + (k & 7) * 16 + (mn & 7) * 2
+__device__ __forceinline__ void mma_split3_mn(uint32_t tmem_d, uint32_t a0, int a_split, int a_lbo, uint32_t b0, int b_split, int b_lbo,
+                                              int ksteps, uint32_t idesc, uint32_t acc) {
+    const int xs[3] = {0, 0, 1}, ws[3] = {0, 1, 0};
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t da = tc::make_smem_desc(a0 + xs[p] * a_split + ks * 256, 128, a_lbo, 0);
+            const uint64_t db = tc::make_smem_desc(b0 + ws[p] * b_split + ks * 256, 128, b_lbo, 0);
+            umma_bf16_ss(tmem_d, da, db, idesc, acc);
+            acc = 1;
+        }
+}
 }  // namespace
 
 __global__ void __launch_bounds__(NTH, 1)
@@ -143,8 +157,7 @@ k_dec_out_tc(DecOutArgs a) {
     unsigned char* WK = smem + OFF_WK;
     unsigned char* DL = smem + OFF_DL;
     unsigned char* WT = smem + OFF_WT;
-    unsigned char* HDT = smem + OFF_HDT;
-    unsigned char* DLT = smem + OFF_DLT;
+    unsigned char* STG = smem + OFF_STAGE;
     unsigned char* keep_s = smem + OFF_KEEP;
     __shared__ __align__(8) uint64_t bar_m;
     __shared__ uint32_t tmem_slot;
@@ -194,7 +207,6 @@ k_dec_out_tc(DecOutArgs a) {
     tc::tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const uint32_t s_hd = tc::smem_u32(HD), s_wk = tc::smem_u32(WK), s_dl = tc::smem_u32(DL), s_wt = tc::smem_u32(WT);
-    const uint32_t s_hdt = tc::smem_u32(HDT), s_dlt = tc::smem_u32(DLT);
 
     // epilogue threads (warps 0-3): thread = row of the tile = TMEM lane
     const int rl = tid;                                        // valid for tid < 128
@@ -268,26 +280,7 @@ k_dec_out_tc(DecOutArgs a) {
                 keep_s[r * NF4 + f] = (unsigned char)kb;
             }
         }
-        __syncthreads();
         DO_MARK(0);
-        // ---- S2) transposed copy HD -> HDT (lanes along rows: conflict-free 2-byte stores)
-        if (want_grad) {
-            for (int idx = tid; idx < TR * (DEC_HP / 8); idx += NTH) {
-                const int r = idx % TR, kc = idx / TR;             // kc: 8 hidden units
-                const int src = kc * LBO_R + (r >> 3) * 128 + (r & 7) * 16;
-#pragma unroll
-                for (int sp = 0; sp < 2; ++sp) {                                   // the two leading terms
-                    const uint4 v = *reinterpret_cast<const uint4*>(HD + sp * HD_SPLIT + src);
-                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int j = kc * 8 + e;
-                        const uint16_t bits = (uint16_t)(w[e >> 1] >> ((e & 1) * 16));
-                        *reinterpret_cast<uint16_t*>(HDT + sp * HDT_SPLIT + (r >> 3) * LBO_R + (j >> 3) * 128 + (j & 7) * 16 + (r & 7) * 2) = bits;
-                    }
-                }
-            }
-        }
         tc::fence_proxy_async();
         __syncthreads();
         DO_MARK(1);
@@ -357,7 +350,7 @@ k_dec_out_tc(DecOutArgs a) {
             if (want_grad) {
 #pragma unroll
                 for (int i = 0; i < HV; ++i) accb[i] += dl[i];
-                // dl -> DL (K = class, K-major) and DLT (class x rows)
+                // dl -> DL (K = class, K-major; the dW contraction reads the same tile MN-major)
 #pragma unroll
                 for (int kq = 0; kq < HV / 8; ++kq) {
                     const int kc = half * (HV / 8) + kq;
@@ -369,14 +362,6 @@ k_dec_out_tc(DecOutArgs a) {
                     const int off = kc * LBO_R + (r2 >> 3) * 128 + (r2 & 7) * 16;
                     *reinterpret_cast<uint4*>(DL + off) = hi;
                     *reinterpret_cast<uint4*>(DL + DL_SPLIT + off) = lo;
-                    const uint32_t wh[4] = {hi.x, hi.y, hi.z, hi.w}, wl[4] = {lo.x, lo.y, lo.z, lo.w};
-#pragma unroll
-                    for (int e8 = 0; e8 < 8; ++e8) {
-                        const int v = kc * 8 + e8;
-                        const int o = (r2 >> 3) * LBO_VT + (v >> 3) * 128 + (v & 7) * 16 + (r2 & 7) * 2;
-                        *reinterpret_cast<uint16_t*>(DLT + o) = (uint16_t)(wh[e8 >> 1] >> ((e8 & 1) * 16));
-                        *reinterpret_cast<uint16_t*>(DLT + DLT_SPLIT + o) = (uint16_t)(wl[e8 >> 1] >> ((e8 & 1) * 16));
-                    }
                 }
             }
             tc::tc_fence_before();
@@ -391,8 +376,8 @@ k_dec_out_tc(DecOutArgs a) {
             tc::tc_fence_after();
             if (elect_one()) {
                 mma_split3(tmem + TC_DH, s_dl, DL_SPLIT, LBO_R, s_wt, WT_SPLIT, LBO_H, VMAX / 16, idesc_bf16(128, KH), 0);
-                mma_split3(tmem + TC_DW, s_hdt, HDT_SPLIT, LBO_R, s_dlt, DLT_SPLIT, LBO_VT, TR / 16, idesc_bf16(128, VMAX),
-                           dw_started ? 1u : 0u);
+                mma_split3_mn(tmem + TC_DW, s_hd, HD_SPLIT, LBO_R, s_dl, DL_SPLIT, LBO_R, TR / 16, idesc_bf16(128, VMAX, 1, 1),
+                              dw_started ? 1u : 0u);
                 tc::umma_commit(&bar_m);
             }
             __syncwarp();
@@ -400,13 +385,10 @@ k_dec_out_tc(DecOutArgs a) {
         dw_started = true;
         if (tile + (int)gridDim.x < ntiles) load_tile(tile + gridDim.x);      // next tile's inputs: in flight under E2
         // ---- E2) dh_out = dh * keep * scale.  TMEM read-out with thread = row (warps w and w + 4 share a lane quadrant and
-        // split the columns) into a padded fp32 tile that reuses the hd^T operand space (its reader, the dW MMA, has
-        // completed; its never-rewritten M-padding rows only feed accumulator rows nobody reads -- unlike HD, whose
-        // K padding must stay zero), then a row-contiguous masked copy to HBM by all 256 threads.
+        // split the columns) into a padded fp32 tile, then a row-contiguous masked copy to HBM by all 256 threads.
         {
             constexpr int SST = DEC_HP + 4;                    // 108 floats: conflict-free float4 rows
-            float* stage = reinterpret_cast<float*>(HDT);
-            static_assert((DEC_HP + 4) * TR * 4 <= 2 * HDT_SPLIT, "staging tile fits the hd^T operand space");
+            float* stage = reinterpret_cast<float*>(STG);
             tc::mbar_wait(&bar_m, mphase & 1);
             tc::tc_fence_after();
             const int r2 = (warp & 3) * 32 + lane;
@@ -434,7 +416,7 @@ k_dec_out_tc(DecOutArgs a) {
             }
         }
         ++mphase;
-        __syncthreads();                                       // both MMAs are done with HD / HDT / DL / DLT
+        __syncthreads();                                       // both MMAs are done with HD / DL, the stage tile is read out
         DO_MARK(3);
     }
 
