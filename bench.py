@@ -381,6 +381,7 @@ def run_ours(args):
     counter = {'it': 0}
 
     stepper = engine.FusedStepper(st, B, L, hp, seed=seed, rf_dim=cfg.losses.wae_mmd.rf_dim) if world == 1 else None
+    dp_stepper = parallel.GraphedDPStepper(st, B, L, hp, noise, seed, gb, graph=not args.no_dp_graph) if world > 1 else None
 
     def step():
         it = counter['it']
@@ -388,9 +389,7 @@ def run_ours(args):
         beta = float(utils.anneal(cfg.vae.beta, it))
         if world == 1:                                             # what train_vae issues per iteration: noise + step, one C call
             return stepper.step(tokens, it, beta)                  # (captured CUDA graph from the third call on)
-        hp.beta = beta
-        engine.fill_step_noise(noise, seed, it, overlap=True)      # next reader is the train step below
-        return parallel.dp_train_step(st, tokens, noise, hp, global_batch=gb)
+        return dp_stepper.step(tokens, it, beta)                   # noise + dp_train_step (collectives included), one captured graph
 
     def barrier():
         if world > 1:
@@ -426,9 +425,13 @@ def run_ours(args):
     # for the per-kernel pass everything is serialised on one stream so that each duration is the kernel's own.
     _lib.set_option('side_stream', 0)
     _lib.profile_enable(True)
+    if dp_stepper is not None:
+        dp_stepper.force_eager = True                              # the profiler hooks the library's eager launches
     prof_ms = timed(step, K)
     rows = _lib.profile_read()
     _lib.profile_enable(False)
+    if dp_stepper is not None:
+        dp_stepper.force_eager = False
     _lib.set_option('side_stream', 1)
     peaks, peak_src = load_peaks()
     roof = build_roofline(rows, K, B, ms_per_step, peaks, peak_src)
@@ -458,6 +461,11 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = gb * K / float(e2e_s.item())
     clock_summary = clocks.summary() if clocks else None
+
+    dp_graph_state = None
+    if dp_stepper is not None:
+        dp_graph_state = 'captured' if dp_stepper.graph is not None else 'capture unavailable, eager launches'
+        dp_stepper.release()                                       # no live graph with captured collectives at teardown
 
     # ---- strong scaling (BASELINE.json configs[2]: global batch 4096 over the N GPUs), N > 1 only
     strong = None
@@ -493,7 +501,9 @@ def run_ours(args):
                    'parallelism': 'dp%d' % world if world > 1 else 'single',
                    'l2_policy': 'per-step working set (activation stash ~1.1 GB) exceeds the 126 MB L2; no flush needed',
                    'noise': 'Philox in-kernel, regenerated every step',
-                   'launch': 'single GPU: one captured CUDA graph per iteration (cpg_wae_train_step_philox); N > 1: eager launches around the NCCL exchanges',
+                   'launch': ('single GPU: one captured CUDA graph per iteration (cpg_wae_train_step_philox)' if world == 1 else
+                              'one captured CUDA graph per rank and iteration, NCCL all-reduces included (parallel.GraphedDPStepper): %s'
+                              % dp_graph_state),
                    'arithmetic': 'fp32 storage and accumulation; recurrence / decoder-output contractions as split-bf16 '
                                  '(x1+x2, 3 products; logits 3 terms) tcgen05 MMAs; heads / [z;c] projection / RF map as split-fp16, their '
                                  'backward as split-bf16 tcgen05 MMAs (3 products); MMD Gram tf32; one remaining fp32 SIMT product '
@@ -545,6 +555,7 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling arm at N > 1')
+    ap.add_argument('--no-dp-graph', action='store_true', help='N > 1: eager launches instead of the captured data-parallel graph')
     ap.add_argument('--class-draws', type=int, default=0, help='CLaSS draws per GPU (default 10M at N=1, 12.5M at N>1)')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -159,6 +159,7 @@ _DEFAULTS = {
                                          # (rows of the round table = unique accepted peptides); False = decode every draw
         'q_fit': 'sklearn',        # mogQ fit: 'sklearn' (reference: host GaussianMixture.fit) | 'device' (EM kernels, cpg_b200.fit)
         'clf_fit': 'sklearn',      # z-space classifiers: 'sklearn' (LogisticRegression lbfgs) | 'device' (Newton, GPU statistics)
+        'dp_graph': True,          # under torch.distributed: replay the iteration (collectives included) from one captured CUDA graph per rank
         'dp_full_mmd': 'local',    # under torch.distributed: 'local' = the log-only full-kernel MMD of this rank's shard,
                                    # 'global' = all-gather z / z_prior and evaluate the global-batch value
     },

@@ -87,6 +87,8 @@ def _signatures(L):
         'cpg_clip_adam_step': (I, [P, P, P, P, P, P, I, POINTER(TrainHparams), P]),
         'cpg_side_stream': (P, [P]),
         'cpg_aux_stream': (P, [P]),
+        'cpg_step_dyn_write': (I, [P, P, POINTER(TrainHparams), c_uint32]),
+        'cpg_step_dyn_use': (I, [P, I]),
         'cpg_dp_tail_count': (I, []),
         'cpg_dp_pack_tail': (I, [P, P, P]),
         'cpg_dp_apply_tail': (I, [P, P, P, P]),

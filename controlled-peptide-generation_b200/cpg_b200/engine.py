@@ -260,6 +260,16 @@ def join_coupled(device):
             cur.wait_stream(torch.cuda.ExternalStream(p, device=device))
 
 
+def step_dyn_write(device, hp, noise_step):
+    """Refresh the per-step scalars (beta, Adam bias corrections of hp.adam_step, noise counter) in the context's device
+    block: what the kernels of a caller-captured iteration read (see step_dyn_use)."""
+    check(lib().cpg_step_dyn_write(context(device), stream_ptr(), byref(hp), int(noise_step)), 'cpg_step_dyn_write')
+
+
+def step_dyn_use(device, on):
+    check(lib().cpg_step_dyn_use(context(device), 1 if on else 0), 'cpg_step_dyn_use')
+
+
 def dp_pack_tail(tail):
     check(lib().cpg_dp_pack_tail(context(tail.device), stream_ptr(), ptr(tail)), 'cpg_dp_pack_tail')
 

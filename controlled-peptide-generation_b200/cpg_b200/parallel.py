@@ -115,15 +115,17 @@ def all_gather_ragged(t, group=None):
     return torch.cat([o[:k] for o, k in zip(outs, ns)])
 
 
-def dp_train_step(state, tokens, noise, hp, p_out=0.3, group=None, full_mmd='local', global_batch=None, eng=None):
+def dp_train_step(state, tokens, noise, hp, p_out=0.3, group=None, full_mmd='local', global_batch=None, eng=None,
+                  _advance=True):
     """One data-parallel iteration on this rank's shard.  Returns the scalar block (device): recon / KL /
     RF-MMD / loss are GLOBAL values; the full-kernel MMD slot is the local-shard value unless
     full_mmd == 'global'.  Pass `global_batch` (sum of the shard sizes) when it is constant to avoid one
     tiny all-reduce + host sync per step.  `eng` (default: cpg_b200.engine) provides the local phases."""
     eng = eng or _engine
     hp.global_batch = int(global_batch) if global_batch else global_batch_size(tokens.shape[0], tokens.device, group)
-    state.step += 1
-    hp.adam_step = state.step
+    if _advance:
+        state.step += 1
+        hp.adam_step = state.step
     local_noise = noise
     z_prior_full = noise.get('z_prior_full')
     if full_mmd != 'local':
@@ -153,3 +155,75 @@ def dp_train_step(state, tokens, noise, hp, p_out=0.3, group=None, full_mmd='loc
         m = eng.SC['mmd']
         eng.mmd_full(zs, zp, hp.mmd_sigma, out=scalars[m:m + 1])
     return scalars
+
+
+class GraphedDPStepper:
+    """The perf-mode data-parallel iteration (Philox noise + dp_train_step, collectives included) as ONE captured CUDA graph
+    per rank, replayed every step: the ~35 kernels, the three all-reduces and the fork / join of the library's lanes cost one
+    graph launch on the host instead of ~45 eager launches from Python.  The per-step scalars (beta, Adam bias corrections,
+    noise counter) live in the library's device block, refreshed by one tiny kernel before each replay
+    (engine.step_dyn_write).  Two eager iterations come first (allocations, attribute set-up); if the capture fails
+    (e.g. a process group whose collectives cannot be captured) the stepper stays on eager launches -- same results.
+
+    `tokens` is copied into a static buffer each step (the graph reads fixed addresses)."""
+
+    def __init__(self, state, B, L, hp, noise, seed, global_batch, group=None, p_word=0.3, p_out=0.3, full_mmd='local',
+                 graph=True):
+        self.state, self.hp, self.noise, self.seed = state, hp, noise, int(seed)
+        self.group, self.p_word, self.p_out, self.full_mmd, self.global_batch = group, p_word, p_out, full_mmd, int(global_batch)
+        self.B, self.L = B, L
+        dev = state.params.device
+        self.dev = dev
+        self.tokens = torch.zeros(B, L, dtype=torch.int64, device=dev)
+        self.want_graph = bool(graph) and full_mmd == 'local'
+        self.graph, self.scalars, self.calls = None, None, 0
+        self.force_eager = False                          # e.g. while the per-kernel profiler is on (it sees eager launches only)
+
+    def _body(self, it):
+        _engine.fill_step_noise(self.noise, self.seed, it, self.p_word, self.p_out, overlap=True)
+        return dp_train_step(self.state, self.tokens, self.noise, self.hp, p_out=self.p_out, group=self.group,
+                             full_mmd=self.full_mmd, global_batch=self.global_batch, _advance=False)
+
+    def step(self, tokens, it, beta):
+        if tokens.data_ptr() != self.tokens.data_ptr():
+            self.tokens.copy_(tokens, non_blocking=True)
+        st, hp = self.state, self.hp
+        st.step += 1
+        hp.adam_step = st.step
+        hp.beta = float(beta)
+        self.calls += 1
+        if self.graph is None and self.want_graph and self.calls >= 3 and not self.force_eager:
+            self._capture(it)
+        if self.graph is not None and not self.force_eager:
+            _engine.step_dyn_write(self.dev, hp, it)
+            self.graph.replay()
+            return self.scalars
+        return self._body(it)
+
+    def release(self):
+        """Drop the captured graph (and the scalar block it owns).  Call before dist.destroy_process_group(): a live graph
+        that holds captured collectives keeps the communicator busy at teardown."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.dev)
+            self.graph, self.scalars = None, None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize(self.dev)
+        self.want_graph = False
+
+    def _capture(self, it):
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        try:
+            _engine.step_dyn_write(self.dev, self.hp, it)
+            _engine.step_dyn_use(self.dev, True)
+            with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                sc = self._body(it)
+            self.graph, self.scalars = g, sc
+        except Exception as e:                                   # noqa: BLE001 -- any capture failure: stay eager
+            warnings.warn('data-parallel step: CUDA-graph capture failed (%s: %s); using eager launches'
+                          % (type(e).__name__, e))
+            self.want_graph = False
+        finally:
+            _engine.step_dyn_use(self.dev, False)
+        torch.cuda.synchronize(self.dev)

@@ -1062,6 +1062,22 @@ int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, fl
 #endif
 }
 
+// ---- per-step scalars in device memory, for callers that capture the iteration themselves --------------------
+int cpg_step_dyn_write(cpg_ctx* ctx, cpg_stream stream, const cpg_train_hparams* hp, uint32_t noise_step) {
+    if (!ctx || !hp) { set_error("cpg_step_dyn_write: null argument"); return CPG_EINVAL; }
+    if (hp->adam_step < 1) { set_error("adam_step is 1-based"); return CPG_EINVAL; }
+#ifndef CPG_EMU
+    k_set_dyn<<<1, 32, 0, (cudaStream_t)stream>>>(make_dyn(hp, noise_step), reinterpret_cast<StepDyn*>(ctx->ints + 32));
+#endif
+    return check_launch("cpg_step_dyn_write");
+}
+
+int cpg_step_dyn_use(cpg_ctx* ctx, int on) {
+    if (!ctx) { set_error("cpg_step_dyn_use: null argument"); return CPG_EINVAL; }
+    g_dyn = on ? reinterpret_cast<const StepDyn*>(ctx->ints + 32) : nullptr;
+    return CPG_OK;
+}
+
 // ---- data-parallel helpers (cpg_b200/parallel.py) ----------------------------------------------------------
 void* cpg_side_stream(cpg_ctx* ctx) {
     if (!ctx || !side_ready(ctx)) return nullptr;

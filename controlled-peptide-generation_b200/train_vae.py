@@ -71,6 +71,7 @@ def _train_fused(cfgv, model, dataset):
         # rank-distinct noise rows; rf_w / rf_b come from the shared seed inside alloc_noise
         rank_seed = (seed + 0x9E3779B97F4A7C15 * (1 + parallel.dist.get_rank())) % (1 << 63)
     stepper, global_batch = None, None
+    dp_steppers = {}                                  # data parallel: (compute_full_mmd, B, L) -> parallel.GraphedDPStepper
     it_range, write = _progress(range(cfgv.s_iter, cfgv.s_iter + cfgv.n_iter + 1))
     last_it = cfgv.s_iter + cfgv.n_iter
     # Host batches go to the device one iteration ahead, on a copy stream, into one of two buffers: the H2D copy of
@@ -117,10 +118,17 @@ def _train_fused(cfgv, model, dataset):
         beta = float(utils.anneal(cfgv.beta, it))
         hp.compute_full_mmd = 1 if (it % every == 0 or log_it) else 0
         if distributed:
-            hp.beta = beta
-            engine.fill_step_noise(stepper.noise, rank_seed, it, p_word, p_out, overlap=True)
-            scal = parallel.dp_train_step(st, tok, stepper.noise, hp, p_out=p_out, global_batch=global_batch,
-                                          full_mmd=str(getattr(cfg.b200, 'dp_full_mmd', 'local')))
+            # one captured graph per rank (noise + both phases + the collectives + clip/Adam); the log-only full-kernel MMD is
+            # evaluated on some iterations only, so there is one stepper (and graph) per value of that switch
+            key = (int(hp.compute_full_mmd), B, L)
+            ds = dp_steppers.get(key)
+            if ds is None:
+                hp_k = type(hp).from_buffer_copy(hp)
+                ds = parallel.GraphedDPStepper(st, B, L, hp_k, stepper.noise, rank_seed, global_batch, p_word=p_word, p_out=p_out,
+                                               full_mmd=str(getattr(cfg.b200, 'dp_full_mmd', 'local')),
+                                               graph=bool(getattr(cfg.b200, 'dp_graph', True)))
+                dp_steppers[key] = ds
+            scal = ds.step(tok, it, beta)
         else:
             scal = stepper.step(tok, it, beta)
         if slot is not None:
@@ -156,6 +164,8 @@ def _train_fused(cfgv, model, dataset):
     if pending_read is not None:
         pending_read[1].synchronize()
         last_scalars = pending_read[0].clone()
+    for ds in dp_steppers.values():                   # no live graph with captured collectives once training is over
+        ds.release()
     return st
 
 

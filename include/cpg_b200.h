@@ -176,6 +176,14 @@ int cpg_wae_step_phase2(cpg_ctx* ctx, cpg_stream stream, const float* params, fl
 int cpg_clip_adam_step(cpg_ctx* ctx, cpg_stream stream, float* params, float* grads, float* adam_m, float* adam_v,
                        int n_vocab, const cpg_train_hparams* hp, float* grad_norm_out);
 
+/* Per-step scalars in device memory, for a caller that captures the iteration into a CUDA graph ITSELF (e.g. the
+ * data-parallel step with its collectives, cpg_b200/parallel.py).  While cpg_step_dyn_use(ctx, 1) is in effect every kernel
+ * the library enqueues reads beta, the Adam bias corrections and the noise counter from the context's device block
+ * instead of from the host arguments of the call; cpg_step_dyn_write refreshes that block (one tiny kernel on `stream`,
+ * outside the captured graph) before each replay.  cpg_wae_train_step_philox does this internally. */
+int cpg_step_dyn_write(cpg_ctx* ctx, cpg_stream stream, const cpg_train_hparams* hp, uint32_t noise_step);
+int cpg_step_dyn_use(cpg_ctx* ctx, int on);
+
 /* Data-parallel plumbing (no reference counterpart: the reference is single-process).
  * cpg_side_stream / cpg_aux_stream: the context's two internal streams (cudaStream_t; NULL when option side_stream = 0).
  *   phase1 produces coupled[1..] on the side stream (under the decoder recurrence of the caller's stream) and coupled[0],

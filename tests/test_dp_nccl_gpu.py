@@ -54,6 +54,46 @@ def _run_rank(rank, world, backend, device_index, full_mmd='global'):
     return torch.stack(out), flat.cpu(), all(torch.equal(gathered[0], g) for g in gathered[1:])
 
 
+def _run_rank_graphed(rank, world, device_index, steps=6):
+    """Perf-mode data-parallel iteration (Philox noise) through parallel.GraphedDPStepper with the captured graph and with
+    eager launches, from identical state: -> (graph was captured, scalars equal bit for bit, params equal, replicas equal)."""
+    import torch.distributed as dist
+    from cpg_b200 import engine, parallel
+    dev = torch.device('cuda', device_index)
+    Bl, L = 40, 25
+    tokens = ow.synthetic_tokens(Bl, V, seed=60 + rank).to(dev).contiguous()
+    res = []
+    for graph in (True, False):
+        st = engine.FlatState(V, dev)
+        if rank == 0:
+            st.load(ow.random_params(V, seed=5))
+        parallel.sync_replicas(st)
+        noise = engine.alloc_noise(Bl, L, dev, seed=77)
+        hp = engine.make_hparams(beta=1.0)
+        ds = parallel.GraphedDPStepper(st, Bl, L, hp, noise, 1234 + rank, Bl * world, graph=graph)
+        sc = [ds.step(tokens, it, 0.5 + 0.1 * it).clone() for it in range(steps)]
+        parallel.check_replicas(st)
+        res.append((ds.graph is not None, torch.stack(sc).cpu(), st.params.clone().cpu()))
+    (captured, sg, pg), (_, se, pe) = res
+    return captured, torch.equal(sg, se), torch.equal(pg, pe)
+
+
+def _worker_graphed(rank, world, port, ret):
+    import sys
+    from conftest import PKG
+    sys.path.insert(0, PKG)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        out = _run_rank_graphed(rank, world, rank)
+        if rank == 0:
+            ret['out'] = out
+    finally:
+        dist.destroy_process_group()
+
+
 def _worker(rank, world, port, backend, same_device, ret):
     import sys
     from conftest import PKG
@@ -128,3 +168,29 @@ def test_two_gpu_nccl_equals_single_gpu():
         pytest.skip('box has %d GPU; the same ranks-vs-single check runs above over gloo on one GPU, and the 2-GPU '
                     'NCCL result of this test is recorded in profiles/ (gpurun --gpus 2)' % torch.cuda.device_count())
     _compare(_spawn(2, 'nccl', False))
+
+
+def test_graphed_dp_stepper_world1_is_bit_identical_to_eager_launches():
+    """The captured data-parallel graph (collectives included) replays exactly what the eager launches compute."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(_free_port()))
+    torch.cuda.set_device(0)
+    dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda', 0))
+    try:
+        captured, same_scalars, same_params = _run_rank_graphed(0, 1, 0)
+    finally:
+        dist.destroy_process_group()
+    assert captured, 'the data-parallel graph was not captured'
+    assert same_scalars and same_params
+
+
+def test_graphed_dp_stepper_two_gpus_is_bit_identical_to_eager_launches():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('box has %d GPU (the world-1 NCCL variant runs above)' % torch.cuda.device_count())
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_graphed, args=(2, _free_port(), ret), nprocs=2, join=True)
+    captured, same_scalars, same_params = ret['out']
+    assert captured, 'the data-parallel graph was not captured'
+    assert same_scalars and same_params
