@@ -203,7 +203,7 @@ def setup_model(device):
 def run_strong(args, cfg, model, st, dev, world, rank, timed, hp):
     """Global batch 4096 split over the ranks (512 per GPU at N = 8); the log-only full-kernel MMD is the GLOBAL-batch
     value (all-gather of z).  Both kernel families are timed: the fp32 SIMT kernels the library picks by
-    itself below 1024 rows per GPU, and the tcgen05 kernels forced on."""
+    itself below 512 rows per GPU, and the tcgen05 kernels forced on."""
     import torch
     import utils
     from cpg_b200 import _lib, engine, parallel, synth

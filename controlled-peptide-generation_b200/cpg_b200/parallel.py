@@ -157,6 +157,31 @@ def dp_train_step(state, tokens, noise, hp, p_out=0.3, group=None, full_mmd='loc
     return scalars
 
 
+_LIVE_STEPPERS = None
+
+
+def release_graphs():
+    """Drop every captured data-parallel graph of this process (see GraphedDPStepper.release)."""
+    for ds in list(_LIVE_STEPPERS or ()):
+        ds.release()
+
+
+def _track(stepper):
+    """Remember the stepper and make dist.destroy_process_group() release the captured graphs first: a live graph that
+    holds captured collectives keeps the communicator busy at teardown (the process would hang at exit)."""
+    global _LIVE_STEPPERS
+    if _LIVE_STEPPERS is None:
+        import weakref
+        _LIVE_STEPPERS = weakref.WeakSet()
+        inner = dist.destroy_process_group
+
+        def destroy_process_group(*a, **kw):
+            release_graphs()
+            return inner(*a, **kw)
+        dist.destroy_process_group = destroy_process_group
+    _LIVE_STEPPERS.add(stepper)
+
+
 class GraphedDPStepper:
     """The perf-mode data-parallel iteration (Philox noise + dp_train_step, collectives included) as ONE captured CUDA graph
     per rank, replayed every step: the ~35 kernels, the three all-reduces and the fork / join of the library's lanes cost one
@@ -178,6 +203,7 @@ class GraphedDPStepper:
         self.want_graph = bool(graph) and full_mmd == 'local'
         self.graph, self.scalars, self.calls = None, None, 0
         self.force_eager = False                          # e.g. while the per-kernel profiler is on (it sees eager launches only)
+        _track(self)
 
     def _body(self, it):
         _engine.fill_step_noise(self.noise, self.seed, it, self.p_word, self.p_out, overlap=True)
@@ -209,7 +235,7 @@ class GraphedDPStepper:
             import gc
             gc.collect()
             torch.cuda.synchronize(self.dev)
-        self.want_graph = False
+            self.calls = 0                                # (a later step() captures again after two eager iterations)
 
     def _capture(self, it):
         torch.cuda.synchronize(self.dev)

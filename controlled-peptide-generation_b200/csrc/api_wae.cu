@@ -271,7 +271,7 @@ static void noise_join(cpg_ctx*, cudaStream_t) {}
 // tiny batches stay on the 32-row fp32 SIMT kernels.  g_opt_gru_tc: 0 = never, 1 = auto, 2 = always.
 int g_opt_gru_tc = 1;
 #ifndef CPG_EMU
-static bool use_gru_tc(int B) { return g_opt_gru_tc == 2 || (g_opt_gru_tc == 1 && B >= 1024); }
+static bool use_gru_tc(int B) { return g_opt_gru_tc == 2 || (g_opt_gru_tc == 1 && B >= 512); }
 #else
 static bool use_gru_tc(int) { return false; }
 #endif

@@ -427,9 +427,9 @@ int launch_fwd(cudaStream_t s, const LatFwdArgs& a) {
 }
 }  // namespace
 
-int g_opt_latent_tc = 1;      // 1: tcgen05 dense layers when B >= 1024, 2: always, 0: fp32 SIMT GEMMs + element-wise kernels
+int g_opt_latent_tc = 1;      // 1: tcgen05 dense layers when B >= 512, 2: always, 0: fp32 SIMT GEMMs + element-wise kernels
 int g_opt_latent_rows = 64;   // batch rows per CTA of the forward kernel (64 | 128)
-bool latent_uses_tc(int B) { return g_opt_latent_tc == 2 || (g_opt_latent_tc == 1 && B >= 1024); }
+bool latent_uses_tc(int B) { return g_opt_latent_tc == 2 || (g_opt_latent_tc == 1 && B >= 512); }
 
 int launch_latent_fwd_tc(cudaStream_t s, const float* hfin, const float* bmu, const float* blv, const float* eps, const float* c,
                          const unsigned char* tiles, int B, float* mu, float* logvar, float* z, float* zc, float* rowbias) {

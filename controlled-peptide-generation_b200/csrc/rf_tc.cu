@@ -272,8 +272,8 @@ bool set_smem(const void* fn, size_t bytes) {
 }
 }  // namespace
 
-int g_opt_rf_tc = 1;          // 1: tcgen05 random-feature kernels when B >= 1024, 2: always, 0: fp32 SIMT GEMMs
-bool rf_uses_tc(int B, int R) { return R % 4 == 0 && R >= 16 && (g_opt_rf_tc == 2 || (g_opt_rf_tc == 1 && B >= 1024)); }
+int g_opt_rf_tc = 1;          // 1: tcgen05 random-feature kernels when B >= 512, 2: always, 0: fp32 SIMT GEMMs
+bool rf_uses_tc(int B, int R) { return R % 4 == 0 && R >= 16 && (g_opt_rf_tc == 2 || (g_opt_rf_tc == 1 && B >= 512)); }
 int rf_tc_halves(int R) { return ceil_div(R, RF_NH); }
 size_t rf_tc_tile_bytes(int R) { return (size_t)rf_tc_halves(R) * 4 * RF_TERM; }
 int rf_tc_parts(int B) { return 4 * ceil_div(B, RF_MF); }

@@ -71,7 +71,9 @@ def _train_fused(cfgv, model, dataset):
         # rank-distinct noise rows; rf_w / rf_b come from the shared seed inside alloc_noise
         rank_seed = (seed + 0x9E3779B97F4A7C15 * (1 + parallel.dist.get_rank())) % (1 << 63)
     stepper, global_batch = None, None
-    dp_steppers = {}                                  # data parallel: (compute_full_mmd, B, L) -> parallel.GraphedDPStepper
+    # data parallel: (compute_full_mmd, B, L, settings) -> parallel.GraphedDPStepper, kept on the state across calls (the
+    # captured graph is valid as long as the flat buffers it reads are: they belong to this state)
+    dp_steppers = st.__dict__.setdefault('_dp_steppers', {})
     it_range, write = _progress(range(cfgv.s_iter, cfgv.s_iter + cfgv.n_iter + 1))
     last_it = cfgv.s_iter + cfgv.n_iter
     # Host batches go to the device one iteration ahead, on a copy stream, into one of two buffers: the H2D copy of
@@ -120,12 +122,14 @@ def _train_fused(cfgv, model, dataset):
         if distributed:
             # one captured graph per rank (noise + both phases + the collectives + clip/Adam); the log-only full-kernel MMD is
             # evaluated on some iterations only, so there is one stepper (and graph) per value of that switch
-            key = (int(hp.compute_full_mmd), B, L)
+            hp_k = type(hp).from_buffer_copy(hp)
+            hp_k.adam_step, hp_k.beta, hp_k.global_batch = 0, 0.0, 0          # per-step / per-call fields are not part of the key
+            mode = str(getattr(cfg.b200, 'dp_full_mmd', 'local'))
+            key = (B, L, rank_seed, p_word, p_out, mode, int(global_batch), bytes(hp_k))
             ds = dp_steppers.get(key)
             if ds is None:
-                hp_k = type(hp).from_buffer_copy(hp)
-                ds = parallel.GraphedDPStepper(st, B, L, hp_k, stepper.noise, rank_seed, global_batch, p_word=p_word, p_out=p_out,
-                                               full_mmd=str(getattr(cfg.b200, 'dp_full_mmd', 'local')),
+                ds = parallel.GraphedDPStepper(st, B, L, type(hp).from_buffer_copy(hp), stepper.noise, rank_seed, global_batch,
+                                               p_word=p_word, p_out=p_out, full_mmd=mode,
                                                graph=bool(getattr(cfg.b200, 'dp_graph', True)))
                 dp_steppers[key] = ds
             scal = ds.step(tok, it, beta)
@@ -164,8 +168,6 @@ def _train_fused(cfgv, model, dataset):
     if pending_read is not None:
         pending_read[1].synchronize()
         last_scalars = pending_read[0].clone()
-    for ds in dp_steppers.values():                   # no live graph with captured collectives once training is over
-        ds.release()
     return st
 
 

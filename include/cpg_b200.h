@@ -357,15 +357,15 @@ int cpg_logreg_stats_len(void);
  * fill the chip; the fp32 SIMT kernels stay for small batches and are what the parity tests compare with):
  *   "mmd_tensor_core"     1 (default) persistent tcgen05 Gram kernel (tf32), 3 one tile per CTA, 0 fp32 SIMT
  *   "wgrad_tensor_core"   1 (default) tf32 tcgen05 weight / token-table gradients when B*L >= 8192, 2 always, 0 never
- *   "gru_tensor_core"     1 (default) split-bf16 tcgen05 recurrences (forward + BPTT) when B >= 1024, 2 always, 0 never
+ *   "gru_tensor_core"     1 (default) split-bf16 tcgen05 recurrences (forward + BPTT) when B >= 512, 2 always, 0 never
  *   "dec_out_tensor_core" 1 (default) tcgen05 decoder-output layer when B*L >= 8192, 2 always, 0 never
  *   "bptt_fused"          1 (default) on the tcgen05 path the BPTT kernels also contract dW_hh and the token-table gradient
  *                         (the gate-gradient planes never reach HBM), 0 = separate tf32 weight-gradient kernels
  *   "latent_tensor_core"  1 (default) the dense layers around the latent code (heads, [z;c] projection and their backward) as two
- *                         fused split-bf16 tcgen05 kernels when B >= 1024, 2 always, 0 fp32 SIMT GEMMs + element-wise kernels
+ *                         fused split-bf16 tcgen05 kernels when B >= 512, 2 always, 0 fp32 SIMT GEMMs + element-wise kernels
  *   "latent_tile_rows"    64 (default) | 128: batch rows per CTA of the forward latent kernel
  *   "rf_tensor_core"      1 (default) random-feature map and its gradient (RF-MMD) as split-precision tcgen05 kernels when
- *                         B >= 1024 (rf_dim a multiple of 4), 2 always, 0 fp32 SIMT GEMMs + element-wise kernels
+ *                         B >= 512 (rf_dim a multiple of 4), 2 always, 0 fp32 SIMT GEMMs + element-wise kernels
  *   "adam_fused"          1 (default) sum of squares, norm, clip and Adam in ONE launch (grid-wide barrier), 0 two launches
  *   "chain_priority"      1 (default) the dependent chain of the fused step runs on a highest-priority internal stream
  *                         (forked from / joined to the caller's), 0 = on the caller's stream
