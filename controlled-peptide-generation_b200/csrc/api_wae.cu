@@ -287,8 +287,15 @@ static Mark forward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, con
     cudaStream_t s = ln.m;
     // the derived weight forms only depend on the parameters: their lane runs beside the token preparation
     order(ctx, ln, s, ln.t);
-    launch_prep_weights(ln.t, params, lay, V, w.d);
-    const Mark weights_ready = mark(ctx, ln, ln.t);
+    Mark weights_ready = nullptr, rest_ready = nullptr;
+    if (ln.on) {
+        launch_prep_weights(ln.t, params, lay, V, w.d, 1);      // what the encoder recurrence reads ...
+        weights_ready = mark(ctx, ln, ln.t);
+        launch_prep_weights(ln.t, params, lay, V, w.d, 2);      // ... the rest lands under it
+        rest_ready = mark(ctx, ln, ln.t);
+    } else {
+        launch_prep_weights(s, params, lay, V, w.d, 3);
+    }
     // gen: this step's noise is drawn here -- the word-dropout mask inside the token preparation, the rest on lane s
     // once the preparation is through (its first reader, the latent layers, joins it)
     launch_prep_tokens(s, in->tokens, in->word_drop, B, L, V, w.tok, w.tokd, w.tgt, ctx->ints, ctx->ints + 1, gen);
@@ -326,6 +333,7 @@ static Mark forward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, con
     } else {
         launch_gru_fwd_enc(s, enc, B, L);
     }
+    wait_mark(s, rest_ready);
     noise_join(ctx, s);                             // eps, c (and the out-dropout mask) of cpg_fill_step_noise_overlapped
     if (latent_uses_tc(B)) {
         // heads -> reparameterisation -> [z;c] -> its input projection, one tcgen05 kernel (latent_tc.cu)

@@ -87,7 +87,8 @@ void launch_step_noise(cudaStream_t s, const StepNoiseArgs& a, int part);
 
 void launch_prep_tokens(cudaStream_t s, const int64_t* tokens, const uint8_t* word_drop, int B, int L, int V,
                         uint8_t* tok, uint8_t* tokd, uint8_t* tgt, int* ntok, int* err, const StepNoiseArgs* gen = nullptr);
-void launch_prep_weights(cudaStream_t s, const float* params, const ParamLayout& lay, int V, const Derived& d);
+// part: 1 = the forms the encoder recurrence reads, 2 = all the others, 3 = everything in one launch
+void launch_prep_weights(cudaStream_t s, const float* params, const ParamLayout& lay, int V, const Derived& d, int part = 3);
 
 void launch_gru_fwd_enc(cudaStream_t s, const GruSeq* two_dirs, int B, int L);
 void launch_gru_fwd_dec(cudaStream_t s, const GruSeq& seq, int B, int L);

@@ -103,8 +103,9 @@ struct PrepArgs {
 };
 
 // blockIdx.y selects the task; blockIdx.x strides over its elements.
-__global__ void k_prep_weights(PrepArgs a) {
-    const int task = blockIdx.y;
+// task_map: 4 bits per blockIdx.y = the task it runs (the encoder's forms are a launch of their own: its recurrence starts first)
+__global__ void k_prep_weights(PrepArgs a, unsigned long long task_map) {
+    const int task = (int)((task_map >> (4 * blockIdx.y)) & 15);
     const int stride = gridDim.x * blockDim.x;
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int V = a.V;
@@ -237,7 +238,7 @@ __global__ void k_prep_weights(PrepArgs a) {
 #endif
 }
 
-void launch_prep_weights(cudaStream_t s, const float* p, const ParamLayout& l, int V, const Derived& d) {
+void launch_prep_weights(cudaStream_t s, const float* p, const ParamLayout& l, int V, const Derived& d, int part) {
     PrepArgs a;
     a.emb = p + l.off[P_EMB];
     a.enc_wih[0] = p + l.off[P_ENC_WIH_F]; a.enc_whh[0] = p + l.off[P_ENC_WHH_F];
@@ -250,8 +251,17 @@ void launch_prep_weights(cudaStream_t s, const float* p, const ParamLayout& l, i
     a.wmu = p + l.off[P_QMU_W]; a.wlv = p + l.off[P_QLV_W];
     a.d = d;
     a.V = V;
-    // 960 warps per table task: ~8 outputs per warp; tasks 8-11 (operand tiles of latent_tc.cu) only where they are used
-    CPG_LAUNCH(k_prep_weights, dim3(120, d.lat_tiles != nullptr ? 12 : 8), 256, 0, s, a);
+    // 960 warps per table task: ~8 outputs per warp; tasks 8-11 (operand tiles of latent_tc.cu) only where they are used.
+    // part 1 = what the encoder recurrence needs (token tables and W_hh^T of both directions), part 2 = the rest
+    int tasks[12], n = 0;
+    if (part & 1) { tasks[n++] = 0; tasks[n++] = 1; tasks[n++] = 3; tasks[n++] = 4; }
+    if (part & 2) {
+        tasks[n++] = 2; tasks[n++] = 5; tasks[n++] = 6; tasks[n++] = 7;
+        if (d.lat_tiles != nullptr) { tasks[n++] = 8; tasks[n++] = 9; tasks[n++] = 10; tasks[n++] = 11; }
+    }
+    unsigned long long map = 0;
+    for (int i = 0; i < n; ++i) map |= (unsigned long long)tasks[i] << (4 * i);
+    CPG_LAUNCH(k_prep_weights, dim3(720, n), 256, 0, s, a, map);      // 5760 warps per task: one token-table output per warp
 }
 
 }  // namespace cpg
