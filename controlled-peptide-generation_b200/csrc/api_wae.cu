@@ -140,6 +140,7 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
     w.gemm_ws = a.take<float>((size_t)w.gemm_splits * 3 * DEC_HP * (2 * ENC_H));
     w.colsum_ws = a.take<float>((size_t)64 * 512);
     w.hg_part = a.take<float>((size_t)latent_bwd_tc_ctas(B) * LT_HG_ROWS * LT_HG_COLS);
+    w.wd_part = a.take<float>(wgrad_dense_part_floats(B));
     w.norm_part = a.take<float>(2 * sm + 8);
     w.clip_coef = a.take<float>(4);
     w.scalars = a.take<float>(SC_COUNT);
@@ -419,8 +420,10 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
     {
         order(ctx, ln, s, ln.t);
         // dW_ih[:,150:] = drow^T @ [z;c]  (a weight gradient: nothing on the BPTT chain waits for it)
-        launch_sgemm(ln.t, 3 * DEC_HP, DEC_HP, B, 1.f, w.drow, 1, 3 * DEC_HP, w.zc, DEC_HP, 1, 0.f, w.dwizc, DEC_HP,
-                     nullptr, w.gemm_splits, w.gemm_ws);
+        const bool wd_tc = latent_uses_tc(B) && g_opt_wgrad_dense_tc != 0;
+        if (wd_tc) launch_wgrad_zc_tc(ln.t, w.drow, w.zc, B, w.wd_part, w.dwizc);
+        else launch_sgemm(ln.t, 3 * DEC_HP, DEC_HP, B, 1.f, w.drow, 1, 3 * DEC_HP, w.zc, DEC_HP, 1, 0.f, w.dwizc, DEC_HP,
+                          nullptr, w.gemm_splits, w.gemm_ws);
         if (fused) {
             launch_wgrad_partial_reduce(ln.t, DEC_HP, DEC_H, V, w.wg_part_dec, w.dt_part_dec, bptt_fused_ctas_dec(B),
                                         grads + lay.off[P_DEC_WHH], w.dT_dec);
@@ -439,11 +442,15 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
     if (latent_uses_tc(B)) {
         // gradient at [z;c] -> latent backward -> gradient at the encoder's final hidden state, one tcgen05 kernel
         wait_mark(s, dz_ready);                     // dz_rf produced on lane s
-        launch_latent_bwd_tc(s, w.drow, w.dh0, w.d.lat_tiles, la, w.dhfin, w.hfin, w.hg_part);
-        // ... which also contracted the head weight / bias gradients over its rows: ordered sum of the partials on lane t
+        const bool wd_tc = g_opt_wgrad_dense_tc != 0;
+        launch_latent_bwd_tc(s, w.drow, w.dh0, w.d.lat_tiles, la, w.dhfin, w.hfin, wd_tc ? nullptr : w.hg_part);
+        // head weight / bias gradients on lane t: a batch contraction of their own, or (option off) the ordered sum of the
+        // partials the kernel above contracted over its rows
         order(ctx, ln, s, ln.t);
-        launch_head_grad_reduce(ln.t, w.hg_part, B, grads + lay.off[P_QMU_W], grads + lay.off[P_QLV_W], grads + lay.off[P_QMU_B],
-                                grads + lay.off[P_QLV_B]);
+        if (wd_tc) launch_wgrad_heads_tc(ln.t, w.dmu, w.dlv, w.hfin, B, w.wd_part, grads + lay.off[P_QMU_W], grads + lay.off[P_QLV_W],
+                                         grads + lay.off[P_QMU_B], grads + lay.off[P_QLV_B]);
+        else launch_head_grad_reduce(ln.t, w.hg_part, B, grads + lay.off[P_QMU_W], grads + lay.off[P_QLV_W], grads + lay.off[P_QMU_B],
+                                     grads + lay.off[P_QLV_B]);
     } else {
         // gradient at [z;c]:  dh0 + drow @ W_ih[:,150:]   (in place on dh0)
         launch_sgemm(s, B, DEC_HP, 3 * DEC_HP, 1.f, w.drow, 3 * DEC_HP, 1, w.d.wizc, DEC_HP, 1, 1.f, w.dh0, DEC_HP,
@@ -1010,7 +1017,7 @@ int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, fl
              (void*)nb->word_drop, (void*)nb->out_keep, (void*)nb->z_prior_full, (void*)nb->z_prior_rf, (void*)nb->rf_w, (void*)nb->rf_b,
              hp->lr, hp->beta1, hp->beta2, hp->adam_eps, hp->clip_norm, hp->lambda_logvar_l1, hp->lambda_logvar_kl, hp->z_regu,
              hp->mmd_sigma, hp->rf_dim, hp->compute_full_mmd, hp->beta != 0.f ? 1 : 0, (unsigned long long)seed, p_word, p_out,
-             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority + 131072 * g_opt_rf_tc + 524288 * g_opt_adam_fused);
+             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority + 131072 * g_opt_rf_tc + 524288 * g_opt_adam_fused + 1048576 * g_opt_wgrad_dense_tc);
     StepGraph* g = find_graph(kb + std::string(scalars ? std::to_string((uintptr_t)scalars) : ""));
     StepDyn* dyn_dev = reinterpret_cast<StepDyn*>(ctx->ints + 32);
     const StepDyn dv = make_dyn(hp, noise_step);

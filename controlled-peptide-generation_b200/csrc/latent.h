@@ -92,6 +92,12 @@ int launch_rf_feat_tc(cudaStream_t s, const float* x, const unsigned char* tiles
 int launch_rf_grad_tc(cudaStream_t s, const float* pre, const unsigned char* tiles, const float* rf_b, const float* coef, int B, int R,
                       float sigma, float* dz);
 void launch_rf_colsum_final(cudaStream_t s, const float* part, int nchunk, int R, float* out);
+// weight gradients of the dense layers around the latent code as batch contractions on tcgen05 (wgrad_dense_tc.cu)
+extern int g_opt_wgrad_dense_tc;     // 1 (default): on the reduction lane with these kernels; 0: head gradients inside k_latent_bwd_tc, dW_ih[:,150:] fp32 SIMT
+size_t wgrad_dense_part_floats(int B);
+int launch_wgrad_zc_tc(cudaStream_t s, const float* drow, const float* zc, int B, float* part, float* dwizc);
+int launch_wgrad_heads_tc(cudaStream_t s, const float* dmu, const float* dlv, const float* hfin, int B, float* part, float* g_wmu,
+                          float* g_wlv, float* g_bmu, float* g_blv);
 void launch_compose_scalars(cudaStream_t s, const ComposeArgs& a);
 // data-parallel tail: extra floats all-reduced together with the flat gradient ([0] = NLL sum; rest reserved)
 constexpr int DP_TAIL = 8;

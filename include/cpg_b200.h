@@ -366,6 +366,9 @@ int cpg_logreg_stats_len(void);
  *   "latent_tile_rows"    64 (default) | 128: batch rows per CTA of the forward latent kernel
  *   "rf_tensor_core"      1 (default) random-feature map and its gradient (RF-MMD) as split-precision tcgen05 kernels when
  *                         B >= 512 (rf_dim a multiple of 4), 2 always, 0 fp32 SIMT GEMMs + element-wise kernels
+ *   "wgrad_dense_tensor_core" 1 (default) head / [z;c]-projection weight gradients as split-bf16 tcgen05 batch contractions on
+ *                         the reduction stream (where the tcgen05 latent layers are on), 0 head gradients inside the latent
+ *                         backward kernel + dW_ih[:,150:] as an fp32 SIMT product
  *   "adam_fused"          1 (default) sum of squares, norm, clip and Adam in ONE launch (grid-wide barrier), 0 two launches
  *   "chain_priority"      1 (default) the dependent chain of the fused step runs on a highest-priority internal stream
  *                         (forked from / joined to the caller's), 0 = on the caller's stream
