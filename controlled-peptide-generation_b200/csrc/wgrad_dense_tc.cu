@@ -199,7 +199,7 @@ int launch_wd(cudaStream_t s, const WdArgs& a, int mtot) {
 }
 }  // namespace
 
-int g_opt_wgrad_dense_tc = 1;
+int g_opt_wgrad_dense_tc = 0;      // (1 once verified on the GPU)
 int wgrad_dense_ctas(int B) { return std::min(WD_GRID, ceil_div(B, WD_ROWS)); }
 size_t wgrad_dense_part_floats(int B) { return (size_t)wgrad_dense_ctas(B) * 320 * 176; }
 
