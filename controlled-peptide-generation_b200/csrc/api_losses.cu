@@ -158,6 +158,9 @@ int cpg_set_option(const char* name, int value) {
     if (strcmp(name, "latent_tensor_core") == 0) { g_opt_latent_tc = value; return CPG_OK; }
     if (strcmp(name, "rf_tensor_core") == 0) { g_opt_rf_tc = value; return CPG_OK; }
     if (strcmp(name, "wgrad_dense_tensor_core") == 0) { g_opt_wgrad_dense_tc = value; return CPG_OK; }
+    if (strcmp(name, "rf_grid") == 0) { g_opt_rf_grid = value; return CPG_OK; }
+    if (strcmp(name, "wgrad_dense_grid") == 0) { g_opt_wd_grid = value < 64 ? value : 64; return CPG_OK; }
+    if (strcmp(name, "mmd_grid") == 0) { g_opt_mmd_grid = value; return CPG_OK; }
     if (strcmp(name, "adam_fused") == 0) { g_opt_adam_fused = value; return CPG_OK; }
     if (strcmp(name, "chain_priority") == 0) { g_opt_chain_priority = value; return CPG_OK; }
     if (strcmp(name, "latent_tile_rows") == 0) {

@@ -882,8 +882,15 @@ static int phase2_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, flo
             launch_int_to_float(q, ctx->ints, const_cast<float*>(coupled) + 0, 1);
             launch_latent_stats(q, w.mu, w.logvar, B, w.lat_part, w.lat_nparts, const_cast<float*>(coupled) + 2);
         }
-        if (want_mmd)
-            if ((rc = launch_mmd_full(q, w.z, nz->z_prior_full, B, hp->mmd_sigma, w.mmd_ws, w.mmd_out))) return rc;
+        if (want_mmd) {
+            // beside the chain the persistent Gram kernel runs on a part of the SMs only: a CTA per SM holds back CTAs of the
+            // BPTT kernels that start under it (measured: 0.648 -> 0.629 ms/step with 64 CTAs instead of 148)
+            const int saved = g_opt_mmd_grid;
+            if (saved == 0 && ln.on) g_opt_mmd_grid = 64;
+            rc = launch_mmd_full(q, w.z, nz->z_prior_full, B, hp->mmd_sigma, w.mmd_ws, w.mmd_out);
+            g_opt_mmd_grid = saved;
+            if (rc) return rc;
+        }
     }
     // reconstruction loss fwd+bwd with the global token count
     DecOutArgs a = dec_out_args(ctx, in, V, B, L);
@@ -1017,7 +1024,7 @@ int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, fl
              (void*)nb->word_drop, (void*)nb->out_keep, (void*)nb->z_prior_full, (void*)nb->z_prior_rf, (void*)nb->rf_w, (void*)nb->rf_b,
              hp->lr, hp->beta1, hp->beta2, hp->adam_eps, hp->clip_norm, hp->lambda_logvar_l1, hp->lambda_logvar_kl, hp->z_regu,
              hp->mmd_sigma, hp->rf_dim, hp->compute_full_mmd, hp->beta != 0.f ? 1 : 0, (unsigned long long)seed, p_word, p_out,
-             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority + 131072 * g_opt_rf_tc + 524288 * g_opt_adam_fused + 1048576 * g_opt_wgrad_dense_tc);
+             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority + 131072 * g_opt_rf_tc + 524288 * g_opt_adam_fused + 1048576 * g_opt_wgrad_dense_tc + 2097152 * (g_opt_mmd_grid & 255) + g_opt_rf_grid * 7 + g_opt_wd_grid * 13);
     StepGraph* g = find_graph(kb + std::string(scalars ? std::to_string((uintptr_t)scalars) : ""));
     StepDyn* dyn_dev = reinterpret_cast<StepDyn*>(ctx->ints + 32);
     const StepDyn dv = make_dyn(hp, noise_step);

@@ -471,7 +471,10 @@ int launch_dec_out_tc(cudaStream_t s, const DecOutArgs& a, int sm_count, int* pa
         attr_set = true;
     }
     const int ntiles = ceil_div(a.B * a.L, TR);
-    const int grid = max(1, min(ntiles, sm_count));
+    // the smallest grid with the same number of tiles on the busiest CTA (800 tiles: 134 CTAs x 6 instead of 148): the SMs
+    // left over run the kernels of the other lanes, whose CTAs would otherwise hold back CTAs of this kernel
+    const int per_cta = ceil_div(ntiles, max(1, min(ntiles, sm_count)));
+    const int grid = max(1, ceil_div(ntiles, per_cta));
     CPG_LAUNCH_NAMED("k_dec_out_tc", k_dec_out_tc, grid, NTH, SMEM_TOTAL, s, a);
     *parts_out = grid;
     return CPG_OK;

@@ -55,6 +55,7 @@ int launch_mmd_full_tc2(cudaStream_t s, const float* z, const float* zp, int N, 
                         float* out);
 // dz = w * d mmd_full_kernel(z, zp) / dz   (fp32 SIMT)
 void launch_mmd_full_grad(cudaStream_t s, const float* z, const float* zp, int N, float sigma, float w, float* dz);
+extern int g_opt_mmd_grid;   // mmd_tc2.cu
 extern int g_opt_mmd_tc;     // 0 = fp32 SIMT, 1 = persistent tcgen05 (default), 3 = one-tile-per-CTA tcgen05
 extern int g_sm_count;
 // tcgen05 versions of the dense layers around the latent code, fused with the element-wise work (latent_tc.cu).
@@ -82,7 +83,7 @@ int launch_latent_bwd_tc(cudaStream_t s, const float* drow, const float* dh0, co
                          float* dhfin, const float* hfin, float* hg_part);
 void launch_head_grad_reduce(cudaStream_t s, const float* hg_part, int B, float* g_wmu, float* g_wlv, float* g_bmu, float* g_blv);
 // tcgen05 random-feature kernels (rf_tc.cu): pre-split rf_w tiles, feature map + column partials, gradient
-extern int g_opt_rf_tc;
+extern int g_opt_rf_tc, g_opt_rf_grid, g_opt_wd_grid;
 bool rf_uses_tc(int B, int R);
 size_t rf_tc_tile_bytes(int R);
 int rf_tc_parts(int B);                  // rows of the column-sum partials written by launch_rf_feat_tc

@@ -189,6 +189,7 @@ k_mmd_gram_tc2(const __grid_constant__ CUtensorMap tmap, const float* __restrict
     if (warp == 5) tc::tmem_dealloc<256>(tmem_d);
 }
 
+int g_opt_mmd_grid = 0;      // CTAs of the persistent Gram kernel (0 = one per SM)
 int launch_mmd_full_tc2(cudaStream_t s, const float* z, const float* zp, int N, float sigma, int sm_count, float* ws,
                         float* out) {
     const int M2 = 2 * N;
@@ -200,7 +201,7 @@ int launch_mmd_full_tc2(cudaStream_t s, const float* z, const float* zp, int N, 
     int ndiag = std::max(1, std::min(256, ceil_div(N, 8)));
     int n_items = 0;
     for (int ti = 0; ti < T; ++ti) n_items += ceil_div(T - ti, G2_CHUNK);
-    const int grid = std::max(1, std::min(n_items, sm_count));
+    const int grid = std::max(1, std::min(n_items, g_opt_mmd_grid > 0 ? g_opt_mmd_grid : sm_count));
     CUtensorMap tmap;
     int rc = make_tmap_2d_f32_sw128(&tmap, X, 128, (uint64_t)M2, (uint64_t)128 * sizeof(float), G2_T);
     if (rc) return rc;

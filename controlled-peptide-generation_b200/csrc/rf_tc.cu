@@ -272,6 +272,7 @@ bool set_smem(const void* fn, size_t bytes) {
 }
 }  // namespace
 
+int g_opt_rf_grid = 0;        // CTAs of the RF kernels (0 = RF_GRID)
 int g_opt_rf_tc = 1;          // 1: tcgen05 random-feature kernels when B >= 512, 2: always, 0: fp32 SIMT GEMMs
 bool rf_uses_tc(int B, int R) { return R % 4 == 0 && R >= 16 && (g_opt_rf_tc == 2 || (g_opt_rf_tc == 1 && B >= 512)); }
 int rf_tc_halves(int R) { return ceil_div(R, RF_NH); }
@@ -291,7 +292,7 @@ int launch_rf_feat_tc(cudaStream_t s, const float* x, const unsigned char* tiles
         set = true;
     }
     RfFeatArgs a{x, tiles, rf_b, pre_out, part, sigma, B, R, rf_tc_halves(R)};
-    CPG_LAUNCH(k_rf_feat_tc, std::min(RF_GRID, ceil_div(B, RF_MF)), LT_THREADS, FE_SMEM, s, a);
+    CPG_LAUNCH(k_rf_feat_tc, std::min(g_opt_rf_grid > 0 ? g_opt_rf_grid : RF_GRID, ceil_div(B, RF_MF)), LT_THREADS, FE_SMEM, s, a);
     return CPG_OK;
 }
 
@@ -303,7 +304,7 @@ int launch_rf_grad_tc(cudaStream_t s, const float* pre, const unsigned char* til
         set = true;
     }
     RfGradArgs a{pre, tiles, rf_b, coef, dz, sigma, B, R, rf_tc_halves(R)};
-    CPG_LAUNCH(k_rf_grad_tc, std::min(RF_GRID, ceil_div(B, RF_M)), LT_THREADS, GR_SMEM, s, a);
+    CPG_LAUNCH(k_rf_grad_tc, std::min(g_opt_rf_grid > 0 ? g_opt_rf_grid : RF_GRID, ceil_div(B, RF_M)), LT_THREADS, GR_SMEM, s, a);
     return CPG_OK;
 }
 

@@ -14,6 +14,7 @@
 #include "tc_dense.cuh"
 
 namespace cpg {
+int wgrad_dense_ctas(int B);
 namespace {
 constexpr int WD_ROWS = 64;                  // batch rows per tile = K of one MMA batch
 constexpr int WD_GRID = 16;
@@ -194,14 +195,15 @@ int launch_wd(cudaStream_t s, const WdArgs& a, int mtot) {
         }
         set_for = smem;
     }
-    CPG_LAUNCH(k_wgrad_dense_tc, std::min(WD_GRID, ceil_div(a.B, WD_ROWS)), LT_THREADS, smem, s, a);
+    CPG_LAUNCH(k_wgrad_dense_tc, wgrad_dense_ctas(a.B), LT_THREADS, smem, s, a);
     return CPG_OK;
 }
 }  // namespace
 
-int g_opt_wgrad_dense_tc = 0;      // (1 once verified on the GPU)
-int wgrad_dense_ctas(int B) { return std::min(WD_GRID, ceil_div(B, WD_ROWS)); }
-size_t wgrad_dense_part_floats(int B) { return (size_t)wgrad_dense_ctas(B) * 320 * 176; }
+int g_opt_wgrad_dense_tc = 1;
+int g_opt_wd_grid = 0;
+int wgrad_dense_ctas(int B) { return std::min(g_opt_wd_grid > 0 ? g_opt_wd_grid : WD_GRID, ceil_div(B, WD_ROWS)); }
+size_t wgrad_dense_part_floats(int B) { return (size_t)std::min(64, ceil_div(B, WD_ROWS)) * 320 * 176; }
 
 // dwizc [3*104][104] (padded layout) = drow^T [z;c]
 int launch_wgrad_zc_tc(cudaStream_t s, const float* drow, const float* zc, int B, float* part, float* dwizc) {
@@ -240,7 +242,7 @@ int launch_wgrad_heads_tc(cudaStream_t s, const float* dmu, const float* dlv, co
 }  // namespace cpg
 #else
 namespace cpg {
-int g_opt_wgrad_dense_tc = 0;
+int g_opt_wgrad_dense_tc = 1;
 int wgrad_dense_ctas(int) { return 1; }
 size_t wgrad_dense_part_floats(int) { return 16; }
 int launch_wgrad_zc_tc(cudaStream_t, const float*, const float*, int, float*, float*) { return CPG_ECUDA; }
