@@ -108,6 +108,8 @@ def kernel_work(B, L=SEQ_LEN, V=N_VOCAB, R=500):
         'k_latent_bwd_tc': (2 * B * (3 * Hd * (Z + 2) + 2 * 2 * Z * (2 * He)), 3 * B * Z * f4),
         # random-feature map (z read) and its gradient (dz written)
         'k_rf_feat_tc': (2 * B * Z * R, B * Z * f4), 'k_rf_grad_tc': (2 * B * Z * R, B * Z * f4),
+        # dW_ih[:,150:] and the head weight / bias gradients (two launches of one kernel: the mean of the two shapes)
+        'k_wgrad_dense_tc': (B * (3 * Hd * (Z + 2) + 2 * Z * (2 * He + 1)), 0),
     }
     # the dense layers, by shape label "MxNxK": heads (B x 100 x 160, x2 + transposes), [z;c] projection, RF map
     return w

@@ -424,15 +424,6 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
         if (wd_tc) launch_wgrad_zc_tc(ln.t, w.drow, w.zc, B, w.wd_part, w.dwizc);
         else launch_sgemm(ln.t, 3 * DEC_HP, DEC_HP, B, 1.f, w.drow, 1, 3 * DEC_HP, w.zc, DEC_HP, 1, 0.f, w.dwizc, DEC_HP,
                           nullptr, w.gemm_splits, w.gemm_ws);
-        if (fused) {
-            launch_wgrad_partial_reduce(ln.t, DEC_HP, DEC_H, V, w.wg_part_dec, w.dt_part_dec, bptt_fused_ctas_dec(B),
-                                        grads + lay.off[P_DEC_WHH], w.dT_dec);
-        } else {
-            const bool t2 = launch_wgrad_hh(ln.t, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, w.tokd, 0, V, B, L, sm, w.wg_part_dec,
-                                            w.dt_part_dec, grads + lay.off[P_DEC_WHH], w.dT_dec, nullptr, nullptr, dg_rounded);
-            if (!t2) launch_dtable(ln.t, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part_dec, w.dT_dec);
-        }
-        launch_input_grads(ln.t, ia, nullptr, 2);   // decoder W_ih / bias gradients: their inputs are complete
     }
     const float* wmu = params + lay.off[P_QMU_W];
     const float* wlv = params + lay.off[P_QLV_W];
@@ -467,6 +458,19 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
                      2 * ENC_H, nullptr, w.gemm_splits, w.gemm_ws);
         launch_colsum(ln.t, w.dmu, B, ZD, ZD, grads + lay.off[P_QMU_B], w.colsum_ws, 64);
         launch_colsum(ln.t, w.dlv, B, ZD, ZD, grads + lay.off[P_QLV_B], w.colsum_ws, 64);
+    }
+    // decoder W_hh / token-table sums and the decoder's input-side gradients: lane t, behind the head gradients (nothing waits
+    // for them before the end of the step, while the head gradients' operands are only complete now)
+    {
+        if (fused) {
+            launch_wgrad_partial_reduce(ln.t, DEC_HP, DEC_H, V, w.wg_part_dec, w.dt_part_dec, bptt_fused_ctas_dec(B),
+                                        grads + lay.off[P_DEC_WHH], w.dT_dec);
+        } else {
+            const bool t2 = launch_wgrad_hh(ln.t, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, w.tokd, 0, V, B, L, sm, w.wg_part_dec,
+                                            w.dt_part_dec, grads + lay.off[P_DEC_WHH], w.dT_dec, nullptr, nullptr, dg_rounded);
+            if (!t2) launch_dtable(ln.t, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part_dec, w.dT_dec);
+        }
+        launch_input_grads(ln.t, ia, nullptr, 2);   // decoder W_ih / bias gradients: their inputs are complete
     }
     // encoder BPTT
     GruSeq enc[2];
