@@ -141,6 +141,7 @@ static size_t layout_workspace(cpg_ctx* ctx, Workspace& w, int B, int L, int V, 
     w.colsum_ws = a.take<float>((size_t)64 * 512);
     w.hg_part = a.take<float>((size_t)latent_bwd_tc_ctas(B) * LT_HG_ROWS * LT_HG_COLS);
     w.wd_part = a.take<float>(wgrad_dense_part_floats(B));
+    w.emb_dec = a.take<float>((size_t)VMAX * EMB);
     w.norm_part = a.take<float>(2 * sm + 8);
     w.clip_coef = a.take<float>(4);
     w.scalars = a.take<float>(SC_COUNT);
@@ -397,6 +398,7 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
     ia.dec_wih = params + lay.off[P_DEC_WIH];
     ia.dT_enc[0] = w.dT_enc[0]; ia.dT_enc[1] = w.dT_enc[1]; ia.dT_dec = w.dT_dec; ia.dwizc = w.dwizc;
     ia.g_emb = grads + lay.off[P_EMB];
+    ia.emb_dec = w.emb_dec;
     ia.g_enc_wih[0] = grads + lay.off[P_ENC_WIH_F]; ia.g_enc_bih[0] = grads + lay.off[P_ENC_BIH_F];
     ia.g_enc_bhh[0] = grads + lay.off[P_ENC_BHH_F];
     ia.g_enc_wih[1] = grads + lay.off[P_ENC_WIH_R]; ia.g_enc_bih[1] = grads + lay.off[P_ENC_BIH_R];
@@ -470,7 +472,7 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
                                             w.dt_part_dec, grads + lay.off[P_DEC_WHH], w.dT_dec, nullptr, nullptr, dg_rounded);
             if (!t2) launch_dtable(ln.t, DEC_HP, w.dec_dg, w.tokd, B, L, 0, V, sm, w.dt_part_dec, w.dT_dec);
         }
-        launch_input_grads(ln.t, ia, nullptr, 2);   // decoder W_ih / bias gradients: their inputs are complete
+        launch_input_grads(ln.t, ia, nullptr, 2 | 8);   // decoder W_ih / bias gradients, its share of the embedding gradient
     }
     // encoder BPTT
     GruSeq enc[2];

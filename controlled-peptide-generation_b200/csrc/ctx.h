@@ -25,7 +25,7 @@ struct Workspace {
     float *mmd_ws, *mmd_out, *mmdrf_out;
     float *do_part_w, *do_part_b, *do_part_nll, *nll_sum;
     float *wg_part, *dt_part, *wg_part_dec, *dt_part_dec, *wg_part_enc1, *dt_part_enc1, *dT_enc[2], *dT_dec, *dwizc;
-    float *gemm_ws, *colsum_ws, *hg_part, *wd_part;
+    float *gemm_ws, *colsum_ws, *hg_part, *wd_part, *emb_dec;
     float *norm_part, *clip_coef, *scalars, *ntok_f, *coupled;
     int lat_nparts, rf_nchunk, gemm_splits;
 };

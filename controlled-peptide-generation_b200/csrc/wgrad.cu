@@ -262,23 +262,28 @@ __global__ void k_input_grads(InputGradArgs a, int task0) {
 // (model.py:47).  786-long contraction per output: EG_Y slices of g per output (short dependent chains), summed in
 // slice order.
 constexpr int EG_Y = 32;
+// dec_part: the decoder table's share only (-> emb_dec; its inputs are complete long before the encoder's); else the two
+// encoder tables' shares + emb_dec -> g_emb
 __global__ void __launch_bounds__(RED_X * EG_Y)
-k_emb_grad(InputGradArgs a) {
+k_emb_grad(InputGradArgs a, int dec_part) {
     __shared__ float red_s[EG_Y][RED_X + 1];
     const int i = blockIdx.x * RED_X + threadIdx.x, y = threadIdx.y;
     const bool ok = i < a.V * EMB;
     const int v = ok ? i / EMB : 0, e = ok ? i % EMB : 0;
     float s0 = 0.f;
     if (ok && v != PAD) {
-        for (int d = 0; d < 2; ++d) {
-            const float* dT = a.dT_enc[d] + v * 4 * ENC_H;
-            const float* w = a.enc_wih[d];
-            for (int g = y; g < 3 * ENC_H; g += EG_Y) s0 = fmaf(dT[g], w[g * EMB + e], s0);
-        }
-        const float* dT = a.dT_dec + v * 4 * DEC_HP;
-        for (int g = y; g < 3 * DEC_H; g += EG_Y) {
-            const int gate = g / DEC_H, j = g % DEC_H;
-            s0 = fmaf(dT[gate * DEC_HP + j], a.dec_wih[(size_t)g * DEC_IN + e], s0);
+        if (dec_part) {
+            const float* dT = a.dT_dec + v * 4 * DEC_HP;
+            for (int g = y; g < 3 * DEC_H; g += EG_Y) {
+                const int gate = g / DEC_H, j = g % DEC_H;
+                s0 = fmaf(dT[gate * DEC_HP + j], a.dec_wih[(size_t)g * DEC_IN + e], s0);
+            }
+        } else {
+            for (int d = 0; d < 2; ++d) {
+                const float* dT = a.dT_enc[d] + v * 4 * ENC_H;
+                const float* w = a.enc_wih[d];
+                for (int g = y; g < 3 * ENC_H; g += EG_Y) s0 = fmaf(dT[g], w[g * EMB + e], s0);
+            }
         }
     }
     red_s[y][threadIdx.x] = s0;
@@ -287,15 +292,17 @@ k_emb_grad(InputGradArgs a) {
         float s = 0.f;
 #pragma unroll
         for (int q = 0; q < EG_Y; ++q) s += red_s[q][threadIdx.x];
-        a.g_emb[i] = s;
+        if (dec_part) a.emb_dec[i] = s;
+        else a.g_emb[i] = s + a.emb_dec[i];
     }
 }
-// parts: 1 = encoder tasks, 2 = decoder task, 4 = embedding gradient (needs all three token-table gradients)
+// parts: 1 = encoder tasks, 2 = decoder task, 8 = decoder share of the embedding gradient, 4 = embedding gradient (after 8)
 void launch_input_grads(cudaStream_t s, const InputGradArgs& a, cudaStream_t s_emb, int parts) {
     if ((parts & 3) == 3) CPG_LAUNCH(k_input_grads, dim3(148, 3), 256, 0, s, a, 0);
     else if (parts & 1) CPG_LAUNCH(k_input_grads, dim3(148, 2), 256, 0, s, a, 0);
     else if (parts & 2) CPG_LAUNCH(k_input_grads, dim3(148, 1), 256, 0, s, a, 2);
-    if (parts & 4) CPG_LAUNCH(k_emb_grad, CPG_RED_GRID(a.V * EMB), dim3(RED_X, EG_Y), 0, s_emb ? s_emb : s, a);   // independent of the kernel above
+    if (parts & 8) CPG_LAUNCH(k_emb_grad, CPG_RED_GRID(a.V * EMB), dim3(RED_X, EG_Y), 0, s_emb ? s_emb : s, a, 1);
+    if (parts & 4) CPG_LAUNCH(k_emb_grad, CPG_RED_GRID(a.V * EMB), dim3(RED_X, EG_Y), 0, s_emb ? s_emb : s, a, 0);   // independent of k_input_grads
 }
 
 }  // namespace cpg

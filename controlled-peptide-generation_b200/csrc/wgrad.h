@@ -11,6 +11,7 @@ struct InputGradArgs {
     const float* dT_dec;            // [V][4*104]
     const float* dwizc;             // [312][104] padded gradient of W_ih[:,150:]
     float* g_emb;
+    float* emb_dec;                 // [V][150] scratch: the decoder table's share of the embedding gradient (computed early)
     float* g_enc_wih[2]; float* g_enc_bih[2]; float* g_enc_bhh[2];
     float* g_dec_wih; float* g_dec_bih; float* g_dec_bhh;
     int V;
@@ -37,7 +38,8 @@ extern int g_opt_wgrad_tc;
 bool wgrad_uses_tc(int nrows);      // would launch_wgrad_hh take the tensor-core path for this many rows?
 void launch_dtable(cudaStream_t s, int HP, const float* dg, const uint8_t* tok, int B, int L, int reverse, int V,
                    int sm_count, float* part, float* dT);
-// s_emb: stream for the embedding gradient; parts: 1 = encoder W_ih / biases, 2 = decoder W_ih / biases, 4 = embedding
-void launch_input_grads(cudaStream_t s, const InputGradArgs& a, cudaStream_t s_emb = nullptr, int parts = 7);
+// s_emb: stream for the embedding gradient; parts: 1 = encoder W_ih / biases, 2 = decoder W_ih / biases,
+// 8 = the decoder table's share of the embedding gradient (-> emb_dec), 4 = embedding gradient (encoder tables + emb_dec)
+void launch_input_grads(cudaStream_t s, const InputGradArgs& a, cudaStream_t s_emb = nullptr, int parts = 15);
 
 }  // namespace cpg
