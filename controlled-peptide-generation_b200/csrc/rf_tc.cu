@@ -216,7 +216,7 @@ k_rf_grad_tc(RfGradArgs a) {
             // A half: G[b][r] = -coef[r] sin(pre[b][r] / sigma + b[r]), K-major (rows = batch, K = feature), split bf16;
             // warp-task = 8 rows x 16 features, lane = (row in block, float4 of the 64-byte piece)
             constexpr int NT = (RF_M / 8) * (RF_NH / 16);
-#pragma unroll 2
+#pragma unroll 4
             for (int t = warp; t < NT; t += LT_THREADS / 32) {
                 const int rb = t % (RF_M / 8), kg = t / (RF_M / 8);
                 const int r = rb * 8 + rl, k0 = kg * 16 + fl * 4, f0 = h * RF_NH + k0;

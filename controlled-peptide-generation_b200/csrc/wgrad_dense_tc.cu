@@ -65,6 +65,7 @@ k_wgrad_dense_tc(WdArgs a) {
         int cbase = 0;
         for (int t = 0; t < a.ntiles; ++t) {
             const WdTile T = a.t[t];
+#pragma unroll 4
             for (int i = tid; i < (T.M / 8) * WD_ROWS; i += LT_THREADS) {
                 const int b = i % WD_ROWS, mc = i / WD_ROWS, m = T.m0 + mc * 8;
                 float x[8];
@@ -87,6 +88,7 @@ k_wgrad_dense_tc(WdArgs a) {
             }
             cbase += T.M / 8;
         }
+#pragma unroll 3
         for (int i = tid; i < (a.N / 8) * WD_ROWS; i += LT_THREADS) {
             const int b = i % WD_ROWS, nc = i / WD_ROWS, n = nc * 8;
             float x[8];
