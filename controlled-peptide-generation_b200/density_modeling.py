@@ -26,6 +26,42 @@ def prior_logpdf(z):
     return float(sampling.prior_logpdf(z.reshape(1, -1).float().to(dev))[0])
 
 
+_RING = {}                                # device index -> (pinned uint8 [2, RING_BYTES], [event, event])
+RING_BYTES = 64 << 20
+
+
+def _to_host_chunked(tensors, dev):
+    """Fresh host tensors with the contents of the device tensors (any dtype / shape, contiguous)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _RING:
+        _RING[key] = (torch.empty(2, RING_BYTES, dtype=torch.uint8, pin_memory=True), [None, None])
+    ring, events = _RING[key]
+    stream = torch.cuda.current_stream(dev)
+    outs, jobs = [], []
+    for t in tensors:
+        t = t.contiguous()
+        out = torch.empty(t.shape, dtype=t.dtype)
+        outs.append(out)
+        src, dst = t.view(-1).view(torch.uint8), out.view(-1).view(torch.uint8)
+        for lo in range(0, src.numel(), RING_BYTES):
+            jobs.append((src, dst, lo, min(lo + RING_BYTES, src.numel())))
+    pending = None                                       # (slot, dst, lo, hi) whose D2H copy is in flight
+    for k, (src, dst, lo, hi) in enumerate(jobs):
+        slot = k & 1
+        ring[slot, :hi - lo].copy_(src[lo:hi], non_blocking=True)
+        events[slot] = stream.record_event()
+        if pending is not None:
+            ps, pd, plo, phi = pending
+            events[ps].synchronize()
+            pd[plo:phi].copy_(ring[ps, :phi - plo])
+        pending = (slot, dst, lo, hi)
+    if pending is not None:
+        ps, pd, plo, phi = pending
+        events[ps].synchronize()
+        pd[plo:phi].copy_(ring[ps, :phi - plo])
+    return outs
+
+
 class RejSampleBase:
     seed = 1238
     _draw_offset = 0
@@ -72,16 +108,12 @@ class RejSampleBase:
             out = sampling.class_sample(self._gmm_device(dev), spec, n_samples, self.seed, self._draw_offset)
             self._draw_offset += n_samples
             z, probs, accum, accept = out['z'], out['probs'], out['accum'], out['accept']
-        # device -> host through pinned staging (one async copy per array, one synchronise): the reference's return
-        # contract is host data -- z as a CPU tensor, scores / mask as numpy arrays
-        def to_host(t):
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            h.copy_(t, non_blocking=True)
-            return h
+        # device -> host: the reference's return contract is host data -- z as a CPU tensor, scores / mask as numpy arrays.
+        # Chunks go through a small pinned ring that lives across calls (pinning hundreds of MB per call costs more than the
+        # copy itself); the host copies chunk k out of the ring into the result while chunk k + 1 crosses PCIe.
         if spec.all_f32:                                 # float32 classifiers score in float32 (see the class docstring)
             probs, accum = probs.float(), accum.float()
-        hz, hp, ha, hm = to_host(z), to_host(probs), to_host(accum), to_host(accept)
-        torch.cuda.current_stream(dev).synchronize()
+        hz, hp, ha, hm = _to_host_chunked([z, probs, accum, accept], dev)
         scores_z = {}
         for i, name in enumerate(spec.names):
             scores_z['{}_{}={}'.format(prefix, name, spec.target[i])] = hp[i].numpy()
