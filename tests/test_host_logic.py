@@ -264,3 +264,32 @@ def test_vocab_and_peptide_formula_known_answers(tmp_path):
     want = (((h[0] + h[1] * np.cos(np.deg2rad(100))) ** 2 + (h[1] * np.sin(np.deg2rad(100))) ** 2) ** 0.5) / 2
     assert op.descriptors('AL')[1] == pytest.approx(want, rel=1e-12)
     assert op.drop_duplicates_first(['a', 'b', 'a', 'c', 'b']) == ([0, 1, 0, 3, 1], [1, 1, 0, 1, 0])
+
+
+def test_rejection_sample_host_copy_ring_logic(monkeypatch):
+    """density_modeling._to_host_chunked: chunks through a two-slot ring into fresh host tensors, every dtype the
+    sampler returns (fp32 z, fp64 / fp32 scores, bool mask), sizes below / across / at multiples of the ring size.
+    The CUDA pieces (pinned allocation, stream events) are replaced by host stand-ins: this checks the indexing."""
+    sys.path.insert(0, PKG)
+    import types
+    dm = importlib.import_module('density_modeling')
+
+    class Ev:
+        def synchronize(self):
+            pass
+
+    class St:
+        def record_event(self):
+            return Ev()
+
+    monkeypatch.setattr(dm, 'RING_BYTES', 1000)
+    monkeypatch.setitem(dm._RING, 0, (torch.empty(2, 1000, dtype=torch.uint8), [None, None]))
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda dev=None: St())
+    dev = types.SimpleNamespace(index=0)
+    g = torch.Generator().manual_seed(3)
+    ts = [torch.randn(37, 100, generator=g), torch.randn(3, 37, generator=g, dtype=torch.float64),
+          torch.randn(250, generator=g), torch.rand(37, generator=g) > 0.5, torch.zeros(0, 5), torch.randn(125, 2, generator=g)]
+    outs = dm._to_host_chunked(ts, dev)
+    for a, b in zip(ts, outs):
+        assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b)
+        assert b.data_ptr() != a.data_ptr() or a.numel() == 0
