@@ -422,6 +422,21 @@ def run_ours(args):
     ms_per_step = total_ms / K
     value = gb * K / (total_ms / 1e3)
 
+    # ---- reduced-precision mode (NOT the headline): BASELINE.json configs[2] names "bf16 matmul tiles"; option matmul_terms=1
+    # keeps only the leading bf16 product of every recurrence / decoder-output contraction (outside the parity bars)
+    reduced = None
+    if world == 1:
+        _lib.set_option('matmul_terms', 1)
+        for _ in range(max(W, 3)):
+            step()
+        r_ms = timed(step, K) / K
+        _lib.set_option('matmul_terms', 3)
+        for _ in range(3):
+            step()
+        reduced = {'option': 'matmul_terms=1 (single bf16 product in the recurrences and the decoder-output layer)', 'ms_per_step': r_ms,
+                   'seq_per_s': gb / (r_ms / 1e3), 'note': 'reduced precision, outside the parity bars (logits ~2e-3, gradients ~4e-3 of max '
+                   'vs the three-product configuration); the headline value above is the three-product fp32-grade configuration'}
+
     # ---- per-kernel durations (CUDA events around every launch of the same step, same stream)
     # The step overlaps its latency-bound loss / weight-gradient kernels with the recurrences on a side stream;
     # for the per-kernel pass everything is serialised on one stream so that each duration is the kernel's own.
@@ -516,6 +531,7 @@ def run_ours(args):
         'gpu_launches': launches, 'launches_per_step': launches / K,
         'profiled_ms_per_step': prof_ms / K,
         'roofline': roof, 'cpu_baseline': cpu, 'clocks': clock_summary, 'class': class_block, 'strong_scaling': strong,
+        'reduced_precision': reduced,
     }
     print(json.dumps(line))
     if world > 1:

@@ -158,6 +158,11 @@ int cpg_set_option(const char* name, int value) {
     if (strcmp(name, "latent_tensor_core") == 0) { g_opt_latent_tc = value; return CPG_OK; }
     if (strcmp(name, "rf_tensor_core") == 0) { g_opt_rf_tc = value; return CPG_OK; }
     if (strcmp(name, "wgrad_dense_tensor_core") == 0) { g_opt_wgrad_dense_tc = value; return CPG_OK; }
+    if (strcmp(name, "matmul_terms") == 0) {
+        if (value != 1 && value != 3) { set_error("matmul_terms must be 3 (split-bf16, fp32-grade) or 1 (single bf16 product)"); return CPG_EINVAL; }
+        g_opt_matmul_terms = value;
+        return CPG_OK;
+    }
     if (strcmp(name, "rf_grid") == 0) { g_opt_rf_grid = value; return CPG_OK; }
     if (strcmp(name, "wgrad_dense_grid") == 0) { g_opt_wd_grid = value < 64 ? value : 64; return CPG_OK; }
     if (strcmp(name, "mmd_grid") == 0) { g_opt_mmd_grid = value; return CPG_OK; }

@@ -379,6 +379,7 @@ static DecOutArgs dec_out_args(cpg_ctx* ctx, const cpg_wae_inputs* in, int V, in
     a.fc_w = w.d.fc_w; a.fc_b = w.d.fc_b; a.tgt = w.tgt;
     a.part_w = w.do_part_w; a.part_b = w.do_part_b; a.part_nll = w.do_part_nll;
     a.B = B; a.L = L; a.V = V;
+    a.nprod = g_opt_matmul_terms == 1 ? 1 : 3;
     return a;
 }
 
@@ -539,6 +540,7 @@ static AdamHyper adam_hyper(const cpg_train_hparams* hp) {
 // ------------------------------------------------------------------------------- captured iteration
 const StepDyn* g_dyn = nullptr;
 int g_opt_chain_priority = 1;         // 1: the fused step's dependent chain runs on the highest-priority internal stream
+int g_opt_matmul_terms = 3;           // 3: split-bf16 products (parity configuration), 1: single bf16 product (reduced precision)
 int g_opt_adam_fused = 1;             // 1: sum of squares + norm + clip + Adam in one launch (grid barrier), 0: two launches
 int g_opt_graph = 1;                  // 1: cpg_wae_train_step_philox replays a captured CUDA graph of the iteration
 __global__ void k_set_dyn(StepDyn v, StepDyn* __restrict__ dst) {
@@ -1030,7 +1032,7 @@ int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, fl
              (void*)nb->word_drop, (void*)nb->out_keep, (void*)nb->z_prior_full, (void*)nb->z_prior_rf, (void*)nb->rf_w, (void*)nb->rf_b,
              hp->lr, hp->beta1, hp->beta2, hp->adam_eps, hp->clip_norm, hp->lambda_logvar_l1, hp->lambda_logvar_kl, hp->z_regu,
              hp->mmd_sigma, hp->rf_dim, hp->compute_full_mmd, hp->beta != 0.f ? 1 : 0, (unsigned long long)seed, p_word, p_out,
-             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority + 131072 * g_opt_rf_tc + 524288 * g_opt_adam_fused + 1048576 * g_opt_wgrad_dense_tc + 2097152 * (g_opt_mmd_grid & 255) + g_opt_rf_grid * 7 + g_opt_wd_grid * 13);
+             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority + 131072 * g_opt_rf_tc + 524288 * g_opt_adam_fused + 1048576 * g_opt_wgrad_dense_tc + 2097152 * (g_opt_mmd_grid & 255) + g_opt_rf_grid * 7 + g_opt_wd_grid * 13 + g_opt_matmul_terms * 101);
     StepGraph* g = find_graph(kb + std::string(scalars ? std::to_string((uintptr_t)scalars) : ""));
     StepDyn* dyn_dev = reinterpret_cast<StepDyn*>(ctx->ints + 32);
     const StepDyn dv = make_dyn(hp, noise_step);

@@ -11,6 +11,7 @@ struct DecOutArgs {
     const float* fc_b;        // [VMAX]
     const uint8_t* tgt;       // [B][L]
     const float* ntok;        // device scalar: global number of non-<pad> targets
+    int nprod;                // 0 / 3: full-precision split products, 1: leading bf16 product only (g_opt_matmul_terms)
     const int* ntok_i;        // ... or, when not null, the same count as the integer the token preparation produced
     const float* dlogits_in;  // [B][L][V] upstream gradient (module API) or null
     float* logits_out;        // [B][L][V] or null

@@ -123,30 +123,34 @@ __device__ __forceinline__ void tmem_ld_16(uint32_t taddr, float (&v)[16]) {
 // three-product split-bf16 contraction over `ksteps` K slices of 16: A and B tiles with their two terms
 // `a_split` / `b_split` bytes apart
 __device__ __forceinline__ void mma_split3(uint32_t tmem_d, uint32_t a0, int a_split, int a_lbo, uint32_t b0, int b_split, int b_lbo,
-                                           int ksteps, uint32_t idesc, uint32_t acc) {
+                                           int ksteps, uint32_t idesc, uint32_t acc, int np = 3) {
     const int xs[3] = {0, 0, 1}, ws[3] = {0, 1, 0};
 #pragma unroll
-    for (int p = 0; p < 3; ++p)
+    for (int p = 0; p < 3; ++p) {
+        if (p >= np) break;
         for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t da = tc::make_smem_desc(a0 + xs[p] * a_split + ks * 2 * a_lbo, a_lbo, 128, 0);
             const uint64_t db = tc::make_smem_desc(b0 + ws[p] * b_split + ks * 2 * b_lbo, b_lbo, 128, 0);
             umma_bf16_ss(tmem_d, da, db, idesc, acc);
             acc = 1;
         }
+    }
 }
 // the same, both operands read MN-major from K-major tiles whose rows are this contraction's K: element (mn, k) of a tile
 // with chunk stride `lbo` sits at (mn >> 3) * lbo + (k >> 3) * 128 + (k & 7) * 16 + (mn & 7) * 2
 __device__ __forceinline__ void mma_split3_mn(uint32_t tmem_d, uint32_t a0, int a_split, int a_lbo, uint32_t b0, int b_split, int b_lbo,
-                                              int ksteps, uint32_t idesc, uint32_t acc) {
+                                              int ksteps, uint32_t idesc, uint32_t acc, int np = 3) {
     const int xs[3] = {0, 0, 1}, ws[3] = {0, 1, 0};
 #pragma unroll
-    for (int p = 0; p < 3; ++p)
+    for (int p = 0; p < 3; ++p) {
+        if (p >= np) break;
         for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t da = tc::make_smem_desc(a0 + xs[p] * a_split + ks * 256, 128, a_lbo, 0);
             const uint64_t db = tc::make_smem_desc(b0 + ws[p] * b_split + ks * 256, 128, b_lbo, 0);
             umma_bf16_ss(tmem_d, da, db, idesc, acc);
             acc = 1;
         }
+    }
 }
 }  // namespace
 
@@ -289,7 +293,8 @@ k_dec_out_tc(DecOutArgs a) {
             tc::tc_fence_after();
             if (elect_one()) {
                 const int xa[6] = {0, 0, 1, 1, 2, 0}, xb[6] = {0, 1, 0, 1, 0, 2};
-                mma_terms(tmem + TC_LG, s_hd, HD_SPLIT, LBO_R, s_wk, WK_SPLIT, LBO_V, KH / 16, idesc_bf16(128, VMAX), 0, xa, xb, 6);
+                mma_terms(tmem + TC_LG, s_hd, HD_SPLIT, LBO_R, s_wk, WK_SPLIT, LBO_V, KH / 16, idesc_bf16(128, VMAX), 0, xa, xb,
+                          a.nprod == 1 ? 1 : 6);
                 tc::umma_commit(&bar_m);
             }
             __syncwarp();
@@ -375,9 +380,9 @@ k_dec_out_tc(DecOutArgs a) {
         if (warp == 4) {
             tc::tc_fence_after();
             if (elect_one()) {
-                mma_split3(tmem + TC_DH, s_dl, DL_SPLIT, LBO_R, s_wt, WT_SPLIT, LBO_H, VMAX / 16, idesc_bf16(128, KH), 0);
+                mma_split3(tmem + TC_DH, s_dl, DL_SPLIT, LBO_R, s_wt, WT_SPLIT, LBO_H, VMAX / 16, idesc_bf16(128, KH), 0, a.nprod == 1 ? 1 : 3);
                 mma_split3_mn(tmem + TC_DW, s_hd, HD_SPLIT, LBO_R, s_dl, DL_SPLIT, LBO_R, TR / 16, idesc_bf16(128, VMAX, 1, 1),
-                              dw_started ? 1u : 0u);
+                              dw_started ? 1u : 0u, a.nprod == 1 ? 1 : 3);
                 tc::umma_commit(&bar_m);
             }
             __syncwarp();

@@ -122,6 +122,7 @@ struct FArgs {
     float* part_w[2];          // [gridDim.x][3*HP][HP] per direction
     float* part_t[2];          // [gridDim.x][V][4*HP]
     int B, L, V;
+    int nprod;                 // 3 | 1 (see g_opt_matmul_terms)
     int two_products;          // long reductions (B*L >= 8192 rows): the gradient contractions drop the x1 . h2 product
     int dbg;                   // developer timing probe (cpg_debug_bptt): skip parts of the work; 0 in production
     long long* tl;             // developer timeline probe: clock64 stamps of CTA (0,0) at step L/2, or null
@@ -204,6 +205,7 @@ k_gru_bwd_fused(FArgs a) {
                 if (!(a.dbg & 4)) {
 #pragma unroll
                     for (int p = 0; p < 3; ++p) {
+                        if (p >= a.nprod) break;
 #pragma unroll
                         for (int ks = 0; ks < C::KSTEPS; ++ks) {
                             const uint64_t dw = tc::make_smem_desc(w0 + WS[p] * C::W_TERM + ks * 2 * C::W_LBO, C::W_LBO, 128, 0);
@@ -229,6 +231,7 @@ k_gru_bwd_fused(FArgs a) {
                         for (int t = 0; t < C::NT_T; ++t) {
 #pragma unroll
                             for (int p = 0; p < 3; ++p) {
+                                if (p >= a.nprod) break;
                                 if (p == 1 && (a.two_products || t >= C::NT_W)) continue;
 #pragma unroll
                                 for (int ks = 0; ks < C::KS_B; ++ks) {
@@ -245,6 +248,7 @@ k_gru_bwd_fused(FArgs a) {
                         for (int t = 0; t < C::NT_W; ++t) {
 #pragma unroll
                             for (int p = 0; p < 3; ++p) {
+                                if (p >= a.nprod) break;
                                 if (p == 1 && a.two_products) continue;
 #pragma unroll
                                 for (int ks = 0; ks < C::KS_B; ++ks) {
@@ -260,6 +264,7 @@ k_gru_bwd_fused(FArgs a) {
                         for (int t = 0; t < C::NT_T; ++t) {
 #pragma unroll
                             for (int p = 0; p < 2; ++p) {                  // (x1 + x2) . onehot
+                                if (p >= a.nprod) break;
 #pragma unroll
                                 for (int ks = 0; ks < C::KS_B; ++ks) {
                                     const uint64_t da = tc::make_smem_desc(x0 + p * C::X_TERM + t * 16 * C::X_LBO + ks * 256, 128, C::X_LBO, 0);
@@ -561,7 +566,7 @@ int launch_gru_bwd_enc_fused(cudaStream_t s, const GruSeq* two, const uint8_t* t
     }
     a.tok = tok;
     a.dh_fin = two[0].dh_fin;
-    a.B = B; a.L = L; a.V = V; a.two_products = g_opt_bptt_two_products; a.dbg = g_bptt_dbg; a.tl = g_bptt_tl;
+    a.B = B; a.L = L; a.V = V; a.nprod = g_opt_matmul_terms == 1 ? 1 : 3; a.two_products = g_opt_bptt_two_products; a.dbg = g_bptt_dbg; a.tl = g_bptt_tl;
     const size_t smem = EncF::smem_bytes(L);
     static size_t set_for = 0;
     if (set_smem_f(k_gru_bwd_fused<EncF>, smem, set_for)) return CPG_ECUDA;
@@ -576,7 +581,7 @@ int launch_gru_bwd_dec_fused(cudaStream_t s, const GruSeq& q, const uint8_t* tok
     a.part_w[0] = part_w; a.part_t[0] = part_t;
     a.tok = tok;
     a.h0 = q.h0; a.dh_out = q.dh_out; a.dh0 = q.dh0; a.drow = q.drow;
-    a.B = B; a.L = L; a.V = V; a.two_products = g_opt_bptt_two_products; a.dbg = g_bptt_dbg; a.tl = g_bptt_tl ? g_bptt_tl + 16 : nullptr;
+    a.B = B; a.L = L; a.V = V; a.nprod = g_opt_matmul_terms == 1 ? 1 : 3; a.two_products = g_opt_bptt_two_products; a.dbg = g_bptt_dbg; a.tl = g_bptt_tl ? g_bptt_tl + 16 : nullptr;
     const size_t smem = DecF::smem_bytes(L);
     static size_t set_for = 0;
     if (set_smem_f(k_gru_bwd_fused<DecF>, smem, set_for)) return CPG_ECUDA;

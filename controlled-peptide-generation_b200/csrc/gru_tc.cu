@@ -105,6 +105,7 @@ struct FwdArgs {
     float* gates[2];           // [ceil(B/32)][L][4][32][HP] tiled gate stash (nullable)
     float* hfin;               // encoder: [B][2*HP]
     int B, L, V;
+    int nprod;                 // 3: split-bf16 products x1 w1 + x1 w2 + x2 w1 (fp32-grade); 1: the leading bf16 product only
 };
 
 template <class C>
@@ -240,6 +241,7 @@ k_gru_fwd_tc(FwdArgs a) {
                     uint32_t acc = 0;
 #pragma unroll
                     for (int p = 0; p < 3; ++p) {
+                        if (p >= a.nprod) break;
 #pragma unroll
                         for (int ks = 0; ks < C::KSTEPS; ++ks) {
                             const uint32_t ta = tmem_d + (uint32_t)(C::WCOL0 + (t * 2 + WS[p]) * C::WCOLS + ks * 8);
@@ -765,7 +767,7 @@ int launch_gru_fwd_enc_tc(cudaStream_t s, const GruSeq* two, int B, int L, int V
         a.hs[d] = two[d].hs; a.gates[d] = two[d].gates;
     }
     a.hfin = two[0].hfin;
-    a.B = B; a.L = L; a.V = V;
+    a.B = B; a.L = L; a.V = V; a.nprod = g_opt_matmul_terms == 1 ? 1 : 3;
     const size_t smem = EncFwd::smem_bytes(V, L);
     static size_t set_for = 0;
     if (set_smem(k_gru_fwd_tc<EncFwd>, smem, set_for)) return CPG_ECUDA;
@@ -778,7 +780,7 @@ int launch_gru_fwd_dec_tc(cudaStream_t s, const GruSeq& q, int B, int L, int V) 
     memset(&a, 0, sizeof(a));
     a.tok = q.tok; a.table[0] = q.table; a.whh[0] = q.whh; a.bhn[0] = q.bhn;
     a.rowbias = q.rowbias; a.h0 = q.h0; a.hs[0] = q.hs; a.gates[0] = q.gates;
-    a.B = B; a.L = L; a.V = V;
+    a.B = B; a.L = L; a.V = V; a.nprod = g_opt_matmul_terms == 1 ? 1 : 3;
     const size_t smem = DecFwd::smem_bytes(V, L);
     static size_t set_for = 0;
     if (set_smem(k_gru_fwd_tc<DecFwd>, smem, set_for)) return CPG_ECUDA;

@@ -70,6 +70,10 @@ struct StepDyn {
     uint32_t noise_step;
 };
 extern const StepDyn* g_dyn;
+// 3 (default): every tensor-core contraction of the recurrences / decoder-output layer as the three split-bf16 products
+// (fp32-grade, the parity configuration); 1: the leading bf16 product only ("bf16 matmul tiles" of BASELINE.json configs[2]:
+// a reduced-precision mode, NOT covered by the parity bars)
+extern int g_opt_matmul_terms;
 
 // per-iteration noise (noise.cu); part bit 0 = eps / c / word dropout, bit 1 = z_prior x2 / out-dropout mask
 struct StepNoiseArgs {

@@ -369,6 +369,9 @@ int cpg_logreg_stats_len(void);
  *   "wgrad_dense_tensor_core" 1 (default) head / [z;c]-projection weight gradients as split-bf16 tcgen05 batch contractions on
  *                         the reduction stream (where the tcgen05 latent layers are on), 0 head gradients inside the latent
  *                         backward kernel + dW_ih[:,150:] as an fp32 SIMT product
+ *   "matmul_terms"        3 (default) every tensor-core contraction of the recurrences / decoder-output layer is the sum of the
+ *                         three split-bf16 products (fp32-grade: the configuration all parity bars are stated for); 1 = the
+ *                         leading bf16 product only ("bf16 matmul tiles", BASELINE.json configs[2]) -- a reduced-precision mode
  *   "adam_fused"          1 (default) sum of squares, norm, clip and Adam in ONE launch (grid-wide barrier), 0 two launches
  *   "chain_priority"      1 (default) the dependent chain of the fused step runs on a highest-priority internal stream
  *                         (forked from / joined to the caller's), 0 = on the caller's stream
