@@ -377,14 +377,19 @@ class FusedStepper:
         self.B, self.L, self.p_word, self.p_out = B, L, float(p_word), float(p_out)
         dev = state.device
         self.noise = alloc_noise(B, L, dev, rf_dim=rf_dim, seed=seed)
-        self.scalars = torch.zeros(SC_COUNT, device=dev)
+        # two scalar blocks used in turn (each has its captured graph): a reader may still be copying step k's block to the
+        # host on another stream while step k + 1 composes its own
+        self._scal = [torch.zeros(SC_COUNT, device=dev), torch.zeros(SC_COUNT, device=dev)]
+        self._flip = 0
+        self.scalars = self._scal[0]
         self.ctx, self.lib = context(dev), lib()
         self.nz = _loss_noise(self.noise)
         self._nb = None
         n = self.noise
         self._noise_args = (ptr(n['eps']), ptr(n['c']), ptr(n['word_drop']), ptr(n['out_keep']),
                             ptr(n.get('z_prior_full')), ptr(n['z_prior_rf']))
-        self._bufs = (ptr(state.params), ptr(state.grads), ptr(state.adam_m), ptr(state.adam_v), ptr(self.scalars))
+        self._bufs = (ptr(state.params), ptr(state.grads), ptr(state.adam_m), ptr(state.adam_v))
+        self._scal_ptrs = [ptr(t) for t in self._scal]
         self._null = c_void_p(None)
 
     def step(self, tokens, it, beta):
@@ -400,7 +405,9 @@ class FusedStepper:
         st.step += 1
         hp.adam_step = st.step
         hp.beta = float(beta)
-        p, g, m, v, sc = self._bufs
+        p, g, m, v = self._bufs
+        self.scalars, sc = self._scal[self._flip], self._scal_ptrs[self._flip]
+        self._flip ^= 1
         check(self.lib.cpg_wae_train_step_philox(self.ctx, stream_ptr(), p, g, m, v, st.n_vocab, self.B, self.L,
                                                  ptr(tokens, torch.int64, allow_none=False), byref(self._nb), byref(hp), self.seed,
                                                  int(it), self.p_word, self.p_out, sc), 'cpg_wae_train_step_philox')

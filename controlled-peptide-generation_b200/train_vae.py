@@ -79,6 +79,7 @@ def _train_fused(cfgv, model, dataset):
     # Host batches go to the device one iteration ahead, on a copy stream, into one of two buffers: the H2D copy of
     # batch i+1 runs under the kernels of iteration i (same number of next_batch calls as the reference loop).
     copy_stream = torch.cuda.Stream(device=dev)
+    read_stream = torch.cuda.Stream(device=dev)     # device -> host reads of the scalar block, off the compute stream
     bufs, used_ev = [None, None], [None, None]       # device token buffers / "last reader has been enqueued" events
     staged = None                                     # (host tokens, slot or None, copy event or None) of the next iteration
     pinned_scal, pending_read = None, None
@@ -151,8 +152,17 @@ def _train_fused(cfgv, model, dataset):
         elif sync_every > 0 and it % sync_every == 0:
             if pinned_scal is None:
                 pinned_scal = torch.empty(scal.shape, dtype=scal.dtype, pin_memory=True)
-            pinned_scal.copy_(scal, non_blocking=True)
-            pending_read = (pinned_scal, torch.cuda.current_stream(dev).record_event())
+            # on its own stream, behind this iteration: the next iteration's launch does not queue behind the copy (the fused
+            # stepper alternates between two scalar blocks, so the block being read is not rewritten for a whole iteration)
+            # (the data-parallel graph owns ONE scalar block: there the copy stays on the compute stream)
+            if distributed:
+                pinned_scal.copy_(scal, non_blocking=True)
+                pending_read = (pinned_scal, torch.cuda.current_stream(dev).record_event())
+            else:
+                read_stream.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(read_stream):
+                    pinned_scal.copy_(scal, non_blocking=True)
+                    pending_read = (pinned_scal, read_stream.record_event())
         if log_it:
             for name, slot in _SCALAR_LOG:
                 log_value('train_' + name, float(vals[engine.SC[slot]]), it)
