@@ -758,7 +758,9 @@ int cpg_fill_step_noise_overlapped(cpg_ctx* ctx, cpg_stream stream, uint64_t see
     // eps, c, z_prior x2, out-dropout mask: lane s, under the token preparation / encoder recurrence (first reader: the
     // latent layers, which join it)
     launch_step_noise(ln.s, a, NOISE_LATENT | NOISE_LATE);
+#ifndef CPG_EMU
     cudaEventRecord((cudaEvent_t)ctx->ev_noise, ln.s);
+#endif
     ctx->noise_pending = true;
     launch_step_noise(s, a, NOISE_WORD);            // word dropout: needed by the token preparation right away
     return check_launch("cpg_fill_step_noise_overlapped");
