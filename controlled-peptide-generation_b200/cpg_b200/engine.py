@@ -324,8 +324,9 @@ def mmd_rf(z, z_prior, rf_w, rf_b, sigma, want_grad=False):
 # ------------------------------------------------------------------ perf-mode noise + trainer
 def fill_step_noise(noise, seed, step, p_word=0.3, p_out=0.3, overlap=False):
     """Regenerate the per-iteration noise tensors in place (Philox; pure function of seed/step).
-    overlap=True: the late-use tensors (z_prior x2, out-dropout mask) are generated on the library's side stream
-    and joined inside the train-step entry points -- only when the next reader IS a train step."""
+    overlap=True: the request is only RECORDED; the train-step / forward entry point that reads these buffers next draws the
+    word-dropout mask inside its token preparation and the rest on the library's side stream -- only when the next reader IS
+    such an entry point (do not read the tensors from Python in between: use overlap=False for that)."""
     B, L = noise['word_drop'].shape
     dev = noise['eps'].device
     fn = lib().cpg_fill_step_noise_overlapped if overlap else lib().cpg_fill_step_noise

@@ -268,6 +268,13 @@ static void order(cpg_ctx*, const Lanes&, cudaStream_t, cudaStream_t) {}
 static void noise_join(cpg_ctx*, cudaStream_t) {}
 #endif
 
+// a noise request recorded by cpg_fill_step_noise_overlapped that no forward consumed: draw everything now, on `s`
+static void flush_deferred_noise(cpg_ctx* ctx, cudaStream_t s) {
+    if (!ctx->gen_deferred) return;
+    ctx->gen_deferred = false;
+    launch_step_noise(s, ctx->gen_args, NOISE_ALL);
+}
+
 // ------------------------------------------------------------------------------------ forward
 // Tensor-core recurrences pay off once a 128-row tile per CTA fills a good part of the chip;
 // tiny batches stay on the 32-row fp32 SIMT kernels.  g_opt_gru_tc: 0 = never, 1 = auto, 2 = always.
@@ -287,6 +294,18 @@ static Mark forward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, con
                          const StepNoiseArgs* gen = nullptr, float* ntok_out = nullptr) {
     Workspace& w = ctx->ws;
     cudaStream_t s = ln.m;
+    StepNoiseArgs deferred;
+    if (ctx->gen_deferred) {
+        // the request of cpg_fill_step_noise_overlapped is for this forward when it names the buffers this forward reads
+        if (gen == nullptr && !encoder_only && ctx->gen_args.B == B && ctx->gen_args.L == L && ctx->gen_args.word_drop != nullptr &&
+            ctx->gen_args.word_drop == in->word_drop) {
+            deferred = ctx->gen_args;
+            gen = &deferred;
+            ctx->gen_deferred = false;
+        } else {
+            flush_deferred_noise(ctx, s);
+        }
+    }
     // the derived weight forms only depend on the parameters: their lane runs beside the token preparation
     order(ctx, ln, s, ln.t);
     Mark weights_ready = nullptr, rest_ready = nullptr;
@@ -722,6 +741,7 @@ int cpg_wae_backward(cpg_ctx* ctx, cpg_stream stream, const float* params, int V
         return CPG_EINVAL;
     }
     cudaStream_t s = (cudaStream_t)stream;
+    flush_deferred_noise(ctx, s);
     noise_join(ctx, s);
     const Lanes ln = lanes(ctx, s);
     ParamLayout lay = make_layout(V);
@@ -753,16 +773,14 @@ int cpg_fill_step_noise_overlapped(cpg_ctx* ctx, cpg_stream stream, uint64_t see
         launch_step_noise(s, a, NOISE_ALL);
         return check_launch("cpg_fill_step_noise_overlapped");
     }
+    // Recorded, not launched: the forward that reads these buffers next (cpg_wae_step_phase1, cpg_wae_train_step,
+    // cpg_wae_forward) draws the word-dropout mask inside its token preparation and the rest on the loss lane once that
+    // preparation is through -- drawn right here, the big kernel would slow the preparation kernels the encoder waits for.
+    // Any other entry point that may read them draws everything first (flush_deferred_noise).
     noise_join(ctx, s);                             // a previous batch of noise nobody consumed yet
-    order(ctx, ln, s, ln.s);                        // earlier readers of these buffers (previous iteration) are on `s`
-    // eps, c, z_prior x2, out-dropout mask: lane s, under the token preparation / encoder recurrence (first reader: the
-    // latent layers, which join it)
-    launch_step_noise(ln.s, a, NOISE_LATENT | NOISE_LATE);
-#ifndef CPG_EMU
-    cudaEventRecord((cudaEvent_t)ctx->ev_noise, ln.s);
-#endif
-    ctx->noise_pending = true;
-    launch_step_noise(s, a, NOISE_WORD);            // word dropout: needed by the token preparation right away
+    flush_deferred_noise(ctx, s);
+    ctx->gen_args = a;
+    ctx->gen_deferred = true;
     return check_launch("cpg_fill_step_noise_overlapped");
 }
 
@@ -863,6 +881,7 @@ static int phase2_impl(cpg_ctx* ctx, cpg_stream stream, const float* params, flo
     const int Bg = hp->global_batch > 0 ? hp->global_batch : B;
     ParamLayout lay = make_layout(V);
     const Lanes ln = lanes(ctx, s);
+    flush_deferred_noise(ctx, s);
     dev_memset(grads, 0, (size_t)lay.total * 4, s);
     // RF-MMD from the global feature sums, then the full-kernel MMD: lane s; the caller's lane waits for the RF gradient
     // right before the latent backward that consumes it, for the (logged) full-kernel MMD only at the end of the step
@@ -1142,6 +1161,8 @@ int cpg_wae_decode_teacher(cpg_ctx* ctx, cpg_stream stream, const float* params,
     cudaStream_t s = (cudaStream_t)stream;
     if ((rc = ensure_workspace(ctx, B, L, V, ctx->ws.R > 0 ? ctx->ws.R : 500, s))) return rc;
     Workspace& w = ctx->ws;
+    flush_deferred_noise(ctx, s);
+    noise_join(ctx, s);
     launch_prep_tokens(s, in->tokens, in->word_drop, B, L, V, w.tok, w.tokd, w.tgt, ctx->ints, ctx->ints + 1);
     launch_prep_weights(s, params, make_layout(V), V, w.d);
     launch_make_zc(s, z, in->c, B, w.zc);

@@ -56,6 +56,10 @@ struct cpg_ctx {
     int ev_next = 0;
     void* ev_noise = nullptr;      // noise generated on the side stream by cpg_fill_step_noise_overlapped, not yet joined
     bool noise_pending = false;
+    // cpg_fill_step_noise_overlapped only RECORDS its request; the next forward draws the word-dropout mask inside its token
+    // preparation and the rest on the loss lane once the preparation is through (api_wae.cu: forward_impl)
+    bool gen_deferred = false;
+    cpg::StepNoiseArgs gen_args;
 };
 
 namespace cpg {

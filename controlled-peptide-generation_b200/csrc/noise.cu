@@ -100,6 +100,10 @@ int cpg_fill_step_noise(cpg_ctx* ctx, cpg_stream stream, uint64_t seed, uint32_t
     StepNoiseArgs a;
     a.seed = seed; a.step = step; a.B = B; a.L = L; a.p_word = p_word; a.p_out = p_out;
     a.eps = eps; a.c = c; a.word_drop = word_drop; a.out_keep = out_keep; a.zp_full = z_prior_full; a.zp_rf = z_prior_rf;
+    if (ctx->gen_deferred) {                       // an unconsumed request of cpg_fill_step_noise_overlapped comes first
+        ctx->gen_deferred = false;
+        launch_step_noise((cudaStream_t)stream, ctx->gen_args, NOISE_ALL);
+    }
     launch_step_noise((cudaStream_t)stream, a, NOISE_ALL);
     return check_launch("cpg_fill_step_noise");
 }

@@ -228,10 +228,13 @@ int cpg_mmd_rf(cpg_ctx* ctx, cpg_stream stream, const float* z, const float* z_p
 int cpg_fill_step_noise(cpg_ctx* ctx, cpg_stream stream, uint64_t seed, uint32_t step, int B, int L, float p_word,
                         float p_out, float* eps, float* c, uint8_t* word_drop, uint8_t* out_keep,
                         float* z_prior_full, float* z_prior_rf);
-/* Same tensors, same values; the parts the step only needs late (z_prior x2, out-dropout mask) are generated on the
- * context's side stream and joined inside the cpg_wae_* entry points that consume them.  ONLY for callers whose
- * next use of these buffers is cpg_wae_step_phase1/2, cpg_wae_train_step, cpg_wae_forward or cpg_wae_backward on
- * the same context and stream (anything else must use cpg_fill_step_noise). */
+/* Same tensors, same values, drawn LATER: the call only records the request.  The entry point that reads the buffers next
+ * draws the word-dropout mask inside its token preparation and everything else on the context's side stream once that
+ * preparation is through (joined where it is consumed) -- drawn at call time, the large noise kernel would slow the
+ * preparation kernels the encoder recurrence waits for.  ONLY for callers whose next use of these buffers is
+ * cpg_wae_step_phase1/2, cpg_wae_train_step, cpg_wae_forward or cpg_wae_backward on the same context and stream with
+ * these very buffers as inputs (in any other case the library draws everything immediately at that later call; a caller
+ * that wants to READ the tensors itself must use cpg_fill_step_noise). */
 int cpg_fill_step_noise_overlapped(cpg_ctx* ctx, cpg_stream stream, uint64_t seed, uint32_t step, int B, int L,
                                    float p_word, float p_out, float* eps, float* c, uint8_t* word_drop,
                                    uint8_t* out_keep, float* z_prior_full, float* z_prior_rf);
