@@ -551,3 +551,30 @@ def test_single_product_bf16_mode_stays_close_to_the_parity_configuration(eng):
     for k in ow.UNIQUE_VAE_PARAMS:
         assert float((g1[k] - g3[k]).abs().max()) <= 3e-2 * float(g3[k].abs().max()) + 1e-12, k
     assert any(float((g1[k] - g3[k]).abs().max()) > 0 for k in ow.UNIQUE_VAE_PARAMS)      # the mode really is a different arithmetic
+
+
+@pytest.mark.parametrize('z_regu,full', [('mmdrf', 0), ('kl', 1), ('kl', 0), ('mmd', 1)])
+def test_captured_graph_equals_eager_for_every_regulariser(eng, z_regu, full):
+    """The captured three-lane iteration replays exactly what eager launches compute, whatever the latent regulariser and
+    with the logged full-kernel MMD on or off (the lanes carry different work in each case)."""
+    from cpg_b200 import _lib, synth
+    dev = torch.device('cuda')
+    B = 1536
+    tokens = synth.synthetic_tokens(B, V, seed=2).to(dev)
+    p = ow.random_params(V, seed=3)
+    res = []
+    try:
+        for graph in (1, 0):
+            _lib.set_option('cuda_graph', graph)
+            st = eng.FlatState(V, dev)
+            st.load(p)
+            hp = eng.make_hparams(z_regu=z_regu, lambda_logvar_l1=0.01)
+            hp.compute_full_mmd = full
+            fs = eng.FusedStepper(st, B, 25, hp, seed=11)
+            sc = [fs.step(tokens, it, 0.3 + 0.1 * it).clone() for it in range(5)]
+            torch.cuda.synchronize()
+            res.append((torch.stack(sc).cpu(), st.params.clone().cpu()))
+    finally:
+        _lib.set_option('cuda_graph', 1)
+    assert torch.isfinite(res[0][0]).all()
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
