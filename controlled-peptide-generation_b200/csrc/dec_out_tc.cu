@@ -24,10 +24,15 @@
 #ifdef CPG_GRU_TIMELINE
 // developer-only probe: cycles thread 0 of CTA 0 spends in each phase (includes the waits at the phase's barrier)
 __device__ long long g_do_tl[16];
+__device__ unsigned long long g_do_cta[3 * 160];               // per CTA: globaltimer at start, after set-up, at exit (ns)
 extern "C" int cpg_debug_dec_out_timeline(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_do_tl, sizeof(g_do_tl)); }
+extern "C" int cpg_debug_dec_out_ctas(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_do_cta, sizeof(g_do_cta)); }
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define DO_CTA(slot) do { if (threadIdx.x == 0 && blockIdx.x < 160) g_do_cta[blockIdx.x * 3 + (slot)] = gtime(); } while (0)
 #define DO_MARK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long _n = clock64(); g_do_acc[slot] += _n - g_do_last; g_do_last = _n; } } while (0)
 #else
 #define DO_MARK(slot) do { } while (0)
+#define DO_CTA(slot) do { } while (0)
 #endif
 
 namespace cpg {
@@ -170,6 +175,7 @@ k_dec_out_tc(DecOutArgs a) {
     __shared__ float ex_s[3][2][TR];                           // row max / sum / target logit of each class half
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    DO_CTA(0);
     const int V = a.V;
     const int nrows = a.B * a.L;
     const bool want_grad = a.dh_out != nullptr;
@@ -178,12 +184,28 @@ k_dec_out_tc(DecOutArgs a) {
     const float ntok_v = a.ntok_i != nullptr ? (float)*a.ntok_i : (a.ntok != nullptr ? *a.ntok : 0.f);
     const float inv_ntok = ntok_v > 0.f ? 1.0f / ntok_v : 0.f;
 
-    // ---- one-time setup: zero every operand tile (K / M padding stays zero), then the two weight tiles
-    for (int i = tid; i < OFF_KEEP / 16; i += NTH) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    // ---- one-time setup: zero what no tile ever rewrites but an MMA reads -- the K padding of hd (hidden 104..111, the last
+    // chunk of each term) and the two weight tiles (their padding rows / columns) -- then stage the weight tiles.  (Every
+    // other byte of hd / dl / the read-out tile is written by each tile before it is read; measured: set-up 6.6 us per CTA
+    // with all 198 KB zeroed and the 13 weight loads of a thread issued one by one.)
+    static_assert(DEC_HP == 104 && KH == 112, "K padding of hd = its last 8-column chunk");
+    for (int i = tid; i < 3 * (LBO_R / 16); i += NTH) {
+        const int term = i / (LBO_R / 16), q16 = i % (LBO_R / 16);
+        reinterpret_cast<uint4*>(HD + term * HD_SPLIT + (KH / 8 - 1) * LBO_R)[q16] = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = tid; i < (OFF_STAGE - OFF_WK) / 16; i += NTH) {
+        if (i < 3 * WK_SPLIT / 16 || i >= (OFF_WT - OFF_WK) / 16) reinterpret_cast<uint4*>(WK)[i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
-    for (int idx = tid; idx < VMAX * DEC_HP; idx += NTH) {
+    static_assert(VMAX * DEC_HP % NTH == 0, "weight staging items");
+    float wreg[VMAX * DEC_HP / NTH];
+#pragma unroll
+    for (int it = 0; it < VMAX * DEC_HP / NTH; ++it) wreg[it] = __ldg(a.fc_w + tid + it * NTH);
+#pragma unroll
+    for (int it = 0; it < VMAX * DEC_HP / NTH; ++it) {
+        const int idx = tid + it * NTH;
         const int v = idx / DEC_HP, j = idx % DEC_HP;
-        const float w = a.fc_w[idx];
+        const float w = wreg[it];
         const __nv_bfloat16 h = __float2bfloat16_rn(w);
         const float wr = w - __bfloat162float(h);
         const __nv_bfloat16 l = __float2bfloat16_rn(wr);
@@ -227,6 +249,7 @@ k_dec_out_tc(DecOutArgs a) {
     long long g_do_last = clock64();
 #endif
     const int ntiles = ceil_div(nrows, TR);
+    DO_CTA(1);
     // Raw inputs of a tile ((row, quad) items: 13 per thread): fetched one tile ahead -- the loads of tile t+1 are issued
     // right after the second MMA batch of tile t and land under its dh epilogue.  Unconditional (clamped) addresses
     // and no use of the loaded values at the issue point, so that the 39 loads of a thread are in flight together.
@@ -463,6 +486,7 @@ k_dec_out_tc(DecOutArgs a) {
     }
     tc::tc_fence_before();
     __syncthreads();
+    DO_CTA(2);
     if (warp == 4) tc::tmem_dealloc<TMEM_COLS>(tmem);
 }
 

@@ -21,3 +21,14 @@ t = list(buf)
 print('k_dec_out_tc CTA 0, cycles summed over its tiles:')
 for name, i in (('tile start (prev tile tail)', 7), ('S1 stage hd', 0), ('S2 transpose', 1), ('M1 + E1 softmax', 2), ('M2 + E2 dh', 3)):
     print('  %-28s %8d' % (name, t[i]))
+
+import numpy as np
+cb = (ctypes.c_ulonglong * (3 * 160))()
+if hasattr(_lib.lib(), 'cpg_debug_dec_out_ctas'):
+    _lib.lib().cpg_debug_dec_out_ctas(cb)
+    t = np.array(list(cb), dtype=np.float64).reshape(160, 3)
+    t = t[t[:, 0] > 0]
+    t0 = t[:, 0].min()
+    print('CTAs %d: start spread %.1f us; set-up mean %.1f us; run (start -> exit) mean %.1f us max %.1f us; last exit at %.1f us after the first start'
+          % (len(t), (t[:, 0].max() - t0) / 1e3, (t[:, 1] - t[:, 0]).mean() / 1e3, (t[:, 2] - t[:, 0]).mean() / 1e3,
+             (t[:, 2] - t[:, 0]).max() / 1e3, (t[:, 2].max() - t0) / 1e3))
