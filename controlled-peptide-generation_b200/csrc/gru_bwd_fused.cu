@@ -153,6 +153,7 @@ k_gru_bwd_fused(FArgs a) {
     // W_hh^T, K-major (rows j, K = gate index): element [j][k] = W_hh[k][j], 16 bytes = 8 consecutive k of one j
     {
         const float* whh = dir ? a.whh[1] : a.whh[0];
+#pragma unroll 2
         for (int idx = tid; idx < (KPAD / 8) * C::W_ROWS; idx += C::NTHREADS) {
             const int kc = idx / C::W_ROWS, j = idx % C::W_ROWS;
             float x[8];
