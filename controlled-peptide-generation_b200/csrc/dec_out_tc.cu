@@ -15,7 +15,7 @@
 // Softmax / CE run with thread = row straight out of TMEM
 // (all 32 class logits of a row in one thread's registers: no shuffles).
 // One persistent CTA per SM, 256 threads: all 8 warps stage, warps 0-3 own the TMEM epilogues, an
-// elected lane of warp 4 issues the MMAs.  Per-CTA partials (dW, db, nll) feed the ordered reduction of dec_out.cu.
+// elected lane of warp 4 issues the MMAs; dh and dW complete on separate mbarriers (the dh read-out runs under the dW contraction).  Per-CTA partials (dW, db, nll) feed the ordered reduction of dec_out.cu.
 #include "ctx.h"
 #ifndef CPG_EMU
 #include <cuda_bf16.h>
@@ -168,7 +168,7 @@ k_dec_out_tc(DecOutArgs a) {
     unsigned char* WT = smem + OFF_WT;
     unsigned char* STG = smem + OFF_STAGE;
     unsigned char* keep_s = smem + OFF_KEEP;
-    __shared__ __align__(8) uint64_t bar_m;
+    __shared__ __align__(8) uint64_t bar_m, bar_w;
     __shared__ uint32_t tmem_slot;
     __shared__ float red_b[8][VMAX / 2];
     __shared__ float red_n[4];
@@ -222,6 +222,7 @@ k_dec_out_tc(DecOutArgs a) {
     if (warp == 4) {
         if (lane == 0) {
             tc::mbar_init(&bar_m, 1);
+            tc::mbar_init(&bar_w, 1);
             tc::fence_barrier_init();
         }
         __syncwarp();
@@ -241,7 +242,7 @@ k_dec_out_tc(DecOutArgs a) {
 #pragma unroll
     for (int v = 0; v < VMAX / 2; ++v) accb[v] = 0.f;
     float accn = 0.f;
-    uint32_t mphase = 0;
+    uint32_t mphase = 0, wphase = 0;
     bool dw_started = false;
 
 #ifdef CPG_GRU_TIMELINE
@@ -329,6 +330,11 @@ k_dec_out_tc(DecOutArgs a) {
             const int half = warp >> 2, v0 = half * HV;
             const int r2 = (warp & 3) * 32 + lane;
             const int row = row0 + r2;
+            // the row's target and the bias do not depend on the MMAs: their (global) loads run under them
+            const int tg = (a.fused_ce && row < nrows) ? a.tgt[row] : PAD;
+            float fb[HV];
+#pragma unroll
+            for (int i = 0; i < HV; ++i) fb[i] = v0 + i < V ? __ldg(a.fc_b + v0 + i) : 0.f;
             tc::mbar_wait(&bar_m, mphase & 1);
             tc::tc_fence_after();
             float lg[HV];
@@ -336,7 +342,7 @@ k_dec_out_tc(DecOutArgs a) {
             float mx = -INFINITY;
 #pragma unroll
             for (int i = 0; i < HV; ++i) {
-                lg[i] = v0 + i < V ? lg[i] + a.fc_b[v0 + i] : -INFINITY;
+                lg[i] = v0 + i < V ? lg[i] + fb[i] : -INFINITY;
                 mx = fmaxf(mx, lg[i]);
             }
             if (row < nrows && a.logits_out != nullptr) {
@@ -348,7 +354,6 @@ k_dec_out_tc(DecOutArgs a) {
 #pragma unroll
             for (int i = 0; i < HV; ++i) dl[i] = 0.f;
             if (a.fused_ce) {
-                const int tg = row < nrows ? a.tgt[row] : PAD;
                 ex_s[0][half][r2] = mx;
                 __syncthreads();
                 mx = fmaxf(ex_s[0][0][r2], ex_s[0][1][r2]);
@@ -404,9 +409,10 @@ k_dec_out_tc(DecOutArgs a) {
             tc::tc_fence_after();
             if (elect_one()) {
                 mma_split3(tmem + TC_DH, s_dl, DL_SPLIT, LBO_R, s_wt, WT_SPLIT, LBO_H, VMAX / 16, idesc_bf16(128, KH), 0, a.nprod == 1 ? 1 : 3);
+                tc::umma_commit(&bar_m);                       // dh is complete: its read-out starts under the dW contraction
                 mma_split3_mn(tmem + TC_DW, s_hd, HD_SPLIT, LBO_R, s_dl, DL_SPLIT, LBO_R, TR / 16, idesc_bf16(128, VMAX, 1, 1),
                               dw_started ? 1u : 0u, a.nprod == 1 ? 1 : 3);
-                tc::umma_commit(&bar_m);
+                tc::umma_commit(&bar_w);
             }
             __syncwarp();
         }
@@ -444,7 +450,9 @@ k_dec_out_tc(DecOutArgs a) {
             }
         }
         ++mphase;
-        __syncthreads();                                       // both MMAs are done with HD / DL, the stage tile is read out
+        tc::mbar_wait(&bar_w, wphase & 1);                     // the dW contraction is done with HD / DL
+        ++wphase;
+        __syncthreads();                                       // ... and the stage tile is read out
         DO_MARK(3);
     }
 

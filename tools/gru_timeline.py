@@ -5,6 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'controlled-peptide-generation_b200'))
 import torch
 from cpg_b200 import engine, _lib
+if os.environ.get('CPG_TL_LIB'): _lib._LIB_PATH = os.environ['CPG_TL_LIB']   # side build with -DCPG_GRU_TIMELINE
 from oracle import wae as ow
 
 dev = torch.device('cuda'); V, L, B = 24, 25, 4096

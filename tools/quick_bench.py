@@ -7,6 +7,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'controlled-pept
 import torch
 import bench
 from cpg_b200 import engine, _lib, synth
+if os.environ.get('CPG_TL_LIB'): _lib._LIB_PATH = os.environ['CPG_TL_LIB']   # side build (A/B runs)
 
 dev = torch.device("cuda"); B = 4096
 cfg, model = bench.setup_model(dev)
