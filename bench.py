@@ -523,8 +523,8 @@ def run_ours(args):
                               % dp_graph_state),
                    'arithmetic': 'fp32 storage and accumulation; recurrence / decoder-output contractions as split-bf16 '
                                  '(x1+x2, 3 products; logits 3 terms) tcgen05 MMAs; heads / [z;c] projection / RF map as split-fp16, their '
-                                 'backward as split-bf16 tcgen05 MMAs (3 products); MMD Gram tf32; one remaining fp32 SIMT product '
-                                 '(dW_ih[:,150:], K = batch)'},
+                                 'backward and the dense weight gradients (dW_ih[:,150:], heads) as split-bf16 tcgen05 MMAs (3 products); '
+                                 'MMD Gram tf32'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * L * 8, 'd2h_bytes_per_step': 16 * 4 + 8,
                 'api': 'train_vae.train_vae(cfgv, model, dataset): pinned host tokens copied H2D every step (one step ahead, copy stream), '
                   'scalar block copied D2H every step (collected after the next step is enqueued)'},

@@ -60,6 +60,54 @@ def token_to_residue(idx2word, n_tokens):
     return out
 
 
+def vocabulary_words(dataset, n_tokens):
+    """The word of every token id, asked of the dataset itself one token at a time (works with the reference's dataset
+    class and with any shim that offers idx2sentences)."""
+    return [str(dataset.idx2sentences([[t]], print_special_tokens=True)[0]) for t in range(n_tokens)]
+
+
+def rows_to_sentences(tokens, lens, words, n_special=4, fallback=None):
+    """dataset.idx2sentences([row[:n] for row, n in zip(tokens, lens)], print_special_tokens=False) for a host matrix of
+    decoded rows (data_processing/dataset.py:288-300 of the reference: special ids dropped, words joined by one space)
+    without a Python loop over tokens: byte matrix [n, 2 W] with the kept characters compacted to the even positions,
+    viewed as fixed-width strings.  Needs every non-special word to be one ASCII character (amino-acid vocabularies);
+    otherwise `fallback(rows)` is called with the list-of-lists form."""
+    tok = np.asarray(tokens)
+    ln = np.asarray(lens).astype(np.int64)
+    n, W = tok.shape
+    single = all(len(w) == 1 and ord(w) < 128 for w in words[n_special:])
+    if not single or n == 0:
+        rows = [r[:k] for r, k in zip(tok.tolist(), ln.tolist())]
+        if fallback is None:
+            return [' '.join(words[i] for i in r if i >= n_special) for r in rows]
+        return fallback(rows)
+    assert len(words) <= 256 and W < 128
+    lut = np.zeros(256, dtype=np.uint8)
+    for i, w in enumerate(words):
+        lut[i] = ord(w) if i >= n_special else 0
+    t = np.clip(tok, 0, 255).astype(np.uint8)
+    ar = np.arange(W, dtype=np.uint8)[None, :]
+    keep = (t >= n_special) & (t < len(words)) & (ar < np.clip(ln, 0, W).astype(np.uint8)[:, None])
+    cnt = keep.sum(axis=1, dtype=np.uint8)[:, None]
+    out = np.empty((n, 2 * W), dtype=np.uint8)
+    if bool((keep == (ar < cnt)).all()):
+        # no special id inside the kept part of any row (what a decoder emits): positions stay where they are
+        ch = lut[t]
+        ch *= keep
+        out[:, 0::2] = ch
+        out[:, 1::2] = (ar + 1 < cnt).view(np.uint8) << 5          # ' ' after every kept token but the last
+    else:
+        out[:] = 0
+        pos = np.cumsum(keep, axis=1, dtype=np.int64) - 1          # output slot of every kept token
+        r, c = np.nonzero(keep)
+        p = pos[r, c]
+        out[r, 2 * p] = lut[t[r, c]]
+        out[r, 2 * p + 1] = 32
+        has = cnt[:, 0] > 0
+        out[np.nonzero(has)[0], 2 * cnt[has, 0].astype(np.int64) - 1] = 0
+    return [b.decode('ascii') for b in out.view('S%d' % (2 * W)).ravel().tolist()]
+
+
 def descriptors_from_tokens(tokens, aa_of_token, scale='eisenberg', ph=7.0, amide=True, angle=100.0):
     """tokens: int32 [n, W] on the device (decoded rows, -1 padded).  -> (H, uH, charge, length) device tensors."""
     n, W = tokens.shape

@@ -148,15 +148,17 @@ class RejSampleBase:
         hyp0 = toks[:, 0, :].contiguous()
         _, is_first = peptides.dedup_rows(hyp0)
         keep = torch.nonzero(is_first, as_tuple=False).squeeze(1)
-        a2t = peptides.token_to_residue(lambda t: dataset.idx2sentences([[t]], print_special_tokens=True)[0], model.n_vocab)
+        words = peptides.vocabulary_words(dataset, model.n_vocab)
+        a2t = peptides.token_to_residue(lambda t: words[t], model.n_vocab)
         H, uH, ch, _ = peptides.descriptors_from_tokens(hyp0, a2t)
         stats['n_unique'] = int(keep.numel())
         self.last_round_stats = stats
         if return_device:
             return {'tokens': hyp0, 'keep': keep, 'z': z, 'idx': idx, 'H': H, 'uH': uH, 'charge': ch, 'accum': accum}
         # device -> host: the unique accepted rows only
-        kt, kl = hyp0[keep].cpu().tolist(), lens[keep, 0].cpu().tolist()
-        seqs = dataset.idx2sentences([row[:n] for row, n in zip(kt, kl)], print_special_tokens=False)
+        # (the table of peptide strings is built without a Python loop over tokens: a round holds ~10^5..10^6 rows)
+        seqs = peptides.rows_to_sentences(hyp0[keep].cpu().numpy(), lens[keep, 0].cpu().numpy(), words,
+                                          fallback=lambda rows: dataset.idx2sentences(rows, print_special_tokens=False))
         cast = (lambda a: a.astype(np.float32)) if spec.all_f32 else (lambda a: a)
         df = {'peptide': seqs, 'z': list(z[keep].cpu().numpy()), 'accept_z': np.ones(len(seqs), dtype=bool),
               'draw_index': idx[keep].cpu().numpy()}

@@ -293,3 +293,27 @@ def test_rejection_sample_host_copy_ring_logic(monkeypatch):
     for a, b in zip(ts, outs):
         assert a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b)
         assert b.data_ptr() != a.data_ptr() or a.numel() == 0
+
+
+def test_rows_to_sentences_equals_the_dataset_loop():
+    """peptides.rows_to_sentences (the round table's peptide strings without a Python loop over tokens) against the
+    reference's idx2sentences semantics (data_processing/dataset.py:288-300: special ids dropped, words joined by ' ')."""
+    sys.path.insert(0, PKG)
+    from cpg_b200 import peptides
+    words = ['<unk>', '<pad>', '<start>', '<eos>'] + list('ACDEFGHIKLMNPQRSTVWY')
+    ds = type('D', (), {'idx2sentences': staticmethod(
+        lambda seqs, print_special_tokens=True: [' '.join(words[int(i)] for i in s if print_special_tokens or int(i) > 3) for s in seqs])})
+    assert peptides.vocabulary_words(ds, 24) == words
+    rng = np.random.default_rng(5)
+    for lo in (0, 4):                                   # with / without special ids inside the kept part of a row
+        tok = rng.integers(lo, 24, size=(5000, 25)).astype(np.int32)
+        ln = rng.integers(0, 26, size=5000)
+        tok[3] = 1
+        ln[4] = 0
+        want = ds.idx2sentences([r[:k] for r, k in zip(tok.tolist(), ln.tolist())], print_special_tokens=False)
+        assert peptides.rows_to_sentences(tok, ln, words) == want
+    # vocabularies with longer words take the caller's fallback (or the plain loop)
+    w2 = words[:4] + ['Ala', 'Gly']
+    assert peptides.rows_to_sentences(np.array([[4, 5, 3, 5]]), [4], w2) == ['Ala Gly Gly']
+    assert peptides.rows_to_sentences(np.array([[4, 5, 3, 5]]), [3], w2, fallback=lambda rows: ['x%d' % len(r) for r in rows]) == ['x3']
+    assert peptides.rows_to_sentences(np.zeros((0, 25), np.int32), [], words) == []
