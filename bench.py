@@ -338,6 +338,37 @@ def run_class(args, st, dev, world, rank, barrier, model):
     bms = reduce_max(e0.elapsed_time(e1))
     tot = n * world
     gbs_rank = 425 * n / (ms_local / 1e3) / 1e9
+    # beam decode against the fp32 FMA peak: per beam and step the recurrent gates (3*102 x 102), the output layer (V x 102)
+    # and the gate math; 5 beams x 25 steps per decoded z (upper bound: finished samples stop early)
+    beam_flops = 2.0 * (3 * 102 * 102 + N_VOCAB * 102) * 5 * 25
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    beam_tf = beam_flops * 8192 / (bms / 1e3) / 1e12
+    beam_roof = {'kernel': 'k_decode<beam>', 'bound': 'fp32 FMA (SIMT: 25 dependent steps of 30-row matrix-vector products per '
+                 'CTA, no tensor-core shape)', 'achieved': round(beam_tf, 2), 'peak': round(fp32_peak, 1), 'unit': 'TFLOP/s',
+                 'frac': round(beam_tf / fp32_peak, 4), 'flops_per_seq': beam_flops,
+                 'peak_source': 'nominal: 148 SMs x 128 FMA lanes x 2 x 1.965 GHz (not in MEASURED_PEAKS.json)'}
+    # mogQ.logpdf / evaluate_nll (density_modeling.py:64-73,100-106): diag-GMM log-density in fp64, one pass over the points
+    logpdf = None
+    try:
+        npts = 4_000_000
+        xp = torch.randn(npts, 100, device=dev)
+        sampling.gmm_logpdf(gmm, xp)
+        barrier()
+        e0.record()
+        lp = sampling.gmm_logpdf(gmm, xp)
+        e1.record()
+        torch.cuda.synchronize()
+        lms = reduce_max(e0.elapsed_time(e1))
+        K = int(gmm.K)
+        lgb = npts * 408 / (lms / 1e3) / 1e9
+        logpdf = {'kernel': 'k_gmm_logpdf', 'points_per_s': npts * world / (lms / 1e3), 'n_points': npts, 'components': K,
+                  'bound': 'hbm', 'achieved': round(lgb, 1), 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(lgb / peaks['hbm_gbs'], 4),
+                  'fp64_gflops': round(npts * K * 100 * 3 / (lms / 1e3) / 1e9, 1),
+                  'note': 'algorithmic bytes = 400 B of z read + 8 B written per point; arithmetic: 3 fp64 FLOP per (point, '
+                          'component, dimension), sklearn\'s ordering'}
+        del xp, lp
+    except Exception as exc:                               # a side measurement must never take the line down
+        logpdf = {'error': repr(exc)[:200]}
     return {'metric': 'class_accepted_samples_per_s', 'value': acc / (cms / 1e3), 'unit': 'samples/s', 'n_gpus': world,
             'scaling': 'weak' if world > 1 else None, 'sharding': 'Philox offset = rank * n_draws_per_gpu, no collective on the data path',
             'draws_per_s': tot / (cms / 1e3), 'accept_rate': acc / tot, 'n_draws': tot, 'n_draws_per_gpu': n,
@@ -353,7 +384,7 @@ def run_class(args, st, dev, world, rank, barrier, model):
                          'n_unique': pipe_unique, 'device_only_accepted_decoded_per_s': pipe_acc / (pipe_dev_ms / 1e3),
                          'api': 'mogQ.rejection_sample_decode(n, model, dataset): flags -> compaction -> re-generation -> beam decode '
                                 '-> dedup -> H/uH/charge on the device, unique accepted peptides to a host table'},
-            'beam_decode_seq_per_s': 8192 * world / (bms / 1e3)}
+            'beam_decode_seq_per_s': 8192 * world / (bms / 1e3), 'beam_roofline': beam_roof, 'logpdf': logpdf}
 
 
 def run_ours(args):

@@ -26,6 +26,10 @@
 #ifndef CPG_EMU
 #include "tc_gru.cuh"
 
+#ifndef CPG_PF_DIST
+#define CPG_PF_DIST 2               // steps between the L2 prefetch of a step's stash and its use
+#endif
+
 namespace cpg {
 int check_launch(const char* where);
 
@@ -282,7 +286,7 @@ k_gru_bwd_fused(FArgs a) {
             __syncwarp();
             // next-but-one step's gate planes (and the h / dh_out rows that go with them) towards L2
             if (!(a.dbg & 32)) {
-                const int sp = L - 1 - i - 2;
+                const int sp = L - 1 - i - CPG_PF_DIST;
                 if (sp >= 0) {
                     const float* gates_g = dir ? a.gates[1] : a.gates[0];
                     // stash tiles of 32 rows: [tile][step][4 planes][32][HP] -> one contiguous 4*32*HP*4-byte block per (tile, step)
@@ -290,6 +294,19 @@ k_gru_bwd_fused(FArgs a) {
                         const int r0t = row0 + t * 32;
                         if (r0t < ((B + 31) & ~31))
                             bulk_prefetch_l2(gates_g + gate_stash_offset<HP>(r0t, sp, L), 4 * 32 * HP * 4);
+                    }
+                    // encoder: the h_prev rows of that step (one 320-byte piece per batch row, written ~0.4 ms earlier: long
+                    // out of L2) by plain per-line prefetches -- as bulk prefetches (one TMA request per row) they cost the
+                    // MMA warp 0.7 us per step (measured: +17 us per iteration)
+                    if (!C::DEC && sp > 0 && !(a.dbg & 64)) {
+                        const char* hs_b = reinterpret_cast<const char*>(dir ? a.hs[1] : a.hs[0]);
+                        for (int idx = lane; idx < NB * 3; idx += 32) {
+                            const int row = row0 + idx / 3;
+                            if (row < B) {
+                                const size_t off = (((size_t)row * L + sp - 1) * HP * 4 & ~(size_t)127) + (size_t)(idx % 3) * 128;
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(hs_b + off));
+                            }
+                        }
                     }
                 }
             }
