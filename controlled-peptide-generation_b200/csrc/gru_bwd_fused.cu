@@ -151,6 +151,42 @@ k_gru_bwd_fused(FArgs a) {
     const int row0 = blockIdx.x * NB;
     const int B = a.B, L = a.L;
 
+    // A step's stash towards L2 (whole warp): the gate planes as one bulk prefetch per 32-row tile; the h_prev (decoder:
+    // and dh_out) rows, one HP-float piece per batch row, by plain per-line prefetches (the encoder's were written
+    // ~0.4 ms earlier: long out of L2) -- as bulk prefetches (one TMA request per row) they cost the MMA warp 0.7 us
+    // per step (measured: +17 us per iteration).
+    auto prefetch_step = [&](int sp) {
+        if (sp < 0) return;
+        const float* gates_g = dir ? a.gates[1] : a.gates[0];
+        // stash tiles of 32 rows: [tile][step][4 planes][32][HP] -> one contiguous 4*32*HP*4-byte block per (tile, step)
+        for (int t = lane; t < NB / 32; t += 32) {
+            const int r0t = row0 + t * 32;
+            if (r0t < ((B + 31) & ~31))
+                bulk_prefetch_l2(gates_g + gate_stash_offset<HP>(r0t, sp, L), 4 * 32 * HP * 4);
+        }
+        if (a.dbg & 64) return;
+        const char* hs_b = reinterpret_cast<const char*>(dir ? a.hs[1] : a.hs[0]);
+        const char* do_b = reinterpret_cast<const char*>(a.dh_out);
+        for (int idx = lane; idx < NB * 4; idx += 32) {
+            const int row = row0 + (idx >> 2), k = idx & 3;
+            if (row >= B) continue;
+            if (sp > 0) {
+                const size_t off = ((size_t)row * L + sp - 1) * HP * 4;
+                if ((off >> 7) + k <= ((off + HP * 4 - 1) >> 7))
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(hs_b + ((off >> 7) + k) * 128));
+            }
+            if (C::DEC) {
+                const size_t off = ((size_t)row * L + sp) * HP * 4;
+                if ((off >> 7) + k <= ((off + HP * 4 - 1) >> 7))
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(do_b + ((off >> 7) + k) * 128));
+            }
+        }
+    };
+    // the first steps' stash: on its way while the weights are staged
+    if (warp == C::NWE && !(a.dbg & 32)) {
+        for (int d = 0; d < CPG_PF_DIST; ++d) prefetch_step(L - 1 - d);
+    }
+
     // ---- one-time setup
     // operand tiles zeroed: K padding of X, the unused one-hot / padding columns of Hx
     for (int i = tid; i < (C::OFF_P - C::OFF_X) / 16; i += C::NTHREADS) reinterpret_cast<uint4*>(Xb)[i] = make_uint4(0, 0, 0, 0);
@@ -285,31 +321,7 @@ k_gru_bwd_fused(FArgs a) {
             }
             __syncwarp();
             // next-but-one step's gate planes (and the h / dh_out rows that go with them) towards L2
-            if (!(a.dbg & 32)) {
-                const int sp = L - 1 - i - CPG_PF_DIST;
-                if (sp >= 0) {
-                    const float* gates_g = dir ? a.gates[1] : a.gates[0];
-                    // stash tiles of 32 rows: [tile][step][4 planes][32][HP] -> one contiguous 4*32*HP*4-byte block per (tile, step)
-                    for (int t = lane; t < NB / 32; t += 32) {
-                        const int r0t = row0 + t * 32;
-                        if (r0t < ((B + 31) & ~31))
-                            bulk_prefetch_l2(gates_g + gate_stash_offset<HP>(r0t, sp, L), 4 * 32 * HP * 4);
-                    }
-                    // encoder: the h_prev rows of that step (one 320-byte piece per batch row, written ~0.4 ms earlier: long
-                    // out of L2) by plain per-line prefetches -- as bulk prefetches (one TMA request per row) they cost the
-                    // MMA warp 0.7 us per step (measured: +17 us per iteration)
-                    if (!C::DEC && sp > 0 && !(a.dbg & 64)) {
-                        const char* hs_b = reinterpret_cast<const char*>(dir ? a.hs[1] : a.hs[0]);
-                        for (int idx = lane; idx < NB * 3; idx += 32) {
-                            const int row = row0 + idx / 3;
-                            if (row < B) {
-                                const size_t off = (((size_t)row * L + sp - 1) * HP * 4 & ~(size_t)127) + (size_t)(idx % 3) * 128;
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(hs_b + off));
-                            }
-                        }
-                    }
-                }
-            }
+            if (!(a.dbg & 32)) prefetch_step(L - 1 - i - CPG_PF_DIST);
         }
     } else {
         // ---------------- epilogue
