@@ -154,7 +154,6 @@ int cpg_set_option(const char* name, int value) {
     if (strcmp(name, "dec_out_tensor_core") == 0) { g_opt_dec_out_tc = value; return CPG_OK; }
     if (strcmp(name, "side_stream") == 0) { g_opt_side_stream = value; return CPG_OK; }
     if (strcmp(name, "bptt_fused") == 0) { g_opt_bptt_fused = value; return CPG_OK; }
-    if (strcmp(name, "tail_order") == 0) { g_opt_tail_order = value; return CPG_OK; }
     if (strcmp(name, "cuda_graph") == 0) { g_opt_graph = value; return CPG_OK; }
     if (strcmp(name, "latent_tensor_core") == 0) { g_opt_latent_tc = value; return CPG_OK; }
     if (strcmp(name, "rf_tensor_core") == 0) { g_opt_rf_tc = value; return CPG_OK; }

@@ -287,7 +287,6 @@ static bool use_gru_tc(int) { return false; }
 // g_opt_bptt_fused: 1 (default) = on the tcgen05 path the BPTT kernels also contract dW_hh / the token-table
 // gradient (no dg planes in HBM, no separate weight-gradient kernel); 0 = k_gru_bwd_tc + k_wgrad_tc
 int g_opt_bptt_fused = 1;
-int g_opt_tail_order = 0;             // developer: 1 = the decoder's partial sums ahead of the dense weight gradients on lane t
 // Returns the mark "mu, logvar, z are final" (made on the caller's lane right after the latent layers) for the loss
 // statistics of the training step; null when the lanes are off.
 static Mark forward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, const ParamLayout& lay, int V, int B, int L,
@@ -442,11 +441,6 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
     // encoder BPTT of the caller's lane (joined before the input-side gradients)
     {
         order(ctx, ln, s, ln.t);
-        // the ordered sum of the decoder BPTT's per-CTA partials first: a streaming kernel that takes ~10 us while the latent
-        // backward leaves 84 SMs free, and 40 us once the encoder BPTT holds 128 of them
-        if (fused && g_opt_tail_order == 1)
-            launch_wgrad_partial_reduce(ln.t, DEC_HP, DEC_H, V, w.wg_part_dec, w.dt_part_dec, bptt_fused_ctas_dec(B),
-                                        grads + lay.off[P_DEC_WHH], w.dT_dec);
         // dW_ih[:,150:] = drow^T @ [z;c]  (a weight gradient: nothing on the BPTT chain waits for it)
         const bool wd_tc = latent_uses_tc(B) && g_opt_wgrad_dense_tc != 0;
         if (wd_tc) launch_wgrad_zc_tc(ln.t, w.drow, w.zc, B, w.wd_part, w.dwizc);
@@ -488,12 +482,12 @@ static void backward_impl(cpg_ctx* ctx, const Lanes& ln, const float* params, co
         launch_colsum(ln.t, w.dlv, B, ZD, ZD, grads + lay.off[P_QLV_B], w.colsum_ws, 64);
     }
     // decoder W_hh / token-table sums and the decoder's input-side gradients: lane t, behind the head gradients (nothing waits
-    // for them before the end of the step, while the head gradients' operands are only complete now)
+    // for them before the end of the step, while the head gradients' operands are only complete now; the sums ahead of the
+    // dense weight gradients, under the latent backward, measured no different in the captured graph)
     {
         if (fused) {
-            if (g_opt_tail_order != 1)
-                launch_wgrad_partial_reduce(ln.t, DEC_HP, DEC_H, V, w.wg_part_dec, w.dt_part_dec, bptt_fused_ctas_dec(B),
-                                            grads + lay.off[P_DEC_WHH], w.dT_dec);
+            launch_wgrad_partial_reduce(ln.t, DEC_HP, DEC_H, V, w.wg_part_dec, w.dt_part_dec, bptt_fused_ctas_dec(B),
+                                        grads + lay.off[P_DEC_WHH], w.dT_dec);
         } else {
             const bool t2 = launch_wgrad_hh(ln.t, DEC_HP, DEC_H, w.dec_dg, w.dec_hs, w.zc, w.tokd, 0, V, B, L, sm, w.wg_part_dec,
                                             w.dt_part_dec, grads + lay.off[P_DEC_WHH], w.dT_dec, nullptr, nullptr, dg_rounded);
@@ -1060,7 +1054,7 @@ int cpg_wae_train_step_philox(cpg_ctx* ctx, cpg_stream stream, float* params, fl
              (void*)nb->word_drop, (void*)nb->out_keep, (void*)nb->z_prior_full, (void*)nb->z_prior_rf, (void*)nb->rf_w, (void*)nb->rf_b,
              hp->lr, hp->beta1, hp->beta2, hp->adam_eps, hp->clip_norm, hp->lambda_logvar_l1, hp->lambda_logvar_kl, hp->z_regu,
              hp->mmd_sigma, hp->rf_dim, hp->compute_full_mmd, hp->beta != 0.f ? 1 : 0, (unsigned long long)seed, p_word, p_out,
-             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority + 131072 * g_opt_rf_tc + 524288 * g_opt_adam_fused + 1048576 * g_opt_wgrad_dense_tc + 2097152 * (g_opt_mmd_grid & 255) + g_opt_rf_grid * 7 + g_opt_wd_grid * 13 + g_opt_matmul_terms * 101 + g_opt_tail_order * 1009);
+             scalars ? 1 : 0, g_opt_side_stream, g_opt_gru_tc, g_opt_bptt_fused, g_opt_dec_out_tc * 16 + g_opt_wgrad_tc * 4 + g_opt_mmd_tc + 64 * g_opt_latent_tc + 256 * g_opt_latent_rows + 65536 * g_opt_chain_priority + 131072 * g_opt_rf_tc + 524288 * g_opt_adam_fused + 1048576 * g_opt_wgrad_dense_tc + 2097152 * (g_opt_mmd_grid & 255) + g_opt_rf_grid * 7 + g_opt_wd_grid * 13 + g_opt_matmul_terms * 101);
     StepGraph* g = find_graph(kb + std::string(scalars ? std::to_string((uintptr_t)scalars) : ""));
     StepDyn* dyn_dev = reinterpret_cast<StepDyn*>(ctx->ints + 32);
     const StepDyn dv = make_dyn(hp, noise_step);

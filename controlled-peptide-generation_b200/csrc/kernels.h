@@ -113,7 +113,6 @@ int launch_gru_bwd_dec_fused(cudaStream_t s, const GruSeq& seq, const uint8_t* t
                              float* part_t);
 extern int g_opt_gru_tc;
 extern int g_opt_bptt_fused;
-extern int g_opt_tail_order;
 extern int g_opt_graph;
 extern int g_opt_side_stream;
 
