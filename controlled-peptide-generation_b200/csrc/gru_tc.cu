@@ -40,6 +40,9 @@
 #ifndef CPG_ENC_FWD_NWG
 #define CPG_ENC_FWD_NWG 10
 #endif
+#ifndef CPG_FWD_STREAM_STORES
+#define CPG_FWD_STREAM_STORES 2      // stash stores with the evict-first policy: 1 = the encoder's, 2 = and the decoder's gate planes (TMA)
+#endif
 #ifndef CPG_ENC_BWD_NWG
 #define CPG_ENC_BWD_NWG 10
 #endif
@@ -224,8 +227,12 @@ k_gru_fwd_tc(FwdArgs a) {
             if (!C::STAGE_G || gates_dst == nullptr || row0 + ch * NB >= B) return;   // no stash wanted / chain entirely past the batch
 #pragma unroll
             for (int pl = 0; pl < 4; ++pl)
-                bulk_store(gates_dst + gate_stash_offset<HP>(row0 + ch * NB, s_done, L) + (size_t)pl * 32 * HP,
-                           Gch + pl * NB * HP, C::G_PLANE);
+                if (CPG_FWD_STREAM_STORES > 1)
+                    bulk_store_stream(gates_dst + gate_stash_offset<HP>(row0 + ch * NB, s_done, L) + (size_t)pl * 32 * HP,
+                                      Gch + pl * NB * HP, C::G_PLANE);
+                else
+                    bulk_store(gates_dst + gate_stash_offset<HP>(row0 + ch * NB, s_done, L) + (size_t)pl * 32 * HP,
+                               Gch + pl * NB * HP, C::G_PLANE);
             bulk_commit();
         };
         for (int s = 0; s < L; ++s) {
@@ -380,13 +387,24 @@ k_gru_fwd_tc(FwdArgs a) {
                 }
                 if (row < B) {
                     const size_t bs = (size_t)row * L + s;
-                    if (hs_g != nullptr) st4(hs_g + bs * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
+                    if (hs_g != nullptr) {
+                        // the encoder's h stash is read again by its BPTT only (~0.4 ms later); the decoder's feeds the output layer next
+                        if (CPG_FWD_STREAM_STORES && !C::DEC) st_stream4(hs_g + bs * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
+                        else st4(hs_g + bs * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
+                    }
                     if (!C::STAGE_G && gates_g != nullptr) {
                         float* g = gates_g + gate_stash_offset<HP>(row, s, L) + j0;
-                        st4(g, make_float4(rr[0], rr[1], rr[2], rr[3]));
-                        st4(g + 32 * HP, make_float4(zz[0], zz[1], zz[2], zz[3]));
-                        st4(g + 2 * 32 * HP, make_float4(nn[0], nn[1], nn[2], nn[3]));
-                        st4(g + 3 * 32 * HP, make_float4(hh[0], hh[1], hh[2], hh[3]));
+                        if (CPG_FWD_STREAM_STORES) {
+                            st_stream4(g, make_float4(rr[0], rr[1], rr[2], rr[3]));
+                            st_stream4(g + 32 * HP, make_float4(zz[0], zz[1], zz[2], zz[3]));
+                            st_stream4(g + 2 * 32 * HP, make_float4(nn[0], nn[1], nn[2], nn[3]));
+                            st_stream4(g + 3 * 32 * HP, make_float4(hh[0], hh[1], hh[2], hh[3]));
+                        } else {
+                            st4(g, make_float4(rr[0], rr[1], rr[2], rr[3]));
+                            st4(g + 32 * HP, make_float4(zz[0], zz[1], zz[2], zz[3]));
+                            st4(g + 2 * 32 * HP, make_float4(nn[0], nn[1], nn[2], nn[3]));
+                            st4(g + 3 * 32 * HP, make_float4(hh[0], hh[1], hh[2], hh[3]));
+                        }
                     }
                     if (!C::DEC && s == L - 1)
                         st4(a.hfin + (size_t)row * (2 * HP) + dir * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));

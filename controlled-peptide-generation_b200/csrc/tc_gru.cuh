@@ -120,6 +120,12 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
     return v;
 }
 
+// streaming 16-byte store (evict-first): activation-stash data that is read again only much later -- written with the
+// default policy it sits dirty in L2 and its write-back taxes the kernels that follow
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // (operand-tile term, weight term) of the three accumulated products
 __device__ constexpr int XS[3] = {0, 0, 1};
 __device__ constexpr int WS[3] = {0, 1, 0};
@@ -134,6 +140,13 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(gdst), "r"(tc::smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+// the same with the evict-first L2 policy (stash data that is read again only after much other traffic)
+__device__ __forceinline__ void bulk_store_stream(void* gdst, const void* smem_src, uint32_t bytes) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(gdst), "r"(tc::smem_u32(smem_src)), "r"(bytes), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
