@@ -90,6 +90,11 @@ __device__ __forceinline__ float4 ld_once4(const float* p) {
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+__device__ __forceinline__ unsigned short ld_once_u16(const unsigned short* p) {
+    unsigned short v;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
@@ -277,8 +282,8 @@ k_dec_out_tc(DecOutArgs a) {
             if (has_mask) {
                 // row * 102 + 4 f is even: two aligned 2-byte loads (the last quad's second pair is clamped, masked below)
                 const unsigned short* kp = reinterpret_cast<const unsigned short*>(a.out_keep + (size_t)row * DEC_H + f * 4);
-                k0[it] = kp[0];
-                k1[it] = kp[f * 4 + 2 < DEC_H ? 1 : 0];
+                k0[it] = ld_once_u16(kp);
+                k1[it] = ld_once_u16(kp + (f * 4 + 2 < DEC_H ? 1 : 0));
             }
         }
     };
