@@ -90,6 +90,10 @@ __device__ __forceinline__ float4 ld_once4(const float* p) {
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
+// 16-byte store that leaves no line in L1 (the next reader is another kernel, through L2)
+__device__ __forceinline__ void st_once4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ unsigned short ld_once_u16(const unsigned short* p) {
     unsigned short v;
     asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
@@ -456,7 +460,7 @@ k_dec_out_tc(DecOutArgs a) {
                 if (row < nrows) {
                     const float4 d = ld4(stage + r * SST + f * 4);
                     const unsigned k = keep_s[r * NF4 + f];
-                    st4(a.dh_out + (size_t)row * DEC_HP + f * 4,
+                    st_once4(a.dh_out + (size_t)row * DEC_HP + f * 4,
                         make_float4((k & 1) ? d.x * sc : 0.f, (k & 2) ? d.y * sc : 0.f, (k & 4) ? d.z * sc : 0.f, (k & 8) ? d.w * sc : 0.f));
                 }
             }

@@ -390,7 +390,7 @@ k_gru_fwd_tc(FwdArgs a) {
                     if (hs_g != nullptr) {
                         // the encoder's h stash is read again by its BPTT only (~0.4 ms later); the decoder's feeds the output layer next
                         if (CPG_FWD_STREAM_STORES && !C::DEC) st_stream4(hs_g + bs * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
-                        else st4(hs_g + bs * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
+                        else st_once4(hs_g + bs * HP + j0, make_float4(hn[0], hn[1], hn[2], hn[3]));
                     }
                     if (!C::STAGE_G && gates_g != nullptr) {
                         float* g = gates_g + gate_stash_offset<HP>(row, s, L) + j0;

@@ -126,6 +126,11 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// 16-byte store that leaves no line in L1 (the next reader is another kernel, through L2)
+__device__ __forceinline__ void st_once4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // (operand-tile term, weight term) of the three accumulated products
 __device__ constexpr int XS[3] = {0, 0, 1};
 __device__ constexpr int WS[3] = {0, 1, 0};
